@@ -1,0 +1,137 @@
+"""Restatement of snap/models/bev_mapper.py (VerticalPooling, BEVMapper forward). Test infrastructure."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import geometry, grids, image_encoder, layers
+from . import streetview_encoder as sv
+
+F = np.float32
+_id = lambda a: a
+
+
+def vertical_pooling_max(features: np.ndarray, valid: np.ndarray):
+    """bev_mapper.py:56-88 with pooling='max': max over axis -2 where valid (double-where), zero if none."""
+    valid_any = valid.any(-1)
+    vaa = np.where(valid_any[..., None], valid, True)
+    pooled = np.where(vaa[..., None], features, -np.inf).max(-2)
+    pooled = np.where(valid_any[..., None], pooled, F(0)).astype(features.dtype)
+    return pooled, valid_any
+
+
+def build_xyz_query(grid: grids.Grid2D, t_view2scene_t: np.ndarray, scene_z_offset: float = 4.0,
+                    scene_z_height: float = 12.0, z_offset: Optional[float] = None):
+    """bev_mapper.py:159-196 for one scene (train=False): xyz [X,Y,Z,3] fp32."""
+    xy = grid.index_to_xyz(grid.grid_index())  # [X,Y,2]
+    if z_offset is None:
+        cam_h = np.median(t_view2scene_t[..., -1].astype(F), axis=-1).astype(F)  # :171
+        z_offset = F(cam_h - F(scene_z_offset))
+    z = (np.arange(0, scene_z_height, grid.cell_size).astype(F) + F(z_offset)).astype(F)
+    z = (z + F(grid.cell_size / 2)).astype(F)  # :189-193 (left-to-right adds)
+    X, Y = grid.extent
+    xyz = np.empty((X, Y, len(z), 3), dtype=F)
+    xyz[..., :2] = xy[:, :, None, :]
+    xyz[..., 2] = z[None, None, :]
+    return xyz, F(z_offset)
+
+
+def np_rd(rd_t: Callable) -> Callable:
+    """Lift a torch rounding hook to numpy arrays."""
+    if rd_t is _id:
+        return _id
+    return lambda a: rd_t(torch.from_numpy(np.ascontiguousarray(a, dtype=F))).numpy()
+
+
+def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene: geometry.Transform3D,
+               xyz: np.ndarray, fusion_params: Dict, feature_dim: int = 128, top_k: int = 4,
+               depth_min_max=(1.0, 32.0), rd: Callable = _id, chunk: int = 1 << 16):
+    """streetview_encoder.py:232-286 for one scene, chunked over voxels.
+
+    f_proj_images [V,Hf,Wf,feature_dim+S] = proj_mlp output; camera ALREADY scaled by 1/stride (:224).
+    Returns f_grid [X,Y,Z,D], valid [X,Y,Z], and per-voxel debug (vis [N,V], p2d [N,V,2]).
+    """
+    rdn = np_rd(rd)
+    grid_shape = xyz.shape[:-1]
+    pts_all = xyz.reshape(-1, 3)
+    V = f_proj_images.shape[0]
+    outs, valids, vis_all, p2d_all = [], [], [], []
+    for s in range(0, len(pts_all), chunk):
+        pts = pts_all[s:s + chunk]
+        p2d, vis, depth, _ = sv.project_points_to_views(t_view2scene, camera, pts)
+        if top_k and V > top_k:  # :241-249
+            idx, _ = sv.view_selection(pts, t_view2scene, vis, top_k)
+            p2d, vis, depth = (np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
+                               for a in (p2d, vis, depth))
+            f_proj = sv.interpolate_views_selective(f_proj_images, p2d, idx, cast=rdn)
+        else:
+            f_proj = sv.interpolate_views_all(f_proj_images, p2d)
+        f_proj = rdn(f_proj)
+        feats, scales = f_proj[..., :feature_dim], f_proj[..., feature_dim:]
+        scores = rdn(sv.interpolate_depth_score(scales, depth, depth_min_max))
+        stats, valid = sv.pool_multiview_features(feats, vis, scores, False, True, rd=rdn)
+        f = layers.mlp(rdn(stats), fusion_params, rd=rdn)  # :281
+        f = np.where(valid[..., None], f, F(0))  # :282
+        outs.append(f.astype(F)); valids.append(valid); vis_all.append(vis); p2d_all.append(p2d)
+    f_grid = np.concatenate(outs).reshape(*grid_shape, -1)
+    valid = np.concatenate(valids).reshape(grid_shape)
+    return f_grid, valid, np.concatenate(vis_all), np.concatenate(p2d_all)
+
+
+def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = _id):
+    """bev_mapper.py:284-291: Dense 128->32, L2-normalise, mask."""
+    rdn = np_rd(rd)
+    f = rdn(layers.dense(plane, p["kernel"], p["bias"]))
+    f = rdn(layers.normalize(f))
+    return np.where(valid[..., None], f, F(0)).astype(F)
+
+
+def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callable = _id,
+                       scene_z_offset: float = 4.0, scene_z_height: float = 12.0, top_k: int = 4,
+                       return_volume: bool = False) -> Dict:
+    """bev_mapper.py:254-296 for a batch (inference, train=False).
+
+    data: 'images' f32 [B,V,H,W,3]; 'camera' geometry.Camera with fields [B,V,2];
+          'T_view2scene' Transform3D R [B,V,3,3], t [B,V,3]; optional 'rasters' {'rgb' [B,G,G,3]}.
+    params: Flax tree under 'bev_mapper'  with numpy leaves.
+    """
+    rdn = np_rd(rd)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F))
+    tt = lambda tree: {k: (tt(v) if isinstance(v, dict) else t(v)) for k, v in tree.items()}
+    B, V = data["images"].shape[:2]
+    svp = params["streetview_encoder"]
+    planes, valids, pred = [], [], {"streetview": []}
+    for b in range(B):
+        feats, strides = image_encoder.image_encoder(t(data["images"][b]), tt(svp["image_encoder"]), False, rd)
+        f_img = feats[-1].numpy()
+        stride = strides[-1]
+        cam = geometry.Camera(wh=data["camera"].wh[b], f=data["camera"].f[b], c=data["camera"].c[b])
+        cam = cam.scale(np.asarray([1 / stride[1], 1 / stride[0]], dtype=F))  # :224 (i,j) -> (x,y)
+        f_proj = layers.mlp(f_img, svp["proj_mlp"], apply_input_activation=True, rd=rdn)  # :229
+        T = geometry.Transform3D(R=data["T_view2scene"].R[b], t=data["T_view2scene"].t[b])
+        xyz, z_off = build_xyz_query(grid, T.t, scene_z_offset, scene_z_height)
+        f_grid, valid, vis, p2d = lift_scene(f_proj, cam, T, xyz, svp["fusion_mlp"], top_k=top_k, rd=rd)
+        plane, pvalid = vertical_pooling_max(f_grid, valid)
+        item = {"f_proj_images": f_proj, "feature_plane": plane, "valid": pvalid, "vis": vis, "p2d": p2d,
+                "z_offset": z_off, "pyramid": [f.numpy() for f in feats]}
+        if return_volume:
+            item["feature_volume"], item["volume_valid"] = f_grid, valid
+        pred["streetview"].append(item)
+        planes_b, valids_b = [plane], [pvalid]
+        if "rasters" in data and "aerial_encoder" in params:
+            afeats, _ = image_encoder.image_encoder(t(data["rasters"]["rgb"][b:b + 1]), tt(params["aerial_encoder"]), True, rd)
+            aplane = afeats[-1].numpy()[0]
+            pred.setdefault("aerial", []).append(aplane)
+            planes_b.append(aplane); valids_b.append(np.ones(aplane.shape[:-1], bool))
+        if len(planes_b) > 1:  # fuse_neural_maps :225-252 == VerticalPooling('max') over the modality axis
+            fused, fvalid = vertical_pooling_max(np.stack(planes_b, -2), np.stack(valids_b, -1))
+        else:
+            fused, fvalid = planes_b[0], valids_b[0]
+        planes.append(fused); valids.append(fvalid)
+    feats_bev = np.stack(planes); valid_bev = np.stack(valids)
+    pred["bev_features"] = {"features": feats_bev, "valid": valid_bev}
+    pred["bev_matching"] = {"features": matching_head(feats_bev, valid_bev, params["matching_proj"], rd),
+                            "valid": valid_bev}
+    return pred

@@ -1,0 +1,66 @@
+"""ctypes binding of libsnapb200.so (the C ABI declared in include/snapb200.h).
+
+There is deliberately no fallback: if the shared library is missing, or a compute entry point is
+called without a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+_LIB_PATH = pathlib.Path(__file__).resolve().parent / "libsnapb200.so"
+_lib = None
+
+
+class SnapB200Error(RuntimeError):
+    pass
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_rows", C.c_longlong), ("a_cols", C.c_int), ("a_ld", C.c_longlong),
+        ("b", C.c_void_p), ("b_rows", C.c_longlong), ("b_cols", C.c_int), ("b_ld", C.c_longlong),
+        ("m_rows", C.c_longlong), ("n", C.c_int), ("num_seg", C.c_int), ("seg_k", C.c_int),
+        ("a_col0", C.c_int), ("seg_off", C.c_int * 9),
+        ("out", C.c_void_p), ("ldo", C.c_longlong), ("out_f32", C.c_int),
+        ("residual", C.c_void_p), ("ldr", C.c_longlong),
+        ("bias", C.c_void_p), ("row_mask", C.c_void_p), ("relu", C.c_int),
+        ("remap", C.c_int), ("rm_R", C.c_int), ("rm_C", C.c_int), ("rm_r0", C.c_int),
+        ("rm_c0", C.c_int), ("rm_Ho", C.c_int), ("rm_Wo", C.c_int),
+        ("bn", C.c_int),
+    ]
+
+
+def lib() -> C.CDLL:
+    """Load the library once. Raises if it has not been built (`python -m snap_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise SnapB200Error(
+                f"{_LIB_PATH} is missing: build it with `python -m snap_b200.build` "
+                "(there is no CPU/PyTorch fallback for the hot path)")
+        l = C.CDLL(str(_LIB_PATH))
+        l.snapb200_last_error.restype = C.c_char_p
+        l.snapb200_launch_count.restype = C.c_longlong
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SnapB200Error(f"libsnapb200 error {rc}: {lib().snapb200_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().snapb200_launch_count())
+
+
+def launch_count_reset() -> None:
+    lib().snapb200_launch_count_reset()
+
+
+# Every symbol include/snapb200.h declares; tests/test_abi.py checks the .so exports each of them.
+EXPORTED_SYMBOLS = [
+    "snapb200_last_error", "snapb200_version", "snapb200_launch_count",
+    "snapb200_launch_count_reset", "snapb200_gemm_bf16",
+]

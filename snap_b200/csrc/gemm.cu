@@ -1,0 +1,105 @@
+// Host launcher + C ABI for the tcgen05 GEMM engine (gemm_tc.cuh).
+#include "gemm_launch.h"
+#include "gemm_tc.cuh"
+
+namespace snapb200 {
+
+template <int BN, int BK>
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       cudaStream_t s) {
+  using Cfg = GemmCfg<BN, BK>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES),
+                        "cudaFuncSetAttribute(gemm_tc)");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<BN, BK><<<grid, 192, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+int launch_gemm(const void* A, long long a_rows, int a_cols, long long a_ld, const void* B,
+                long long b_rows, int b_cols, long long b_ld, int bn, int bk, const GemmParams& p,
+                cudaStream_t s) {
+  SNAP_REQUIRE(p.m_tiles > 0 && p.n_tiles > 0 && p.nkb > 0, "empty GEMM");
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, A, a_rows, a_cols, a_ld, 128, bk);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, B, b_rows, b_cols, b_ld, bn, bk);
+  if (rc) return rc;
+#define SNAP_GEMM_CASE(BN_, BK_) \
+  if (bn == BN_ && bk == BK_) return launch_inst<BN_, BK_>(tmA, tmB, p, s);
+  SNAP_GEMM_CASE(16, 64)
+  SNAP_GEMM_CASE(64, 64)
+  SNAP_GEMM_CASE(128, 64)
+  SNAP_GEMM_CASE(160, 64)
+  SNAP_GEMM_CASE(256, 64)
+  SNAP_GEMM_CASE(48, 32)
+  SNAP_GEMM_CASE(64, 32)
+  SNAP_GEMM_CASE(128, 32)
+  SNAP_GEMM_CASE(256, 32)
+#undef SNAP_GEMM_CASE
+  return set_error(SNAPB200_ERR_INVALID, "no GEMM instance for bn=%d bk=%d", bn, bk);
+}
+
+int pick_bn(int n, int bk) {
+  if (n <= 16 && bk == 64) return 16;
+  if (n == 160 && bk == 64) return 160;
+  if (n <= 64) return 64;
+  if (n <= 128) return 128;
+  return 256;
+}
+
+}  // namespace snapb200
+
+using namespace snapb200;
+
+extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
+  SNAP_REQUIRE(q != nullptr, "null params");
+  SNAP_REQUIRE(q->a && q->b && q->out, "null operand");
+  SNAP_REQUIRE(q->num_seg >= 1 && q->num_seg <= 9, "num_seg must be in 1..9 (got %d)", q->num_seg);
+  SNAP_REQUIRE(q->seg_k >= 32 && q->seg_k % 32 == 0, "seg_k must be a multiple of 32 (got %d)",
+               q->seg_k);
+  SNAP_REQUIRE(q->n >= 16 && q->n % 16 == 0, "n must be a multiple of 16 (got %d)", q->n);
+  SNAP_REQUIRE(q->m_rows > 0, "m_rows must be positive");
+  SNAP_REQUIRE(q->ldo % 8 == 0, "ldo must be a multiple of 8");
+  SNAP_REQUIRE(q->residual == nullptr || q->ldr % 8 == 0, "ldr must be a multiple of 8");
+  const int bk = (q->seg_k % 64 == 0) ? 64 : 32;
+  const int bn = q->bn > 0 ? q->bn : pick_bn(q->n, bk);
+  GemmParams p = {};
+  p.m_tiles = (int)((q->m_rows + 127) / 128);
+  p.n_tiles = (q->n + bn - 1) / bn;
+  p.kps = q->seg_k / bk;
+  p.nkb = q->num_seg * p.kps;
+  p.seg_kstride = q->seg_k;
+  p.a_col0 = q->a_col0;
+  p.seg_mode = SEG_TABLE;
+  for (int i = 0; i < 9; ++i) p.seg_off[i] = i < q->num_seg ? q->seg_off[i] : 0;
+  p.tile_mode = TILE_LINEAR;
+  p.epi = EPI_STORE;
+  p.M_valid = q->m_rows;
+  p.N = q->n;
+  p.out = q->out;
+  p.ldo = q->ldo;
+  p.out_f32 = q->out_f32;
+  p.residual = static_cast<const __nv_bfloat16*>(q->residual);
+  p.ldr = q->ldr;
+  p.bias = q->bias;
+  p.row_mask = q->row_mask;
+  p.relu = q->relu;
+  p.remap = q->remap;
+  p.rm_R = q->rm_R;
+  p.rm_C = q->rm_C;
+  p.rm_r0 = q->rm_r0;
+  p.rm_c0 = q->rm_c0;
+  p.rm_Ho = q->rm_Ho;
+  p.rm_Wo = q->rm_Wo;
+  if (q->remap) SNAP_REQUIRE(q->rm_R > 0 && q->rm_C > 0 && q->rm_Ho > 0 && q->rm_Wo > 0, "bad remap");
+  return launch_gemm(q->a, q->a_rows, q->a_cols, q->a_ld, q->b, q->b_rows, q->b_cols, q->b_ld, bn,
+                     bk, p, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,94 @@
+#include "host_common.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace snapb200 {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return SNAPB200_OK;
+  return set_error(SNAPB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+void count_launch() { ++g_launches; }
+
+int check_launch(const char* what) {
+  ++g_launches;
+  return check_cuda(cudaPeekAtLastError(), what);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, long long rows, long long cols,
+                      long long ld, int box_rows, int box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  SNAP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SNAP_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", ld);
+  SNAP_REQUIRE(box_cols == 64 || box_cols == 32, "box_cols must be 32 or 64");
+  SNAP_REQUIRE(box_rows >= 1 && box_rows <= 256, "box_rows out of range");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SNAPB200_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d",
+                     (int)r, rows, cols, ld, box_rows, box_cols);
+  return SNAPB200_OK;
+}
+
+}  // namespace snapb200
+
+extern "C" {
+const char* snapb200_last_error(void) { return snapb200::g_err; }
+int snapb200_version(void) { return 100; }
+long long snapb200_launch_count(void) { return snapb200::g_launches; }
+void snapb200_launch_count_reset(void) { snapb200::g_launches = 0; }
+}

@@ -1,0 +1,29 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error string, launch
+// counter, device properties and TMA tensor-map construction (driver entry point resolved at run
+// time so the library does not link against libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/snapb200.h"
+
+namespace snapb200 {
+
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what);  // cudaPeekAtLastError + launch counter
+int num_sms();
+void count_launch();
+
+// 2D bf16 tensor map: dims {cols (inner), rows}, row pitch ld elements, box {box_cols, box_rows},
+// swizzle = box_cols * 2 bytes (64 or 128), zero fill out of bounds.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, long long rows, long long cols,
+                      long long ld, int box_rows, int box_cols);
+
+#define SNAP_REQUIRE(cond, ...)                                        \
+  do {                                                                 \
+    if (!(cond)) return set_error(SNAPB200_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+}  // namespace snapb200

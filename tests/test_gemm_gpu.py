@@ -1,0 +1,94 @@
+"""tcgen05 GEMM engine vs a plain fp32 reference of the same op (bf16 inputs, fp32 accumulate).
+
+Tolerance: outputs are fp32 sums of exactly-representable bf16 products, so only the summation
+order differs: |err| <= 1e-4 * max|ref| (fp32 output) and one bf16 ulp on top for bf16 outputs.
+"""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
+
+
+def _check(out, ref, bf16_out=False):
+    out = out.float().cpu()
+    scale = ref.abs().max().item() + 1e-6
+    tol = 1e-4 * scale + (2.0 ** -8) * ref.abs() * (1.0 if bf16_out else 0.0)
+    bad = (out - ref).abs() > tol + 1e-6
+    assert not bad.any(), f"{int(bad.sum())} mismatches, max err {(out - ref).abs().max().item()} scale {scale}"
+
+
+@pytest.mark.parametrize("M,K,N", [
+    (128, 64, 64), (300, 128, 64), (1000, 256, 128), (777, 512, 256), (4096, 1024, 512),
+    (129, 128, 160), (640, 64, 16), (500, 96, 64), (500, 160, 64), (900, 288, 256), (260, 288, 128),
+    (128 * 320 + 5, 64, 256),
+])
+def test_gemm_plain_f32(M, K, N):
+    from snap_b200 import ops
+    a, b = _rand((M, K), 1), _rand((N, K), 2)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(a.cuda(), b.cuda(), out)
+    torch.cuda.synchronize()
+    _check(out, a.float() @ b.float().T)
+
+
+def test_gemm_epilogue_bias_residual_relu_mask():
+    from snap_b200 import ops
+    M, K, N = 700, 256, 128
+    a, b = _rand((M, K), 3), _rand((N, K), 4)
+    res = _rand((M, N), 5)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(6))
+    mask = (torch.rand(M, generator=torch.Generator().manual_seed(7)) > 0.3).to(torch.uint8)
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a.cuda(), b.cuda(), out, residual=res.cuda(), bias=bias.cuda(), row_mask=mask.cuda(), relu=True)
+    torch.cuda.synchronize()
+    ref = torch.relu(a.float() @ b.float().T + bias + res.float()) * mask[:, None].float()
+    _check(out, ref, bf16_out=True)
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_gemm_conv3x3_segments(stride):
+    """3x3 conv = 9 row-shifted K-segments over a zero-bordered (stride 1) or phase-split (stride 2) buffer."""
+    from snap_b200 import ops
+    n_img, H, W, Cin, Cout = 2, 12, 20, 64, 128
+    x = _rand((n_img, H, W, Cin), 8)
+    w = _rand((3, 3, Cin, Cout), 9, 0.1)  # HWIO
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(3, 2, 0, 1),
+                                     stride=stride, padding=1).permute(0, 2, 3, 1)
+    bmat = w.permute(3, 0, 1, 2).reshape(Cout, 9 * Cin).contiguous()
+    xp = torch.zeros((n_img, H + 2, W + 2, Cin), dtype=torch.bfloat16)
+    xp[:, 1:-1, 1:-1] = x
+    if stride == 1:
+        Hp, Wp = H + 2, W + 2
+        a = xp.reshape(-1, Cin)
+        seg_off = [(kh - 1) * Wp + (kw - 1) for kh in range(3) for kw in range(3)]
+        remap = (Hp, Wp, 1, 1, H, W)
+        m_rows = n_img * Hp * Wp
+        Ho, Wo = H, W
+    else:
+        Ho, Wo = H // 2, W // 2
+        Hq, Wq = Ho + 1, Wo + 1
+        planes = torch.stack([xp[:, a_::2, b_::2] for a_ in range(2) for b_ in range(2)])  # [4,n,Hq,Wq,C]
+        assert planes.shape[2:4] == (Hq, Wq)
+        a = planes.reshape(-1, Cin)
+        plane_rows = n_img * Hq * Wq
+        seg_off = [((kh % 2) * 2 + (kw % 2)) * plane_rows + (kh // 2) * Wq + (kw // 2)
+                   for kh in range(3) for kw in range(3)]
+        remap = (Hq, Wq, 0, 0, Ho, Wo)
+        m_rows = plane_rows
+    out = torch.full((n_img * Ho * Wo, Cout), float("nan"), device="cuda")
+    ops.gemm(a.contiguous().cuda(), bmat.cuda(), out, m_rows=m_rows, seg_off=seg_off, seg_k=Cin, remap=remap)
+    torch.cuda.synchronize()
+    _check(out, ref.reshape(-1, Cout))
+
+
+def test_gemm_rejects_bad_shapes():
+    from snap_b200 import _lib, ops
+    a, b = _rand((128, 48), 1).cuda(), _rand((64, 48), 2).cuda()
+    out = torch.zeros((128, 64), device="cuda")
+    with pytest.raises(_lib.SnapB200Error):
+        ops.gemm(a, b, out)  # K=48 is not a multiple of 32
