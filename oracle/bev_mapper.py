@@ -83,7 +83,7 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
 def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = _id):
     """bev_mapper.py:284-291: Dense 128->32, L2-normalise, mask."""
     rdn = np_rd(rd)
-    f = rdn(layers.dense(plane, p["kernel"], p["bias"]))
+    f = rdn(rdn(layers.dense(plane, p["kernel"], None)) + p["bias"].astype(F))
     f = rdn(layers.normalize(f))
     return np.where(valid[..., None], f, F(0)).astype(F)
 

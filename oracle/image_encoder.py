@@ -36,13 +36,13 @@ def fpn_decoder(feats: List[torch.Tensor], p: Dict, rd: Callable = _id) -> List[
     return out
 
 
-def image_encoder(image: torch.Tensor, p: Dict, skip_root_block: bool = False, rd: Callable = _id):
+def image_encoder(image: torch.Tensor, p: Dict, skip_root_block: bool = False, rd: Callable = _id, trace=None):
     """image_encoder.py:119-144.  image [B,H,W,3] in [0,1] -> (features coarse->fine (cropped), strides)."""
     h, w = image.shape[1:3]
     num_levels = sum(1 for k in p["encoder"] if k.startswith("block"))
     max_stride = (0 if skip_root_block else 2) + num_levels - 1  # :109-111
     padded = pad_to_multiple(rd(image), 2 ** max_stride)
-    stages = resnet.resnet_v2(padded, p["encoder"], skip_root_block, rd)
+    stages = resnet.resnet_v2(padded, p["encoder"], skip_root_block, rd, trace)
     skips = stages[::-1]  # :114, coarse -> fine
     outs = fpn_decoder(skips, p["decoder"], rd)
     feats, strides = [], []

@@ -32,6 +32,9 @@ def mlp(x: np.ndarray, params: dict, apply_input_activation: bool = False, rd=la
     while f"Dense_{i}" in params:
         if i > 0 or apply_input_activation:
             x = np.maximum(x, 0)
-        x = rd(dense(x, params[f"Dense_{i}"]["kernel"], params[f"Dense_{i}"].get("bias")))
+        # flax.linen.Dense: y = dot_general(x, kernel) [materialised in dtype]; y += bias [again in dtype]
+        x = rd(dense(x, params[f"Dense_{i}"]["kernel"], None))
+        if params[f"Dense_{i}"].get("bias") is not None:
+            x = rd(x + params[f"Dense_{i}"]["bias"].astype(F))
         i += 1
     return x

@@ -67,25 +67,30 @@ def residual_unit(x: Tensor, p: Dict, stride: int, rd: Callable = _id) -> Tensor
     return rd(y + residual)
 
 
-def resnet_stage(x: Tensor, p: Dict, first_stride: int, rd: Callable = _id) -> Tensor:
-    """resnet.py:137-155; returns the last unit's output."""
+def resnet_stage(x: Tensor, p: Dict, first_stride: int, rd: Callable = _id, trace=None) -> Tensor:
+    """resnet.py:137-155; returns the last unit's output.  `trace` (list) records (input, output) per unit."""
     names = sorted(k for k in p if k.startswith("unit"))
     for i, name in enumerate(names):
-        x = residual_unit(x, p[name], first_stride if i == 0 else 1, rd)
+        y = residual_unit(x, p[name], first_stride if i == 0 else 1, rd)
+        if trace is not None:
+            trace.append((x, y))
+        x = y
     return x
 
 
-def resnet_v2(image: Tensor, p: Dict, skip_root_block: bool = False, rd: Callable = _id):
+def resnet_v2(image: Tensor, p: Dict, skip_root_block: bool = False, rd: Callable = _id, trace=None):
     """resnet.py:184-216; returns [stage1, stage2, ...] outputs (last unit of each stage)."""
     x = rd(rd(image) * 2 - 1)  # resnet.py:199
     if skip_root_block:
         x = conv(x, std_kernel(p["conv_root"]["kernel"], rd), stride=1, padding=1, rd=rd)  # :200-208
     else:
         x = root_block(x, p["root_block"], rd)
+    if trace is not None:
+        trace.append((None, x))
     outs = []
     i = 1
     while f"block{i}" in p:
-        x = resnet_stage(x, p[f"block{i}"], 1 if i == 1 else 2, rd)
+        x = resnet_stage(x, p[f"block{i}"], 1 if i == 1 else 2, rd, trace)
         outs.append(x)
         i += 1
     return outs

@@ -64,3 +64,34 @@ EXPORTED_SYMBOLS = [
     "snapb200_last_error", "snapb200_version", "snapb200_launch_count",
     "snapb200_launch_count_reset", "snapb200_gemm_bf16",
 ]
+
+
+class WeightDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("partial", C.c_void_p),
+                ("K", C.c_int), ("Cout", C.c_int), ("ldb", C.c_int), ("standardize", C.c_int),
+                ("ksplit", C.c_int), ("pad_", C.c_int)]
+
+
+MAX_VIEWS = 8
+
+
+class LiftView(C.Structure):
+    _fields_ = [("Rinv", C.c_float * 9), ("tinv", C.c_float * 3), ("f", C.c_float * 2),
+                ("c", C.c_float * 2), ("wh", C.c_float * 2), ("k_radial", C.c_float * 3),
+                ("tan_half_fov", C.c_float), ("fisheye", C.c_int)]
+
+
+class LiftParams(C.Structure):
+    _fields_ = [("V", C.c_int), ("Hf", C.c_int), ("Wf", C.c_int), ("CF", C.c_int), ("D", C.c_int),
+                ("S", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
+                ("depth_min", C.c_float), ("depth_max", C.c_float), ("inv_log_range", C.c_float),
+                ("stats_ld", C.c_int), ("view", LiftView * MAX_VIEWS)]
+
+
+EXPORTED_SYMBOLS += [
+    "snapb200_std_weights_batched", "snapb200_root_im2col", "snapb200_maxpool3x3s2",
+    "snapb200_gn_workspace_bytes", "snapb200_gn_stats", "snapb200_gn_apply", "snapb200_upsample2x",
+    "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_vertical_max", "snapb200_match_head",
+    "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_rot_templates",
+    "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores",
+]

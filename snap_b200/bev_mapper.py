@@ -1,0 +1,139 @@
+"""B200 implementation behind `snap.models.bev_mapper.{VerticalPooling, BEVMapper}`
+(`snap/models/bev_mapper.py:40-296`)."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, configs, image_encoder, ops, streetview_encoder, types
+
+F = np.float32
+
+
+class VerticalPooling:
+    """`bev_mapper.py:40-88`; only the default `pooling='max'` is built (others: SURVEY §8(f).3)."""
+
+    def __init__(self, config=None, dtype=torch.bfloat16):
+        self.config = config if config is not None else configs.vertical_pooling()
+        if self.config.pooling != "max":
+            raise NotImplementedError(self.config.pooling)
+
+    def apply(self, variables, feature_volume: types.FeatureVolume) -> Dict:
+        f, v = feature_volume.features, feature_volume.valid
+        lead, Z, C = f.shape[:-2], f.shape[-2], f.shape[-1]
+        cells = int(np.prod(lead))
+        plane = torch.empty((*lead, C), dtype=torch.bfloat16, device=f.device)
+        pvalid = torch.empty(lead, dtype=torch.uint8, device=f.device)
+        ops.vertical_max(f.contiguous(), v.contiguous(), cells, Z, C, plane, pvalid)
+        return {"plane": types.FeaturePlane(features=plane, valid=pvalid)}
+
+    __call__ = apply
+
+
+class BEVMapper:
+    """Mirror of `snap.models.bev_mapper.BEVMapper(config, grid, semantic_map_classes, dtype)`."""
+
+    default_config = staticmethod(configs.bev_mapper)
+
+    def __init__(self, config=None, grid: types.Grid2D = None, semantic_map_classes=None, dtype=torch.bfloat16):
+        self.config = config if config is not None else configs.bev_mapper()
+        self.grid = grid
+        self.dtype = dtype
+        c = self.config
+        if c.semantic_encoder is not None:
+            raise NotImplementedError("semantic raster modality is out of scope (SURVEY.md §2)")
+        if c.bev_net is not None:
+            raise NotImplementedError("BEV network not yet implemented")  # bev_mapper.py:141-142
+        if c.matching_dim not in (None, 32) or c.add_confidence:
+            raise NotImplementedError("matching_dim must be 32; confidence head not built")
+        self.streetview_encoder = self.aerial_encoder = None
+        if c.streetview_encoder is not None:
+            self.streetview_encoder = streetview_encoder.StreetViewEncoder(c.streetview_encoder, dtype)
+            self.vertical_pooling = VerticalPooling(c.pooling, dtype)
+        if c.aerial_encoder is not None:
+            self.aerial_encoder = image_encoder.ImageEncoder(c.aerial_encoder, dtype)
+        if self.streetview_encoder is None and self.aerial_encoder is None:
+            raise ValueError("Need to create at least one input encoder.")
+        if self.streetview_encoder is not None and self.aerial_encoder is not None:
+            self.modality_fusion = VerticalPooling(c.modality_fusion, dtype)
+        self._cache: Dict = {}
+
+    def build_xyz_grid(self, data: Dict):
+        """`bev_mapper.py:159-196` (inference): separable voxel-centre coordinates, fp32, host side."""
+        t = data["T_view2scene"].t
+        xs, ys = self.grid.cell_centers(0), self.grid.cell_centers(1)
+        z_offset = data.get("z_offset")
+        if z_offset is None:
+            cam_h = np.median(t[..., -1].astype(F), axis=-1).astype(F)                      # :171
+            z_offset = (cam_h - F(self.config.get("scene_z_offset", 4.0))).astype(F)       # :173-174
+        z_offset = np.asarray(z_offset, dtype=F).reshape(-1)
+        base = np.arange(0, self.config.get("scene_z_height", 12.0), self.grid.cell_size).astype(F)
+        zs = ((base[None] + z_offset[:, None]).astype(F) + F(self.grid.cell_size / 2)).astype(F)  # :188-192
+        return xs, ys, zs
+
+    def encode_streetview(self, params, data, train, is_query, debug=False) -> Dict:
+        if "xyz_query" in data and "xyz_grid" not in data:
+            raise NotImplementedError("explicit non-separable xyz_query (BEVLocalizer frustum) is a 'next' row")
+        if "xyz_grid" not in data:
+            data = dict(data)
+            data["xyz_grid"] = self.build_xyz_grid(data)
+        pred = self.streetview_encoder.apply({"params": params["streetview_encoder"]}, data, train, debug=debug)
+        pred["vertical_pooling"] = self.vertical_pooling.apply(None, pred["feature_volume"])
+        pred["feature_plane"] = pred["vertical_pooling"].pop("plane")
+        return pred
+
+    def encode_aerial(self, params, aerial_rgb, train=False) -> Dict:  # bev_mapper.py:203-212
+        if not isinstance(aerial_rgb, torch.Tensor):
+            aerial_rgb = torch.from_numpy(np.ascontiguousarray(aerial_rgb, dtype=F)).cuda()
+        pyr = self.aerial_encoder.apply({"params": params["aerial_encoder"]}, aerial_rgb, train)
+        feats = pyr.features[-1]
+        valid = torch.ones(feats.shape[:-1], dtype=torch.uint8, device=feats.device)
+        return {"feature_plane": types.FeaturePlane(features=feats, valid=valid)}
+
+    def fuse_neural_maps(self, planes, train: bool = False) -> types.FeaturePlane:  # bev_mapper.py:225-252
+        if not planes:
+            raise ValueError("No feature plane given.")
+        if len(planes) == 1:
+            return planes[0]
+        assert len(planes) == 2
+        a, b = planes
+        fa, fb = a.features.contiguous(), b.features.contiguous()
+        cells, C = fa.numel() // fa.shape[-1], fa.shape[-1]
+        out = torch.empty_like(fa)
+        vout = torch.empty(fa.shape[:-1], dtype=torch.uint8, device=fa.device)
+        ops.fuse_max(fa, a.valid.contiguous(), fb, b.valid.contiguous(), cells, C, out, vout)
+        return types.FeaturePlane(features=out, valid=vout)
+
+    def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False,
+              is_query: bool = False) -> Dict:
+        if train:
+            raise NotImplementedError("training (backward kernels) is a 'next' row of SURVEY.md §8(f)")
+        params = variables["params"] if "params" in variables else variables
+        pred, planes = {}, []
+        if self.streetview_encoder is not None:
+            pred["streetview"] = self.encode_streetview(params, data, train, is_query, debug)
+            planes.append(pred["streetview"]["feature_plane"])
+        if self.aerial_encoder is not None and "rasters" in data:
+            pred["aerial"] = self.encode_aerial(params, data["rasters"]["rgb"], train)
+            planes.append(pred["aerial"]["feature_plane"])
+        if not planes:
+            raise ValueError("No map encoder given.")
+        plane = pred["bev_features"] = self.fuse_neural_maps(planes)
+        if self.config.matching_dim is not None:  # bev_mapper.py:284-291
+            dev = plane.features.device
+            key = (id(params), str(dev))
+            if key not in self._cache:
+                mp = params["matching_proj"]
+                self._cache[key] = (torch.from_numpy(np.ascontiguousarray(mp["kernel"], dtype=F)).to(dev),
+                                    torch.from_numpy(np.ascontiguousarray(mp["bias"], dtype=F)).to(dev))
+            k, bvec = self._cache[key]
+            f = plane.features.contiguous()
+            cells = f.numel() // f.shape[-1]
+            out = torch.empty((*f.shape[:-1], self.config.matching_dim), dtype=torch.bfloat16, device=dev)
+            ops.match_head(f, plane.valid.contiguous(), cells, f.shape[-1], k, bvec, out)
+            pred["bev_matching"] = types.FeaturePlane(features=out, valid=plane.valid)
+        return pred
+
+    __call__ = apply

@@ -1,0 +1,500 @@
+// HBM-bound kernels of the image encoder (everything that is not a GEMM):
+//   weight standardisation (StdConv, snap/models/resnet.py:34-41,73-79) -> GEMM B operand
+//   root im2col (2x-1 normalisation + zero/"-1" padding, resnet.py:199, image_encoder.py:32-39)
+//   3x3/2 max-pool (resnet.py:99), GroupNorm statistics + apply (resnet.py:46-70),
+//   x2 bilinear up-sampling (image_encoder.py:86-91), crop(+ReLU) (image_encoder.py:137-141).
+// All are coalesced 16-byte-vector streaming kernels over NHWC bf16.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace snapb200 {
+
+// ------------------------------------------------------------------------------------------
+// weight standardisation (batched over all convs of an encoder in two launches):
+//   HWIO fp32 [K, Cout] (K = KH*KW*Cin) -> bf16 [Cout, ldb], column = k, zero padded to ldb.
+// Kernel A: partial (sum, sumsq) per (conv, cout tile, k split); kernel B: finalise + transpose.
+// ------------------------------------------------------------------------------------------
+struct WeightDesc {
+  const float* w;
+  __nv_bfloat16* out;
+  float2* partial;  // [ksplit][Cout]
+  int K, Cout, ldb, standardize, ksplit, pad_;
+};
+
+__global__ void std_weights_stats_kernel(const WeightDesc* __restrict__ descs,
+                                         const int4* __restrict__ map) {
+  const int4 m = map[blockIdx.x];  // (desc, cout tile, k split, -)
+  const WeightDesc d = descs[m.x];
+  __shared__ float2 red[8][33];
+  const int co = m.y * 32 + threadIdx.x;
+  const bool ok = co < d.Cout;
+  const int kc = (d.K + d.ksplit - 1) / d.ksplit;
+  const int k0 = m.z * kc, k1 = min(d.K, k0 + kc);
+  float s = 0.f, q = 0.f;
+  for (int k = k0 + threadIdx.y; k < k1; k += 8) {
+    const float v = ok ? d.w[(size_t)k * d.Cout + co] : 0.f;
+    s += v;
+    q += v * v;
+  }
+  red[threadIdx.y][threadIdx.x] = make_float2(s, q);
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    float2 t = make_float2(0.f, 0.f);
+    for (int i = 0; i < 8; ++i) {
+      t.x += red[i][threadIdx.x].x;
+      t.y += red[i][threadIdx.x].y;
+    }
+    d.partial[(size_t)m.z * d.Cout + co] = t;
+  }
+}
+
+__global__ void std_weights_write_kernel(const WeightDesc* __restrict__ descs,
+                                         const int4* __restrict__ map, float eps) {
+  const int4 m = map[blockIdx.x];  // (desc, cout tile, k tile of 32, -)
+  const WeightDesc d = descs[m.x];
+  __shared__ float s_mean[32], s_rstd[32];
+  __shared__ float tile[32][33];
+  if (threadIdx.y == 0) {
+    const int co = m.y * 32 + threadIdx.x;
+    float mean = 0.f, rstd = 1.f;
+    if (d.standardize && co < d.Cout) {
+      double s = 0.0, q = 0.0;
+      for (int i = 0; i < d.ksplit; ++i) {
+        const float2 t = d.partial[(size_t)i * d.Cout + co];
+        s += (double)t.x;
+        q += (double)t.y;
+      }
+      const double mu = s / (double)d.K;
+      double var = q / (double)d.K - mu * mu;  // == mean((x - mu)^2)
+      if (var < 0.0) var = 0.0;
+      mean = (float)mu;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+  }
+  __syncthreads();
+  const int co = m.y * 32 + threadIdx.x;
+  const int kb = m.z * 32;
+  for (int kk = threadIdx.y; kk < 32; kk += 8) {
+    const int k = kb + kk;
+    float v = 0.f;
+    if (co < d.Cout && k < d.K) v = (d.w[(size_t)k * d.Cout + co] - s_mean[threadIdx.x]) * s_rstd[threadIdx.x];
+    tile[kk][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int cc = threadIdx.y; cc < 32; cc += 8) {
+    const int c2 = m.y * 32 + cc;
+    const int k = kb + threadIdx.x;
+    if (c2 < d.Cout && k < d.ldb) d.out[(size_t)c2 * d.ldb + k] = __float2bfloat16(tile[threadIdx.x][cc]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// root im2col: image f32 [Nimg,H,W,3] in [0,1] -> A [Nimg*Ho*Wo, Kp] bf16 for a KHxKW/stride conv
+// over the (Hp,Wp) zero-padded-then-normalised image (pad value becomes -1, resnet.py:199).
+// ------------------------------------------------------------------------------------------
+__global__ void root_im2col_kernel(const float* __restrict__ img, int Nimg, int H, int W, int Hp,
+                                   int Wp, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                                   __nv_bfloat16* __restrict__ out, int Kp) {
+  const int chunks = Kp / 8;
+  const long long total = (long long)Nimg * Ho * Wo * chunks;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % chunks);
+  const long long row = idx / chunks;
+  const int wo = (int)(row % Wo);
+  const int ho = (int)((row / Wo) % Ho);
+  const int n = (int)(row / ((long long)Wo * Ho));
+  const int K = KH * KW * 3;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = ch * 8 + j;
+    float val = 0.f;
+    if (k < K) {
+      const int c = k % 3;
+      const int kw = (k / 3) % KW;
+      const int kh = k / (3 * KW);
+      const int hi = ho * stride + kh - pad;
+      const int wi = wo * stride + kw - pad;
+      if (hi >= 0 && hi < Hp && wi >= 0 && wi < Wp) {
+        if (hi < H && wi < W) {
+          const float x = __bfloat162float(__float2bfloat16(img[(((size_t)n * H + hi) * W + wi) * 3 + c]));
+          val = __bfloat162float(__float2bfloat16(x * 2.0f - 1.0f));
+        } else {
+          val = -1.0f;
+        }
+      }
+    }
+    v[j] = val;
+  }
+  uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                       pack_bf16(v[6], v[7]));
+  *reinterpret_cast<uint4*>(out + row * Kp + ch * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 stride-2 max pool, pad 1 (-inf)
+// ------------------------------------------------------------------------------------------
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W,
+                                    int C, __nv_bfloat16* __restrict__ y, int Ho, int Wo) {
+  const int cv = C / 8;
+  const long long total = (long long)Nimg * Ho * Wo * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int wo = (int)(pix % Wo);
+  const int ho = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int hi = ho * 2 + kh - 1;
+    if (hi < 0 || hi >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int wi = wo * 2 + kw - 1;
+      if (wi < 0 || wi >= W) continue;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * C + c8 * 8));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(uu[j]);
+        m[2 * j] = fmaxf(m[2 * j], f.x);
+        m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) =
+      make_uint4(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]), pack_bf16(m[4], m[5]), pack_bf16(m[6], m[7]));
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics (32 groups).  partial[img][chunk][g] = (sum, sumsq) over the chunk's pixels
+// ------------------------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+
+__global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pre_relu,
+                                  int pix_per_chunk, float2* __restrict__ partial) {
+  const int CV = C / 8;            // 16B vectors per pixel (<= 256)
+  const int PL = GN_THREADS / CV;  // pixel lanes
+  const int cpg = C / 32;
+  const int nsub = cpg >= 8 ? 1 : 8 / cpg;  // groups touched by one 8-channel vector
+  const int chans_per_sub = 8 / nsub;
+  const int cv = threadIdx.x % CV;
+  const int pl = threadIdx.x / CV;
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_chunk;
+  const int p1 = min(HW, p0 + pix_per_chunk);
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (pl < PL) {
+    const __nv_bfloat16* base = x + ((size_t)img * HW) * C + cv * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16(uu[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = pre_relu ? fmaxf(f[j], 0.f) : f[j];
+        const int sub = j / chans_per_sub;
+        s[sub] += v;
+        q[sub] += v * v;
+      }
+    }
+  }
+  __shared__ float2 sm[GN_THREADS][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sm[threadIdx.x][k] = make_float2(s[k], q[k]);
+  __syncthreads();
+  // stage 1: reduce over pixel lanes -> one value per (cv, sub)
+  __shared__ float2 sm2[256 * 4 / 1];
+  const int entries = CV * nsub;
+  for (int e = threadIdx.x; e < entries; e += GN_THREADS) {
+    const int ecv = e / nsub, esub = e % nsub;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int l = 0; l < PL; ++l) {
+      const float2 t = sm[l * CV + ecv][esub];
+      acc.x += t.x;
+      acc.y += t.y;
+    }
+    sm2[e] = acc;
+  }
+  __syncthreads();
+  // stage 2: entries are ordered by channel; group g owns entries [g*epg, (g+1)*epg)
+  if (threadIdx.x < 32) {
+    const int epg = entries / 32;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int e = threadIdx.x * epg; e < (threadIdx.x + 1) * epg; ++e) {
+      acc.x += sm2[e].x;
+      acc.y += sm2[e].y;
+    }
+    partial[((size_t)img * gridDim.x + blockIdx.x) * 32 + threadIdx.x] = acc;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int Nimg, int chunks,
+                                   double count, float eps, float2* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nimg * 32) return;
+  const int img = i / 32, g = i % 32;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < chunks; ++c) {
+    const float2 t = partial[((size_t)img * chunks + c) * 32 + g];
+    s += (double)t.x;
+    q += (double)t.y;
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// layouts written by gn_apply
+enum { LAYOUT_DENSE = 0, LAYOUT_PADDED = 1, LAYOUT_PHASE = 2 };
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int C,
+                                const float2* __restrict__ stats, const float* __restrict__ scale,
+                                const float* __restrict__ bias, int pre_relu, int post_relu,
+                                int layout, __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ out_sub) {
+  const int cv = C / 8;
+  const long long total = (long long)Nimg * H * W * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const int c0 = c8 * 8;
+  const int cpg = C / 32;
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * C + c0));
+  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16(uu[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float2 st = __ldg(&stats[n * 32 + c / cpg]);
+    float v = pre_relu ? fmaxf(f[j], 0.f) : f[j];
+    // resnet.py:39-41,57-69 with a bf16 dtype: standardise in fp32 -> bf16, * scale -> bf16, + bias -> bf16
+    v = bf16_round((v - st.x) * st.y);
+    v = bf16_round(v * __ldg(scale + c));
+    v = bf16_round(v + __ldg(bias + c));
+    f[j] = post_relu ? fmaxf(v, 0.f) : v;
+  }
+  const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                             pack_bf16(f[6], f[7]));
+  size_t orow;
+  if (layout == LAYOUT_DENSE) {
+    orow = (size_t)pix;
+  } else if (layout == LAYOUT_PADDED) {
+    orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+  } else {
+    const int Hq = H / 2 + 1, Wq = W / 2 + 1;
+    const int hp = h + 1, wp = w + 1;
+    const size_t plane = (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)Nimg * Hq * Wq);
+    orow = plane + ((size_t)n * Hq + (hp >> 1)) * Wq + (wp >> 1);
+  }
+  *reinterpret_cast<uint4*>(out + orow * C + c0) = o;
+  if (out_sub != nullptr && (h & 1) == 0 && (w & 1) == 0) {
+    const size_t srow = ((size_t)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+    *reinterpret_cast<uint4*>(out_sub + srow * C + c0) = o;
+  }
+}
+
+// x2 bilinear (half-pixel centres, edge clamp): [Nimg,h,w,C] -> [Nimg,2h,2w,C]
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int h, int w, int C,
+                                  __nv_bfloat16* __restrict__ y) {
+  const int cv = C / 8;
+  const int H = 2 * h, W = 2 * w;
+  const long long total = (long long)Nimg * H * W * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int wo = (int)(pix % W);
+  const int ho = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  // source coordinate (o + 0.5)/2 - 0.5 = o/2 - 0.25
+  const int h0 = (ho & 1) ? (ho >> 1) : (ho >> 1) - 1;
+  const int w0 = (wo & 1) ? (wo >> 1) : (wo >> 1) - 1;
+  const float fh = (ho & 1) ? 0.25f : 0.75f;  // weight of the upper tap h0+1
+  const float fw = (wo & 1) ? 0.25f : 0.75f;
+  const int ha = max(h0, 0), hb = min(h0 + 1, h - 1);
+  const int wa = max(w0, 0), wb = min(w0 + 1, w - 1);
+  const __nv_bfloat16* base = x + (size_t)n * h * w * C + c8 * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int hs[2] = {ha, hb}, ws[2] = {wa, wb};
+  const float whs[2] = {1.f - fh, fh}, wws[2] = {1.f - fw, fw};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const float wt = whs[a] * wws[b];
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)hs[a] * w + ws[b]) * C));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16(uu[j]);
+        acc[2 * j] += wt * t.x;
+        acc[2 * j + 1] += wt * t.y;
+      }
+    }
+  *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) =
+      make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                 pack_bf16(acc[6], acc[7]));
+}
+
+// crop top-left (h,w) of [Nimg,Hs,Ws,C] with optional ReLU -> dense [Nimg,h,w,C]
+__global__ void crop_relu_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int Hs, int Ws, int C,
+                                 int h, int w, int relu, __nv_bfloat16* __restrict__ y) {
+  const int cv = C / 8;
+  const long long total = (long long)Nimg * h * w * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int ww = (int)(pix % w);
+  const int hh = (int)((pix / w) % h);
+  const int n = (int)(pix / ((long long)w * h));
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * Hs + hh) * Ws + ww) * C + c8 * 8));
+  if (relu) {
+    uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t = unpack_bf16(uu[j]);
+      uu[j] = pack_bf16(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f));
+    }
+    u = make_uint4(uu[0], uu[1], uu[2], uu[3]);
+  }
+  *reinterpret_cast<uint4*>(y + pix * C + c8 * 8) = u;
+}
+
+static inline unsigned blocks_for(long long total, int threads) {
+  return (unsigned)((total + threads - 1) / threads);
+}
+
+}  // namespace snapb200
+
+using namespace snapb200;
+
+extern "C" {
+
+/* Batched StdConv weight standardisation (resnet.py:34-41,73-79; eps 1e-10) + relayout to the GEMM
+   B operand.  `descs` is a DEVICE array of SnapWeightDesc; mapA / mapB are DEVICE int4 work lists
+   (desc, cout tile, k split | k tile, 0) built by the host once per parameter set. */
+int snapb200_std_weights_batched(const void* descs, const void* mapA, int nA, const void* mapB, int nB,
+                                 void* stream) {
+  SNAP_REQUIRE(descs && mapB && nB > 0, "null pointer");
+  dim3 block(32, 8);
+  if (nA > 0) {
+    SNAP_REQUIRE(mapA != nullptr, "null mapA");
+    std_weights_stats_kernel<<<nA, block, 0, (cudaStream_t)stream>>>((const WeightDesc*)descs,
+                                                                    (const int4*)mapA);
+    int rc = check_launch("std_weights_stats_kernel");
+    if (rc) return rc;
+  }
+  std_weights_write_kernel<<<nB, block, 0, (cudaStream_t)stream>>>((const WeightDesc*)descs,
+                                                                  (const int4*)mapB, 1e-10f);
+  return check_launch("std_weights_write_kernel");
+}
+
+int snapb200_root_im2col(const float* images, int Nimg, int H, int W, int Hp, int Wp, int KH, int KW,
+                         int stride, int pad, void* out_bf16, int Kp, void* stream) {
+  SNAP_REQUIRE(images && out_bf16, "null pointer");
+  SNAP_REQUIRE(Kp % 32 == 0 && Kp >= KH * KW * 3, "Kp must be a multiple of 32 covering KH*KW*3");
+  SNAP_REQUIRE(Hp >= H && Wp >= W && stride >= 1, "bad padded size");
+  const int Ho = (Hp + 2 * pad - KH) / stride + 1, Wo = (Wp + 2 * pad - KW) / stride + 1;
+  const long long total = (long long)Nimg * Ho * Wo * (Kp / 8);
+  root_im2col_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      images, Nimg, H, W, Hp, Wp, KH, KW, stride, pad, Ho, Wo, (__nv_bfloat16*)out_bf16, Kp);
+  return check_launch("root_im2col_kernel");
+}
+
+int snapb200_maxpool3x3s2(const void* x, int Nimg, int H, int W, int C, void* y, void* stream) {
+  SNAP_REQUIRE(x && y, "null pointer");
+  SNAP_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)Nimg * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, Nimg, H, W, C, (__nv_bfloat16*)y, Ho, Wo);
+  return check_launch("maxpool3x3s2_kernel");
+}
+
+size_t snapb200_gn_workspace_bytes(int Nimg, int HW) {
+  const int chunks = (HW + 1023) / 1024 > 0 ? (HW + 1023) / 1024 : 1;
+  return (size_t)Nimg * chunks * 32 * sizeof(float2);
+}
+
+/* GroupNorm(32 groups, eps 1e-5) statistics of x [Nimg, HW, C] (optionally of relu(x)):
+   stats[img][g] = (mean, 1/sqrt(var+eps)).  workspace: snapb200_gn_workspace_bytes. */
+int snapb200_gn_stats(const void* x, int Nimg, int HW, int C, int pre_relu, void* stats,
+                      void* workspace, void* stream) {
+  SNAP_REQUIRE(x && stats && workspace, "null pointer");
+  SNAP_REQUIRE(C % 64 == 0 && C <= 2048, "GroupNorm kernel needs C %% 64 == 0 and C <= 2048 (got %d)", C);
+  const int ppc = 1024;
+  const int chunks = (HW + ppc - 1) / ppc;
+  dim3 grid(chunks, Nimg);
+  gn_partial_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, HW, C, pre_relu, ppc, (float2*)workspace);
+  int rc = check_launch("gn_partial_kernel");
+  if (rc) return rc;
+  const double count = (double)HW * (double)(C / 32);
+  gn_finalize_kernel<<<(Nimg * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      (const float2*)workspace, Nimg, chunks, count, 1e-5f, (float2*)stats);
+  return check_launch("gn_finalize_kernel");
+}
+
+/* y = post_relu?( (pre_relu?(x) - mean) * rstd * scale + bias ), written in `layout`
+   (0 dense [Nimg*H*W, C]; 1 zero-bordered [Nimg,(H+2),(W+2),C]; 2 phase-split);
+   out_sub (optional) additionally receives the even-pixel subsample, dense [Nimg,H/2,W/2,C]. */
+int snapb200_gn_apply(const void* x, int Nimg, int H, int W, int C, const void* stats,
+                      const float* scale, const float* bias, int pre_relu, int post_relu, int layout,
+                      void* out, void* out_sub, void* stream) {
+  SNAP_REQUIRE(x && stats && scale && bias && out, "null pointer");
+  SNAP_REQUIRE(C % 32 == 0, "C must be a multiple of 32");
+  SNAP_REQUIRE(layout >= 0 && layout <= 2, "bad layout");
+  SNAP_REQUIRE((layout != LAYOUT_PHASE && out_sub == nullptr) || (H % 2 == 0 && W % 2 == 0),
+               "phase / subsampled layouts need even H, W");
+  const long long total = (long long)Nimg * H * W * (C / 8);
+  gn_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, Nimg, H, W, C, (const float2*)stats, scale, bias, pre_relu, post_relu,
+      layout, (__nv_bfloat16*)out, (__nv_bfloat16*)out_sub);
+  return check_launch("gn_apply_kernel");
+}
+
+int snapb200_upsample2x(const void* x, int Nimg, int h, int w, int C, void* y, void* stream) {
+  SNAP_REQUIRE(x && y && C % 8 == 0, "bad arguments");
+  const long long total = (long long)Nimg * 4 * h * w * (C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, Nimg, h, w, C, (__nv_bfloat16*)y);
+  return check_launch("upsample2x_kernel");
+}
+
+int snapb200_crop_relu(const void* x, int Nimg, int Hs, int Ws, int C, int h, int w, int relu, void* y,
+                       void* stream) {
+  SNAP_REQUIRE(x && y && C % 8 == 0 && h <= Hs && w <= Ws, "bad arguments");
+  const long long total = (long long)Nimg * h * w * (C / 8);
+  crop_relu_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, Nimg, Hs, Ws, C, h, w, relu, (__nv_bfloat16*)y);
+  return check_launch("crop_relu_kernel");
+}
+
+}  // extern "C"

@@ -241,9 +241,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            // The reference materialises every op output in the compute dtype (bf16): conv/dot result,
+            // then "+ bias", then "+ residual".  Round at the same points when the output is bf16.
+            const bool rnd = !p.out_f32;
+            if (rnd) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = bf16_round(f[j]);
+            }
             if (p.bias) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + col + j);
+              for (int j = 0; j < 16; ++j) {
+                f[j] += __ldg(p.bias + col + j);
+                if (rnd) f[j] = bf16_round(f[j]);
+              }
             }
             if (p.residual) {
               const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);

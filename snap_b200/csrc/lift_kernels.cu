@@ -1,0 +1,386 @@
+// Camera -> BEV lift, v1 (unfused): gather + multi-view pooling kernel that writes the 257-wide
+// statistics rows consumed by the fusion MLP (two tcgen05 GEMMs, gemm_tc.cuh), then vertical /
+// modality max pooling and the matching head.
+//
+// Reference: snap/models/streetview_encoder.py:42-65 (projection), :69-76 + snap/utils/grids.py:116-137
+// (bilinear gather), :109-124 (depth score), :141-178 (weighted pooling), snap/models/bev_mapper.py:56-88
+// (vertical pooling), :225-252 (modality fusion), :284-291 + snap/models/layers.py:45-52 (matching head).
+//
+// The projection prologue uses explicit round-to-nearest mul/add/div in the oracle's operation order
+// (no FMA contraction) so that visibility masks and tap indices are bit-exact w.r.t. oracle/geometry.py.
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace snapb200 {
+
+constexpr int LIFT_MAX_VIEWS = 8;
+
+struct LiftView {
+  float Rinv[9];  // row-major inverse rotation (scene -> view)
+  float tinv[3];
+  float f[2], c[2], wh[2];  // camera scaled to feature resolution, (x, y) order
+  float k_radial[3];
+  float tan_half_fov;
+  int fisheye;
+};
+
+struct LiftParams {
+  int V, Hf, Wf, CF, D, S;  // CF = D + S channels per texel
+  int X, Y, Z;
+  float depth_min, depth_max, inv_log_range;  // 1 / log(max/min)
+  int stats_ld;                               // row pitch of the stats matrix (>= 2*D + 1, mult of 32)
+  LiftView view[LIFT_MAX_VIEWS];
+};
+
+struct Proj {
+  float row, col, depth;
+  bool vis;
+};
+
+__device__ __forceinline__ Proj project_point(const LiftView& v, float px, float py, float pz) {
+  float pv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float s = __fmul_rn(v.Rinv[3 * i + 0], px);
+    s = __fadd_rn(s, __fmul_rn(v.Rinv[3 * i + 1], py));
+    s = __fadd_rn(s, __fmul_rn(v.Rinv[3 * i + 2], pz));
+    pv[i] = __fadd_rn(v.tinv[i], s);
+  }
+  const float eps = 1e-3f;
+  bool vis = pv[2] >= eps;
+  const float zc = fmaxf(pv[2], eps);
+  float x = __fdiv_rn(pv[0], zc);
+  float y = __fdiv_rn(pv[1], zc);
+  if (v.fisheye) {  // snap/utils/geometry.py:260-272 (float tolerance only: atan differs in ulps)
+    const float eps2 = __fmul_rn(eps, eps);
+    const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    const bool in_center = r2 < eps2;
+    const float radius = sqrtf(in_center ? eps2 : r2);
+    const float theta = atanf(radius);
+    const float t2 = theta * theta;
+    const float offset = v.k_radial[0] * t2 + v.k_radial[1] * t2 * t2 + v.k_radial[2] * t2 * t2 * t2;
+    float dist = (offset + 1.0f) * theta / radius;
+    if (in_center) dist = 1.0f;
+    x *= dist;
+    y *= dist;
+    vis = vis && (in_center || (radius < v.tan_half_fov && dist > 0.f));
+  }
+  const float u = __fadd_rn(__fmul_rn(x, v.f[0]), v.c[0]);
+  const float w = __fadd_rn(__fmul_rn(y, v.f[1]), v.c[1]);
+  vis = vis && u >= 0.f && u < v.wh[0] && w >= 0.f && w < v.wh[1];
+  Proj p;
+  p.row = w;  // flipped to (row, col), streetview_encoder.py:59
+  p.col = u;
+  p.depth = pv[2];
+  p.vis = vis;
+  return p;
+}
+
+struct Taps {
+  int r0, r1, c0, c1;  // clamped tap indices
+  int rlo, clo;        // unclamped floor (for the parity debug output)
+  float wr1, wc1;      // weights of the upper taps
+};
+
+__device__ __forceinline__ Taps make_taps(float row, float col, int Hf, int Wf) {
+  Taps t;
+  const float pr = __fadd_rn(row, -0.5f), pc = __fadd_rn(col, -0.5f);
+  const float fr = floorf(pr), fc = floorf(pc);
+  t.rlo = (int)fr;
+  t.clo = (int)fc;
+  t.wr1 = __fadd_rn(pr, -fr);
+  t.wc1 = __fadd_rn(pc, -fc);
+  t.r0 = min(max(t.rlo, 0), Hf - 1);
+  t.r1 = min(max(t.rlo + 1, 0), Hf - 1);
+  t.c0 = min(max(t.clo, 0), Wf - 1);
+  t.c1 = min(max(t.clo + 1, 0), Wf - 1);
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16(uu[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+// One warp per voxel; one CTA (8 warps) per (x,y) column.  D must be 128 (16 lanes x 8 channels).
+__global__ void __launch_bounds__(256)
+lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const __nv_bfloat16* __restrict__ fimg,
+                        const float* __restrict__ xs, const float* __restrict__ ys,
+                        const float* __restrict__ zs, __nv_bfloat16* __restrict__ stats,
+                        uint8_t* __restrict__ valid, uint8_t* __restrict__ dbg_vis,
+                        int* __restrict__ dbg_taps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col_id = blockIdx.x;  // x * Y + y
+  const int ix = col_id / P.Y, iy = col_id - ix * P.Y;
+  const float px = xs[ix], py = ys[iy];
+  const int half = lane >> 4;  // 0: lower row tap, 1: upper row tap
+  const int c8 = lane & 15;    // feature channels [8*c8, 8*c8+8)
+  const float score_scale = (float)(P.S - 1);
+
+  for (int iz = warp; iz < P.Z; iz += 8) {
+    const long long n = (long long)col_id * P.Z + iz;
+    const float pz = zs[iz];
+    float fv[LIFT_MAX_VIEWS][8];
+    float score[LIFT_MAX_VIEWS];
+    unsigned vis_mask = 0;
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+      score[v] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fv[v][j] = 0.f;
+    }
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+      if (v >= P.V) break;
+      const Proj pr = project_point(P.view[v], px, py, pz);
+      const Taps t = make_taps(pr.row, pr.col, P.Hf, P.Wf);
+      if (dbg_vis != nullptr && lane == 0) {
+        dbg_vis[n * P.V + v] = pr.vis ? 1 : 0;
+        dbg_taps[(n * P.V + v) * 2 + 0] = t.rlo;
+        dbg_taps[(n * P.V + v) * 2 + 1] = t.clo;
+      }
+      if (!pr.vis) continue;  // warp-uniform
+      vis_mask |= 1u << v;
+      const __nv_bfloat16* img = fimg + (size_t)v * P.Hf * P.Wf * P.CF;
+      // --- features: each half-warp reads one tap row, both column taps -------------------------
+      const int rr = half ? t.r1 : t.r0;
+      const float wr = half ? t.wr1 : __fadd_rn(1.0f, -t.wr1);
+      const float wc0 = __fadd_rn(1.0f, -t.wc1);
+      const uint4 ua = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)rr * P.Wf + t.c0) * P.CF + c8 * 8));
+      const uint4 ub = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)rr * P.Wf + t.c1) * P.CF + c8 * 8));
+      float fa[8], fb[8];
+      unpack8(ua, fa);
+      unpack8(ub, fb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float part = wr * (wc0 * fa[j] + t.wc1 * fb[j]);
+        part += __shfl_xor_sync(0xffffffffu, part, 16);
+        fv[v][j] = bf16_round(part);  // interpolated features are materialised in the feature dtype
+      }
+      // --- depth score: linear interpolation over the S log-depth bins of the 4 taps ------------
+      const float d = fminf(fmaxf(pr.depth, P.depth_min), P.depth_max);
+      const float tt = logf(d / P.depth_min) * P.inv_log_range;
+      const float bi = tt * score_scale;  // (0.5 + t*(S-1)) - 0.5
+      const float bf = floorf(bi);
+      const int b0 = min(max((int)bf, 0), P.S - 1), b1 = min(max((int)bf + 1, 0), P.S - 1);
+      const float wb1 = bi - bf;
+      // lanes 0..7 = 4 taps x 2 bins: spatial interpolation per bin (-> bf16, as the reference
+      // interpolates all S logits first), then the linear interpolation across bins (-> bf16)
+      float sp = 0.f;
+      if (lane < 8) {
+        const int tap = lane >> 1, bsel = lane & 1;
+        const int r = (tap & 2) ? t.r1 : t.r0;
+        const int c = (tap & 1) ? t.c1 : t.c0;
+        const float wt = ((tap & 2) ? t.wr1 : 1.0f - t.wr1) * ((tap & 1) ? t.wc1 : 1.0f - t.wc1);
+        const float s = __bfloat162float(img[((size_t)r * P.Wf + c) * P.CF + P.D + (bsel ? b1 : b0)]);
+        sp = wt * s;
+      }
+      sp += __shfl_xor_sync(0xffffffffu, sp, 2);
+      sp += __shfl_xor_sync(0xffffffffu, sp, 4);
+      sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
+      sp += __shfl_xor_sync(0xffffffffu, sp, 1);
+      sp = bf16_round(sp);
+      score[v] = __shfl_sync(0xffffffffu, sp, 0);
+    }
+    // --- weighted pooling over views (softmax with where=valid, initial=0) ----------------------
+    float mean[8], var[8], smax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
+    if (vis_mask != 0) {
+      float mx = 0.f;
+#pragma unroll
+      for (int v = 0; v < LIFT_MAX_VIEWS; ++v)
+        if (vis_mask & (1u << v)) {
+          mx = fmaxf(mx, score[v]);
+          smax = fmaxf(smax, score[v]);
+        }
+      float wv[LIFT_MAX_VIEWS], den = 0.f;
+#pragma unroll
+      for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+        wv[v] = (vis_mask & (1u << v)) ? expf(score[v] - mx) : 0.f;
+        den += wv[v];
+      }
+#pragma unroll
+      for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+        wv[v] = __fdiv_rn(wv[v], den);  // true division: a single visible view gets weight exactly 1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mean[j] += wv[v] * fv[v][j];
+      }
+#pragma unroll
+      for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dd = fv[v][j] - mean[j];
+          var[j] += wv[v] * dd * dd;
+        }
+      }
+    } else {
+      smax = 0.f;
+    }
+    // --- write the statistics row: [mean(D) | var(D) | score_max | 0 ...] -----------------------
+    __nv_bfloat16* row = stats + n * P.stats_ld;
+    const float* src = half ? var : mean;
+    *reinterpret_cast<uint4*>(row + half * P.D + c8 * 8) =
+        make_uint4(pack_bf16(src[0], src[1]), pack_bf16(src[2], src[3]), pack_bf16(src[4], src[5]),
+                   pack_bf16(src[6], src[7]));
+    const int tail_vecs = (P.stats_ld - 2 * P.D) / 8;
+    if (lane < tail_vecs) {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      if (lane == 0) z.x = pack_bf16(smax, 0.f);
+      *reinterpret_cast<uint4*>(row + 2 * P.D + lane * 8) = z;
+    }
+    if (lane == 0) valid[n] = vis_mask != 0 ? 1 : 0;
+  }
+}
+
+// max over the Z axis where valid; zero (and invalid) where no z is valid.  [cells, Z, C] -> [cells, C]
+__global__ void vertical_max_kernel(const __nv_bfloat16* __restrict__ vol, const uint8_t* __restrict__ valid,
+                                    long long cells, int Z, int C, __nv_bfloat16* __restrict__ plane,
+                                    uint8_t* __restrict__ pvalid) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells * cv) return;
+  const int c8 = (int)(idx % cv);
+  const long long cell = idx / cv;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  bool any = false;
+  for (int z = 0; z < Z; ++z) {
+    if (!valid[cell * Z + z]) continue;
+    any = true;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(vol + ((size_t)cell * Z + z) * C + c8 * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+  }
+  if (!any) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;
+  }
+  *reinterpret_cast<uint4*>(plane + cell * C + c8 * 8) =
+      make_uint4(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]), pack_bf16(m[4], m[5]), pack_bf16(m[6], m[7]));
+  if (c8 == 0) pvalid[cell] = any ? 1 : 0;
+}
+
+// Dense(C -> DM) + bias, (bf16 round), L2-normalise (eps 1e-5), mask.  One warp per cell, DM == 32.
+__global__ void __launch_bounds__(256)
+match_head_kernel(const __nv_bfloat16* __restrict__ plane, const uint8_t* __restrict__ valid,
+                  long long cells, int C, const float* __restrict__ kernel /*[C,32]*/,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float wsm[];  // [C][32]
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) wsm[i] = kernel[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float b = bias[lane];
+  for (long long cell = (long long)blockIdx.x * 8 + warp; cell < cells; cell += (long long)gridDim.x * 8) {
+    float acc = 0.f;
+    for (int k0 = 0; k0 < C; k0 += 32) {
+      const float xk = __bfloat162float(plane[cell * C + k0 + lane]);
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc += __shfl_sync(0xffffffffu, xk, k) * wsm[(k0 + k) * 32 + lane];
+    }
+    const float y = bf16_round(bf16_round(acc) + b);  // nn.Dense: dot -> dtype, + bias -> dtype
+    float ss = y * y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(ss);
+    float z = (nrm < 1e-5f) ? 0.f : y / nrm;
+    if (!valid[cell]) z = 0.f;
+    out[cell * 32 + lane] = __float2bfloat16(z);
+  }
+}
+
+// modality fusion: max over up to 3 planes where valid (VerticalPooling('max') over the modality axis)
+__global__ void fuse_max_kernel(const __nv_bfloat16* __restrict__ a, const uint8_t* __restrict__ va,
+                                const __nv_bfloat16* __restrict__ b, const uint8_t* __restrict__ vb,
+                                long long cells, int C, __nv_bfloat16* __restrict__ out,
+                                uint8_t* __restrict__ vout) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells * cv) return;
+  const int c8 = (int)(idx % cv);
+  const long long cell = idx / cv;
+  const bool oa = va[cell] != 0, ob = (vb == nullptr) ? true : vb[cell] != 0;
+  float fa[8], fb[8], m[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a + cell * C + c8 * 8)), fa);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + cell * C + c8 * 8)), fb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = -INFINITY;
+    if (oa) v = fmaxf(v, fa[j]);
+    if (ob) v = fmaxf(v, fb[j]);
+    m[j] = (oa || ob) ? v : 0.f;
+  }
+  *reinterpret_cast<uint4*>(out + cell * C + c8 * 8) =
+      make_uint4(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]), pack_bf16(m[4], m[5]), pack_bf16(m[6], m[7]));
+  if (c8 == 0) vout[cell] = (oa || ob) ? 1 : 0;
+}
+
+}  // namespace snapb200
+
+using namespace snapb200;
+
+extern "C" {
+
+/* Host-side mirror of LiftParams/LiftView: the caller fills SnapLiftParams (include/snapb200.h). */
+int snapb200_lift_gather_pool(const SnapLiftParams* q, const void* fimg, const float* xs, const float* ys,
+                              const float* zs, void* stats, uint8_t* valid, uint8_t* dbg_vis,
+                              int* dbg_taps, void* stream) {
+  SNAP_REQUIRE(q && fimg && xs && ys && zs && stats && valid, "null pointer");
+  SNAP_REQUIRE(q->V >= 1 && q->V <= LIFT_MAX_VIEWS, "1 <= V <= %d required (got %d)", LIFT_MAX_VIEWS, q->V);
+  SNAP_REQUIRE(q->D == 128, "feature_dim must be 128 (got %d)", q->D);
+  SNAP_REQUIRE(q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
+  SNAP_REQUIRE(q->stats_ld % 32 == 0 && q->stats_ld >= 2 * q->D + 8 && q->stats_ld <= 2 * q->D + 256,
+               "bad stats_ld %d", q->stats_ld);
+  SNAP_REQUIRE((dbg_vis == nullptr) == (dbg_taps == nullptr), "debug outputs come as a pair");
+  static_assert(sizeof(SnapLiftView) == sizeof(LiftView), "SnapLiftView layout");
+  static_assert(sizeof(SnapLiftParams) == sizeof(LiftParams), "SnapLiftParams layout");
+  LiftParams P;
+  memcpy(&P, q, sizeof(P));
+  const unsigned grid = (unsigned)(q->X * q->Y);
+  lift_gather_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      P, (const __nv_bfloat16*)fimg, xs, ys, zs, (__nv_bfloat16*)stats, valid, dbg_vis, dbg_taps);
+  return check_launch("lift_gather_pool_kernel");
+}
+
+int snapb200_vertical_max(const void* volume, const uint8_t* valid, long long cells, int Z, int C,
+                          void* plane, uint8_t* plane_valid, void* stream) {
+  SNAP_REQUIRE(volume && valid && plane && plane_valid && C % 8 == 0, "bad arguments");
+  const long long total = cells * (C / 8);
+  vertical_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)volume, valid, cells, Z, C, (__nv_bfloat16*)plane, plane_valid);
+  return check_launch("vertical_max_kernel");
+}
+
+int snapb200_match_head(const void* plane, const uint8_t* valid, long long cells, int C,
+                        const float* kernel, const float* bias, int dm, void* out, void* stream) {
+  SNAP_REQUIRE(plane && valid && kernel && bias && out, "null pointer");
+  SNAP_REQUIRE(dm == 32 && C % 32 == 0 && C <= 256, "matching head needs matching_dim 32, C %% 32 == 0, C <= 256");
+  const size_t smem = (size_t)C * 32 * sizeof(float);
+  unsigned grid = (unsigned)((cells + 7) / 8);
+  if (grid > 4u * 148u) grid = 4u * 148u;
+  match_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)plane, valid, cells, C, kernel, bias, (__nv_bfloat16*)out);
+  return check_launch("match_head_kernel");
+}
+
+int snapb200_fuse_max(const void* a, const uint8_t* va, const void* b, const uint8_t* vb, long long cells,
+                      int C, void* out, uint8_t* vout, void* stream) {
+  SNAP_REQUIRE(a && va && b && out && vout && C % 8 == 0, "bad arguments");
+  const long long total = cells * (C / 8);
+  fuse_max_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, va, (const __nv_bfloat16*)b, vb, cells, C, (__nv_bfloat16*)out, vout);
+  return check_launch("fuse_max_kernel");
+}
+
+}  // extern "C"

@@ -87,3 +87,138 @@ def gemm(
     p.bn = bn
     _lib.check(_lib.lib().snapb200_gemm_bf16(C.byref(p), _stream()))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# image-encoder kernels
+# --------------------------------------------------------------------------------------------
+def std_weights_batched(descs: torch.Tensor, mapA: Optional[torch.Tensor], mapB: torch.Tensor) -> None:
+    nA = 0 if mapA is None else mapA.shape[0]
+    _lib.check(_lib.lib().snapb200_std_weights_batched(
+        C.c_void_p(_ptr(descs)), C.c_void_p(_ptr(mapA) if nA else None), C.c_int(nA),
+        C.c_void_p(_ptr(mapB)), C.c_int(mapB.shape[0]), _stream()))
+
+
+def root_im2col(images: torch.Tensor, Hp: int, Wp: int, KH: int, KW: int, stride: int, pad: int,
+                out: torch.Tensor) -> None:
+    _require(images, torch.float32, "images")
+    n, H, W, c = images.shape
+    assert c == 3 and images.is_contiguous()
+    _lib.check(_lib.lib().snapb200_root_im2col(
+        C.c_void_p(_ptr(images)), n, H, W, Hp, Wp, KH, KW, stride, pad, C.c_void_p(_ptr(out)),
+        C.c_int(out.shape[1]), _stream()))
+
+
+def maxpool3x3s2(x: torch.Tensor, n: int, H: int, W: int, Cc: int, y: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_maxpool3x3s2(C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(y)), _stream()))
+
+
+def gn_workspace_bytes(n: int, hw: int) -> int:
+    f = _lib.lib().snapb200_gn_workspace_bytes
+    f.restype = C.c_size_t
+    return int(f(C.c_int(n), C.c_int(hw)))
+
+
+def gn_stats(x: torch.Tensor, n: int, hw: int, Cc: int, pre_relu: bool, stats: torch.Tensor,
+             workspace: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_gn_stats(C.c_void_p(_ptr(x)), n, hw, Cc, int(pre_relu),
+                                            C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(workspace)), _stream()))
+
+
+LAYOUT_DENSE, LAYOUT_PADDED, LAYOUT_PHASE = 0, 1, 2
+
+
+def gn_apply(x: torch.Tensor, n: int, H: int, W: int, Cc: int, stats: torch.Tensor, scale: torch.Tensor,
+             bias: torch.Tensor, pre_relu: bool, post_relu: bool, layout: int, out: torch.Tensor,
+             out_sub: Optional[torch.Tensor] = None) -> None:
+    _lib.check(_lib.lib().snapb200_gn_apply(
+        C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(scale)),
+        C.c_void_p(_ptr(bias)), int(pre_relu), int(post_relu), layout, C.c_void_p(_ptr(out)),
+        C.c_void_p(_ptr(out_sub)), _stream()))
+
+
+def upsample2x(x: torch.Tensor, n: int, h: int, w: int, Cc: int, y: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_upsample2x(C.c_void_p(_ptr(x)), n, h, w, Cc, C.c_void_p(_ptr(y)), _stream()))
+
+
+def crop_relu(x: torch.Tensor, n: int, Hs: int, Ws: int, Cc: int, h: int, w: int, relu: bool,
+              y: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_crop_relu(C.c_void_p(_ptr(x)), n, Hs, Ws, Cc, h, w, int(relu),
+                                             C.c_void_p(_ptr(y)), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# lift
+# --------------------------------------------------------------------------------------------
+def lift_gather_pool(p: "_lib.LiftParams", fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                     zs: torch.Tensor, stats: torch.Tensor, valid: torch.Tensor,
+                     dbg_vis: Optional[torch.Tensor] = None, dbg_taps: Optional[torch.Tensor] = None) -> None:
+    _require(fimg, torch.bfloat16, "fimg")
+    _lib.check(_lib.lib().snapb200_lift_gather_pool(
+        C.byref(p), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
+        C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(valid)),
+        C.c_void_p(_ptr(dbg_vis)), C.c_void_p(_ptr(dbg_taps)), _stream()))
+
+
+def vertical_max(volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, Cc: int,
+                 plane: torch.Tensor, pvalid: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_vertical_max(
+        C.c_void_p(_ptr(volume)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Z, Cc,
+        C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(pvalid)), _stream()))
+
+
+def match_head(plane: torch.Tensor, valid: torch.Tensor, cells: int, Cc: int, kernel: torch.Tensor,
+               bias: torch.Tensor, out: torch.Tensor) -> None:
+    _require(kernel, torch.float32, "kernel")
+    _lib.check(_lib.lib().snapb200_match_head(
+        C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Cc,
+        C.c_void_p(_ptr(kernel)), C.c_void_p(_ptr(bias)), C.c_int(kernel.shape[1]),
+        C.c_void_p(_ptr(out)), _stream()))
+
+
+def fuse_max(a: torch.Tensor, va: torch.Tensor, b: torch.Tensor, vb: Optional[torch.Tensor], cells: int,
+             Cc: int, out: torch.Tensor, vout: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_fuse_max(
+        C.c_void_p(_ptr(a)), C.c_void_p(_ptr(va)), C.c_void_p(_ptr(b)), C.c_void_p(_ptr(vb)),
+        C.c_longlong(cells), Cc, C.c_void_p(_ptr(out)), C.c_void_p(_ptr(vout)), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# exhaustive pose voting
+# --------------------------------------------------------------------------------------------
+def xcorr_padded_cols(G: int) -> int:
+    return int(_lib.lib().snapb200_xcorr_padded_cols(C.c_int(G)))
+
+
+def rot_templates(feats: torch.Tensor, valid: torch.Tensor, conf: Optional[torch.Tensor], rot_host,
+                  centers: torch.Tensor, cell_size: float, R: int, templates: torch.Tensor,
+                  t_valid: torch.Tensor) -> None:
+    _require(feats, torch.bfloat16, "feats")
+    B, G, _, D = feats.shape
+    rot = (C.c_float * (R // 4 * 4))(*[float(x) for x in rot_host.reshape(-1)])
+    _lib.check(_lib.lib().snapb200_rot_templates(
+        C.c_void_p(_ptr(feats)), C.c_void_p(_ptr(valid)), C.c_void_p(_ptr(conf)), rot,
+        C.c_void_p(_ptr(centers)), C.c_float(cell_size), B, R, G, D, C.c_void_p(_ptr(templates)),
+        C.c_void_p(_ptr(t_valid)), _stream()))
+
+
+def xcorr_pad_map(m: torch.Tensor, out: torch.Tensor) -> None:
+    _require(m, torch.bfloat16, "m")
+    B, G, _, D = m.shape
+    _lib.check(_lib.lib().snapb200_xcorr_pad_map(C.c_void_p(_ptr(m)), B, G, D, C.c_void_p(_ptr(out)), _stream()))
+
+
+def xcorr_count(t_valid: torch.Tensor, m_valid: torch.Tensor, cnt: torch.Tensor, den: torch.Tensor) -> None:
+    B, R, G, _ = t_valid.shape
+    _lib.check(_lib.lib().snapb200_xcorr_count(
+        C.c_void_p(_ptr(t_valid)), C.c_void_p(_ptr(m_valid)), B, R, G, C.c_void_p(_ptr(cnt)),
+        C.c_void_p(_ptr(den)), _stream()))
+
+
+def xcorr_scores(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optional[torch.Tensor],
+                 den: Optional[torch.Tensor], thr: float, scores: torch.Tensor) -> None:
+    B, R, G, _, D = templates.shape
+    _require(scores, torch.float32, "scores")
+    _lib.check(_lib.lib().snapb200_xcorr_scores(
+        C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)),
+        C.c_void_p(_ptr(den)), B, R, G, D, C.c_float(thr), C.c_void_p(_ptr(scores)), _stream()))

@@ -1,0 +1,154 @@
+"""B200 implementation behind `snap.models.streetview_encoder.StreetViewEncoder`
+(`snap/models/streetview_encoder.py:181-287`): image encoder -> proj MLP -> camera->voxel lift ->
+multi-view pooling -> fusion MLP -> FeatureVolume.
+
+v1 pipeline (unfused): crop+ReLU -> proj GEMM (128->160, bias) -> `lift_gather_pool` kernel (projection,
+bilinear gather, depth score, softmax pooling; writes the 257-wide statistics rows) -> fusion MLP as two
+tcgen05 GEMMs (bias+ReLU / bias+valid-mask epilogues).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, configs, image_encoder, ops, types
+
+F = np.float32
+
+
+def fill_lift_params(cfg, camera: types.Camera, T_view2scene: types.Transform3D, b: int, stride,
+                     hf: int, wf: int, X: int, Y: int, Z: int, stats_ld: int) -> "_lib.LiftParams":
+    """Host-side, fp32, in the oracle's operation order: scaled cameras (`streetview_encoder.py:224`) and
+    inverse view transforms (`snap/utils/geometry.py:52-56`)."""
+    V = camera.f.shape[1]
+    if V > _lib.MAX_VIEWS:
+        raise NotImplementedError(f"V={V} > {_lib.MAX_VIEWS}: the top-k view-selection path is a 'next' row")
+    cam = camera.scale(np.asarray([1 / stride[1], 1 / stride[0]], dtype=F))
+    Tinv = types.Transform3D(R=T_view2scene.R[b], t=T_view2scene.t[b]).inv
+    p = _lib.LiftParams()
+    p.V, p.Hf, p.Wf = V, hf, wf
+    p.D, p.S = cfg.feature_dim, cfg.num_scale_bins
+    p.CF = p.D + p.S
+    p.X, p.Y, p.Z = X, Y, Z
+    dmin, dmax = cfg.depth_min_max
+    p.depth_min, p.depth_max = dmin, dmax
+    p.inv_log_range = float(F(1.0) / np.log(F(dmax / dmin)).astype(F))
+    p.stats_ld = stats_ld
+    for v in range(V):
+        lv = p.view[v]
+        for i, x in enumerate(Tinv.R[v].reshape(-1)):
+            lv.Rinv[i] = float(x)
+        for i in range(3):
+            lv.tinv[i] = float(Tinv.t[v, i])
+        for i in range(2):
+            lv.f[i], lv.c[i], lv.wh[i] = float(cam.f[b, v, i]), float(cam.c[b, v, i]), float(cam.wh[b, v, i])
+        if isinstance(camera, types.FisheyeCamera):
+            lv.fisheye = 1
+            for i in range(3):
+                lv.k_radial[i] = float(camera.k_radial[b, v, i])
+            lv.tan_half_fov = float(np.tan(F(0.5) * camera.max_fov[b, v]).astype(F))
+    return p
+
+
+class StreetViewEncoder:
+    """Mirror of `snap.models.streetview_encoder.StreetViewEncoder` (`:181-287`)."""
+
+    default_config = staticmethod(configs.streetview_encoder)
+
+    def __init__(self, config=None, dtype=torch.bfloat16):
+        self.config = config if config is not None else configs.streetview_encoder()
+        c = self.config
+        if not c.do_weighted_fusion or c.fusion_add_minmax or not c.fusion_use_variance or c.depth_mlp is not None:
+            raise NotImplementedError("only the default weighted fusion (mean+var+score_max) is built")
+        if tuple(c.fusion.layers) != (256, 128) or c.feature_dim != 128:
+            raise NotImplementedError("fusion MLP must be 257->256->128")
+        self.dtype = dtype
+        self.image_encoder = image_encoder.ImageEncoder(c.image_encoder, dtype)
+        self._cache: Dict = {}
+
+    def _weights(self, params: Dict, device):
+        key = (id(params), str(device))
+        if key not in self._cache:
+            bank = image_encoder._WeightBank(device)
+            f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).reshape(-1)).to(device)
+            w = dict(bank=bank,
+                     proj=bank.add(params["proj_mlp"]["Dense_0"]["kernel"], False),
+                     fus0=bank.add(params["fusion_mlp"]["Dense_0"]["kernel"], False, k_multiple=32),
+                     fus1=bank.add(params["fusion_mlp"]["Dense_1"]["kernel"], False),
+                     proj_b=f32(params["proj_mlp"]["Dense_0"]["bias"]),
+                     fus0_b=f32(params["fusion_mlp"]["Dense_0"]["bias"]),
+                     fus1_b=f32(params["fusion_mlp"]["Dense_1"]["bias"]))
+            bank.finalize()
+            self._cache[key] = w
+        return self._cache[key]
+
+    def _buffers(self, device, B, V, hf, wf, X, Y, Z):
+        key = ("buf", str(device), B, V, hf, wf, X, Y, Z)
+        if key not in self._cache:
+            N = X * Y * Z
+            z = lambda *s, dt=torch.bfloat16: torch.zeros(s, dtype=dt, device=device)
+            rows_img = max(V * hf * wf, 128)
+            self._cache[key] = dict(
+                crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
+                volume=z(B, N, 128), valid=z(B, N, dt=torch.uint8))
+        return self._cache[key]
+
+    def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False) -> Dict:
+        if train:
+            raise NotImplementedError("training (backward kernels) is a 'next' row of SURVEY.md §8(f)")
+        params = variables["params"] if "params" in variables else variables
+        cfg = self.config
+        images = data["images"]
+        if not isinstance(images, torch.Tensor):
+            images = torch.from_numpy(np.ascontiguousarray(images, dtype=F)).cuda()
+        B, V, H, W, _ = images.shape
+        dev = images.device
+        pyr = data.get("image_feature_pyr")
+        if pyr is None:
+            pyr = self.image_encoder.apply({"params": params["image_encoder"]},
+                                           images.reshape(B * V, H, W, 3), train)
+        f_images = pyr.features[-1]            # [B*V, hf, wf, 128] view of the (uncropped) FPN buffer
+        stride = pyr.strides[-1]
+        hf, wf = f_images.shape[1:3]
+        xs, ys, zs = data["xyz_grid"]          # xs [X], ys [Y] (NumPy fp32), zs [B, Z]
+        X, Y, Z = len(xs), len(ys), zs.shape[1]
+        wts = self._weights(params, dev)
+        buf = self._buffers(dev, B, V, hf, wf, X, Y, Z)
+        bank = wts["bank"]
+        bank.run()
+        Bm = bank.b_mats
+        N = X * Y * Z
+        xs_d, ys_d = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+        zs_d = torch.from_numpy(np.ascontiguousarray(zs, dtype=F)).to(dev)
+        full = pyr.uncropped[-1] if getattr(pyr, "uncropped", None) is not None else f_images.contiguous()
+        Hs, Ws = full.shape[1], full.shape[2]
+        dbg = {}
+        for b in range(B):
+            # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`)
+            ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, True, buf["crop"])
+            ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"][b], m_rows=V * hf * wf, bias=wts["proj_b"])
+            lp = fill_lift_params(cfg, data["camera"], data["T_view2scene"], b, stride, hf, wf, X, Y, Z, 288)
+            dv = dt = None
+            if debug:
+                dv = torch.zeros((N, V), dtype=torch.uint8, device=dev)
+                dt = torch.zeros((N, V, 2), dtype=torch.int32, device=dev)
+                dbg.setdefault("vis", []).append(dv)
+                dbg.setdefault("taps", []).append(dt)
+            ops.lift_gather_pool(lp, buf["fimg"][b], xs_d, ys_d, zs_d[b], buf["stats"], buf["valid"][b], dv, dt)
+            # fusion MLP 257 -> 256 -> 128 (`:281`), zero where invalid (`:282`)
+            ops.gemm(buf["stats"], Bm[wts["fus0"]], buf["hid"], m_rows=N, seg_k=288, bias=wts["fus0_b"], relu=True)
+            ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],
+                     row_mask=buf["valid"][b])
+        pred = {"image_feature_pyramid": pyr,
+                "scores_images": buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)[..., 128:],
+                "feature_volume": types.FeatureVolume(features=buf["volume"].view(B, X, Y, Z, 128),
+                                                      valid=buf["valid"].view(B, X, Y, Z))}
+        if debug:
+            pred["debug"] = {k: torch.stack(v) for k, v in dbg.items()}
+            pred["debug"]["f_proj_images"] = buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)
+        return pred
+
+    __call__ = apply

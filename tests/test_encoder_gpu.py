@@ -1,0 +1,185 @@
+"""Image-encoder kernels and the full ImageEncoder vs the oracle (oracle/resnet.py, oracle/image_encoder.py)."""
+import numpy as np
+import pytest
+import torch
+
+from util import F, assert_close_bf16, bf16_np, rd_bf16, rel_l2
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=F))
+
+
+def test_std_weights_vs_oracle():
+    from oracle import resnet as ores
+    from snap_b200.image_encoder import _WeightBank
+    rng = np.random.default_rng(0)
+    shapes = [(7, 7, 3, 64), (1, 1, 64, 256), (3, 3, 128, 128), (1, 1, 2048, 128), (257, 256)]
+    stds = [True, True, True, False, False]
+    bank = _WeightBank(torch.device("cuda"))
+    ks = [bank.add((rng.standard_normal(s) * 0.1 + 0.02).astype(F), st, 32) for s, st in zip(shapes, stds)]
+    bank.finalize()
+    bank.run()
+    torch.cuda.synchronize()
+    for i, (s, st) in enumerate(zip(shapes, stds)):
+        w = bank.entries[i][0]  # [K, Cout]
+        ref = ores.std_kernel(_t(w).reshape(*s)).reshape(-1, s[-1]).numpy() if st else w
+        out = bank.b_mats[i].float().cpu().numpy()
+        K = w.shape[0]
+        assert_close_bf16(out[: s[-1], :K], ref.T, f"std_weights{s}", atol_scale=1e-4)
+        assert not out[:, K:].any()
+
+
+def test_gn_maxpool_upsample_im2col_vs_oracle():
+    from oracle import resnet as ores
+    from snap_b200 import ops
+    import torch.nn.functional as Fnn
+    rng = np.random.default_rng(1)
+    dev = "cuda"
+    # GroupNorm stats + apply in all three layouts
+    for (n, h, w, c) in [(2, 12, 20, 64), (1, 6, 10, 2048), (3, 8, 8, 256)]:
+        x = bf16_np(rng.standard_normal((n, h, w, c)) * 2 + 0.5)
+        scale, bias = (1 + 0.3 * rng.standard_normal(c)).astype(F), (0.2 * rng.standard_normal(c)).astype(F)
+        ref = torch.relu(ores.group_norm(_t(x), _t(scale), _t(bias))).numpy()
+        xd = _t(x).to(torch.bfloat16).to(dev)
+        stats = torch.zeros((n, 32, 2), device=dev)
+        ws = torch.zeros(ops.gn_workspace_bytes(n, h * w) // 4 + 16, device=dev)
+        ops.gn_stats(xd, n, h * w, c, False, stats, ws)
+        dense = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=dev)
+        sub = torch.zeros((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=dev)
+        ops.gn_apply(xd, n, h, w, c, stats, _t(scale).to(dev), _t(bias).to(dev), False, True, ops.LAYOUT_DENSE, dense, sub)
+        padded = torch.zeros((n, h + 2, w + 2, c), dtype=torch.bfloat16, device=dev)
+        ops.gn_apply(xd, n, h, w, c, stats, _t(scale).to(dev), _t(bias).to(dev), False, True, ops.LAYOUT_PADDED, padded)
+        phase = torch.zeros((2, 2, n, h // 2 + 1, w // 2 + 1, c), dtype=torch.bfloat16, device=dev)
+        ops.gn_apply(xd, n, h, w, c, stats, _t(scale).to(dev), _t(bias).to(dev), False, True, ops.LAYOUT_PHASE, phase)
+        torch.cuda.synchronize()
+        assert_close_bf16(dense.float().cpu().numpy(), ref, f"gn dense {c}")
+        assert_close_bf16(sub.float().cpu().numpy(), ref[:, ::2, ::2], f"gn sub {c}")
+        refp = np.zeros((n, h + 2, w + 2, c), F)
+        refp[:, 1:-1, 1:-1] = ref
+        assert np.array_equal(padded.float().cpu().numpy()[:, 1:-1, 1:-1], dense.float().cpu().numpy())
+        assert not padded.float().cpu().numpy()[:, 0].any() and not padded.float().cpu().numpy()[:, :, -1].any()
+        ph = phase.float().cpu().numpy()
+        dn = np.zeros((n, h + 2, w + 2, c), F)
+        dn[:, 1:-1, 1:-1] = dense.float().cpu().numpy()
+        for a in range(2):
+            for b in range(2):
+                assert np.array_equal(ph[a, b], dn[:, a::2, b::2]), (a, b)
+    # FPN-style GN: relu first, no relu after
+    n, h, w, c = 1, 8, 8, 512
+    x = bf16_np(rng.standard_normal((n, h, w, c)))
+    scale, bias = (1 + 0.3 * rng.standard_normal(c)).astype(F), (0.2 * rng.standard_normal(c)).astype(F)
+    ref = ores.group_norm(torch.relu(_t(x)), _t(scale), _t(bias)).numpy()
+    xd = _t(x).to(torch.bfloat16).to(dev)
+    stats = torch.zeros((n, 32, 2), device=dev)
+    ws = torch.zeros(ops.gn_workspace_bytes(n, h * w) // 4 + 16, device=dev)
+    out = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=dev)
+    ops.gn_stats(xd, n, h * w, c, True, stats, ws)
+    ops.gn_apply(xd, n, h, w, c, stats, _t(scale).to(dev), _t(bias).to(dev), True, False, ops.LAYOUT_DENSE, out)
+    torch.cuda.synchronize()
+    assert_close_bf16(out.float().cpu().numpy(), ref, "gn fpn")
+    # max pool
+    x = bf16_np(rng.standard_normal((2, 16, 24, 64)))
+    ref = Fnn.max_pool2d(_t(x).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).numpy()
+    y = torch.zeros((2, 8, 12, 64), dtype=torch.bfloat16, device=dev)
+    ops.maxpool3x3s2(_t(x).to(torch.bfloat16).to(dev), 2, 16, 24, 64, y)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.float().cpu().numpy(), ref)
+    # x2 bilinear
+    x = bf16_np(rng.standard_normal((2, 5, 7, 128)))
+    ref = Fnn.interpolate(_t(x).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1).numpy()
+    y = torch.zeros((2, 10, 14, 128), dtype=torch.bfloat16, device=dev)
+    ops.upsample2x(_t(x).to(torch.bfloat16).to(dev), 2, 5, 7, 128, y)
+    torch.cuda.synchronize()
+    assert_close_bf16(y.float().cpu().numpy(), ref, "upsample2x")
+    # root im2col (+ pad semantics: padded region is -1 after 2x-1, conv padding is 0)
+    img = rng.random((2, 10, 14, 3), dtype=F)
+    Hp, Wp = 32, 32
+    a = torch.zeros((2 * 16 * 16, 160), dtype=torch.bfloat16, device=dev)
+    ops.root_im2col(_t(img).to(dev), Hp, Wp, 7, 7, 2, 3, a)
+    torch.cuda.synchronize()
+    xb = torch.full((2, Hp, Wp, 3), -1.0)
+    xb[:, :10, :14] = rd_bf16(rd_bf16(_t(img)) * 2 - 1)
+    cols = Fnn.unfold(xb.permute(0, 3, 1, 2), 7, padding=3, stride=2)  # [n, 3*49, L] channel-major
+    cols = cols.reshape(2, 3, 49, -1).permute(0, 3, 2, 1).reshape(2 * 256, 147).numpy()
+    out = a.float().cpu().numpy()
+    assert np.array_equal(out[:, :147], cols) and not out[:, 147:].any()
+
+
+@pytest.mark.parametrize("skip_root,hw", [(False, (40, 72)), (True, (24, 24))])
+def test_image_encoder_units_teacher_forced(skip_root, hw):
+    """Every residual unit, the root block and the FPN, each fed the ORACLE's (bf16-mode) input of that
+    block, vs the oracle's output of that block.  Both sides round at the same points, so the only
+    differences are fp32 summation order and the rare bf16 rounding flips they cause:
+    relative L2 <= 4e-3 per block (bf16 eps = 7.8e-3)."""
+    from oracle import image_encoder as oie
+    from snap_b200 import configs, image_encoder, params
+    rng = np.random.default_rng(2)
+    cfg = configs.aerial_encoder() if skip_root else configs.image_encoder()
+    p = params.round_to_bf16(params.perturb_affine(rng, params.init_image_encoder(rng, cfg)))
+    img = rng.random((2, *hw, 3), dtype=F)
+    tt = lambda tree: {k: (tt(v) if isinstance(v, dict) else _t(v)) for k, v in tree.items()}
+    trace = []
+    ref_bf, strides = oie.image_encoder(_t(img), tt(p), skip_root, rd_bf16, trace)
+    enc = image_encoder.ImageEncoder(cfg)
+    plan = enc.plan(p, 2, *hw, torch.device("cuda"))
+    plan.bank.run()
+    x0 = plan.run_root(_t(img).cuda())
+    torch.cuda.synchronize()
+    rows0 = trace[0][1].numel() // trace[0][1].shape[-1]
+    e = rel_l2(x0[:rows0].float().cpu().numpy(), trace[0][1].reshape(rows0, -1).numpy())
+    print(f"root: rel_l2 {e:.5f}")
+    assert e < 4e-3
+    worst = 0.0
+    for i, u in enumerate(plan.units):
+        xin, yout = trace[i + 1]
+        rows_in, rows_out = xin.numel() // xin.shape[-1], yout.numel() // yout.shape[-1]
+        xd = torch.zeros((max(128, -(-rows_in // 128) * 128), xin.shape[-1]), dtype=torch.bfloat16, device="cuda")
+        xd[:rows_in] = xin.reshape(rows_in, -1).to(torch.bfloat16).cuda()
+        out = plan.run_unit(u, xd)
+        torch.cuda.synchronize()
+        e = rel_l2(out[:rows_out].float().cpu().numpy(), yout.reshape(rows_out, -1).numpy())
+        worst = max(worst, e)
+        print(f"unit {i} (cin {u['cin']} stride {u['stride']} {u['h']}x{u['w']}): rel_l2 {e:.5f}")
+        assert e < 4e-3, f"unit {i}"
+    # FPN, teacher-forced with the oracle's stage outputs
+    ends = np.cumsum(plan.blocks)
+    for (buf, h, w, c), end in zip(plan.stage_out, ends):
+        y = trace[end][1]
+        buf[: y.numel() // c] = y.reshape(-1, c).to(torch.bfloat16).cuda()
+    outs = plan.run_fpn()
+    torch.cuda.synchronize()
+    for lvl, (o, (hh, ww), rb) in enumerate(zip(outs, plan.cropped_shapes(), ref_bf)):
+        e = rel_l2(o[:, :hh, :ww].float().cpu().numpy(), rb.numpy())
+        print(f"fpn level {lvl}: rel_l2 {e:.5f}")
+        assert e < 4e-3
+
+
+@pytest.mark.parametrize("skip_root,hw", [(False, (40, 72)), (True, (24, 24))])
+def test_image_encoder_end_to_end(skip_root, hw):
+    """Free-running ImageEncoder vs the oracle.  A 50-layer bf16 network with random weights amplifies
+    every flipped rounding through ~100 GroupNorms (the oracle's own bf16 mode is 10-20 % away from its
+    fp32 mode on these tiny maps), so the end-to-end bound is relative: the CUDA result must be no farther
+    from the fp32 oracle than 1.5x the distance of the reference's own bf16 mode, per pyramid level."""
+    from oracle import image_encoder as oie
+    from snap_b200 import configs, image_encoder, params
+    rng = np.random.default_rng(2)
+    cfg = configs.aerial_encoder() if skip_root else configs.image_encoder()
+    p = params.round_to_bf16(params.perturb_affine(rng, params.init_image_encoder(rng, cfg)))
+    img = rng.random((2, *hw, 3), dtype=F)
+    tt = lambda tree: {k: (tt(v) if isinstance(v, dict) else _t(v)) for k, v in tree.items()}
+    ref_bf, strides = oie.image_encoder(_t(img), tt(p), skip_root, rd_bf16)
+    ref_32, _ = oie.image_encoder(_t(img), tt(p), skip_root)
+    enc = image_encoder.ImageEncoder(cfg)
+    pyr = enc.apply({"params": p}, _t(img).cuda())
+    torch.cuda.synchronize()
+    assert len(pyr.features) == len(ref_bf)
+    for lvl, (o, rb, r32, s, s_ref) in enumerate(zip(pyr.features, ref_bf, ref_32, pyr.strides, strides)):
+        assert tuple(o.shape) == tuple(rb.shape), (lvl, o.shape, rb.shape)
+        assert tuple(s) == tuple(s_ref)
+        got = o.float().cpu().numpy()
+        e_bf, e_32, e_ref = rel_l2(got, rb.numpy()), rel_l2(got, r32.numpy()), rel_l2(rb.numpy(), r32.numpy())
+        print(f"level {lvl}: vs bf16-oracle {e_bf:.4f}, vs fp32-oracle {e_32:.4f}, bf16-oracle vs fp32-oracle {e_ref:.4f}")
+        assert e_32 < 1.5 * e_ref + 1e-3

@@ -46,7 +46,8 @@ def test_gemm_epilogue_bias_residual_relu_mask():
     out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
     ops.gemm(a.cuda(), b.cuda(), out, residual=res.cuda(), bias=bias.cuda(), row_mask=mask.cuda(), relu=True)
     torch.cuda.synchronize()
-    ref = torch.relu(a.float() @ b.float().T + bias + res.float()) * mask[:, None].float()
+    r = lambda t: t.to(torch.bfloat16).float()  # the epilogue rounds like the reference: dot, +bias, +residual
+    ref = torch.relu(r(r(a.float() @ b.float().T) + bias) + res.float()) * mask[:, None].float()
     _check(out, ref, bf16_out=True)
 
 

