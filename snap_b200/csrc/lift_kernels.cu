@@ -33,7 +33,6 @@ struct LiftParams {
   int X, Y, Z;
   float depth_min, depth_max, inv_log_range;  // 1 / log(max/min)
   int stats_ld;                               // row pitch of the stats matrix (>= 2*D + 1, mult of 32)
-  LiftView view[LIFT_MAX_VIEWS];
 };
 
 struct Proj {
@@ -113,11 +112,18 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 
 // One warp per voxel; one CTA (8 warps) per (x,y) column.  D must be 128 (16 lanes x 8 channels).
 __global__ void __launch_bounds__(256)
-lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const __nv_bfloat16* __restrict__ fimg,
+lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const LiftView* __restrict__ views,
+                        const __nv_bfloat16* __restrict__ fimg,
                         const float* __restrict__ xs, const float* __restrict__ ys,
                         const float* __restrict__ zs, __nv_bfloat16* __restrict__ stats,
                         uint8_t* __restrict__ valid, uint8_t* __restrict__ dbg_vis,
                         int* __restrict__ dbg_taps) {
+  // camera / pose table lives in device memory (not in the launch parameters) so that a captured
+  // CUDA graph can be replayed for a new scene after a plain H2D copy of the table
+  __shared__ LiftView sview[LIFT_MAX_VIEWS];
+  for (int i = threadIdx.x; i < P.V * (int)(sizeof(LiftView) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sview)[i] = reinterpret_cast<const uint32_t*>(views)[i];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col_id = blockIdx.x;  // x * Y + y
   const int ix = col_id / P.Y, iy = col_id - ix * P.Y;
@@ -141,7 +147,7 @@ lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const __nv_bfloat1
 #pragma unroll
     for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
       if (v >= P.V) break;
-      const Proj pr = project_point(P.view[v], px, py, pz);
+      const Proj pr = project_point(sview[v], px, py, pz);
       const Taps t = make_taps(pr.row, pr.col, P.Hf, P.Wf);
       if (dbg_vis != nullptr && lane == 0) {
         dbg_vis[n * P.V + v] = pr.vis ? 1 : 0;
@@ -333,10 +339,11 @@ using namespace snapb200;
 extern "C" {
 
 /* Host-side mirror of LiftParams/LiftView: the caller fills SnapLiftParams (include/snapb200.h). */
-int snapb200_lift_gather_pool(const SnapLiftParams* q, const void* fimg, const float* xs, const float* ys,
+int snapb200_lift_gather_pool(const SnapLiftParams* q, const SnapLiftView* views, const void* fimg,
+                              const float* xs, const float* ys,
                               const float* zs, void* stats, uint8_t* valid, uint8_t* dbg_vis,
                               int* dbg_taps, void* stream) {
-  SNAP_REQUIRE(q && fimg && xs && ys && zs && stats && valid, "null pointer");
+  SNAP_REQUIRE(q && views && fimg && xs && ys && zs && stats && valid, "null pointer");
   SNAP_REQUIRE(q->V >= 1 && q->V <= LIFT_MAX_VIEWS, "1 <= V <= %d required (got %d)", LIFT_MAX_VIEWS, q->V);
   SNAP_REQUIRE(q->D == 128, "feature_dim must be 128 (got %d)", q->D);
   SNAP_REQUIRE(q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
@@ -349,7 +356,8 @@ int snapb200_lift_gather_pool(const SnapLiftParams* q, const void* fimg, const f
   memcpy(&P, q, sizeof(P));
   const unsigned grid = (unsigned)(q->X * q->Y);
   lift_gather_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      P, (const __nv_bfloat16*)fimg, xs, ys, zs, (__nv_bfloat16*)stats, valid, dbg_vis, dbg_taps);
+      P, reinterpret_cast<const LiftView*>(views), (const __nv_bfloat16*)fimg, xs, ys, zs,
+      (__nv_bfloat16*)stats, valid, dbg_vis, dbg_taps);
   return check_launch("lift_gather_pool_kernel");
 }
 

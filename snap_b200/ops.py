@@ -150,12 +150,12 @@ def crop_relu(x: torch.Tensor, n: int, Hs: int, Ws: int, Cc: int, h: int, w: int
 # --------------------------------------------------------------------------------------------
 # lift
 # --------------------------------------------------------------------------------------------
-def lift_gather_pool(p: "_lib.LiftParams", fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+def lift_gather_pool(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
                      zs: torch.Tensor, stats: torch.Tensor, valid: torch.Tensor,
                      dbg_vis: Optional[torch.Tensor] = None, dbg_taps: Optional[torch.Tensor] = None) -> None:
     _require(fimg, torch.bfloat16, "fimg")
     _lib.check(_lib.lib().snapb200_lift_gather_pool(
-        C.byref(p), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
+        C.byref(p), C.c_void_p(_ptr(views)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
         C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(valid)),
         C.c_void_p(_ptr(dbg_vis)), C.c_void_p(_ptr(dbg_taps)), _stream()))
 

@@ -8,6 +8,7 @@ tcgen05 GEMMs (bias+ReLU / bias+valid-mask epilogues).
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Dict, Optional
 
@@ -19,15 +20,10 @@ from . import _lib, configs, image_encoder, ops, types
 F = np.float32
 
 
-def fill_lift_params(cfg, camera: types.Camera, T_view2scene: types.Transform3D, b: int, stride,
-                     hf: int, wf: int, X: int, Y: int, Z: int, stats_ld: int) -> "_lib.LiftParams":
-    """Host-side, fp32, in the oracle's operation order: scaled cameras (`streetview_encoder.py:224`) and
-    inverse view transforms (`snap/utils/geometry.py:52-56`)."""
-    V = camera.f.shape[1]
+def fill_lift_params(cfg, V: int, hf: int, wf: int, X: int, Y: int, Z: int, stats_ld: int) -> "_lib.LiftParams":
+    """Static (shape) part of the lift launch."""
     if V > _lib.MAX_VIEWS:
         raise NotImplementedError(f"V={V} > {_lib.MAX_VIEWS}: the top-k view-selection path is a 'next' row")
-    cam = camera.scale(np.asarray([1 / stride[1], 1 / stride[0]], dtype=F))
-    Tinv = types.Transform3D(R=T_view2scene.R[b], t=T_view2scene.t[b]).inv
     p = _lib.LiftParams()
     p.V, p.Hf, p.Wf = V, hf, wf
     p.D, p.S = cfg.feature_dim, cfg.num_scale_bins
@@ -37,8 +33,22 @@ def fill_lift_params(cfg, camera: types.Camera, T_view2scene: types.Transform3D,
     p.depth_min, p.depth_max = dmin, dmax
     p.inv_log_range = float(F(1.0) / np.log(F(dmax / dmin)).astype(F))
     p.stats_ld = stats_ld
+    return p
+
+
+VIEW_WORDS = C.sizeof(_lib.LiftView) // 4
+
+
+def pack_views(camera: types.Camera, T_view2scene: types.Transform3D, b: int, stride) -> np.ndarray:
+    """Per-scene camera/pose table (`SnapLiftView[V]` as raw 32-bit words), computed on the host in fp32
+    in the oracle's operation order: cameras scaled by 1/stride (`streetview_encoder.py:224`) and inverse
+    view transforms (`snap/utils/geometry.py:52-56`)."""
+    V = camera.f.shape[1]
+    cam = camera.scale(np.asarray([1 / stride[1], 1 / stride[0]], dtype=F))
+    Tinv = types.Transform3D(R=T_view2scene.R[b], t=T_view2scene.t[b]).inv
+    views = (_lib.LiftView * V)()
     for v in range(V):
-        lv = p.view[v]
+        lv = views[v]
         for i, x in enumerate(Tinv.R[v].reshape(-1)):
             lv.Rinv[i] = float(x)
         for i in range(3):
@@ -50,7 +60,7 @@ def fill_lift_params(cfg, camera: types.Camera, T_view2scene: types.Transform3D,
             for i in range(3):
                 lv.k_radial[i] = float(camera.k_radial[b, v, i])
             lv.tan_half_fov = float(np.tan(F(0.5) * camera.max_fov[b, v]).astype(F))
-    return p
+    return np.frombuffer(bytes(views), dtype=np.int32).copy()
 
 
 class StreetViewEncoder:
@@ -85,16 +95,41 @@ class StreetViewEncoder:
             self._cache[key] = w
         return self._cache[key]
 
-    def _buffers(self, device, B, V, hf, wf, X, Y, Z):
-        key = ("buf", str(device), B, V, hf, wf, X, Y, Z)
+    def _buffers(self, device, B, V, H, W, hf, wf, X, Y, Z):
+        key = ("buf", str(device), B, V, H, W, hf, wf, X, Y, Z)
         if key not in self._cache:
             N = X * Y * Z
             z = lambda *s, dt=torch.bfloat16: torch.zeros(s, dtype=dt, device=device)
+            pin = lambda *s, dt: torch.zeros(s, dtype=dt).pin_memory()
             rows_img = max(V * hf * wf, 128)
             self._cache[key] = dict(
                 crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
-                volume=z(B, N, 128), valid=z(B, N, dt=torch.uint8))
+                volume=z(B, N, 128), valid=z(B, N, dt=torch.uint8),
+                # per-scene inputs: pinned host staging + device copies (a captured CUDA graph re-reads the
+                # staging buffers at every replay, see `stage_inputs`)
+                images_host=pin(B, V, H, W, 3, dt=torch.float32), images=z(B, V, H, W, 3, dt=torch.float32),
+                zs_host=pin(B, Z, dt=torch.float32), zs=z(B, Z, dt=torch.float32),
+                views_host=pin(B, _lib.MAX_VIEWS * VIEW_WORDS, dt=torch.int32),
+                views=z(B, _lib.MAX_VIEWS * VIEW_WORDS, dt=torch.int32),
+                xs=None, ys=None)
         return self._cache[key]
+
+    def stage_inputs(self, data: Dict, buf: Dict, stride) -> bool:
+        """Host-only: write this batch's images (if they live on the host), voxel heights and camera/pose
+        tables into the pinned staging buffers.  Returns True if the images were staged from the host."""
+        xs, ys, zs = data["xyz_grid"]
+        B = zs.shape[0]
+        buf["zs_host"].copy_(torch.from_numpy(np.ascontiguousarray(zs, dtype=F)))
+        for b in range(B):
+            pack = pack_views(data["camera"], data["T_view2scene"], b, stride)
+            buf["views_host"][b, : len(pack)].copy_(torch.from_numpy(pack))
+        images = data["images"]
+        if isinstance(images, np.ndarray):
+            images = torch.from_numpy(np.ascontiguousarray(images, dtype=F))
+        if not images.is_cuda:
+            buf["images_host"].copy_(images)
+            return True
+        return False
 
     def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False) -> Dict:
         if train:
@@ -102,42 +137,47 @@ class StreetViewEncoder:
         params = variables["params"] if "params" in variables else variables
         cfg = self.config
         images = data["images"]
-        if not isinstance(images, torch.Tensor):
-            images = torch.from_numpy(np.ascontiguousarray(images, dtype=F)).cuda()
         B, V, H, W, _ = images.shape
-        dev = images.device
-        pyr = data.get("image_feature_pyr")
-        if pyr is None:
-            pyr = self.image_encoder.apply({"params": params["image_encoder"]},
-                                           images.reshape(B * V, H, W, 3), train)
-        f_images = pyr.features[-1]            # [B*V, hf, wf, 128] view of the (uncropped) FPN buffer
-        stride = pyr.strides[-1]
-        hf, wf = f_images.shape[1:3]
+        dev = images.device if isinstance(images, torch.Tensor) and images.is_cuda else torch.device("cuda")
         xs, ys, zs = data["xyz_grid"]          # xs [X], ys [Y] (NumPy fp32), zs [B, Z]
         X, Y, Z = len(xs), len(ys), zs.shape[1]
+        enc_plan = self.image_encoder.plan(params["image_encoder"], B * V, H, W, dev)
+        hf, wf = enc_plan.cropped_shapes()[-1]
+        stride = enc_plan.strides[-1]
+        buf = self._buffers(dev, B, V, H, W, hf, wf, X, Y, Z)
+        if buf["xs"] is None:
+            buf["xs"], buf["ys"] = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+        from_host = self.stage_inputs(data, buf, stride)
+        if from_host:
+            buf["images"].copy_(buf["images_host"], non_blocking=True)
+            images = buf["images"]
+        buf["zs"].copy_(buf["zs_host"], non_blocking=True)
+        buf["views"].copy_(buf["views_host"], non_blocking=True)
+
+        pyr = data.get("image_feature_pyr")
+        if pyr is None:
+            pyr = self.image_encoder.apply({"params": params["image_encoder"]}, images.reshape(B * V, H, W, 3), train)
+        full = pyr.uncropped[-1]               # [B*V, Hs, Ws, 128] un-cropped finest FPN level
+        Hs, Ws = full.shape[1], full.shape[2]
         wts = self._weights(params, dev)
-        buf = self._buffers(dev, B, V, hf, wf, X, Y, Z)
         bank = wts["bank"]
         bank.run()
         Bm = bank.b_mats
         N = X * Y * Z
-        xs_d, ys_d = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
-        zs_d = torch.from_numpy(np.ascontiguousarray(zs, dtype=F)).to(dev)
-        full = pyr.uncropped[-1] if getattr(pyr, "uncropped", None) is not None else f_images.contiguous()
-        Hs, Ws = full.shape[1], full.shape[2]
+        lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, 288)
         dbg = {}
         for b in range(B):
             # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`)
             ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, True, buf["crop"])
             ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"][b], m_rows=V * hf * wf, bias=wts["proj_b"])
-            lp = fill_lift_params(cfg, data["camera"], data["T_view2scene"], b, stride, hf, wf, X, Y, Z, 288)
             dv = dt = None
             if debug:
                 dv = torch.zeros((N, V), dtype=torch.uint8, device=dev)
                 dt = torch.zeros((N, V, 2), dtype=torch.int32, device=dev)
                 dbg.setdefault("vis", []).append(dv)
                 dbg.setdefault("taps", []).append(dt)
-            ops.lift_gather_pool(lp, buf["fimg"][b], xs_d, ys_d, zs_d[b], buf["stats"], buf["valid"][b], dv, dt)
+            ops.lift_gather_pool(lp, buf["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], buf["zs"][b],
+                                 buf["stats"], buf["valid"][b], dv, dt)
             # fusion MLP 257 -> 256 -> 128 (`:281`), zero where invalid (`:282`)
             ops.gemm(buf["stats"], Bm[wts["fus0"]], buf["hid"], m_rows=N, seg_k=288, bias=wts["fus0_b"], relu=True)
             ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],

@@ -118,10 +118,11 @@ for fisheye, V in [(False, 3), (False, 1)]:
     scfg = configs.streetview_encoder()
     Z = zs.shape[1]; N = G * G * Z
     fimg_np = bf16_np(rng.standard_normal((V, hf, wf, 160)))
-    lp = sve.fill_lift_params(scfg, data["camera"], data["T_view2scene"], 0, (4.0, 4.0), hf, wf, G, G, Z, 288)
+    lp = sve.fill_lift_params(scfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to("cuda")
     stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
     valid = torch.zeros(N, dtype=torch.uint8, device=dev)
-    ops.lift_gather_pool(lp, _t(fimg_np).to(torch.bfloat16).to(dev), _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid)
+    ops.lift_gather_pool(lp, views, _t(fimg_np).to(torch.bfloat16).to(dev), _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid)
     torch.cuda.synchronize()
     ocam, oT = to_oracle_geometry(data, 0)
     ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))

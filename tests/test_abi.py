@@ -1,0 +1,56 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/snapb200.h declares;
+argument validation fails loudly before any CUDA call.  (No compute without a GPU.)"""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "snapb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(snapb200_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from snap_b200 import _lib
+    lib = _lib.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/snapb200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "python binding list and header disagree"
+
+
+def test_struct_layouts_match_header():
+    from snap_b200 import _lib
+    # sizes asserted in csrc/lift_kernels.cu (static_assert) and mirrored here
+    assert C.sizeof(_lib.LiftView) == 92
+    assert C.sizeof(_lib.LiftParams) == 52
+    assert C.sizeof(_lib.WeightDesc) == 48
+    assert C.sizeof(_lib.GemmParams) % 8 == 0
+
+
+def test_invalid_arguments_fail_loudly_without_gpu():
+    from snap_b200 import _lib
+    lib = _lib.lib()
+    assert lib.snapb200_version() == 100
+    p = _lib.GemmParams()
+    rc = lib.snapb200_gemm_bf16(C.byref(p), None)
+    assert rc == -1 and b"null operand" in lib.snapb200_last_error()
+    with pytest.raises(_lib.SnapB200Error):
+        _lib.check(rc)
+    assert lib.snapb200_xcorr_padded_cols(128) == 384 and lib.snapb200_xcorr_padded_cols(64) == 192
+    rc = lib.snapb200_xcorr_count(None, None, 1, 36, 128, None, None, None)
+    assert rc == -1
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from snap_b200 import _lib, ops
+    a = torch.zeros((128, 64), dtype=torch.bfloat16)
+    with pytest.raises(_lib.SnapB200Error):
+        ops.gemm(a, a, torch.zeros((128, 128)))

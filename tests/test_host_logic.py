@@ -1,0 +1,112 @@
+"""Host-side logic of the product package (no GPU): geometry/grid preparation must be BIT-identical to the
+oracle (it feeds the bit-exact visibility kernels), configs mirror defaults.py, parameter trees carry the
+Flax names of SURVEY.md Appendix B."""
+import numpy as np
+import torch
+
+from oracle import bev_mapper as obm, geometry as ogeo, grids as ogrids, pose_exhaustive_voting as opv
+from snap_b200 import _lib, bev_mapper, configs, params, pose_exhaustive_voting as pv, streetview_encoder as sve
+from snap_b200 import synthetic, types
+
+F = np.float32
+
+
+def test_xyz_grid_bit_identical_to_oracle():
+    for G, V in [(64, 1), (128, 4), (32, 3)]:
+        data = synthetic.make_tile(3, V, (96, 128), G, batch=2)
+        mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), types.Grid2D((G, G), 0.2))
+        xs, ys, zs = mapper.build_xyz_grid(data)
+        for b in range(2):
+            xyz, zoff = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), data["T_view2scene"].t[b])
+            assert np.array_equal(xyz[:, 0, 0, 0], xs) and np.array_equal(xyz[0, :, 0, 1], ys)
+            assert np.array_equal(xyz[0, 0, :, 2], zs[b]) and zs.shape[1] == 60
+
+
+def test_view_table_bit_identical_to_oracle_inverse_and_scale():
+    data = synthetic.make_tile(5, 4, (480, 640), 128, fisheye=True)
+    words = sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))
+    raw = words.tobytes()
+    T = ogeo.Transform3D(R=data["T_view2scene"].R[0], t=data["T_view2scene"].t[0]).inv
+    cam = ogeo.Camera(wh=data["camera"].wh[0], f=data["camera"].f[0], c=data["camera"].c[0]).scale(np.asarray([0.25, 0.25], F))
+    for v in range(4):
+        lv = _lib.LiftView.from_buffer_copy(raw[v * 92:(v + 1) * 92])
+        assert np.array_equal(np.array(lv.Rinv[:], F).reshape(3, 3), T.R[v])
+        assert np.array_equal(np.array(lv.tinv[:], F), T.t[v])
+        assert np.array_equal(np.array(lv.f[:], F), cam.f[v]) and np.array_equal(np.array(lv.wh[:], F), cam.wh[v])
+        assert lv.fisheye == 1 and np.isclose(lv.tan_half_fov, np.tan(np.deg2rad(57.5)), rtol=1e-6)
+
+
+def test_template_rotation_params_bit_identical_to_oracle():
+    for G, R in [(128, 36), (64, 8)]:
+        rot = pv.template_rotation_params(R, types.Grid2D((G, G), 0.2))
+        t = opv.template_transforms(R, ogrids.Grid2D((G, G), 0.2))
+        nq = R // 4
+        ref = np.stack([np.cos(t.angle[:nq]), np.sin(t.angle[:nq]), t.t[:nq, 0], t.t[:nq, 1]], -1).astype(F)
+        assert np.array_equal(rot, ref)
+
+
+def test_rot90_index_map_of_the_kernel():
+    """csrc/xcorr.cu rot90_src: template quadrant k at (a,b) reads the quarter at (i,j)."""
+    G = 7
+    base = np.arange(G * G).reshape(G, G)
+
+    def src(k, a, b):
+        return [(a, b), (G - 1 - b, a), (G - 1 - a, G - 1 - b), (b, G - 1 - a)][k]
+    for k in range(4):
+        ref = np.rot90(base[None], k, axes=(2, 1))[0]
+        got = np.array([[base[src(k, a, b)] for b in range(G)] for a in range(G)])
+        assert np.array_equal(got, ref), k
+
+
+def test_pose_index_roundtrip_product_side():
+    g = types.Grid2D((128, 128), 0.2)
+    idx = pv.exhaustive_tfm_to_index(*pv.exhaustive_index_to_tfm(np.array([7, 200, 31]), g, 36), g, 36)
+    assert np.allclose(idx, [7, 200, 31], atol=2e-3)
+
+
+def test_configs_mirror_reference_defaults():
+    c = configs.bev_mapper()
+    sv = c.streetview_encoder
+    assert (sv.feature_dim, sv.num_scale_bins, sv.top_k_view_selection, tuple(sv.depth_min_max)) == (128, 32, 4, (1.0, 32.0))
+    assert tuple(sv.fusion.layers) == (256, 128) and sv.proj_mlp.apply_input_activation and sv.do_weighted_fusion
+    assert (c.scene_z_offset, c.scene_z_height, c.matching_dim, c.pooling.pooling) == (4.0, 12.0, 32, "max")
+    assert c.aerial_encoder.encoder.skip_root_block and not sv.image_encoder.encoder.skip_root_block
+    assert configs.get_block_desc(50) == [3, 4, 6, 3]
+
+
+def test_param_tree_names_and_shapes():
+    p = params.init_bev_mapper(np.random.default_rng(0), configs.bev_mapper())
+    enc = p["streetview_encoder"]["image_encoder"]["encoder"]
+    assert enc["root_block"]["conv_root"]["kernel"].shape == (7, 7, 3, 64)
+    assert enc["block1"]["unit01"]["conv_proj"]["kernel"].shape == (1, 1, 64, 256)
+    assert enc["block4"]["unit03"]["conv2"]["kernel"].shape == (3, 3, 512, 512)
+    assert "conv_proj" not in enc["block2"]["unit02"] and enc["block3"]["unit06"]["gn1"]["scale"].shape == (1, 1, 1, 1024)
+    dec = p["streetview_encoder"]["image_encoder"]["decoder"]
+    assert dec["0_skip_conv"]["kernel"].shape == (1, 1, 2048, 128) and dec["3_skip_norm"]["bias"].shape == (1, 1, 1, 256)
+    assert p["streetview_encoder"]["proj_mlp"]["Dense_0"]["kernel"].shape == (128, 160)
+    assert p["streetview_encoder"]["fusion_mlp"]["Dense_0"]["kernel"].shape == (257, 256)
+    assert p["aerial_encoder"]["encoder"]["conv_root"]["kernel"].shape == (3, 3, 3, 64)
+    assert p["matching_proj"]["kernel"].shape == (128, 32)
+    n = sum(x.size for x in _leaves(p))
+    assert 47.5e6 < n < 48.5e6
+
+
+def _leaves(t):
+    for v in t.values():
+        if isinstance(v, dict):
+            yield from _leaves(v)
+        else:
+            yield v
+
+
+def test_unsupported_configs_fail_loudly():
+    import pytest
+    c = configs.bev_mapper()
+    c.streetview_encoder.fusion_add_minmax = True
+    with pytest.raises(NotImplementedError):
+        bev_mapper.BEVMapper(c, types.Grid2D((8, 8), 0.2))
+    c2 = configs.image_encoder()
+    c2.encoder_name = "vit"
+    with pytest.raises(ValueError):
+        from snap_b200 import image_encoder
+        image_encoder.ImageEncoder(c2)

@@ -32,14 +32,15 @@ def test_lift_visibility_and_taps_bit_exact(G, hw_img):
     cfg = configs.streetview_encoder()
     Z = zs.shape[1]
     N = G * G * Z
-    lp = sve.fill_lift_params(cfg, data["camera"], data["T_view2scene"], 0, (4.0, 4.0), hf, wf, G, G, Z, 288)
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to("cuda")
     dev = "cuda"
     fimg = torch.zeros((V, hf, wf, 160), dtype=torch.bfloat16, device=dev)
     stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
     valid = torch.zeros(N, dtype=torch.uint8, device=dev)
     vis = torch.zeros((N, V), dtype=torch.uint8, device=dev)
     taps = torch.zeros((N, V, 2), dtype=torch.int32, device=dev)
-    ops.lift_gather_pool(lp, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid, vis, taps)
+    ops.lift_gather_pool(lp, views, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid, vis, taps)
     torch.cuda.synchronize()
     ocam, oT = to_oracle_geometry(data, 0)
     ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
@@ -70,11 +71,12 @@ def test_lift_stats_and_volume_vs_oracle(fisheye):
     fimg_np = bf16_np(rng.standard_normal((V, hf, wf, 160)))
     fp = params.round_to_bf16(params.perturb_affine(rng, params.init_mlp(rng, 257, (256, 128))))
     dev = "cuda"
-    lp = sve.fill_lift_params(cfg, data["camera"], data["T_view2scene"], 0, (4.0, 4.0), hf, wf, G, G, Z, 288)
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to("cuda")
     fimg = _t(fimg_np).to(torch.bfloat16).to(dev)
     stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
     valid = torch.zeros(N, dtype=torch.uint8, device=dev)
-    ops.lift_gather_pool(lp, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid)
+    ops.lift_gather_pool(lp, views, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid)
     bank = _WeightBank(torch.device(dev))
     w0 = bank.add(fp["Dense_0"]["kernel"], False, 32)
     w1 = bank.add(fp["Dense_1"]["kernel"], False)
