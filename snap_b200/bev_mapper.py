@@ -37,7 +37,11 @@ class BEVMapper:
 
     default_config = staticmethod(configs.bev_mapper)
 
-    def __init__(self, config=None, grid: types.Grid2D = None, semantic_map_classes=None, dtype=torch.bfloat16):
+    def __init__(self, config=None, grid: types.Grid2D = None, semantic_map_classes=None, dtype=torch.bfloat16,
+                 fused_lift: bool = True):
+        # fused_lift: run lift + fusion MLP + vertical pooling as one kernel (no 'feature_volume' in the
+        # result); debug=True or fused_lift=False use the unfused path that materialises the volume.
+        self.fused_lift = fused_lift
         self.config = config if config is not None else configs.bev_mapper()
         self.grid = grid
         self.dtype = dtype
@@ -79,9 +83,13 @@ class BEVMapper:
         if "xyz_grid" not in data:
             data = dict(data)
             data["xyz_grid"] = self.build_xyz_grid(data)
-        pred = self.streetview_encoder.apply({"params": params["streetview_encoder"]}, data, train, debug=debug)
-        pred["vertical_pooling"] = self.vertical_pooling.apply(None, pred["feature_volume"])
-        pred["feature_plane"] = pred["vertical_pooling"].pop("plane")
+        fused = self.fused_lift and not debug and self.config.pooling.pooling == "max" \
+            and data["T_view2scene"].t.shape[1] <= 4
+        pred = self.streetview_encoder.apply({"params": params["streetview_encoder"]}, data, train, debug=debug,
+                                             fused=fused)
+        if not fused:
+            pred["vertical_pooling"] = self.vertical_pooling.apply(None, pred["feature_volume"])
+            pred["feature_plane"] = pred["vertical_pooling"].pop("plane")
         return pred
 
     def encode_aerial(self, params, aerial_rgb, train=False) -> Dict:  # bev_mapper.py:203-212

@@ -175,12 +175,16 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int Nim
 }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm statistics (32 groups).  partial[img][chunk][g] = (sum, sumsq) over the chunk's pixels
+// GroupNorm (32 groups).  Statistics are RAW accumulators acc[img][g] = (sum, sumsq) in double,
+// normally produced by the epilogue of the conv that wrote the tensor (gemm_tc.cuh); this standalone
+// kernel covers tensors that no GEMM produced (max-pool output, tests).  Double atomics make the
+// result independent of the accumulation order to ~1e-16, i.e. bitwise stable once rounded to fp32.
 // ------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
 
-__global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pre_relu,
-                                  int pix_per_chunk, float2* __restrict__ partial) {
+__global__ void __launch_bounds__(GN_THREADS)
+gn_accumulate_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pre_relu,
+                     int pix_per_block, double* __restrict__ acc) {
   const int CV = C / 8;            // 16B vectors per pixel (<= 256)
   const int PL = GN_THREADS / CV;  // pixel lanes
   const int cpg = C / 32;
@@ -189,11 +193,12 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int HW, i
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
   const int img = blockIdx.y;
-  const int p0 = blockIdx.x * pix_per_chunk;
-  const int p1 = min(HW, p0 + pix_per_chunk);
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (pl < PL) {
     const __nv_bfloat16* base = x + ((size_t)img * HW) * C + cv * 8;
+#pragma unroll 4
     for (int p = p0 + pl; p < p1; p += PL) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
       const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
@@ -217,105 +222,105 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int HW, i
 #pragma unroll
   for (int k = 0; k < 4; ++k) sm[threadIdx.x][k] = make_float2(s[k], q[k]);
   __syncthreads();
-  // stage 1: reduce over pixel lanes -> one value per (cv, sub)
-  __shared__ float2 sm2[256 * 4 / 1];
+  __shared__ float2 sm2[256 * 4];
   const int entries = CV * nsub;
   for (int e = threadIdx.x; e < entries; e += GN_THREADS) {
     const int ecv = e / nsub, esub = e % nsub;
-    float2 acc = make_float2(0.f, 0.f);
+    float2 a = make_float2(0.f, 0.f);
     for (int l = 0; l < PL; ++l) {
       const float2 t = sm[l * CV + ecv][esub];
-      acc.x += t.x;
-      acc.y += t.y;
+      a.x += t.x;
+      a.y += t.y;
     }
-    sm2[e] = acc;
+    sm2[e] = a;
   }
   __syncthreads();
-  // stage 2: entries are ordered by channel; group g owns entries [g*epg, (g+1)*epg)
   if (threadIdx.x < 32) {
     const int epg = entries / 32;
-    float2 acc = make_float2(0.f, 0.f);
+    float2 a = make_float2(0.f, 0.f);
     for (int e = threadIdx.x * epg; e < (threadIdx.x + 1) * epg; ++e) {
-      acc.x += sm2[e].x;
-      acc.y += sm2[e].y;
+      a.x += sm2[e].x;
+      a.y += sm2[e].y;
     }
-    partial[((size_t)img * gridDim.x + blockIdx.x) * 32 + threadIdx.x] = acc;
+    atomicAdd(&acc[((size_t)img * 32 + threadIdx.x) * 2 + 0], (double)a.x);
+    atomicAdd(&acc[((size_t)img * 32 + threadIdx.x) * 2 + 1], (double)a.y);
   }
-}
-
-__global__ void gn_finalize_kernel(const float2* __restrict__ partial, int Nimg, int chunks,
-                                   double count, float eps, float2* __restrict__ stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Nimg * 32) return;
-  const int img = i / 32, g = i % 32;
-  double s = 0.0, q = 0.0;
-  for (int c = 0; c < chunks; ++c) {
-    const float2 t = partial[((size_t)img * chunks + c) * 32 + g];
-    s += (double)t.x;
-    q += (double)t.y;
-  }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
 // layouts written by gn_apply
 enum { LAYOUT_DENSE = 0, LAYOUT_PADDED = 1, LAYOUT_PHASE = 2 };
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int C,
-                                const float2* __restrict__ stats, const float* __restrict__ scale,
-                                const float* __restrict__ bias, int pre_relu, int post_relu,
-                                int layout, __nv_bfloat16* __restrict__ out,
-                                __nv_bfloat16* __restrict__ out_sub) {
-  const int cv = C / 8;
-  const long long total = (long long)Nimg * H * W * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % cv);
-  const long long pix = idx / cv;
-  const int w = (int)(pix % W);
-  const int h = (int)((pix / W) % H);
-  const int n = (int)(pix / ((long long)W * H));
-  const int c0 = c8 * 8;
+// One thread owns a fixed 8-channel vector (its scale/bias/mean/rstd live in registers) and walks
+// over pixels; consecutive threads -> consecutive 16 B chunks (coalesced).
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int C,
+                const double* __restrict__ acc, const float* __restrict__ scale,
+                const float* __restrict__ bias, int pre_relu, int post_relu, int layout,
+                int pix_per_block, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_sub) {
+  const int CV = C / 8;
+  const int PL = 256 / CV;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  if (pl >= PL) return;
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int c0 = cv * 8;
   const int cpg = C / 32;
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * C + c0));
-  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 t = unpack_bf16(uu[j]);
-    f[2 * j] = t.x;
-    f[2 * j + 1] = t.y;
-  }
+  const double count = (double)HW * (double)cpg;
+  float mean[8], rstd[8], sc[8], bi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    const float2 st = __ldg(&stats[n * 32 + c / cpg]);
-    float v = pre_relu ? fmaxf(f[j], 0.f) : f[j];
-    // resnet.py:39-41,57-69 with a bf16 dtype: standardise in fp32 -> bf16, * scale -> bf16, + bias -> bf16
-    v = bf16_round((v - st.x) * st.y);
-    v = bf16_round(v * __ldg(scale + c));
-    v = bf16_round(v + __ldg(bias + c));
-    f[j] = post_relu ? fmaxf(v, 0.f) : v;
+    const int g = (c0 + j) / cpg;
+    const double su = acc[((size_t)n * 32 + g) * 2], sq = acc[((size_t)n * 32 + g) * 2 + 1];
+    const double mu = su / count;
+    double var = sq / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[j] = (float)mu;
+    rstd[j] = (float)(1.0 / sqrt(var + 1e-5));
+    sc[j] = __ldg(scale + c0 + j);
+    bi[j] = __ldg(bias + c0 + j);
   }
-  const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                             pack_bf16(f[6], f[7]));
-  size_t orow;
-  if (layout == LAYOUT_DENSE) {
-    orow = (size_t)pix;
-  } else if (layout == LAYOUT_PADDED) {
-    orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
-  } else {
-    const int Hq = H / 2 + 1, Wq = W / 2 + 1;
-    const int hp = h + 1, wp = w + 1;
-    const size_t plane = (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)Nimg * Hq * Wq);
-    orow = plane + ((size_t)n * Hq + (hp >> 1)) * Wq + (wp >> 1);
-  }
-  *reinterpret_cast<uint4*>(out + orow * C + c0) = o;
-  if (out_sub != nullptr && (h & 1) == 0 && (w & 1) == 0) {
-    const size_t srow = ((size_t)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
-    *reinterpret_cast<uint4*>(out_sub + srow * C + c0) = o;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const __nv_bfloat16* xin = x + (size_t)n * HW * C + c0;
+  const int Hq = H / 2 + 1, Wq = W / 2 + 1;
+#pragma unroll 2
+  for (int p = p0 + pl; p < p1; p += PL) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)p * C));
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_bf16(uu[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = pre_relu ? fmaxf(f[j], 0.f) : f[j];
+      // resnet.py:39-41,57-69 with a bf16 dtype: standardise in fp32 -> bf16, * scale -> bf16, + bias -> bf16
+      v = bf16_round((v - mean[j]) * rstd[j]);
+      v = bf16_round(v * sc[j]);
+      v = bf16_round(v + bi[j]);
+      f[j] = post_relu ? fmaxf(v, 0.f) : v;
+    }
+    const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                               pack_bf16(f[6], f[7]));
+    const int h = p / W, w = p - h * W;
+    size_t orow;
+    if (layout == LAYOUT_DENSE) {
+      orow = (size_t)n * HW + p;
+    } else if (layout == LAYOUT_PADDED) {
+      orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+    } else {
+      const int hp = h + 1, wp = w + 1;
+      const size_t plane = (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)Nimg * Hq * Wq);
+      orow = plane + ((size_t)n * Hq + (hp >> 1)) * Wq + (wp >> 1);
+    }
+    *reinterpret_cast<uint4*>(out + orow * C + c0) = o;
+    if (out_sub != nullptr && (h & 1) == 0 && (w & 1) == 0) {
+      const size_t srow = ((size_t)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+      *reinterpret_cast<uint4*>(out_sub + srow * C + c0) = o;
+    }
   }
 }
 
@@ -438,45 +443,39 @@ int snapb200_maxpool3x3s2(const void* x, int Nimg, int H, int W, int C, void* y,
   return check_launch("maxpool3x3s2_kernel");
 }
 
-size_t snapb200_gn_workspace_bytes(int Nimg, int HW) {
-  const int chunks = (HW + 1023) / 1024 > 0 ? (HW + 1023) / 1024 : 1;
-  return (size_t)Nimg * chunks * 32 * sizeof(float2);
-}
-
-/* GroupNorm(32 groups, eps 1e-5) statistics of x [Nimg, HW, C] (optionally of relu(x)):
-   stats[img][g] = (mean, 1/sqrt(var+eps)).  workspace: snapb200_gn_workspace_bytes. */
-int snapb200_gn_stats(const void* x, int Nimg, int HW, int C, int pre_relu, void* stats,
-                      void* workspace, void* stream) {
-  SNAP_REQUIRE(x && stats && workspace, "null pointer");
+/* Accumulate GroupNorm(32 groups) raw statistics of x [Nimg, HW, C] (optionally of relu(x)) into
+   acc[img][g] = (sum, sumsq) doubles.  acc must be zeroed by the caller; conv outputs get the same
+   accumulators from the GEMM epilogue (SnapGemmParams.gn_acc) without this extra pass. */
+int snapb200_gn_stats(const void* x, int Nimg, int HW, int C, int pre_relu, double* acc, void* stream) {
+  SNAP_REQUIRE(x && acc, "null pointer");
   SNAP_REQUIRE(C % 64 == 0 && C <= 2048, "GroupNorm kernel needs C %% 64 == 0 and C <= 2048 (got %d)", C);
-  const int ppc = 1024;
-  const int chunks = (HW + ppc - 1) / ppc;
-  dim3 grid(chunks, Nimg);
-  gn_partial_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, HW, C, pre_relu, ppc, (float2*)workspace);
-  int rc = check_launch("gn_partial_kernel");
-  if (rc) return rc;
-  const double count = (double)HW * (double)(C / 32);
-  gn_finalize_kernel<<<(Nimg * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      (const float2*)workspace, Nimg, chunks, count, 1e-5f, (float2*)stats);
-  return check_launch("gn_finalize_kernel");
+  int ppb = 64 * (GN_THREADS / (C / 8));  // 64 pixels per thread lane
+  if (ppb > HW) ppb = HW > 0 ? HW : 1;
+  dim3 grid((HW + ppb - 1) / ppb, Nimg);
+  gn_accumulate_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, HW, C,
+                                                                     pre_relu, ppb, acc);
+  return check_launch("gn_accumulate_kernel");
 }
 
-/* y = post_relu?( (pre_relu?(x) - mean) * rstd * scale + bias ), written in `layout`
+/* y = post_relu?( (pre_relu?(x) - mean) * rstd * scale + bias ) with mean/rstd derived from the raw
+   accumulators acc[img][g] = (sum, sumsq) (eps 1e-5, resnet.py:34-70), written in `layout`
    (0 dense [Nimg*H*W, C]; 1 zero-bordered [Nimg,(H+2),(W+2),C]; 2 phase-split);
    out_sub (optional) additionally receives the even-pixel subsample, dense [Nimg,H/2,W/2,C]. */
-int snapb200_gn_apply(const void* x, int Nimg, int H, int W, int C, const void* stats,
+int snapb200_gn_apply(const void* x, int Nimg, int H, int W, int C, const double* acc,
                       const float* scale, const float* bias, int pre_relu, int post_relu, int layout,
                       void* out, void* out_sub, void* stream) {
-  SNAP_REQUIRE(x && stats && scale && bias && out, "null pointer");
-  SNAP_REQUIRE(C % 32 == 0, "C must be a multiple of 32");
+  SNAP_REQUIRE(x && acc && scale && bias && out, "null pointer");
+  SNAP_REQUIRE(C % 64 == 0 && C <= 2048, "C must be a multiple of 64, <= 2048");
   SNAP_REQUIRE(layout >= 0 && layout <= 2, "bad layout");
   SNAP_REQUIRE((layout != LAYOUT_PHASE && out_sub == nullptr) || (H % 2 == 0 && W % 2 == 0),
                "phase / subsampled layouts need even H, W");
-  const long long total = (long long)Nimg * H * W * (C / 8);
-  gn_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, Nimg, H, W, C, (const float2*)stats, scale, bias, pre_relu, post_relu,
-      layout, (__nv_bfloat16*)out, (__nv_bfloat16*)out_sub);
+  const int HW = H * W;
+  int ppb = 16 * (256 / (C / 8));  // 16 pixels per thread lane
+  if (ppb > HW) ppb = HW;
+  dim3 grid((HW + ppb - 1) / ppb, Nimg);
+  gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, Nimg, H, W, C, acc, scale, bias, pre_relu, post_relu, layout, ppb,
+      (__nv_bfloat16*)out, (__nv_bfloat16*)out_sub);
   return check_launch("gn_apply_kernel");
 }
 

@@ -99,6 +99,16 @@ extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
   p.rm_c0 = q->rm_c0;
   p.rm_Ho = q->rm_Ho;
   p.rm_Wo = q->rm_Wo;
+  p.gn_acc = q->gn_acc;
+  p.gn_acc_relu = q->gn_acc_relu;
+  p.gn_rows_per_img = q->gn_rows_per_img;
+  p.gn_cpg = q->n / 32;
+  if (q->gn_acc != nullptr) {
+    SNAP_REQUIRE(q->n % 64 == 0 && q->gn_rows_per_img > 0, "gn_acc needs n %% 64 == 0 and gn_rows_per_img");
+    SNAP_REQUIRE(!q->out_f32 && q->bias == nullptr && !q->relu && q->row_mask == nullptr,
+                 "gn_acc is only defined for plain bf16 conv outputs (optional residual)");
+  }
+  SNAP_REQUIRE(q->gn_acc_relu == nullptr || q->gn_acc != nullptr, "gn_acc_relu needs gn_acc");
   if (q->remap) SNAP_REQUIRE(q->rm_R > 0 && q->rm_C > 0 && q->rm_Ho > 0 && q->rm_Wo > 0, "bad remap");
   return launch_gemm(q->a, q->a_rows, q->a_cols, q->a_ld, q->b, q->b_rows, q->b_cols, q->b_ld, bn,
                      bk, p, static_cast<cudaStream_t>(stream));

@@ -46,6 +46,11 @@ struct GemmParams {
   int relu;
   // row remap: m -> (img, r, c) over (rm_R, rm_C); valid iff r0<=r<r0+Ho && c0<=c<c0+Wo
   int remap, rm_R, rm_C, rm_r0, rm_c0, rm_Ho, rm_Wo;
+  // fused GroupNorm statistics of the stored output (see snapb200.h)
+  double* gn_acc;
+  double* gn_acc_relu;
+  long long gn_rows_per_img;
+  int gn_cpg;  // channels per group = N / 32
   // EPI_XCORR
   const float* xc_cnt;
   const float* xc_den;
@@ -101,6 +106,51 @@ __device__ __forceinline__ int seg_row_offset(const GemmParams& p, int seg) {
   int i = seg / p.xc_G;
   int j = seg - i * p.xc_G;
   return i * p.xc_P + j;
+}
+
+// Accumulate (sum, sumsq) of 16 consecutive output columns of one row into the GroupNorm accumulators.
+// Rows of a warp normally belong to one image: reduce over the 32 rows with shuffles and issue one
+// double atomic per (group, moment); warps straddling an image boundary fall back to per-row atomics.
+template <int SPAN>  // columns per group inside the 16-column chunk: 2, 4, 8 or 16
+__device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row_ok, int img, int col,
+                                                  int cpg, double* acc, bool uniform, int img_ref,
+                                                  int lane) {
+#pragma unroll
+  for (int g = 0; g < 16 / SPAN; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < SPAN; ++j) {
+      s += v[g * SPAN + j];
+      q += v[g * SPAN + j] * v[g * SPAN + j];
+    }
+    if (!row_ok) s = q = 0.f;
+    const int group = (col + g * SPAN) / cpg;
+    if (uniform) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0 && img_ref >= 0) {
+        atomicAdd(&acc[((size_t)img_ref * 32 + group) * 2 + 0], (double)s);
+        atomicAdd(&acc[((size_t)img_ref * 32 + group) * 2 + 1], (double)q);
+      }
+    } else if (row_ok) {
+      atomicAdd(&acc[((size_t)img * 32 + group) * 2 + 0], (double)s);
+      atomicAdd(&acc[((size_t)img * 32 + group) * 2 + 1], (double)q);
+    }
+  }
+}
+
+__device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool row_ok, int img, int col,
+                                                int cpg, double* acc, bool uniform, int img_ref,
+                                                int lane) {
+  switch (cpg) {
+    case 2: gn_accumulate16_t<2>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
+    case 4: gn_accumulate16_t<4>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
+    case 8: gn_accumulate16_t<8>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
+    default: gn_accumulate16_t<16>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
+  }
 }
 
 template <int BN, int BK>
@@ -231,12 +281,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           orow = (img * p.rm_Ho + (r - p.rm_r0)) * p.rm_Wo + (c - p.rm_c0);
         }
         const bool keep = row_ok && (p.row_mask == nullptr || p.row_mask[row_ok ? orow : 0] != 0);
+        int gn_img = -1, gn_ref = -1;
+        bool gn_uniform = true;
+        if (p.gn_acc != nullptr) {
+          gn_img = row_ok ? (int)(orow / p.gn_rows_per_img) : -1;
+          gn_ref = __reduce_max_sync(0xffffffffu, gn_img);
+          gn_uniform = __all_sync(0xffffffffu, gn_img == gn_ref || gn_img == -1);
+        }
 #pragma unroll 1
         for (int c16 = 0; c16 < BN / 16; ++c16) {
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
           tmem_ld_wait();
           const int col = n0 + c16 * 16;
+          if (p.gn_acc != nullptr && col < p.N) {
+            // statistics of exactly what is stored (all roundings applied); warp-collective
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = bf16_round(__uint_as_float(v[j]));
+            if (p.residual && row_ok) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 x = unpack_bf16(rr[j]);
+                g[2 * j] = bf16_round(g[2 * j] + x.x);
+                g[2 * j + 1] = bf16_round(g[2 * j + 1] + x.y);
+              }
+            }
+            gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc, gn_uniform, gn_ref, lane);
+            if (p.gn_acc_relu != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) g[j] = fmaxf(g[j], 0.f);
+              gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc_relu, gn_uniform, gn_ref, lane);
+            }
+          }
           if (row_ok && col < p.N) {
             float f[16];
 #pragma unroll

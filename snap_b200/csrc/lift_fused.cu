@@ -1,0 +1,514 @@
+// Fused camera->BEV lift as ONE persistent sm_100a kernel:
+//
+//   voxel visibility (bit-exact projection)  ->  compaction of the visible voxels into 128-row tiles
+//   -> bilinear gather + depth score + multi-view softmax pooling -> statistics tile A[128 x 256] in
+//   swizzled shared memory -> tcgen05 GEMM1 (x W1, resident in smem, + rank-1 term of the score column)
+//   -> bias / ReLU epilogue writes H[128 x 256] back into the same smem tile -> tcgen05 GEMM2 (x W2,
+//   streamed by TMA through a 2-slot ring) -> bias epilogue -> running max over z per BEV column
+//   -> plane[G*G, 128] + valid[G*G].
+//
+// Nothing but the projected feature maps is read from HBM/L2 and nothing but the BEV plane is written:
+// the [N,V,160] gather result, the [N,257] statistics, the [N,256] hidden layer and the [N,128] feature
+// volume of the reference (streetview_encoder.py:251-286, bev_mapper.py:56-88) never exist in memory.
+// Voxels no camera sees are defined as zero / invalid by the reference (:282) and are skipped before the
+// MLP ("valid-voxel compaction"); results are identical.
+//
+// Warp roles (18 warps): 0 = TMA producer (W1 once, W2 ring), 1 = TMEM owner + MMA issuer,
+// 2..17 = 16 worker warps (visibility pass, gather/pool, both epilogues, z-max).
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "lift_common.cuh"
+
+namespace snapb200 {
+
+constexpr int FL_WORKERS = 16;                       // worker warps
+constexpr int FL_THREADS = (2 + FL_WORKERS) * 32;    // 576
+constexpr int FL_BATCH_COLS = 4;                     // BEV columns per visibility batch (4 x 64 z-slots)
+constexpr int FL_LIST_CAP = 384;                     // ring of compacted visible voxels (>= 127 + 256)
+constexpr int FL_MAXV = 4;                           // views handled by the fused kernel
+
+// shared memory map (bytes); every MMA operand region is 1024-aligned
+constexpr int SM_W1 = 0;                  // 4 K-chunks x [256 x 64] bf16, 128B-swizzled   (131072)
+constexpr int SM_AH = 131072;             // A / H / volume staging: 4 x [128 x 64] bf16   ( 65536)
+constexpr int SM_W2 = 196608;             // ring: 2 x [128 x 64] bf16                      ( 32768)
+constexpr int SM_LIST = 229376;           // uint32[FL_LIST_CAP]                            (  1536)
+constexpr int SM_SMAX = SM_LIST + 4 * FL_LIST_CAP;   // bf16[128] score_max per tile row    (   256)
+constexpr int SM_BAR = SM_SMAX + 256;     // mbarriers + control words                      (   256)
+constexpr int SM_VIEW = SM_BAR + 256;     // LiftView[FL_MAXV]                              (   384)
+constexpr int FL_SMEM_BYTES = SM_VIEW + 384;
+static_assert(sizeof(LiftView) * FL_MAXV <= 384, "view table");
+static_assert(FL_SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
+constexpr int VOL_STRIDE = 272;           // bytes per staged volume row (256 + 16: conflict-free)
+
+struct FusedArgs {
+  LiftParams P;
+  const LiftView* views;
+  const __nv_bfloat16* fimg;
+  const float *xs, *ys, *zs;
+  const float* w256;  // W1[256, :] (score_max input row) as f32[256]
+  const float* b1;    // f32[256]
+  const float* b2;    // f32[128]
+  __nv_bfloat16* plane;
+  uint8_t* pvalid;
+  int* col_counter;   // zeroed by the host wrapper
+};
+
+struct Ctl {  // lives at SM_BAR
+  uint64_t w1_full, w2_full[2], w2_empty[2], a_full, acc1_full, h_full, acc2_full;  // 9 x 8 B
+  uint32_t tmem_ptr;
+  int list_head, list_count, cols_done, batch_col0, more;
+  int warp_cnt[8];
+};
+static_assert(sizeof(Ctl) <= 256, "control block");
+
+__device__ __forceinline__ void worker_bar() {  // named barrier 1 over the 16 worker warps
+  asm volatile("bar.sync 1, %0;" ::"n"(FL_WORKERS * 32) : "memory");
+}
+
+__global__ void __launch_bounds__(FL_THREADS, 1)
+lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ FusedArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const LiftParams& P = A.P;
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + SM_BAR);
+  uint32_t* list = reinterpret_cast<uint32_t*>(smem + SM_LIST);
+  __nv_bfloat16* smax_s = reinterpret_cast<__nv_bfloat16*>(smem + SM_SMAX);
+  LiftView* sview = reinterpret_cast<LiftView*>(smem + SM_VIEW);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled operands need a 1024 B aligned base
+
+  for (int i = threadIdx.x; i < P.V * (int)(sizeof(LiftView) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sview)[i] = reinterpret_cast<const uint32_t*>(A.views)[i];
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(&ctl->w1_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->w2_full[s], 1);
+      mbar_init(&ctl->w2_empty[s], 1);
+    }
+    mbar_init(&ctl->a_full, FL_WORKERS * 32);
+    mbar_init(&ctl->acc1_full, 1);
+    mbar_init(&ctl->h_full, FL_WORKERS * 32);
+    mbar_init(&ctl->acc2_full, 1);
+    ctl->list_head = 0;
+    ctl->list_count = 0;
+    ctl->cols_done = 0;
+    ctl->more = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_ptr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_ptr;
+  const uint32_t tmem_acc1 = tmem_base;        // 256 columns
+  const uint32_t tmem_acc2 = tmem_base + 256;  // 128 columns
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&ctl->w1_full, 4 * 32768);
+      for (int kc = 0; kc < 4; ++kc) tma_load_2d(&tmW1, &ctl->w1_full, smem + SM_W1 + kc * 32768, kc * 64, 0);
+      uint32_t tile_phase = 0;
+      int slot = 0;
+      uint32_t ring_phase = 0;
+      while (true) {
+        mbar_wait(&ctl->a_full, tile_phase);
+        tile_phase ^= 1;
+        if (*reinterpret_cast<volatile int*>(&ctl->more) == 0) break;
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&ctl->w2_empty[slot], ring_phase ^ 1);
+          mbar_arrive_expect_tx(&ctl->w2_full[slot], 16384);
+          tma_load_2d(&tmW2, &ctl->w2_full[slot], smem + SM_W2 + slot * 16384, kc * 64, 0);
+          if (++slot == 2) {
+            slot = 0;
+            ring_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (elect_one()) {
+      constexpr uint32_t idesc1 = make_idesc_bf16_m128(256);
+      constexpr uint32_t idesc2 = make_idesc_bf16_m128(128);
+      mbar_wait(&ctl->w1_full, 0);
+      uint32_t tile_phase = 0;
+      int slot = 0;
+      uint32_t ring_phase = 0;
+      const uint32_t sAH = smem_u32(smem + SM_AH), sW1 = smem_u32(smem + SM_W1), sW2 = smem_u32(smem + SM_W2);
+      while (true) {
+        mbar_wait(&ctl->a_full, tile_phase);
+        if (*reinterpret_cast<volatile int*>(&ctl->more) == 0) break;
+        tc_fence_after_sync();
+        // GEMM1: acc1[128 x 256] = A[128 x 256] * W1^T
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          const uint64_t da = make_kmajor_desc<128>(sAH + kc * 16384);
+          const uint64_t db = make_kmajor_desc<128>(sW1 + kc * 32768);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_acc1, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kc | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&ctl->acc1_full);
+        // GEMM2: acc2[128 x 128] = H[128 x 256] * W2^T  (H written by the workers into the A tile)
+        mbar_wait(&ctl->h_full, tile_phase);
+        tc_fence_after_sync();
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&ctl->w2_full[slot], ring_phase);
+          tc_fence_after_sync();
+          const uint64_t da = make_kmajor_desc<128>(sAH + kc * 16384);
+          const uint64_t db = make_kmajor_desc<128>(sW2 + slot * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_acc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (kc | k) != 0 ? 1u : 0u);
+          umma_commit(&ctl->w2_empty[slot]);
+          if (++slot == 2) {
+            slot = 0;
+            ring_phase ^= 1;
+          }
+        }
+        umma_commit(&ctl->acc2_full);
+        tile_phase ^= 1;
+      }
+    }
+  } else {
+    // ============================ worker warps ============================
+    const int ww = warp - 2;             // 0..15
+    const int wtid = threadIdx.x - 64;   // 0..511
+    const int q = warp & 3;              // TMEM lane quadrant this warp may touch
+    const int sub = ww >> 2;             // which quarter of the accumulator columns it drains
+    const int ncols = P.X * P.Y;
+    const int half = lane >> 4, c8 = lane & 15;
+    const float score_scale = (float)(P.S - 1);
+    uint32_t tile_phase = 0;
+    int zm_col = -1;       // z-max carry of thread wtid < 128 (one output channel each)
+    float zm_val = 0.f;
+
+    while (true) {
+      // ---------- visibility batches: fill the list with >= 128 visible voxels ----------
+      while (true) {
+        worker_bar();
+        if (ctl->list_count >= 128 || ctl->cols_done) break;
+        if (wtid == 0) {
+          const int c0 = atomicAdd(A.col_counter, FL_BATCH_COLS);
+          ctl->batch_col0 = c0;
+          if (c0 >= ncols) ctl->cols_done = 1;
+        }
+        worker_bar();
+        if (ctl->cols_done) continue;
+        bool valid = false;
+        uint32_t entry = 0;
+        if (wtid < FL_BATCH_COLS * 64) {
+          const int cl = wtid >> 6, z = wtid & 63;
+          const int col = ctl->batch_col0 + cl;
+          if (col < ncols && z < P.Z) {
+            const int ix = col / P.Y, iy = col - ix * P.Y;
+            const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
+            uint32_t vm = 0;
+            for (int v = 0; v < P.V; ++v)
+              if (project_point(sview[v], px, py, pz).vis) vm |= 1u << v;
+            valid = vm != 0;
+            entry = ((uint32_t)col << 14) | ((uint32_t)z << 8) | vm;
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+          if (lane == 0) ctl->warp_cnt[ww] = __popc(bal);
+          worker_bar();
+          if (valid) {
+            int idx = ctl->list_count + __popc(bal & ((1u << lane) - 1u));
+            for (int w2 = 0; w2 < ww; ++w2) idx += ctl->warp_cnt[w2];
+            list[(ctl->list_head + idx) % FL_LIST_CAP] = entry;
+          }
+        } else {
+          worker_bar();
+        }
+        worker_bar();
+        if (wtid == 0) {
+          int tot = 0;
+          for (int w2 = 0; w2 < 8; ++w2) tot += ctl->warp_cnt[w2];
+          ctl->list_count += tot;
+        }
+      }
+      const int rows = min(128, ctl->list_count);
+      const int head = ctl->list_head;
+      if (wtid == 0) ctl->more = rows > 0 ? 1 : 0;
+      worker_bar();
+      if (rows == 0) {
+        mbar_arrive(&ctl->a_full);
+        break;
+      }
+
+      // ---------- gather + pool: one warp per tile row ----------
+      for (int r = ww; r < 128; r += FL_WORKERS) {
+        float mean[8], var[8], smaxv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
+        if (r < rows) {
+          const uint32_t e = list[(head + r) % FL_LIST_CAP];
+          const int col = (int)(e >> 14), z = (int)((e >> 8) & 63);
+          const uint32_t vm = e & 0xffu;
+          const int ix = col / P.Y, iy = col - ix * P.Y;
+          const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
+          float fv[FL_MAXV][8], score[FL_MAXV];
+#pragma unroll
+          for (int v = 0; v < FL_MAXV; ++v) {
+            score[v] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fv[v][j] = 0.f;
+          }
+#pragma unroll
+          for (int v = 0; v < FL_MAXV; ++v) {
+            if (v >= P.V || !(vm & (1u << v))) continue;  // warp-uniform
+            const Proj pr = project_point(sview[v], px, py, pz);
+            const Taps t = make_taps(pr.row, pr.col, P.Hf, P.Wf);
+            const __nv_bfloat16* img = A.fimg + (size_t)v * P.Hf * P.Wf * P.CF;
+            const int rr = half ? t.r1 : t.r0;
+            const float wr = half ? t.wr1 : __fadd_rn(1.0f, -t.wr1);
+            const float wc0 = __fadd_rn(1.0f, -t.wc1);
+            const uint4 ua = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)rr * P.Wf + t.c0) * P.CF + c8 * 8));
+            const uint4 ub = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)rr * P.Wf + t.c1) * P.CF + c8 * 8));
+            // depth score taps (lanes 0..7 = 4 taps x 2 bins), issued together with the feature loads
+            const float d = fminf(fmaxf(pr.depth, P.depth_min), P.depth_max);
+            const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
+            const float bf = floorf(bi);
+            const int b0 = min(max((int)bf, 0), P.S - 1), b1i = min(max((int)bf + 1, 0), P.S - 1);
+            const float wb1 = bi - bf;
+            float sp = 0.f;
+            if (lane < 8) {
+              const int tap = lane >> 1, bsel = lane & 1;
+              const int trr = (tap & 2) ? t.r1 : t.r0;
+              const int tcc = (tap & 1) ? t.c1 : t.c0;
+              const float wt = ((tap & 2) ? t.wr1 : 1.0f - t.wr1) * ((tap & 1) ? t.wc1 : 1.0f - t.wc1);
+              sp = wt * __bfloat162float(img[((size_t)trr * P.Wf + tcc) * P.CF + P.D + (bsel ? b1i : b0)]);
+            }
+            float fa[8], fb[8];
+            unpack8(ua, fa);
+            unpack8(ub, fb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float part = wr * (wc0 * fa[j] + t.wc1 * fb[j]);
+              part += __shfl_xor_sync(0xffffffffu, part, 16);
+              fv[v][j] = bf16_round(part);
+            }
+            sp += __shfl_xor_sync(0xffffffffu, sp, 2);
+            sp += __shfl_xor_sync(0xffffffffu, sp, 4);
+            sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
+            sp += __shfl_xor_sync(0xffffffffu, sp, 1);
+            score[v] = __shfl_sync(0xffffffffu, bf16_round(sp), 0);
+          }
+          float mx = 0.f;
+          smaxv = -INFINITY;
+#pragma unroll
+          for (int v = 0; v < FL_MAXV; ++v)
+            if (vm & (1u << v)) {
+              mx = fmaxf(mx, score[v]);
+              smaxv = fmaxf(smaxv, score[v]);
+            }
+          float wv[FL_MAXV], den = 0.f;
+#pragma unroll
+          for (int v = 0; v < FL_MAXV; ++v) {
+            wv[v] = (vm & (1u << v)) ? expf(score[v] - mx) : 0.f;
+            den += wv[v];
+          }
+#pragma unroll
+          for (int v = 0; v < FL_MAXV; ++v) {
+            wv[v] = __fdiv_rn(wv[v], den);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mean[j] += wv[v] * fv[v][j];
+          }
+#pragma unroll
+          for (int v = 0; v < FL_MAXV; ++v) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float dd = fv[v][j] - mean[j];
+              var[j] += wv[v] * dd * dd;
+            }
+          }
+        }
+        // A[r][k]: lanes 0..15 -> mean (k = 8*c8..), lanes 16..31 -> var (k = 128 + 8*c8..); K-chunk of 64,
+        // 16-byte slot (k%64)/8 XOR (r%8) inside the 128-byte row (SWIZZLE_128B, as TMA would write it)
+        const float* src = half ? var : mean;
+        const int kc = half * 2 + (c8 >> 3);
+        const int slot16 = (c8 & 7) ^ (r & 7);
+        *reinterpret_cast<uint4*>(smem + SM_AH + kc * 16384 + r * 128 + slot16 * 16) =
+            make_uint4(pack_bf16(src[0], src[1]), pack_bf16(src[2], src[3]), pack_bf16(src[4], src[5]),
+                       pack_bf16(src[6], src[7]));
+        if (lane == 0) smax_s[r] = __float2bfloat16(smaxv);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
+      mbar_arrive(&ctl->a_full);
+
+      // ---------- epilogue 1: H = relu(bf16(bf16(acc1 + smax * w256) + b1)) -> smem (A tile) ----------
+      mbar_wait(&ctl->acc1_full, tile_phase);
+      tc_fence_after_sync();
+      {
+        const int row = q * 32 + lane;
+        const float sm = __bfloat162float(smax_s[row]);
+        const uint32_t taddr = tmem_acc1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64);
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
+          tmem_ld_wait();
+          const int n0 = sub * 64 + c16 * 16;
+          float f[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w256 + n0) + j4);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.b1 + n0) + j4);
+            const float ws[4] = {w4.x, w4.y, w4.z, w4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              float x = bf16_round(__uint_as_float(v[j]) + sm * ws[e]);  // dot over all 257 inputs -> dtype
+              x = bf16_round(x + bs[e]);                                  // + bias -> dtype
+              f[j] = fmaxf(x, 0.f);
+            }
+          }
+          const int kc = n0 >> 6;  // H column n0 is K index n0 of GEMM2
+          const int s0 = (n0 & 63) >> 3;
+          uint8_t* rowp = smem + SM_AH + kc * 16384 + row * 128;
+          *reinterpret_cast<uint4*>(rowp + ((s0 ^ (row & 7)) * 16)) =
+              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          *reinterpret_cast<uint4*>(rowp + (((s0 + 1) ^ (row & 7)) * 16)) =
+              make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                         pack_bf16(f[14], f[15]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&ctl->h_full);
+
+      // ---------- epilogue 2: volume rows = bf16(bf16(acc2) + b2) -> smem staging ----------
+      mbar_wait(&ctl->acc2_full, tile_phase);
+      tc_fence_after_sync();
+      {
+        const int row = q * 32 + lane;
+        const uint32_t taddr = tmem_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 32);
+#pragma unroll 1
+        for (int c16 = 0; c16 < 2; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
+          tmem_ld_wait();
+          const int n0 = sub * 32 + c16 * 16;
+          float f[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.b2 + n0) + j4);
+            const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[j4 * 4 + e] = bf16_round(bf16_round(__uint_as_float(v[j4 * 4 + e])) + bs[e]);
+          }
+          uint8_t* rowp = smem + SM_AH + row * VOL_STRIDE + n0 * 2;
+          *reinterpret_cast<uint4*>(rowp) =
+              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          *reinterpret_cast<uint4*>(rowp + 16) =
+              make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                         pack_bf16(f[14], f[15]));
+        }
+      }
+      tc_fence_before_sync();
+      worker_bar();
+
+      // ---------- vertical max (bev_mapper.py:56-88): thread c owns output channel c ----------
+      if (wtid < 128) {
+        for (int r = 0; r < rows; ++r) {
+          const int col = (int)(list[(head + r) % FL_LIST_CAP] >> 14);
+          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(smem + SM_AH + r * VOL_STRIDE + wtid * 2));
+          if (col != zm_col) {
+            if (zm_col >= 0) {
+              A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
+              if (wtid == 0) A.pvalid[zm_col] = 1;
+            }
+            zm_col = col;
+            zm_val = x;
+          } else {
+            zm_val = fmaxf(zm_val, x);
+          }
+        }
+      }
+      worker_bar();
+      if (wtid == 0) {
+        ctl->list_head = (head + rows) % FL_LIST_CAP;
+        ctl->list_count -= rows;
+      }
+      tile_phase ^= 1;
+    }
+    if (wtid < 128 && zm_col >= 0) {
+      A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
+      if (wtid == 0) A.pvalid[zm_col] = 1;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace snapb200
+
+using namespace snapb200;
+
+extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* views, const void* fimg,
+                                   const float* xs, const float* ys, const float* zs, const void* w1t,
+                                   long long ldw1, const float* w256, const float* b1, const void* w2t,
+                                   const float* b2, void* plane, uint8_t* pvalid, int* col_counter,
+                                   void* stream) {
+  SNAP_REQUIRE(q && views && fimg && xs && ys && zs && w1t && w256 && b1 && w2t && b2 && plane && pvalid &&
+                   col_counter,
+               "null pointer");
+  SNAP_REQUIRE(q->V >= 1 && q->V <= FL_MAXV, "fused lift handles 1..%d views (got %d)", FL_MAXV, q->V);
+  SNAP_REQUIRE(q->D == 128 && q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
+  SNAP_REQUIRE(q->Z >= 1 && q->Z <= 64, "Z must be <= 64 (got %d)", q->Z);
+  SNAP_REQUIRE((long long)q->X * q->Y < (1 << 18), "too many BEV columns");
+  static_assert(sizeof(SnapLiftView) == sizeof(LiftView), "SnapLiftView layout");
+  static_assert(sizeof(SnapLiftParams) == sizeof(LiftParams), "SnapLiftParams layout");
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    int rc = check_cuda(cudaFuncSetAttribute(lift_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             FL_SMEM_BYTES),
+                        "cudaFuncSetAttribute(lift_fused)");
+    if (rc) return rc;
+    configured = true;
+  }
+  CUtensorMap tmW1, tmW2;
+  int rc = make_tmap_2d_bf16(&tmW1, w1t, 256, 256, ldw1, 256, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmW2, w2t, 128, 256, 256, 128, 64);
+  if (rc) return rc;
+  const long long cells = (long long)q->X * q->Y;
+  rc = check_cuda(cudaMemsetAsync(plane, 0, (size_t)cells * 128 * 2, s), "memset plane");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(pvalid, 0, (size_t)cells, s), "memset valid");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(col_counter, 0, sizeof(int), s), "memset counter");
+  if (rc) return rc;
+  FusedArgs a;
+  memcpy(&a.P, q, sizeof(LiftParams));
+  a.views = reinterpret_cast<const LiftView*>(views);
+  a.fimg = (const __nv_bfloat16*)fimg;
+  a.xs = xs;
+  a.ys = ys;
+  a.zs = zs;
+  a.w256 = w256;
+  a.b1 = b1;
+  a.b2 = b2;
+  a.plane = (__nv_bfloat16*)plane;
+  a.pvalid = pvalid;
+  a.col_counter = col_counter;
+  int grid = num_sms();
+  const int max_useful = (int)((cells + FL_BATCH_COLS - 1) / FL_BATCH_COLS);
+  if (grid > max_useful) grid = max_useful;
+  lift_fused_kernel<<<grid, FL_THREADS, FL_SMEM_BYTES, s>>>(tmW1, tmW2, a);
+  return check_launch("lift_fused_kernel");
+}

@@ -128,7 +128,6 @@ class EncoderPlan:
         h, w = self.x0HW
         max_rows_c = 0
         self.stage_out = []
-        gn_ws = 0
         for si, nunits in enumerate(blocks):
             nmid, nout = width * 2 ** si, width * 2 ** si * 4
             for u in range(nunits):
@@ -154,7 +153,6 @@ class EncoderPlan:
                     unit["out"] = self.units[-2]["out"]  # ping-pong inside the stage
                 self.units.append(unit)
                 max_rows_c = max(max_rows_c, n_img * h * w * cin, n_img * ho * wo * nout)
-                gn_ws = max(gn_ws, ops.gn_workspace_bytes(n_img, h * w))
                 cin, h, w = nout, ho, wo
             # the last unit's output is an FPN skip feature: give it a private buffer
             self.units[-1]["out"] = bf(n_img * h * w, cin)
@@ -162,8 +160,17 @@ class EncoderPlan:
         self.buf_a = torch.zeros(max_rows_c + 128 * 2048, dtype=torch.bfloat16, device=device)  # gn1 / gn3 outputs
         self.buf_y = torch.zeros(max_rows_c + 128 * 2048, dtype=torch.bfloat16, device=device)  # conv1 / conv2 outputs
         self.buf_res = torch.zeros(max_rows_c + 128 * 2048, dtype=torch.bfloat16, device=device)
-        self.gn_ws = torch.zeros(max(gn_ws, 256) // 4 + 64, dtype=torch.float32, device=device)
-        self.gn_stats = torch.zeros((n_img, 32, 2), dtype=torch.float32, device=device)
+        # GroupNorm accumulators (sum, sumsq) f64 [slot, img, 32, 2]: 3 per unit (gn1 input, conv1 out, conv2 out),
+        # one per FPN level (statistics of relu(stage output)), one scratch; zeroed once per forward.
+        self.gn_acc_all = torch.zeros((3 * len(self.units) + len(blocks) + 1, n_img, 32, 2), dtype=torch.float64,
+                                      device=device)
+        for i, u in enumerate(self.units):
+            u["acc"] = [self.gn_acc_all[3 * i + k] for k in range(3)]
+        self.fpn_acc = [self.gn_acc_all[3 * len(self.units) + k] for k in range(len(blocks))]
+        self.acc_scratch = self.gn_acc_all[-1]
+        ends = np.cumsum(blocks) - 1   # index of the last unit of each stage
+        for si, e in enumerate(ends):
+            self.units[e]["fpn_acc"] = self.fpn_acc[si]
 
         # ---- FPN ----
         self.fpn = []
@@ -182,62 +189,88 @@ class EncoderPlan:
     def _view(self, buf: torch.Tensor, rows: int, c: int) -> torch.Tensor:
         return buf[: _round_up(max(rows, 128), 128) * c].view(-1, c)
 
-    def _gn(self, x, n, h, w, c, gn, pre_relu, post_relu, layout, out, out_sub=None):
-        ops.gn_stats(x, n, h * w, c, pre_relu, self.gn_stats, self.gn_ws)
-        ops.gn_apply(x, n, h, w, c, self.gn_stats, gn[0], gn[1], pre_relu, post_relu, layout, out, out_sub)
-
     def run_root(self, images: torch.Tensor) -> torch.Tensor:
+        """resnet.py:82-100,199-208.  Also produces the GroupNorm statistics of the first unit's input."""
         n = self.n
         assert tuple(images.shape) == (n, self.H, self.W, 3), images.shape
         kh, kw, st, pd = self.root_geom
         H0, W0 = self.rootHW
+        acc0 = self.units[0]["acc"][0]
         ops.root_im2col(images, self.Hp, self.Wp, kh, kw, st, pd, self.a_root)
-        ops.gemm(self.a_root, self.bank.b_mats[self.root_w], self.y_root, m_rows=n * H0 * W0, seg_k=self.root_kp)
-        if not self.skip_root:
+        if self.skip_root:
+            ops.gemm(self.a_root, self.bank.b_mats[self.root_w], self.y_root, m_rows=n * H0 * W0, seg_k=self.root_kp,
+                     gn_acc=acc0, gn_rows_per_img=H0 * W0)
+        else:
+            ops.gemm(self.a_root, self.bank.b_mats[self.root_w], self.y_root, m_rows=n * H0 * W0, seg_k=self.root_kp)
             ops.maxpool3x3s2(self.y_root, n, H0, W0, self.y_root.shape[1], self.x0)
+            ops.gn_stats(self.x0, n, self.x0HW[0] * self.x0HW[1], self.y_root.shape[1], False, acc0)
         return self.x0
 
-    def run_unit(self, u: Dict, x: torch.Tensor) -> torch.Tensor:
-        """One pre-activation bottleneck (`snap/models/resnet.py:103-134`); x: bf16 [>= n*h*w, cin]."""
+    def run_unit(self, u: Dict, x: torch.Tensor, next_acc: Optional[torch.Tensor] = None,
+                 forced_input: bool = False) -> torch.Tensor:
+        """One pre-activation bottleneck (`snap/models/resnet.py:103-134`); x: bf16 [>= n*h*w, cin].
+
+        The statistics of x must already be in u['acc'][0] (written by the producer's epilogue) unless
+        `forced_input` (teacher-forced tests), in which case they are computed here.  The epilogue of conv3
+        accumulates the statistics of the unit's output into `next_acc` (next unit's gn1) and, for the last
+        unit of a stage, the statistics of relu(output) for the FPN."""
         n, B = self.n, self.bank.b_mats
         cin, nmid, nout, s = u["cin"], u["nmid"], u["nout"], u["stride"]
         h, w, ho, wo = u["h"], u["w"], u["ho"], u["wo"]
         rows_in, rows_out = n * h * w, n * ho * wo
+        acc1, acc2, acc3 = u["acc"]
+        if forced_input:
+            acc1.zero_(); acc2.zero_(); acc3.zero_()
+            ops.gn_stats(x, n, h * w, cin, False, acc1)
         a1 = self._view(self.buf_a, rows_in, cin)
-        self._gn(x, n, h, w, cin, u["gn"][0], False, True, ops.LAYOUT_DENSE, a1, u.get("a1_sub"))
+        ops.gn_apply(x, n, h, w, cin, acc1, u["gn"][0][0], u["gn"][0][1], False, True, ops.LAYOUT_DENSE, a1,
+                     u.get("a1_sub"))
         if u["wproj"] is not None:  # resnet.py:121-122 (projection of the pre-activated tensor)
             res = self._view(self.buf_res, rows_out, nout)
             ops.gemm(u["a1_sub"] if s == 2 else a1, B[u["wproj"]], res, m_rows=rows_out)
         else:
             res = x
         y1 = self._view(self.buf_y, rows_in, nmid)
-        ops.gemm(a1, B[u["w1"]], y1, m_rows=rows_in)
+        ops.gemm(a1, B[u["w1"]], y1, m_rows=rows_in, gn_acc=acc2, gn_rows_per_img=h * w)
         if s == 1:
-            self._gn(y1, n, h, w, nmid, u["gn"][1], False, True, ops.LAYOUT_PADDED, u["a2"])
+            ops.gn_apply(y1, n, h, w, nmid, acc2, u["gn"][1][0], u["gn"][1][1], False, True, ops.LAYOUT_PADDED, u["a2"])
             hp, wp = h + 2, w + 2
             seg = [(a - 1) * wp + (b - 1) for a in range(3) for b in range(3)]
             m_rows, remap = n * hp * wp, (hp, wp, 1, 1, h, w)
         else:
-            self._gn(y1, n, h, w, nmid, u["gn"][1], False, True, ops.LAYOUT_PHASE, u["a2"])
+            ops.gn_apply(y1, n, h, w, nmid, acc2, u["gn"][1][0], u["gn"][1][1], False, True, ops.LAYOUT_PHASE, u["a2"])
             hq, wq = h // 2 + 1, w // 2 + 1
             plane = n * hq * wq
             seg = [((a % 2) * 2 + (b % 2)) * plane + (a // 2) * wq + (b // 2) for a in range(3) for b in range(3)]
             m_rows, remap = plane, (hq, wq, 0, 0, ho, wo)
         y2 = self._view(self.buf_y, rows_out, nmid)  # y1 is dead once a2 is written
-        ops.gemm(u["a2"], B[u["w2"]], y2, m_rows=m_rows, seg_off=seg, seg_k=nmid, remap=remap)
+        ops.gemm(u["a2"], B[u["w2"]], y2, m_rows=m_rows, seg_off=seg, seg_k=nmid, remap=remap,
+                 gn_acc=acc3, gn_rows_per_img=ho * wo)
         a3 = self._view(self.buf_a, rows_out, nmid)
-        self._gn(y2, n, ho, wo, nmid, u["gn"][2], False, True, ops.LAYOUT_DENSE, a3)
-        ops.gemm(a3, B[u["w3"]], u["out"], m_rows=rows_out, residual=res)
+        ops.gn_apply(y2, n, ho, wo, nmid, acc3, u["gn"][2][0], u["gn"][2][1], False, True, ops.LAYOUT_DENSE, a3)
+        fpn_acc = u.get("fpn_acc")
+        if forced_input and fpn_acc is not None:
+            fpn_acc.zero_()
+        if next_acc is None and fpn_acc is not None:
+            next_acc = self.acc_scratch
+        ops.gemm(a3, B[u["w3"]], u["out"], m_rows=rows_out, residual=res, gn_acc=next_acc, gn_acc_relu=fpn_acc,
+                 gn_rows_per_img=ho * wo)
         return u["out"]
 
-    def run_fpn(self) -> List[torch.Tensor]:
+    def run_fpn(self, forced_input: bool = False) -> List[torch.Tensor]:
         """`snap/models/image_encoder.py:79-94` over the stage outputs (coarse -> fine)."""
         n, B = self.n, self.bank.b_mats
         outs, prev = [], None
-        for f in self.fpn:
+        nlev = len(self.fpn)
+        for level, f in enumerate(self.fpn):
             rows = n * f["h"] * f["w"]
+            acc = self.fpn_acc[nlev - 1 - level]
+            if forced_input:
+                acc.zero_()
+                ops.gn_stats(f["x"], n, f["h"] * f["w"], f["c"], True, acc)
             a = self._view(self.buf_a, rows, f["c"])
-            self._gn(f["x"], n, f["h"], f["w"], f["c"], f["gn"], True, False, ops.LAYOUT_DENSE, a)
+            ops.gn_apply(f["x"], n, f["h"], f["w"], f["c"], acc, f["gn"][0], f["gn"][1], True, False,
+                         ops.LAYOUT_DENSE, a)
             if prev is not None:
                 ops.upsample2x(prev["out"], n, prev["h"], prev["w"], self.out_dim, f["up"])
             ops.gemm(a, B[f["wk"]], f["out"], m_rows=rows, residual=f["up"] if prev is not None else None)
@@ -247,10 +280,12 @@ class EncoderPlan:
 
     def run(self, images: torch.Tensor) -> List[torch.Tensor]:
         """images f32 [n,H,W,3] in [0,1] (device) -> FPN features coarse->fine, each [n,h,w,C] bf16 (uncropped)."""
+        self.gn_acc_all.zero_()
         self.bank.run()
         x = self.run_root(images)
-        for u in self.units:
-            x = self.run_unit(u, x)
+        for i, u in enumerate(self.units):
+            nxt = self.units[i + 1]["acc"][0] if i + 1 < len(self.units) else None
+            x = self.run_unit(u, x, nxt)
         return self.run_fpn()
 
     def cropped_shapes(self) -> List[Tuple[int, int]]:

@@ -47,6 +47,9 @@ def gemm(
     relu: bool = False,
     remap: Optional[Sequence[int]] = None,   # (R, C, r0, c0, Ho, Wo)
     bn: int = 0,
+    gn_acc: Optional[torch.Tensor] = None,       # f64 [n_img, 32, 2] accumulators (zeroed by the caller)
+    gn_acc_relu: Optional[torch.Tensor] = None,
+    gn_rows_per_img: int = 0,
 ) -> torch.Tensor:
     """out = epilogue(sum_s A[m + seg_off[s], a_col0 : a_col0+seg_k] @ B[:, s*seg_k:(s+1)*seg_k].T)."""
     _require(a, torch.bfloat16, "a")
@@ -85,6 +88,12 @@ def gemm(
         p.remap = 1
         p.rm_R, p.rm_C, p.rm_r0, p.rm_c0, p.rm_Ho, p.rm_Wo = (int(x) for x in remap)
     p.bn = bn
+    if gn_acc is not None:
+        _require(gn_acc, torch.float64, "gn_acc")
+        p.gn_acc, p.gn_rows_per_img = _ptr(gn_acc), gn_rows_per_img
+        if gn_acc_relu is not None:
+            _require(gn_acc_relu, torch.float64, "gn_acc_relu")
+            p.gn_acc_relu = _ptr(gn_acc_relu)
     _lib.check(_lib.lib().snapb200_gemm_bf16(C.byref(p), _stream()))
     return out
 
@@ -113,26 +122,21 @@ def maxpool3x3s2(x: torch.Tensor, n: int, H: int, W: int, Cc: int, y: torch.Tens
     _lib.check(_lib.lib().snapb200_maxpool3x3s2(C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(y)), _stream()))
 
 
-def gn_workspace_bytes(n: int, hw: int) -> int:
-    f = _lib.lib().snapb200_gn_workspace_bytes
-    f.restype = C.c_size_t
-    return int(f(C.c_int(n), C.c_int(hw)))
-
-
-def gn_stats(x: torch.Tensor, n: int, hw: int, Cc: int, pre_relu: bool, stats: torch.Tensor,
-             workspace: torch.Tensor) -> None:
+def gn_stats(x: torch.Tensor, n: int, hw: int, Cc: int, pre_relu: bool, acc: torch.Tensor) -> None:
+    """Accumulate raw GroupNorm statistics of x into acc f64 [n, 32, 2] (must be zeroed by the caller)."""
+    _require(acc, torch.float64, "acc")
     _lib.check(_lib.lib().snapb200_gn_stats(C.c_void_p(_ptr(x)), n, hw, Cc, int(pre_relu),
-                                            C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(workspace)), _stream()))
+                                            C.c_void_p(_ptr(acc)), _stream()))
 
 
 LAYOUT_DENSE, LAYOUT_PADDED, LAYOUT_PHASE = 0, 1, 2
 
 
-def gn_apply(x: torch.Tensor, n: int, H: int, W: int, Cc: int, stats: torch.Tensor, scale: torch.Tensor,
+def gn_apply(x: torch.Tensor, n: int, H: int, W: int, Cc: int, acc: torch.Tensor, scale: torch.Tensor,
              bias: torch.Tensor, pre_relu: bool, post_relu: bool, layout: int, out: torch.Tensor,
              out_sub: Optional[torch.Tensor] = None) -> None:
     _lib.check(_lib.lib().snapb200_gn_apply(
-        C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(scale)),
+        C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(acc)), C.c_void_p(_ptr(scale)),
         C.c_void_p(_ptr(bias)), int(pre_relu), int(post_relu), layout, C.c_void_p(_ptr(out)),
         C.c_void_p(_ptr(out_sub)), _stream()))
 
@@ -158,6 +162,23 @@ def lift_gather_pool(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tens
         C.byref(p), C.c_void_p(_ptr(views)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
         C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(valid)),
         C.c_void_p(_ptr(dbg_vis)), C.c_void_p(_ptr(dbg_taps)), _stream()))
+
+
+def lift_fused(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+               zs: torch.Tensor, w1t: torch.Tensor, w256: torch.Tensor, b1: torch.Tensor, w2t: torch.Tensor,
+               b2: torch.Tensor, plane: torch.Tensor, pvalid: torch.Tensor, counter: torch.Tensor) -> None:
+    _require(fimg, torch.bfloat16, "fimg")
+    _require(w1t, torch.bfloat16, "w1t")
+    _require(w2t, torch.bfloat16, "w2t")
+    for t, n in ((w256, "w256"), (b1, "b1"), (b2, "b2")):
+        _require(t, torch.float32, n)
+    _require(counter, torch.int32, "counter")
+    assert w1t.shape[0] >= 256 and w2t.shape == (128, 256) and w2t.is_contiguous()
+    _lib.check(_lib.lib().snapb200_lift_fused(
+        C.byref(p), C.c_void_p(_ptr(views)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
+        C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(w1t)), C.c_longlong(w1t.stride(0)), C.c_void_p(_ptr(w256)),
+        C.c_void_p(_ptr(b1)), C.c_void_p(_ptr(w2t)), C.c_void_p(_ptr(b2)), C.c_void_p(_ptr(plane)),
+        C.c_void_p(_ptr(pvalid)), C.c_void_p(_ptr(counter)), _stream()))
 
 
 def vertical_max(volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, Cc: int,

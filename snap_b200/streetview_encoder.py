@@ -90,7 +90,8 @@ class StreetViewEncoder:
                      fus1=bank.add(params["fusion_mlp"]["Dense_1"]["kernel"], False),
                      proj_b=f32(params["proj_mlp"]["Dense_0"]["bias"]),
                      fus0_b=f32(params["fusion_mlp"]["Dense_0"]["bias"]),
-                     fus1_b=f32(params["fusion_mlp"]["Dense_1"]["bias"]))
+                     fus1_b=f32(params["fusion_mlp"]["Dense_1"]["bias"]),
+                     w256=f32(params["fusion_mlp"]["Dense_0"]["kernel"][256]))
             bank.finalize()
             self._cache[key] = w
         return self._cache[key]
@@ -104,7 +105,8 @@ class StreetViewEncoder:
             rows_img = max(V * hf * wf, 128)
             self._cache[key] = dict(
                 crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
-                volume=z(B, N, 128), valid=z(B, N, dt=torch.uint8),
+                volume=None, valid=None,   # [B,N,128] / [B,N]: allocated on first unfused call
+                plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 1, dt=torch.int32),
                 # per-scene inputs: pinned host staging + device copies (a captured CUDA graph re-reads the
                 # staging buffers at every replay, see `stage_inputs`)
                 images_host=pin(B, V, H, W, 3, dt=torch.float32), images=z(B, V, H, W, 3, dt=torch.float32),
@@ -131,7 +133,10 @@ class StreetViewEncoder:
             return True
         return False
 
-    def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False) -> Dict:
+    def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False,
+              fused: bool = False) -> Dict:
+        """`fused=True` runs the whole lift as one kernel and returns 'feature_plane' (bev_mapper.py:56-88 applied)
+        instead of materialising 'feature_volume' (which then is absent from the result)."""
         if train:
             raise NotImplementedError("training (backward kernels) is a 'next' row of SURVEY.md §8(f)")
         params = variables["params"] if "params" in variables else variables
@@ -166,10 +171,18 @@ class StreetViewEncoder:
         N = X * Y * Z
         lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, 288)
         dbg = {}
+        if not fused and buf["volume"] is None:
+            buf["volume"] = torch.zeros((B, N, 128), dtype=torch.bfloat16, device=dev)
+            buf["valid"] = torch.zeros((B, N), dtype=torch.uint8, device=dev)
         for b in range(B):
             # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`)
             ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, True, buf["crop"])
             ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"][b], m_rows=V * hf * wf, bias=wts["proj_b"])
+            if fused:
+                ops.lift_fused(lp, buf["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], buf["zs"][b],
+                               Bm[wts["fus0"]], wts["w256"], wts["fus0_b"], Bm[wts["fus1"]], wts["fus1_b"],
+                               buf["plane"][b], buf["pvalid"][b], buf["counter"][b])
+                continue
             dv = dt = None
             if debug:
                 dv = torch.zeros((N, V), dtype=torch.uint8, device=dev)
@@ -183,9 +196,13 @@ class StreetViewEncoder:
             ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],
                      row_mask=buf["valid"][b])
         pred = {"image_feature_pyramid": pyr,
-                "scores_images": buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)[..., 128:],
-                "feature_volume": types.FeatureVolume(features=buf["volume"].view(B, X, Y, Z, 128),
-                                                      valid=buf["valid"].view(B, X, Y, Z))}
+                "scores_images": buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)[..., 128:]}
+        if fused:
+            pred["feature_plane"] = types.FeaturePlane(features=buf["plane"].view(B, X, Y, 128),
+                                                       valid=buf["pvalid"].view(B, X, Y))
+        else:
+            pred["feature_volume"] = types.FeatureVolume(features=buf["volume"].view(B, X, Y, Z, 128),
+                                                         valid=buf["valid"].view(B, X, Y, Z))
         if debug:
             pred["debug"] = {k: torch.stack(v) for k, v in dbg.items()}
             pred["debug"]["f_proj_images"] = buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)

@@ -93,3 +93,27 @@ def test_gemm_rejects_bad_shapes():
     out = torch.zeros((128, 64), device="cuda")
     with pytest.raises(_lib.SnapB200Error):
         ops.gemm(a, b, out)  # K=48 is not a multiple of 32
+
+
+@pytest.mark.parametrize("n,cpg_n", [(64, 64), (256, 256), (2048, 2048)])
+def test_gemm_epilogue_groupnorm_accumulators(n, cpg_n):
+    """Fused GroupNorm statistics: acc[img][g] = (sum, sumsq) of the STORED bf16 output (with residual),
+    including M-tiles that straddle an image boundary and rows beyond M."""
+    from snap_b200 import ops
+    rows_per_img, n_img, K = 200, 3, 128
+    M = rows_per_img * n_img
+    a, b = _rand((M, K), 21), _rand((n, K), 22, 0.2)
+    res = _rand((M, n), 23)
+    out = torch.zeros((M, n), dtype=torch.bfloat16, device="cuda")
+    acc = torch.zeros((n_img, 32, 2), dtype=torch.float64, device="cuda")
+    acc_relu = torch.zeros((n_img, 32, 2), dtype=torch.float64, device="cuda")
+    ops.gemm(a.cuda(), b.cuda(), out, residual=res.cuda(), gn_acc=acc, gn_acc_relu=acc_relu, gn_rows_per_img=rows_per_img)
+    torch.cuda.synchronize()
+    r = lambda t: t.to(torch.bfloat16).float()
+    ref = r(r(a.float() @ b.float().T) + res.float())
+    assert torch.equal(out.float().cpu(), ref) or (out.float().cpu() - ref).abs().max() <= 2.0 ** -7 * ref.abs().max()
+    o = out.float().cpu().double().reshape(n_img, rows_per_img, 32, n // 32)
+    for accd, x in ((acc, o), (acc_relu, o.clamp(min=0))):
+        s, q = x.sum(dim=(1, 3)), (x * x).sum(dim=(1, 3))
+        assert torch.allclose(accd.cpu()[..., 0], s, rtol=1e-5, atol=1e-3)
+        assert torch.allclose(accd.cpu()[..., 1], q, rtol=1e-5, atol=1e-3)

@@ -185,3 +185,55 @@ def test_bev_mapper_vs_oracle(name, V, hw_img, G, aerial):
         print(f"{name} {k}: vs bf16-oracle {a:.4f} | vs fp32-oracle {b:.4f} | bf16-oracle vs fp32-oracle {c:.4f}")
     for key in ("bev_features", "bev_matching"):
         assert e[key][1] < 1.5 * e[key][2] + 1e-2, key
+
+
+@pytest.mark.parametrize("G,V,hw_img", [(24, 3, (64, 96)), (64, 1, (224, 224)), (128, 4, (480, 640))])
+def test_fused_lift_equals_unfused_path(G, V, hw_img):
+    """The single-kernel lift (visibility -> compaction -> gather/pool -> tcgen05 MLP -> z-max) must produce
+    the SAME plane as the unfused path (gather kernel + 2 GEMMs + vertical max): identical rounding points,
+    only the fp32 summation order of the 257th input (rank-1 term) differs -> <= 1 bf16 ulp on a few values;
+    valid mask bit-exact.  The unfused path is pinned against the oracle above."""
+    from snap_b200 import configs, ops, params, streetview_encoder as sve
+    from snap_b200.image_encoder import _WeightBank
+    data, grid, mapper, xs, ys, zs = _lift_inputs(G, hw_img, V, 7)
+    hf, wf = -(-hw_img[0] // 4), -(-hw_img[1] // 4)
+    rng = np.random.default_rng(3)
+    cfg = configs.streetview_encoder()
+    Z = zs.shape[1]
+    N = G * G * Z
+    dev = "cuda"
+    fimg = _t(bf16_np(rng.standard_normal((V, hf, wf, 160)))).to(torch.bfloat16).to(dev)
+    fp = params.round_to_bf16(params.perturb_affine(rng, params.init_mlp(rng, 257, (256, 128))))
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    bank = _WeightBank(torch.device(dev))
+    w0 = bank.add(fp["Dense_0"]["kernel"], False, 32)
+    w1 = bank.add(fp["Dense_1"]["kernel"], False)
+    bank.finalize(); bank.run()
+    b1, b2 = _t(fp["Dense_0"]["bias"]).to(dev), _t(fp["Dense_1"]["bias"]).to(dev)
+    xs_d, ys_d, zs_d = _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev)
+    # unfused
+    stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
+    valid = torch.zeros(N, dtype=torch.uint8, device=dev)
+    ops.lift_gather_pool(lp, views, fimg, xs_d, ys_d, zs_d, stats, valid)
+    hid = torch.zeros((N, 256), dtype=torch.bfloat16, device=dev)
+    vol = torch.zeros((N, 128), dtype=torch.bfloat16, device=dev)
+    ops.gemm(stats, bank.b_mats[w0], hid, m_rows=N, seg_k=288, bias=b1, relu=True)
+    ops.gemm(hid, bank.b_mats[w1], vol, m_rows=N, bias=b2, row_mask=valid)
+    plane_ref = torch.zeros((G * G, 128), dtype=torch.bfloat16, device=dev)
+    pv_ref = torch.zeros(G * G, dtype=torch.uint8, device=dev)
+    ops.vertical_max(vol, valid, G * G, Z, 128, plane_ref, pv_ref)
+    # fused
+    plane = torch.full((G * G, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    pv = torch.full((G * G,), 9, dtype=torch.uint8, device=dev)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    w256 = _t(fp["Dense_0"]["kernel"][256]).to(dev)
+    for _ in range(2):  # twice: the kernel must be re-entrant on the same buffers
+        ops.lift_fused(lp, views, fimg, xs_d, ys_d, zs_d, bank.b_mats[w0], w256, b1, bank.b_mats[w1], b2, plane, pv, counter)
+    torch.cuda.synchronize()
+    assert torch.equal(pv, pv_ref), "valid plane differs"
+    a, b = plane.float().cpu().numpy(), plane_ref.float().cpu().numpy()
+    ne = a != b
+    print(f"G={G} V={V}: valid cells {int(pv_ref.sum())}, differing elements {ne.mean():.5%}, rel_l2 {rel_l2(a, b):.2e}")
+    assert ne.mean() < 2e-3 and rel_l2(a, b) < 1e-3
+    assert np.abs(a - b).max() <= 2.0 ** -6 * np.abs(b).max()
