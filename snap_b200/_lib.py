@@ -29,6 +29,7 @@ class GemmParams(C.Structure):
         ("rm_c0", C.c_int), ("rm_Ho", C.c_int), ("rm_Wo", C.c_int),
         ("bn", C.c_int),
         ("gn_acc", C.c_void_p), ("gn_acc_relu", C.c_void_p), ("gn_rows_per_img", C.c_longlong),
+        ("gn_replica_stride", C.c_int),
     ]
 
 
@@ -93,6 +94,6 @@ EXPORTED_SYMBOLS += [
     "snapb200_std_weights_batched", "snapb200_root_im2col", "snapb200_maxpool3x3s2",
     "snapb200_gn_stats", "snapb200_gn_apply", "snapb200_upsample2x",
     "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_lift_fused", "snapb200_vertical_max", "snapb200_match_head",
-    "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_rot_templates",
+    "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_xcorr_padded_rotations", "snapb200_rot_templates",
     "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores",
 ]

@@ -254,57 +254,74 @@ enum { LAYOUT_DENSE = 0, LAYOUT_PADDED = 1, LAYOUT_PHASE = 2 };
 // over pixels; consecutive threads -> consecutive 16 B chunks (coalesced).
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int C,
-                const double* __restrict__ acc, const float* __restrict__ scale,
+                const double* __restrict__ acc, int replica_stride, const float* __restrict__ scale,
                 const float* __restrict__ bias, int pre_relu, int post_relu, int layout,
                 int pix_per_block, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_sub) {
   const int CV = C / 8;
   const int PL = 256 / CV;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  if (pl >= PL) return;
   const int n = blockIdx.y;
   const int HW = H * W;
   const int c0 = cv * 8;
   const int cpg = C / 32;
-  const double count = (double)HW * (double)cpg;
-  float mean[8], rstd[8], sc[8], bi[8];
+  // one double-precision finalisation per group and CTA (mean, 1/sqrt(var + eps)), shared through smem
+  __shared__ float2 s_stat[32];
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    const double count = (double)HW * (double)cpg;
+    double su = 0.0, sq = 0.0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
-    const double su = acc[((size_t)n * 32 + g) * 2], sq = acc[((size_t)n * 32 + g) * 2 + 1];
+    for (int rep = 0; rep < 8; ++rep) {  // SNAPB200_GN_REPLICAS copies, fixed summation order
+      su += acc[(size_t)rep * replica_stride + ((size_t)n * 32 + g) * 2];
+      sq += acc[(size_t)rep * replica_stride + ((size_t)n * 32 + g) * 2 + 1];
+    }
     const double mu = su / count;
     double var = sq / count - mu * mu;
     if (var < 0.0) var = 0.0;
-    mean[j] = (float)mu;
-    rstd[j] = (float)(1.0 / sqrt(var + 1e-5));
-    sc[j] = __ldg(scale + c0 + j);
-    bi[j] = __ldg(bias + c0 + j);
+    s_stat[g] = make_float2((float)mu, (float)(1.0 / sqrt(var + 1e-5)));
   }
+  __syncthreads();
+  if (pl >= PL) return;
+  float mean[8], rstd[8];
+  __nv_bfloat162 sc2[4], bi2[4];  // scale / bias as packed bf16 (they are bf16 parameters in the reference)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 st = s_stat[(c0 + j) / cpg];
+    mean[j] = st.x;
+    rstd[j] = st.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc2[j] = __floats2bfloat162_rn(__ldg(scale + c0 + 2 * j), __ldg(scale + c0 + 2 * j + 1));
+    bi2[j] = __floats2bfloat162_rn(__ldg(bias + c0 + 2 * j), __ldg(bias + c0 + 2 * j + 1));
+  }
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const __nv_bfloat16* xin = x + (size_t)n * HW * C + c0;
   const int Hq = H / 2 + 1, Wq = W / 2 + 1;
-#pragma unroll 2
+#pragma unroll 4
   for (int p = p0 + pl; p < p1; p += PL) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)p * C));
     const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
+    uint32_t ov[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 t = unpack_bf16(uu[j]);
-      f[2 * j] = t.x;
-      f[2 * j + 1] = t.y;
+      float2 t = unpack_bf16(uu[j]);
+      if (pre_relu) {
+        t.x = fmaxf(t.x, 0.f);
+        t.y = fmaxf(t.y, 0.f);
+      }
+      // resnet.py:39-41,57-69 with a bf16 dtype: standardise in fp32 -> bf16, * scale -> bf16, + bias -> bf16.
+      // The two bf16 ops run as packed HMUL2/HADD2.BF16 (exact product / sum, one rounding each).
+      __nv_bfloat162 v = __floats2bfloat162_rn((t.x - mean[2 * j]) * rstd[2 * j],
+                                               (t.y - mean[2 * j + 1]) * rstd[2 * j + 1]);
+      v = __hmul2_rn(v, sc2[j]);  // _rn: never contracted into an FMA (two roundings, like the reference)
+      v = __hadd2_rn(v, bi2[j]);
+      if (post_relu) v = __hmax2(v, zero2);
+      ov[j] = *reinterpret_cast<uint32_t*>(&v);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = pre_relu ? fmaxf(f[j], 0.f) : f[j];
-      // resnet.py:39-41,57-69 with a bf16 dtype: standardise in fp32 -> bf16, * scale -> bf16, + bias -> bf16
-      v = bf16_round((v - mean[j]) * rstd[j]);
-      v = bf16_round(v * sc[j]);
-      v = bf16_round(v + bi[j]);
-      f[j] = post_relu ? fmaxf(v, 0.f) : v;
-    }
-    const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                               pack_bf16(f[6], f[7]));
+    const uint4 o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
     const int h = p / W, w = p - h * W;
     size_t orow;
     if (layout == LAYOUT_DENSE) {
@@ -461,20 +478,21 @@ int snapb200_gn_stats(const void* x, int Nimg, int HW, int C, int pre_relu, doub
    accumulators acc[img][g] = (sum, sumsq) (eps 1e-5, resnet.py:34-70), written in `layout`
    (0 dense [Nimg*H*W, C]; 1 zero-bordered [Nimg,(H+2),(W+2),C]; 2 phase-split);
    out_sub (optional) additionally receives the even-pixel subsample, dense [Nimg,H/2,W/2,C]. */
-int snapb200_gn_apply(const void* x, int Nimg, int H, int W, int C, const double* acc,
+int snapb200_gn_apply(const void* x, int Nimg, int H, int W, int C, const double* acc, int replica_stride,
                       const float* scale, const float* bias, int pre_relu, int post_relu, int layout,
                       void* out, void* out_sub, void* stream) {
   SNAP_REQUIRE(x && acc && scale && bias && out, "null pointer");
+  SNAP_REQUIRE(replica_stride >= Nimg * 64, "replica_stride must cover [Nimg][32][2] doubles");
   SNAP_REQUIRE(C % 64 == 0 && C <= 2048, "C must be a multiple of 64, <= 2048");
   SNAP_REQUIRE(layout >= 0 && layout <= 2, "bad layout");
   SNAP_REQUIRE((layout != LAYOUT_PHASE && out_sub == nullptr) || (H % 2 == 0 && W % 2 == 0),
                "phase / subsampled layouts need even H, W");
   const int HW = H * W;
-  int ppb = 16 * (256 / (C / 8));  // 16 pixels per thread lane
+  int ppb = 8 * (256 / (C / 8));  // 8 pixels per thread lane
   if (ppb > HW) ppb = HW;
   dim3 grid((HW + ppb - 1) / ppb, Nimg);
   gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, Nimg, H, W, C, acc, scale, bias, pre_relu, post_relu, layout, ppb,
+      (const __nv_bfloat16*)x, Nimg, H, W, C, acc, replica_stride, scale, bias, pre_relu, post_relu, layout, ppb,
       (__nv_bfloat16*)out, (__nv_bfloat16*)out_sub);
   return check_launch("gn_apply_kernel");
 }

@@ -5,27 +5,39 @@
 namespace snapb200 {
 
 template <int BN, int BK>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int ctas_per_sm,
                        cudaStream_t s) {
   using Cfg = GemmCfg<BN, BK>;
   static bool configured = false;
   if (!configured) {
     int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES),
+                                             Cfg::smem_bytes(Cfg::MAX_STAGES)),
                         "cudaFuncSetAttribute(gemm_tc)");
     if (rc) return rc;
     configured = true;
   }
+  // occupancy plan: `ctas_per_sm` co-resident CTAs share the SM's 227 KB of shared memory and 512 TMEM
+  // columns; memory-bound layers (small K) want several CTAs so that epilogues overlap main loops
+  int max_by_tmem = 512 / Cfg::TMEM_COLS;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > max_by_tmem) ctas_per_sm = max_by_tmem;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;  // register budget: __launch_bounds__(320, 2)
+  int stages = p.nkb < Cfg::MAX_STAGES ? p.nkb : Cfg::MAX_STAGES;
+  if (stages < 2) stages = 2;
+  while (stages > 2 && ctas_per_sm * Cfg::smem_bytes(stages) > 225 * 1024) --stages;
+  while (ctas_per_sm > 1 && ctas_per_sm * Cfg::smem_bytes(stages) > 225 * 1024) --ctas_per_sm;
+  p.stages = stages;
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, BK><<<grid, 192, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  const int cap = num_sms() * ctas_per_sm;
+  const int grid = total < cap ? total : cap;
+  gemm_tc_kernel<BN, BK><<<grid, GEMM_THREADS, Cfg::smem_bytes(stages), s>>>(tmA, tmB, p);
   return check_launch("gemm_tc_kernel");
 }
 
 int launch_gemm(const void* A, long long a_rows, int a_cols, long long a_ld, const void* B,
                 long long b_rows, int b_cols, long long b_ld, int bn, int bk, const GemmParams& p,
-                cudaStream_t s) {
+                cudaStream_t s, int ctas_per_sm) {
   SNAP_REQUIRE(p.m_tiles > 0 && p.n_tiles > 0 && p.nkb > 0, "empty GEMM");
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d_bf16(&tmA, A, a_rows, a_cols, a_ld, 128, bk);
@@ -33,7 +45,7 @@ int launch_gemm(const void* A, long long a_rows, int a_cols, long long a_ld, con
   rc = make_tmap_2d_bf16(&tmB, B, b_rows, b_cols, b_ld, bn, bk);
   if (rc) return rc;
 #define SNAP_GEMM_CASE(BN_, BK_) \
-  if (bn == BN_ && bk == BK_) return launch_inst<BN_, BK_>(tmA, tmB, p, s);
+  if (bn == BN_ && bk == BK_) return launch_inst<BN_, BK_>(tmA, tmB, p, ctas_per_sm, s);
   SNAP_GEMM_CASE(16, 64)
   SNAP_GEMM_CASE(64, 64)
   SNAP_GEMM_CASE(128, 64)
@@ -55,6 +67,18 @@ int pick_bn(int n, int bk) {
   return 256;
 }
 
+// Tile-shape / occupancy heuristic for the conv & dense layers (M = pixels is large, N = channels):
+// K >= 1024 and N >= 256 are tensor-bound -> 128x256 tiles, one CTA per SM, deep pipeline;
+// everything else is bound by streaming A / the output -> 128x128 (or 128x64) tiles, 2-3 CTAs per SM.
+void pick_config(int n, int k_total, int bk, int* bn, int* ctas_per_sm) {
+  if (bk == 64 && n == 160) { *bn = 160; *ctas_per_sm = 1; return; }
+  if (n <= 16 && bk == 64) { *bn = 16; *ctas_per_sm = 2; return; }
+  if (n <= 64) { *bn = 64; *ctas_per_sm = 3; return; }
+  if (k_total >= 1024 && n >= 256) { *bn = 256; *ctas_per_sm = 1; return; }
+  *bn = 128;
+  *ctas_per_sm = 2;
+}
+
 }  // namespace snapb200
 
 using namespace snapb200;
@@ -70,7 +94,12 @@ extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
   SNAP_REQUIRE(q->ldo % 8 == 0, "ldo must be a multiple of 8");
   SNAP_REQUIRE(q->residual == nullptr || q->ldr % 8 == 0, "ldr must be a multiple of 8");
   const int bk = (q->seg_k % 64 == 0) ? 64 : 32;
-  const int bn = q->bn > 0 ? q->bn : pick_bn(q->n, bk);
+  int bn = 0, ctas = 1;
+  pick_config(q->n, q->num_seg * q->seg_k, bk, &bn, &ctas);
+  if (q->bn > 0) {
+    bn = q->bn;
+    ctas = bn <= 64 ? 3 : (bn <= 128 ? 2 : 1);
+  }
   GemmParams p = {};
   p.m_tiles = (int)((q->m_rows + 127) / 128);
   p.n_tiles = (q->n + bn - 1) / bn;
@@ -103,13 +132,15 @@ extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
   p.gn_acc_relu = q->gn_acc_relu;
   p.gn_rows_per_img = q->gn_rows_per_img;
   p.gn_cpg = q->n / 32;
+  p.gn_replica_stride = q->gn_replica_stride;
   if (q->gn_acc != nullptr) {
     SNAP_REQUIRE(q->n % 64 == 0 && q->gn_rows_per_img > 0, "gn_acc needs n %% 64 == 0 and gn_rows_per_img");
+    SNAP_REQUIRE(q->gn_replica_stride > 0, "gn_replica_stride (doubles between accumulator replicas) required");
     SNAP_REQUIRE(!q->out_f32 && q->bias == nullptr && !q->relu && q->row_mask == nullptr,
                  "gn_acc is only defined for plain bf16 conv outputs (optional residual)");
   }
   SNAP_REQUIRE(q->gn_acc_relu == nullptr || q->gn_acc != nullptr, "gn_acc_relu needs gn_acc");
   if (q->remap) SNAP_REQUIRE(q->rm_R > 0 && q->rm_C > 0 && q->rm_Ho > 0 && q->rm_Wo > 0, "bad remap");
   return launch_gemm(q->a, q->a_rows, q->a_cols, q->a_ld, q->b, q->b_rows, q->b_cols, q->b_ld, bn,
-                     bk, p, static_cast<cudaStream_t>(stream));
+                     bk, p, static_cast<cudaStream_t>(stream), ctas);
 }

@@ -19,8 +19,10 @@ namespace snapb200 {
 enum { SEG_TABLE = 0, SEG_XCORR = 1 };
 enum { TILE_LINEAR = 0, TILE_XCORR = 1 };
 enum { EPI_STORE = 0, EPI_XCORR = 1 };
+constexpr int GN_REPLICAS = 8;  // independent accumulator copies; consumers sum them
 
 struct GemmParams {
+  int stages;       // smem pipeline depth (2..GemmCfg::MAX_STAGES), chosen by the host per layer
   int m_tiles, n_tiles;
   int nkb;          // K blocks per tile (= num_seg * kps)
   int kps;          // K blocks per segment
@@ -28,6 +30,7 @@ struct GemmParams {
   int a_col0;       // first A column (elements)
   int seg_mode;
   int seg_off[9];   // SEG_TABLE: A row offset of each segment
+  int b_seg_rows;   // 0: B = [N, segments*K] (K-major rows); > 0: B = [segment][b_seg_rows][K] row blocks
   // SEG_XCORR / TILE_XCORR geometry
   int xc_G, xc_P, xc_U, xc_vt, xc_R;
   long long xc_rows_per_b;
@@ -51,11 +54,15 @@ struct GemmParams {
   double* gn_acc_relu;
   long long gn_rows_per_img;
   int gn_cpg;  // channels per group = N / 32
+  int gn_replica_stride;  // doubles between the GN_REPLICAS copies of the accumulator (contention spreading)
   // EPI_XCORR
   const float* xc_cnt;
   const float* xc_den;
   float xc_thr;
 };
+
+constexpr int GEMM_EPI_WARPS = 8;                       // two per TMEM lane quadrant
+constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;  // 320
 
 template <int BN, int BK>
 struct GemmCfg {
@@ -64,18 +71,18 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int MAX_STAGES = STAGES_RAW > 16 ? 16 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32)    ? 32
                                    : (2 * BN <= 64)  ? 64
                                    : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
-  // +1024 for manual alignment, +256 for barriers / tmem pointer
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  // +1024 for manual alignment, +512 for barriers (2 x 16 stage + 4 accumulator) / tmem pointer
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 512; }
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(BK == 64 || BK == 32, "BK is one swizzle span: 128B or 64B of bf16");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage tiles must stay 1024B aligned");
-  static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(MAX_STAGES >= 2, "need at least a double buffer");
 };
 
 struct TileCoord {
@@ -96,7 +103,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
     int u = (t.mt / p.xc_vt) % p.xc_U;
     int b = t.mt / (p.xc_vt * p.xc_U);
     t.a_row = (int)(b * p.xc_rows_per_b) + u * p.xc_P + vt * 128;
-    t.b_row = b * p.xc_R + t.nt * bn;
+    t.b_row = p.b_seg_rows == 0 ? b * p.xc_R + t.nt * bn : b * p.xc_G * p.xc_G * p.b_seg_rows + t.nt * bn;
   }
   return t;
 }
@@ -154,11 +161,11 @@ __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool row_o
 }
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, BK>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -171,6 +178,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // contiguous tile range per CTA (same image / same A rows stay together: L2 locality, fewer GN flushes)
+  const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -181,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -196,18 +206,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile, BN);
+        int seg = 0, kc = 0, xi = 0, xj = 0;  // (xi, xj): window shift of the SEG_XCORR segment
         for (int kb = 0; kb < p.nkb; ++kb) {
-          const int seg = kb / p.kps;
-          const int kc = kb - seg * p.kps;
+          const int a_off = p.seg_mode == SEG_TABLE ? p.seg_off[seg] : xi * p.xc_P + xj;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          tma_load_2d(&tmA, &full_bar[stage], sa, p.a_col0 + kc * BK,
-                      t.a_row + seg_row_offset(p, seg));
-          tma_load_2d(&tmB, &full_bar[stage], sb, seg * p.seg_kstride + kc * BK, t.b_row);
+          tma_load_2d(&tmA, &full_bar[stage], sa, p.a_col0 + kc * BK, t.a_row + a_off);
+          if (p.b_seg_rows == 0)
+            tma_load_2d(&tmB, &full_bar[stage], sb, seg * p.seg_kstride + kc * BK, t.b_row);
+          else  // B stored segment-major: [segment][rows][BK] (contiguous tile per segment)
+            tma_load_2d(&tmB, &full_bar[stage], sb, kc * BK, t.b_row + seg * p.b_seg_rows);
+          if (++kc == p.kps) {
+            kc = 0;
+            ++seg;
+            if (++xj == p.xc_G) {
+              xj = 0;
+              ++xi;
+            }
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -223,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -255,10 +275,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q = warp & 3;         // TMEM lane quadrant this warp may access
+    const int hw = (warp - 2) >> 2;  // 0/1: which half of the 16-column chunks (interleaved) it drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const TileCoord t = decode_tile(p, tile, BN);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -280,7 +301,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                    c < p.rm_c0 + p.rm_Wo;
           orow = (img * p.rm_Ho + (r - p.rm_r0)) * p.rm_Wo + (c - p.rm_c0);
         }
-        const bool keep = row_ok && (p.row_mask == nullptr || p.row_mask[row_ok ? orow : 0] != 0);
+        if (!row_ok) orow = 0;
+        const bool keep = row_ok && (p.row_mask == nullptr || p.row_mask[orow] != 0);
         int gn_img = -1, gn_ref = -1;
         bool gn_uniform = true;
         if (p.gn_acc != nullptr) {
@@ -288,86 +310,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           gn_ref = __reduce_max_sync(0xffffffffu, gn_img);
           gn_uniform = __all_sync(0xffffffffu, gn_img == gn_ref || gn_img == -1);
         }
-#pragma unroll 1
-        for (int c16 = 0; c16 < BN / 16; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
-          tmem_ld_wait();
+        const bool rnd = !p.out_f32;
+        const bool has_res = p.residual != nullptr;
+        const __nv_bfloat16* res_row = has_res ? p.residual + orow * p.ldr : nullptr;
+
+        // One 16-column chunk: all roundings the reference applies (dot -> dtype, + bias -> dtype,
+        // + residual -> dtype), fused GroupNorm statistics of exactly what is stored, then the store.
+        auto process = [&](const uint32_t (&v)[16], const uint4& r0, const uint4& r1, int c16) {
           const int col = n0 + c16 * 16;
-          if (p.gn_acc != nullptr && col < p.N) {
-            // statistics of exactly what is stored (all roundings applied); warp-collective
-            float g[16];
+          if (col >= p.N) return;  // warp-uniform
+          float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = bf16_round(__uint_as_float(v[j]));
-            if (p.residual && row_ok) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
-              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          for (int j = 0; j < 16; ++j) f[j] = rnd ? bf16_round(__uint_as_float(v[j])) : __uint_as_float(v[j]);
+          if (p.bias) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 x = unpack_bf16(rr[j]);
-                g[2 * j] = bf16_round(g[2 * j] + x.x);
-                g[2 * j + 1] = bf16_round(g[2 * j + 1] + x.y);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j4);
+              const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x = f[j4 * 4 + e] + bs[e];
+                f[j4 * 4 + e] = rnd ? bf16_round(x) : x;
               }
-            }
-            gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc, gn_uniform, gn_ref, lane);
-            if (p.gn_acc_relu != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) g[j] = fmaxf(g[j], 0.f);
-              gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc_relu, gn_uniform, gn_ref, lane);
             }
           }
-          if (row_ok && col < p.N) {
-            float f[16];
+          if (has_res) {
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            // The reference materialises every op output in the compute dtype (bf16): conv/dot result,
-            // then "+ bias", then "+ residual".  Round at the same points when the output is bf16.
-            const bool rnd = !p.out_f32;
-            if (rnd) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = bf16_round(f[j]);
+            for (int j = 0; j < 8; ++j) {
+              const float2 x = unpack_bf16(rr[j]);
+              f[2 * j] += x.x;
+              f[2 * j + 1] += x.y;
             }
-            if (p.bias) {
+          }
+          if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                f[j] += __ldg(p.bias + col + j);
-                if (rnd) f[j] = bf16_round(f[j]);
-              }
-            }
-            if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col);
-              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (!keep) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 x = unpack_bf16(rr[j]);
-                f[2 * j] += x.x;
-                f[2 * j + 1] += x.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (!keep) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = 0.f;
-            }
-            if (p.out_f32) {
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+          }
+          if (p.out_f32) {
+            if (row_ok) {
               float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + col);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) +
-                                                   orow * p.ldo + col);
-              op[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
-                                 pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-              op[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]),
-                                 pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+            }
+            return;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+          if (row_ok) {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col);
+            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (p.gn_acc != nullptr) {
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 x = unpack_bf16(pk[j]);  // the stored (rounded) values
+              g[2 * j] = x.x;
+              g[2 * j + 1] = x.y;
+            }
+            const size_t rep = (size_t)(blockIdx.x % GN_REPLICAS) * p.gn_replica_stride;
+            gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc + rep, gn_uniform, gn_ref, lane);
+            if (p.gn_acc_relu != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) g[j] = fmaxf(g[j], 0.f);
+              gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc_relu + rep, gn_uniform, gn_ref, lane);
             }
           }
+        };
+        auto load_res = [&](int c16, uint4& r0, uint4& r1) {
+          const int col = n0 + c16 * 16;
+          if (has_res && row_ok && col < p.N) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_row + col);
+            r0 = __ldg(rp);
+            r1 = __ldg(rp + 1);
+          }
+        };
+        // software pipeline over this warp's chunks (hw, hw+2, ...): the TMEM load and the residual
+        // load of the next chunk are in flight while the current chunk is processed
+        constexpr int NCH = BN / 16;
+        uint32_t va[16], vb[16];
+        uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+        int c = hw;
+        if (c < NCH) {
+          tmem_ld16(taddr + (uint32_t)(c * 16), va);
+          load_res(c, ra0, ra1);
+        }
+#pragma unroll 1
+        while (c < NCH) {
+          tmem_ld_wait();
+          if (c + 2 < NCH) {
+            tmem_ld16(taddr + (uint32_t)((c + 2) * 16), vb);
+            load_res(c + 2, rb0, rb1);
+          }
+          process(va, ra0, ra1, c);
+          c += 2;
+          if (c >= NCH) break;
+          tmem_ld_wait();
+          if (c + 2 < NCH) {
+            tmem_ld16(taddr + (uint32_t)((c + 2) * 16), va);
+            load_res(c + 2, ra0, ra1);
+          }
+          process(vb, rb0, rb1, c);
+          c += 2;
         }
       } else {
         // EPI_XCORR: tile = (example b, shift row u, 128 shift columns); column n = rotation r.
@@ -378,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool row_ok = vv < p.xc_U;
         float* outp = static_cast<float*>(p.out);
 #pragma unroll 1
-        for (int c16 = 0; c16 < BN / 16; ++c16) {
+        for (int c16 = hw; c16 < BN / 16; c16 += 2) {
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
           tmem_ld_wait();

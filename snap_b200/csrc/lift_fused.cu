@@ -188,6 +188,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const int half = lane >> 4, c8 = lane & 15;
     const float score_scale = (float)(P.S - 1);
     uint32_t tile_phase = 0;
+    int n_tiles = 0, n_rows = 0;  // work counters (reported through col_counter[1..2])
     int zm_col = -1;       // z-max carry of thread wtid < 128 (one output channel each)
     float zm_val = 0.f;
 
@@ -438,7 +439,13 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         ctl->list_head = (head + rows) % FL_LIST_CAP;
         ctl->list_count -= rows;
       }
+      n_tiles += 1;
+      n_rows += rows;
       tile_phase ^= 1;
+    }
+    if (wtid == 0) {
+      atomicAdd(A.col_counter + 1, n_tiles);
+      atomicAdd(A.col_counter + 2, n_rows);
     }
     if (wtid < 128 && zm_col >= 0) {
       A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
@@ -491,7 +498,7 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
   if (rc) return rc;
   rc = check_cuda(cudaMemsetAsync(pvalid, 0, (size_t)cells, s), "memset valid");
   if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(col_counter, 0, sizeof(int), s), "memset counter");
+  rc = check_cuda(cudaMemsetAsync(col_counter, 0, 4 * sizeof(int), s), "memset counter");
   if (rc) return rc;
   FusedArgs a;
   memcpy(&a.P, q, sizeof(LiftParams));

@@ -30,14 +30,14 @@ __device__ __forceinline__ void rot90_src(int k, int G, int a, int b, int& i, in
   }
 }
 
-__global__ void rot_templates_kernel(const __grid_constant__ RotParams RP,
+__global__ void rot_templates_kernel(const __grid_constant__ RotParams RP_,
                                      const __nv_bfloat16* __restrict__ feats,
                                      const uint8_t* __restrict__ valid, const float* __restrict__ conf,
-                                     const float* __restrict__ centers, float cell, int B, int R, int G,
-                                     int D, __nv_bfloat16* __restrict__ templates,
+                                     const float* __restrict__ centers, float cell, int B, int R, int RP,
+                                     int G, int D, __nv_bfloat16* __restrict__ templates,
                                      uint8_t* __restrict__ t_valid) {
   const int dv = D / 8;
-  const long long total = (long long)B * R * G * G * dv;
+  const long long total = (long long)B * RP * G * G * dv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c8 = (int)(idx % dv);
@@ -46,13 +46,19 @@ __global__ void rot_templates_kernel(const __grid_constant__ RotParams RP,
   rest /= G;
   const int aa = (int)(rest % G);
   rest /= G;
-  const int r = (int)(rest % R);
-  const int b = (int)(rest / R);
-  const int k = r / RP.nq, r0 = r - k * RP.nq;
+  const int r = (int)(rest % RP);
+  const int b = (int)(rest / RP);
+  // templates are stored cell-major for the correlation GEMM: [b][a*G+bb][r (padded to RP)][D]
+  const size_t trow = (((size_t)b * G + aa) * G + bb) * RP + r;
+  if (r >= R) {  // zero padding rows of the B operand
+    *reinterpret_cast<uint4*>(templates + trow * D + c8 * 8) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int k = r / RP_.nq, r0 = r - k * RP_.nq;
   int i, j;
   rot90_src(k, G, aa, bb, i, j);
   // templates_xy = t + R(angle) @ grid_xy (snap/utils/geometry.py:138-140 order), uv = xy / cell
-  const float cs = RP.rot[r0][0], sn = RP.rot[r0][1], tx = RP.rot[r0][2], ty = RP.rot[r0][3];
+  const float cs = RP_.rot[r0][0], sn = RP_.rot[r0][1], tx = RP_.rot[r0][2], ty = RP_.rot[r0][3];
   const float x = centers[i], y = centers[j];
   const float ux = __fdiv_rn(__fadd_rn(tx, __fadd_rn(__fmul_rn(cs, x), __fmul_rn(-sn, y))), cell);
   const float uy = __fdiv_rn(__fadd_rn(ty, __fadd_rn(__fmul_rn(sn, x), __fmul_rn(cs, y))), cell);
@@ -87,7 +93,7 @@ __global__ void rot_templates_kernel(const __grid_constant__ RotParams RP,
       }
   }
   const size_t o = (((size_t)b * R + r) * G + aa) * G + bb;
-  *reinterpret_cast<uint4*>(templates + o * D + c8 * 8) =
+  *reinterpret_cast<uint4*>(templates + trow * D + c8 * 8) =
       make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
                  pack_bf16(acc[6], acc[7]));
   if (c8 == 0) t_valid[o] = ok ? 1 : 0;
@@ -193,6 +199,9 @@ using namespace snapb200;
 
 extern "C" {
 
+/* rows per cell of the template tensor: R rounded up to the N tile (48) of the correlation GEMM */
+int snapb200_xcorr_padded_rotations(int R) { return (R + 47) / 48 * 48; }
+
 int snapb200_xcorr_padded_cols(int G) {
   const int U = 2 * G - 1;
   const int vt = (U + 127) / 128;
@@ -209,9 +218,10 @@ int snapb200_rot_templates(const void* feats, const uint8_t* valid, const float*
   RP.nq = R / 4;
   for (int i = 0; i < RP.nq; ++i)
     for (int j = 0; j < 4; ++j) RP.rot[i][j] = rot_host[i * 4 + j];
-  const long long total = (long long)B * R * G * G * (D / 8);
+  const int RPad = snapb200_xcorr_padded_rotations(R);
+  const long long total = (long long)B * RPad * G * G * (D / 8);
   rot_templates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      RP, (const __nv_bfloat16*)feats, valid, conf, centers, cell_size, B, R, G, D,
+      RP, (const __nv_bfloat16*)feats, valid, conf, centers, cell_size, B, R, RPad, G, D,
       (__nv_bfloat16*)templates, t_valid);
   return check_launch("rot_templates_kernel");
 }
@@ -264,8 +274,10 @@ int snapb200_xcorr_scores(const void* templates, const void* m_pad, const float*
   p.xc_vt = (U + 127) / 128;
   p.xc_R = R;
   p.xc_rows_per_b = (long long)Prows * Pal;
+  const int RPad = snapb200_xcorr_padded_rotations(R);
+  p.b_seg_rows = RPad;
   p.m_tiles = B * U * p.xc_vt;
-  p.n_tiles = (R + bn - 1) / bn;
+  p.n_tiles = RPad / bn;
   p.nkb = G * G;
   p.kps = 1;
   p.seg_kstride = D;
@@ -278,8 +290,8 @@ int snapb200_xcorr_scores(const void* templates, const void* m_pad, const float*
   p.xc_den = den;
   p.xc_thr = thr;
   SNAP_REQUIRE((long long)B * Prows * Pal < (1ll << 31), "padded map too large for 32-bit TMA rows");
-  return launch_gemm(m_pad, (long long)B * Prows * Pal, D, D, templates, (long long)B * R, G * G * D,
-                     (long long)G * G * D, bn, 32, p, (cudaStream_t)stream);
+  return launch_gemm(m_pad, (long long)B * Prows * Pal, D, D, templates, (long long)B * G * G * RPad, D, D, bn, 32,
+                     p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -160,10 +160,10 @@ class EncoderPlan:
         self.buf_a = torch.zeros(max_rows_c + 128 * 2048, dtype=torch.bfloat16, device=device)  # gn1 / gn3 outputs
         self.buf_y = torch.zeros(max_rows_c + 128 * 2048, dtype=torch.bfloat16, device=device)  # conv1 / conv2 outputs
         self.buf_res = torch.zeros(max_rows_c + 128 * 2048, dtype=torch.bfloat16, device=device)
-        # GroupNorm accumulators (sum, sumsq) f64 [slot, img, 32, 2]: 3 per unit (gn1 input, conv1 out, conv2 out),
+        # GroupNorm accumulators (sum, sumsq) f64 [slot, replica, img, 32, 2]: 3 per unit (gn1 input, conv1 out, conv2 out),
         # one per FPN level (statistics of relu(stage output)), one scratch; zeroed once per forward.
-        self.gn_acc_all = torch.zeros((3 * len(self.units) + len(blocks) + 1, n_img, 32, 2), dtype=torch.float64,
-                                      device=device)
+        self.gn_acc_all = torch.zeros((3 * len(self.units) + len(blocks) + 1, ops.GN_REPLICAS, n_img, 32, 2),
+                                      dtype=torch.float64, device=device)
         for i, u in enumerate(self.units):
             u["acc"] = [self.gn_acc_all[3 * i + k] for k in range(3)]
         self.fpn_acc = [self.gn_acc_all[3 * len(self.units) + k] for k in range(len(blocks))]

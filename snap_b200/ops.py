@@ -47,7 +47,7 @@ def gemm(
     relu: bool = False,
     remap: Optional[Sequence[int]] = None,   # (R, C, r0, c0, Ho, Wo)
     bn: int = 0,
-    gn_acc: Optional[torch.Tensor] = None,       # f64 [n_img, 32, 2] accumulators (zeroed by the caller)
+    gn_acc: Optional[torch.Tensor] = None,       # f64 [GN_REPLICAS, n_img, 32, 2] accumulators (zeroed by the caller)
     gn_acc_relu: Optional[torch.Tensor] = None,
     gn_rows_per_img: int = 0,
 ) -> torch.Tensor:
@@ -90,7 +90,8 @@ def gemm(
     p.bn = bn
     if gn_acc is not None:
         _require(gn_acc, torch.float64, "gn_acc")
-        p.gn_acc, p.gn_rows_per_img = _ptr(gn_acc), gn_rows_per_img
+        assert gn_acc.dim() == 4 and gn_acc.shape[0] == GN_REPLICAS and gn_acc.is_contiguous()
+        p.gn_acc, p.gn_rows_per_img, p.gn_replica_stride = _ptr(gn_acc), gn_rows_per_img, gn_acc.stride(0)
         if gn_acc_relu is not None:
             _require(gn_acc_relu, torch.float64, "gn_acc_relu")
             p.gn_acc_relu = _ptr(gn_acc_relu)
@@ -122,9 +123,14 @@ def maxpool3x3s2(x: torch.Tensor, n: int, H: int, W: int, Cc: int, y: torch.Tens
     _lib.check(_lib.lib().snapb200_maxpool3x3s2(C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(y)), _stream()))
 
 
+GN_REPLICAS = 8
+
+
 def gn_stats(x: torch.Tensor, n: int, hw: int, Cc: int, pre_relu: bool, acc: torch.Tensor) -> None:
-    """Accumulate raw GroupNorm statistics of x into acc f64 [n, 32, 2] (must be zeroed by the caller)."""
+    """Accumulate raw GroupNorm statistics of x into replica 0 of acc f64 [GN_REPLICAS, n, 32, 2]
+    (must be zeroed by the caller)."""
     _require(acc, torch.float64, "acc")
+    assert acc.dim() == 4 and acc.shape[0] == GN_REPLICAS
     _lib.check(_lib.lib().snapb200_gn_stats(C.c_void_p(_ptr(x)), n, hw, Cc, int(pre_relu),
                                             C.c_void_p(_ptr(acc)), _stream()))
 
@@ -136,7 +142,7 @@ def gn_apply(x: torch.Tensor, n: int, H: int, W: int, Cc: int, acc: torch.Tensor
              bias: torch.Tensor, pre_relu: bool, post_relu: bool, layout: int, out: torch.Tensor,
              out_sub: Optional[torch.Tensor] = None) -> None:
     _lib.check(_lib.lib().snapb200_gn_apply(
-        C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(acc)), C.c_void_p(_ptr(scale)),
+        C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(acc)), C.c_int(acc.stride(0)), C.c_void_p(_ptr(scale)),
         C.c_void_p(_ptr(bias)), int(pre_relu), int(post_relu), layout, C.c_void_p(_ptr(out)),
         C.c_void_p(_ptr(out_sub)), _stream()))
 
@@ -211,6 +217,10 @@ def xcorr_padded_cols(G: int) -> int:
     return int(_lib.lib().snapb200_xcorr_padded_cols(C.c_int(G)))
 
 
+def xcorr_padded_rotations(R: int) -> int:
+    return int(_lib.lib().snapb200_xcorr_padded_rotations(C.c_int(R)))
+
+
 def rot_templates(feats: torch.Tensor, valid: torch.Tensor, conf: Optional[torch.Tensor], rot_host,
                   centers: torch.Tensor, cell_size: float, R: int, templates: torch.Tensor,
                   t_valid: torch.Tensor) -> None:
@@ -238,7 +248,10 @@ def xcorr_count(t_valid: torch.Tensor, m_valid: torch.Tensor, cnt: torch.Tensor,
 
 def xcorr_scores(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optional[torch.Tensor],
                  den: Optional[torch.Tensor], thr: float, scores: torch.Tensor) -> None:
-    B, R, G, _, D = templates.shape
+    """templates: cell-major bf16 [B, G, G, padded_rotations(R), D]; scores f32 [B, R, 2G-1, 2G-1]."""
+    B, G, _, RP, D = templates.shape
+    R = scores.shape[1]
+    assert RP == xcorr_padded_rotations(R)
     _require(scores, torch.float32, "scores")
     _lib.check(_lib.lib().snapb200_xcorr_scores(
         C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)),

@@ -44,24 +44,35 @@ def template_rotation_params(num_rotations: int, grid: types.Grid2D) -> np.ndarr
 
 def sample_query_templates(features: torch.Tensor, valid: torch.Tensor, num_rotations: int, grid: types.Grid2D,
                            conf_q: Optional[torch.Tensor] = None):
-    """`:37-69`, batched: features bf16 [B,G,G,D], valid u8 [B,G,G] -> templates [B,R,G,G,D], t_valid [B,R,G,G]."""
+    """`:37-69`, batched: features bf16 [B,G,G,D], valid u8 [B,G,G] -> templates, t_valid u8 [B,R,G,G].
+
+    Templates are returned CELL-MAJOR, bf16 [B, G, G, RP, D] with RP = R rounded up to a multiple of 48 (zero rows):
+    `templates[b, i, j, r]` is the reference's `templates[r, i, j]`; this is the B operand layout of the
+    correlation GEMM.  Use `templates_to_reference_layout` to get [B,R,G,G,D]."""
     if grid.extent[0] != grid.extent[1] or num_rotations % 4:
         raise ValueError("exhaustive voting needs a square grid and num_rotations % 4 == 0")  # SURVEY D10
     B, G, _, D = features.shape
     dev = features.device
     rot = template_rotation_params(num_rotations, grid)
     centers = torch.from_numpy(grid.cell_centers(0)).to(dev)
-    templates = torch.empty((B, num_rotations, G, G, D), dtype=torch.bfloat16, device=dev)
+    templates = torch.empty((B, G, G, ops.xcorr_padded_rotations(num_rotations), D), dtype=torch.bfloat16, device=dev)
     t_valid = torch.empty((B, num_rotations, G, G), dtype=torch.uint8, device=dev)
     ops.rot_templates(features.contiguous(), valid.contiguous(), conf_q, rot, centers, float(F(grid.cell_size)),
                       num_rotations, templates, t_valid)
     return templates, t_valid
 
 
+def templates_to_reference_layout(templates: torch.Tensor, num_rotations: int) -> torch.Tensor:
+    """cell-major [B,G,G,RP,D] -> the reference's [B,R,G,G,D]."""
+    return templates[:, :, :, :num_rotations].permute(0, 3, 1, 2, 4).contiguous()
+
+
 def template_matching(q: torch.Tensor, q_valid: torch.Tensor, m: torch.Tensor, m_valid: torch.Tensor,
                       min_overlap: Optional[float] = 0.05) -> torch.Tensor:
-    """`:72-104` (do_padding=True), batched: q bf16 [B,R,G,G,D], m bf16 [B,G,G,D] -> f32 [B,R,2G-1,2G-1]."""
-    B, R, G, _, D = q.shape
+    """`:72-104` (do_padding=True), batched: q = cell-major templates bf16 [B,G,G,RP,D], q_valid u8 [B,R,G,G],
+    m bf16 [B,G,G,D] -> f32 [B,R,2G-1,2G-1]."""
+    B, G, _, RP, D = q.shape
+    R = q_valid.shape[1]
     dev = q.device
     U = 2 * G - 1
     m_pad = torch.empty((B, 3 * G - 2, ops.xcorr_padded_cols(G), D), dtype=torch.bfloat16, device=dev)

@@ -106,7 +106,7 @@ class StreetViewEncoder:
             self._cache[key] = dict(
                 crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
                 volume=None, valid=None,   # [B,N,128] / [B,N]: allocated on first unfused call
-                plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 1, dt=torch.int32),
+                plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 4, dt=torch.int32),
                 # per-scene inputs: pinned host staging + device copies (a captured CUDA graph re-reads the
                 # staging buffers at every replay, see `stage_inputs`)
                 images_host=pin(B, V, H, W, 3, dt=torch.float32), images=z(B, V, H, W, 3, dt=torch.float32),
@@ -116,22 +116,15 @@ class StreetViewEncoder:
                 xs=None, ys=None)
         return self._cache[key]
 
-    def stage_inputs(self, data: Dict, buf: Dict, stride) -> bool:
-        """Host-only: write this batch's images (if they live on the host), voxel heights and camera/pose
-        tables into the pinned staging buffers.  Returns True if the images were staged from the host."""
+    def stage_inputs(self, data: Dict, buf: Dict, stride) -> None:
+        """Host-only: write this batch's voxel heights and camera/pose tables into the pinned staging buffers
+        (a captured CUDA graph re-reads them at every replay)."""
         xs, ys, zs = data["xyz_grid"]
         B = zs.shape[0]
         buf["zs_host"].copy_(torch.from_numpy(np.ascontiguousarray(zs, dtype=F)))
         for b in range(B):
             pack = pack_views(data["camera"], data["T_view2scene"], b, stride)
             buf["views_host"][b, : len(pack)].copy_(torch.from_numpy(pack))
-        images = data["images"]
-        if isinstance(images, np.ndarray):
-            images = torch.from_numpy(np.ascontiguousarray(images, dtype=F))
-        if not images.is_cuda:
-            buf["images_host"].copy_(images)
-            return True
-        return False
 
     def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False,
               fused: bool = False) -> Dict:
@@ -152,9 +145,14 @@ class StreetViewEncoder:
         buf = self._buffers(dev, B, V, H, W, hf, wf, X, Y, Z)
         if buf["xs"] is None:
             buf["xs"], buf["ys"] = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
-        from_host = self.stage_inputs(data, buf, stride)
-        if from_host:
-            buf["images"].copy_(buf["images_host"], non_blocking=True)
+        self.stage_inputs(data, buf, stride)
+        if isinstance(images, np.ndarray):
+            images = torch.from_numpy(np.ascontiguousarray(images, dtype=F))
+        if not images.is_cuda:   # host images: pinned -> direct async H2D, pageable -> via the pinned staging buffer
+            if not images.is_pinned():
+                buf["images_host"].copy_(images)
+                images = buf["images_host"]
+            buf["images"].copy_(images, non_blocking=True)
             images = buf["images"]
         buf["zs"].copy_(buf["zs_host"], non_blocking=True)
         buf["views"].copy_(buf["views_host"], non_blocking=True)

@@ -44,7 +44,7 @@ def test_gn_maxpool_upsample_im2col_vs_oracle():
         scale, bias = (1 + 0.3 * rng.standard_normal(c)).astype(F), (0.2 * rng.standard_normal(c)).astype(F)
         ref = torch.relu(ores.group_norm(_t(x), _t(scale), _t(bias))).numpy()
         xd = _t(x).to(torch.bfloat16).to(dev)
-        stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=dev)
+        stats = torch.zeros((8, n, 32, 2), dtype=torch.float64, device=dev)
         ops.gn_stats(xd, n, h * w, c, False, stats)
         dense = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=dev)
         sub = torch.zeros((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=dev)
@@ -72,7 +72,7 @@ def test_gn_maxpool_upsample_im2col_vs_oracle():
     scale, bias = (1 + 0.3 * rng.standard_normal(c)).astype(F), (0.2 * rng.standard_normal(c)).astype(F)
     ref = ores.group_norm(torch.relu(_t(x)), _t(scale), _t(bias)).numpy()
     xd = _t(x).to(torch.bfloat16).to(dev)
-    stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=dev)
+    stats = torch.zeros((8, n, 32, 2), dtype=torch.float64, device=dev)
     out = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=dev)
     ops.gn_stats(xd, n, h * w, c, True, stats)
     ops.gn_apply(xd, n, h, w, c, stats, _t(scale).to(dev), _t(bias).to(dev), True, False, ops.LAYOUT_DENSE, out)

@@ -105,8 +105,8 @@ def test_gemm_epilogue_groupnorm_accumulators(n, cpg_n):
     a, b = _rand((M, K), 21), _rand((n, K), 22, 0.2)
     res = _rand((M, n), 23)
     out = torch.zeros((M, n), dtype=torch.bfloat16, device="cuda")
-    acc = torch.zeros((n_img, 32, 2), dtype=torch.float64, device="cuda")
-    acc_relu = torch.zeros((n_img, 32, 2), dtype=torch.float64, device="cuda")
+    acc = torch.zeros((8, n_img, 32, 2), dtype=torch.float64, device="cuda")
+    acc_relu = torch.zeros((8, n_img, 32, 2), dtype=torch.float64, device="cuda")
     ops.gemm(a.cuda(), b.cuda(), out, residual=res.cuda(), gn_acc=acc, gn_acc_relu=acc_relu, gn_rows_per_img=rows_per_img)
     torch.cuda.synchronize()
     r = lambda t: t.to(torch.bfloat16).float()
@@ -115,5 +115,5 @@ def test_gemm_epilogue_groupnorm_accumulators(n, cpg_n):
     o = out.float().cpu().double().reshape(n_img, rows_per_img, 32, n // 32)
     for accd, x in ((acc, o), (acc_relu, o.clamp(min=0))):
         s, q = x.sum(dim=(1, 3)), (x * x).sum(dim=(1, 3))
-        assert torch.allclose(accd.cpu()[..., 0], s, rtol=1e-5, atol=1e-3)
-        assert torch.allclose(accd.cpu()[..., 1], q, rtol=1e-5, atol=1e-3)
+        assert torch.allclose(accd.cpu().sum(0)[..., 0], s, rtol=1e-5, atol=1e-3)
+        assert torch.allclose(accd.cpu().sum(0)[..., 1], q, rtol=1e-5, atol=1e-3)

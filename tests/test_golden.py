@@ -1,0 +1,109 @@
+"""The oracle (oracle/) against golden fixtures produced by the REFERENCE'S OWN source executed under a NumPy/SciPy
+stand-in for jax (tests/golden/make_golden.py, tests/golden/jaxshim).  Boolean / integer outputs must match exactly;
+floats to fp32 round-off (the stand-in evaluates some expressions in float64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry, grids, image_encoder as oie, layers, pose_exhaustive_voting as opv, resnet as ores
+from oracle import streetview_encoder as osv
+
+F = np.float32
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(G, name + ".npz")))
+
+
+def close(a, b, tol=2e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    assert np.array_equal(a[~fin], b[~fin], equal_nan=True)
+    scale = np.abs(b[fin]).max() + 1e-12 if fin.any() else 1.0
+    assert np.abs(a[fin] - b[fin]).max() <= tol * scale, np.abs(a[fin] - b[fin]).max() / scale
+
+
+def _setup():
+    g = load("geometry")
+    T = geometry.Transform3D(R=g["R"], t=g["t"])
+    cam = geometry.Camera(wh=g["wh"], f=g["f"], c=g["c"])
+    return g, T, cam
+
+
+def test_interpolate_nd():
+    d = load("interp")
+    v, ok = grids.interpolate_nd(d["arr"], d["pts"])
+    close(v, d["val"]); assert np.array_equal(ok, d["valid"])
+    _, ok2 = grids.interpolate_nd(d["arr"], d["pts"], d["mask"])
+    assert np.array_equal(ok2, d["valid_masked"])
+
+
+def test_geometry_and_projection():
+    g, T, cam = _setup()
+    Ti = T.inv
+    close(Ti.R, g["Rinv"], 1e-7); close(Ti.t, g["tinv"], 1e-6)
+    close(cam.scale(F([0.25, 0.25])).f, g["cam_scaled_f"], 1e-7)
+    p = load("project")
+    p2d, vis, depth, rays = osv.project_points_to_views(T, cam, g["pts"])
+    # visibility may only differ where a point sits within fp32 round-off of an image border / eps plane
+    margin = np.minimum.reduce([np.abs(p["p2d"][..., 0]), np.abs(p["p2d"][..., 1]),
+                                np.abs(p["p2d"][..., 0] - cam.wh[None, :, 1]), np.abs(p["p2d"][..., 1] - cam.wh[None, :, 0])])
+    strict = margin > 1e-3
+    assert np.array_equal(vis[strict], p["vis"][strict]) and (vis != p["vis"]).mean() < 1e-2
+    sel = p["vis"] & vis
+    close(p2d[sel], p["p2d"][sel], 1e-5); close(depth, p["depth"], 1e-5); close(rays, p["rays"], 1e-5)
+    pf = load("project_fisheye")
+    fcam = geometry.FisheyeCamera(wh=g["wh"], f=g["f"], c=g["c"], k_radial=g["k_radial"], max_fov=g["max_fov"])
+    p2df, visf, _, _ = osv.project_points_to_views(T, fcam, g["pts"])
+    assert (visf != pf["vis"]).mean() < 1e-2
+    sel = pf["vis"] & visf
+    close(p2df[sel], pf["p2d"][sel], 1e-4)
+
+
+def test_lift_pieces():
+    g, T, cam = _setup()
+    d = load("interp_views_all")
+    out = osv.interpolate_views_all(d["fimg"][0], d["p2d"])
+    close(out, d["out"][0])
+    ds = load("depth_score")
+    close(osv.interpolate_depth_score(ds["scales"][0], ds["depth"]), ds["out"][0])
+    for tag, use_scores, minmax in (("weighted", True, False), ("plain", False, False), ("minmax", True, True)):
+        pw = load("pool_" + tag)
+        base = load("pool_weighted")
+        st, va = osv.pool_multiview_features(base["feats"][0], base["valid"], ds["out"][0] if use_scores else None, minmax, True)
+        close(st, pw["stats"][0], 5e-5)
+        if "valid_any" in pw:
+            assert np.array_equal(va, pw["valid_any"][0])
+    vs = load("view_selection")
+    idx, md = osv.view_selection(g["pts"], T, load("pool_weighted")["valid"], 2)
+    assert np.array_equal(idx, vs["idx"][0]); close(md, vs["min_dist"][0])
+    sl = load("interp_views_selective")
+    close(osv.interpolate_views_selective(d["fimg"][0], sl["p2d"][0], sl["idx"][0]), sl["out"][0])
+
+
+def test_layers_resnet_pad():
+    d = load("normalize")
+    close(layers.normalize(d["x"]), d["out"], 1e-6)
+    s = load("standardize")
+    close(ores.standardize(torch.from_numpy(s["w"]), [0, 1, 2], 1e-10).numpy(), s["out"], 1e-5)
+    close(ores.standardize(torch.from_numpy(s["w"]).reshape(1, 3, 3, 5, 4), [1, 2, 4], 1e-5).numpy(), s["gn"], 1e-5)
+    p = load("pad")
+    for key, stride in (("p8", 8), ("p32", 32)):
+        assert np.array_equal(oie.pad_to_multiple(torch.from_numpy(p["img"]), stride).numpy(), p[key])
+
+
+def test_exhaustive_voting():
+    d = load("voting")
+    grid = grids.Grid2D((12, 12), 0.2)
+    t, tv = opv.sample_query_templates(d["fq"], d["vq"], 8, grid)
+    assert np.array_equal(tv, d["t_valid"]); close(t, d["templates"], 1e-5)
+    close(opv.template_matching(d["templates"], d["t_valid"], d["fm"], d["vm"]), d["scores"], 1e-5)
+    close(opv.exhaustive_pose_voting(d["fq"], d["vq"], d["fm"], d["vm"], 8, grid, d["conf"]), d["scores_conf"], 1e-5)
+    tf = opv.exhaustive_index_to_tfm(np.array([3, 14, 9]), grid, 8)
+    close(tf.angle, d["tfm_angle"], 1e-6); close(tf.t, d["tfm_t"], 1e-5)
+    close(opv.exhaustive_tfm_to_index(tf, grid, 8), d["index_back"], 1e-5)

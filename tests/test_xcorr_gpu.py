@@ -41,9 +41,11 @@ def test_templates_count_scores_vs_oracle(G, R):
     for b in range(B):
         ot, otv = opv.sample_query_templates(q[b], qv[b], R, ogrid)
         assert np.array_equal(t_valid[b].cpu().numpy().astype(bool), otv), "template validity must be bit-exact"
-        assert_close_bf16(templates[b].float().cpu().numpy(), ot, "templates")
+        tref = pv.templates_to_reference_layout(templates, R)
+        assert not templates[:, :, :, R:].any(), "padding rotations must be zero"
+        assert_close_bf16(tref[b].float().cpu().numpy(), ot, "templates")
         # scores on IDENTICAL bf16 templates: only the fp32 summation order differs
-        tb = templates[b].float().cpu().numpy()
+        tb = tref[b].float().cpu().numpy()
         ref = opv.template_matching(tb, otv, m[b], mv[b])
         got = scores[b].cpu().numpy()
         assert np.array_equal(np.isneginf(got), np.isneginf(ref)), "-inf (min-overlap) mask must be bit-exact"
@@ -91,7 +93,7 @@ def test_voting_full_size_properties():
     md, mvd = _t(m).to(torch.bfloat16).to(dev), torch.from_numpy(np.ones_like(mv).astype(np.uint8)).to(dev)
     templates, t_valid = pv.sample_query_templates(md, mvd, R, grid)
     # quadrant property (`pose_exhaustive_voting.py:63-68`): template k*R/4+r == rot90(template r, k, axes=(2,1))
-    tq = templates[0].float().cpu().numpy()
+    tq = pv.templates_to_reference_layout(templates, R)[0].float().cpu().numpy()
     for k in range(1, 4):
         assert np.array_equal(tq[k * (R // 4):(k + 1) * (R // 4)], np.rot90(tq[: R // 4], k, axes=(2, 1)))
     s1 = pv.template_matching(templates, t_valid, md, mvd)
