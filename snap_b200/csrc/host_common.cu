@@ -84,6 +84,27 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, long long rows, long l
   return SNAPB200_OK;
 }
 
+int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld,
+                            int box_rows, int box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  SNAP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SNAP_REQUIRE((ld * 2) % 16 == 0 && box_cols % 8 == 0, "TMA pitch / box width must be multiples of 16 bytes");
+  SNAP_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_cols <= 256, "box out of range");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled(plain) failed (%d) rows=%lld cols=%lld box=%dx%d",
+                     (int)r, rows, cols, box_rows, box_cols);
+  return SNAPB200_OK;
+}
+
 }  // namespace snapb200
 
 extern "C" {

@@ -21,6 +21,11 @@ void count_launch();
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, long long rows, long long cols,
                       long long ld, int box_rows, int box_cols);
 
+// same, but un-swizzled (INTERLEAVE_NONE / SWIZZLE_NONE) with an arbitrary 16-byte-multiple box width:
+// used to build the "8 rows x 16 B core matrix" K-major operand layout of the sliding-window correlation
+int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld,
+                            int box_rows, int box_cols);
+
 #define SNAP_REQUIRE(cond, ...)                                        \
   do {                                                                 \
     if (!(cond)) return set_error(SNAPB200_ERR_INVALID, __VA_ARGS__);  \

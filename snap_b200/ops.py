@@ -256,3 +256,18 @@ def xcorr_scores(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optional[tor
     _lib.check(_lib.lib().snapb200_xcorr_scores(
         C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)),
         C.c_void_p(_ptr(den)), B, R, G, D, C.c_float(thr), C.c_void_p(_ptr(scores)), _stream()))
+
+
+def xcorr_sw_supported(R: int, G: int) -> bool:
+    return xcorr_padded_rotations(R) == 48 and G % 4 == 0 and G <= 129
+
+
+def xcorr_scores_sw(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optional[torch.Tensor],
+                    den: Optional[torch.Tensor], thr: float, scores: torch.Tensor) -> None:
+    """Sliding-window variant of `xcorr_scores` (same arguments)."""
+    B, G, _, RP, D = templates.shape
+    R = scores.shape[1]
+    _require(scores, torch.float32, "scores")
+    _lib.check(_lib.lib().snapb200_xcorr_scores_sw(
+        C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)),
+        C.c_void_p(_ptr(den)), B, R, G, D, C.c_float(thr), C.c_void_p(_ptr(scores)), _stream()))

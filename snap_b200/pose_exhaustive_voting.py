@@ -68,7 +68,7 @@ def templates_to_reference_layout(templates: torch.Tensor, num_rotations: int) -
 
 
 def template_matching(q: torch.Tensor, q_valid: torch.Tensor, m: torch.Tensor, m_valid: torch.Tensor,
-                      min_overlap: Optional[float] = 0.05) -> torch.Tensor:
+                      min_overlap: Optional[float] = 0.05, kernel: str = "auto") -> torch.Tensor:
     """`:72-104` (do_padding=True), batched: q = cell-major templates bf16 [B,G,G,RP,D], q_valid u8 [B,R,G,G],
     m bf16 [B,G,G,D] -> f32 [B,R,2G-1,2G-1]."""
     B, G, _, RP, D = q.shape
@@ -82,7 +82,9 @@ def template_matching(q: torch.Tensor, q_valid: torch.Tensor, m: torch.Tensor, m
     ops.xcorr_count(q_valid.contiguous(), m_valid.contiguous(), cnt, den)
     scores = torch.empty((B, R, U, U), dtype=torch.float32, device=dev)
     thr = float(F(min_overlap * G * G)) if min_overlap is not None else 0.0
-    ops.xcorr_scores(q.contiguous(), m_pad, cnt if min_overlap is not None else None, den, thr, scores)
+    use_sw = kernel == "sw" or (kernel == "auto" and ops.xcorr_sw_supported(R, G))
+    fn = ops.xcorr_scores_sw if use_sw else ops.xcorr_scores
+    fn(q.contiguous(), m_pad, cnt if min_overlap is not None else None, den, thr, scores)
     return scores
 
 
