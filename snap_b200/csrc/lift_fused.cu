@@ -44,6 +44,18 @@ static_assert(sizeof(LiftView) * FL_MAXV <= 384, "view table");
 static_assert(FL_SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 constexpr int VOL_STRIDE = 272;           // bytes per staged volume row (256 + 16: conflict-free)
 
+// Per (visible voxel, view) gather record, written by the thread-per-voxel visibility pass and read by the
+// half-warp-per-voxel gather pass (global scratch, L2 resident): clamped tap indices, upper-tap weights,
+// depth-score bins.  32 bytes.
+struct TapRec {
+  uint16_t r0, r1, c0, c1;
+  float wr1, wc1;
+  float wb1;
+  uint16_t b0, b1;
+  uint32_t pad_[2];
+};
+static_assert(sizeof(TapRec) == 32, "TapRec layout");
+
 struct FusedArgs {
   LiftParams P;
   const LiftView* views;
@@ -55,6 +67,7 @@ struct FusedArgs {
   __nv_bfloat16* plane;
   uint8_t* pvalid;
   int* col_counter;   // zeroed by the host wrapper
+  TapRec* scratch;    // [gridDim.x][FL_LIST_CAP][FL_MAXV]
 };
 
 struct Ctl {  // lives at SM_BAR
@@ -185,7 +198,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const int q = warp & 3;              // TMEM lane quadrant this warp may touch
     const int sub = ww >> 2;             // which quarter of the accumulator columns it drains
     const int ncols = P.X * P.Y;
-    const int half = lane >> 4, c8 = lane & 15;
+    const int half = lane >> 4;
     const float score_scale = (float)(P.S - 1);
     uint32_t tile_phase = 0;
     int n_tiles = 0, n_rows = 0;  // work counters (reported through col_counter[1..2])
@@ -209,12 +222,17 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         if (wtid < FL_BATCH_COLS * 64) {
           const int cl = wtid >> 6, z = wtid & 63;
           const int col = ctl->batch_col0 + cl;
+          Proj pr[FL_MAXV];
+          uint32_t vm = 0;
           if (col < ncols && z < P.Z) {
             const int ix = col / P.Y, iy = col - ix * P.Y;
             const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
-            uint32_t vm = 0;
-            for (int v = 0; v < P.V; ++v)
-              if (project_point(sview[v], px, py, pz).vis) vm |= 1u << v;
+#pragma unroll
+            for (int v = 0; v < FL_MAXV; ++v) {
+              if (v >= P.V) break;
+              pr[v] = project_point(sview[v], px, py, pz);
+              if (pr[v].vis) vm |= 1u << v;
+            }
             valid = vm != 0;
             entry = ((uint32_t)col << 14) | ((uint32_t)z << 8) | vm;
           }
@@ -224,7 +242,29 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           if (valid) {
             int idx = ctl->list_count + __popc(bal & ((1u << lane) - 1u));
             for (int w2 = 0; w2 < ww; ++w2) idx += ctl->warp_cnt[w2];
-            list[(ctl->list_head + idx) % FL_LIST_CAP] = entry;
+            const int slot = (ctl->list_head + idx) % FL_LIST_CAP;
+            list[slot] = entry;
+            // gather records of the visible views (same tap / bin arithmetic as the unfused kernel)
+            TapRec* rec = A.scratch + ((size_t)blockIdx.x * FL_LIST_CAP + slot) * FL_MAXV;
+#pragma unroll
+            for (int v = 0; v < FL_MAXV; ++v) {
+              if (v >= P.V || !(vm & (1u << v))) continue;
+              const Taps t = make_taps(pr[v].row, pr[v].col, P.Hf, P.Wf);
+              const float d = fminf(fmaxf(pr[v].depth, P.depth_min), P.depth_max);
+              const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
+              const float bf = floorf(bi);
+              TapRec q;
+              q.r0 = (uint16_t)t.r0; q.r1 = (uint16_t)t.r1; q.c0 = (uint16_t)t.c0; q.c1 = (uint16_t)t.c1;
+              q.wr1 = t.wr1; q.wc1 = t.wc1;
+              q.wb1 = bi - bf;
+              q.b0 = (uint16_t)min(max((int)bf, 0), P.S - 1);
+              q.b1 = (uint16_t)min(max((int)bf + 1, 0), P.S - 1);
+              q.pad_[0] = q.pad_[1] = 0;
+              const uint4* src = reinterpret_cast<const uint4*>(&q);
+              reinterpret_cast<uint4*>(rec + v)[0] = src[0];
+              reinterpret_cast<uint4*>(rec + v)[1] = src[1];
+            }
+            __threadfence();  // records must be in L2 before the gather warps read them (ld.global.cg)
           }
         } else {
           worker_bar();
@@ -245,64 +285,75 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         break;
       }
 
-      // ---------- gather + pool: one warp per tile row ----------
-      for (int r = ww; r < 128; r += FL_WORKERS) {
+      // ---------- gather + pool: one HALF-warp per tile row (16 lanes x 8 channels) ----------
+      for (int r0 = ww * 2; r0 < 128; r0 += FL_WORKERS * 2) {
+        const int r = r0 + half;          // this half-warp's row
+        const int l16 = lane & 15;        // channels [8*l16, 8*l16+8)
         float mean[8], var[8], smaxv = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
+        uint32_t vm = 0;
+        int slot = 0;
         if (r < rows) {
-          const uint32_t e = list[(head + r) % FL_LIST_CAP];
-          const int col = (int)(e >> 14), z = (int)((e >> 8) & 63);
-          const uint32_t vm = e & 0xffu;
-          const int ix = col / P.Y, iy = col - ix * P.Y;
-          const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
-          float fv[FL_MAXV][8], score[FL_MAXV];
+          slot = (head + r) % FL_LIST_CAP;
+          vm = list[slot] & 0xffu;
+        }
+        const TapRec* rec = A.scratch + ((size_t)blockIdx.x * FL_LIST_CAP + slot) * FL_MAXV;
+        const uint32_t vm_any = __reduce_or_sync(0xffffffffu, vm);
+        float fv[FL_MAXV][8], score[FL_MAXV];
 #pragma unroll
-          for (int v = 0; v < FL_MAXV; ++v) {
-            score[v] = 0.f;
+        for (int v = 0; v < FL_MAXV; ++v) {
+          score[v] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fv[v][j] = 0.f;
-          }
+          for (int j = 0; j < 8; ++j) fv[v][j] = 0.f;
+        }
 #pragma unroll
-          for (int v = 0; v < FL_MAXV; ++v) {
-            if (v >= P.V || !(vm & (1u << v))) continue;  // warp-uniform
-            const Proj pr = project_point(sview[v], px, py, pz);
-            const Taps t = make_taps(pr.row, pr.col, P.Hf, P.Wf);
+        for (int v = 0; v < FL_MAXV; ++v) {
+          if (!(vm_any & (1u << v))) continue;  // no half needs this view (warp-uniform)
+          const bool mine = (vm >> v) & 1u;
+          float sp = 0.f, wb1 = 0.f;
+          if (mine) {
+            const uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(rec + v));
+            const uint4 q1 = __ldcg(reinterpret_cast<const uint4*>(rec + v) + 1);
+            const int tr0 = q0.x & 0xffff, tr1 = q0.x >> 16, tc0 = q0.y & 0xffff, tc1 = q0.y >> 16;
+            const float wr1 = __uint_as_float(q0.z), wc1 = __uint_as_float(q0.w);
+            wb1 = __uint_as_float(q1.x);
+            const int b0 = q1.y & 0xffff, b1i = q1.y >> 16;
+            const float wr0 = __fadd_rn(1.0f, -wr1), wc0 = __fadd_rn(1.0f, -wc1);
             const __nv_bfloat16* img = A.fimg + (size_t)v * P.Hf * P.Wf * P.CF;
-            const int rr = half ? t.r1 : t.r0;
-            const float wr = half ? t.wr1 : __fadd_rn(1.0f, -t.wr1);
-            const float wc0 = __fadd_rn(1.0f, -t.wc1);
-            const uint4 ua = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)rr * P.Wf + t.c0) * P.CF + c8 * 8));
-            const uint4 ub = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)rr * P.Wf + t.c1) * P.CF + c8 * 8));
-            // depth score taps (lanes 0..7 = 4 taps x 2 bins), issued together with the feature loads
-            const float d = fminf(fmaxf(pr.depth, P.depth_min), P.depth_max);
-            const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
-            const float bf = floorf(bi);
-            const int b0 = min(max((int)bf, 0), P.S - 1), b1i = min(max((int)bf + 1, 0), P.S - 1);
-            const float wb1 = bi - bf;
-            float sp = 0.f;
-            if (lane < 8) {
-              const int tap = lane >> 1, bsel = lane & 1;
-              const int trr = (tap & 2) ? t.r1 : t.r0;
-              const int tcc = (tap & 1) ? t.c1 : t.c0;
-              const float wt = ((tap & 2) ? t.wr1 : 1.0f - t.wr1) * ((tap & 1) ? t.wc1 : 1.0f - t.wc1);
+            const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr0 * P.Wf + tc0) * P.CF + l16 * 8));
+            const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr0 * P.Wf + tc1) * P.CF + l16 * 8));
+            const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr1 * P.Wf + tc0) * P.CF + l16 * 8));
+            const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr1 * P.Wf + tc1) * P.CF + l16 * 8));
+            if (l16 < 8) {  // depth-score taps: 4 taps x 2 bins on the first 8 lanes of the half
+              const int tap = l16 >> 1, bsel = l16 & 1;
+              const int trr = (tap & 2) ? tr1 : tr0;
+              const int tcc = (tap & 1) ? tc1 : tc0;
+              const float wt = ((tap & 2) ? wr1 : 1.0f - wr1) * ((tap & 1) ? wc1 : 1.0f - wc1);
               sp = wt * __bfloat162float(img[((size_t)trr * P.Wf + tcc) * P.CF + P.D + (bsel ? b1i : b0)]);
             }
-            float fa[8], fb[8];
-            unpack8(ua, fa);
-            unpack8(ub, fb);
+            float f00[8], f01[8], f10[8], f11[8];
+            unpack8(u00, f00);
+            unpack8(u01, f01);
+            unpack8(u10, f10);
+            unpack8(u11, f11);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float part = wr * (wc0 * fa[j] + t.wc1 * fb[j]);
-              part += __shfl_xor_sync(0xffffffffu, part, 16);
-              fv[v][j] = bf16_round(part);
+              // same association as the unfused kernel: row-weight * (column blend), lower row + upper row
+              const float lo = wr0 * (wc0 * f00[j] + wc1 * f01[j]);
+              const float hi = wr1 * (wc0 * f10[j] + wc1 * f11[j]);
+              fv[v][j] = bf16_round(lo + hi);
             }
-            sp += __shfl_xor_sync(0xffffffffu, sp, 2);
-            sp += __shfl_xor_sync(0xffffffffu, sp, 4);
-            sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
-            sp += __shfl_xor_sync(0xffffffffu, sp, 1);
-            score[v] = __shfl_sync(0xffffffffu, bf16_round(sp), 0);
           }
+          // bin-wise spatial interpolation (-> bf16), then interpolation across the two bins (-> bf16);
+          // xor 2/4/1 stay inside the 8 score lanes of each half
+          sp += __shfl_xor_sync(0xffffffffu, sp, 2);
+          sp += __shfl_xor_sync(0xffffffffu, sp, 4);
+          sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
+          sp += __shfl_xor_sync(0xffffffffu, sp, 1);
+          score[v] = __shfl_sync(0xffffffffu, bf16_round(sp), lane & 16);  // broadcast from the half's lane 0
+        }
+        if (vm != 0) {
           float mx = 0.f;
           smaxv = -INFINITY;
 #pragma unroll
@@ -320,11 +371,13 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
 #pragma unroll
           for (int v = 0; v < FL_MAXV; ++v) {
             wv[v] = __fdiv_rn(wv[v], den);
+            if (!(vm & (1u << v))) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j) mean[j] += wv[v] * fv[v][j];
           }
 #pragma unroll
           for (int v = 0; v < FL_MAXV; ++v) {
+            if (!(vm & (1u << v))) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float dd = fv[v][j] - mean[j];
@@ -332,15 +385,19 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             }
           }
         }
-        // A[r][k]: lanes 0..15 -> mean (k = 8*c8..), lanes 16..31 -> var (k = 128 + 8*c8..); K-chunk of 64,
-        // 16-byte slot (k%64)/8 XOR (r%8) inside the 128-byte row (SWIZZLE_128B, as TMA would write it)
-        const float* src = half ? var : mean;
-        const int kc = half * 2 + (c8 >> 3);
-        const int slot16 = (c8 & 7) ^ (r & 7);
-        *reinterpret_cast<uint4*>(smem + SM_AH + kc * 16384 + r * 128 + slot16 * 16) =
-            make_uint4(pack_bf16(src[0], src[1]), pack_bf16(src[2], src[3]), pack_bf16(src[4], src[5]),
-                       pack_bf16(src[6], src[7]));
-        if (lane == 0) smax_s[r] = __float2bfloat16(smaxv);
+        // A[r][k]: mean at k = 8*l16.., var at k = 128 + 8*l16..; K-chunk of 64, 16-byte slot (k%64)/8 XOR (r%8)
+        // inside the 128-byte row (SWIZZLE_128B, as TMA would write it)
+        {
+          const int kc_m = l16 >> 3, kc_v = 2 + (l16 >> 3);
+          const int slot16 = (l16 & 7) ^ (r & 7);
+          *reinterpret_cast<uint4*>(smem + SM_AH + kc_m * 16384 + r * 128 + slot16 * 16) =
+              make_uint4(pack_bf16(mean[0], mean[1]), pack_bf16(mean[2], mean[3]), pack_bf16(mean[4], mean[5]),
+                         pack_bf16(mean[6], mean[7]));
+          *reinterpret_cast<uint4*>(smem + SM_AH + kc_v * 16384 + r * 128 + slot16 * 16) =
+              make_uint4(pack_bf16(var[0], var[1]), pack_bf16(var[2], var[3]), pack_bf16(var[4], var[5]),
+                         pack_bf16(var[6], var[7]));
+          if (l16 == 0) smax_s[r] = __float2bfloat16(smaxv);
+        }
       }
       fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
       mbar_arrive(&ctl->a_full);
@@ -465,11 +522,15 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
 
 using namespace snapb200;
 
+extern "C" size_t snapb200_lift_fused_scratch_bytes(void) {
+  return (size_t)num_sms() * FL_LIST_CAP * FL_MAXV * sizeof(TapRec);
+}
+
 extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* views, const void* fimg,
                                    const float* xs, const float* ys, const float* zs, const void* w1t,
                                    long long ldw1, const float* w256, const float* b1, const void* w2t,
                                    const float* b2, void* plane, uint8_t* pvalid, int* col_counter,
-                                   void* stream) {
+                                   void* scratch, size_t scratch_bytes, void* stream) {
   SNAP_REQUIRE(q && views && fimg && xs && ys && zs && w1t && w256 && b1 && w2t && b2 && plane && pvalid &&
                    col_counter,
                "null pointer");
@@ -516,6 +577,9 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
   int grid = num_sms();
   const int max_useful = (int)((cells + FL_BATCH_COLS - 1) / FL_BATCH_COLS);
   if (grid > max_useful) grid = max_useful;
+  SNAP_REQUIRE(scratch != nullptr && scratch_bytes >= (size_t)grid * FL_LIST_CAP * FL_MAXV * sizeof(TapRec),
+               "scratch too small: need snapb200_lift_fused_scratch_bytes()");
+  a.scratch = reinterpret_cast<TapRec*>(scratch);
   lift_fused_kernel<<<grid, FL_THREADS, FL_SMEM_BYTES, s>>>(tmW1, tmW2, a);
   return check_launch("lift_fused_kernel");
 }

@@ -172,7 +172,8 @@ def lift_gather_pool(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tens
 
 def lift_fused(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
                zs: torch.Tensor, w1t: torch.Tensor, w256: torch.Tensor, b1: torch.Tensor, w2t: torch.Tensor,
-               b2: torch.Tensor, plane: torch.Tensor, pvalid: torch.Tensor, counter: torch.Tensor) -> None:
+               b2: torch.Tensor, plane: torch.Tensor, pvalid: torch.Tensor, counter: torch.Tensor,
+               scratch: torch.Tensor) -> None:
     _require(fimg, torch.bfloat16, "fimg")
     _require(w1t, torch.bfloat16, "w1t")
     _require(w2t, torch.bfloat16, "w2t")
@@ -184,7 +185,14 @@ def lift_fused(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs
         C.byref(p), C.c_void_p(_ptr(views)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
         C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(w1t)), C.c_longlong(w1t.stride(0)), C.c_void_p(_ptr(w256)),
         C.c_void_p(_ptr(b1)), C.c_void_p(_ptr(w2t)), C.c_void_p(_ptr(b2)), C.c_void_p(_ptr(plane)),
-        C.c_void_p(_ptr(pvalid)), C.c_void_p(_ptr(counter)), _stream()))
+        C.c_void_p(_ptr(pvalid)), C.c_void_p(_ptr(counter)), C.c_void_p(_ptr(scratch)),
+        C.c_size_t(scratch.numel() * scratch.element_size()), _stream()))
+
+
+def lift_fused_scratch_bytes() -> int:
+    f = _lib.lib().snapb200_lift_fused_scratch_bytes
+    f.restype = C.c_size_t
+    return int(f())
 
 
 def vertical_max(volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, Cc: int,

@@ -107,6 +107,7 @@ class StreetViewEncoder:
                 crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
                 volume=None, valid=None,   # [B,N,128] / [B,N]: allocated on first unfused call
                 plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 4, dt=torch.int32),
+                scratch=z(ops.lift_fused_scratch_bytes(), dt=torch.uint8),
                 # per-scene inputs: pinned host staging + device copies (a captured CUDA graph re-reads the
                 # staging buffers at every replay, see `stage_inputs`)
                 images_host=pin(B, V, H, W, 3, dt=torch.float32), images=z(B, V, H, W, 3, dt=torch.float32),
@@ -179,7 +180,7 @@ class StreetViewEncoder:
             if fused:
                 ops.lift_fused(lp, buf["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], buf["zs"][b],
                                Bm[wts["fus0"]], wts["w256"], wts["fus0_b"], Bm[wts["fus1"]], wts["fus1_b"],
-                               buf["plane"][b], buf["pvalid"][b], buf["counter"][b])
+                               buf["plane"][b], buf["pvalid"][b], buf["counter"][b], buf["scratch"])
                 continue
             dv = dt = None
             if debug:

@@ -227,9 +227,10 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
     plane = torch.full((G * G, 128), 7.0, dtype=torch.bfloat16, device=dev)
     pv = torch.full((G * G,), 9, dtype=torch.uint8, device=dev)
     counter = torch.zeros(4, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(ops.lift_fused_scratch_bytes(), dtype=torch.uint8, device=dev)
     w256 = _t(fp["Dense_0"]["kernel"][256]).to(dev)
     for _ in range(2):  # twice: the kernel must be re-entrant on the same buffers
-        ops.lift_fused(lp, views, fimg, xs_d, ys_d, zs_d, bank.b_mats[w0], w256, b1, bank.b_mats[w1], b2, plane, pv, counter)
+        ops.lift_fused(lp, views, fimg, xs_d, ys_d, zs_d, bank.b_mats[w0], w256, b1, bank.b_mats[w1], b2, plane, pv, counter, scratch)
     torch.cuda.synchronize()
     assert torch.equal(pv, pv_ref), "valid plane differs"
     assert int(counter[2]) == int(valid.sum()), "fused kernel must process exactly the visible voxels"
