@@ -269,7 +269,7 @@ def main():
 
     def phase_timer():
         import snap_b200.ops as ops_mod
-        names = ["lift_fused", "lift_gather_pool", "vertical_max", "gemm", "gn_stats", "gn_apply", "std_weights_batched",
+        names = ["lift_fused", "lift_gather_pool", "vertical_max", "gemm", "conv_gn", "gn_stats", "gn_apply", "std_weights_batched",
                  "root_im2col", "maxpool3x3s2", "upsample2x", "crop_relu", "match_head"]
         orig = {n: getattr(ops_mod, n) for n in names}
         evs = []
@@ -279,6 +279,8 @@ def main():
                 key = n
                 if n == "gemm":
                     key = f"gemm[k={a[0].shape[1]},n={a[1].shape[0]},seg={len(k.get('seg_off', (0,)))}]"
+                if n == "conv_gn":
+                    key = f"conv_gn[c={a[4]},n={a[8].shape[0]},taps={k.get('taps', 1)},s={k.get('stride', 1)}]"
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record(); r = orig[n](*a, **k); e.record()
                 evs.append((key, s, e))

@@ -64,8 +64,20 @@ def launch_count_reset() -> None:
 # Every symbol include/snapb200.h declares; tests/test_abi.py checks the .so exports each of them.
 EXPORTED_SYMBOLS = [
     "snapb200_last_error", "snapb200_version", "snapb200_launch_count",
-    "snapb200_launch_count_reset", "snapb200_gemm_bf16",
+    "snapb200_launch_count_reset", "snapb200_gemm_bf16", "snapb200_conv_gn_bf16",
 ]
+
+
+class ConvGnParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("acc", C.c_void_p), ("replica_stride", C.c_int), ("scale", C.c_void_p), ("bias", C.c_void_p),
+        ("pre_relu", C.c_int), ("post_relu", C.c_int), ("taps", C.c_int), ("stride", C.c_int),
+        ("b", C.c_void_p), ("b_rows", C.c_longlong), ("b_cols", C.c_int), ("b_ld", C.c_longlong),
+        ("n", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong), ("residual", C.c_void_p),
+        ("ldr", C.c_longlong), ("gn_acc", C.c_void_p), ("gn_acc_relu", C.c_void_p),
+        ("gn_replica_stride", C.c_int),
+    ]
 
 
 class WeightDesc(C.Structure):

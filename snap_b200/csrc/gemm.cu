@@ -81,7 +81,104 @@ void pick_config(int n, int k_total, int bk, int* bn, int* ctas_per_sm) {
 
 }  // namespace snapb200
 
+namespace snapb200 {
+template <int BN, int AMODE>
+static int launch_gn_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t s) {
+  using Cfg = GemmCfg<BN, 64>;
+  static bool configured = false;
+  if (!configured) {
+    const int want = Cfg::smem_bytes(Cfg::MAX_STAGES, true);
+    int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, 64, AMODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             want > 227 * 1024 ? 227 * 1024 : want),
+                        "cudaFuncSetAttribute(gemm_tc<gn>)");
+    if (rc) return rc;
+    configured = true;
+  }
+  int stages = p.nkb < Cfg::MAX_STAGES ? p.nkb : Cfg::MAX_STAGES;
+  if (stages < 2) stages = 2;
+  while (stages > 2 && Cfg::smem_bytes(stages, true) > 225 * 1024) --stages;
+  p.stages = stages;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  const int threads = AMODE == AMODE_TGN ? GEMM_THREADS_TGN : GEMM_THREADS_GN;
+  gemm_tc_kernel<BN, 64, AMODE><<<grid, threads, Cfg::smem_bytes(stages, true), s>>>(tmA, tmB, p);
+  return check_launch("gemm_tc_kernel<gn>");
+}
+}  // namespace snapb200
+
 using namespace snapb200;
+
+/* conv( relu?( GroupNorm( relu?(x) ) ) ) in ONE launch: the A operand of the tcgen05 GEMM is produced in-kernel
+   from the raw activation tensor (see SnapConvGnParams). */
+extern "C" int snapb200_conv_gn_bf16(const SnapConvGnParams* q, void* stream) {
+  SNAP_REQUIRE(q != nullptr, "null params");
+  SNAP_REQUIRE(q->x && q->acc && q->scale && q->bias && q->b && q->out, "null operand");
+  SNAP_REQUIRE(q->C % 64 == 0 && q->C <= 2048, "C must be a multiple of 64, <= 2048 (got %d)", q->C);
+  SNAP_REQUIRE(q->n_img >= 1 && q->n_img <= GEMM_GN_MAX_IMG, "n_img must be in 1..%d", GEMM_GN_MAX_IMG);
+  SNAP_REQUIRE(q->taps == 1 || q->taps == 9, "taps must be 1 (1x1) or 9 (3x3, pad 1)");
+  SNAP_REQUIRE(q->stride == 1 || q->stride == 2, "stride must be 1 or 2");
+  SNAP_REQUIRE(q->n >= 16 && q->n % 16 == 0 && q->ldo % 8 == 0, "n must be a multiple of 16, ldo of 8");
+  SNAP_REQUIRE(q->replica_stride >= q->n_img * 64, "replica_stride too small");
+  const int Ho = (q->H - 1) / q->stride + 1, Wo = (q->W - 1) / q->stride + 1;
+  GemmParams p = {};
+  int bn = q->n >= 256 ? 256 : (q->n > 64 ? 128 : 64);
+  const long long M = (long long)q->n_img * Ho * Wo;
+  p.m_tiles = (int)((M + 127) / 128);
+  p.n_tiles = (q->n + bn - 1) / bn;
+  p.kps = q->C / 64;
+  p.nkb = q->taps * p.kps;
+  p.seg_kstride = q->C;
+  p.seg_mode = SEG_TABLE;
+  p.tile_mode = TILE_LINEAR;
+  p.epi = EPI_STORE;
+  p.M_valid = M;
+  p.N = q->n;
+  p.out = q->out;
+  p.ldo = q->ldo;
+  p.residual = static_cast<const __nv_bfloat16*>(q->residual);
+  p.ldr = q->ldr;
+  p.gn_acc = q->gn_acc;
+  p.gn_acc_relu = q->gn_acc_relu;
+  p.gn_rows_per_img = (long long)Ho * Wo;
+  p.gn_cpg = q->n / 32;
+  p.gn_replica_stride = q->gn_replica_stride;
+  if (q->gn_acc != nullptr)
+    SNAP_REQUIRE(q->n % 64 == 0 && q->gn_replica_stride > 0, "gn_acc needs n %% 64 == 0 and gn_replica_stride");
+  SNAP_REQUIRE(q->gn_acc_relu == nullptr || q->gn_acc != nullptr, "gn_acc_relu needs gn_acc");
+  p.g_raw = static_cast<const __nv_bfloat16*>(q->x);
+  p.g_acc = q->acc;
+  p.g_scale = q->scale;
+  p.g_bias = q->bias;
+  p.g_rep_stride = q->replica_stride;
+  p.g_nimg = q->n_img;
+  p.g_C = q->C;
+  p.g_H = q->H;
+  p.g_W = q->W;
+  p.g_Ho = Ho;
+  p.g_Wo = Wo;
+  p.g_stride = q->stride;
+  p.g_taps = q->taps;
+  p.g_pre_relu = q->pre_relu;
+  p.g_post_relu = q->post_relu;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmB, q->b, q->b_rows, q->b_cols, q->b_ld, bn, 64);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (q->stride == 1) {
+    // TMA loads the RAW tile from the dense tensor (row-shifted per tap); transformer warps normalise in smem
+    rc = make_tmap_2d_bf16(&tmA, q->x, (long long)q->n_img * q->H * q->W, q->C, q->C, 128, 64);
+    if (rc) return rc;
+    for (int t = 0; t < q->taps; ++t)
+      p.seg_off[t] = q->taps == 9 ? (t / 3 - 1) * q->W + (t % 3 - 1) : 0;
+    if (bn == 64) return launch_gn_inst<64, AMODE_TGN>(tmA, tmB, p, s);
+    if (bn == 128) return launch_gn_inst<128, AMODE_TGN>(tmA, tmB, p, s);
+    return launch_gn_inst<256, AMODE_TGN>(tmA, tmB, p, s);
+  }
+  if (bn == 64) return launch_gn_inst<64, AMODE_GN>(tmB, tmB, p, s);
+  if (bn == 128) return launch_gn_inst<128, AMODE_GN>(tmB, tmB, p, s);
+  return launch_gn_inst<256, AMODE_GN>(tmB, tmB, p, s);
+}
 
 extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
   SNAP_REQUIRE(q != nullptr, "null params");

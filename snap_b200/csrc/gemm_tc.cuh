@@ -55,6 +55,14 @@ struct GemmParams {
   long long gn_rows_per_img;
   int gn_cpg;  // channels per group = N / 32
   int gn_replica_stride;  // doubles between the GN_REPLICAS copies of the accumulator (contention spreading)
+  // A_GN mode: the A operand is produced in-kernel from the RAW activation tensor [n_img, H, W, C]:
+  // GroupNorm (statistics from `g_acc`) + affine + ReLU with the reference's bf16 rounding chain, implicit
+  // 1x1 / 3x3 (pad 1) window with stride 1 or 2, zero outside the image.  m = (img*Ho + ho)*Wo + wo.
+  const __nv_bfloat16* g_raw;
+  const double* g_acc;
+  const float* g_scale;
+  const float* g_bias;
+  int g_rep_stride, g_nimg, g_C, g_H, g_W, g_Ho, g_Wo, g_stride, g_taps, g_pre_relu, g_post_relu;
   // EPI_XCORR
   const float* xc_cnt;
   const float* xc_den;
@@ -63,6 +71,13 @@ struct GemmParams {
 
 constexpr int GEMM_EPI_WARPS = 8;                       // two per TMEM lane quadrant
 constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;  // 320
+constexpr int GEMM_GN_WARPS = 4;                         // A_GN mode: producer warps (one thread per tile row)
+constexpr int GEMM_THREADS_GN = GEMM_THREADS + GEMM_GN_WARPS * 32;  // 448
+constexpr int GEMM_TGN_WARPS = 8;                        // A_TGN mode: in-smem transformer warps (2 threads per row)
+constexpr int GEMM_THREADS_TGN = GEMM_THREADS + GEMM_TGN_WARPS * 32;  // 576
+enum { AMODE_TMA = 0, AMODE_GN = 1, AMODE_TGN = 2 };
+constexpr int GEMM_GN_MAX_IMG = 32;
+constexpr int GEMM_GN_TABLE_BYTES = GEMM_GN_MAX_IMG * 32 * 8 + 2048 * 4;  // statistics + packed scale/bias
 
 template <int BN, int BK>
 struct GemmCfg {
@@ -78,7 +93,9 @@ struct GemmCfg {
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
   // +1024 for manual alignment, +512 for barriers (2 x 16 stage + 4 accumulator) / tmem pointer
-  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 + 512; }
+  static constexpr int smem_bytes(int stages, bool gn_tables = false) {
+    return stages * STAGE_BYTES + 1024 + 512 + (gn_tables ? GEMM_GN_TABLE_BYTES : 0);
+  }
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(BK == 64 || BK == 32, "BK is one swizzle span: 128B or 64B of bf16");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "stage tiles must stay 1024B aligned");
@@ -160,11 +177,17 @@ __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool row_o
   }
 }
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+// AMODE_TMA: A tiles come straight from TMA.  AMODE_GN: producer warps build the A tile from the raw tensor through
+// registers (any stride).  AMODE_TGN: TMA loads the RAW tile (dense layout, row-shifted per 3x3 tap) and
+// transformer warps apply GroupNorm + affine + ReLU IN PLACE in shared memory (stride 1 only).
+template <int BN, int BK, int AMODE = AMODE_TMA>
+__global__ void __launch_bounds__(AMODE == AMODE_GN ? GEMM_THREADS_GN : (AMODE == AMODE_TGN ? GEMM_THREADS_TGN : GEMM_THREADS),
+                                  AMODE == AMODE_TMA ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, BK>;
+  constexpr bool AGN = AMODE == AMODE_GN;
+  constexpr bool TGN = AMODE == AMODE_TGN;
   const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -174,6 +197,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ready_bar = tmem_empty + 4;  // [STAGES] A_TGN: tile transformed, MMA may consume it
+  // A_GN / A_TGN tables (after the 512 B barrier block): per (image, group) (mean, rstd) and per channel pair packed
+  // bf16x2 scale / bias
+  float2* g_stat = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES + 512);
+  uint32_t* g_sc2 = reinterpret_cast<uint32_t*>(g_stat + GEMM_GN_MAX_IMG * 32);
+  uint32_t* g_bi2 = g_sc2 + 1024;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,8 +215,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], AGN ? 1 + GEMM_GN_WARPS * 32 : 1);
       mbar_init(&empty_bar[s], 1);
+      if (TGN) mbar_init(&ready_bar[s], GEMM_TGN_WARPS * 32);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -196,6 +226,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  if ((AGN || TGN) && warp >= 2 + GEMM_EPI_WARPS) {
+    const int t = threadIdx.x - (2 + GEMM_EPI_WARPS) * 32;
+    constexpr int NT = (TGN ? GEMM_TGN_WARPS : GEMM_GN_WARPS) * 32;
+    const int cpg = p.g_C / 32;
+    const double count = (double)p.g_H * (double)p.g_W * (double)cpg;
+    for (int e = t; e < p.g_nimg * 32; e += NT) {
+      double su = 0.0, sq = 0.0;
+#pragma unroll
+      for (int rep = 0; rep < GN_REPLICAS; ++rep) {
+        su += p.g_acc[(size_t)rep * p.g_rep_stride + (size_t)e * 2];
+        sq += p.g_acc[(size_t)rep * p.g_rep_stride + (size_t)e * 2 + 1];
+      }
+      const double mu = su / count;
+      double var = sq / count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      g_stat[e] = make_float2((float)mu, (float)(1.0 / sqrt(var + 1e-5)));
+    }
+    for (int c2 = t; c2 < p.g_C / 2; c2 += NT) {
+      g_sc2[c2] = pack_bf16(__ldg(p.g_scale + 2 * c2), __ldg(p.g_scale + 2 * c2 + 1));
+      g_bi2[c2] = pack_bf16(__ldg(p.g_bias + 2 * c2), __ldg(p.g_bias + 2 * c2 + 1));
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -212,10 +264,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.nkb; ++kb) {
           const int a_off = p.seg_mode == SEG_TABLE ? p.seg_off[seg] : xi * p.xc_P + xj;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], AGN ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          tma_load_2d(&tmA, &full_bar[stage], sa, p.a_col0 + kc * BK, t.a_row + a_off);
+          if (!AGN) tma_load_2d(&tmA, &full_bar[stage], sa, p.a_col0 + kc * BK, t.a_row + a_off);
           if (p.b_seg_rows == 0)
             tma_load_2d(&tmB, &full_bar[stage], sb, seg * p.seg_kstride + kc * BK, t.b_row);
           else  // B stored segment-major: [segment][rows][BK] (contiguous tile per segment)
@@ -248,7 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(TGN ? &ready_bar[stage] : &full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -270,6 +322,151 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (TGN && warp >= 2 + GEMM_EPI_WARPS) {
+    // ===================== A_TGN transformer warps: GroupNorm + ReLU in place on the raw smem tile =====
+    if constexpr (TGN && BK == 64) {
+      const int tt = threadIdx.x - (2 + GEMM_EPI_WARPS) * 32;  // 0..255
+      const int t = tt & 127;                                   // tile row
+      const int qh = tt >> 7;                                    // which four 16-byte chunks of the row
+      const int C = p.g_C, cpg = C / 32;
+      const long long per_img = (long long)p.g_Ho * p.g_Wo;
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int mt = tile / p.n_tiles;
+        const long long m = (long long)mt * 128 + t;
+        const bool row_ok = m < p.M_valid;
+        const int img = row_ok ? (int)(m / per_img) : 0;
+        const int rem = row_ok ? (int)(m - (long long)img * per_img) : 0;
+        const int ho = rem / p.g_Wo, wo = rem - ho * p.g_Wo;
+        const float2* stat = g_stat + img * 32;
+        int seg = 0, kc = 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          bool inb = row_ok;
+          if (p.g_taps == 9) {  // stride 1, pad 1: the row-shifted dense tile wraps at image borders -> zero there
+            const int kh = seg / 3, kw = seg - 3 * kh;
+            const int hi = ho + kh - 1, wi = wo + kw - 1;
+            inb = inb && hi >= 0 && hi < p.g_H && wi >= 0 && wi < p.g_W;
+          }
+          mbar_wait(&full_bar[stage], phase);  // raw tile (and the weights) have landed
+          uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + t * 128;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c = qh * 4 + cc;
+            uint4* slot = reinterpret_cast<uint4*>(rowp + ((c ^ (t & 7)) * 16));
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (inb) {
+              const uint4 u = *slot;
+              const int ch0 = kc * 64 + c * 8;
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              uint32_t r[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int ch = ch0 + 2 * jj;
+                const float2 st = stat[ch / cpg];
+                float2 x = unpack_bf16(w[jj]);
+                if (p.g_pre_relu) {
+                  x.x = fmaxf(x.x, 0.f);
+                  x.y = fmaxf(x.y, 0.f);
+                }
+                __nv_bfloat162 v = __floats2bfloat162_rn((x.x - st.x) * st.y, (x.y - st.x) * st.y);
+                const uint32_t s2 = g_sc2[ch >> 1], b2 = g_bi2[ch >> 1];
+                v = __hmul2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&s2));
+                v = __hadd2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&b2));
+                if (p.g_post_relu) v = __hmax2(v, zero2);
+                r[jj] = *reinterpret_cast<uint32_t*>(&v);
+              }
+              o = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            *slot = o;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&ready_bar[stage]);
+          if (++kc == p.kps) {
+            kc = 0;
+            ++seg;
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (AGN && warp >= 2 + GEMM_EPI_WARPS) {
+    // ===================== A_GN producer warps: thread t owns tile row t =====================
+    if constexpr (AGN && BK == 64) {
+      const int t = threadIdx.x - (2 + GEMM_EPI_WARPS) * 32;
+      const int C = p.g_C, cpg = C / 32;
+      const int pad = p.g_taps == 9 ? 1 : 0;
+      const long long per_img = (long long)p.g_Ho * p.g_Wo;
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int mt = tile / p.n_tiles;
+        const long long m = (long long)mt * 128 + t;
+        const bool row_ok = m < p.M_valid;
+        const int img = row_ok ? (int)(m / per_img) : 0;
+        const int rem = row_ok ? (int)(m - (long long)img * per_img) : 0;
+        const int ho = rem / p.g_Wo, wo = rem - ho * p.g_Wo;
+        const float2* stat = g_stat + img * 32;
+        int seg = 0, kc = 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const int kh = p.g_taps == 9 ? seg / 3 : 0, kw = p.g_taps == 9 ? seg - 3 * (seg / 3) : 0;
+          const int hi = ho * p.g_stride + kh - pad, wi = wo * p.g_stride + kw - pad;
+          const bool inb = row_ok && hi >= 0 && hi < p.g_H && wi >= 0 && wi < p.g_W;
+          uint4 u[8];
+          if (inb) {
+            const uint4* src = reinterpret_cast<const uint4*>(
+                p.g_raw + (((size_t)img * p.g_H + hi) * p.g_W + wi) * C + kc * 64);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) u[c] = __ldg(src + c);
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + t * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (inb) {
+              const int ch0 = kc * 64 + c * 8;
+              const uint32_t w[4] = {u[c].x, u[c].y, u[c].z, u[c].w};
+              uint32_t r[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int ch = ch0 + 2 * jj;
+                const float2 st = stat[ch / cpg];
+                float2 x = unpack_bf16(w[jj]);
+                if (p.g_pre_relu) {
+                  x.x = fmaxf(x.x, 0.f);
+                  x.y = fmaxf(x.y, 0.f);
+                }
+                // resnet.py:39-41,57-69 in bf16: standardise (fp32) -> bf16, * scale -> bf16, + bias -> bf16
+                __nv_bfloat162 v = __floats2bfloat162_rn((x.x - st.x) * st.y, (x.y - st.x) * st.y);
+                const uint32_t s2 = g_sc2[ch >> 1], b2 = g_bi2[ch >> 1];
+                v = __hmul2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&s2));
+                v = __hadd2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&b2));
+                if (p.g_post_relu) v = __hmax2(v, zero2);
+                r[jj] = *reinterpret_cast<uint32_t*>(&v);
+              }
+              o = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (t & 7)) * 16)) = o;  // SWIZZLE_128B position of chunk c
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[stage]);
+          if (++kc == p.kps) {
+            kc = 0;
+            ++seg;
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }

@@ -82,7 +82,12 @@ class _WeightBank:
 class EncoderPlan:
     """Launch plan + workspace of one ImageEncoder for a fixed input shape [n_img, H, W, 3]."""
 
-    def __init__(self, params: Dict, config, n_img: int, H: int, W: int, device: torch.device):
+    def __init__(self, params: Dict, config, n_img: int, H: int, W: int, device: torch.device,
+                 fused_gn: bool = False):
+        # fused_gn: GroupNorm+ReLU fused into the conv's A-operand path (`snapb200_conv_gn_bf16`, one launch per
+        # conv, no normalised copies in HBM).  Parity-green but currently slower than the two-launch path
+        # (GroupNorm-apply kernel + TMA GEMM with two CTAs per SM), so off by default (profiles/r01_notes.md).
+        self.fused_gn = fused_gn
         enc_cfg = config.encoder
         self.cfg = config
         self.n, self.H, self.W = n_img, H, W
@@ -222,6 +227,26 @@ class EncoderPlan:
         if forced_input:
             acc1.zero_(); acc2.zero_(); acc3.zero_()
             ops.gn_stats(x, n, h * w, cin, False, acc1)
+        if self.fused_gn:
+            gn1, gn2, gn3 = u["gn"]
+            # every conv normalises its input on the fly (GroupNorm + ReLU fused into the GEMM's A producer)
+            if u["wproj"] is not None:  # resnet.py:121-122 (projection of the pre-activated tensor, strided)
+                res = self._view(self.buf_res, rows_out, nout)
+                ops.conv_gn(x, n, h, w, cin, acc1, gn1[0], gn1[1], B[u["wproj"]], res, taps=1, stride=s)
+            else:
+                res = x
+            y1 = self._view(self.buf_y, rows_in, nmid)
+            ops.conv_gn(x, n, h, w, cin, acc1, gn1[0], gn1[1], B[u["w1"]], y1, taps=1, stride=1, gn_acc=acc2)
+            y2 = self._view(self.buf_a, rows_out, nmid)
+            ops.conv_gn(y1, n, h, w, nmid, acc2, gn2[0], gn2[1], B[u["w2"]], y2, taps=9, stride=s, gn_acc=acc3)
+            fpn_acc = u.get("fpn_acc")
+            if forced_input and fpn_acc is not None:
+                fpn_acc.zero_()
+            if next_acc is None and fpn_acc is not None:
+                next_acc = self.acc_scratch
+            ops.conv_gn(y2, n, ho, wo, nmid, acc3, gn3[0], gn3[1], B[u["w3"]], u["out"], taps=1, stride=1,
+                        residual=res, gn_acc=next_acc, gn_acc_relu=fpn_acc)
+            return u["out"]
         a1 = self._view(self.buf_a, rows_in, cin)
         ops.gn_apply(x, n, h, w, cin, acc1, u["gn"][0][0], u["gn"][0][1], False, True, ops.LAYOUT_DENSE, a1,
                      u.get("a1_sub"))
@@ -268,12 +293,20 @@ class EncoderPlan:
             if forced_input:
                 acc.zero_()
                 ops.gn_stats(f["x"], n, f["h"] * f["w"], f["c"], True, acc)
-            a = self._view(self.buf_a, rows, f["c"])
-            ops.gn_apply(f["x"], n, f["h"], f["w"], f["c"], acc, f["gn"][0], f["gn"][1], True, False,
-                         ops.LAYOUT_DENSE, a)
-            if prev is not None:
-                ops.upsample2x(prev["out"], n, prev["h"], prev["w"], self.out_dim, f["up"])
-            ops.gemm(a, B[f["wk"]], f["out"], m_rows=rows, residual=f["up"] if prev is not None else None)
+            if self.fused_gn:
+                if prev is not None:
+                    ops.upsample2x(prev["out"], n, prev["h"], prev["w"], self.out_dim, f["up"])
+                # relu -> GroupNorm -> 1x1 conv (+ up-sampled coarser level) in one launch
+                ops.conv_gn(f["x"], n, f["h"], f["w"], f["c"], acc, f["gn"][0], f["gn"][1], B[f["wk"]], f["out"],
+                            taps=1, stride=1, pre_relu=True, post_relu=False,
+                            residual=f["up"] if prev is not None else None)
+            else:
+                a = self._view(self.buf_a, rows, f["c"])
+                ops.gn_apply(f["x"], n, f["h"], f["w"], f["c"], acc, f["gn"][0], f["gn"][1], True, False,
+                             ops.LAYOUT_DENSE, a)
+                if prev is not None:
+                    ops.upsample2x(prev["out"], n, prev["h"], prev["w"], self.out_dim, f["up"])
+                ops.gemm(a, B[f["wk"]], f["out"], m_rows=rows, residual=f["up"] if prev is not None else None)
             outs.append(f["out"][:rows].view(n, f["h"], f["w"], self.out_dim))
             prev = f
         return outs
@@ -301,7 +334,8 @@ class ImageEncoder:
 
     default_config = staticmethod(configs.image_encoder)
 
-    def __init__(self, config=None, dtype=torch.bfloat16):
+    def __init__(self, config=None, dtype=torch.bfloat16, fused_gn: bool = False):
+        self.fused_gn = fused_gn
         if dtype != torch.bfloat16:
             raise NotImplementedError("the B200 path computes in bf16 (fp32 accumulate / statistics)")
         self.config = config if config is not None else configs.image_encoder()
@@ -313,7 +347,7 @@ class ImageEncoder:
     def plan(self, params: Dict, n: int, H: int, W: int, device) -> EncoderPlan:
         key = (id(params), n, H, W, str(device))
         if key not in self._plans:
-            self._plans[key] = EncoderPlan(params, self.config, n, H, W, device)
+            self._plans[key] = EncoderPlan(params, self.config, n, H, W, device, fused_gn=self.fused_gn)
         return self._plans[key]
 
     def apply(self, variables: Dict, image: torch.Tensor, train: bool = False) -> types.FeatureImagePyramid:

@@ -99,6 +99,36 @@ def gemm(
     return out
 
 
+def conv_gn(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int, acc: torch.Tensor, scale: torch.Tensor,
+            bias: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, taps: int = 1, stride: int = 1,
+            pre_relu: bool = False, post_relu: bool = True, residual: Optional[torch.Tensor] = None,
+            gn_acc: Optional[torch.Tensor] = None, gn_acc_relu: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = conv(act(GroupNorm(pre(x)))) in one launch; x is the RAW activation [n_img*H*W, Cc] bf16, its
+    GroupNorm statistics are in `acc` (f64 [GN_REPLICAS, n_img, 32, 2])."""
+    _require(x, torch.bfloat16, "x")
+    _require(b, torch.bfloat16, "b")
+    _require(out, torch.bfloat16, "out")
+    _require(acc, torch.float64, "acc")
+    p = _lib.ConvGnParams()
+    p.x, p.n_img, p.H, p.W, p.C = _ptr(x), n_img, H, W, Cc
+    p.acc, p.replica_stride = _ptr(acc), acc.stride(0)
+    p.scale, p.bias = _ptr(scale), _ptr(bias)
+    p.pre_relu, p.post_relu, p.taps, p.stride = int(pre_relu), int(post_relu), taps, stride
+    p.b, p.b_rows, p.b_cols, p.b_ld = _ptr(b), b.shape[0], b.shape[1], b.stride(0)
+    p.n = b.shape[0]
+    p.out, p.ldo = _ptr(out), out.stride(0)
+    if residual is not None:
+        _require(residual, torch.bfloat16, "residual")
+        p.residual, p.ldr = _ptr(residual), residual.stride(0)
+    if gn_acc is not None:
+        _require(gn_acc, torch.float64, "gn_acc")
+        p.gn_acc, p.gn_replica_stride = _ptr(gn_acc), gn_acc.stride(0)
+        if gn_acc_relu is not None:
+            p.gn_acc_relu = _ptr(gn_acc_relu)
+    _lib.check(_lib.lib().snapb200_conv_gn_bf16(C.byref(p), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # image-encoder kernels
 # --------------------------------------------------------------------------------------------

@@ -106,8 +106,9 @@ def test_gn_maxpool_upsample_im2col_vs_oracle():
     assert np.array_equal(out[:, :147], cols) and not out[:, 147:].any()
 
 
-@pytest.mark.parametrize("skip_root,hw", [(False, (40, 72)), (True, (24, 24))])
-def test_image_encoder_units_teacher_forced(skip_root, hw):
+@pytest.mark.parametrize("skip_root,hw,fused_gn", [(False, (40, 72), False), (True, (24, 24), False),
+                                                   (False, (40, 72), True), (True, (24, 24), True)])
+def test_image_encoder_units_teacher_forced(skip_root, hw, fused_gn):
     """Every residual unit, the root block and the FPN, each fed the ORACLE's (bf16-mode) input of that
     block, vs the oracle's output of that block.  Both sides round at the same points, so the only
     differences are fp32 summation order and the rare bf16 rounding flips they cause:
@@ -121,7 +122,7 @@ def test_image_encoder_units_teacher_forced(skip_root, hw):
     tt = lambda tree: {k: (tt(v) if isinstance(v, dict) else _t(v)) for k, v in tree.items()}
     trace = []
     ref_bf, strides = oie.image_encoder(_t(img), tt(p), skip_root, rd_bf16, trace)
-    enc = image_encoder.ImageEncoder(cfg)
+    enc = image_encoder.ImageEncoder(cfg, fused_gn=fused_gn)  # fused_gn: GroupNorm fused into the conv's A path
     plan = enc.plan(p, 2, *hw, torch.device("cuda"))
     plan.bank.run()
     plan.gn_acc_all.zero_()
