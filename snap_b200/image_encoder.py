@@ -194,14 +194,15 @@ class EncoderPlan:
     def _view(self, buf: torch.Tensor, rows: int, c: int) -> torch.Tensor:
         return buf[: _round_up(max(rows, 128), 128) * c].view(-1, c)
 
-    def run_root(self, images: torch.Tensor) -> torch.Tensor:
+    def run_root(self, images: torch.Tensor, im2col_done: bool = False) -> torch.Tensor:
         """resnet.py:82-100,199-208.  Also produces the GroupNorm statistics of the first unit's input."""
         n = self.n
         assert tuple(images.shape) == (n, self.H, self.W, 3), images.shape
         kh, kw, st, pd = self.root_geom
         H0, W0 = self.rootHW
         acc0 = self.units[0]["acc"][0]
-        ops.root_im2col(images, self.Hp, self.Wp, kh, kw, st, pd, self.a_root)
+        if not im2col_done:
+            ops.root_im2col(images, self.Hp, self.Wp, kh, kw, st, pd, self.a_root)
         if self.skip_root:
             ops.gemm(self.a_root, self.bank.b_mats[self.root_w], self.y_root, m_rows=n * H0 * W0, seg_k=self.root_kp,
                      gn_acc=acc0, gn_rows_per_img=H0 * W0)
@@ -250,9 +251,15 @@ class EncoderPlan:
         a1 = self._view(self.buf_a, rows_in, cin)
         ops.gn_apply(x, n, h, w, cin, acc1, u["gn"][0][0], u["gn"][0][1], False, True, ops.LAYOUT_DENSE, a1,
                      u.get("a1_sub"))
+        joined = True
         if u["wproj"] is not None:  # resnet.py:121-122 (projection of the pre-activated tensor)
             res = self._view(self.buf_res, rows_out, nout)
-            ops.gemm(u["a1_sub"] if s == 2 else a1, B[u["wproj"]], res, m_rows=rows_out)
+            # conv_proj and conv1 both read a1 and are independent: run the projection on a side stream
+            main, side = torch.cuda.current_stream(), self._side()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.gemm(u["a1_sub"] if s == 2 else a1, B[u["wproj"]], res, m_rows=rows_out)
+            joined = False
         else:
             res = x
         y1 = self._view(self.buf_y, rows_in, nmid)
@@ -271,6 +278,9 @@ class EncoderPlan:
         y2 = self._view(self.buf_y, rows_out, nmid)  # y1 is dead once a2 is written
         ops.gemm(u["a2"], B[u["w2"]], y2, m_rows=m_rows, seg_off=seg, seg_k=nmid, remap=remap,
                  gn_acc=acc3, gn_rows_per_img=ho * wo)
+        if not joined:
+            # a3 reuses the buffer of a1, which the projection (side stream) is still reading
+            torch.cuda.current_stream().wait_stream(self._side())
         a3 = self._view(self.buf_a, rows_out, nmid)
         ops.gn_apply(y2, n, ho, wo, nmid, acc3, u["gn"][2][0], u["gn"][2][1], False, True, ops.LAYOUT_DENSE, a3)
         fpn_acc = u.get("fpn_acc")
@@ -311,11 +321,23 @@ class EncoderPlan:
             prev = f
         return outs
 
+    def _side(self) -> torch.cuda.Stream:
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.dev)
+        return self._side_stream
+
     def run(self, images: torch.Tensor) -> List[torch.Tensor]:
         """images f32 [n,H,W,3] in [0,1] (device) -> FPN features coarse->fine, each [n,h,w,C] bf16 (uncropped)."""
+        main, side = torch.cuda.current_stream(), self._side()
+        # the StdConv weight standardisation does not depend on the images: overlap it with the root im2col
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.bank.run()
         self.gn_acc_all.zero_()
-        self.bank.run()
-        x = self.run_root(images)
+        kh, kw, st, pd = self.root_geom
+        ops.root_im2col(images, self.Hp, self.Wp, kh, kw, st, pd, self.a_root)
+        main.wait_stream(side)
+        x = self.run_root(images, im2col_done=True)
         for i, u in enumerate(self.units):
             nxt = self.units[i + 1]["acc"][0] if i + 1 < len(self.units) else None
             x = self.run_unit(u, x, nxt)
