@@ -76,6 +76,11 @@ def cpu_reference_tile(seed: int, threads: int):
     from oracle import bev_mapper as obm, geometry as ogeo, grids as ogrids
     from snap_b200 import configs, params, synthetic
     torch.set_num_threads(threads)
+    try:  # torchrun exports OMP_NUM_THREADS=1: lift the BLAS / OpenMP pools back to all host cores
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=threads)
+    except Exception:
+        pass
     cfg = configs.bev_mapper(("streetview",))
     p = params.init_bev_mapper(np.random.default_rng(7), cfg)
     data = synthetic.make_tile(seed, V, IMG_HW, G)
@@ -132,7 +137,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from snap_b200 import _lib, bev_mapper, configs, params, synthetic, types
+    from snap_b200 import _lib, bev_mapper, configs, parallel, params, synthetic, types
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -179,10 +184,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = parallel.max_over_ranks(ms, dev)   # job time = slowest rank
         barrier()
         return ms
 
@@ -395,6 +397,8 @@ def main():
                          "ms_per_launch": lift_ms, "algorithmic_flops": LIFT_FLOPS, "algorithmic_bytes": LIFT_BYTES,
                          "executed_flops": executed_flops, "executed_tflops": executed_flops / (lift_ms * 1e-3) / 1e12,
                          "visible_voxels": cnt[2], "voxels": G * G * Z,
+                         "worker_phase_share": dict(zip(["fill", "gather", "wait_mma1", "epilogue1", "wait_mma2", "epilogue2", "zmax"],
+                                                        [round(c / max(1, sum(cnt[4:11])), 3) for c in cnt[4:11]])),
                          "note": "achieved uses the ALGORITHMIC flops of the reference (MLP on every voxel); the kernel "
                                  "skips the MLP on voxels no camera sees (zero/invalid by streetview_encoder.py:282), so "
                                  "executed_flops < algorithmic_flops and frac may exceed the dense-GEMM ceiling",

@@ -97,44 +97,49 @@ __global__ void std_weights_write_kernel(const WeightDesc* __restrict__ descs,
 // root im2col: image f32 [Nimg,H,W,3] in [0,1] -> A [Nimg*Ho*Wo, Kp] bf16 for a KHxKW/stride conv
 // over the (Hp,Wp) zero-padded-then-normalised image (pad value becomes -1, resnet.py:199).
 // ------------------------------------------------------------------------------------------
-__global__ void root_im2col_kernel(const float* __restrict__ img, int Nimg, int H, int W, int Hp,
-                                   int Wp, int KH, int KW, int stride, int pad, int Ho, int Wo,
-                                   __nv_bfloat16* __restrict__ out, int Kp) {
-  const int chunks = Kp / 8;
-  const long long total = (long long)Nimg * Ho * Wo * chunks;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ch = (int)(idx % chunks);
-  const long long row = idx / chunks;
-  const int wo = (int)(row % Wo);
-  const int ho = (int)((row / Wo) % Ho);
-  const int n = (int)(row / ((long long)Wo * Ho));
-  const int K = KH * KW * 3;
-  float v[8];
+// One warp per output pixel; lane l writes the bf16 pairs (k = 2l, 2l+1), (2l+64, ..): the K axis of a row is
+// contiguous in the output (coalesced 128 B stores) and nearly contiguous in the NHWC image (kw, c fastest).
+template <int KW>
+__global__ void __launch_bounds__(256)
+root_im2col_kernel(const float* __restrict__ img, int Nimg, int H, int W, int Hp, int Wp, int KH,
+                   int stride, int pad, int Ho, int Wo, __nv_bfloat16* __restrict__ out, int Kp) {
+  const int lane = threadIdx.x & 31;
+  const int warp_id = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int total = Nimg * Ho * Wo;  // < 2^31 (checked by the host wrapper)
+  constexpr int KW3 = KW * 3;
+  const int K = KH * KW3;
+  for (int row = warp_id; row < total; row += nwarps) {
+    const int wo = row % Wo;
+    const int t_ = row / Wo;
+    const int ho = t_ % Ho;
+    const int n = t_ / Ho;
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    const float* base = img + (size_t)n * H * W * 3;
+    for (int k2 = lane * 2; k2 < Kp; k2 += 64) {
+      float v[2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = ch * 8 + j;
-    float val = 0.f;
-    if (k < K) {
-      const int c = k % 3;
-      const int kw = (k / 3) % KW;
-      const int kh = k / (3 * KW);
-      const int hi = ho * stride + kh - pad;
-      const int wi = wo * stride + kw - pad;
-      if (hi >= 0 && hi < Hp && wi >= 0 && wi < Wp) {
-        if (hi < H && wi < W) {
-          const float x = __bfloat162float(__float2bfloat16(img[(((size_t)n * H + hi) * W + wi) * 3 + c]));
-          val = __bfloat162float(__float2bfloat16(x * 2.0f - 1.0f));
-        } else {
-          val = -1.0f;
+      for (int e = 0; e < 2; ++e) {
+        const int k = k2 + e;
+        float val = 0.f;
+        if (k < K) {
+          const int kh = k / KW3, r = k - kh * KW3;
+          const int kw = r / 3, c = r - kw * 3;
+          const int hi = h0 + kh, wi = w0 + kw;
+          if (hi >= 0 && hi < Hp && wi >= 0 && wi < Wp) {
+            if (hi < H && wi < W) {
+              const float x = bf16_round(__ldg(base + ((size_t)hi * W + wi) * 3 + c));  // images.astype(dtype)
+              val = bf16_round(x * 2.0f - 1.0f);                                        // resnet.py:199
+            } else {
+              val = -1.0f;  // zero padding of pad_to_multiple, after 2x - 1
+            }
+          }
         }
+        v[e] = val;
       }
+      *reinterpret_cast<uint32_t*>(out + (size_t)row * Kp + k2) = pack_bf16(v[0], v[1]);
     }
-    v[j] = val;
   }
-  uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                       pack_bf16(v[6], v[7]));
-  *reinterpret_cast<uint4*>(out + row * Kp + ch * 8) = o;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -444,9 +449,16 @@ int snapb200_root_im2col(const float* images, int Nimg, int H, int W, int Hp, in
   SNAP_REQUIRE(Kp % 32 == 0 && Kp >= KH * KW * 3, "Kp must be a multiple of 32 covering KH*KW*3");
   SNAP_REQUIRE(Hp >= H && Wp >= W && stride >= 1, "bad padded size");
   const int Ho = (Hp + 2 * pad - KH) / stride + 1, Wo = (Wp + 2 * pad - KW) / stride + 1;
-  const long long total = (long long)Nimg * Ho * Wo * (Kp / 8);
-  root_im2col_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      images, Nimg, H, W, Hp, Wp, KH, KW, stride, pad, Ho, Wo, (__nv_bfloat16*)out_bf16, Kp);
+  const long long total_warps = (long long)Nimg * Ho * Wo;
+  long long blocks = (total_warps + 7) / 8;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;  // grid-stride over pixels
+  SNAP_REQUIRE(total_warps < (1ll << 31) && (KW == 7 || KW == 3), "root conv must be 7x7 or 3x3; too many pixels");
+  if (KW == 7)
+    root_im2col_kernel<7><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        images, Nimg, H, W, Hp, Wp, KH, stride, pad, Ho, Wo, (__nv_bfloat16*)out_bf16, Kp);
+  else
+    root_im2col_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        images, Nimg, H, W, Hp, Wp, KH, stride, pad, Ho, Wo, (__nv_bfloat16*)out_bf16, Kp);
   return check_launch("root_im2col_kernel");
 }
 

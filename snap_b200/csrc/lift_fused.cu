@@ -202,6 +202,14 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const float score_scale = (float)(P.S - 1);
     uint32_t tile_phase = 0;
     int n_tiles = 0, n_rows = 0;  // work counters (reported through col_counter[1..2])
+    long long tprof[7] = {0, 0, 0, 0, 0, 0, 0};  // cycles: fill, gather, wait acc1, epi1, wait acc2, epi2, z-max
+    long long tmark = clock64();
+#define LIFT_MARK(i)                  \
+  do {                                \
+    const long long now_ = clock64(); \
+    tprof[i] += now_ - tmark;         \
+    tmark = now_;                     \
+  } while (0)
     int zm_col = -1;       // z-max carry of thread wtid < 128 (one output channel each)
     float zm_val = 0.f;
 
@@ -278,6 +286,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       }
       const int rows = min(128, ctl->list_count);
       const int head = ctl->list_head;
+      LIFT_MARK(0);
       if (wtid == 0) ctl->more = rows > 0 ? 1 : 0;
       worker_bar();
       if (rows == 0) {
@@ -401,10 +410,12 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       }
       fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
       mbar_arrive(&ctl->a_full);
+      LIFT_MARK(1);
 
       // ---------- epilogue 1: H = relu(bf16(bf16(acc1 + smax * w256) + b1)) -> smem (A tile) ----------
       mbar_wait(&ctl->acc1_full, tile_phase);
       tc_fence_after_sync();
+      LIFT_MARK(2);
       {
         const int row = q * 32 + lane;
         const float sm = __bfloat162float(smax_s[row]);
@@ -442,10 +453,12 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&ctl->h_full);
+      LIFT_MARK(3);
 
       // ---------- epilogue 2: volume rows = bf16(bf16(acc2) + b2) -> smem staging ----------
       mbar_wait(&ctl->acc2_full, tile_phase);
       tc_fence_after_sync();
+      LIFT_MARK(4);
       {
         const int row = q * 32 + lane;
         const uint32_t taddr = tmem_acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 32);
@@ -473,21 +486,60 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       }
       tc_fence_before_sync();
       worker_bar();
+      LIFT_MARK(5);
 
-      // ---------- vertical max (bev_mapper.py:56-88): thread c owns output channel c ----------
-      if (wtid < 128) {
-        for (int r = 0; r < rows; ++r) {
+      // ---------- vertical max (bev_mapper.py:56-88) ----------
+      // 4 row parts x 128 channels: thread (part, c) scans 32 rows.  Column segments that start and end strictly
+      // inside a part are complete and written directly; the first / last segment of each part go to shared
+      // memory and are stitched (with the carry from the previous tile) by the 128 threads of part 0.
+      {
+        const int part = wtid >> 7, c = wtid & 127;
+        const int r_lo = part * 32, r_hi = min(rows, r_lo + 32);
+        int fcol = -1, lcol = -1;   // first / last column of this part
+        float fmax_ = 0.f, lmax_ = 0.f;
+        for (int r = r_lo; r < r_hi; ++r) {
           const int col = (int)(list[(head + r) % FL_LIST_CAP] >> 14);
-          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(smem + SM_AH + r * VOL_STRIDE + wtid * 2));
-          if (col != zm_col) {
+          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(smem + SM_AH + r * VOL_STRIDE + c * 2));
+          if (col != lcol) {
+            if (lcol >= 0 && lcol != fcol) {  // a middle segment just ended: complete
+              A.plane[(size_t)lcol * 128 + c] = __float2bfloat16(lmax_);
+              if (c == 0) A.pvalid[lcol] = 1;
+            }
+            if (fcol < 0) fcol = col;
+            lcol = col;
+            lmax_ = x;
+          } else {
+            lmax_ = fmaxf(lmax_, x);
+          }
+          if (lcol == fcol) fmax_ = lmax_;
+        }
+        // boundary record of (part, c): {fcol, fmax, lcol, lmax}; placed after the staged volume rows
+        float4* brec = reinterpret_cast<float4*>(smem + SM_AH + 128 * VOL_STRIDE + 256) + (part * 128 + c);
+        *brec = make_float4(__int_as_float(fcol), fmax_, __int_as_float(lcol), lmax_);
+      }
+      worker_bar();
+      if (wtid < 128) {
+        const float4* brec = reinterpret_cast<const float4*>(smem + SM_AH + 128 * VOL_STRIDE + 256);
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+          const float4 b4 = brec[part * 128 + wtid];
+          const int fcol = __float_as_int(b4.x), lcol = __float_as_int(b4.z);
+          if (fcol < 0) continue;  // part without rows
+          if (fcol == zm_col) {
+            zm_val = fmaxf(zm_val, b4.y);
+          } else {
             if (zm_col >= 0) {
               A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
               if (wtid == 0) A.pvalid[zm_col] = 1;
             }
-            zm_col = col;
-            zm_val = x;
-          } else {
-            zm_val = fmaxf(zm_val, x);
+            zm_col = fcol;
+            zm_val = b4.y;
+          }
+          if (lcol != fcol) {  // the first segment ended inside this part; the last one stays open
+            A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
+            if (wtid == 0) A.pvalid[zm_col] = 1;
+            zm_col = lcol;
+            zm_val = b4.w;
           }
         }
       }
@@ -499,10 +551,12 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       n_tiles += 1;
       n_rows += rows;
       tile_phase ^= 1;
+      LIFT_MARK(6);
     }
     if (wtid == 0) {
       atomicAdd(A.col_counter + 1, n_tiles);
       atomicAdd(A.col_counter + 2, n_rows);
+      for (int i = 0; i < 7; ++i) atomicAdd(A.col_counter + 4 + i, (int)(tprof[i] >> 4));  // units of 16 cycles
     }
     if (wtid < 128 && zm_col >= 0) {
       A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
@@ -559,7 +613,7 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
   if (rc) return rc;
   rc = check_cuda(cudaMemsetAsync(pvalid, 0, (size_t)cells, s), "memset valid");
   if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(col_counter, 0, 4 * sizeof(int), s), "memset counter");
+  rc = check_cuda(cudaMemsetAsync(col_counter, 0, 16 * sizeof(int), s), "memset counter");
   if (rc) return rc;
   FusedArgs a;
   memcpy(&a.P, q, sizeof(LiftParams));

@@ -106,7 +106,7 @@ class StreetViewEncoder:
             self._cache[key] = dict(
                 crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
                 volume=None, valid=None,   # [B,N,128] / [B,N]: allocated on first unfused call
-                plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 4, dt=torch.int32),
+                plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 16, dt=torch.int32),
                 scratch=z(ops.lift_fused_scratch_bytes(), dt=torch.uint8),
                 # per-scene inputs: pinned host staging + device copies (a captured CUDA graph re-reads the
                 # staging buffers at every replay, see `stage_inputs`)

@@ -226,7 +226,7 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
     # fused
     plane = torch.full((G * G, 128), 7.0, dtype=torch.bfloat16, device=dev)
     pv = torch.full((G * G,), 9, dtype=torch.uint8, device=dev)
-    counter = torch.zeros(4, dtype=torch.int32, device=dev)
+    counter = torch.zeros(16, dtype=torch.int32, device=dev)
     scratch = torch.zeros(ops.lift_fused_scratch_bytes(), dtype=torch.uint8, device=dev)
     w256 = _t(fp["Dense_0"]["kernel"][256]).to(dev)
     for _ in range(2):  # twice: the kernel must be re-entrant on the same buffers
