@@ -84,6 +84,14 @@ def bev_mapper(modalities: Iterable[str] = ("streetview", "aerial")) -> ConfigDi
     return cfg
 
 
+def semantic_net() -> ConfigDict:  # defaults.py:286-335 with the head of configs/train_semantics.py:27-30
+    return ConfigDict(bev_mapper=bev_mapper(), decoder_type="resnet_stage", decoder_dim=256, mlp_num_layers=2,
+                      resnet_num_units=2, apply_random_flip=False,
+                      area_classes=("crosswalk", "sidewalk", "road", "terrain", "building"),
+                      object_classes_exclusive=("fence", "pole", "tree"),
+                      object_classes_independent=("traffic_sign", "traffic_light", "street_light"))
+
+
 def get_block_desc(depth):  # snap/models/resnet.py:158-167
     if isinstance(depth, list):
         depth = tuple(depth)

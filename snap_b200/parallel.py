@@ -43,3 +43,49 @@ def sum_over_ranks(value: float, device: torch.device | str = "cpu") -> float:
 def job_throughput(units_this_rank: int, seconds_this_rank: float, device: torch.device | str = "cpu") -> float:
     """Whole-job units/s: all units of all ranks divided by the max-over-ranks time."""
     return sum_over_ranks(units_this_rank, device) / max_over_ranks(seconds_this_rank, device)
+
+
+# ---- data-parallel gradient mean (SURVEY §8a row 21) ----------------------------------------------------------
+
+def _leaves(tree, prefix=()):
+    if isinstance(tree, dict):
+        for k in sorted(tree):
+            yield from _leaves(tree[k], prefix + (k,))
+    elif isinstance(tree, (list, tuple)):
+        for i, v in enumerate(tree):
+            yield from _leaves(v, prefix + (i,))
+    elif tree is not None:
+        yield prefix, tree
+
+
+def pmean_tree(tree, bucket_bytes: int = 256 << 20, group=None):
+    """In-place mean over ranks of every tensor of a (nested dict / list) gradient tree — the counterpart of
+    `jax.lax.pmean(grad, axis_name='batch')` (`snap/trainer.py:231-234`).
+
+    Leaves are packed, in sorted key order (identical on every rank), into flat fp32 buckets of at most
+    `bucket_bytes` and each bucket is reduced with ONE all-reduce: the ≈48 M-parameter tree of the localisation
+    model (≈193 MB fp32) goes out in a single NCCL call instead of ≈330 per-leaf calls, so the cost is NVLink
+    bandwidth rather than launch latency.  Accumulation is fp32 whatever the leaf dtype; results are written back
+    into the leaves.  Identity without a process group.  Returns the number of all-reduce calls issued."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = dist.get_world_size(group)
+    leaves = [t for _, t in _leaves(tree)]
+    calls, i = 0, 0
+    while i < len(leaves):
+        j, nbytes = i, 0
+        while j < len(leaves) and (j == i or nbytes + leaves[j].numel() * 4 <= bucket_bytes):
+            nbytes += leaves[j].numel() * 4
+            j += 1
+        chunk = leaves[i:j]
+        flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in chunk])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        o = 0
+        for t in chunk:
+            n = t.numel()
+            t.detach().copy_(flat[o:o + n].view(t.shape))
+            o += n
+        calls += 1
+        i = j
+    return calls

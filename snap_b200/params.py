@@ -117,6 +117,22 @@ def init_bev_mapper(rng, cfg) -> Dict:
     return p
 
 
+def init_semantic_decoder(rng, cfg, in_dim: int = 128) -> Dict:
+    """`snap/models/semantic_net.py:145-165` (decoder_type='resnet_stage'): layers_0 Dense, layers_1 ResNetStage,
+    layers_3 MLP (Appendix B names)."""
+    dim = cfg.decoder_dim
+    nmid = dim // 4
+    k = len(cfg.area_classes) + len(cfg.object_classes_exclusive) + len(cfg.object_classes_independent) + 1
+    stage = {}
+    for u in range(cfg.resnet_num_units):
+        stage[f"unit{u + 1:02d}"] = {"gn1": _gn(dim), "gn2": _gn(nmid), "gn3": _gn(nmid),
+                                     "conv1": {"kernel": lecun_normal(rng, (1, 1, dim, nmid))},
+                                     "conv2": {"kernel": lecun_normal(rng, (3, 3, nmid, nmid))},
+                                     "conv3": {"kernel": lecun_normal(rng, (1, 1, nmid, dim))}}
+    return {"layers_0": {"kernel": glorot_uniform(rng, (in_dim, dim)), "bias": np.zeros((dim,), F)},
+            "layers_1": stage, "layers_3": init_mlp(rng, dim, (dim, k))}
+
+
 def perturb_affine(rng, tree: Dict, scale: float = 0.2) -> Dict:
     """Make GroupNorm scale/bias and Dense biases non-trivial so parity tests exercise them."""
     out = {}

@@ -23,7 +23,22 @@ def _worker(rank, world, port, out):
     parallel.barrier()
     thr = parallel.job_throughput(len(tiles), secs)
     mx = parallel.max_over_ranks(secs)
-    out.put((rank, tiles, thr, mx))
+    # gradient mean over ranks in flat buckets (row 21): rank r holds (r+1) * base
+    g = torch.Generator().manual_seed(3)
+    base = {"bev_mapper": {"fusion": {"kernel": torch.randn(257, 16, generator=g), "bias": torch.randn(16, generator=g)}},
+            "head": [torch.randn(5, generator=g).to(torch.bfloat16), torch.randn(3, 3, generator=g)]}
+    scale = lambda t: {k: scale(v) for k, v in t.items()} if isinstance(t, dict) else (
+        [scale(v) for v in t] if isinstance(t, list) else t * (rank + 1))
+    grads = scale(base)
+    calls_one = parallel.pmean_tree(grads)
+    want = lambda t: {k: want(v) for k, v in t.items()} if isinstance(t, dict) else (
+        [want(v) for v in t] if isinstance(t, list) else t.float() * 1.5)
+    flat = lambda t: torch.cat([x.float().reshape(-1) for _, x in parallel._leaves(t)])
+    err = float((flat(grads) - flat(want(base))).abs().max())
+    grads2 = scale(base)
+    calls_small = parallel.pmean_tree(grads2, bucket_bytes=64)
+    err2 = float((flat(grads2) - flat(grads)).abs().max())
+    out.put((rank, tiles, thr, mx, calls_one, err, calls_small, err2))
     dist.destroy_process_group()
 
 
@@ -39,7 +54,11 @@ def test_two_rank_gloo_sharding_and_timing():
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
-    (r0, t0, thr0, mx0), (r1, t1, thr1, mx1) = res
+    (r0, t0, thr0, mx0, *g0), (r1, t1, thr1, mx1, *g1) = res
+    assert g0 == g1
+    calls_one, err, calls_small, err2 = g0
+    assert calls_one == 1 and err < 2e-2                   # one bucket; bf16 leaf rounds on write-back
+    assert calls_small == 3 and err2 == 0.0                # bucketing does not change the result
     assert t0 == [0, 1, 2] and t1 == [3, 4, 5, 6]        # disjoint, complete, balanced
     assert mx0 == mx1 == 2.5
     assert abs(thr0 - 7 / 2.5) < 1e-9 and thr0 == thr1   # whole-job units / slowest rank
@@ -48,4 +67,5 @@ def test_two_rank_gloo_sharding_and_timing():
 def test_single_process_fallbacks():
     from snap_b200 import parallel
     assert parallel.shard_tiles(list(range(5)), 0, 1) == [0, 1, 2, 3, 4]
+    assert parallel.pmean_tree({"a": torch.ones(3)}) == 0
     assert parallel.max_over_ranks(3.0) == 3.0 and parallel.job_throughput(4, 2.0) == 2.0
