@@ -256,11 +256,14 @@ gn_accumulate_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int pre
 enum { LAYOUT_DENSE = 0, LAYOUT_PADDED = 1, LAYOUT_PHASE = 2 };
 
 // One thread owns a fixed 8-channel vector (its scale/bias/mean/rstd live in registers) and walks
-// over pixels; consecutive threads -> consecutive 16 B chunks (coalesced).
-__global__ void __launch_bounds__(256)
+// over pixels; consecutive threads -> consecutive 16 B chunks (coalesced).  The kernel is issue-sensitive (about 10
+// instructions per channel pair of useful math), so the pixel -> (h, w) bookkeeping is incremental (no division in
+// the loop) and compiled out of the dense layout.
+template <int LAYOUT, bool SUB, bool PRE>
+__global__ void __launch_bounds__(256, 3)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int C,
                 const double* __restrict__ acc, int replica_stride, const float* __restrict__ scale,
-                const float* __restrict__ bias, int pre_relu, int post_relu, int layout,
+                const float* __restrict__ bias, int post_relu,
                 int pix_per_block, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_sub) {
   const int CV = C / 8;
   const int PL = 256 / CV;
@@ -271,6 +274,15 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int
   const int cpg = C / 32;
   // one double-precision finalisation per group and CTA (mean, 1/sqrt(var + eps)), shared through smem
   __shared__ float2 s_stat[32];
+  // per-thread affine parameters do not depend on the statistics: fetch them while the statistics are finalised
+  __nv_bfloat162 sc2[4], bi2[4];  // scale / bias as packed bf16 (they are bf16 parameters in the reference)
+  if (pl < PL) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc2[j] = __floats2bfloat162_rn(__ldg(scale + c0 + 2 * j), __ldg(scale + c0 + 2 * j + 1));
+      bi2[j] = __floats2bfloat162_rn(__ldg(bias + c0 + 2 * j), __ldg(bias + c0 + 2 * j + 1));
+    }
+  }
   if (threadIdx.x < 32) {
     const int g = threadIdx.x;
     const double count = (double)HW * (double)cpg;
@@ -288,32 +300,34 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int
   __syncthreads();
   if (pl >= PL) return;
   float mean[8], rstd[8];
-  __nv_bfloat162 sc2[4], bi2[4];  // scale / bias as packed bf16 (they are bf16 parameters in the reference)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float2 st = s_stat[(c0 + j) / cpg];
     mean[j] = st.x;
     rstd[j] = st.y;
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sc2[j] = __floats2bfloat162_rn(__ldg(scale + c0 + 2 * j), __ldg(scale + c0 + 2 * j + 1));
-    bi2[j] = __floats2bfloat162_rn(__ldg(bias + c0 + 2 * j), __ldg(bias + c0 + 2 * j + 1));
-  }
   const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  const __nv_bfloat16* xin = x + (size_t)n * HW * C + c0;
+  int p = p0 + pl;
+  const uint4* xin = reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * C + c0);
+  const size_t xstep = (size_t)PL * CV;  // uint4 units between this thread's consecutive pixels
+  // incremental (h, w) of pixel p; per step: w += dw, h += dh, one carry
+  int h = 0, w = 0;
+  const int dh = PL / W, dw = PL - dh * W;
+  if (LAYOUT != LAYOUT_DENSE || SUB) {
+    h = p / W;
+    w = p - h * W;
+  }
   const int Hq = H / 2 + 1, Wq = W / 2 + 1;
-#pragma unroll 4
-  for (int p = p0 + pl; p < p1; p += PL) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)p * C));
-    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+  uint4* odense = reinterpret_cast<uint4*>(out + ((size_t)n * HW + p) * C + c0);
+  auto transform = [&](const uint4& uin) -> uint4 {
+    const uint32_t uu[4] = {uin.x, uin.y, uin.z, uin.w};
     uint32_t ov[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 t = unpack_bf16(uu[j]);
-      if (pre_relu) {
+      if (PRE) {
         t.x = fmaxf(t.x, 0.f);
         t.y = fmaxf(t.y, 0.f);
       }
@@ -326,23 +340,47 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int
       if (post_relu) v = __hmax2(v, zero2);
       ov[j] = *reinterpret_cast<uint32_t*>(&v);
     }
-    const uint4 o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-    const int h = p / W, w = p - h * W;
-    size_t orow;
-    if (layout == LAYOUT_DENSE) {
-      orow = (size_t)n * HW + p;
-    } else if (layout == LAYOUT_PADDED) {
-      orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+    return make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  };
+  auto store = [&](const uint4& o, uint4* dense_ptr) {
+    if (LAYOUT == LAYOUT_DENSE) {
+      *dense_ptr = o;
+    } else if (LAYOUT == LAYOUT_PADDED) {
+      const size_t orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+      *reinterpret_cast<uint4*>(out + orow * C + c0) = o;
     } else {
       const int hp = h + 1, wp = w + 1;
       const size_t plane = (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)Nimg * Hq * Wq);
-      orow = plane + ((size_t)n * Hq + (hp >> 1)) * Wq + (wp >> 1);
+      const size_t orow = plane + ((size_t)n * Hq + (hp >> 1)) * Wq + (wp >> 1);
+      *reinterpret_cast<uint4*>(out + orow * C + c0) = o;
     }
-    *reinterpret_cast<uint4*>(out + orow * C + c0) = o;
-    if (out_sub != nullptr && (h & 1) == 0 && (w & 1) == 0) {
+    if (SUB && (h & 1) == 0 && (w & 1) == 0) {
       const size_t srow = ((size_t)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
       *reinterpret_cast<uint4*>(out_sub + srow * C + c0) = o;
     }
+    if (LAYOUT != LAYOUT_DENSE || SUB) {
+      w += dw;
+      h += dh;
+      if (w >= W) {
+        w -= W;
+        ++h;
+      }
+    }
+  };
+  constexpr int UN = 8;
+  for (; p + (UN - 1) * PL < p1; p += UN * PL) {  // full batches: 8 loads in flight, no predicates
+    uint4 u[UN];
+#pragma unroll
+    for (int i = 0; i < UN; ++i) u[i] = __ldg(xin + i * xstep);
+#pragma unroll
+    for (int i = 0; i < UN; ++i) store(transform(u[i]), odense + i * xstep);
+    xin += UN * xstep;
+    odense += UN * xstep;
+  }
+  for (; p < p1; p += PL) {
+    store(transform(__ldg(xin)), odense);
+    xin += xstep;
+    odense += xstep;
   }
 }
 
@@ -500,12 +538,29 @@ int snapb200_gn_apply(const void* x, int Nimg, int H, int W, int C, const double
   SNAP_REQUIRE((layout != LAYOUT_PHASE && out_sub == nullptr) || (H % 2 == 0 && W % 2 == 0),
                "phase / subsampled layouts need even H, W");
   const int HW = H * W;
-  int ppb = 8 * (256 / (C / 8));  // 8 pixels per thread lane
+  // pixels per thread lane: 32 (amortises the per-CTA statistics finalisation) unless that leaves the GPU short of
+  // CTAs (8 x 148 resident), then 16 / 8
+  const int PL = 256 / (C / 8);
+  int ppl = 32;
+  while (ppl > 8 && (long long)Nimg * ((HW + PL * ppl - 1) / (PL * ppl)) < 8LL * num_sms()) ppl >>= 1;
+  int ppb = ppl * PL;
   if (ppb > HW) ppb = HW;
   dim3 grid((HW + ppb - 1) / ppb, Nimg);
-  gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, Nimg, H, W, C, acc, replica_stride, scale, bias, pre_relu, post_relu, layout, ppb,
-      (__nv_bfloat16*)out, (__nv_bfloat16*)out_sub);
+#define SNAP_GN_APPLY(L_, S_, P_)                                                                 \
+  gn_apply_kernel<L_, S_, P_><<<grid, 256, 0, (cudaStream_t)stream>>>(                               \
+      (const __nv_bfloat16*)x, Nimg, H, W, C, acc, replica_stride, scale, bias, post_relu, ppb,     \
+      (__nv_bfloat16*)out, (__nv_bfloat16*)out_sub)
+#define SNAP_GN_APPLY2(L_, S_) \
+  do { if (pre_relu) SNAP_GN_APPLY(L_, S_, true); else SNAP_GN_APPLY(L_, S_, false); } while (0)
+  if (layout == LAYOUT_DENSE) {
+    if (out_sub != nullptr) SNAP_GN_APPLY2(LAYOUT_DENSE, true); else SNAP_GN_APPLY2(LAYOUT_DENSE, false);
+  } else if (layout == LAYOUT_PADDED) {
+    if (out_sub != nullptr) SNAP_GN_APPLY2(LAYOUT_PADDED, true); else SNAP_GN_APPLY2(LAYOUT_PADDED, false);
+  } else {
+    if (out_sub != nullptr) SNAP_GN_APPLY2(LAYOUT_PHASE, true); else SNAP_GN_APPLY2(LAYOUT_PHASE, false);
+  }
+#undef SNAP_GN_APPLY2
+#undef SNAP_GN_APPLY
   return check_launch("gn_apply_kernel");
 }
 

@@ -1,12 +1,20 @@
 // Host launcher + C ABI for the tcgen05 GEMM engine (gemm_tc.cuh).
+#include <stdlib.h>
+#include <string.h>
+
 #include "gemm_launch.h"
 #include "gemm_tc.cuh"
 
 namespace snapb200 {
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v != nullptr && *v != 0 ? atoi(v) : dflt;
+}
+
 template <int BN, int BK>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int ctas_per_sm,
-                       cudaStream_t s) {
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                       const CUtensorMap& tmR, GemmParams p, int ctas_per_sm, cudaStream_t s) {
   using Cfg = GemmCfg<BN, BK>;
   static bool configured = false;
   if (!configured) {
@@ -23,29 +31,50 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > max_by_tmem) ctas_per_sm = max_by_tmem;
   if (ctas_per_sm > 2) ctas_per_sm = 2;  // register budget: __launch_bounds__(320, 2)
+  static const int env_ctas = env_int("SNAPB200_GEMM_CTAS", 0);  // tuning overrides (tools/gemm_sweep.py)
+  if (env_ctas > 0) ctas_per_sm = env_ctas > 2 ? 2 : env_ctas;
+  const bool so = p.stage_out != 0;
   int stages = p.nkb < Cfg::MAX_STAGES ? p.nkb : Cfg::MAX_STAGES;
   if (stages < 2) stages = 2;
-  while (stages > 2 && ctas_per_sm * Cfg::smem_bytes(stages) > 225 * 1024) --stages;
-  while (ctas_per_sm > 1 && ctas_per_sm * Cfg::smem_bytes(stages) > 225 * 1024) --ctas_per_sm;
+  while (stages > 2 && ctas_per_sm * Cfg::smem_bytes(stages, false, so) > 225 * 1024) --stages;
+  while (ctas_per_sm > 1 && ctas_per_sm * Cfg::smem_bytes(stages, false, so) > 225 * 1024) --ctas_per_sm;
   p.stages = stages;
   const int total = p.m_tiles * p.n_tiles;
   const int cap = num_sms() * ctas_per_sm;
   const int grid = total < cap ? total : cap;
-  gemm_tc_kernel<BN, BK><<<grid, GEMM_THREADS, Cfg::smem_bytes(stages), s>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, BK><<<grid, GEMM_THREADS, Cfg::smem_bytes(stages, false, so), s>>>(tmA, tmB, tmO, tmR, p);
   return check_launch("gemm_tc_kernel");
 }
 
 int launch_gemm(const void* A, long long a_rows, int a_cols, long long a_ld, const void* B,
-                long long b_rows, int b_cols, long long b_ld, int bn, int bk, const GemmParams& p,
+                long long b_rows, int b_cols, long long b_ld, int bn, int bk, const GemmParams& p_in,
                 cudaStream_t s, int ctas_per_sm) {
+  GemmParams p = p_in;
   SNAP_REQUIRE(p.m_tiles > 0 && p.n_tiles > 0 && p.nkb > 0, "empty GEMM");
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO, tmR;
+  memset(&tmO, 0, sizeof(tmO));
+  memset(&tmR, 0, sizeof(tmR));
+  // dense bf16 outputs leave through shared memory + TMA (whole 128-byte lines instead of 32 B per lane)
+  static const int env_so = env_int("SNAPB200_GEMM_STAGE_OUT", 1);
+  p.stage_out = env_so && p.epi == EPI_STORE && !p.remap && !p.out_f32 && (bn == 64 || bn == 128) && bk == 64 &&
+                p.N % 64 == 0 && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  if (p.stage_out) {
+    int rc = make_tmap_2d_bf16(&tmO, p.out, p.M_valid, p.N, p.ldo, 32, 64);
+    if (rc) return rc;
+    static const int env_rt = env_int("SNAPB200_GEMM_RES_TMA", 1);
+    p.res_tma = env_rt && p.residual != nullptr && p.ldr % 8 == 0 &&
+                (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+    if (p.res_tma) {
+      rc = make_tmap_2d_bf16(&tmR, p.residual, p.M_valid, p.N, p.ldr, 32, 64);
+      if (rc) return rc;
+    }
+  }
   int rc = make_tmap_2d_bf16(&tmA, A, a_rows, a_cols, a_ld, 128, bk);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, B, b_rows, b_cols, b_ld, bn, bk);
   if (rc) return rc;
 #define SNAP_GEMM_CASE(BN_, BK_) \
-  if (bn == BN_ && bk == BK_) return launch_inst<BN_, BK_>(tmA, tmB, p, ctas_per_sm, s);
+  if (bn == BN_ && bk == BK_) return launch_inst<BN_, BK_>(tmA, tmB, tmO, tmR, p, ctas_per_sm, s);
   SNAP_GEMM_CASE(16, 64)
   SNAP_GEMM_CASE(64, 64)
   SNAP_GEMM_CASE(128, 64)
@@ -102,7 +131,9 @@ static int launch_gn_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPa
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   const int threads = AMODE == AMODE_TGN ? GEMM_THREADS_TGN : GEMM_THREADS_GN;
-  gemm_tc_kernel<BN, 64, AMODE><<<grid, threads, Cfg::smem_bytes(stages, true), s>>>(tmA, tmB, p);
+  p.stage_out = 0;
+  p.res_tma = 0;
+  gemm_tc_kernel<BN, 64, AMODE><<<grid, threads, Cfg::smem_bytes(stages, true), s>>>(tmA, tmB, tmA, tmA, p);
   return check_launch("gemm_tc_kernel<gn>");
 }
 }  // namespace snapb200

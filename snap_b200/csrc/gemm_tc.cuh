@@ -55,6 +55,10 @@ struct GemmParams {
   long long gn_rows_per_img;
   int gn_cpg;  // channels per group = N / 32
   int gn_replica_stride;  // doubles between the GN_REPLICAS copies of the accumulator (contention spreading)
+  // staged output: the epilogue writes the bf16 tile into (128B-swizzled) shared memory and TMA stores it as whole
+  // 128-byte lines (dense row-major outputs without remap; BN = 64 or 128)
+  int stage_out;
+  int res_tma;  // with stage_out: the residual tile is TMA-loaded into the staging slab and added in place
   // A_GN mode: the A operand is produced in-kernel from the RAW activation tensor [n_img, H, W, C]:
   // GroupNorm (statistics from `g_acc`) + affine + ReLU with the reference's bf16 rounding chain, implicit
   // 1x1 / 3x3 (pad 1) window with stride 1 or 2, zero outside the image.  m = (img*Ho + ho)*Wo + wo.
@@ -93,8 +97,10 @@ struct GemmCfg {
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
   // +1024 for manual alignment, +512 for barriers (2 x 16 stage + 4 accumulator) / tmem pointer
-  static constexpr int smem_bytes(int stages, bool gn_tables = false) {
-    return stages * STAGE_BYTES + 1024 + 512 + (gn_tables ? GEMM_GN_TABLE_BYTES : 0);
+  static constexpr int OUT_STAGE_BYTES = BM * BN * 2;  // staged-output buffer (one 32-row slab per TMEM quadrant)
+  static constexpr int smem_bytes(int stages, bool gn_tables = false, bool stage_out = false) {
+    return stages * STAGE_BYTES + (stage_out ? OUT_STAGE_BYTES : 0) + 1024 + 512 +
+           (gn_tables ? GEMM_GN_TABLE_BYTES : 0);
   }
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(BK == 64 || BK == 32, "BK is one swizzle span: 128B or 64B of bf16");
@@ -133,36 +139,49 @@ __device__ __forceinline__ int seg_row_offset(const GemmParams& p, int seg) {
 }
 
 // Accumulate (sum, sumsq) of 16 consecutive output columns of one row into the GroupNorm accumulators.
-// Rows of a warp normally belong to one image: reduce over the 32 rows with shuffles and issue one
-// double atomic per (group, moment); warps straddling an image boundary fall back to per-row atomics.
+// Rows of a warp normally belong to one image: the NV = 2 * (groups in the chunk) partial moments of the 32 rows
+// are reduced with a recursive-halving exchange (NV-1 + (5 - log2 NV) shuffles instead of 5 * NV): after it, lane L
+// holds the warp total of value index L >> (5 - log2 NV), and those lanes issue ONE coalesced double atomic
+// instruction.  Warps straddling an image boundary fall back to per-row atomics.
 template <int SPAN>  // columns per group inside the 16-column chunk: 2, 4, 8 or 16
 __device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row_ok, int img, int col,
                                                   int cpg, double* acc, bool uniform, int img_ref,
                                                   int lane) {
+  constexpr int NG = 16 / SPAN;
+  constexpr int NV = 2 * NG;
+  float val[NV];
 #pragma unroll
-  for (int g = 0; g < 16 / SPAN; ++g) {
+  for (int g = 0; g < NG; ++g) {
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int j = 0; j < SPAN; ++j) {
       s += v[g * SPAN + j];
       q += v[g * SPAN + j] * v[g * SPAN + j];
     }
-    if (!row_ok) s = q = 0.f;
-    const int group = (col + g * SPAN) / cpg;
-    if (uniform) {
+    val[2 * g] = row_ok ? s : 0.f;
+    val[2 * g + 1] = row_ok ? q : 0.f;
+  }
+  const int group0 = col / cpg;
+  if (uniform) {
+    int off = 16;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
+    for (int h = NV / 2; h >= 1; h >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const float send = up ? val[i] : val[i + h];
+        const float keep = up ? val[i + h] : val[i];
+        val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
       }
-      if (lane == 0 && img_ref >= 0) {
-        atomicAdd(&acc[((size_t)img_ref * 32 + group) * 2 + 0], (double)s);
-        atomicAdd(&acc[((size_t)img_ref * 32 + group) * 2 + 1], (double)q);
-      }
-    } else if (row_ok) {
-      atomicAdd(&acc[((size_t)img * 32 + group) * 2 + 0], (double)s);
-      atomicAdd(&acc[((size_t)img * 32 + group) * 2 + 1], (double)q);
+      off >>= 1;
     }
+    for (; off >= 1; off >>= 1) val[0] += __shfl_xor_sync(0xffffffffu, val[0], off);
+    constexpr int LOG = NV == 16 ? 4 : (NV == 8 ? 3 : (NV == 4 ? 2 : 1));
+    if ((lane & ((1 << (5 - LOG)) - 1)) == 0 && img_ref >= 0)
+      atomicAdd(&acc[((size_t)img_ref * 32 + group0) * 2 + (lane >> (5 - LOG))], (double)val[0]);
+  } else if (row_ok) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) atomicAdd(&acc[((size_t)img * 32 + group0) * 2 + i], (double)val[i]);
   }
 }
 
@@ -184,6 +203,7 @@ template <int BN, int BK, int AMODE = AMODE_TMA>
 __global__ void __launch_bounds__(AMODE == AMODE_GN ? GEMM_THREADS_GN : (AMODE == AMODE_TGN ? GEMM_THREADS_TGN : GEMM_THREADS),
                                   AMODE == AMODE_TMA ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, BK>;
   constexpr bool AGN = AMODE == AMODE_GN;
@@ -192,15 +212,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage tiles are multiples of 1024 B)
+  const int out_stage_bytes = p.stage_out ? Cfg::OUT_STAGE_BYTES : 0;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + out_stage_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* ready_bar = tmem_empty + 4;  // [STAGES] A_TGN: tile transformed, MMA may consume it
+  uint64_t* ready_bar = tmem_empty + 4;  // [16] A_TGN: tile transformed, MMA may consume it
+  uint64_t* res_bar = ready_bar + 16;    // [4] staged residual slab of TMEM quadrant q has landed
   // A_GN / A_TGN tables (after the 512 B barrier block): per (image, group) (mean, rstd) and per channel pair packed
   // bf16x2 scale / bias
-  float2* g_stat = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES + 512);
+  float2* g_stat = reinterpret_cast<float2*>(out_stage + out_stage_bytes + 512);
   uint32_t* g_sc2 = reinterpret_cast<uint32_t*>(g_stat + GEMM_GN_MAX_IMG * 32);
   uint32_t* g_bi2 = g_sc2 + 1024;
 
@@ -214,6 +237,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.stage_out) tma_prefetch_desc(&tmO);
+    if (p.res_tma) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], AGN ? 1 + GEMM_GN_WARPS * 32 : 1);
       mbar_init(&empty_bar[s], 1);
@@ -476,6 +502,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int hw = (warp - 2) >> 2;  // 0/1: which half of the 16-column chunks (interleaved) it drains
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
+    uint8_t* slab = out_stage + q * (BN / 64) * 4096;  // this quadrant's 32-row staging slab
+    // residual slab of a tile: BN/64 boxes of 32 rows x 64 columns (issued by one thread per quadrant)
+    auto issue_residual = [&](int tile_id) {
+      if constexpr (BN % 64 == 0) {
+        const TileCoord tn = decode_tile(p, tile_id, BN);
+        int nbox = 0;
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h) nbox += (tn.nt * BN + h * 64 < p.N) ? 1 : 0;
+        mbar_arrive_expect_tx(&res_bar[q], (uint32_t)nbox * 4096u);
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h)
+          if (tn.nt * BN + h * 64 < p.N)
+            tma_load_2d(&tmR, &res_bar[q], slab + h * 4096, tn.nt * BN + h * 64, tn.mt * 128 + q * 32);
+      }
+    };
+    if (p.res_tma && hw == 0 && lane == 0 && tile_begin < tile_end) issue_residual(tile_begin);
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const TileCoord t = decode_tile(p, tile, BN);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -508,7 +551,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           gn_uniform = __all_sync(0xffffffffu, gn_img == gn_ref || gn_img == -1);
         }
         const bool rnd = !p.out_f32;
-        const bool has_res = p.residual != nullptr;
+        // conv fast path: no bias / activation / mask (rows beyond M are clipped by the store, masked in the statistics)
+        const bool fast = rnd && p.bias == nullptr && !p.relu && p.row_mask == nullptr;
+        const bool has_res = p.residual != nullptr && !p.res_tma;
         const __nv_bfloat16* res_row = has_res ? p.residual + orow * p.ldr : nullptr;
 
         // One 16-column chunk: all roundings the reference applies (dot -> dtype, + bias -> dtype,
@@ -516,51 +561,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         auto process = [&](const uint32_t (&v)[16], const uint4& r0, const uint4& r1, int c16) {
           const int col = n0 + c16 * 16;
           if (col >= p.N) return;  // warp-uniform
-          float f[16];
+          uint32_t pk[8];
+          if (fast) {
+            // plain conv output (+ residual): the dot product is rounded to bf16 while packing (one F2FP per pair)
+            // and the residual is added as packed bf16 (HADD2.BF16 = exact sum, one rounding: identical to the
+            // fp32 add + cast of the reference because both addends are bf16)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = rnd ? bf16_round(__uint_as_float(v[j])) : __uint_as_float(v[j]);
-          if (p.bias) {
+            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if (p.res_tma) {
+              const uint8_t* rowp = slab + (c16 >> 2) * 4096 + lane * 128;
+              const int j = (c16 & 3) * 2, sw = lane & 7;
+              const uint4 s0 = *reinterpret_cast<const uint4*>(rowp + ((j ^ sw) << 4));
+              const uint4 s1 = *reinterpret_cast<const uint4*>(rowp + (((j + 1) ^ sw) << 4));
+              const uint32_t rr[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j4);
-              const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+              for (int j2 = 0; j2 < 8; ++j2) pk[j2] = hadd2_bf16_rn(pk[j2], rr[j2]);
+            } else if (has_res) {
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x = f[j4 * 4 + e] + bs[e];
-                f[j4 * 4 + e] = rnd ? bf16_round(x) : x;
+              for (int j2 = 0; j2 < 8; ++j2) pk[j2] = hadd2_bf16_rn(pk[j2], rr[j2]);
+            }
+          } else {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = rnd ? bf16_round(__uint_as_float(v[j])) : __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j4);
+                const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x = f[j4 * 4 + e] + bs[e];
+                  f[j4 * 4 + e] = rnd ? bf16_round(x) : x;
+                }
               }
             }
-          }
-          if (has_res) {
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            if (p.res_tma) {
+              const uint8_t* rowp = slab + (c16 >> 2) * 4096 + lane * 128;
+              const int j = (c16 & 3) * 2, sw = lane & 7;
+              const uint4 s0 = *reinterpret_cast<const uint4*>(rowp + ((j ^ sw) << 4));
+              const uint4 s1 = *reinterpret_cast<const uint4*>(rowp + (((j + 1) ^ sw) << 4));
+              const uint32_t rr[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 x = unpack_bf16(rr[j]);
-              f[2 * j] += x.x;
-              f[2 * j + 1] += x.y;
+              for (int j2 = 0; j2 < 8; ++j2) {
+                const float2 x = unpack_bf16(rr[j2]);
+                f[2 * j2] += x.x;
+                f[2 * j2 + 1] += x.y;
+              }
+            } else if (has_res) {
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 x = unpack_bf16(rr[j]);
+                f[2 * j] += x.x;
+                f[2 * j + 1] += x.y;
+              }
             }
-          }
-          if (p.relu) {
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (!keep) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = 0.f;
-          }
-          if (p.out_f32) {
-            if (row_ok) {
-              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            return;
-          }
-          uint32_t pk[8];
+            if (!keep) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-          if (row_ok) {
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+            }
+            if (p.out_f32) {
+              if (row_ok) {
+                float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + col);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              }
+              return;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+          }
+          if (p.stage_out) {
+            // slab of this TMEM quadrant: [BN/64 halves][32 rows][128 B], 16-byte chunks XOR-swizzled by row % 8
+            // (the TMA SWIZZLE_128B pattern; also makes the row-per-lane 16 B stores bank-conflict free)
+            uint8_t* rowp = slab + (c16 >> 2) * 4096 + lane * 128;
+            const int j = (c16 & 3) * 2, sw = lane & 7;
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(rowp + (((j + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else if (row_ok) {
             uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col);
             op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -593,6 +678,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // software pipeline over this warp's chunks (hw, hw+2, ...): the TMEM load and the residual
         // load of the next chunk are in flight while the current chunk is processed
         constexpr int NCH = BN / 16;
+        if (p.res_tma) {  // residual slab landed (which also implies the previous store released the slab)
+          mbar_wait(&res_bar[q], res_phase);
+          res_phase ^= 1;
+        } else if (p.stage_out) {  // the slab is free once the previous tile's TMA store has read it
+          if (hw == 0 && lane == 0) bulk_wait_group_read0();
+          pair_bar_sync(q);
+        }
         uint32_t va[16], vb[16];
         uint4 ra0 = make_uint4(0, 0, 0, 0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
         int c = hw;
@@ -617,6 +709,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           process(vb, rb0, rb1, c);
           c += 2;
+        }
+        if (p.stage_out) {
+          fence_proxy_async_smem();
+          pair_bar_sync(q);
+          if (hw == 0 && lane == 0) {
+            if constexpr (BN % 64 == 0) {
+#pragma unroll
+              for (int h = 0; h < BN / 64; ++h)
+                if (n0 + h * 64 < p.N)
+                  tma_store_2d(&tmO, slab + h * 4096, n0 + h * 64, t.mt * 128 + q * 32);
+            }
+            bulk_commit_group();
+            if (p.res_tma && tile + 1 < tile_end) {  // prefetch the next tile's residual behind the MMA wait
+              bulk_wait_group_read0();
+              issue_residual(tile + 1);
+            }
+          }
         }
       } else {
         // EPI_XCORR: tile = (example b, shift row u, 128 shift columns); column n = rotation r.
@@ -652,6 +761,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1;
       }
     }
+    if (p.stage_out && hw == 0 && lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before_sync();
