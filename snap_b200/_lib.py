@@ -80,6 +80,15 @@ class ConvGnParams(C.Structure):
     ]
 
 
+class RootConvParams(C.Structure):
+    _fields_ = [
+        ("packed", C.c_void_p), ("n_img", C.c_int), ("Hq", C.c_int), ("Wq", C.c_int), ("cp", C.c_int),
+        ("KH", C.c_int), ("stride", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int),
+        ("b", C.c_void_p), ("n", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong),
+        ("gn_acc", C.c_void_p), ("gn_replica_stride", C.c_int),
+    ]
+
+
 class WeightDesc(C.Structure):
     _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("partial", C.c_void_p),
                 ("K", C.c_int), ("Cout", C.c_int), ("ldb", C.c_int), ("standardize", C.c_int),
@@ -103,7 +112,8 @@ class LiftParams(C.Structure):
 
 
 EXPORTED_SYMBOLS += [
-    "snapb200_std_weights_batched", "snapb200_root_im2col", "snapb200_maxpool3x3s2",
+    "snapb200_std_weights_batched", "snapb200_root_im2col", "snapb200_root_pack_image", "snapb200_root_pack_weights",
+    "snapb200_root_conv_bf16", "snapb200_maxpool3x3s2",
     "snapb200_gn_stats", "snapb200_gn_apply", "snapb200_upsample2x",
     "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_lift_fused", "snapb200_lift_fused_scratch_bytes", "snapb200_vertical_max", "snapb200_match_head",
     "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_xcorr_padded_rotations", "snapb200_rot_templates",

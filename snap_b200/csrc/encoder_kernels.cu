@@ -53,7 +53,7 @@ __global__ void std_weights_stats_kernel(const WeightDesc* __restrict__ descs,
 
 __global__ void std_weights_write_kernel(const WeightDesc* __restrict__ descs,
                                          const int4* __restrict__ map, float eps) {
-  const int4 m = map[blockIdx.x];  // (desc, cout tile, k tile of 32, -)
+  const int4 m = map[blockIdx.x];  // (desc, cout tile, k chunk of 8 x 32, -)
   const WeightDesc d = descs[m.x];
   __shared__ float s_mean[32], s_rstd[32];
   __shared__ float tile[32][33];
@@ -78,19 +78,68 @@ __global__ void std_weights_write_kernel(const WeightDesc* __restrict__ descs,
   }
   __syncthreads();
   const int co = m.y * 32 + threadIdx.x;
-  const int kb = m.z * 32;
-  for (int kk = threadIdx.y; kk < 32; kk += 8) {
-    const int k = kb + kk;
-    float v = 0.f;
-    if (co < d.Cout && k < d.K) v = (d.w[(size_t)k * d.Cout + co] - s_mean[threadIdx.x]) * s_rstd[threadIdx.x];
-    tile[kk][threadIdx.x] = v;
+  // a block converts up to 8 consecutive 32 x 32 tiles (256 k) of its 32 output channels: the statistics prologue
+  // above (a chain of dependent global loads) is paid once per 8 tiles
+  for (int sub = 0; sub < 8; ++sub) {
+    const int kb = (m.z * 8 + sub) * 32;
+    if (kb >= d.ldb) break;
+    for (int kk = threadIdx.y; kk < 32; kk += 8) {
+      const int k = kb + kk;
+      float v = 0.f;
+      if (co < d.Cout && k < d.K) v = (d.w[(size_t)k * d.Cout + co] - s_mean[threadIdx.x]) * s_rstd[threadIdx.x];
+      tile[kk][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int cc = threadIdx.y; cc < 32; cc += 8) {
+      const int c2 = m.y * 32 + cc;
+      const int k = kb + threadIdx.x;
+      if (c2 < d.Cout && k < d.ldb) d.out[(size_t)c2 * d.ldb + k] = __float2bfloat16(tile[threadIdx.x][cc]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int cc = threadIdx.y; cc < 32; cc += 8) {
-    const int c2 = m.y * 32 + cc;
-    const int k = kb + threadIdx.x;
-    if (c2 < d.Cout && k < d.ldb) d.out[(size_t)c2 * d.ldb + k] = __float2bfloat16(tile[threadIdx.x][cc]);
+}
+
+// ------------------------------------------------------------------------------------------
+// implicit root conv: packed image + per-kernel-row weight layout (see snapb200.h)
+// ------------------------------------------------------------------------------------------
+__global__ void root_pack_image_kernel(const float* __restrict__ img, int Nimg, int H, int W, int Hp, int Wp, int pad,
+                                       int cp, int Hq, int Wq, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)Nimg * Hq * Wq;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wq = (int)(idx % Wq);
+  const long long t = idx / Wq;
+  const int hq = (int)(t % Hq);
+  const int n = (int)(t / Hq);
+  const int h = hq - pad, w = wq - pad;
+  float v[3] = {0.f, 0.f, 0.f};
+  if (h >= 0 && h < Hp && w >= 0 && w < Wp) {
+    if (h < H && w < W) {
+      const float* px = img + (((size_t)n * H + h) * W + w) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = bf16_round(bf16_round(__ldg(px + c)) * 2.0f - 1.0f);  // resnet.py:199
+    } else {
+      v[0] = v[1] = v[2] = -1.0f;  // zero padding of pad_to_multiple, after 2x - 1
+    }
   }
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + (size_t)idx * cp);
+  o[0] = pack_bf16(v[0], v[1]);
+  o[1] = pack_bf16(v[2], 0.f);
+  if (cp == 8) {
+    o[2] = 0u;
+    o[3] = 0u;
+  }
+}
+
+__global__ void root_pack_weights_kernel(const __nv_bfloat16* __restrict__ b, int Cout, int ldb, int KH, int KW, int cp,
+                                         __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * KH * 32) return;
+  const int e = idx % 32, kh = (idx / 32) % KH, co = idx / (32 * KH);
+  const int kw = e / cp, c = e - kw * cp;
+  __nv_bfloat16 v = __float2bfloat16(0.f);
+  if (kw < KW && c < 3) v = b[(size_t)co * ldb + (kh * KW + kw) * 3 + c];
+  out[idx] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -479,6 +528,25 @@ int snapb200_std_weights_batched(const void* descs, const void* mapA, int nA, co
   std_weights_write_kernel<<<nB, block, 0, (cudaStream_t)stream>>>((const WeightDesc*)descs,
                                                                   (const int4*)mapB, 1e-10f);
   return check_launch("std_weights_write_kernel");
+}
+
+int snapb200_root_pack_image(const float* images, int Nimg, int H, int W, int Hp, int Wp, int pad, int cp, int Hq,
+                             int Wq, void* out, void* stream) {
+  SNAP_REQUIRE(images && out && Nimg > 0, "bad arguments");
+  SNAP_REQUIRE(cp == 4 || cp == 8, "cp must be 4 or 8");
+  SNAP_REQUIRE(Hq >= Hp + 2 * pad && Wq >= Wp + 2 * pad && (Wq * cp * 2) % 16 == 0, "bad packed geometry");
+  const long long total = (long long)Nimg * Hq * Wq;
+  root_pack_image_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, Nimg, H, W, Hp, Wp, pad, cp,
+                                                                                  Hq, Wq, (__nv_bfloat16*)out);
+  return check_launch("root_pack_image_kernel");
+}
+
+int snapb200_root_pack_weights(const void* b_std, int Cout, int ldb, int KH, int KW, int cp, void* out, void* stream) {
+  SNAP_REQUIRE(b_std && out && KW * cp <= 32 && KH * KW * 3 <= ldb, "bad arguments");
+  const long long total = (long long)Cout * KH * 32;
+  root_pack_weights_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)b_std, Cout, ldb, KH, KW, cp, (__nv_bfloat16*)out);
+  return check_launch("root_pack_weights_kernel");
 }
 
 int snapb200_root_im2col(const float* images, int Nimg, int H, int W, int Hp, int Wp, int KH, int KW,

@@ -272,3 +272,60 @@ extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
   return launch_gemm(q->a, q->a_rows, q->a_cols, q->a_ld, q->b, q->b_rows, q->b_cols, q->b_ld, bn,
                      bk, p, static_cast<cudaStream_t>(stream), ctas);
 }
+
+/* Implicit root conv: see snapb200.h.  M space = [n_img*Ho row blocks] x [wtiles*128 columns]; the epilogue's row remap
+   drops the columns >= Wo of the last block. */
+extern "C" int snapb200_root_conv_bf16(const SnapRootConvParams* q, void* stream) {
+  SNAP_REQUIRE(q != nullptr && q->packed && q->b && q->out, "null operand");
+  SNAP_REQUIRE(q->cp == 4 || q->cp == 8, "cp must be 4 or 8");
+  SNAP_REQUIRE(q->stride * q->cp * 2 == 16, "window step must be 16 bytes (stride 2 with cp 4, stride 1 with cp 8)");
+  SNAP_REQUIRE(q->KH >= 1 && q->KH <= 9, "KH out of range");
+  SNAP_REQUIRE(q->n >= 16 && q->n % 16 == 0 && q->n <= 256 && q->ldo % 8 == 0, "bad n / ldo");
+  SNAP_REQUIRE((q->Ho - 1) * q->stride + q->KH <= q->Hq, "packed image too short");
+  SNAP_REQUIRE(((q->Wo - 1) * q->stride) * q->cp + 32 <= q->Wq * q->cp, "packed image too narrow");
+  const int wtiles = (q->Wo + 127) / 128;
+  GemmParams p = {};
+  p.a4d = 1;
+  p.r4_wtiles = wtiles;
+  p.r4_Ho = q->Ho;
+  p.r4_stride = q->stride;
+  const int bn = pick_bn(q->n, 32);
+  p.m_tiles = q->n_img * q->Ho * wtiles;
+  p.n_tiles = (q->n + bn - 1) / bn;
+  p.kps = 1;
+  p.nkb = q->KH;
+  p.seg_kstride = 32;
+  p.seg_mode = SEG_TABLE;
+  p.tile_mode = TILE_LINEAR;
+  p.epi = EPI_STORE;
+  p.M_valid = (long long)p.m_tiles * 128;
+  p.N = q->n;
+  p.out = q->out;
+  p.ldo = q->ldo;
+  p.remap = 1;
+  p.rm_R = q->Ho;
+  p.rm_C = wtiles * 128;
+  p.rm_r0 = 0;
+  p.rm_c0 = 0;
+  p.rm_Ho = q->Ho;
+  p.rm_Wo = q->Wo;
+  p.gn_acc = q->gn_acc;
+  p.gn_rows_per_img = (long long)q->Ho * q->Wo;
+  p.gn_cpg = q->n / 32;
+  p.gn_replica_stride = q->gn_replica_stride;
+  if (q->gn_acc != nullptr)
+    SNAP_REQUIRE(q->n % 64 == 0 && q->gn_replica_stride > 0, "gn_acc needs n %% 64 == 0 and gn_replica_stride");
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_window4d_bf16(&tmA, q->packed, q->Wo, (long long)q->stride * q->cp * 2, q->Hq,
+                                   (long long)q->Wq * q->cp * 2, q->n_img);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, q->b, q->n, q->KH * 32, q->KH * 32, bn, 32);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch_inst<64, 32>(tmA, tmB, tmA, tmA, p, 2, s);
+    case 128: return launch_inst<128, 32>(tmA, tmB, tmA, tmA, p, 2, s);
+    case 256: return launch_inst<256, 32>(tmA, tmB, tmA, tmA, p, 1, s);
+    default: return set_error(SNAPB200_ERR_INVALID, "root conv: unsupported channel count %d", q->n);
+  }
+}

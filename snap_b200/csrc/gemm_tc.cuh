@@ -35,6 +35,9 @@ struct GemmParams {
   int xc_G, xc_P, xc_U, xc_vt, xc_R;
   long long xc_rows_per_b;
   int tile_mode;
+  // implicit root conv (a4d): A is a 4D sliding-window map over the packed image; m-tile mt = (image row block
+  // n*Ho + ho, block of 128 output columns), segment = kernel row kh, one 32-element k-block per segment
+  int a4d, r4_wtiles, r4_Ho, r4_stride;
   // epilogue
   int epi;
   long long M_valid;
@@ -293,7 +296,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive_expect_tx(&full_bar[stage], AGN ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          if (!AGN) tma_load_2d(&tmA, &full_bar[stage], sa, p.a_col0 + kc * BK, t.a_row + a_off);
+          if (!AGN) {
+            if (p.a4d) {
+              const int rb = t.mt / p.r4_wtiles, wb = t.mt - rb * p.r4_wtiles;
+              const int n = rb / p.r4_Ho, ho = rb - n * p.r4_Ho;
+              tma_load_4d(&tmA, &full_bar[stage], sa, 0, wb * 128, ho * p.r4_stride + seg, n);
+            } else {
+              tma_load_2d(&tmA, &full_bar[stage], sa, p.a_col0 + kc * BK, t.a_row + a_off);
+            }
+          }
           if (p.b_seg_rows == 0)
             tma_load_2d(&tmB, &full_bar[stage], sb, seg * p.seg_kstride + kc * BK, t.b_row);
           else  // B stored segment-major: [segment][rows][BK] (contiguous tile per segment)

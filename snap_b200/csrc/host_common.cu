@@ -105,6 +105,26 @@ int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, long long rows, 
   return SNAPB200_OK;
 }
 
+int make_tmap_window4d_bf16(CUtensorMap* out, const void* base, int Wo, long long step_bytes, int Hq,
+                            long long row_bytes, int N) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  SNAP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SNAP_REQUIRE(step_bytes % 16 == 0 && row_bytes % 16 == 0, "window step / row pitch must be multiples of 16 bytes");
+  cuuint64_t dims[4] = {32, (cuuint64_t)Wo, (cuuint64_t)Hq, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)step_bytes, (cuuint64_t)row_bytes, (cuuint64_t)row_bytes * (cuuint64_t)Hq};
+  cuuint32_t box[4] = {32, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled(window4d) failed (%d) Wo=%d step=%lld Hq=%d row=%lld N=%d",
+                     (int)r, Wo, step_bytes, Hq, row_bytes, N);
+  return SNAPB200_OK;
+}
+
 }  // namespace snapb200
 
 extern "C" {

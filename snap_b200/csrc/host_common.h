@@ -26,6 +26,11 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, long long rows, long l
 int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld,
                             int box_rows, int box_cols);
 
+// 4D bf16 "sliding window" map over a packed NHWC image (implicit root conv): dims {32 (window elements, contiguous),
+// Wo (stride step_bytes: windows OVERLAP), Hq (row pitch), N}; box {32, 128, 1, 1}; SWIZZLE_64B.
+int make_tmap_window4d_bf16(CUtensorMap* out, const void* base, int Wo, long long step_bytes, int Hq,
+                            long long row_bytes, int N);
+
 #define SNAP_REQUIRE(cond, ...)                                        \
   do {                                                                 \
     if (!(cond)) return set_error(SNAPB200_ERR_INVALID, __VA_ARGS__);  \

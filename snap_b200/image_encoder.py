@@ -68,7 +68,7 @@ class _WeightBank:
             ct = (cout + 31) // 32
             if std:
                 mapA += [(i, c, s, 0) for c in range(ct) for s in range(ksplit)]
-            mapB += [(i, c, t, 0) for c in range(ct) for t in range(ldb // 32)]
+            mapB += [(i, c, t, 0) for c in range(ct) for t in range((ldb + 255) // 256)]
         raw = np.frombuffer(bytes(descs), dtype=np.uint8).copy()
         self.descs = torch.from_numpy(raw).to(dev)
         self.mapA = torch.tensor(mapA, dtype=torch.int32, device=dev) if mapA else None
@@ -119,7 +119,13 @@ class EncoderPlan:
             H0, W0 = self.Hp // 2, self.Wp // 2
         self.rootHW = (H0, W0)
         self.root_kp = bank.entries[self.root_w][3]
-        self.a_root = bf(n_img * H0 * W0, self.root_kp)
+        # implicit root conv: packed bf16 image (+ one row of slack for the last window) and per-kernel-row weights
+        kh_, kw_, st_, pd_ = self.root_geom
+        self.root_pack = ops.root_packed_geometry(self.Hp, self.Wp, kh_, kw_, st_, pd_)
+        cp_, Hq_, Wq_, Ho_, Wo_ = self.root_pack
+        assert (Ho_, Wo_) == (H0, W0), (Ho_, Wo_, H0, W0)
+        self.img_packed = torch.zeros(n_img * Hq_ * Wq_ * cp_ + 64, dtype=torch.bfloat16, device=device)
+        self.root_b = torch.zeros((max(width, 16), kh_ * 32), dtype=torch.bfloat16, device=device)
         self.y_root = bf(n_img * H0 * W0, width)
         if self.skip_root:
             self.x0, self.x0HW = self.y_root, (H0, W0)
@@ -201,13 +207,15 @@ class EncoderPlan:
         kh, kw, st, pd = self.root_geom
         H0, W0 = self.rootHW
         acc0 = self.units[0]["acc"][0]
+        cp, Hq, Wq, _, _ = self.root_pack
+        width = self.y_root.shape[1]
         if not im2col_done:
-            ops.root_im2col(images, self.Hp, self.Wp, kh, kw, st, pd, self.a_root)
+            ops.root_pack_image(images, self.Hp, self.Wp, pd, cp, Hq, Wq, self.img_packed)
+        ops.root_pack_weights(self.bank.b_mats[self.root_w], width, kh, kw, cp, self.root_b)
         if self.skip_root:
-            ops.gemm(self.a_root, self.bank.b_mats[self.root_w], self.y_root, m_rows=n * H0 * W0, seg_k=self.root_kp,
-                     gn_acc=acc0, gn_rows_per_img=H0 * W0)
+            ops.root_conv(self.img_packed, n, Hq, Wq, cp, kh, st, H0, W0, self.root_b, width, self.y_root, gn_acc=acc0)
         else:
-            ops.gemm(self.a_root, self.bank.b_mats[self.root_w], self.y_root, m_rows=n * H0 * W0, seg_k=self.root_kp)
+            ops.root_conv(self.img_packed, n, Hq, Wq, cp, kh, st, H0, W0, self.root_b, width, self.y_root)
             ops.maxpool3x3s2(self.y_root, n, H0, W0, self.y_root.shape[1], self.x0)
             ops.gn_stats(self.x0, n, self.x0HW[0] * self.x0HW[1], self.y_root.shape[1], False, acc0)
         return self.x0
@@ -329,13 +337,14 @@ class EncoderPlan:
     def run(self, images: torch.Tensor) -> List[torch.Tensor]:
         """images f32 [n,H,W,3] in [0,1] (device) -> FPN features coarse->fine, each [n,h,w,C] bf16 (uncropped)."""
         main, side = torch.cuda.current_stream(), self._side()
-        # the StdConv weight standardisation does not depend on the images: overlap it with the root im2col
+        # the StdConv weight standardisation does not depend on the images: overlap it with the image packing
         side.wait_stream(main)
         with torch.cuda.stream(side):
             self.bank.run()
         self.gn_acc_all.zero_()
         kh, kw, st, pd = self.root_geom
-        ops.root_im2col(images, self.Hp, self.Wp, kh, kw, st, pd, self.a_root)
+        cp, Hq, Wq, _, _ = self.root_pack
+        ops.root_pack_image(images, self.Hp, self.Wp, pd, cp, Hq, Wq, self.img_packed)
         main.wait_stream(side)
         x = self.run_root(images, im2col_done=True)
         for i, u in enumerate(self.units):

@@ -149,6 +149,46 @@ def root_im2col(images: torch.Tensor, Hp: int, Wp: int, KH: int, KW: int, stride
         C.c_int(out.shape[1]), _stream()))
 
 
+def root_packed_geometry(Hp: int, Wp: int, KH: int, KW: int, stride: int, pad: int):
+    """(cp, Hq, Wq, Ho, Wo) of the packed image of the implicit root conv (see include/snapb200.h)."""
+    cp = 8 // stride  # window step stride*cp*2 B must be 16 B
+    assert stride in (1, 2) and KW * cp <= 32
+    Ho, Wo = (Hp + 2 * pad - KH) // stride + 1, (Wp + 2 * pad - KW) // stride + 1
+    Hq = max(Hp + 2 * pad, (Ho - 1) * stride + KH)
+    Wq = max(Wp + 2 * pad, (Wo - 1) * stride + 32 // cp)
+    Wq += Wq % 2
+    return cp, Hq, Wq, Ho, Wo
+
+
+def root_pack_image(images: torch.Tensor, Hp: int, Wp: int, pad: int, cp: int, Hq: int, Wq: int,
+                    out: torch.Tensor) -> None:
+    _require(images, torch.float32, "images")
+    _require(out, torch.bfloat16, "out")
+    n, H, W, c = images.shape
+    assert c == 3 and images.is_contiguous() and out.numel() >= n * Hq * Wq * cp
+    _lib.check(_lib.lib().snapb200_root_pack_image(C.c_void_p(_ptr(images)), n, H, W, Hp, Wp, pad, cp, Hq, Wq,
+                                                   C.c_void_p(_ptr(out)), _stream()))
+
+
+def root_pack_weights(b_std: torch.Tensor, cout: int, KH: int, KW: int, cp: int, out: torch.Tensor) -> None:
+    _require(b_std, torch.bfloat16, "b_std")
+    assert out.shape[1] == KH * 32 and out.shape[0] >= cout
+    _lib.check(_lib.lib().snapb200_root_pack_weights(C.c_void_p(_ptr(b_std)), cout, b_std.stride(0), KH, KW, cp,
+                                                     C.c_void_p(_ptr(out)), _stream()))
+
+
+def root_conv(packed: torch.Tensor, n: int, Hq: int, Wq: int, cp: int, KH: int, stride: int, Ho: int, Wo: int,
+              b: torch.Tensor, cout: int, out: torch.Tensor, gn_acc: Optional[torch.Tensor] = None) -> None:
+    p = _lib.RootConvParams()
+    p.packed, p.n_img, p.Hq, p.Wq, p.cp = _ptr(packed), n, Hq, Wq, cp
+    p.KH, p.stride, p.Ho, p.Wo = KH, stride, Ho, Wo
+    p.b, p.n, p.out, p.ldo = _ptr(b), cout, _ptr(out), out.stride(0)
+    if gn_acc is not None:
+        _require(gn_acc, torch.float64, "gn_acc")
+        p.gn_acc, p.gn_replica_stride = _ptr(gn_acc), gn_acc.stride(0)
+    _lib.check(_lib.lib().snapb200_root_conv_bf16(C.byref(p), _stream()))
+
+
 def maxpool3x3s2(x: torch.Tensor, n: int, H: int, W: int, Cc: int, y: torch.Tensor) -> None:
     _lib.check(_lib.lib().snapb200_maxpool3x3s2(C.c_void_p(_ptr(x)), n, H, W, Cc, C.c_void_p(_ptr(y)), _stream()))
 

@@ -183,3 +183,42 @@ def test_image_encoder_end_to_end(skip_root, hw):
         e_bf, e_32, e_ref = rel_l2(got, rb.numpy()), rel_l2(got, r32.numpy()), rel_l2(rb.numpy(), r32.numpy())
         print(f"level {lvl}: vs bf16-oracle {e_bf:.4f}, vs fp32-oracle {e_32:.4f}, bf16-oracle vs fp32-oracle {e_ref:.4f}")
         assert e_32 < 1.5 * e_ref + 1e-3
+
+
+@pytest.mark.parametrize("KH,stride,pad,hw", [(7, 2, 3, (70, 300)), (3, 1, 1, (40, 150))])
+def test_implicit_root_conv_vs_im2col_gemm(KH, stride, pad, hw):
+    """The sliding-window (4D TMA) root conv equals the explicit im2col + GEMM of the same bf16 operands, including
+    the pad_to_multiple (-1) and conv padding (0) rings and several 128-column blocks per output row."""
+    from snap_b200 import ops
+    rng = np.random.default_rng(21)
+    n, (H, W) = 3, hw
+    mult = 32 if stride == 2 else 8
+    Hp, Wp = H + (mult - H % mult), W + (mult - W % mult)
+    img = _t(rng.random((n, H, W, 3), dtype=F)).cuda()
+    cout = 64
+    K = KH * KH * 3
+    ldb = (K + 31) // 32 * 32
+    b_std = torch.zeros((cout, ldb), dtype=torch.bfloat16, device="cuda")
+    b_std[:, :K] = (torch.randn((cout, K), device="cuda") * 0.1).to(torch.bfloat16)
+    cp, Hq, Wq, Ho, Wo = ops.root_packed_geometry(Hp, Wp, KH, KH, stride, pad)
+    # reference: explicit im2col + GEMM
+    a = torch.zeros(((n * Ho * Wo + 127) // 128 * 128, ldb), dtype=torch.bfloat16, device="cuda")
+    ops.root_im2col(img, Hp, Wp, KH, KH, stride, pad, a)
+    ref = torch.zeros((a.shape[0], cout), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, b_std, ref, m_rows=n * Ho * Wo, seg_k=ldb)
+    # implicit
+    packed = torch.zeros(n * Hq * Wq * cp + 64, dtype=torch.bfloat16, device="cuda")
+    ops.root_pack_image(img, Hp, Wp, pad, cp, Hq, Wq, packed)
+    bw = torch.zeros((cout, KH * 32), dtype=torch.bfloat16, device="cuda")
+    ops.root_pack_weights(b_std, cout, KH, KH, cp, bw)
+    out = torch.full((a.shape[0], cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64, device="cuda")
+    ops.root_conv(packed, n, Hq, Wq, cp, KH, stride, Ho, Wo, bw, cout, out, gn_acc=acc)
+    torch.cuda.synchronize()
+    got, want = out[: n * Ho * Wo].float().cpu().numpy(), ref[: n * Ho * Wo].float().cpu().numpy()
+    assert_close_bf16(got, want, "implicit root conv")
+    assert (out[n * Ho * Wo:] == 7.0).all()                       # nothing written past the last pixel
+    s = acc.sum(0).cpu().numpy()                                   # fused statistics of what was stored
+    g = got.reshape(n, Ho * Wo, 32, cout // 32).astype(np.float64)
+    assert np.allclose(s[..., 0], g.sum((1, 3)), rtol=1e-6, atol=1e-3)
+    assert np.allclose(s[..., 1], (g * g).sum((1, 3)), rtol=1e-6, atol=1e-3)

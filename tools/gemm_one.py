@@ -1,0 +1,29 @@
+"""One encoder GEMM configuration, a few launches (ncu target): python tools/gemm_one.py conv3|conv1|conv2"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from snap_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "conv3"
+NIMG, h, w = 16, 128, 168
+rows = NIMG * h * w
+bf = lambda r, c: (torch.randn((r, c), device=dev) * 0.5).to(torch.bfloat16)
+acc = torch.zeros((ops.GN_REPLICAS, NIMG, 32, 2), dtype=torch.float64, device=dev)
+if which == "conv3":
+    a, b, out, r = bf(rows + 128, 64), bf(256, 64), bf(rows + 128, 256), bf(rows + 128, 256)
+    fn = lambda: ops.gemm(a, b, out, m_rows=rows, residual=r, gn_acc=acc, gn_rows_per_img=h * w)
+elif which == "conv1":
+    a, b, out = bf(rows + 128, 256), bf(64, 256), bf(rows + 128, 64)
+    fn = lambda: ops.gemm(a, b, out, m_rows=rows, gn_acc=acc, gn_rows_per_img=h * w)
+else:
+    hp, wp = h + 2, w + 2
+    a, b, out = bf(NIMG * hp * wp + 4 * wp + 256, 64), bf(64, 576), bf(rows + 128, 64)
+    seg = [i * wp + j for i in range(3) for j in range(3)]
+    fn = lambda: ops.gemm(a, b, out, m_rows=NIMG * hp * wp, seg_off=seg, seg_k=64, remap=(hp, wp, 0, 0, h, w),
+                          gn_acc=acc, gn_rows_per_img=h * w)
+for _ in range(4):
+    fn()
+torch.cuda.synchronize()
