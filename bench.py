@@ -274,7 +274,8 @@ def main():
     def phase_timer():
         import snap_b200.ops as ops_mod
         names = ["lift_fused", "lift_gather_pool", "vertical_max", "gemm", "conv_gn", "gn_stats", "gn_apply", "std_weights_batched",
-                 "root_im2col", "maxpool3x3s2", "upsample2x", "crop_relu", "match_head"]
+                 "root_pack_image", "root_pack_weights", "root_conv", "maxpool3x3s2", "upsample2x", "crop_relu",
+                 "match_head"]
         orig = {n: getattr(ops_mod, n) for n in names}
         evs = []
 
@@ -382,7 +383,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
             "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": BT, "launch": "cuda-graph replay" if graph is not None else "eager",
-                       "l2": "per-step working set ~1.5 GB (im2col, activations, voxel statistics) >> 126 MB L2; "
+                       "l2": "per-step working set ~1 GB (activations, voxel statistics) >> 126 MB L2; "
                              "4 distinct tiles rotate",
                        "weights": "random-init Flax tree (48.1 M params), StdConv standardisation inside every step"},
             "e2e": {"value": e2e_val, "unit": "tiles/s", "ms_per_step": ms_e2e / args.steps,

@@ -12,13 +12,13 @@ static int env_int(const char* name, int dflt) {
   return v != nullptr && *v != 0 ? atoi(v) : dflt;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool CONVEPI = false>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, GemmParams p, int ctas_per_sm, cudaStream_t s) {
   using Cfg = GemmCfg<BN, BK>;
   static bool configured = false;
   if (!configured) {
-    int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>,
+    int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, AMODE_TMA, CONVEPI>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::smem_bytes(Cfg::MAX_STAGES)),
                         "cudaFuncSetAttribute(gemm_tc)");
@@ -42,7 +42,8 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int total = p.m_tiles * p.n_tiles;
   const int cap = num_sms() * ctas_per_sm;
   const int grid = total < cap ? total : cap;
-  gemm_tc_kernel<BN, BK><<<grid, GEMM_THREADS, Cfg::smem_bytes(stages, false, so), s>>>(tmA, tmB, tmO, tmR, p);
+  gemm_tc_kernel<BN, BK, AMODE_TMA, CONVEPI><<<grid, GEMM_THREADS, Cfg::smem_bytes(stages, false, so), s>>>(
+      tmA, tmB, tmO, tmR, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -73,6 +74,12 @@ int launch_gemm(const void* A, long long a_rows, int a_cols, long long a_ld, con
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, B, b_rows, b_cols, b_ld, bn, bk);
   if (rc) return rc;
+  // plain conv outputs take the specialised epilogue
+  const bool conv_epi = p.stage_out && p.bias == nullptr && !p.relu && p.row_mask == nullptr && p.N % bn == 0 &&
+                        (p.residual == nullptr || p.res_tma) && p.M_valid < (1LL << 31) &&
+                        (p.gn_acc == nullptr || p.gn_rows_per_img < (1LL << 31));
+  if (conv_epi && bk == 64 && bn == 64) return launch_inst<64, 64, true>(tmA, tmB, tmO, tmR, p, ctas_per_sm, s);
+  if (conv_epi && bk == 64 && bn == 128) return launch_inst<128, 64, true>(tmA, tmB, tmO, tmR, p, ctas_per_sm, s);
 #define SNAP_GEMM_CASE(BN_, BK_) \
   if (bn == BN_ && bk == BK_) return launch_inst<BN_, BK_>(tmA, tmB, tmO, tmR, p, ctas_per_sm, s);
   SNAP_GEMM_CASE(16, 64)
@@ -173,6 +180,9 @@ extern "C" int snapb200_conv_gn_bf16(const SnapConvGnParams* q, void* stream) {
   p.gn_acc_relu = q->gn_acc_relu;
   p.gn_rows_per_img = (long long)Ho * Wo;
   p.gn_cpg = q->n / 32;
+  p.gn_cpg_log = 0;
+  while ((1 << p.gn_cpg_log) < p.gn_cpg) ++p.gn_cpg_log;
+  if (q->gn_acc != nullptr) SNAP_REQUIRE((1 << p.gn_cpg_log) == p.gn_cpg, "gn_acc needs a power-of-two n / 32");
   p.gn_replica_stride = q->gn_replica_stride;
   if (q->gn_acc != nullptr)
     SNAP_REQUIRE(q->n % 64 == 0 && q->gn_replica_stride > 0, "gn_acc needs n %% 64 == 0 and gn_replica_stride");
@@ -260,6 +270,9 @@ extern "C" int snapb200_gemm_bf16(const SnapGemmParams* q, void* stream) {
   p.gn_acc_relu = q->gn_acc_relu;
   p.gn_rows_per_img = q->gn_rows_per_img;
   p.gn_cpg = q->n / 32;
+  p.gn_cpg_log = 0;
+  while ((1 << p.gn_cpg_log) < p.gn_cpg) ++p.gn_cpg_log;
+  if (q->gn_acc != nullptr) SNAP_REQUIRE((1 << p.gn_cpg_log) == p.gn_cpg, "gn_acc needs a power-of-two n / 32");
   p.gn_replica_stride = q->gn_replica_stride;
   if (q->gn_acc != nullptr) {
     SNAP_REQUIRE(q->n % 64 == 0 && q->gn_rows_per_img > 0, "gn_acc needs n %% 64 == 0 and gn_rows_per_img");
@@ -312,6 +325,9 @@ extern "C" int snapb200_root_conv_bf16(const SnapRootConvParams* q, void* stream
   p.gn_acc = q->gn_acc;
   p.gn_rows_per_img = (long long)q->Ho * q->Wo;
   p.gn_cpg = q->n / 32;
+  p.gn_cpg_log = 0;
+  while ((1 << p.gn_cpg_log) < p.gn_cpg) ++p.gn_cpg_log;
+  if (q->gn_acc != nullptr) SNAP_REQUIRE((1 << p.gn_cpg_log) == p.gn_cpg, "gn_acc needs a power-of-two n / 32");
   p.gn_replica_stride = q->gn_replica_stride;
   if (q->gn_acc != nullptr)
     SNAP_REQUIRE(q->n % 64 == 0 && q->gn_replica_stride > 0, "gn_acc needs n %% 64 == 0 and gn_replica_stride");

@@ -56,7 +56,8 @@ struct GemmParams {
   double* gn_acc;
   double* gn_acc_relu;
   long long gn_rows_per_img;
-  int gn_cpg;  // channels per group = N / 32
+  int gn_cpg;  // channels per group = N / 32 (a power of two)
+  int gn_cpg_log;
   int gn_replica_stride;  // doubles between the GN_REPLICAS copies of the accumulator (contention spreading)
   // staged output: the epilogue writes the bf16 tile into (128B-swizzled) shared memory and TMA stores it as whole
   // 128-byte lines (dense row-major outputs without remap; BN = 64 or 128)
@@ -147,9 +148,8 @@ __device__ __forceinline__ int seg_row_offset(const GemmParams& p, int seg) {
 // holds the warp total of value index L >> (5 - log2 NV), and those lanes issue ONE coalesced double atomic
 // instruction.  Warps straddling an image boundary fall back to per-row atomics.
 template <int SPAN>  // columns per group inside the 16-column chunk: 2, 4, 8 or 16
-__device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row_ok, int img, int col,
-                                                  int cpg, double* acc, bool uniform, int img_ref,
-                                                  int lane) {
+__device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row_ok, int img, int group0,
+                                                  double* acc, bool uniform, int img_ref, int lane) {
   constexpr int NG = 16 / SPAN;
   constexpr int NV = 2 * NG;
   float val[NV];
@@ -164,7 +164,6 @@ __device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row
     val[2 * g] = row_ok ? s : 0.f;
     val[2 * g + 1] = row_ok ? q : 0.f;
   }
-  const int group0 = col / cpg;
   if (uniform) {
     int off = 16;
 #pragma unroll
@@ -188,21 +187,25 @@ __device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row
   }
 }
 
+// cpg_log = log2(channels per group); group of column col = col >> cpg_log
 __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool row_ok, int img, int col,
-                                                int cpg, double* acc, bool uniform, int img_ref,
+                                                int cpg_log, double* acc, bool uniform, int img_ref,
                                                 int lane) {
-  switch (cpg) {
-    case 2: gn_accumulate16_t<2>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
-    case 4: gn_accumulate16_t<4>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
-    case 8: gn_accumulate16_t<8>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
-    default: gn_accumulate16_t<16>(v, row_ok, img, col, cpg, acc, uniform, img_ref, lane); break;
+  const int group0 = col >> cpg_log;
+  switch (cpg_log) {
+    case 1: gn_accumulate16_t<2>(v, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+    case 2: gn_accumulate16_t<4>(v, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+    case 3: gn_accumulate16_t<8>(v, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+    default: gn_accumulate16_t<16>(v, row_ok, img, group0, acc, uniform, img_ref, lane); break;
   }
 }
 
 // AMODE_TMA: A tiles come straight from TMA.  AMODE_GN: producer warps build the A tile from the raw tensor through
 // registers (any stride).  AMODE_TGN: TMA loads the RAW tile (dense layout, row-shifted per 3x3 tap) and
 // transformer warps apply GroupNorm + affine + ReLU IN PLACE in shared memory (stride 1 only).
-template <int BN, int BK, int AMODE = AMODE_TMA>
+// CONVEPI: epilogue specialised for plain conv outputs (bf16, staged TMA store, optional TMA residual, optional
+// GroupNorm statistics; no bias / activation / mask / remap): the generic epilogue is compiled out.
+template <int BN, int BK, int AMODE = AMODE_TMA, bool CONVEPI = false>
 __global__ void __launch_bounds__(AMODE == AMODE_GN ? GEMM_THREADS_GN : (AMODE == AMODE_TGN ? GEMM_THREADS_TGN : GEMM_THREADS),
                                   AMODE == AMODE_TMA ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -212,9 +215,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool AGN = AMODE == AMODE_GN;
   constexpr bool TGN = AMODE == AMODE_TGN;
   const int STAGES = p.stages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked), so every
+  // buffer below is a constant offset from the window base instead of a runtime-aligned pointer
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage tiles are multiples of 1024 B)
   const int out_stage_bytes = p.stage_out ? Cfg::OUT_STAGE_BYTES : 0;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + out_stage_bytes);
@@ -530,6 +534,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     if (p.res_tma && hw == 0 && lane == 0 && tile_begin < tile_end) issue_residual(tile_begin);
+    if constexpr (CONVEPI && BN % 64 == 0) {
+      // ---------------- conv epilogue: warp (q, hw) drains the contiguous column half hw of TMEM quadrant q ----------
+      constexpr int NCW = BN / 32;  // 16-column chunks per warp
+      const int cbase = hw * NCW;
+      uint8_t* rowp = slab + ((cbase * 16) / 64) * 4096 + lane * 128;  // this lane's row inside its 64-column half
+      // 16-byte slot of chunk i: (2 * ((cbase & 3) + i)) ^ (row % 8); the chunk part never carries into the rest
+      const uint32_t swz16 = (uint32_t)(((lane & 7) ^ ((cbase & 3) * 2)) << 4);
+      double* gacc = p.gn_acc != nullptr ? p.gn_acc + (size_t)(blockIdx.x % GN_REPLICAS) * p.gn_replica_stride : nullptr;
+      double* gacc_relu =
+          p.gn_acc_relu != nullptr ? p.gn_acc_relu + (size_t)(blockIdx.x % GN_REPLICAS) * p.gn_replica_stride : nullptr;
+      const int m_valid = (int)p.M_valid;
+      const int rpi = (int)p.gn_rows_per_img;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbase * 16);
+        const int m0 = t.mt * 128 + q * 32;
+        const bool row_ok = m0 + lane < m_valid;
+        const int col0 = t.nt * BN + cbase * 16;
+        int gn_img = -1, gn_ref = -1;
+        bool gn_uniform = true;
+        if (gacc != nullptr && m0 < m_valid) {
+          gn_ref = m0 / rpi;
+          const int last = min(m0 + 31, m_valid - 1) / rpi;
+          gn_uniform = gn_ref == last;
+          if (!gn_uniform) gn_img = row_ok ? (m0 + lane) / rpi : -1;
+        }
+        if (p.res_tma) {  // residual slab landed (which also implies the previous store released the slab)
+          mbar_wait(&res_bar[q], res_phase);
+          res_phase ^= 1;
+        } else {          // the slab is free once the previous tile's TMA store has read it
+          if (hw == 0 && lane == 0) bulk_wait_group_read0();
+          pair_bar_sync(q);
+        }
+        uint32_t v[2][16];
+        tmem_ld16(taddr, v[0]);
+#pragma unroll
+        for (int i = 0; i < NCW; ++i) {
+          tmem_ld_wait();
+          if (i + 1 < NCW) tmem_ld16(taddr + (uint32_t)((i + 1) * 16), v[(i + 1) & 1]);
+          const uint32_t(&vv)[16] = v[i & 1];
+          uint8_t* p0 = rowp + (((uint32_t)(2 * i) << 4) ^ swz16);
+          uint8_t* p1 = rowp + (((uint32_t)(2 * i + 1) << 4) ^ swz16);
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(vv[2 * j]), __uint_as_float(vv[2 * j + 1]));
+          if (p.res_tma) {
+            const uint4 s0 = *reinterpret_cast<const uint4*>(p0);
+            const uint4 s1 = *reinterpret_cast<const uint4*>(p1);
+            const uint32_t rr[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = hadd2_bf16_rn(pk[j], rr[j]);
+          }
+          *reinterpret_cast<uint4*>(p0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(p1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (gacc != nullptr) {
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 x = unpack_bf16(pk[j]);  // the stored (rounded) values
+              g[2 * j] = x.x;
+              g[2 * j + 1] = x.y;
+            }
+            gn_accumulate16(g, row_ok, gn_img, col0 + i * 16, p.gn_cpg_log, gacc, gn_uniform, gn_ref, lane);
+            if (gacc_relu != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) g[j] = fmaxf(g[j], 0.f);
+              gn_accumulate16(g, row_ok, gn_img, col0 + i * 16, p.gn_cpg_log, gacc_relu, gn_uniform, gn_ref, lane);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        pair_bar_sync(q);
+        if (hw == 0 && lane == 0) {
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h)
+            tma_store_2d(&tmO, slab + h * 4096, t.nt * BN + h * 64, t.mt * 128 + q * 32);
+          bulk_commit_group();
+          if (p.res_tma && tile + 1 < tile_end) {  // prefetch the next tile's residual behind the MMA wait
+            bulk_wait_group_read0();
+            issue_residual(tile + 1);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (hw == 0 && lane == 0) bulk_wait_group0();
+    } else
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const TileCoord t = decode_tile(p, tile, BN);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -670,11 +768,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               g[2 * j + 1] = x.y;
             }
             const size_t rep = (size_t)(blockIdx.x % GN_REPLICAS) * p.gn_replica_stride;
-            gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc + rep, gn_uniform, gn_ref, lane);
+            gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg_log, p.gn_acc + rep, gn_uniform, gn_ref, lane);
             if (p.gn_acc_relu != nullptr) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) g[j] = fmaxf(g[j], 0.f);
-              gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg, p.gn_acc_relu + rep, gn_uniform, gn_ref, lane);
+              gn_accumulate16(g, row_ok, gn_img, col, p.gn_cpg_log, p.gn_acc_relu + rep, gn_uniform, gn_ref, lane);
             }
           }
         };
