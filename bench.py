@@ -329,7 +329,7 @@ def main():
         wedge = (np.abs(np.arctan2(jj - G / 2 + 0.5, ii - G * 0.1)) < np.deg2rad(36)) & (ii > G * 0.1)
         vq = torch.from_numpy(wedge.astype(np.uint8))[None].to(dev)
         vm = torch.ones((1, G, G), dtype=torch.uint8, device=dev)
-        names_x = ["rot_templates", "xcorr_pad_map", "xcorr_count", "xcorr_scores", "xcorr_scores_sw"]
+        names_x = ["rot_templates", "xcorr_pad_map", "xcorr_count", "xcorr_scores", "xcorr_scores_sw", "xcorr_scores_rows"]
         orig_x = {nm: getattr(_ops, nm) for nm in names_x}
         evx = []
 
@@ -410,10 +410,15 @@ def main():
             U = 2 * G - 1
             xflops = 2.0 * 36 * U * U * G * G * 32
             xbytes = 2 * G * G * 32 * 2 + 2 * G * G + 36 * U * U * 4
-            xkey = "xcorr_scores_sw" if "xcorr_scores_sw" in xc else "xcorr_scores"
+            xkey = next(k for k in ("xcorr_scores_rows", "xcorr_scores_sw", "xcorr_scores") if k in xc)
+            xdesc = {"xcorr_scores_rows": "xcorr_rows_kernel: map strips resident in smem, sliding tcgen05 descriptor, "
+                                          "4 template rows stacked per M=128 x N=144 MMA (the launch includes the "
+                                          "template re-layout kernel)",
+                     "xcorr_scores_sw": "xcorr_sw_kernel: map strips resident in smem, sliding tcgen05 descriptor",
+                     "xcorr_scores": "gemm_tc_kernel<48,32>, segmented tcgen05 GEMM"}[xkey]
             xms = xc[xkey]
             line["roofline_xcorr"] = {
-                "kernel": "exhaustive (x,y,theta) correlation, G=128 R=36 D=32, 1 example (" + ("xcorr_sw_kernel: map strips resident in smem, sliding tcgen05 descriptor" if xkey.endswith("_sw") else "gemm_tc_kernel<48,32>, segmented tcgen05 GEMM") + ")",
+                "kernel": "exhaustive (x,y,theta) correlation, G=128 R=36 D=32, 1 example (" + xdesc + ")",
                 "bound": "tensor", "achieved": xflops / (xms * 1e-3) / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
                 "frac": xflops / (xms * 1e-3) / 1e12 / tf_sus, "traffic": None, "ms_per_launch": xms,
                 "algorithmic_flops": xflops, "algorithmic_bytes": xbytes, "peak_source": peak_src,

@@ -117,5 +117,5 @@ EXPORTED_SYMBOLS += [
     "snapb200_gn_stats", "snapb200_gn_apply", "snapb200_upsample2x",
     "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_lift_fused", "snapb200_lift_fused_scratch_bytes", "snapb200_vertical_max", "snapb200_match_head",
     "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_xcorr_padded_rotations", "snapb200_rot_templates",
-    "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores", "snapb200_xcorr_scores_sw",
+    "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores", "snapb200_xcorr_scores_sw", "snapb200_xcorr_scores_rows", "snapb200_xcorr_scores_rows_workspace",
 ]

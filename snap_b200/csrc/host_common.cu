@@ -125,6 +125,33 @@ int make_tmap_window4d_bf16(CUtensorMap* out, const void* base, int Wo, long lon
   return SNAPB200_OK;
 }
 
+int make_tmap_nd_bf16_plain(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  SNAP_REQUIRE(rank >= 2 && rank <= 5, "tensor-map rank must be 2..5");
+  SNAP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    SNAP_REQUIRE(box[i] >= 1 && box[i] <= 256, "box extent out of range");
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    st[i] = strides_bytes[i];
+    SNAP_REQUIRE(st[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  }
+  SNAP_REQUIRE((box[0] * 2) % 16 == 0, "inner box extent must be a multiple of 16 bytes");
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r);
+  return SNAPB200_OK;
+}
+
 }  // namespace snapb200
 
 extern "C" {

@@ -31,6 +31,10 @@ int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, long long rows, 
 int make_tmap_window4d_bf16(CUtensorMap* out, const void* base, int Wo, long long step_bytes, int Hq,
                             long long row_bytes, int N);
 
+// rank-N (<= 5) un-swizzled bf16 map: dims / box innermost first, strides_bytes[i] = pitch of dimension i + 1
+int make_tmap_nd_bf16_plain(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box);
+
 #define SNAP_REQUIRE(cond, ...)                                        \
   do {                                                                 \
     if (!(cond)) return set_error(SNAPB200_ERR_INVALID, __VA_ARGS__);  \

@@ -349,3 +349,30 @@ def xcorr_scores_sw(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optional[
     _lib.check(_lib.lib().snapb200_xcorr_scores_sw(
         C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)),
         C.c_void_p(_ptr(den)), B, R, G, D, C.c_float(thr), C.c_void_p(_ptr(scores)), _stream()))
+
+
+def xcorr_rows_supported(R: int, G: int) -> bool:
+    return R % 4 == 0 and R <= 64 and G % 2 == 0 and 8 <= G <= 129
+
+
+def xcorr_rows_workspace_bytes(B: int, R: int, G: int, D: int) -> int:
+    f = _lib.lib().snapb200_xcorr_scores_rows_workspace
+    f.restype = C.c_size_t
+    return int(f(B, R, G, D))
+
+
+def xcorr_scores_rows(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optional[torch.Tensor],
+                      den: Optional[torch.Tensor], thr: float, scores: torch.Tensor,
+                      workspace: Optional[torch.Tensor] = None) -> None:
+    """Map-row-major variant of `xcorr_scores` (same arguments + workspace of `xcorr_rows_workspace_bytes`)."""
+    B, G, _, RP, D = templates.shape
+    R = scores.shape[1]
+    _require(scores, torch.float32, "scores")
+    need = xcorr_rows_workspace_bytes(B, R, G, D)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=templates.device)
+    assert workspace.numel() * workspace.element_size() >= need
+    _lib.check(_lib.lib().snapb200_xcorr_scores_rows(
+        C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)), C.c_void_p(_ptr(den)),
+        B, R, G, D, C.c_float(thr), C.c_void_p(_ptr(scores)), C.c_void_p(_ptr(workspace)),
+        C.c_size_t(workspace.numel() * workspace.element_size()), _stream()))

@@ -82,8 +82,10 @@ def template_matching(q: torch.Tensor, q_valid: torch.Tensor, m: torch.Tensor, m
     ops.xcorr_count(q_valid.contiguous(), m_valid.contiguous(), cnt, den)
     scores = torch.empty((B, R, U, U), dtype=torch.float32, device=dev)
     thr = float(F(min_overlap * G * G)) if min_overlap is not None else 0.0
-    use_sw = kernel == "sw" or (kernel == "auto" and ops.xcorr_sw_supported(R, G))
-    fn = ops.xcorr_scores_sw if use_sw else ops.xcorr_scores
+    # "rows": map-row-major stacked-template MMAs (fastest); "sw": sliding window, N = 48; "gemm": segmented GEMM
+    if kernel == "auto":
+        kernel = "rows" if ops.xcorr_rows_supported(R, G) else ("sw" if ops.xcorr_sw_supported(R, G) else "gemm")
+    fn = {"rows": ops.xcorr_scores_rows, "sw": ops.xcorr_scores_sw, "gemm": ops.xcorr_scores}[kernel]
     fn(q.contiguous(), m_pad, cnt if min_overlap is not None else None, den, thr, scores)
     return scores
 

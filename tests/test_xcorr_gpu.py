@@ -36,12 +36,18 @@ def test_templates_count_scores_vs_oracle(G, R):
     qd, md = _t(q).to(torch.bfloat16).to(dev), _t(m).to(torch.bfloat16).to(dev)
     qvd, mvd = torch.from_numpy(qv.astype(np.uint8)).to(dev), torch.from_numpy(mv.astype(np.uint8)).to(dev)
     templates, t_valid = pv.sample_query_templates(qd, qvd, R, grid)
-    scores = pv.template_matching(templates, t_valid, md, mvd)                 # sliding-window kernel
+    scores = pv.template_matching(templates, t_valid, md, mvd)                 # map-row-major kernel ("rows")
+    assert ops.xcorr_rows_supported(R, G)
     scores_v1 = pv.template_matching(templates, t_valid, md, mvd, kernel="gemm")  # segmented-GEMM kernel
     torch.cuda.synchronize()
     assert torch.equal(torch.isneginf(scores), torch.isneginf(scores_v1))
     fin_ = torch.isfinite(scores)
     assert (scores[fin_] - scores_v1[fin_]).abs().max() <= 1e-4 * scores_v1[fin_].abs().max()
+    if ops.xcorr_sw_supported(R, G):
+        scores_sw = pv.template_matching(templates, t_valid, md, mvd, kernel="sw")  # sliding window, N = 48
+        torch.cuda.synchronize()
+        assert torch.equal(torch.isneginf(scores), torch.isneginf(scores_sw))
+        assert (scores[fin_] - scores_sw[fin_]).abs().max() <= 1e-4 * scores_v1[fin_].abs().max()
     for b in range(B):
         ot, otv = opv.sample_query_templates(q[b], qv[b], R, ogrid)
         assert np.array_equal(t_valid[b].cpu().numpy().astype(bool), otv), "template validity must be bit-exact"
