@@ -163,13 +163,6 @@ def main():
         d = dict(tiles[i % NT]); d["images"] = dev_imgs[i % NT]
         return mapper.apply({"params": p}, d)
 
-    def step_e2e(i):
-        d = dict(tiles[i % NT]); d["images"] = host_imgs[i % NT]
-        pred = mapper.apply({"params": p}, d)
-        out_host.copy_(pred["bev_matching"].features, non_blocking=True)
-        valid_host.copy_(pred["bev_matching"].valid, non_blocking=True)
-        return pred
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -204,67 +197,132 @@ def main():
         torch.cuda.profiler.stop()
         return
 
-    # ---- CUDA graph of one resident-input step (poses / heights re-read from pinned staging at replay) ----
+    # ---- CUDA graphs: one per distinct tile (its pose / height staging slot is baked in and written once) ----
     sve = mapper.streetview_encoder
-    graph = None
-    if not args.no_graph:
-        d0 = dict(tiles[0]); d0["images"] = img_in
-        d0["xyz_grid"] = mapper.build_xyz_grid(d0)
-        side = torch.cuda.Stream()
+    graphs = None
+    side = torch.cuda.Stream()
+    enc_plan = sve.image_encoder.plan(p["streetview_encoder"]["image_encoder"], BT * V, *IMG_HW, dev)
+    SLOT0 = 100   # explicit staging slots of the captured graphs (eager calls rotate over slots 0..3)
+
+    def tile_data(t, images):
+        d = dict(tiles[t]); d["images"] = images; d["staging_slot"] = SLOT0 + t
+        d["xyz_grid"] = mapper.build_xyz_grid(d)
+        return d
+
+    def capture(fn):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            img_in.copy_(dev_imgs[0])
-            mapper.apply({"params": p}, d0)
+            fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            pred_g = mapper.apply({"params": p}, d0)
-        enc_plan = sve.image_encoder.plan(p["streetview_encoder"]["image_encoder"], BT * V, *IMG_HW, dev)
-        hf, wf = enc_plan.cropped_shapes()[-1]
-        gbuf = sve._buffers(dev, BT, V, *IMG_HW, hf, wf, G, G, Z)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    if not args.no_graph:
+        preds_g = {}
+
+        def resident_fn(t):
+            preds_g[t] = mapper.apply({"params": p}, tile_data(t, img_in))
+        graphs = [capture(lambda t=t: resident_fn(t)) for t in range(NT)]
 
         def step_graph(i):
-            d = dict(tiles[i % NT]); d["images"] = img_in
-            d["xyz_grid"] = mapper.build_xyz_grid(d)
-            sve.stage_inputs(d, gbuf, enc_plan.strides[-1])     # host only: poses + heights -> pinned staging
             img_in.copy_(dev_imgs[i % NT], non_blocking=True)    # device-resident input of this step
-            graph.replay()
+            graphs[i % NT].replay()
         for i in range(args.warmup):
             step_graph(i)
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     sampler.start()
-    run_fn = step_graph if graph is not None else step_resident
+    run_fn = step_graph if graphs is not None else step_resident
     ms = timed(run_fn, args.steps)
-    # ---- e2e through the public API with HOST (pinned) images: H2D of the 4 images and D2H of the result
-    # inside the timed region.  One captured graph per distinct host tile (its pinned address is baked in);
-    # poses / heights are re-staged on the host before every replay.
-    e2e_graphs = []
-    if graph is not None:
-        for t_i in range(NT):
-            d = dict(tiles[t_i]); d["images"] = host_imgs[t_i]
-            d["xyz_grid"] = mapper.build_xyz_grid(d)
-            with torch.cuda.stream(side):
-                step_e2e(t_i)
-            torch.cuda.synchronize()
-            g_e = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_e):
-                pr = mapper.apply({"params": p}, d)
-                out_host.copy_(pr["bev_matching"].features, non_blocking=True)
-                valid_host.copy_(pr["bev_matching"].valid, non_blocking=True)
-            e2e_graphs.append((g_e, d))
 
-        def step_e2e_run(i):
-            g_e, d = e2e_graphs[i % NT]
-            sve.stage_inputs(d, gbuf, enc_plan.strides[-1])
-            g_e.replay()
-    else:
-        step_e2e_run = step_e2e
-    for i in range(2):
-        step_e2e_run(i)
-    ms_e2e = timed(step_e2e_run, args.steps)
+    # ---- e2e through the public API with HOST (pinned) images.  Every step's images go host -> device and its
+    # result device -> host inside the timed region; the upload of step i+1 (copy stream, second device buffer)
+    # overlaps the compute of step i, as any input pipeline does.  The first upload is fully exposed.
+    img_bufs = [torch.empty_like(dev_imgs[0]) for _ in range(2)]
+
+    SLOT_E = 200  # e2e staging slots: one per distinct tile (re-staged with identical content by every upload, so a
+                  # host that runs ahead of the GPU never changes a pinned buffer under a pending copy)
+
+    def e2e_data(t):
+        d = tile_data(t, img_bufs[t % 2])
+        d["staging_slot"] = SLOT_E + t
+        d["staging_uploaded"] = True
+        return d
+
+    def upload(t):   # on the copy stream: images + voxel heights + camera / pose tables of tile t
+        img_bufs[t % 2].copy_(host_imgs[t], non_blocking=True)
+        sve.upload_staging({"params": p["streetview_encoder"]}, e2e_data(t), dev)
+
+    def e2e_fn(t):
+        pr = mapper.apply({"params": p}, e2e_data(t))
+        out_host.copy_(pr["bev_matching"].features, non_blocking=True)
+        valid_host.copy_(pr["bev_matching"].valid, non_blocking=True)
+
+    assert NT % 2 == 0
+    e2e_graphs = [capture(lambda t=t: e2e_fn(t)) for t in range(NT)] if graphs is not None else None
+    copy_stream = torch.cuda.Stream()
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(steps, do_upload=True):
+        """K uploads, K computes, K result downloads; returns device ms between the first upload and the last D2H."""
+        barrier()
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        copy_stream.wait_event(e0)
+        with torch.cuda.stream(copy_stream):
+            if do_upload:
+                upload(0)
+            ev_up[0].record(copy_stream)
+        for i in range(steps):
+            b = i % 2
+            main.wait_event(ev_up[b])
+            if e2e_graphs is not None:
+                e2e_graphs[i % NT].replay()
+            else:
+                e2e_fn(i % NT)
+            ev_done[b].record(main)
+            if i + 1 < steps:
+                nb = (i + 1) % 2
+                if i >= 1:
+                    copy_stream.wait_event(ev_done[nb])   # the compute of step i-1 no longer reads that buffer
+                with torch.cuda.stream(copy_stream):
+                    if do_upload:
+                        upload((i + 1) % NT)
+                    ev_up[nb].record(copy_stream)
+        e1.record(main)
+        torch.cuda.synchronize()
+        ms_ = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+        barrier()
+        return ms_
+
+    e2e_loop(3)
+    ms_e2e = e2e_loop(args.steps)
+    if graphs is not None:
+        # the pipelined path must deliver the same map as the resident path for the last tile it processed
+        t_last = (args.steps - 1) % NT
+        got_f, got_v = out_host.clone(), valid_host.clone()
+        step_graph(t_last)
+        torch.cuda.synchronize()
+        ref_f, ref_v = preds_g[t_last]["bev_matching"].features.cpu(), preds_g[t_last]["bev_matching"].valid.cpu()
+        rel = float((got_f.float() - ref_f.float()).norm() / (ref_f.float().norm() + 1e-12))
+        if not torch.equal(got_v, ref_v) or rel > 1e-3:   # identical up to the summation order of the GN atomics
+            raise SystemExit(f"bench: e2e (pipelined upload) result differs from the resident-input result (rel {rel:.3e})")
+    if os.environ.get("BENCH_E2E_DEBUG") and rank == 0:
+        ms_nu = e2e_loop(args.steps, do_upload=False)
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        for _ in range(5):
+            img_bufs[0].copy_(host_imgs[0], non_blocking=True)
+        e1_.record()
+        torch.cuda.synchronize()
+        print(f"  e2e debug: full {ms_e2e / args.steps:.3f} ms/step, without uploads {ms_nu / args.steps:.3f} ms/step, "
+              f"resident {ms / args.steps:.3f} ms/step, one upload alone {e0_.elapsed_time(e1_) / 5:.3f} ms", file=sys.stderr)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -382,15 +440,17 @@ def main():
             "metric": "neural-map tiles/sec", "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
-            "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": BT, "launch": "cuda-graph replay" if graph is not None else "eager",
+            "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": BT, "launch": "cuda-graph replay (one graph per distinct tile)" if graphs is not None else "eager",
                        "l2": "per-step working set ~1 GB (activations, voxel statistics) >> 126 MB L2; "
                              "4 distinct tiles rotate",
                        "weights": "random-init Flax tree (48.1 M params), StdConv standardisation inside every step"},
             "e2e": {"value": e2e_val, "unit": "tiles/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + BT * 4 * (Z + 8 * 23)),
                     "d2h_bytes_per_step": int(out_host.numel() * 2 + valid_host.numel()),
-                    "path": "BEVMapper.apply(host pinned images) + D2H of bev_matching, " +
-                            ("captured once per host tile and replayed" if graph is not None else "eager launches")},
+                    "path": "pinned host images -> device (copy stream, double-buffered: the upload of step i+1 overlaps "
+                            "the compute of step i; K uploads inside the K-step region, the first one exposed) -> "
+                            "BEVMapper.apply -> D2H of bev_matching into pinned memory, " +
+                            ("one captured graph per tile" if graphs is not None else "eager launches")},
             "gpu_launches": int(launches_per_step * args.steps), "tiles_per_step": BT * world,
             "clocks": sampler.summary(),
             "roofline": {"kernel": lift_desc, "bound": "tensor", "achieved": achieved_tf, "peak": tf_sus, "unit": "TFLOP/s",
@@ -419,13 +479,14 @@ def main():
             xms = xc[xkey]
             line["roofline_xcorr"] = {
                 "kernel": "exhaustive (x,y,theta) correlation, G=128 R=36 D=32, 1 example (" + xdesc + ")",
-                "bound": "tensor", "achieved": xflops / (xms * 1e-3) / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
-                "frac": xflops / (xms * 1e-3) / 1e12 / tf_sus, "traffic": None, "ms_per_launch": xms,
+                "bound": "tensor", "achieved": xflops / (xms * 1e-3) / 1e12, "peak": tf_burst, "unit": "TFLOP/s",
+                "frac": xflops / (xms * 1e-3) / 1e12 / tf_burst, "traffic": None, "ms_per_launch": xms,
+                "peak_kind": "burst (the correlation is timed alone, a few ms per launch); the sustained figure is %.1f" % tf_sus,
                 "algorithmic_flops": xflops, "algorithmic_bytes": xbytes, "peak_source": peak_src,
                 "whole_voting_ms": sum(v for k, v in xc.items() if k != "_b4"),
                 "phases_ms": {k: round(v, 4) for k, v in xc.items() if k != "_b4"},
                 "batch4_ms_per_example": {k: round(v, 4) for k, v in xc.get("_b4", {}).items()},
-                "batch4_frac": (xflops / (xc["_b4"][xkey] * 1e-3) / 1e12 / tf_sus) if "_b4" in xc else None}
+                "batch4_frac": (xflops / (xc["_b4"][xkey] * 1e-3) / 1e12 / tf_burst) if "_b4" in xc else None}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             t = cpu_reference_tile(99, cores)
