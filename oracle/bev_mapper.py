@@ -22,6 +22,60 @@ def vertical_pooling_max(features: np.ndarray, valid: np.ndarray):
     return pooled, valid_any
 
 
+def log_sigmoid(x: np.ndarray) -> np.ndarray:
+    """jax.nn.log_sigmoid = -softplus(-x), fp32."""
+    x = x.astype(F)
+    return (-(np.maximum(-x, F(0)) + np.log1p(np.exp(-np.abs(x)).astype(F)).astype(F))).astype(F)
+
+
+def vertical_pooling(features: np.ndarray, valid: np.ndarray, pooling: str = "max", params: Optional[Dict] = None,
+                     rd: Callable = _id) -> Dict:
+    """bev_mapper.py:56-88, all pooling modes.  features [..., Z, C] (already in the feature dtype), valid [..., Z]
+    -> {'plane': (features [..., C], valid [...]), ['scores', 'weights' [..., Z] fp32]}.
+    `rd` (numpy -> numpy) models the feature dtype: nn.Dense materialises dot and dot + bias in it (:64),
+    `features.astype(feature dtype)` (:73), and half-precision sum / mean accumulate in fp32 and cast back."""
+    valid = valid.astype(bool)
+    valid_any = valid.any(-1)
+    vaa = np.where(valid_any[..., None], valid, True)  # double-where (:58-60)
+    out: Dict = {}
+    f32 = features.astype(F)
+    if pooling in ("weighted", "softmax"):
+        head = params["confidence_head"]
+        scores = rd(rd(layers.dense(f32, head["kernel"], None)) + head["bias"].astype(F))[..., 0].astype(F)
+        if pooling == "weighted":
+            scores = log_sigmoid(scores)
+        out["scores"] = scores
+        # jax.nn.softmax(where=, initial=0): shift by max(0, max over where) (SURVEY A.6)
+        mx = np.maximum(np.where(vaa, scores, -np.inf).max(-1, keepdims=True), F(0)).astype(F)
+        e = np.where(vaa, np.exp((scores - mx).astype(F)), F(0)).astype(F)
+        w = (e / e.sum(-1, keepdims=True)).astype(F)
+        w = out["weights"] = np.where(valid, w, F(0)).astype(F)
+        pooled = rd(np.sum(f32 * w[..., None], axis=-2).astype(F))
+    elif pooling == "mlp":
+        x = np.where(valid[..., None], f32, F(0))
+        x = x.reshape(*x.shape[:-2], -1)
+        pooled = layers.mlp(x, params["fusion_mlp"], rd=rd)
+    elif pooling == "max":
+        pooled = np.where(vaa[..., None], f32, -np.inf).max(-2)
+    elif pooling == "sum":
+        pooled = rd(np.where(vaa[..., None], f32, F(0)).sum(-2).astype(F))
+    elif pooling == "mean":
+        cnt = vaa.sum(-1).astype(F)[..., None]
+        pooled = rd((np.where(vaa[..., None], f32, F(0)).sum(-2).astype(F) / cnt).astype(F))
+    else:
+        raise NotImplementedError(pooling)  # :53-54
+    pooled = np.where(valid_any[..., None], pooled, F(0)).astype(F)
+    out["plane"] = (pooled, valid_any)
+    return out
+
+
+def bev_confidence(plane: np.ndarray, valid: np.ndarray, params: Dict, rd: Callable = _id) -> np.ndarray:
+    """bev_mapper.py:292-295: where(valid, log_sigmoid(Dense(1)(plane)), 0); params = confidence_head tree."""
+    head = params["layers_0"]
+    s = rd(rd(layers.dense(plane.astype(F), head["kernel"], None)) + head["bias"].astype(F))[..., 0]
+    return np.where(valid, log_sigmoid(s), F(0)).astype(F)
+
+
 def build_xyz_query(grid: grids.Grid2D, t_view2scene_t: np.ndarray, scene_z_offset: float = 4.0,
                     scene_z_height: float = 12.0, z_offset: Optional[float] = None):
     """bev_mapper.py:159-196 for one scene (train=False): xyz [X,Y,Z,3] fp32."""
@@ -47,11 +101,13 @@ def np_rd(rd_t: Callable) -> Callable:
 
 def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene: geometry.Transform3D,
                xyz: np.ndarray, fusion_params: Dict, feature_dim: int = 128, top_k: int = 4,
-               depth_min_max=(1.0, 32.0), rd: Callable = _id, chunk: int = 1 << 16):
+               depth_min_max=(1.0, 32.0), rd: Callable = _id, chunk: int = 1 << 16,
+               max_view_distance: Optional[float] = None, debug: Optional[Dict] = None):
     """streetview_encoder.py:232-286 for one scene, chunked over voxels.
 
     f_proj_images [V,Hf,Wf,feature_dim+S] = proj_mlp output; camera ALREADY scaled by 1/stride (:224).
-    Returns f_grid [X,Y,Z,D], valid [X,Y,Z], and per-voxel debug (vis [N,V], p2d [N,V,2]).
+    Returns f_grid [X,Y,Z,D], valid [X,Y,Z], and per-voxel debug (vis [N,V], p2d [N,V,2]); with view selection
+    (V > top_k) vis / p2d are the GATHERED [N,top_k] arrays and `debug` (if given) collects 'view_indices'.
     """
     rdn = np_rd(rd)
     grid_shape = xyz.shape[:-1]
@@ -61,8 +117,11 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
     for s in range(0, len(pts_all), chunk):
         pts = pts_all[s:s + chunk]
         p2d, vis, depth, _ = sv.project_points_to_views(t_view2scene, camera, pts)
+        min_dist = None
         if top_k and V > top_k:  # :241-249
-            idx, _ = sv.view_selection(pts, t_view2scene, vis, top_k)
+            idx, min_dist = sv.view_selection(pts, t_view2scene, vis, top_k)
+            if debug is not None:
+                debug.setdefault("view_indices", []).append(idx)
             p2d, vis, depth = (np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
                                for a in (p2d, vis, depth))
             f_proj = sv.interpolate_views_selective(f_proj_images, p2d, idx, cast=rdn)
@@ -72,6 +131,10 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
         feats, scales = f_proj[..., :feature_dim], f_proj[..., feature_dim:]
         scores = rdn(sv.interpolate_depth_score(scales, depth, depth_min_max))
         stats, valid = sv.pool_multiview_features(feats, vis, scores, False, True, rd=rdn)
+        if max_view_distance is not None and min_dist is not None:  # :275-279
+            valid = valid & (min_dist <= F(max_view_distance))
+        if debug is not None:
+            debug.setdefault("stats", []).append(stats)
         f = layers.mlp(rdn(stats), fusion_params, rd=rdn)  # :281
         f = np.where(valid[..., None], f, F(0))  # :282
         outs.append(f.astype(F)); valids.append(valid); vis_all.append(vis); p2d_all.append(p2d)

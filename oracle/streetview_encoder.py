@@ -42,7 +42,8 @@ def interpolate_views_selective(f_images: np.ndarray, p2d: np.ndarray, index: np
     `cast` models `point.astype(arrays.dtype)` (:88): identity for fp32 features."""
     size = np.asarray(f_images.shape[1:3], dtype=F)
     pt = cast(p2d.astype(F))
-    pt = np.maximum(np.minimum(cast(pt - F(0.5)), size - 1), 0).astype(F)
+    # jnp.minimum(bf16 point, int32 size - 1) promotes the size to the feature dtype (exact below 256)
+    pt = np.maximum(np.minimum(cast(pt - F(0.5)), cast((size - 1).astype(F))), 0).astype(F)
     lower = np.floor(pt).astype(np.int32)
     upper = lower + 1
     w_upper = cast((pt - lower).astype(F))

@@ -13,21 +13,75 @@ F = np.float32
 
 
 class VerticalPooling:
-    """`bev_mapper.py:40-88`; only the default `pooling='max'` is built (others: SURVEY §8(f).3)."""
+    """`bev_mapper.py:40-88`: pooling in {'max', 'sum', 'mean', 'softmax', 'weighted', 'mlp'}.
+
+    Parameters (Flax names): 'confidence_head' {kernel [C,1], bias [1]} for 'softmax' / 'weighted',
+    'fusion_mlp' {Dense_i} for 'mlp'.  The default 'max' needs none (and is normally fused into the lift kernel)."""
+
+    POOLINGS = ("max", "sum", "mean", "softmax", "weighted", "mlp")
 
     def __init__(self, config=None, dtype=torch.bfloat16):
         self.config = config if config is not None else configs.vertical_pooling()
-        if self.config.pooling != "max":
-            raise NotImplementedError(self.config.pooling)
+        if self.config.pooling not in self.POOLINGS:
+            raise NotImplementedError(self.config.pooling)   # bev_mapper.py:53-54
+        self._cache: Dict = {}
+
+    def _mlp_weights(self, params: Dict, device):
+        key = (id(params), str(device))
+        if key not in self._cache:
+            bank = image_encoder._WeightBank(device)
+            f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).reshape(-1)).to(device)
+            n = 0
+            while f"Dense_{n}" in params["fusion_mlp"]:
+                n += 1
+            ids = [bank.add(params["fusion_mlp"][f"Dense_{i}"]["kernel"], False) for i in range(n)]
+            bias = [f32(params["fusion_mlp"][f"Dense_{i}"]["bias"]) for i in range(n)]
+            bank.finalize()
+            self._cache[key] = (bank, ids, bias)
+        return self._cache[key]
 
     def apply(self, variables, feature_volume: types.FeatureVolume) -> Dict:
-        f, v = feature_volume.features, feature_volume.valid
+        f, v = feature_volume.features.contiguous(), feature_volume.valid.contiguous()
         lead, Z, C = f.shape[:-2], f.shape[-2], f.shape[-1]
         cells = int(np.prod(lead))
-        plane = torch.empty((*lead, C), dtype=torch.bfloat16, device=f.device)
-        pvalid = torch.empty(lead, dtype=torch.uint8, device=f.device)
-        ops.vertical_max(f.contiguous(), v.contiguous(), cells, Z, C, plane, pvalid)
-        return {"plane": types.FeaturePlane(features=plane, valid=pvalid)}
+        dev = f.device
+        mode = self.config.pooling
+        plane = torch.empty((*lead, C), dtype=torch.bfloat16, device=dev)
+        pvalid = torch.empty(lead, dtype=torch.uint8, device=dev)
+        pred: Dict = {}
+        if mode == "max":
+            ops.vertical_max(f, v, cells, Z, C, plane, pvalid)
+        elif mode in ("sum", "mean"):
+            ops.vertical_pool(mode, f, v, cells, Z, C, None, 0.0, plane, pvalid)
+        elif mode in ("softmax", "weighted"):
+            params = variables["params"] if "params" in variables else variables
+            head = params["confidence_head"]
+            key = ("conf", id(params), str(dev))
+            if key not in self._cache:
+                self._cache[key] = (torch.from_numpy(np.ascontiguousarray(head["kernel"], dtype=F).reshape(-1)).to(dev),
+                                    float(np.asarray(head["bias"], dtype=F).reshape(-1)[0]))
+            w, b = self._cache[key]
+            pred["scores"] = torch.empty((*lead, Z), dtype=torch.float32, device=dev)
+            pred["weights"] = torch.empty((*lead, Z), dtype=torch.float32, device=dev)
+            ops.vertical_pool(mode, f, v, cells, Z, C, w, b, plane, pvalid, pred["scores"], pred["weights"])
+        else:  # 'mlp' (:74-77): zero the invalid voxels, flatten each column to [Z*C], MLP, zero where no z is valid
+            params = variables["params"] if "params" in variables else variables
+            bank, ids, bias = self._mlp_weights(params, dev)
+            bank.run()
+            x = torch.zeros((max(cells, 128), Z * C), dtype=torch.bfloat16, device=dev)
+            ops.mask_rows(f, v, cells * Z, C, x)
+            ops.valid_any(v, cells, Z, pvalid)
+            for i, wid in enumerate(ids):
+                last = i == len(ids) - 1
+                n_out = bank.entries[wid][2]
+                y = plane.view(cells, C) if last else torch.zeros((max(cells, 128), n_out), dtype=torch.bfloat16, device=dev)
+                if last and n_out != C:
+                    raise NotImplementedError("the 'mlp' pooling must end in the feature dimension")
+                ops.gemm(x, bank.b_mats[wid], y, m_rows=cells, bias=bias[i], relu=not last,
+                         row_mask=pvalid.view(-1) if last else None)
+                x = y
+        pred["plane"] = types.FeaturePlane(features=plane, valid=pvalid)
+        return pred
 
     __call__ = apply
 
@@ -50,8 +104,10 @@ class BEVMapper:
             raise NotImplementedError("semantic raster modality is out of scope (SURVEY.md §2)")
         if c.bev_net is not None:
             raise NotImplementedError("BEV network not yet implemented")  # bev_mapper.py:141-142
-        if c.matching_dim not in (None, 32) or c.add_confidence:
-            raise NotImplementedError("matching_dim must be 32; confidence head not built")
+        if c.matching_dim not in (None, 32):
+            raise NotImplementedError("matching_dim must be 32 (or None)")
+        if c.matching_dim is not None and not c.normalize_matching_features:
+            raise NotImplementedError("un-normalised matching features are not built (the default normalises, defaults.py:254)")
         self.streetview_encoder = self.aerial_encoder = None
         if c.streetview_encoder is not None:
             self.streetview_encoder = streetview_encoder.StreetViewEncoder(c.streetview_encoder, dtype)
@@ -83,12 +139,14 @@ class BEVMapper:
         if "xyz_grid" not in data:
             data = dict(data)
             data["xyz_grid"] = self.build_xyz_grid(data)
-        fused = self.fused_lift and not debug and self.config.pooling.pooling == "max" \
-            and data["T_view2scene"].t.shape[1] <= 4
+        V = data["T_view2scene"].t.shape[1]
+        fused = self.fused_lift and not debug and self.config.pooling.pooling == "max" and V <= 4 \
+            and not self.streetview_encoder.uses_view_selection(V)
         pred = self.streetview_encoder.apply({"params": params["streetview_encoder"]}, data, train, debug=debug,
                                              fused=fused)
         if not fused:
-            pred["vertical_pooling"] = self.vertical_pooling.apply(None, pred["feature_volume"])
+            pred["vertical_pooling"] = self.vertical_pooling.apply({"params": params.get("vertical_pooling", {})},
+                                                                   pred["feature_volume"])
             pred["feature_plane"] = pred["vertical_pooling"].pop("plane")
         return pred
 
@@ -100,19 +158,23 @@ class BEVMapper:
         valid = torch.ones(feats.shape[:-1], dtype=torch.uint8, device=feats.device)
         return {"feature_plane": types.FeaturePlane(features=feats, valid=valid)}
 
-    def fuse_neural_maps(self, planes, train: bool = False) -> types.FeaturePlane:  # bev_mapper.py:225-252
+    def fuse_neural_maps(self, planes, train: bool = False, params: Optional[Dict] = None) -> types.FeaturePlane:  # bev_mapper.py:225-252
         if not planes:
             raise ValueError("No feature plane given.")
         if len(planes) == 1:
             return planes[0]
-        assert len(planes) == 2
-        a, b = planes
-        fa, fb = a.features.contiguous(), b.features.contiguous()
-        cells, C = fa.numel() // fa.shape[-1], fa.shape[-1]
-        out = torch.empty_like(fa)
-        vout = torch.empty(fa.shape[:-1], dtype=torch.uint8, device=fa.device)
-        ops.fuse_max(fa, a.valid.contiguous(), fb, b.valid.contiguous(), cells, C, out, vout)
-        return types.FeaturePlane(features=out, valid=vout)
+        if self.config.modality_fusion.pooling == "max" and len(planes) == 2:
+            a, b = planes
+            fa, fb = a.features.contiguous(), b.features.contiguous()
+            cells, C = fa.numel() // fa.shape[-1], fa.shape[-1]
+            out = torch.empty_like(fa)
+            vout = torch.empty(fa.shape[:-1], dtype=torch.uint8, device=fa.device)
+            ops.fuse_max(fa, a.valid.contiguous(), fb, b.valid.contiguous(), cells, C, out, vout)
+            return types.FeaturePlane(features=out, valid=vout)
+        # other fusion modes: VerticalPooling over the stacked modality axis (:247-252)
+        stacked = types.FeatureVolume(features=torch.stack([p.features for p in planes], dim=-2),
+                                      valid=torch.stack([p.valid for p in planes], dim=-1))
+        return self.modality_fusion.apply({"params": (params or {}).get("modality_fusion", {})}, stacked)["plane"]
 
     def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False,
               is_query: bool = False) -> Dict:
@@ -128,7 +190,7 @@ class BEVMapper:
             planes.append(pred["aerial"]["feature_plane"])
         if not planes:
             raise ValueError("No map encoder given.")
-        plane = pred["bev_features"] = self.fuse_neural_maps(planes)
+        plane = pred["bev_features"] = self.fuse_neural_maps(planes, train, params)
         if self.config.matching_dim is not None:  # bev_mapper.py:284-291
             dev = plane.features.device
             key = (id(params), str(dev))
@@ -142,6 +204,18 @@ class BEVMapper:
             out = torch.empty((*f.shape[:-1], self.config.matching_dim), dtype=torch.bfloat16, device=dev)
             ops.match_head(f, plane.valid.contiguous(), cells, f.shape[-1], k, bvec, out)
             pred["bev_matching"] = types.FeaturePlane(features=out, valid=plane.valid)
+        if self.config.add_confidence:  # bev_mapper.py:292-295
+            dev = plane.features.device
+            key = ("conf", id(params), str(dev))
+            if key not in self._cache:
+                head = params["confidence_head"]["layers_0"]
+                self._cache[key] = (torch.from_numpy(np.ascontiguousarray(head["kernel"], dtype=F).reshape(-1)).to(dev),
+                                    float(np.asarray(head["bias"], dtype=F).reshape(-1)[0]))
+            cw, cb = self._cache[key]
+            f = plane.features.contiguous()
+            conf = torch.empty(f.shape[:-1], dtype=torch.float32, device=dev)
+            ops.confidence(f, plane.valid.contiguous(), f.numel() // f.shape[-1], f.shape[-1], cw, cb, conf)
+            pred["bev_confidence"] = conf
         return pred
 
     __call__ = apply

@@ -240,6 +240,21 @@ def lift_gather_pool(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tens
         C.c_void_p(_ptr(dbg_vis)), C.c_void_p(_ptr(dbg_taps)), _stream()))
 
 
+def lift_select_pool(p: "_lib.LiftParams", top_k: int, max_view_distance: Optional[float], views: torch.Tensor,
+                     view_centers: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                     zs: torch.Tensor, stats: torch.Tensor, valid: torch.Tensor,
+                     dbg_idx: Optional[torch.Tensor] = None, dbg_vis: Optional[torch.Tensor] = None,
+                     dbg_taps: Optional[torch.Tensor] = None) -> None:
+    """V > top_k path: view selection + selective sampling + pooling (`streetview_encoder.py:127-138,80-105`)."""
+    _require(fimg, torch.bfloat16, "fimg")
+    _require(view_centers, torch.float32, "view_centers")
+    _lib.check(_lib.lib().snapb200_lift_select_pool(
+        C.byref(p), C.c_int(top_k), C.c_float(-1.0 if max_view_distance is None else max_view_distance),
+        C.c_void_p(_ptr(views)), C.c_void_p(_ptr(view_centers)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)),
+        C.c_void_p(_ptr(ys)), C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(valid)),
+        C.c_void_p(_ptr(dbg_idx)), C.c_void_p(_ptr(dbg_vis)), C.c_void_p(_ptr(dbg_taps)), _stream()))
+
+
 def lift_fused(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
                zs: torch.Tensor, w1t: torch.Tensor, w256: torch.Tensor, b1: torch.Tensor, w2t: torch.Tensor,
                b2: torch.Tensor, plane: torch.Tensor, pvalid: torch.Tensor, counter: torch.Tensor,
@@ -270,6 +285,43 @@ def vertical_max(volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, 
     _lib.check(_lib.lib().snapb200_vertical_max(
         C.c_void_p(_ptr(volume)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Z, Cc,
         C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(pvalid)), _stream()))
+
+
+POOL_MODES = {"sum": 1, "mean": 2, "softmax": 3, "weighted": 4}
+
+
+def vertical_pool(mode: str, volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, Cc: int,
+                  conf_w: Optional[torch.Tensor], conf_b: float, plane: torch.Tensor, pvalid: torch.Tensor,
+                  scores: Optional[torch.Tensor] = None, weights: Optional[torch.Tensor] = None) -> None:
+    """VerticalPooling 'sum' / 'mean' / 'softmax' / 'weighted' (`bev_mapper.py:56-88`)."""
+    _require(volume, torch.bfloat16, "volume")
+    if conf_w is not None:
+        _require(conf_w, torch.float32, "conf_w")
+    _lib.check(_lib.lib().snapb200_vertical_pool(
+        C.c_int(POOL_MODES[mode]), C.c_void_p(_ptr(volume)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Z, Cc,
+        C.c_void_p(_ptr(conf_w)), C.c_float(conf_b), C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(pvalid)),
+        C.c_void_p(_ptr(scores)), C.c_void_p(_ptr(weights)), _stream()))
+
+
+def confidence(plane: torch.Tensor, valid: torch.Tensor, cells: int, Cc: int, conf_w: torch.Tensor, conf_b: float,
+               out: torch.Tensor) -> None:
+    """`bev_mapper.py:292-295`: where(valid, log_sigmoid(Dense(C -> 1)(plane)), 0) -> f32 [cells]."""
+    _require(plane, torch.bfloat16, "plane")
+    _require(conf_w, torch.float32, "conf_w")
+    _require(out, torch.float32, "out")
+    _lib.check(_lib.lib().snapb200_confidence(C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Cc,
+                                              C.c_void_p(_ptr(conf_w)), C.c_float(conf_b), C.c_void_p(_ptr(out)), _stream()))
+
+
+def mask_rows(x: torch.Tensor, valid: torch.Tensor, rows: int, Cc: int, y: torch.Tensor) -> None:
+    _require(x, torch.bfloat16, "x")
+    _lib.check(_lib.lib().snapb200_mask_rows(C.c_void_p(_ptr(x)), C.c_void_p(_ptr(valid)), C.c_longlong(rows), Cc,
+                                             C.c_void_p(_ptr(y)), _stream()))
+
+
+def valid_any(valid: torch.Tensor, cells: int, Z: int, out: torch.Tensor) -> None:
+    _lib.check(_lib.lib().snapb200_valid_any(C.c_void_p(_ptr(valid)), C.c_longlong(cells), Z,
+                                             C.c_void_p(_ptr(out)), _stream()))
 
 
 def match_head(plane: torch.Tensor, valid: torch.Tensor, cells: int, Cc: int, kernel: torch.Tensor,

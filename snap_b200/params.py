@@ -109,6 +109,25 @@ def init_bev_mapper(rng, cfg) -> Dict:
     if cfg.aerial_encoder is not None:
         p["aerial_encoder"] = init_image_encoder(rng, cfg.aerial_encoder)
         dim = cfg.aerial_encoder.output_dim
+    def pooling_params(pcfg, z: int):
+        """`VerticalPooling.setup` (`bev_mapper.py:48-54`): confidence_head Dense(1) or fusion_mlp over Z*C inputs."""
+        if pcfg.pooling in ("weighted", "softmax"):
+            return {"confidence_head": {"kernel": lecun_normal(rng, (dim, 1)), "bias": np.zeros((1,), F)}}
+        if pcfg.pooling == "mlp":
+            return {"fusion_mlp": init_mlp(rng, z * dim, pcfg.mlp.layers)}
+        return {}
+
+    if cfg.streetview_encoder is not None:
+        z = int(round(cfg.scene_z_height / cfg.get("voxel_size", 0.2)))
+        vp = pooling_params(cfg.pooling, z)
+        if vp:
+            p["vertical_pooling"] = vp
+    if cfg.streetview_encoder is not None and cfg.aerial_encoder is not None:
+        mf = pooling_params(cfg.modality_fusion, 2)
+        if mf:
+            p["modality_fusion"] = mf
+    if cfg.add_confidence:  # nn.Sequential([nn.Dense(1)]) (`bev_mapper.py:154-157`)
+        p["confidence_head"] = {"layers_0": {"kernel": lecun_normal(rng, (dim, 1)), "bias": np.zeros((1,), F)}}
     if cfg.matching_dim is not None:
         # variance_scaling(1/sqrt(matching_dim), 'fan_in', 'truncated_normal') (`bev_mapper.py:145-153`)
         std = np.sqrt((1.0 / np.sqrt(cfg.matching_dim)) / dim)

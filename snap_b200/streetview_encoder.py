@@ -22,8 +22,13 @@ F = np.float32
 
 def fill_lift_params(cfg, V: int, hf: int, wf: int, X: int, Y: int, Z: int, stats_ld: int) -> "_lib.LiftParams":
     """Static (shape) part of the lift launch."""
-    if V > _lib.MAX_VIEWS:
-        raise NotImplementedError(f"V={V} > {_lib.MAX_VIEWS}: the top-k view-selection path is a 'next' row")
+    k_vs = cfg.top_k_view_selection
+    if k_vs and V > k_vs:      # view-selection path (`:241-249`)
+        if V > _lib.MAX_SELECT_VIEWS or k_vs > _lib.MAX_VIEWS:
+            raise NotImplementedError(f"view selection supports top_k <= {_lib.MAX_VIEWS} < V <= {_lib.MAX_SELECT_VIEWS} "
+                                      f"(got top_k={k_vs}, V={V})")
+    elif V > _lib.MAX_VIEWS:   # all-views path
+        raise NotImplementedError(f"all-views lift supports V <= {_lib.MAX_VIEWS} (got V={V} with top_k_view_selection={k_vs})")
     p = _lib.LiftParams()
     p.V, p.Hf, p.Wf = V, hf, wf
     p.D, p.S = cfg.feature_dim, cfg.num_scale_bins
@@ -124,8 +129,10 @@ class StreetViewEncoder:
             pin = lambda *s, dt: torch.zeros(s, dtype=dt).pin_memory()
             z = lambda *s, dt: torch.zeros(s, dtype=dt, device=device)
             self._cache[key] = dict(zs_host=pin(B, Z, dt=torch.float32), zs=z(B, Z, dt=torch.float32),
-                                    views_host=pin(B, _lib.MAX_VIEWS * VIEW_WORDS, dt=torch.int32),
-                                    views=z(B, _lib.MAX_VIEWS * VIEW_WORDS, dt=torch.int32), event=None)
+                                    views_host=pin(B, _lib.MAX_SELECT_VIEWS * VIEW_WORDS, dt=torch.int32),
+                                    views=z(B, _lib.MAX_SELECT_VIEWS * VIEW_WORDS, dt=torch.int32),
+                                    centers_host=pin(B, _lib.MAX_SELECT_VIEWS * 3, dt=torch.float32),
+                                    centers=z(B, _lib.MAX_SELECT_VIEWS * 3, dt=torch.float32), event=None)
         return self._cache[key]
 
     def stage_inputs(self, data: Dict, buf: Dict, stride) -> None:
@@ -137,6 +144,8 @@ class StreetViewEncoder:
         for b in range(B):
             pack = pack_views(data["camera"], data["T_view2scene"], b, stride)
             buf["views_host"][b, : len(pack)].copy_(torch.from_numpy(pack))
+            cen = np.ascontiguousarray(data["T_view2scene"].t[b], dtype=F).reshape(-1)   # camera centres (`:131`)
+            buf["centers_host"][b, : len(cen)].copy_(torch.from_numpy(cen))
 
     def upload_staging(self, variables: Dict, data: Dict, device=None) -> None:
         """Input-pipeline hook: stage this batch's voxel heights and camera / pose tables and enqueue their H2D copies
@@ -153,17 +162,27 @@ class StreetViewEncoder:
         self.stage_inputs(data, stg, enc_plan.strides[-1])
         stg["zs"].copy_(stg["zs_host"], non_blocking=True)
         stg["views"].copy_(stg["views_host"], non_blocking=True)
+        stg["centers"].copy_(stg["centers_host"], non_blocking=True)
+
+    def uses_view_selection(self, V: int) -> bool:
+        """`:241`: the top-k view-selection path runs iff the scene has more views than top_k_view_selection."""
+        k_vs = self.config.top_k_view_selection
+        return bool(k_vs) and V > k_vs
 
     def apply(self, variables: Dict, data: Dict, train: bool = False, debug: bool = False,
               fused: bool = False) -> Dict:
         """`fused=True` runs the whole lift as one kernel and returns 'feature_plane' (bev_mapper.py:56-88 applied)
-        instead of materialising 'feature_volume' (which then is absent from the result)."""
+        instead of materialising 'feature_volume' (which then is absent from the result); the fused kernel only
+        covers the all-views path (V <= top_k_view_selection, V <= 4)."""
         if train:
             raise NotImplementedError("training (backward kernels) is a 'next' row of SURVEY.md §8(f)")
         params = variables["params"] if "params" in variables else variables
         cfg = self.config
         images = data["images"]
         B, V, H, W, _ = images.shape
+        select = self.uses_view_selection(V)
+        if fused and select:
+            raise ValueError("the fused lift kernel has no view selection: call with fused=False when V > top_k_view_selection")
         dev = images.device if isinstance(images, torch.Tensor) and images.is_cuda else torch.device("cuda")
         xs, ys, zs = data["xyz_grid"]          # xs [X], ys [Y] (NumPy fp32), zs [B, Z]
         X, Y, Z = len(xs), len(ys), zs.shape[1]
@@ -202,6 +221,8 @@ class StreetViewEncoder:
         if not pre_uploaded:
             stg["zs"].copy_(stg["zs_host"], non_blocking=True)
             stg["views"].copy_(stg["views_host"], non_blocking=True)
+            if select:
+                stg["centers"].copy_(stg["centers_host"], non_blocking=True)
             if not capturing:
                 stg["event"] = torch.cuda.Event()
                 stg["event"].record()
@@ -230,14 +251,23 @@ class StreetViewEncoder:
                                Bm[wts["fus0"]], wts["w256"], wts["fus0_b"], Bm[wts["fus1"]], wts["fus1_b"],
                                buf["plane"][b], buf["pvalid"][b], buf["counter"][b], buf["scratch"])
                 continue
-            dv = dt = None
+            dv = dt = di = None
+            Kd = cfg.top_k_view_selection if select else V
             if debug:
-                dv = torch.zeros((N, V), dtype=torch.uint8, device=dev)
-                dt = torch.zeros((N, V, 2), dtype=torch.int32, device=dev)
+                dv = torch.zeros((N, Kd), dtype=torch.uint8, device=dev)
+                dt = torch.zeros((N, Kd, 2), dtype=torch.int32, device=dev)
                 dbg.setdefault("vis", []).append(dv)
                 dbg.setdefault("taps", []).append(dt)
-            ops.lift_gather_pool(lp, stg["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b],
-                                 buf["stats"], buf["valid"][b], dv, dt)
+                if select:
+                    di = torch.zeros((N, Kd), dtype=torch.int32, device=dev)
+                    dbg.setdefault("view_indices", []).append(di)
+            if select:   # V > top_k: view selection + selective sampling (`:241-249`)
+                ops.lift_select_pool(lp, cfg.top_k_view_selection, cfg.get("max_view_distance"), stg["views"][b],
+                                     stg["centers"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b],
+                                     buf["stats"], buf["valid"][b], di, dv, dt)
+            else:
+                ops.lift_gather_pool(lp, stg["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b],
+                                     buf["stats"], buf["valid"][b], dv, dt)
             # fusion MLP 257 -> 256 -> 128 (`:281`), zero where invalid (`:282`)
             ops.gemm(buf["stats"], Bm[wts["fus0"]], buf["hid"], m_rows=N, seg_k=288, bias=wts["fus0_b"], relu=True)
             ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],

@@ -143,6 +143,7 @@ def test_match_head_and_fuse_vs_oracle():
 @pytest.mark.parametrize("name,V,hw_img,G,aerial", [
     ("config1", 1, (224, 224), 64, False),     # BASELINE.json configs[0]
     ("sv+aerial", 4, (96, 128), 32, True),
+    ("sv-view-selection", 6, (96, 128), 32, False),   # V > top_k_view_selection = 4 (production scenes: 10-20 views)
 ])
 def test_bev_mapper_vs_oracle(name, V, hw_img, G, aerial):
     """Whole BEVMapper forward vs the oracle in bf16-emulation mode.
@@ -239,3 +240,103 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
     print(f"G={G} V={V}: valid cells {int(pv_ref.sum())}, differing elements {ne.mean():.5%}, rel_l2 {rel_l2(a, b):.2e}")
     assert ne.mean() < 2e-3 and rel_l2(a, b) < 1e-3
     assert np.abs(a - b).max() <= 2.0 ** -6 * np.abs(b).max()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# V > top_k_view_selection: view selection + selective sampling
+# ------------------------------------------------------------------------------------------------------------
+def _select_launch(G, V, hw_img, seed, fimg_np, K=4, max_dist=None, debug=True):
+    from snap_b200 import configs, ops, streetview_encoder as sve
+    data, grid, mapper, xs, ys, zs = _lift_inputs(G, hw_img, V, seed)
+    hf, wf = -(-hw_img[0] // 4), -(-hw_img[1] // 4)
+    cfg = configs.streetview_encoder()
+    cfg.top_k_view_selection = K
+    Z = zs.shape[1]
+    N = G * G * Z
+    dev = "cuda"
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    centers = _t(data["T_view2scene"].t[0].reshape(-1)).to(dev)
+    fimg = (torch.zeros((V, hf, wf, 160), dtype=torch.bfloat16, device=dev) if fimg_np is None
+            else _t(fimg_np).to(torch.bfloat16).to(dev))
+    stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
+    valid = torch.zeros(N, dtype=torch.uint8, device=dev)
+    idx = torch.full((N, K), -1, dtype=torch.int32, device=dev) if debug else None
+    vis = torch.zeros((N, K), dtype=torch.uint8, device=dev) if debug else None
+    taps = torch.zeros((N, K, 2), dtype=torch.int32, device=dev) if debug else None
+    ops.lift_select_pool(lp, K, max_dist, views, centers, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev),
+                         stats, valid, idx, vis, taps)
+    torch.cuda.synchronize()
+    return data, (xs, ys, zs), (hf, wf), stats, valid, idx, vis, taps
+
+
+@pytest.mark.parametrize("G,V,hw_img,K", [(32, 10, (96, 128), 4), (128, 12, (480, 640), 4), (24, 5, (64, 96), 3)])
+def test_view_selection_indices_and_taps_bit_exact(G, V, hw_img, K):
+    """top-k view indices (int32), gathered visibility and the taps of the bf16-cast coordinates: BIT-EXACT."""
+    from oracle import bev_mapper as obm, grids as ogrids, streetview_encoder as osv
+    data, (xs, ys, zs), (hf, wf), stats, valid, idx, vis, taps = _select_launch(G, V, hw_img, 3, None, K)
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    pts = xyz.reshape(-1, 3)
+    p2d, ovis, depth, _ = osv.project_points_to_views(oT, ocam, pts)
+    oidx, omin = osv.view_selection(pts, oT, ovis, K)
+    assert np.array_equal(idx.cpu().numpy(), oidx), "selected view indices differ"
+    gvis = np.take_along_axis(ovis, oidx, 1)
+    assert np.array_equal(vis.cpu().numpy().astype(bool), gvis), "gathered visibility differs"
+    assert np.array_equal(valid.cpu().numpy().astype(bool), gvis.any(-1))
+    assert gvis.any(-1).mean() > 0.005 and (ovis.sum(-1) > K).any(), "the case must exercise a real selection"
+    # lower taps of interpolate_views_selective with bf16 coordinates (streetview_encoder.py:88-95)
+    rdn = obm.np_rd(rd_bf16)
+    gp = np.take_along_axis(p2d, oidx[..., None], 1)
+    size = np.asarray([hf, wf], dtype=F)
+    pt = rdn(rdn(gp) - F(0.5))
+    pt = np.maximum(np.minimum(pt, rdn(size - 1)), 0)
+    lower = np.floor(pt).astype(np.int32)
+    assert np.array_equal(taps.cpu().numpy()[gvis], lower[gvis]), "tap indices differ"
+
+
+@pytest.mark.parametrize("max_dist", [None, 4.0])
+def test_view_selection_stats_and_volume_vs_oracle(max_dist):
+    """selective gather (bf16 tap arithmetic) + depth score + pooling + fusion MLP on identical bf16 inputs."""
+    from oracle import bev_mapper as obm, grids as ogrids
+    from snap_b200 import ops, params
+    from snap_b200.image_encoder import _WeightBank
+    G, V, hw_img, K = 24, 7, (64, 96), 4
+    rng = np.random.default_rng(11)
+    fimg_np = bf16_np(rng.standard_normal((V, 16, 24, 160)))
+    fp = params.round_to_bf16(params.perturb_affine(rng, params.init_mlp(rng, 257, (256, 128))))
+    data, (xs, ys, zs), (hf, wf), stats, valid, idx, vis, taps = _select_launch(G, V, hw_img, 5, fimg_np, K, max_dist)
+    dev = "cuda"
+    Z = zs.shape[1]
+    N = G * G * Z
+    bank = _WeightBank(torch.device(dev))
+    w0 = bank.add(fp["Dense_0"]["kernel"], False, 32)
+    w1 = bank.add(fp["Dense_1"]["kernel"], False)
+    bank.finalize(); bank.run()
+    hid = torch.zeros((N, 256), dtype=torch.bfloat16, device=dev)
+    vol = torch.zeros((N, 128), dtype=torch.bfloat16, device=dev)
+    ops.gemm(stats, bank.b_mats[w0], hid, m_rows=N, seg_k=288, bias=_t(fp["Dense_0"]["bias"]).to(dev), relu=True)
+    ops.gemm(hid, bank.b_mats[w1], vol, m_rows=N, bias=_t(fp["Dense_1"]["bias"]).to(dev), row_mask=valid)
+    torch.cuda.synchronize()
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    dbg = {}
+    f_grid, ovalid, ovis, _ = obm.lift_scene(fimg_np, ocam, oT, xyz, fp, top_k=K, rd=rd_bf16,
+                                             max_view_distance=max_dist, debug=dbg)
+    v = valid.cpu().numpy().astype(bool)
+    assert np.array_equal(v, ovalid.reshape(-1))
+    assert np.array_equal(idx.cpu().numpy(), np.concatenate(dbg["view_indices"]))
+    if max_dist is not None:
+        assert (ovis.any(-1) & ~ovalid.reshape(-1)).any(), "max_view_distance must reject some visible voxels"
+    ostats = np.concatenate(dbg["stats"])
+    any_vis = ovis.any(-1)
+    e_stats = rel_l2(stats.float().cpu().numpy()[any_vis][:, :257], ostats[any_vis])
+    e_vol = rel_l2(vol.float().cpu().numpy()[v], f_grid.reshape(-1, 128)[v])
+    print(f"max_dist={max_dist}: valid frac {v.mean():.3f}, rel_l2 stats {e_stats:.5f}, volume {e_vol:.5f}")
+    # identical bf16 inputs and rounding points (every tap product / partial sum is rounded to bf16 on both sides);
+    # residual = expf/logf ulps and fp32 summation order of the pooling -> relative L2 <= 5e-3
+    assert e_stats < 5e-3 and e_vol < 5e-3
+    assert not vol.float().cpu().numpy()[~v].any(), "invalid voxels must be zero (streetview_encoder.py:282)"
+    assert not stats.float().cpu().numpy()[~any_vis].any(), "statistics of unseen voxels must be zero (:177)"

@@ -102,6 +102,35 @@ def test_vertical_pooling_double_where():
     assert pv.tolist() == [True, False] and plane.tolist() == [[2.0, -5.0], [0.0, 0.0]]
 
 
+def test_vertical_pooling_modes_known_answers():
+    """bev_mapper.py:56-88: sum / mean / softmax / weighted / mlp on hand-computable columns."""
+    f = np.array([[[1.0, -5.0], [2.0, -7.0], [9.0, 9.0]], [[1, 1], [2, 2], [3, 3]]], F)  # 2 cells, Z=3, C=2
+    v = np.array([[True, True, False], [False, False, False]])
+    r = obm.vertical_pooling(f, v, "max")["plane"]
+    assert r[1].tolist() == [True, False] and r[0].tolist() == [[2.0, -5.0], [0.0, 0.0]]
+    assert obm.vertical_pooling(f, v, "sum")["plane"][0].tolist() == [[3.0, -12.0], [0.0, 0.0]]
+    assert obm.vertical_pooling(f, v, "mean")["plane"][0].tolist() == [[1.5, -6.0], [0.0, 0.0]]
+    # zero confidence kernel: every logit = bias; softmax -> uniform over the valid levels
+    head = {"confidence_head": {"kernel": np.zeros((2, 1), F), "bias": np.array([0.7], F)}}
+    r = obm.vertical_pooling(f, v, "softmax", head)
+    assert np.allclose(r["scores"], 0.7) and np.allclose(r["weights"], [[0.5, 0.5, 0], [0, 0, 0]])
+    assert np.allclose(r["plane"][0], [[1.5, -6.0], [0, 0]])
+    # 'weighted': logits go through log_sigmoid; kernel picks channel 0 -> logits (1, 2, 9)
+    head = {"confidence_head": {"kernel": np.array([[1.0], [0.0]], F), "bias": np.zeros(1, F)}}
+    r = obm.vertical_pooling(f, v, "weighted", head)
+    ls = -np.log1p(np.exp(-np.array([1.0, 2.0])))
+    w = np.exp(ls - 0.0) / np.exp(ls - 0.0).sum()     # shift = max(0, max ls) = 0 since log_sigmoid < 0
+    assert np.allclose(r["scores"][0, :2], ls, atol=1e-6) and np.allclose(r["weights"][0], [w[0], w[1], 0], atol=1e-6)
+    assert np.allclose(r["plane"][0][0], [w[0] * 1 + w[1] * 2, w[0] * -5 + w[1] * -7], atol=1e-5)
+    # 'mlp': the invalid level is zeroed before the flatten, so a sum-all kernel gives the sum over valid levels
+    mlp = {"fusion_mlp": {"Dense_0": {"kernel": np.ones((6, 1), F), "bias": np.array([0.5], F)}}}
+    r = obm.vertical_pooling(f, v, "mlp", mlp)
+    assert r["plane"][0].tolist() == [[1 - 5 + 2 - 7 + 0.5], [0.0]]
+    conf = obm.bev_confidence(np.array([[1.0, 0.0], [3.0, 0.0]], F), np.array([True, False]),
+                              {"layers_0": {"kernel": np.array([[1.0], [0.0]], F), "bias": np.zeros(1, F)}})
+    assert np.allclose(conf, [-np.log1p(np.exp(-1.0)), 0.0], atol=1e-6)
+
+
 def test_normalize_zero_vector():
     x = np.array([[3.0, 4.0], [0.0, 0.0], [1e-7, 0.0]], F)
     assert np.allclose(layers.normalize(x), [[0.6, 0.8], [0, 0], [0, 0]])
