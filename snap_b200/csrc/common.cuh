@@ -70,6 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// for single-thread roles that wait through a whole phase of the worker warps (microseconds): sleep between probes so
+// that the polling loop does not compete with the workers of the same scheduler for issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------
@@ -225,12 +231,26 @@ __device__ __forceinline__ uint32_t hadd2_bf16_rn(uint32_t a, uint32_t b) {
   x = __hadd2_rn(x, y);
   return *reinterpret_cast<uint32_t*>(&x);
 }
-__device__ __forceinline__ float bf16_round(float x) {
-  return __bfloat162float(__float2bfloat16_rn(x));
+// bf16 -> f32 is a shift / mask (ALU pipe)
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+// round-to-nearest-even to bf16, result as f32.  Goes through the PACKED conversion (F2FP.BF16.F32.PACK_AB, ALU
+// pipe) + a shift: the scalar cvt.rn.bf16.f32 compiles to F2F.BF16.F32, a quarter-rate conversion-unit instruction
+// that dominated the issue slots of the rounding-heavy epilogues.
+__device__ __forceinline__ float bf16_round(float x) { return bf16_lo(pack_bf16(x, 0.f)); }
+// round two values at once: one conversion + shift + mask
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t u = pack_bf16(a, b);
+  a = bf16_lo(u);
+  b = bf16_hi(u);
 }
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) { return make_float2(bf16_lo(u), bf16_hi(u)); }
+// packed bf16 max (HMNMX2.BF16)
+__device__ __forceinline__ uint32_t hmax2_bf16(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  const __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  x = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&x);
 }
 
 }  // namespace snapb200

@@ -29,6 +29,7 @@ constexpr int FL_WORKERS = 16;                       // worker warps
 constexpr int FL_THREADS = (2 + FL_WORKERS) * 32;    // 576
 constexpr int FL_BATCH_COLS = 4;                     // BEV columns per visibility batch (4 x 64 z-slots)
 constexpr int FL_LIST_CAP = 384;                     // ring of compacted visible voxels (>= 127 + 256)
+static_assert(FL_BATCH_COLS * 64 * 2 == FL_WORKERS * 32, "visibility pass: two worker threads per voxel slot");
 constexpr int FL_MAXV = 4;                           // views handled by the fused kernel
 
 // shared memory map (bytes); every MMA operand region is 1024-aligned
@@ -73,8 +74,8 @@ struct FusedArgs {
 struct Ctl {  // lives at SM_BAR
   uint64_t w1_full, w2_full[2], w2_empty[2], a_full, acc1_full, h_full, acc2_full;  // 9 x 8 B
   uint32_t tmem_ptr;
-  int list_head, list_count, cols_done, batch_col0, more;
-  int warp_cnt[8];
+  int batch_col0, more;
+  int warp_cnt[FL_WORKERS];
 };
 static_assert(sizeof(Ctl) <= 256, "control block");
 
@@ -109,9 +110,6 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     mbar_init(&ctl->acc1_full, 1);
     mbar_init(&ctl->h_full, FL_WORKERS * 32);
     mbar_init(&ctl->acc2_full, 1);
-    ctl->list_head = 0;
-    ctl->list_count = 0;
-    ctl->cols_done = 0;
     ctl->more = 0;
     fence_barrier_init();
   }
@@ -132,11 +130,11 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       int slot = 0;
       uint32_t ring_phase = 0;
       while (true) {
-        mbar_wait(&ctl->a_full, tile_phase);
+        mbar_wait_sleep(&ctl->a_full, tile_phase, 256);
         tile_phase ^= 1;
         if (*reinterpret_cast<volatile int*>(&ctl->more) == 0) break;
         for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(&ctl->w2_empty[slot], ring_phase ^ 1);
+          mbar_wait_sleep(&ctl->w2_empty[slot], ring_phase ^ 1, 64);
           mbar_arrive_expect_tx(&ctl->w2_full[slot], 16384);
           tma_load_2d(&tmW2, &ctl->w2_full[slot], smem + SM_W2 + slot * 16384, kc * 64, 0);
           if (++slot == 2) {
@@ -157,7 +155,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       uint32_t ring_phase = 0;
       const uint32_t sAH = smem_u32(smem + SM_AH), sW1 = smem_u32(smem + SM_W1), sW2 = smem_u32(smem + SM_W2);
       while (true) {
-        mbar_wait(&ctl->a_full, tile_phase);
+        mbar_wait_sleep(&ctl->a_full, tile_phase, 128);
         if (*reinterpret_cast<volatile int*>(&ctl->more) == 0) break;
         tc_fence_after_sync();
         // GEMM1: acc1[128 x 256] = A[128 x 256] * W1^T
@@ -171,7 +169,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         }
         umma_commit(&ctl->acc1_full);
         // GEMM2: acc2[128 x 128] = H[128 x 256] * W2^T  (H written by the workers into the A tile)
-        mbar_wait(&ctl->h_full, tile_phase);
+        mbar_wait_sleep(&ctl->h_full, tile_phase, 64);
         tc_fence_after_sync();
         for (int kc = 0; kc < 4; ++kc) {
           mbar_wait(&ctl->w2_full[slot], ring_phase);
@@ -199,96 +197,101 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const int sub = ww >> 2;             // which quarter of the accumulator columns it drains
     const int ncols = P.X * P.Y;
     const int half = lane >> 4;
+    const int l16 = lane & 15;           // channels [8*l16, 8*l16+8) of the half-warp's row
     const float score_scale = (float)(P.S - 1);
+    const unsigned FULL = 0xffffffffu;
+    TapRec* const my_scratch = A.scratch + (size_t)blockIdx.x * FL_LIST_CAP * FL_MAXV;
+    // z-max scratch inside the A/H region (free between the end of GEMM2 and the next gather)
+    uint16_t* const rowcol = reinterpret_cast<uint16_t*>(smem + SM_AH + 128 * VOL_STRIDE);        // BEV column of row r
+    uint4* const brec = reinterpret_cast<uint4*>(smem + SM_AH + 128 * VOL_STRIDE + 256);          // [8 parts][64]
     uint32_t tile_phase = 0;
     int n_tiles = 0, n_rows = 0;  // work counters (reported through col_counter[1..2])
-    long long tprof[7] = {0, 0, 0, 0, 0, 0, 0};  // cycles: fill, gather, wait acc1, epi1, wait acc2, epi2, z-max
-    long long tmark = clock64();
-#define LIFT_MARK(i)                  \
-  do {                                \
-    const long long now_ = clock64(); \
-    tprof[i] += now_ - tmark;         \
-    tmark = now_;                     \
+    // ring state: replicated in the registers of every worker thread (all of them take the same decisions)
+    int list_head = 0, list_count = 0;
+    bool cols_done = false;
+    unsigned tprof[7] = {0, 0, 0, 0, 0, 0, 0};  // cycles: fill, gather, wait acc1, epi1, wait acc2, epi2, z-max
+    unsigned tmark = (unsigned)clock();
+#define LIFT_MARK(i)                        \
+  do {                                      \
+    const unsigned now_ = (unsigned)clock(); \
+    tprof[i] += now_ - tmark;               \
+    tmark = now_;                           \
   } while (0)
-    int zm_col = -1;       // z-max carry of thread wtid < 128 (one output channel each)
-    float zm_val = 0.f;
+    int zm_col = -1;        // z-max carry of thread wtid < 64 (two output channels each, packed bf16x2)
+    uint32_t zm_val = 0;
+
+    if (wtid == 0) ctl->batch_col0 = atomicAdd(A.col_counter, FL_BATCH_COLS);  // first batch claim
 
     while (true) {
       // ---------- visibility batches: fill the list with >= 128 visible voxels ----------
-      while (true) {
-        worker_bar();
-        if (ctl->list_count >= 128 || ctl->cols_done) break;
-        if (wtid == 0) {
-          const int c0 = atomicAdd(A.col_counter, FL_BATCH_COLS);
-          ctl->batch_col0 = c0;
-          if (c0 >= ncols) ctl->cols_done = 1;
+      // Two threads per voxel (thread s of the pair projects views 2s, 2s+1 and writes their gather records);
+      // the next batch is claimed from the global counter while the current one is being processed.
+      while (list_count < 128 && !cols_done) {
+        worker_bar();  // batch_col0 of this round visible; previous readers of warp_cnt are done
+        const int c0 = ctl->batch_col0;
+        if (c0 >= ncols) {
+          cols_done = true;
+          break;
         }
-        worker_bar();
-        if (ctl->cols_done) continue;
-        bool valid = false;
-        uint32_t entry = 0;
-        if (wtid < FL_BATCH_COLS * 64) {
-          const int cl = wtid >> 6, z = wtid & 63;
-          const int col = ctl->batch_col0 + cl;
-          Proj pr[FL_MAXV];
-          uint32_t vm = 0;
-          if (col < ncols && z < P.Z) {
-            const int ix = col / P.Y, iy = col - ix * P.Y;
-            const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
+        const int vox = wtid >> 1, s2 = wtid & 1;
+        const int cl = vox >> 6, z = vox & 63;
+        const int col = c0 + cl;
+        Proj pr[2];
+        uint32_t vm = 0;
+        if (col < ncols && z < P.Z) {
+          const int ix = col / P.Y, iy = col - ix * P.Y;
+          const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
 #pragma unroll
-            for (int v = 0; v < FL_MAXV; ++v) {
-              if (v >= P.V) break;
-              pr[v] = project_point(sview[v], px, py, pz);
-              if (pr[v].vis) vm |= 1u << v;
+          for (int k = 0; k < 2; ++k) {
+            const int v = 2 * s2 + k;
+            if (v < P.V) {
+              pr[k] = project_point(sview[v], px, py, pz);
+              if (pr[k].vis) vm |= 1u << v;
             }
-            valid = vm != 0;
-            entry = ((uint32_t)col << 14) | ((uint32_t)z << 8) | vm;
           }
-          const uint32_t bal = __ballot_sync(0xffffffffu, valid);
-          if (lane == 0) ctl->warp_cnt[ww] = __popc(bal);
-          worker_bar();
-          if (valid) {
-            int idx = ctl->list_count + __popc(bal & ((1u << lane) - 1u));
-            for (int w2 = 0; w2 < ww; ++w2) idx += ctl->warp_cnt[w2];
-            const int slot = (ctl->list_head + idx) % FL_LIST_CAP;
-            list[slot] = entry;
-            // gather records of the visible views (same tap / bin arithmetic as the unfused kernel)
-            TapRec* rec = A.scratch + ((size_t)blockIdx.x * FL_LIST_CAP + slot) * FL_MAXV;
-#pragma unroll
-            for (int v = 0; v < FL_MAXV; ++v) {
-              if (v >= P.V || !(vm & (1u << v))) continue;
-              const Taps t = make_taps(pr[v].row, pr[v].col, P.Hf, P.Wf);
-              const float d = fminf(fmaxf(pr[v].depth, P.depth_min), P.depth_max);
-              const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
-              const float bf = floorf(bi);
-              TapRec q;
-              q.r0 = (uint16_t)t.r0; q.r1 = (uint16_t)t.r1; q.c0 = (uint16_t)t.c0; q.c1 = (uint16_t)t.c1;
-              q.wr1 = t.wr1; q.wc1 = t.wc1;
-              q.wb1 = bi - bf;
-              q.b0 = (uint16_t)min(max((int)bf, 0), P.S - 1);
-              q.b1 = (uint16_t)min(max((int)bf + 1, 0), P.S - 1);
-              q.pad_[0] = q.pad_[1] = 0;
-              const uint4* src = reinterpret_cast<const uint4*>(&q);
-              reinterpret_cast<uint4*>(rec + v)[0] = src[0];
-              reinterpret_cast<uint4*>(rec + v)[1] = src[1];
-            }
-            __threadfence();  // records must be in L2 before the gather warps read them (ld.global.cg)
-          }
-        } else {
-          worker_bar();
         }
+        vm |= __shfl_xor_sync(FULL, vm, 1);
+        const bool valid = vm != 0;
+        const uint32_t bal = __ballot_sync(FULL, valid) & 0x55555555u;  // one bit per voxel (its even lane)
+        if (lane == 0) ctl->warp_cnt[ww] = __popc(bal);
         worker_bar();
-        if (wtid == 0) {
-          int tot = 0;
-          for (int w2 = 0; w2 < 8; ++w2) tot += ctl->warp_cnt[w2];
-          ctl->list_count += tot;
+        if (wtid == 0) ctl->batch_col0 = atomicAdd(A.col_counter, FL_BATCH_COLS);  // everyone has read c0
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < FL_WORKERS; ++w2) {
+          const int c = ctl->warp_cnt[w2];
+          tot += c;
+          if (w2 < ww) before += c;
         }
+        if (valid) {
+          int slot = list_head + list_count + before + __popc(bal & ((1u << (lane & 30)) - 1u));
+          if (slot >= FL_LIST_CAP) slot -= FL_LIST_CAP;
+          if (s2 == 0) list[slot] = ((uint32_t)col << 14) | ((uint32_t)z << 8) | vm;
+          // gather records of this thread's visible views (same tap / bin arithmetic as the unfused kernel)
+          TapRec* rec = my_scratch + (size_t)slot * FL_MAXV;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int v = 2 * s2 + k;
+            if (!((vm >> v) & 1u)) continue;
+            const Taps t = make_taps(pr[k].row, pr[k].col, P.Hf, P.Wf);
+            const float d = fminf(fmaxf(pr[k].depth, P.depth_min), P.depth_max);
+            const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
+            const float bf = floorf(bi);
+            const uint32_t b0 = (uint32_t)min(max((int)bf, 0), P.S - 1);
+            const uint32_t b1 = (uint32_t)min(max((int)bf + 1, 0), P.S - 1);
+            uint4* dst = reinterpret_cast<uint4*>(rec + v);
+            dst[0] = make_uint4((uint32_t)t.r0 | ((uint32_t)t.r1 << 16), (uint32_t)t.c0 | ((uint32_t)t.c1 << 16),
+                                __float_as_uint(t.wr1), __float_as_uint(t.wc1));
+            dst[1] = make_uint4(__float_as_uint(bi - bf), b0 | (b1 << 16), 0u, 0u);
+          }
+        }
+        list_count += tot;
       }
-      const int rows = min(128, ctl->list_count);
-      const int head = ctl->list_head;
+      worker_bar();  // list entries and records of the last batch are visible to every worker (bar.sync orders them)
+      const int rows = min(128, list_count);
+      const int head = list_head;
       LIFT_MARK(0);
-      if (wtid == 0) ctl->more = rows > 0 ? 1 : 0;
-      worker_bar();
+      if (wtid == 0) ctl->more = rows > 0 ? 1 : 0;  // published by this thread's arrive (release) on a_full
       if (rows == 0) {
         mbar_arrive(&ctl->a_full);
         break;
@@ -297,24 +300,22 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       // ---------- gather + pool: one HALF-warp per tile row (16 lanes x 8 channels) ----------
       for (int r0 = ww * 2; r0 < 128; r0 += FL_WORKERS * 2) {
         const int r = r0 + half;          // this half-warp's row
-        const int l16 = lane & 15;        // channels [8*l16, 8*l16+8)
-        float mean[8], var[8], smaxv = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
         uint32_t vm = 0;
         int slot = 0;
         if (r < rows) {
-          slot = (head + r) % FL_LIST_CAP;
-          vm = list[slot] & 0xffu;
+          slot = head + r;
+          if (slot >= FL_LIST_CAP) slot -= FL_LIST_CAP;
+          vm = list[slot] & 0xfu;
         }
-        const TapRec* rec = A.scratch + ((size_t)blockIdx.x * FL_LIST_CAP + slot) * FL_MAXV;
-        const uint32_t vm_any = __reduce_or_sync(0xffffffffu, vm);
-        float fv[FL_MAXV][8], score[FL_MAXV];
+        const TapRec* rec = my_scratch + (size_t)slot * FL_MAXV;
+        const uint32_t vm_any = __reduce_or_sync(FULL, vm);
+        uint32_t fvp[FL_MAXV][4];  // interpolated features of each view, already in the feature dtype (packed bf16x2)
+        float score[FL_MAXV];
 #pragma unroll
         for (int v = 0; v < FL_MAXV; ++v) {
           score[v] = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) fv[v][j] = 0.f;
+          for (int j = 0; j < 4; ++j) fvp[v][j] = 0u;
         }
 #pragma unroll
         for (int v = 0; v < FL_MAXV; ++v) {
@@ -330,39 +331,59 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             const int b0 = q1.y & 0xffff, b1i = q1.y >> 16;
             const float wr0 = __fadd_rn(1.0f, -wr1), wc0 = __fadd_rn(1.0f, -wc1);
             const __nv_bfloat16* img = A.fimg + (size_t)v * P.Hf * P.Wf * P.CF;
-            const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr0 * P.Wf + tc0) * P.CF + l16 * 8));
-            const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr0 * P.Wf + tc1) * P.CF + l16 * 8));
-            const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr1 * P.Wf + tc0) * P.CF + l16 * 8));
-            const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)tr1 * P.Wf + tc1) * P.CF + l16 * 8));
+            const __nv_bfloat16* p00 = img + ((size_t)tr0 * P.Wf + tc0) * P.CF;
+            const __nv_bfloat16* p01 = img + ((size_t)tr0 * P.Wf + tc1) * P.CF;
+            const __nv_bfloat16* p10 = img + ((size_t)tr1 * P.Wf + tc0) * P.CF;
+            const __nv_bfloat16* p11 = img + ((size_t)tr1 * P.Wf + tc1) * P.CF;
+            const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(p00 + l16 * 8));
+            const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(p01 + l16 * 8));
+            const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(p10 + l16 * 8));
+            const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(p11 + l16 * 8));
+            // tap weights: row weight x column weight (one rounding each), shared with the unfused kernel
+            const float w00 = __fmul_rn(wr0, wc0), w01 = __fmul_rn(wr0, wc1);
+            const float w10 = __fmul_rn(wr1, wc0), w11 = __fmul_rn(wr1, wc1);
             if (l16 < 8) {  // depth-score taps: 4 taps x 2 bins on the first 8 lanes of the half
               const int tap = l16 >> 1, bsel = l16 & 1;
-              const int trr = (tap & 2) ? tr1 : tr0;
-              const int tcc = (tap & 1) ? tc1 : tc0;
+              const __nv_bfloat16* pt = (tap & 2) ? ((tap & 1) ? p11 : p10) : ((tap & 1) ? p01 : p00);
               const float wt = ((tap & 2) ? wr1 : 1.0f - wr1) * ((tap & 1) ? wc1 : 1.0f - wc1);
-              sp = wt * __bfloat162float(img[((size_t)trr * P.Wf + tcc) * P.CF + P.D + (bsel ? b1i : b0)]);
+              sp = wt * __bfloat162float(pt[P.D + (bsel ? b1i : b0)]);
             }
-            float f00[8], f01[8], f10[8], f11[8];
-            unpack8(u00, f00);
-            unpack8(u01, f01);
-            unpack8(u10, f10);
-            unpack8(u11, f11);
+            const uint32_t a00[4] = {u00.x, u00.y, u00.z, u00.w}, a01[4] = {u01.x, u01.y, u01.z, u01.w};
+            const uint32_t a10[4] = {u10.x, u10.y, u10.z, u10.w}, a11[4] = {u11.x, u11.y, u11.z, u11.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              // same association as the unfused kernel: row-weight * (column blend), lower row + upper row
-              const float lo = wr0 * (wc0 * f00[j] + wc1 * f01[j]);
-              const float hi = wr1 * (wc0 * f10[j] + wc1 * f11[j]);
-              fv[v][j] = bf16_round(lo + hi);
+            for (int j = 0; j < 4; ++j) {
+              // (w00 f00 + w01 f01) + (w10 f10 + w11 f11): lower tap row + upper tap row, as in the unfused kernel
+              const float lo_a = __fmaf_rn(w01, bf16_lo(a01[j]), __fmul_rn(w00, bf16_lo(a00[j])));
+              const float hi_a = __fmaf_rn(w11, bf16_lo(a11[j]), __fmul_rn(w10, bf16_lo(a10[j])));
+              const float lo_b = __fmaf_rn(w01, bf16_hi(a01[j]), __fmul_rn(w00, bf16_hi(a00[j])));
+              const float hi_b = __fmaf_rn(w11, bf16_hi(a11[j]), __fmul_rn(w10, bf16_hi(a10[j])));
+              fvp[v][j] = pack_bf16(__fadd_rn(lo_a, hi_a), __fadd_rn(lo_b, hi_b));  // -> feature dtype
             }
           }
           // bin-wise spatial interpolation (-> bf16), then interpolation across the two bins (-> bf16);
           // xor 2/4/1 stay inside the 8 score lanes of each half
-          sp += __shfl_xor_sync(0xffffffffu, sp, 2);
-          sp += __shfl_xor_sync(0xffffffffu, sp, 4);
+          sp += __shfl_xor_sync(FULL, sp, 2);
+          sp += __shfl_xor_sync(FULL, sp, 4);
           sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
-          sp += __shfl_xor_sync(0xffffffffu, sp, 1);
-          score[v] = __shfl_sync(0xffffffffu, bf16_round(sp), lane & 16);  // broadcast from the half's lane 0
+          sp += __shfl_xor_sync(FULL, sp, 1);
+          score[v] = __shfl_sync(FULL, bf16_round(sp), lane & 16);  // broadcast from the half's lane 0
         }
-        if (vm != 0) {
+        uint32_t mean_p[4], var_p[4];
+        float smaxv = 0.f;
+        const float ssum = (score[0] + score[1]) + (score[2] + score[3]);
+        if (__popc(vm) <= 1 && ssum > -80.f) {
+          // one visible view: its softmax weight is exactly 1 (x / x), so mean = its features, variance = +0 and
+          // score_max = its score; the other views' registers are zero (a fully invisible row gives all zeros)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mean_p[j] = (fvp[0][j] | fvp[1][j]) | (fvp[2][j] | fvp[3][j]);
+            var_p[j] = 0u;
+          }
+          smaxv = ssum;
+        } else {
+          float mean[8], var[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
           float mx = 0.f;
           smaxv = -INFINITY;
 #pragma unroll
@@ -379,19 +400,28 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           }
 #pragma unroll
           for (int v = 0; v < FL_MAXV; ++v) {
-            wv[v] = __fdiv_rn(wv[v], den);
             if (!(vm & (1u << v))) continue;
+            wv[v] = __fdiv_rn(wv[v], den);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mean[j] += wv[v] * fv[v][j];
+            for (int j = 0; j < 4; ++j) {
+              mean[2 * j] += wv[v] * bf16_lo(fvp[v][j]);
+              mean[2 * j + 1] += wv[v] * bf16_hi(fvp[v][j]);
+            }
           }
 #pragma unroll
           for (int v = 0; v < FL_MAXV; ++v) {
             if (!(vm & (1u << v))) continue;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float dd = fv[v][j] - mean[j];
-              var[j] += wv[v] * dd * dd;
+            for (int j = 0; j < 4; ++j) {
+              const float da = bf16_lo(fvp[v][j]) - mean[2 * j], db = bf16_hi(fvp[v][j]) - mean[2 * j + 1];
+              var[2 * j] += wv[v] * da * da;
+              var[2 * j + 1] += wv[v] * db * db;
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mean_p[j] = pack_bf16(mean[2 * j], mean[2 * j + 1]);
+            var_p[j] = pack_bf16(var[2 * j], var[2 * j + 1]);
           }
         }
         // A[r][k]: mean at k = 8*l16.., var at k = 128 + 8*l16..; K-chunk of 64, 16-byte slot (k%64)/8 XOR (r%8)
@@ -400,11 +430,9 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           const int kc_m = l16 >> 3, kc_v = 2 + (l16 >> 3);
           const int slot16 = (l16 & 7) ^ (r & 7);
           *reinterpret_cast<uint4*>(smem + SM_AH + kc_m * 16384 + r * 128 + slot16 * 16) =
-              make_uint4(pack_bf16(mean[0], mean[1]), pack_bf16(mean[2], mean[3]), pack_bf16(mean[4], mean[5]),
-                         pack_bf16(mean[6], mean[7]));
+              make_uint4(mean_p[0], mean_p[1], mean_p[2], mean_p[3]);
           *reinterpret_cast<uint4*>(smem + SM_AH + kc_v * 16384 + r * 128 + slot16 * 16) =
-              make_uint4(pack_bf16(var[0], var[1]), pack_bf16(var[2], var[3]), pack_bf16(var[4], var[5]),
-                         pack_bf16(var[6], var[7]));
+              make_uint4(var_p[0], var_p[1], var_p[2], var_p[3]);
           if (l16 == 0) smax_s[r] = __float2bfloat16(smaxv);
         }
       }
@@ -413,6 +441,9 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       LIFT_MARK(1);
 
       // ---------- epilogue 1: H = relu(bf16(bf16(acc1 + smax * w256) + b1)) -> smem (A tile) ----------
+      // Packed bf16 arithmetic after the first rounding: HADD2.BF16 of two bf16 values is the exactly rounded sum,
+      // i.e. identical to the fp32 add + round of the reference's "+ bias -> dtype"; biases are bf16 parameters
+      // (flax param_dtype = dtype), an fp32 bias is rounded to bf16 first.
       mbar_wait(&ctl->acc1_full, tile_phase);
       tc_fence_after_sync();
       LIFT_MARK(2);
@@ -426,28 +457,26 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
           tmem_ld_wait();
           const int n0 = sub * 64 + c16 * 16;
-          float f[16];
+          uint32_t h[8];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w256 + n0) + j4);
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.b1 + n0) + j4);
-            const float ws[4] = {w4.x, w4.y, w4.z, w4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              float x = bf16_round(__uint_as_float(v[j]) + sm * ws[e]);  // dot over all 257 inputs -> dtype
-              x = bf16_round(x + bs[e]);                                  // + bias -> dtype
-              f[j] = fmaxf(x, 0.f);
-            }
+            // dot over all 257 inputs -> dtype, + bias -> dtype, ReLU
+            uint32_t p0 = pack_bf16(__fmaf_rn(sm, w4.x, __uint_as_float(v[j4 * 4 + 0])),
+                                    __fmaf_rn(sm, w4.y, __uint_as_float(v[j4 * 4 + 1])));
+            uint32_t p1 = pack_bf16(__fmaf_rn(sm, w4.z, __uint_as_float(v[j4 * 4 + 2])),
+                                    __fmaf_rn(sm, w4.w, __uint_as_float(v[j4 * 4 + 3])));
+            p0 = hadd2_bf16_rn(p0, pack_bf16(b4.x, b4.y));
+            p1 = hadd2_bf16_rn(p1, pack_bf16(b4.z, b4.w));
+            h[j4 * 2 + 0] = hmax2_bf16(p0, 0u);
+            h[j4 * 2 + 1] = hmax2_bf16(p1, 0u);
           }
           const int kc = n0 >> 6;  // H column n0 is K index n0 of GEMM2
           const int s0 = (n0 & 63) >> 3;
           uint8_t* rowp = smem + SM_AH + kc * 16384 + row * 128;
-          *reinterpret_cast<uint4*>(rowp + ((s0 ^ (row & 7)) * 16)) =
-              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(rowp + (((s0 + 1) ^ (row & 7)) * 16)) =
-              make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                         pack_bf16(f[14], f[15]));
+          *reinterpret_cast<uint4*>(rowp + ((s0 ^ (row & 7)) * 16)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(rowp + (((s0 + 1) ^ (row & 7)) * 16)) = make_uint4(h[4], h[5], h[6], h[7]);
         }
       }
       fence_proxy_async_smem();
@@ -468,20 +497,23 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
           tmem_ld_wait();
           const int n0 = sub * 32 + c16 * 16;
-          float f[16];
+          uint32_t o[8];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.b2 + n0) + j4);
-            const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) f[j4 * 4 + e] = bf16_round(bf16_round(__uint_as_float(v[j4 * 4 + e])) + bs[e]);
+            o[j4 * 2 + 0] = hadd2_bf16_rn(pack_bf16(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1])),
+                                          pack_bf16(b4.x, b4.y));
+            o[j4 * 2 + 1] = hadd2_bf16_rn(pack_bf16(__uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3])),
+                                          pack_bf16(b4.z, b4.w));
           }
           uint8_t* rowp = smem + SM_AH + row * VOL_STRIDE + n0 * 2;
-          *reinterpret_cast<uint4*>(rowp) =
-              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(rowp + 16) =
-              make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                         pack_bf16(f[14], f[15]));
+          *reinterpret_cast<uint4*>(rowp) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(rowp + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        if (sub == 0 && row < rows) {  // BEV column of every tile row, for the z-max scan
+          int slot = head + row;
+          if (slot >= FL_LIST_CAP) slot -= FL_LIST_CAP;
+          rowcol[row] = (uint16_t)(list[slot] >> 14);
         }
       }
       tc_fence_before_sync();
@@ -489,65 +521,62 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       LIFT_MARK(5);
 
       // ---------- vertical max (bev_mapper.py:56-88) ----------
-      // 4 row parts x 128 channels: thread (part, c) scans 32 rows.  Column segments that start and end strictly
-      // inside a part are complete and written directly; the first / last segment of each part go to shared
-      // memory and are stitched (with the carry from the previous tile) by the 128 threads of part 0.
+      // 8 row parts x 64 channel pairs: thread (part, c2) scans 16 rows with packed bf16x2 max.  Column segments that
+      // start and end strictly inside a part are complete and written directly; the first / last segment of each part
+      // go to shared memory and are stitched (with the carry from the previous tile) by the 64 threads of part 0.
       {
-        const int part = wtid >> 7, c = wtid & 127;
-        const int r_lo = part * 32, r_hi = min(rows, r_lo + 32);
+        const int part = wtid >> 6, c2 = wtid & 63;
+        const int r_lo = part * 16, r_hi = min(rows, r_lo + 16);
         int fcol = -1, lcol = -1;   // first / last column of this part
-        float fmax_ = 0.f, lmax_ = 0.f;
+        uint32_t fmax_ = 0u, lmax_ = 0u;
+        uint32_t* plane32 = reinterpret_cast<uint32_t*>(A.plane);
         for (int r = r_lo; r < r_hi; ++r) {
-          const int col = (int)(list[(head + r) % FL_LIST_CAP] >> 14);
-          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(smem + SM_AH + r * VOL_STRIDE + c * 2));
+          const int col = rowcol[r];
+          const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + SM_AH + r * VOL_STRIDE + c2 * 4);
           if (col != lcol) {
             if (lcol >= 0 && lcol != fcol) {  // a middle segment just ended: complete
-              A.plane[(size_t)lcol * 128 + c] = __float2bfloat16(lmax_);
-              if (c == 0) A.pvalid[lcol] = 1;
+              plane32[(size_t)lcol * 64 + c2] = lmax_;
+              if (c2 == 0) A.pvalid[lcol] = 1;
             }
             if (fcol < 0) fcol = col;
             lcol = col;
             lmax_ = x;
           } else {
-            lmax_ = fmaxf(lmax_, x);
+            lmax_ = hmax2_bf16(lmax_, x);
           }
           if (lcol == fcol) fmax_ = lmax_;
         }
-        // boundary record of (part, c): {fcol, fmax, lcol, lmax}; placed after the staged volume rows
-        float4* brec = reinterpret_cast<float4*>(smem + SM_AH + 128 * VOL_STRIDE + 256) + (part * 128 + c);
-        *brec = make_float4(__int_as_float(fcol), fmax_, __int_as_float(lcol), lmax_);
+        brec[part * 64 + c2] = make_uint4((uint32_t)fcol, fmax_, (uint32_t)lcol, lmax_);
       }
       worker_bar();
-      if (wtid < 128) {
-        const float4* brec = reinterpret_cast<const float4*>(smem + SM_AH + 128 * VOL_STRIDE + 256);
+      if (wtid < 64) {
+        uint32_t* plane32 = reinterpret_cast<uint32_t*>(A.plane);
 #pragma unroll
-        for (int part = 0; part < 4; ++part) {
-          const float4 b4 = brec[part * 128 + wtid];
-          const int fcol = __float_as_int(b4.x), lcol = __float_as_int(b4.z);
+        for (int part = 0; part < 8; ++part) {
+          const uint4 b4 = brec[part * 64 + wtid];
+          const int fcol = (int)b4.x, lcol = (int)b4.z;
           if (fcol < 0) continue;  // part without rows
           if (fcol == zm_col) {
-            zm_val = fmaxf(zm_val, b4.y);
+            zm_val = hmax2_bf16(zm_val, b4.y);
           } else {
             if (zm_col >= 0) {
-              A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
+              plane32[(size_t)zm_col * 64 + wtid] = zm_val;
               if (wtid == 0) A.pvalid[zm_col] = 1;
             }
             zm_col = fcol;
             zm_val = b4.y;
           }
           if (lcol != fcol) {  // the first segment ended inside this part; the last one stays open
-            A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
+            plane32[(size_t)zm_col * 64 + wtid] = zm_val;
             if (wtid == 0) A.pvalid[zm_col] = 1;
             zm_col = lcol;
             zm_val = b4.w;
           }
         }
       }
-      worker_bar();
-      if (wtid == 0) {
-        ctl->list_head = (head + rows) % FL_LIST_CAP;
-        ctl->list_count -= rows;
-      }
+      list_head = head + rows;
+      if (list_head >= FL_LIST_CAP) list_head -= FL_LIST_CAP;
+      list_count -= rows;
       n_tiles += 1;
       n_rows += rows;
       tile_phase ^= 1;
@@ -556,10 +585,11 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     if (wtid == 0) {
       atomicAdd(A.col_counter + 1, n_tiles);
       atomicAdd(A.col_counter + 2, n_rows);
+#pragma unroll
       for (int i = 0; i < 7; ++i) atomicAdd(A.col_counter + 4 + i, (int)(tprof[i] >> 4));  // units of 16 cycles
     }
-    if (wtid < 128 && zm_col >= 0) {
-      A.plane[(size_t)zm_col * 128 + wtid] = __float2bfloat16(zm_val);
+    if (wtid < 64 && zm_col >= 0) {
+      reinterpret_cast<uint32_t*>(A.plane)[(size_t)zm_col * 64 + wtid] = zm_val;
       if (wtid == 0) A.pvalid[zm_col] = 1;
     }
   }
@@ -591,7 +621,7 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
   SNAP_REQUIRE(q->V >= 1 && q->V <= FL_MAXV, "fused lift handles 1..%d views (got %d)", FL_MAXV, q->V);
   SNAP_REQUIRE(q->D == 128 && q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
   SNAP_REQUIRE(q->Z >= 1 && q->Z <= 64, "Z must be <= 64 (got %d)", q->Z);
-  SNAP_REQUIRE((long long)q->X * q->Y < (1 << 18), "too many BEV columns");
+  SNAP_REQUIRE((long long)q->X * q->Y <= 65536, "too many BEV columns (X*Y <= 65536: 16-bit column ids in the z-max scan)");
   static_assert(sizeof(SnapLiftView) == sizeof(LiftView), "SnapLiftView layout");
   static_assert(sizeof(SnapLiftParams) == sizeof(LiftParams), "SnapLiftParams layout");
   cudaStream_t s = (cudaStream_t)stream;

@@ -74,10 +74,14 @@ lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const LiftView* __
       float fa[8], fb[8];
       unpack8(ua, fa);
       unpack8(ub, fb);
+      // tap weights = row weight x column weight (one rounding each); (w_r0 f_00 + w_r1 f_01) per tap row, then the
+      // two tap rows are added: the same operation sequence as the fused kernel (lift_fused.cu), pinned with
+      // explicit round-to-nearest intrinsics so that both produce identical bits
+      const float wx0 = __fmul_rn(wr, wc0), wx1 = __fmul_rn(wr, t.wc1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float part = wr * (wc0 * fa[j] + t.wc1 * fb[j]);
-        part += __shfl_xor_sync(0xffffffffu, part, 16);
+        float part = __fmaf_rn(wx1, fb[j], __fmul_rn(wx0, fa[j]));
+        part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, 16));
         fv[v][j] = bf16_round(part);  // interpolated features are materialised in the feature dtype
       }
       // --- depth score: linear interpolation over the S log-depth bins of the 4 taps ------------

@@ -20,10 +20,14 @@ def _rot_cam(yaw: float) -> np.ndarray:
 
 
 def make_tile(tile_id: int, num_views: int, image_hw, grid_side: int, cell_size: float = 0.2,
-              aerial: bool = False, batch: int = 1, fisheye: bool = False) -> Dict:
+              aerial: bool = False, batch: int = 1, fisheye: bool = False, spacing: float = 3.0,
+              same_side: bool = False) -> Dict:
     """Returns the reference's batch dict (`snap/data/loader.py:89-110`) with NumPy leaves:
     'images' f32 [B,V,H,W,3], 'camera' Camera [B,V], 'T_view2scene' Transform3D [B,V], optional
-    'rasters': {'rgb' [B,G,G,3]}."""
+    'rasters': {'rgb' [B,G,G,3]}.  `spacing` (m between consecutive cameras) and `same_side` (all cameras look to
+    the same side of the street instead of alternating) control how many views overlap on a voxel: the defaults
+    give the sparse street layout of SURVEY §8(d), small spacing + same_side the dense many-view case that the
+    top-k view selection exists for."""
     H, W = image_hw
     ext = grid_side * cell_size
     images, Rs, ts, rgbs = [], [], [], []
@@ -32,9 +36,9 @@ def make_tile(tile_id: int, num_views: int, image_hw, grid_side: int, cell_size:
         images.append(rng.random((num_views, H, W, 3), dtype=F))
         R_b, t_b = [], []
         for v in range(num_views):
-            along = (v - (num_views - 1) / 2) * 3.0 + rng.uniform(-0.5, 0.5)
+            along = (v - (num_views - 1) / 2) * spacing + rng.uniform(-0.5, 0.5) * spacing / 3.0
             pos = np.array([ext / 2 + along, ext / 2 + rng.uniform(-0.3, 0.3), 2.5 + rng.uniform(-0.2, 0.2)])
-            yaw = (np.pi / 2 if v % 2 == 0 else -np.pi / 2) + np.deg2rad(rng.uniform(-10, 10))
+            yaw = (np.pi / 2 if (v % 2 == 0 or same_side) else -np.pi / 2) + np.deg2rad(rng.uniform(-10, 10))
             R_b.append(_rot_cam(yaw))
             t_b.append(pos)
         Rs.append(np.stack(R_b)); ts.append(np.stack(t_b))

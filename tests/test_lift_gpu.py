@@ -12,9 +12,9 @@ def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=F))
 
 
-def _lift_inputs(G, hw_img, V, seed, fisheye=False):
+def _lift_inputs(G, hw_img, V, seed, fisheye=False, **layout):
     from snap_b200 import bev_mapper, configs, synthetic, types
-    data = synthetic.make_tile(seed, V, hw_img, G, fisheye=fisheye)
+    data = synthetic.make_tile(seed, V, hw_img, G, fisheye=fisheye, **layout)
     grid = types.Grid2D((G, G), 0.2)
     mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), grid)
     xs, ys, zs = mapper.build_xyz_grid(data)
@@ -247,7 +247,8 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
 # ------------------------------------------------------------------------------------------------------------
 def _select_launch(G, V, hw_img, seed, fimg_np, K=4, max_dist=None, debug=True):
     from snap_b200 import configs, ops, streetview_encoder as sve
-    data, grid, mapper, xs, ys, zs = _lift_inputs(G, hw_img, V, seed)
+    # dense layout: cameras 0.5 m apart looking to the same side, so that many voxels are seen by more than K views
+    data, grid, mapper, xs, ys, zs = _lift_inputs(G, hw_img, V, seed, spacing=0.5, same_side=True)
     hf, wf = -(-hw_img[0] // 4), -(-hw_img[1] // 4)
     cfg = configs.streetview_encoder()
     cfg.top_k_view_selection = K
@@ -285,7 +286,7 @@ def test_view_selection_indices_and_taps_bit_exact(G, V, hw_img, K):
     gvis = np.take_along_axis(ovis, oidx, 1)
     assert np.array_equal(vis.cpu().numpy().astype(bool), gvis), "gathered visibility differs"
     assert np.array_equal(valid.cpu().numpy().astype(bool), gvis.any(-1))
-    assert gvis.any(-1).mean() > 0.005 and (ovis.sum(-1) > K).any(), "the case must exercise a real selection"
+    assert gvis.any(-1).mean() > 0.005 and (ovis.sum(-1) > K).mean() > 0.005, "the case must exercise a real selection"
     # lower taps of interpolate_views_selective with bf16 coordinates (streetview_encoder.py:88-95)
     rdn = obm.np_rd(rd_bf16)
     gp = np.take_along_axis(p2d, oidx[..., None], 1)
@@ -296,7 +297,7 @@ def test_view_selection_indices_and_taps_bit_exact(G, V, hw_img, K):
     assert np.array_equal(taps.cpu().numpy()[gvis], lower[gvis]), "tap indices differ"
 
 
-@pytest.mark.parametrize("max_dist", [None, 4.0])
+@pytest.mark.parametrize("max_dist", [None, 2.0])
 def test_view_selection_stats_and_volume_vs_oracle(max_dist):
     """selective gather (bf16 tap arithmetic) + depth score + pooling + fusion MLP on identical bf16 inputs."""
     from oracle import bev_mapper as obm, grids as ogrids
