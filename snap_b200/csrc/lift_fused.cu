@@ -28,7 +28,7 @@ namespace snapb200 {
 constexpr int FL_WORKERS = 16;                       // worker warps
 constexpr int FL_THREADS = (2 + FL_WORKERS) * 32;    // 576
 constexpr int FL_BATCH_COLS = 4;                     // BEV columns per visibility batch (4 x 64 z-slots)
-constexpr int FL_LIST_CAP = 384;                     // ring of compacted visible voxels (>= 127 + 256)
+constexpr int FL_LIST_CAP = 512;                     // ring of compacted visible voxels (>= 128 in flight + 127 + 256)
 static_assert(FL_BATCH_COLS * 64 * 2 == FL_WORKERS * 32, "visibility pass: two worker threads per voxel slot");
 constexpr int FL_MAXV = 4;                           // views handled by the fused kernel
 
@@ -36,7 +36,7 @@ constexpr int FL_MAXV = 4;                           // views handled by the fus
 constexpr int SM_W1 = 0;                  // 4 K-chunks x [256 x 64] bf16, 128B-swizzled   (131072)
 constexpr int SM_AH = 131072;             // A / H / volume staging: 4 x [128 x 64] bf16   ( 65536)
 constexpr int SM_W2 = 196608;             // ring: 2 x [128 x 64] bf16                      ( 32768)
-constexpr int SM_LIST = 229376;           // uint32[FL_LIST_CAP]                            (  1536)
+constexpr int SM_LIST = 229376;           // uint32[FL_LIST_CAP]                            (  2048)
 constexpr int SM_SMAX = SM_LIST + 4 * FL_LIST_CAP;   // bf16[128] score_max per tile row    (   256)
 constexpr int SM_BAR = SM_SMAX + 256;     // mbarriers + control words                      (   256)
 constexpr int SM_VIEW = SM_BAR + 256;     // LiftView[FL_MAXV]                              (   384)
@@ -222,11 +222,15 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
 
     if (wtid == 0) ctl->batch_col0 = atomicAdd(A.col_counter, FL_BATCH_COLS);  // first batch claim
 
+    // Software pipeline: the visibility batches that top up the list for tile i+1 run while the tensor core computes
+    // GEMM1 of tile i (whose rows stay in the ring until its z-max is done); then the epilogues of tile i, then the
+    // gather of tile i+1.
+    int rows = 0, head = 0;  // tile in flight (gathered, GEMM1 issued); rows == 0: none
     while (true) {
-      // ---------- visibility batches: fill the list with >= 128 visible voxels ----------
+      // ---------- visibility batches: >= 128 visible voxels beyond the tile in flight ----------
       // Two threads per voxel (thread s of the pair projects views 2s, 2s+1 and writes their gather records);
       // the next batch is claimed from the global counter while the current one is being processed.
-      while (list_count < 128 && !cols_done) {
+      while (list_count - rows < 128 && !cols_done) {
         worker_bar();  // batch_col0 of this round visible; previous readers of warp_cnt are done
         const int c0 = ctl->batch_col0;
         if (c0 >= ncols) {
@@ -264,8 +268,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           if (w2 < ww) before += c;
         }
         if (valid) {
-          int slot = list_head + list_count + before + __popc(bal & ((1u << (lane & 30)) - 1u));
-          if (slot >= FL_LIST_CAP) slot -= FL_LIST_CAP;
+          const int slot = (list_head + list_count + before + __popc(bal & ((1u << (lane & 30)) - 1u))) & (FL_LIST_CAP - 1);
           if (s2 == 0) list[slot] = ((uint32_t)col << 14) | ((uint32_t)z << 8) | vm;
           // gather records of this thread's visible views (same tap / bin arithmetic as the unfused kernel)
           TapRec* rec = my_scratch + (size_t)slot * FL_MAXV;
@@ -282,164 +285,14 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             uint4* dst = reinterpret_cast<uint4*>(rec + v);
             dst[0] = make_uint4((uint32_t)t.r0 | ((uint32_t)t.r1 << 16), (uint32_t)t.c0 | ((uint32_t)t.c1 << 16),
                                 __float_as_uint(t.wr1), __float_as_uint(t.wc1));
-            dst[1] = make_uint4(__float_as_uint(bi - bf), b0 | (b1 << 16), 0u, 0u);
+            dst[1] = make_uint4(__float_as_uint(bi - bf), b0 | (b1 << 16), (uint32_t)v, 0u);
           }
         }
         list_count += tot;
       }
-      worker_bar();  // list entries and records of the last batch are visible to every worker (bar.sync orders them)
-      const int rows = min(128, list_count);
-      const int head = list_head;
       LIFT_MARK(0);
-      if (wtid == 0) ctl->more = rows > 0 ? 1 : 0;  // published by this thread's arrive (release) on a_full
-      if (rows == 0) {
-        mbar_arrive(&ctl->a_full);
-        break;
-      }
 
-      // ---------- gather + pool: one HALF-warp per tile row (16 lanes x 8 channels) ----------
-      for (int r0 = ww * 2; r0 < 128; r0 += FL_WORKERS * 2) {
-        const int r = r0 + half;          // this half-warp's row
-        uint32_t vm = 0;
-        int slot = 0;
-        if (r < rows) {
-          slot = head + r;
-          if (slot >= FL_LIST_CAP) slot -= FL_LIST_CAP;
-          vm = list[slot] & 0xfu;
-        }
-        const TapRec* rec = my_scratch + (size_t)slot * FL_MAXV;
-        const uint32_t vm_any = __reduce_or_sync(FULL, vm);
-        uint32_t fvp[FL_MAXV][4];  // interpolated features of each view, already in the feature dtype (packed bf16x2)
-        float score[FL_MAXV];
-#pragma unroll
-        for (int v = 0; v < FL_MAXV; ++v) {
-          score[v] = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) fvp[v][j] = 0u;
-        }
-#pragma unroll
-        for (int v = 0; v < FL_MAXV; ++v) {
-          if (!(vm_any & (1u << v))) continue;  // no half needs this view (warp-uniform)
-          const bool mine = (vm >> v) & 1u;
-          float sp = 0.f, wb1 = 0.f;
-          if (mine) {
-            const uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(rec + v));
-            const uint4 q1 = __ldcg(reinterpret_cast<const uint4*>(rec + v) + 1);
-            const int tr0 = q0.x & 0xffff, tr1 = q0.x >> 16, tc0 = q0.y & 0xffff, tc1 = q0.y >> 16;
-            const float wr1 = __uint_as_float(q0.z), wc1 = __uint_as_float(q0.w);
-            wb1 = __uint_as_float(q1.x);
-            const int b0 = q1.y & 0xffff, b1i = q1.y >> 16;
-            const float wr0 = __fadd_rn(1.0f, -wr1), wc0 = __fadd_rn(1.0f, -wc1);
-            const __nv_bfloat16* img = A.fimg + (size_t)v * P.Hf * P.Wf * P.CF;
-            const __nv_bfloat16* p00 = img + ((size_t)tr0 * P.Wf + tc0) * P.CF;
-            const __nv_bfloat16* p01 = img + ((size_t)tr0 * P.Wf + tc1) * P.CF;
-            const __nv_bfloat16* p10 = img + ((size_t)tr1 * P.Wf + tc0) * P.CF;
-            const __nv_bfloat16* p11 = img + ((size_t)tr1 * P.Wf + tc1) * P.CF;
-            const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(p00 + l16 * 8));
-            const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(p01 + l16 * 8));
-            const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(p10 + l16 * 8));
-            const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(p11 + l16 * 8));
-            // tap weights: row weight x column weight (one rounding each), shared with the unfused kernel
-            const float w00 = __fmul_rn(wr0, wc0), w01 = __fmul_rn(wr0, wc1);
-            const float w10 = __fmul_rn(wr1, wc0), w11 = __fmul_rn(wr1, wc1);
-            if (l16 < 8) {  // depth-score taps: 4 taps x 2 bins on the first 8 lanes of the half
-              const int tap = l16 >> 1, bsel = l16 & 1;
-              const __nv_bfloat16* pt = (tap & 2) ? ((tap & 1) ? p11 : p10) : ((tap & 1) ? p01 : p00);
-              const float wt = ((tap & 2) ? wr1 : 1.0f - wr1) * ((tap & 1) ? wc1 : 1.0f - wc1);
-              sp = wt * __bfloat162float(pt[P.D + (bsel ? b1i : b0)]);
-            }
-            const uint32_t a00[4] = {u00.x, u00.y, u00.z, u00.w}, a01[4] = {u01.x, u01.y, u01.z, u01.w};
-            const uint32_t a10[4] = {u10.x, u10.y, u10.z, u10.w}, a11[4] = {u11.x, u11.y, u11.z, u11.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              // (w00 f00 + w01 f01) + (w10 f10 + w11 f11): lower tap row + upper tap row, as in the unfused kernel
-              const float lo_a = __fmaf_rn(w01, bf16_lo(a01[j]), __fmul_rn(w00, bf16_lo(a00[j])));
-              const float hi_a = __fmaf_rn(w11, bf16_lo(a11[j]), __fmul_rn(w10, bf16_lo(a10[j])));
-              const float lo_b = __fmaf_rn(w01, bf16_hi(a01[j]), __fmul_rn(w00, bf16_hi(a00[j])));
-              const float hi_b = __fmaf_rn(w11, bf16_hi(a11[j]), __fmul_rn(w10, bf16_hi(a10[j])));
-              fvp[v][j] = pack_bf16(__fadd_rn(lo_a, hi_a), __fadd_rn(lo_b, hi_b));  // -> feature dtype
-            }
-          }
-          // bin-wise spatial interpolation (-> bf16), then interpolation across the two bins (-> bf16);
-          // xor 2/4/1 stay inside the 8 score lanes of each half
-          sp += __shfl_xor_sync(FULL, sp, 2);
-          sp += __shfl_xor_sync(FULL, sp, 4);
-          sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
-          sp += __shfl_xor_sync(FULL, sp, 1);
-          score[v] = __shfl_sync(FULL, bf16_round(sp), lane & 16);  // broadcast from the half's lane 0
-        }
-        uint32_t mean_p[4], var_p[4];
-        float smaxv = 0.f;
-        const float ssum = (score[0] + score[1]) + (score[2] + score[3]);
-        if (__popc(vm) <= 1 && ssum > -80.f) {
-          // one visible view: its softmax weight is exactly 1 (x / x), so mean = its features, variance = +0 and
-          // score_max = its score; the other views' registers are zero (a fully invisible row gives all zeros)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mean_p[j] = (fvp[0][j] | fvp[1][j]) | (fvp[2][j] | fvp[3][j]);
-            var_p[j] = 0u;
-          }
-          smaxv = ssum;
-        } else {
-          float mean[8], var[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
-          float mx = 0.f;
-          smaxv = -INFINITY;
-#pragma unroll
-          for (int v = 0; v < FL_MAXV; ++v)
-            if (vm & (1u << v)) {
-              mx = fmaxf(mx, score[v]);
-              smaxv = fmaxf(smaxv, score[v]);
-            }
-          float wv[FL_MAXV], den = 0.f;
-#pragma unroll
-          for (int v = 0; v < FL_MAXV; ++v) {
-            wv[v] = (vm & (1u << v)) ? expf(score[v] - mx) : 0.f;
-            den += wv[v];
-          }
-#pragma unroll
-          for (int v = 0; v < FL_MAXV; ++v) {
-            if (!(vm & (1u << v))) continue;
-            wv[v] = __fdiv_rn(wv[v], den);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              mean[2 * j] += wv[v] * bf16_lo(fvp[v][j]);
-              mean[2 * j + 1] += wv[v] * bf16_hi(fvp[v][j]);
-            }
-          }
-#pragma unroll
-          for (int v = 0; v < FL_MAXV; ++v) {
-            if (!(vm & (1u << v))) continue;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float da = bf16_lo(fvp[v][j]) - mean[2 * j], db = bf16_hi(fvp[v][j]) - mean[2 * j + 1];
-              var[2 * j] += wv[v] * da * da;
-              var[2 * j + 1] += wv[v] * db * db;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mean_p[j] = pack_bf16(mean[2 * j], mean[2 * j + 1]);
-            var_p[j] = pack_bf16(var[2 * j], var[2 * j + 1]);
-          }
-        }
-        // A[r][k]: mean at k = 8*l16.., var at k = 128 + 8*l16..; K-chunk of 64, 16-byte slot (k%64)/8 XOR (r%8)
-        // inside the 128-byte row (SWIZZLE_128B, as TMA would write it)
-        {
-          const int kc_m = l16 >> 3, kc_v = 2 + (l16 >> 3);
-          const int slot16 = (l16 & 7) ^ (r & 7);
-          *reinterpret_cast<uint4*>(smem + SM_AH + kc_m * 16384 + r * 128 + slot16 * 16) =
-              make_uint4(mean_p[0], mean_p[1], mean_p[2], mean_p[3]);
-          *reinterpret_cast<uint4*>(smem + SM_AH + kc_v * 16384 + r * 128 + slot16 * 16) =
-              make_uint4(var_p[0], var_p[1], var_p[2], var_p[3]);
-          if (l16 == 0) smax_s[r] = __float2bfloat16(smaxv);
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
-      mbar_arrive(&ctl->a_full);
-      LIFT_MARK(1);
-
+      if (rows > 0) {
       // ---------- epilogue 1: H = relu(bf16(bf16(acc1 + smax * w256) + b1)) -> smem (A tile) ----------
       // Packed bf16 arithmetic after the first rounding: HADD2.BF16 of two bf16 values is the exactly rounded sum,
       // i.e. identical to the fp32 add + round of the reference's "+ bias -> dtype"; biases are bf16 parameters
@@ -574,13 +427,188 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           }
         }
       }
-      list_head = head + rows;
-      if (list_head >= FL_LIST_CAP) list_head -= FL_LIST_CAP;
+      list_head = (head + rows) & (FL_LIST_CAP - 1);   // release the rows of the finished tile
       list_count -= rows;
       n_tiles += 1;
       n_rows += rows;
       tile_phase ^= 1;
       LIFT_MARK(6);
+      }  // rows > 0: epilogues of the tile in flight
+
+      // ---------- next tile ----------
+      worker_bar();  // list entries / records of this round's batches visible; z-max scratch of the last tile is dead
+      rows = min(128, list_count);
+      head = list_head;
+      if (wtid == 0) ctl->more = rows > 0 ? 1 : 0;  // published by this thread's arrive (release) on a_full
+      if (rows == 0) {
+        mbar_arrive(&ctl->a_full);
+        break;
+      }
+      // ---------- gather + pool: one HALF-warp per tile row (16 lanes x 8 channels) ----------
+      // Record prefetch: a warp handles rows {2 ww + 32 it + half}, it = 0..3.  Lane 4 it + k of each half loads the
+      // gather record of the k-th visible view of the half's row of iteration it, so all record reads of the tile are
+      // in flight at once (one exposed L2 round trip instead of one per row and view); the loop below fetches the words
+      // with shuffles.  Views are processed by RANK (k-th visible view of the row), not by view index: the two halves
+      // of a warp then need max(popc) iterations instead of popc(union), and the pooling is symmetric in the views.
+      uint32_t pvm = 0;
+      uint4 pq0 = make_uint4(0u, 0u, 0u, 0u), pq1 = make_uint4(0u, 0u, 0u, 0u);
+      {
+        const int pit = l16 >> 2, pk = l16 & 3;
+        const int prow = ww * 2 + 32 * pit + half;
+        if (prow < rows) {
+          const int slot = (head + prow) & (FL_LIST_CAP - 1);
+          pvm = list[slot] & 0xfu;
+          uint32_t m = pvm;  // drop the pk lowest set bits
+          if (pk > 0) m &= m - 1u;
+          if (pk > 1) m &= m - 1u;
+          if (pk > 2) m &= m - 1u;
+          if (m != 0u) {
+            const TapRec* rec = my_scratch + (size_t)slot * FL_MAXV + (__ffs(m) - 1);
+            pq0 = __ldcg(reinterpret_cast<const uint4*>(rec));
+            pq1 = __ldcg(reinterpret_cast<const uint4*>(rec) + 1);
+          }
+        }
+      }
+      for (int it = 0; it < 4; ++it) {
+        const int r = ww * 2 + 32 * it + half;  // this half-warp's row
+        const int src = (lane & 16) + 4 * it;   // lane of this half that holds rank 0 of iteration it
+        const uint32_t vm = __shfl_sync(FULL, pvm, src);
+        const int nv = __popc(vm);
+        const int nv_any = max(nv, __shfl_xor_sync(FULL, nv, 16));
+        uint32_t fvp[FL_MAXV][4];  // interpolated features of the k-th visible view, already in the feature dtype (bf16x2)
+        float score[FL_MAXV];
+#pragma unroll
+        for (int k = 0; k < FL_MAXV; ++k) {
+          score[k] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) fvp[k][j] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < FL_MAXV; ++k) {
+          if (k >= nv_any) break;  // warp-uniform
+          const uint32_t x0 = __shfl_sync(FULL, pq0.x, src + k), x1 = __shfl_sync(FULL, pq0.y, src + k);
+          const uint32_t x2 = __shfl_sync(FULL, pq0.z, src + k), x3 = __shfl_sync(FULL, pq0.w, src + k);
+          const uint32_t y0 = __shfl_sync(FULL, pq1.x, src + k), y1 = __shfl_sync(FULL, pq1.y, src + k);
+          const uint32_t y2 = __shfl_sync(FULL, pq1.z, src + k);
+          const bool mine = k < nv;
+          float sp = 0.f, wb1 = 0.f;
+          if (mine) {
+            const int tr0 = x0 & 0xffff, tr1 = x0 >> 16, tc0 = x1 & 0xffff, tc1 = x1 >> 16;
+            const float wr1 = __uint_as_float(x2), wc1 = __uint_as_float(x3);
+            wb1 = __uint_as_float(y0);
+            const int b0 = y1 & 0xffff, b1i = y1 >> 16;
+            const int v = (int)y2;  // view index of this rank
+            const float wr0 = __fadd_rn(1.0f, -wr1), wc0 = __fadd_rn(1.0f, -wc1);
+            const __nv_bfloat16* img = A.fimg + (size_t)v * P.Hf * P.Wf * P.CF;
+            const __nv_bfloat16* p00 = img + ((size_t)tr0 * P.Wf + tc0) * P.CF;
+            const __nv_bfloat16* p01 = img + ((size_t)tr0 * P.Wf + tc1) * P.CF;
+            const __nv_bfloat16* p10 = img + ((size_t)tr1 * P.Wf + tc0) * P.CF;
+            const __nv_bfloat16* p11 = img + ((size_t)tr1 * P.Wf + tc1) * P.CF;
+            const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(p00 + l16 * 8));
+            const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(p01 + l16 * 8));
+            const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(p10 + l16 * 8));
+            const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(p11 + l16 * 8));
+            // tap weights: row weight x column weight (one rounding each), shared with the unfused kernel
+            const float w00 = __fmul_rn(wr0, wc0), w01 = __fmul_rn(wr0, wc1);
+            const float w10 = __fmul_rn(wr1, wc0), w11 = __fmul_rn(wr1, wc1);
+            if (l16 < 8) {  // depth-score taps: 4 taps x 2 bins on the first 8 lanes of the half
+              const int tap = l16 >> 1, bsel = l16 & 1;
+              const __nv_bfloat16* pt = (tap & 2) ? ((tap & 1) ? p11 : p10) : ((tap & 1) ? p01 : p00);
+              const float wt = ((tap & 2) ? wr1 : 1.0f - wr1) * ((tap & 1) ? wc1 : 1.0f - wc1);
+              sp = wt * __bfloat162float(pt[P.D + (bsel ? b1i : b0)]);
+            }
+            const uint32_t a00[4] = {u00.x, u00.y, u00.z, u00.w}, a01[4] = {u01.x, u01.y, u01.z, u01.w};
+            const uint32_t a10[4] = {u10.x, u10.y, u10.z, u10.w}, a11[4] = {u11.x, u11.y, u11.z, u11.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // (w00 f00 + w01 f01) + (w10 f10 + w11 f11): lower tap row + upper tap row, as in the unfused kernel
+              const float lo_a = __fmaf_rn(w01, bf16_lo(a01[j]), __fmul_rn(w00, bf16_lo(a00[j])));
+              const float hi_a = __fmaf_rn(w11, bf16_lo(a11[j]), __fmul_rn(w10, bf16_lo(a10[j])));
+              const float lo_b = __fmaf_rn(w01, bf16_hi(a01[j]), __fmul_rn(w00, bf16_hi(a00[j])));
+              const float hi_b = __fmaf_rn(w11, bf16_hi(a11[j]), __fmul_rn(w10, bf16_hi(a10[j])));
+              fvp[k][j] = pack_bf16(__fadd_rn(lo_a, hi_a), __fadd_rn(lo_b, hi_b));  // -> feature dtype
+            }
+          }
+          // bin-wise spatial interpolation (-> bf16), then interpolation across the two bins (-> bf16);
+          // xor 2/4/1 stay inside the 8 score lanes of each half
+          sp += __shfl_xor_sync(FULL, sp, 2);
+          sp += __shfl_xor_sync(FULL, sp, 4);
+          sp = bf16_round(sp) * ((lane & 1) ? wb1 : 1.0f - wb1);
+          sp += __shfl_xor_sync(FULL, sp, 1);
+          score[k] = __shfl_sync(FULL, bf16_round(sp), lane & 16);  // broadcast from the half's lane 0
+        }
+        uint32_t mean_p[4], var_p[4];
+        float smaxv = 0.f;
+        const float ssum = (score[0] + score[1]) + (score[2] + score[3]);
+        if (nv <= 1 && ssum > -80.f) {
+          // one visible view: its softmax weight is exactly 1 (x / x), so mean = its features, variance = +0 and
+          // score_max = its score (rank 0; a fully invisible row gives all zeros)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mean_p[j] = fvp[0][j];
+            var_p[j] = 0u;
+          }
+          smaxv = ssum;
+        } else {
+          float mean[8], var[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mean[j] = var[j] = 0.f;
+          float mx = 0.f;
+          smaxv = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < FL_MAXV; ++k)
+            if (k < nv) {
+              mx = fmaxf(mx, score[k]);
+              smaxv = fmaxf(smaxv, score[k]);
+            }
+          float wv[FL_MAXV], den = 0.f;
+#pragma unroll
+          for (int k = 0; k < FL_MAXV; ++k) {
+            wv[k] = (k < nv) ? expf(score[k] - mx) : 0.f;
+            den += wv[k];
+          }
+#pragma unroll
+          for (int k = 0; k < FL_MAXV; ++k) {
+            if (k >= nv) continue;
+            wv[k] = __fdiv_rn(wv[k], den);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mean[2 * j] += wv[k] * bf16_lo(fvp[k][j]);
+              mean[2 * j + 1] += wv[k] * bf16_hi(fvp[k][j]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < FL_MAXV; ++k) {
+            if (k >= nv) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float da = bf16_lo(fvp[k][j]) - mean[2 * j], db = bf16_hi(fvp[k][j]) - mean[2 * j + 1];
+              var[2 * j] += wv[k] * da * da;
+              var[2 * j + 1] += wv[k] * db * db;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mean_p[j] = pack_bf16(mean[2 * j], mean[2 * j + 1]);
+            var_p[j] = pack_bf16(var[2 * j], var[2 * j + 1]);
+          }
+        }
+        // A[r][k]: mean at k = 8*l16.., var at k = 128 + 8*l16..; K-chunk of 64, 16-byte slot (k%64)/8 XOR (r%8)
+        // inside the 128-byte row (SWIZZLE_128B, as TMA would write it)
+        {
+          const int kc_m = l16 >> 3, kc_v = 2 + (l16 >> 3);
+          const int slot16 = (l16 & 7) ^ (r & 7);
+          *reinterpret_cast<uint4*>(smem + SM_AH + kc_m * 16384 + r * 128 + slot16 * 16) =
+              make_uint4(mean_p[0], mean_p[1], mean_p[2], mean_p[3]);
+          *reinterpret_cast<uint4*>(smem + SM_AH + kc_v * 16384 + r * 128 + slot16 * 16) =
+              make_uint4(var_p[0], var_p[1], var_p[2], var_p[3]);
+          if (l16 == 0) smax_s[r] = __float2bfloat16(smaxv);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
+      mbar_arrive(&ctl->a_full);
+      LIFT_MARK(1);
+
     }
     if (wtid == 0) {
       atomicAdd(A.col_counter + 1, n_tiles);
