@@ -46,14 +46,13 @@ static_assert(FL_SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 constexpr int VOL_STRIDE = 272;           // bytes per staged volume row (256 + 16: conflict-free)
 
 // Per (visible voxel, view) gather record, written by the thread-per-voxel visibility pass and read by the
-// half-warp-per-voxel gather pass (global scratch, L2 resident): clamped tap indices, upper-tap weights,
-// depth-score bins.  32 bytes.
+// half-warp-per-voxel gather pass (global scratch, L2 resident): tap offsets (so that the gather needs one
+// 64-bit add per tap instead of the row/column/view address arithmetic), upper-tap weights, depth-score bins.  32 bytes.
 struct TapRec {
-  uint16_t r0, r1, c0, c1;
-  float wr1, wc1;
-  float wb1;
-  uint16_t b0, b1;
-  uint32_t pad_[2];
+  uint32_t off00, off01, off10, off11;  // element offsets of the four taps into fimg (view base included)
+  float wr1, wc1;                       // weights of the upper taps
+  float wb1;                            // weight of the upper depth bin
+  uint16_t b0, b1;                      // depth bins
 };
 static_assert(sizeof(TapRec) == 32, "TapRec layout");
 
@@ -72,7 +71,7 @@ struct FusedArgs {
 };
 
 struct Ctl {  // lives at SM_BAR
-  uint64_t w1_full, w2_full[2], w2_empty[2], a_full, acc1_full, h_full, acc2_full;  // 9 x 8 B
+  uint64_t w1_full, w2_full[2], w2_empty[2], a_full, acc1_full, h_full[4], acc2_full;  // 12 x 8 B
   uint32_t tmem_ptr;
   int batch_col0, more;
   int warp_cnt[FL_WORKERS];
@@ -108,7 +107,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     }
     mbar_init(&ctl->a_full, FL_WORKERS * 32);
     mbar_init(&ctl->acc1_full, 1);
-    mbar_init(&ctl->h_full, FL_WORKERS * 32);
+    for (int kc = 0; kc < 4; ++kc) mbar_init(&ctl->h_full[kc], FL_WORKERS * 32);
     mbar_init(&ctl->acc2_full, 1);
     ctl->more = 0;
     fence_barrier_init();
@@ -168,10 +167,10 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             umma_bf16(tmem_acc1, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc1, (kc | k) != 0 ? 1u : 0u);
         }
         umma_commit(&ctl->acc1_full);
-        // GEMM2: acc2[128 x 128] = H[128 x 256] * W2^T  (H written by the workers into the A tile)
-        mbar_wait_sleep(&ctl->h_full, tile_phase, 64);
-        tc_fence_after_sync();
+        // GEMM2: acc2[128 x 128] = H[128 x 256] * W2^T  (H written by the workers into the A tile, one K-chunk
+        // at a time: the MMAs of chunk kc run while the workers are still writing chunks kc+1..3)
         for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait_sleep(&ctl->h_full[kc], tile_phase, 32);
           mbar_wait(&ctl->w2_full[slot], ring_phase);
           tc_fence_after_sync();
           const uint64_t da = make_kmajor_desc<128>(sAH + kc * 16384);
@@ -282,10 +281,11 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             const float bf = floorf(bi);
             const uint32_t b0 = (uint32_t)min(max((int)bf, 0), P.S - 1);
             const uint32_t b1 = (uint32_t)min(max((int)bf + 1, 0), P.S - 1);
+            const uint32_t row0 = (uint32_t)((v * P.Hf + t.r0) * P.Wf), row1 = (uint32_t)((v * P.Hf + t.r1) * P.Wf);
             uint4* dst = reinterpret_cast<uint4*>(rec + v);
-            dst[0] = make_uint4((uint32_t)t.r0 | ((uint32_t)t.r1 << 16), (uint32_t)t.c0 | ((uint32_t)t.c1 << 16),
-                                __float_as_uint(t.wr1), __float_as_uint(t.wc1));
-            dst[1] = make_uint4(__float_as_uint(bi - bf), b0 | (b1 << 16), (uint32_t)v, 0u);
+            dst[0] = make_uint4((row0 + (uint32_t)t.c0) * (uint32_t)P.CF, (row0 + (uint32_t)t.c1) * (uint32_t)P.CF,
+                                (row1 + (uint32_t)t.c0) * (uint32_t)P.CF, (row1 + (uint32_t)t.c1) * (uint32_t)P.CF);
+            dst[1] = make_uint4(__float_as_uint(t.wr1), __float_as_uint(t.wc1), __float_as_uint(bi - bf), b0 | (b1 << 16));
           }
         }
         list_count += tot;
@@ -301,15 +301,17 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       tc_fence_after_sync();
       LIFT_MARK(2);
       {
+        // warp (q, sub) owns rows 32q..32q+31 and, of every 64-column K-chunk c of H, columns 16 sub..16 sub+15: chunk c
+        // is complete (and handed to the tensor core) after the c-th step of all 16 warps
         const int row = q * 32 + lane;
         const float sm = __bfloat162float(smax_s[row]);
-        const uint32_t taddr = tmem_acc1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 64);
+        const uint32_t taddr = tmem_acc1 + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 16);
 #pragma unroll 1
-        for (int c16 = 0; c16 < 4; ++c16) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
+          tmem_ld16(taddr + (uint32_t)(c * 64), v);
           tmem_ld_wait();
-          const int n0 = sub * 64 + c16 * 16;
+          const int n0 = c * 64 + sub * 16;
           uint32_t h[8];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -325,16 +327,15 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             h[j4 * 2 + 0] = hmax2_bf16(p0, 0u);
             h[j4 * 2 + 1] = hmax2_bf16(p1, 0u);
           }
-          const int kc = n0 >> 6;  // H column n0 is K index n0 of GEMM2
-          const int s0 = (n0 & 63) >> 3;
-          uint8_t* rowp = smem + SM_AH + kc * 16384 + row * 128;
+          const int s0 = sub * 2;  // 16-byte slot of column n0 inside the 128-byte row of chunk c
+          uint8_t* rowp = smem + SM_AH + c * 16384 + row * 128;
           *reinterpret_cast<uint4*>(rowp + ((s0 ^ (row & 7)) * 16)) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(rowp + (((s0 + 1) ^ (row & 7)) * 16)) = make_uint4(h[4], h[5], h[6], h[7]);
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(&ctl->h_full[c]);
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(&ctl->h_full);
       LIFT_MARK(3);
 
       // ---------- epilogue 2: volume rows = bf16(bf16(acc2) + b2) -> smem staging ----------
@@ -383,7 +384,16 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         int fcol = -1, lcol = -1;   // first / last column of this part
         uint32_t fmax_ = 0u, lmax_ = 0u;
         uint32_t* plane32 = reinterpret_cast<uint32_t*>(A.plane);
-        for (int r = r_lo; r < r_hi; ++r) {
+        const bool one_col = r_lo < r_hi && rowcol[r_lo] == rowcol[r_hi - 1];  // rows are sorted by column
+        if (one_col) {  // the common case (a column has up to Z rows): a plain packed max over the part
+          const uint8_t* base = smem + SM_AH + c2 * 4;
+          uint32_t m = *reinterpret_cast<const uint32_t*>(base + r_lo * VOL_STRIDE);
+          for (int r = r_lo + 1; r < r_hi; ++r)
+            m = hmax2_bf16(m, *reinterpret_cast<const uint32_t*>(base + r * VOL_STRIDE));
+          fcol = lcol = rowcol[r_lo];
+          fmax_ = lmax_ = m;
+        }
+        for (int r = r_lo; r < (one_col ? r_lo : r_hi); ++r) {
           const int col = rowcol[r];
           const uint32_t x = *reinterpret_cast<const uint32_t*>(smem + SM_AH + r * VOL_STRIDE + c2 * 4);
           if (col != lcol) {
@@ -489,21 +499,18 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           const uint32_t x0 = __shfl_sync(FULL, pq0.x, src + k), x1 = __shfl_sync(FULL, pq0.y, src + k);
           const uint32_t x2 = __shfl_sync(FULL, pq0.z, src + k), x3 = __shfl_sync(FULL, pq0.w, src + k);
           const uint32_t y0 = __shfl_sync(FULL, pq1.x, src + k), y1 = __shfl_sync(FULL, pq1.y, src + k);
-          const uint32_t y2 = __shfl_sync(FULL, pq1.z, src + k);
+          const uint32_t y2 = __shfl_sync(FULL, pq1.z, src + k), y3 = __shfl_sync(FULL, pq1.w, src + k);
           const bool mine = k < nv;
           float sp = 0.f, wb1 = 0.f;
           if (mine) {
-            const int tr0 = x0 & 0xffff, tr1 = x0 >> 16, tc0 = x1 & 0xffff, tc1 = x1 >> 16;
-            const float wr1 = __uint_as_float(x2), wc1 = __uint_as_float(x3);
-            wb1 = __uint_as_float(y0);
-            const int b0 = y1 & 0xffff, b1i = y1 >> 16;
-            const int v = (int)y2;  // view index of this rank
+            const float wr1 = __uint_as_float(y0), wc1 = __uint_as_float(y1);
+            wb1 = __uint_as_float(y2);
+            const int b0 = y3 & 0xffff, b1i = y3 >> 16;
             const float wr0 = __fadd_rn(1.0f, -wr1), wc0 = __fadd_rn(1.0f, -wc1);
-            const __nv_bfloat16* img = A.fimg + (size_t)v * P.Hf * P.Wf * P.CF;
-            const __nv_bfloat16* p00 = img + ((size_t)tr0 * P.Wf + tc0) * P.CF;
-            const __nv_bfloat16* p01 = img + ((size_t)tr0 * P.Wf + tc1) * P.CF;
-            const __nv_bfloat16* p10 = img + ((size_t)tr1 * P.Wf + tc0) * P.CF;
-            const __nv_bfloat16* p11 = img + ((size_t)tr1 * P.Wf + tc1) * P.CF;
+            const __nv_bfloat16* p00 = A.fimg + x0;
+            const __nv_bfloat16* p01 = A.fimg + x1;
+            const __nv_bfloat16* p10 = A.fimg + x2;
+            const __nv_bfloat16* p11 = A.fimg + x3;
             const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(p00 + l16 * 8));
             const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(p01 + l16 * 8));
             const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(p10 + l16 * 8));
@@ -649,6 +656,7 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
   SNAP_REQUIRE(q->V >= 1 && q->V <= FL_MAXV, "fused lift handles 1..%d views (got %d)", FL_MAXV, q->V);
   SNAP_REQUIRE(q->D == 128 && q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
   SNAP_REQUIRE(q->Z >= 1 && q->Z <= 64, "Z must be <= 64 (got %d)", q->Z);
+  SNAP_REQUIRE((long long)q->V * q->Hf * q->Wf * q->CF < (1LL << 31), "feature maps too large for 32-bit tap offsets");
   SNAP_REQUIRE((long long)q->X * q->Y <= 65536, "too many BEV columns (X*Y <= 65536: 16-bit column ids in the z-max scan)");
   static_assert(sizeof(SnapLiftView) == sizeof(LiftView), "SnapLiftView layout");
   static_assert(sizeof(SnapLiftParams) == sizeof(LiftParams), "SnapLiftParams layout");
