@@ -28,6 +28,12 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "cfg2: R50+FPN encoder + bev_mapper, 4x StreetView 640x480 -> 128x128x60 voxels, bf16"
 V, IMG_HW, G, Z = 4, (480, 640), 128, 60
 LIFT_FLOPS = 2.0 * (257 * 256 + 256 * 128) * G * G * Z          # fusion MLP, SURVEY.md §8(d)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (cold L2: ncu flushes
+# the caches before every replay, so this is the compulsory traffic; with a warm L2 the lift reads 4.7 MB from DRAM)
+LIFT_NCU_DRAM_BYTES = 27_518_720 + 944_640
+LIFT_NCU_SOURCE = "profiles/r01_v8_lift_fused_ncu_full.txt (cold L2); warm L2: profiles/r01_v11_lift_fused_ncu_full.txt"
+XCORR_NCU_DRAM_BYTES = 56_541_696 + 2_496_512
+XCORR_NCU_SOURCE = "profiles/r01_v8_xcorr_rows_ncu_full.txt (includes the chunk-major template copy written by the re-layout kernel)"
 LIFT_BYTES = V * 120 * 160 * 160 * 2 + (257 * 256 + 256 + 256 * 128 + 128) * 2 + G * G * 128 * 2 + G * G
 
 
@@ -445,7 +451,9 @@ def main():
                              "4 distinct tiles rotate",
                        "weights": "random-init Flax tree (48.1 M params), StdConv standardisation inside every step"},
             "e2e": {"value": e2e_val, "unit": "tiles/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + BT * 4 * (Z + 8 * 23)),
+                    "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + sum(
+                        t.numel() * t.element_size() for k_, t in sve._staging(dev, BT, Z, SLOT_E).items()
+                        if k_ in ("zs", "views", "centers"))),
                     "d2h_bytes_per_step": int(out_host.numel() * 2 + valid_host.numel()),
                     "path": "pinned host images -> device (copy stream, double-buffered: the upload of step i+1 overlaps "
                             "the compute of step i; K uploads inside the K-step region, the first one exposed) -> "
@@ -454,7 +462,8 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps), "tiles_per_step": BT * world,
             "clocks": sampler.summary(),
             "roofline": {"kernel": lift_desc, "bound": "tensor", "achieved": achieved_tf, "peak": tf_sus, "unit": "TFLOP/s",
-                         "frac": achieved_tf / tf_sus, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved_tf / tf_sus, "traffic": LIFT_NCU_DRAM_BYTES, "traffic_source": LIFT_NCU_SOURCE,
+                         "peak_source": peak_src,
                          "ms_per_launch": lift_ms, "algorithmic_flops": LIFT_FLOPS, "algorithmic_bytes": LIFT_BYTES,
                          "executed_flops": executed_flops, "executed_tflops": executed_flops / (lift_ms * 1e-3) / 1e12,
                          "visible_voxels": cnt[2], "voxels": G * G * Z,
@@ -480,7 +489,8 @@ def main():
             line["roofline_xcorr"] = {
                 "kernel": "exhaustive (x,y,theta) correlation, G=128 R=36 D=32, 1 example (" + xdesc + ")",
                 "bound": "tensor", "achieved": xflops / (xms * 1e-3) / 1e12, "peak": tf_burst, "unit": "TFLOP/s",
-                "frac": xflops / (xms * 1e-3) / 1e12 / tf_burst, "traffic": None, "ms_per_launch": xms,
+                "frac": xflops / (xms * 1e-3) / 1e12 / tf_burst, "traffic": XCORR_NCU_DRAM_BYTES,
+                "traffic_source": XCORR_NCU_SOURCE, "ms_per_launch": xms,
                 "peak_kind": "burst (the correlation is timed alone, a few ms per launch); the sustained figure is %.1f" % tf_sus,
                 "algorithmic_flops": xflops, "algorithmic_bytes": xbytes, "peak_source": peak_src,
                 "whole_voting_ms": sum(v for k, v in xc.items() if k != "_b4"),
