@@ -109,7 +109,7 @@ class LiftParams(C.Structure):
     _fields_ = [("V", C.c_int), ("Hf", C.c_int), ("Wf", C.c_int), ("CF", C.c_int), ("D", C.c_int),
                 ("S", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
                 ("depth_min", C.c_float), ("depth_max", C.c_float), ("inv_log_range", C.c_float),
-                ("stats_ld", C.c_int)]
+                ("stats_ld", C.c_int), ("xy_paired", C.c_int)]
 
 
 EXPORTED_SYMBOLS += [
@@ -119,4 +119,12 @@ EXPORTED_SYMBOLS += [
     "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_lift_select_pool", "snapb200_lift_fused", "snapb200_lift_fused_scratch_bytes", "snapb200_vertical_max", "snapb200_vertical_pool", "snapb200_mask_rows", "snapb200_confidence", "snapb200_valid_any", "snapb200_match_head",
     "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_xcorr_padded_rotations", "snapb200_rot_templates",
     "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores", "snapb200_xcorr_scores_sw", "snapb200_xcorr_scores_rows", "snapb200_xcorr_scores_rows_workspace",
+    "snapb200_loc_softmax_stats", "snapb200_loc_point_weights", "snapb200_loc_sample", "snapb200_loc_ransac_poses",
+    "snapb200_loc_refine_poses", "snapb200_loc_pose_scoring_workspace", "snapb200_loc_pose_scoring",
+    "snapb200_argmax_rows", "snapb200_loc_nll",
 ]
+
+
+class LocScoreParams(C.Structure):
+    _fields_ = [("B", C.c_int), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("P", C.c_int),
+                ("cell_size", C.c_float), ("mask_out_of_bounds", C.c_int), ("i_xy_batched", C.c_int)]

@@ -123,7 +123,25 @@ class BEVMapper:
     def build_xyz_grid(self, data: Dict):
         """`bev_mapper.py:159-196` (inference): separable voxel-centre coordinates, fp32, host side."""
         t = data["T_view2scene"].t
-        xs, ys = self.grid.cell_centers(0), self.grid.cell_centers(1)
+        xy_shape = None
+        xy = data.get("xy_bev")                                                             # :163
+        if xy is None:
+            xs, ys = self.grid.cell_centers(0), self.grid.cell_centers(1)                   # :164-165
+        else:
+            xy = np.asarray(xy, dtype=F)
+            if xy.ndim == 4:    # batched: the kernels take one set of BEV points per call
+                if not all(np.array_equal(xy[0], xy[b]) for b in range(1, len(xy))):
+                    raise NotImplementedError("per-example xy_bev is not built (BEVLocalizer repeats one frustum, bev_localizer.py:140)")
+                xy = xy[0]
+            key = ("xy_bev", id(data["xy_bev"]))
+            if key not in self._cache:
+                if np.array_equal(xy[..., 0], np.broadcast_to(xy[:, :1, 0], xy.shape[:2])) and \
+                        np.array_equal(xy[..., 1], np.broadcast_to(xy[:1, :, 1], xy.shape[:2])):
+                    self._cache[key] = (np.ascontiguousarray(xy[:, 0, 0]), np.ascontiguousarray(xy[0, :, 1]), None, data["xy_bev"])
+                else:           # arbitrary BEV points (e.g. the field-of-view filtered query frustum, [N,1,2])
+                    self._cache[key] = (np.ascontiguousarray(xy[..., 0].reshape(-1)), np.ascontiguousarray(xy[..., 1].reshape(-1)),
+                                        tuple(xy.shape[:2]), data["xy_bev"])
+            xs, ys, xy_shape, _ = self._cache[key]
         z_offset = data.get("z_offset")
         if z_offset is None:
             cam_h = np.median(t[..., -1].astype(F), axis=-1).astype(F)                      # :171
@@ -131,6 +149,8 @@ class BEVMapper:
         z_offset = np.asarray(z_offset, dtype=F).reshape(-1)
         base = np.arange(0, self.config.get("scene_z_height", 12.0), self.grid.cell_size).astype(F)
         zs = ((base[None] + z_offset[:, None]).astype(F) + F(self.grid.cell_size / 2)).astype(F)  # :188-192
+        if xy_shape is not None:
+            data["xy_shape"] = xy_shape
         return xs, ys, zs
 
     def encode_streetview(self, params, data, train, is_query, debug=False) -> Dict:

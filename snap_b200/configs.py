@@ -97,3 +97,11 @@ def get_block_desc(depth):  # snap/models/resnet.py:158-167
         depth = tuple(depth)
     return {26: [2, 2, 2, 2], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3],
             200: [3, 24, 36, 3]}.get(depth, depth)
+
+
+def bev_localizer() -> ConfigDict:  # defaults.py:343-361
+    return ConfigDict(bev_mapper=bev_mapper(), bev_mapper_query=None, add_confidence_query=False,
+                      add_confidence_map=False, mask_score_out_of_bounds=False, clip_negative_scores=True,
+                      add_temperature=True, init_temperature=2.0, num_pose_samples=None,
+                      num_pose_sampling_retries=1, query_frustum_depth=16.0, filter_points_in_fov=False,
+                      threshold_remove_accurate_poses=None, do_grid_refinement=False)

@@ -26,6 +26,7 @@ struct LiftParams {
   int X, Y, Z;
   float depth_min, depth_max, inv_log_range;  // 1 / log(max/min)
   int stats_ld;                               // row pitch of the stats matrix (>= 2*D + 1, mult of 32)
+  int xy_paired;                              // 0: xs[X], ys[Y] (separable grid); 1: xs[X*Y], ys[X*Y] per column
 };
 
 struct Proj {

@@ -243,7 +243,7 @@ lift_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         uint32_t vm = 0;
         if (col < ncols && z < P.Z) {
           const int ix = col / P.Y, iy = col - ix * P.Y;
-          const float px = A.xs[ix], py = A.ys[iy], pz = A.zs[z];
+          const float px = A.xs[P.xy_paired ? col : ix], py = A.ys[P.xy_paired ? col : iy], pz = A.zs[z];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int v = 2 * s2 + k;

@@ -35,7 +35,7 @@ lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const LiftView* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col_id = blockIdx.x;  // x * Y + y
   const int ix = col_id / P.Y, iy = col_id - ix * P.Y;
-  const float px = xs[ix], py = ys[iy];
+  const float px = xs[P.xy_paired ? col_id : ix], py = ys[P.xy_paired ? col_id : iy];
   const int half = lane >> 4;  // 0: lower row tap, 1: upper row tap
   const int c8 = lane & 15;    // feature channels [8*c8, 8*c8+8)
   const float score_scale = (float)(P.S - 1);

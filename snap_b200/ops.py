@@ -428,3 +428,133 @@ def xcorr_scores_rows(templates: torch.Tensor, m_pad: torch.Tensor, cnt: Optiona
         C.c_void_p(_ptr(templates)), C.c_void_p(_ptr(m_pad)), C.c_void_p(_ptr(cnt)), C.c_void_p(_ptr(den)),
         B, R, G, D, C.c_float(thr), C.c_void_p(_ptr(scores)), C.c_void_p(_ptr(workspace)),
         C.c_size_t(workspace.numel() * workspace.element_size()), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# sampling localizer (bev_localizer.py:156-218, pose_estimation.py)
+# --------------------------------------------------------------------------------------------
+def loc_softmax_stats(sim: torch.Tensor, H: int, W: int, scale: float, row_max: torch.Tensor,
+                      chunk_sum: torch.Tensor, row_sum: Optional[torch.Tensor] = None) -> None:
+    """sim bf16 [..., H*W] (contiguous) -> row_max f32 [rows], chunk_sum f32 [rows, H], row_sum f32 [rows]."""
+    _require(sim, torch.bfloat16, "sim")
+    _require(row_max, torch.float32, "row_max")
+    _require(chunk_sum, torch.float32, "chunk_sum")
+    rows = sim.numel() // (H * W)
+    assert sim.is_contiguous() and row_max.numel() == rows and chunk_sum.numel() == rows * H
+    _lib.check(_lib.lib().snapb200_loc_softmax_stats(
+        C.c_void_p(_ptr(sim)), C.c_longlong(rows), H, W, C.c_float(scale), C.c_void_p(_ptr(row_max)),
+        C.c_void_p(_ptr(row_sum)), C.c_void_p(_ptr(chunk_sum)), _stream()))
+
+
+def loc_point_weights(valid_points: torch.Tensor, conf: Optional[torch.Tensor], exp_t: float,
+                      point_scale: torch.Tensor, row_cdf: torch.Tensor) -> None:
+    _require(valid_points, torch.uint8, "valid_points")
+    B, N = valid_points.shape
+    if conf is not None:
+        _require(conf, torch.float32, "conf")
+        assert conf.shape == (B, N) and conf.is_contiguous()
+    assert valid_points.is_contiguous() and point_scale.shape == (B, N) and row_cdf.shape == (B, N)
+    _lib.check(_lib.lib().snapb200_loc_point_weights(
+        C.c_void_p(_ptr(valid_points)), C.c_void_p(_ptr(conf)), B, N, C.c_float(exp_t),
+        C.c_void_p(_ptr(point_scale)), C.c_void_p(_ptr(row_cdf)), _stream()))
+
+
+def loc_sample(sim: torch.Tensor, row_max: torch.Tensor, chunk_sum: torch.Tensor, row_cdf: torch.Tensor,
+               uniforms: torch.Tensor, H: int, W: int, scale: float, indices: torch.Tensor) -> None:
+    """uniforms f32 [B,K,2] -> indices i32 [B,K,3] = (point, map row, map column)."""
+    _require(sim, torch.bfloat16, "sim")
+    _require(uniforms, torch.float32, "uniforms")
+    _require(indices, torch.int32, "indices")
+    B, N = row_cdf.shape
+    K = uniforms.shape[1]
+    assert uniforms.shape == (B, K, 2) and indices.shape == (B, K, 3) and uniforms.is_contiguous()
+    _lib.check(_lib.lib().snapb200_loc_sample(
+        C.c_void_p(_ptr(sim)), C.c_void_p(_ptr(row_max)), C.c_void_p(_ptr(chunk_sum)), C.c_void_p(_ptr(row_cdf)),
+        C.c_void_p(_ptr(uniforms)), B, N, H, W, K, C.c_float(scale), C.c_void_p(_ptr(indices)), _stream()))
+
+
+def loc_ransac_poses(indices: torch.Tensor, i_xy: torch.Tensor, num_poses: int, num_retries: int,
+                     cell_size: float, poses: torch.Tensor) -> None:
+    """indices i32 [B, num_poses*num_retries*2, 3], i_xy f32 [N,2] or [B,N,2] -> poses f32 [B,num_poses,3]."""
+    _require(indices, torch.int32, "indices")
+    _require(i_xy, torch.float32, "i_xy")
+    _require(poses, torch.float32, "poses")
+    B = indices.shape[0]
+    assert indices.shape[1] == num_poses * num_retries * 2 and indices.is_contiguous() and i_xy.is_contiguous()
+    assert poses.shape == (B, num_poses, 3)
+    _lib.check(_lib.lib().snapb200_loc_ransac_poses(
+        C.c_void_p(_ptr(indices)), C.c_void_p(_ptr(i_xy)), int(i_xy.dim() == 3), B, i_xy.shape[-2], num_poses,
+        num_retries, C.c_float(cell_size), C.c_void_p(_ptr(poses)), _stream()))
+
+
+def loc_refine_poses(init: torch.Tensor, rot_rad: torch.Tensor, off_x: torch.Tensor, off_y: torch.Tensor,
+                     poses: torch.Tensor) -> None:
+    _require(init, torch.float32, "init")
+    B = init.shape[0]
+    nr, nx, ny = rot_rad.numel(), off_x.numel(), off_y.numel()
+    assert poses.shape == (B, nr * nx * ny, 3) and init.is_contiguous()
+    _lib.check(_lib.lib().snapb200_loc_refine_poses(
+        C.c_void_p(_ptr(init)), B, C.c_void_p(_ptr(rot_rad)), nr, C.c_void_p(_ptr(off_x)), nx,
+        C.c_void_p(_ptr(off_y)), ny, C.c_void_p(_ptr(poses)), _stream()))
+
+
+def loc_pose_scoring(sim: torch.Tensor, point_scale: torch.Tensor, i_xy: torch.Tensor,
+                     valid_j: Optional[torch.Tensor], poses: torch.Tensor, H: int, W: int, cell_size: float,
+                     mask_out_of_bounds: bool, scores: torch.Tensor,
+                     workspace: Optional[torch.Tensor] = None) -> None:
+    """sim bf16 [B,N,H*W], point_scale f32 [B,N], poses f32 [B,P,3] -> scores f32 [B,P]."""
+    _require(sim, torch.bfloat16, "sim")
+    _require(poses, torch.float32, "poses")
+    _require(scores, torch.float32, "scores")
+    _require(i_xy, torch.float32, "i_xy")
+    B, N = point_scale.shape
+    P = poses.shape[1]
+    assert poses.shape == (B, P, 3) and scores.shape == (B, P) and poses.is_contiguous() and sim.is_contiguous()
+    assert sim.numel() == B * N * H * W and i_xy.is_contiguous()
+    p = _lib.LocScoreParams()
+    p.B, p.N, p.H, p.W, p.P = B, N, H, W, P
+    p.cell_size = cell_size
+    p.mask_out_of_bounds = int(mask_out_of_bounds)
+    p.i_xy_batched = int(i_xy.dim() == 3)
+    f = _lib.lib().snapb200_loc_pose_scoring_workspace
+    f.restype = C.c_size_t
+    need = int(f(C.byref(p)))
+    if need == 0:
+        raise _lib.SnapB200Error(f"loc_pose_scoring: {_lib.lib().snapb200_last_error().decode()}")
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=sim.device)
+    assert workspace.numel() * workspace.element_size() >= need
+    if valid_j is not None:
+        _require(valid_j, torch.uint8, "valid_j")
+    _lib.check(_lib.lib().snapb200_loc_pose_scoring(
+        C.byref(p), C.c_void_p(_ptr(sim)), C.c_void_p(_ptr(point_scale)), C.c_void_p(_ptr(i_xy)),
+        C.c_void_p(_ptr(valid_j)), C.c_void_p(_ptr(poses)), C.c_void_p(_ptr(workspace)),
+        C.c_size_t(workspace.numel() * workspace.element_size()), C.c_void_p(_ptr(scores)), _stream()))
+
+
+def argmax_rows(x: torch.Tensor, start: int, idx: torch.Tensor, rows3: Optional[torch.Tensor] = None,
+                best_row3: Optional[torch.Tensor] = None) -> None:
+    _require(x, torch.float32, "x")
+    _require(idx, torch.int32, "idx")
+    rows, cols = x.shape
+    assert x.is_contiguous() and idx.numel() == rows
+    if rows3 is not None:
+        assert rows3.shape == (rows, cols, 3) and rows3.is_contiguous() and best_row3.shape == (rows, 3)
+    _lib.check(_lib.lib().snapb200_argmax_rows(
+        C.c_void_p(_ptr(x)), rows, cols, start, C.c_void_p(_ptr(idx)), C.c_void_p(_ptr(rows3)),
+        C.c_void_p(_ptr(best_row3)), _stream()))
+
+
+def loc_nll(scores: torch.Tensor, samples: torch.Tensor, best: torch.Tensor, gt: torch.Tensor,
+            remove: Optional[Sequence[float]], out: torch.Tensor, dr_samples: Optional[torch.Tensor] = None,
+            dt_samples: Optional[torch.Tensor] = None) -> None:
+    for t, nm in ((scores, "scores"), (samples, "samples"), (best, "best"), (gt, "gt"), (out, "out")):
+        _require(t, torch.float32, nm)
+        assert t.is_contiguous()
+    B, P1 = scores.shape
+    assert samples.shape == (B, P1, 3) and best.shape == (B, 3) and gt.shape == (B, 3) and out.shape == (B, 7)
+    dr_min, dt_min = (float(remove[0]), float(remove[1])) if remove is not None else (0.0, 0.0)
+    _lib.check(_lib.lib().snapb200_loc_nll(
+        C.c_void_p(_ptr(scores)), C.c_void_p(_ptr(samples)), C.c_void_p(_ptr(best)), C.c_void_p(_ptr(gt)), B, P1,
+        int(remove is not None), C.c_float(dr_min), C.c_float(dt_min), C.c_void_p(_ptr(out)),
+        C.c_void_p(_ptr(dr_samples)), C.c_void_p(_ptr(dt_samples)), _stream()))

@@ -20,7 +20,8 @@ from . import _lib, configs, image_encoder, ops, types
 F = np.float32
 
 
-def fill_lift_params(cfg, V: int, hf: int, wf: int, X: int, Y: int, Z: int, stats_ld: int) -> "_lib.LiftParams":
+def fill_lift_params(cfg, V: int, hf: int, wf: int, X: int, Y: int, Z: int, stats_ld: int,
+                     xy_paired: bool = False) -> "_lib.LiftParams":
     """Static (shape) part of the lift launch."""
     k_vs = cfg.top_k_view_selection
     if k_vs and V > k_vs:      # view-selection path (`:241-249`)
@@ -38,6 +39,7 @@ def fill_lift_params(cfg, V: int, hf: int, wf: int, X: int, Y: int, Z: int, stat
     p.depth_min, p.depth_max = dmin, dmax
     p.inv_log_range = float(F(1.0) / np.log(F(dmax / dmin)).astype(F))
     p.stats_ld = stats_ld
+    p.xy_paired = int(xy_paired)
     return p
 
 
@@ -186,12 +188,17 @@ class StreetViewEncoder:
         dev = images.device if isinstance(images, torch.Tensor) and images.is_cuda else torch.device("cuda")
         xs, ys, zs = data["xyz_grid"]          # xs [X], ys [Y] (NumPy fp32), zs [B, Z]
         X, Y, Z = len(xs), len(ys), zs.shape[1]
+        paired = "xy_shape" in data            # data['xy_bev'] that is not a separable grid: xs, ys per column [X*Y]
+        if paired:
+            X, Y = data["xy_shape"]
+            assert len(xs) == X * Y and len(ys) == X * Y
         enc_plan = self.image_encoder.plan(params["image_encoder"], B * V, H, W, dev)
         hf, wf = enc_plan.cropped_shapes()[-1]
         stride = enc_plan.strides[-1]
         buf = self._buffers(dev, B, V, H, W, hf, wf, X, Y, Z)
-        if buf["xs"] is None:
+        if buf["xs"] is None or (paired and buf.get("xs_src") is not xs):
             buf["xs"], buf["ys"] = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+            buf["xs_src"] = xs
         capturing = torch.cuda.is_current_stream_capturing()
         slot = data.get("staging_slot")
         if slot is None:
@@ -237,7 +244,7 @@ class StreetViewEncoder:
         bank.run()
         Bm = bank.b_mats
         N = X * Y * Z
-        lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, 288)
+        lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, 288, paired)
         dbg = {}
         if not fused and buf["volume"] is None:
             buf["volume"] = torch.zeros((B, N, 128), dtype=torch.bfloat16, device=dev)

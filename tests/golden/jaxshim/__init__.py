@@ -139,7 +139,13 @@ class DataclassArray:
         return jnp
 
     def __getitem__(self, idx):
-        return type(self)(**{n: getattr(self, n)[idx] for n in self._fields})
+        # the index addresses the BATCH dimensions only: expand an Ellipsis to the batch rank
+        tup = idx if isinstance(idx, tuple) else (idx,)
+        if any(i is Ellipsis for i in tup):
+            k = sum(1 for i in tup if i is not Ellipsis and i is not None)
+            pos = [j for j, i in enumerate(tup) if i is Ellipsis][0]
+            tup = tup[:pos] + (slice(None),) * (len(self.shape) - k) + tup[pos + 1:]
+        return type(self)(**{n: getattr(self, n)[tup] for n in self._fields})
 
     def __len__(self):
         return self.shape[0]
@@ -237,6 +243,21 @@ def softmax(x, axis=-1, where=None, initial=None):
     return (e / e.sum(axis=axis, keepdims=True)).astype(x.dtype)
 
 
+def random_choice(rng, a, shape=(), replace=True, p=None):
+    """Stand-in for jax.random.choice(key, a, shape, replace=True, p): inverse CDF `searchsorted(cumsum(p),
+    total * (1 - u))` with `rng` a numpy Generator instead of a threefry key."""
+    assert replace and p is not None
+    cdf = np.cumsum(np.asarray(p, np.float64))
+    u = rng.random(shape)
+    return np.minimum(np.searchsorted(cdf, cdf[-1] * (1.0 - u), side="left"), a - 1)
+
+
+def log_softmax(x, axis=-1):
+    x = np.asarray(x)
+    m = x.max(axis=axis, keepdims=True)
+    return (x - m - np.log(np.exp(x - m).sum(axis=axis, keepdims=True))).astype(x.dtype)
+
+
 class _Permissive(types.ModuleType):
     """Module stub: any attribute is a permissive object (class / decorator / callable)."""
 
@@ -295,6 +316,9 @@ def install(reference_root: str) -> None:
     jnn.initializers = _Permissive("jax.nn.initializers")
     jax.scipy, jax.lax, jax.nn = jsp, lax, jnn
     jax.random, jax.image, jax.tree_util = _Permissive("jax.random"), _Permissive("jax.image"), _Permissive("jax.tree_util")
+    jax.random.choice = random_choice
+    jnn.log_softmax = log_softmax
+    jnn.relu = lambda x: np.maximum(x, 0)
     mods = {"jax": jax, "jax.numpy": jnp, "jax.scipy": jsp, "jax.scipy.ndimage": jnd, "jax.scipy.signal": jsg,
             "jax.lax": lax, "jax.nn": jnn, "jax.nn.initializers": jnn.initializers, "jax.random": jax.random}
     dca = types.ModuleType("dataclass_array"); dca.DataclassArray = DataclassArray
