@@ -431,7 +431,65 @@ def main():
         finally:
             for nm in names_x:
                 setattr(_ops, nm, orig_x[nm])
+    # ---- sampling localizer at the config-4 per-example shape: 4,652 frustum points x 128 x 128 map, D = 32,
+    #      10,000 RANSAC poses x 8 retries (train_localization.py:26-30) + 41^3 grid refinement (eval_localization.py:42)
+    lc = {}
+    if rank == 0:
+        try:
+            from snap_b200 import bev_localizer as bl, ops as _ops, pose_estimation as pe
+            _, _, q_xy = bl.build_query_frustum_grid(0.2, 16.0, True, 72.0)
+            NP = q_xy.shape[0]
+            gq = torch.Generator(device="cpu").manual_seed(7)
+            fqp = torch.nn.functional.normalize(torch.randn((1, NP, 32), generator=gq), dim=-1)
+            fmp = torch.nn.functional.normalize(torch.randn((1, G, G, 32), generator=gq), dim=-1)
+            vqp = (torch.rand((1, NP), generator=gq) < 0.6)
+            fqp = (fqp * vqp[..., None]).to(torch.bfloat16).to(dev)
+            fmp = fmp.to(torch.bfloat16).to(dev)
+            vqp = vqp.to(torch.uint8).to(dev)
+            q_xy_d = torch.from_numpy(np.ascontiguousarray(q_xy[:, 0])).to(dev)
+            gsamp = torch.Generator(device=dev).manual_seed(3)
+            names_l = ["gemm", "loc_softmax_stats", "loc_point_weights", "loc_sample", "loc_ransac_poses", "loc_refine_poses",
+                       "loc_pose_scoring", "argmax_rows"]
+            orig_l = {nm: getattr(_ops, nm) for nm in names_l}
+            evl = []
+
+            def wrapl(nm):
+                def f(*a, **k):
+                    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_.record(); r_ = orig_l[nm](*a, **k); e_.record()
+                    key = nm
+                    if nm == "loc_pose_scoring":
+                        key = "loc_pose_scoring[P=%d]" % a[4].shape[1]
+                    evl.append((key, s_, e_))
+                    return r_
+                return f
+            for nm in names_l:
+                setattr(_ops, nm, wrapl(nm))
+            try:
+                reps = 5
+                for rep in range(reps + 2):
+                    if rep == 2:
+                        evl.clear()
+                    maps = pe.point_similarities(fqp, vqp, fmp, 2.0, True, None)
+                    poses = pe.sample_transforms_ransac_batched(gsamp, maps, q_xy_d, 10_000, 8, grid)
+                    sc_ = pe.pose_scoring_many_batched(poses, maps, q_xy_d, None, grid, False)
+                    bi_ = torch.empty((1,), dtype=torch.int32, device=dev)
+                    bp_ = torch.empty((1, 3), dtype=torch.float32, device=dev)
+                    _ops.argmax_rows(sc_, 0, bi_, poses, bp_)
+                    pe.grid_refinement_batched(bp_, maps, q_xy_d, None, grid, False)
+                torch.cuda.synchronize()
+                for nm, s_, e_ in evl:
+                    lc[nm] = lc.get(nm, 0.0) + s_.elapsed_time(e_) / reps
+                lc["_valid_points"] = int(vqp.sum().item())
+                lc["_points"] = NP
+            finally:
+                for nm in names_l:
+                    setattr(_ops, nm, orig_l[nm])
+        except Exception as e:  # the localizer block must never take the headline measurement down
+            lc = {"_error": repr(e)}
     if args.phases and rank == 0:
+        print("  sampling localizer (N=4652, G=128, P=10000x8, 41^3 refinement): " +
+              ", ".join(f"{k} {v:.3f} ms" for k, v in lc.items() if not k.startswith("_")), file=sys.stderr)
         print("  exhaustive voting (G=128, R=36, D=32, 1 example): " + ", ".join(f"{k} {v:.3f} ms" for k, v in xc.items() if k != "_b4"), file=sys.stderr)
         print("  batch of 4, per example: " + ", ".join(f"{k} {v:.3f} ms" for k, v in xc.get("_b4", {}).items()), file=sys.stderr)
         for k, v in sorted(phases.items(), key=lambda kv: -kv[1]):
@@ -497,6 +555,26 @@ def main():
                 "phases_ms": {k: round(v, 4) for k, v in xc.items() if k != "_b4"},
                 "batch4_ms_per_example": {k: round(v, 4) for k, v in xc.get("_b4", {}).items()},
                 "batch4_frac": (xflops / (xc["_b4"][xkey] * 1e-3) / 1e12 / tf_burst) if "_b4" in xc else None}
+        if lc and "_error" in lc:
+            line["localizer"] = {"error": lc["_error"]}
+        elif lc:
+            nvp, NPt = lc["_valid_points"], lc["_points"]
+            k_ref = "loc_pose_scoring[P=68921]"
+            ref_ms = lc.get(k_ref, 0.0)
+            # pose_scoring_many on the refinement lattice: every valid point's similarity map is read once
+            # (bf16 G x G), 4 taps + ~60 instructions per (pose, point) pair; the CUDA-core issue rate is the tighter
+            # bound (HBM: nvp * G*G*2 B, a few tens of microseconds)
+            pairs = 68921.0 * nvp
+            line["localizer"] = {
+                "workload": "sampling localizer of bev_localizer.py:156-218 per example: %d frustum points (%d valid) x "
+                            "%dx%d map, D=32, 10,000 poses x 8 retries, 41^3 grid refinement" % (NPt, nvp, G, G),
+                "phases_ms": {k: round(v, 4) for k, v in lc.items() if not k.startswith("_")},
+                "total_ms": round(sum(v for k, v in lc.items() if not k.startswith("_")), 4),
+                "refinement_scoring": {"ms": ref_ms, "pose_point_pairs": pairs,
+                                       "gpairs_per_s": pairs / (ref_ms * 1e-3) / 1e9 if ref_ms else None,
+                                       "algorithmic_bytes": nvp * G * G * 2 + 68921 * 16,
+                                       "hbm_gbs_if_bytes_only": (nvp * G * G * 2 + 68921 * 16) / (ref_ms * 1e-3) / 1e9 if ref_ms else None,
+                                       "hbm_peak_gbs": hbm_peak}}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             t = cpu_reference_tile(99, cores)
