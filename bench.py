@@ -482,6 +482,30 @@ def main():
                     lc[nm] = lc.get(nm, 0.0) + s_.elapsed_time(e_) / reps
                 lc["_valid_points"] = int(vqp.sum().item())
                 lc["_points"] = NP
+                # the same chain as ONE captured CUDA graph (fixed uniforms): launch-latency-free time per example
+                u_fix = torch.rand((1, 10_000 * 8 * 2, 2), dtype=torch.float32, device=dev, generator=gsamp)
+                for nm in names_l:
+                    setattr(_ops, nm, orig_l[nm])
+
+                def chain():
+                    maps = pe.point_similarities(fqp, vqp, fmp, 2.0, True, None)
+                    poses = pe.transforms_from_correspondences(pe.sample_correspondences(maps, u_fix), q_xy_d, 10_000, 8, grid)
+                    sc_ = pe.pose_scoring_many_batched(poses, maps, q_xy_d, None, grid, False)
+                    bi_ = torch.empty((1,), dtype=torch.int32, device=dev)
+                    bp_ = torch.empty((1, 3), dtype=torch.float32, device=dev)
+                    _ops.argmax_rows(sc_, 0, bi_, poses, bp_)
+                    return pe.grid_refinement_batched(bp_, maps, q_xy_d, None, grid, False)
+                g_loc = capture(chain)
+                for _ in range(3):
+                    g_loc.replay()
+                torch.cuda.synchronize()
+                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0_.record()
+                for _ in range(20):
+                    g_loc.replay()
+                e1_.record()
+                torch.cuda.synchronize()
+                lc["_graph_ms"] = e0_.elapsed_time(e1_) / 20
             finally:
                 for nm in names_l:
                     setattr(_ops, nm, orig_l[nm])
@@ -570,6 +594,9 @@ def main():
                             "%dx%d map, D=32, 10,000 poses x 8 retries, 41^3 grid refinement" % (NPt, nvp, G, G),
                 "phases_ms": {k: round(v, 4) for k, v in lc.items() if not k.startswith("_")},
                 "total_ms": round(sum(v for k, v in lc.items() if not k.startswith("_")), 4),
+                "total_ms_cuda_graph": round(lc.get("_graph_ms", 0.0), 4),
+                "note": "phases_ms are event-bracketed eager launches (short kernels include host launch latency); "
+                        "total_ms_cuda_graph replays the whole chain as one captured graph",
                 "refinement_scoring": {"ms": ref_ms, "pose_point_pairs": pairs,
                                        "gpairs_per_s": pairs / (ref_ms * 1e-3) / 1e9 if ref_ms else None,
                                        "algorithmic_bytes": nvp * G * G * 2 + 68921 * 16,

@@ -347,7 +347,8 @@ __global__ void loc_refine_poses_kernel(const float* __restrict__ init, const fl
 // ---------------------------------------------------------------------------------------------------------------------
 // pose_scoring_many (pose_estimation.py:65-85): score[p] = sum_n valid_n * interp(sim_points[n], (T_p i_xy[n]) / cell)
 //
-// grid (point splits S, pose chunks, B); block = 512 threads, PPT poses per thread held in registers (cos, sin, t).
+// grid (pose chunks, point splits S, B); block = 256 threads (two blocks per SM: one computes while the other waits
+// for its next map), PPT poses per thread held in registers as (cos, sin, t) / cell_size.
 // The block walks the valid points of its split: the similarity map of one point (H*W bf16, 32 KB at G = 128) is
 // streamed into shared memory with cp.async (double-buffered when two maps fit) and every pose of the chunk gathers
 // its four bilinear taps from there (grids.interpolate_nd: taps of (uv - 0.5), clamped indices, corner order
@@ -372,21 +373,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int PPT>
-__global__ void __launch_bounds__(512, 1)
+constexpr int LOC_SCORE_THREADS = 256;
+
+// Shared-memory layout of one similarity map: rows of RS = W + 8 bf16 (16-byte aligned rows for cp.async, 8 zero
+// columns on the right) and one zero row below.  Coordinates are clamped to [0, H-1] x [0, W-1] BEFORE the floor:
+// a point left of / above the map then has weights (1, 0) on taps (0, 1) and a point right of / below it weights
+// (1, 0) on taps (last, zero padding) -- the same value as the reference's index-clamped taps (whose two weights sum
+// to 1 on the same edge texel), with no per-tap clamps in the inner loop.
+template <int PPT, bool MASK>
+__global__ void __launch_bounds__(LOC_SCORE_THREADS, 2)
 loc_pose_scoring_kernel(const LocScoreArgs A) {
+  constexpr int NT = LOC_SCORE_THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int HW = A.H * A.W;
-  const int b = blockIdx.z, split = blockIdx.x;
+  const int RS = A.W + 8;                 // padded row stride (elements)
+  const int MAPSZ = (A.H + 1) * RS;       // elements per padded map
+  const int b = blockIdx.z, split = blockIdx.y;  // x = pose chunk: co-scheduled blocks share their maps in L2
   const int tid = threadIdx.x;
-  // shared memory: nbuf maps, then the point list of this split (index, x, y, scale), then the map validity
+  // shared memory: nbuf padded maps, then the point list of this split (index, x, y, scale), then the map validity
   unsigned short* maps = reinterpret_cast<unsigned short*>(smem_raw);
   const int per = (A.N + A.S - 1) / A.S;
   const int n0 = min(split * per, A.N), n1 = min(n0 + per, A.N);
-  float4* plist = reinterpret_cast<float4*>(smem_raw + (size_t)A.nbuf * HW * 2);
+  float4* plist = reinterpret_cast<float4*>(smem_raw + (size_t)A.nbuf * MAPSZ * 2);
   uint8_t* vj = reinterpret_cast<uint8_t*>(plist + per);
   __shared__ int s_count;
   if (tid == 0) s_count = 0;
+  // zero padding (never touched by the cp.async copies): 8 columns right of every row, one row below
+  for (int buf = 0; buf < A.nbuf; ++buf) {
+    unsigned short* m = maps + (size_t)buf * MAPSZ;
+    for (int k = tid; k < A.H * 8; k += NT) m[(k >> 3) * RS + A.W + (k & 7)] = 0;
+    for (int k = tid; k < RS; k += NT) m[A.H * RS + k] = 0;
+  }
   __syncthreads();
   // compaction of the valid points (order inside the list does not matter for the result up to fp32 summation
   // order; keep it deterministic: warp 0 walks the range in order)
@@ -406,39 +423,47 @@ loc_pose_scoring_kernel(const LocScoreArgs A) {
     }
     if (tid == 0) s_count = cnt;
   }
-  if (A.mask_oob) {
+  if (MASK) {
     const uint8_t* g = A.valid_j + (size_t)b * HW;
-    for (int k = tid; k < HW; k += 512) vj[k] = g[k];
+    for (int k = tid; k < HW; k += NT) vj[k] = g[k];
   }
-  // poses of this thread
+  // poses of this thread, pre-divided by the cell size: uv - 0.5 = (c x - s y + tx) / cell - 0.5
   float pc[PPT], psn[PPT], ptx[PPT], pty[PPT], acc[PPT];
-  const int p0 = blockIdx.y * (512 * PPT);
+  const int p0 = blockIdx.x * (NT * PPT);
+  const float inv_cell = __fdiv_rn(1.f, A.cell);
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
-    const int p = p0 + k * 512 + tid;
+    const int p = p0 + k * NT + tid;
     acc[k] = 0.f;
     if (p < A.P) {
       const float* q = A.poses + ((size_t)b * A.P + p) * 3;
-      sincosf(q[0], &psn[k], &pc[k]);
-      ptx[k] = q[1];
-      pty[k] = q[2];
+      float sn, cs;
+      sincosf(q[0], &sn, &cs);
+      pc[k] = cs * inv_cell;
+      psn[k] = sn * inv_cell;
+      ptx[k] = q[1] * inv_cell - 0.5f;
+      pty[k] = q[2] * inv_cell - 0.5f;
     } else {
-      pc[k] = 1.f; psn[k] = 0.f; ptx[k] = 0.f; pty[k] = 0.f;
+      pc[k] = inv_cell; psn[k] = 0.f; ptx[k] = 0.f; pty[k] = 0.f;
     }
   }
   __syncthreads();
   const int count = s_count;
   const __nv_bfloat16* simb = A.sim + (size_t)b * A.N * HW;
-  const int vecs = HW / 8;  // 16-byte vectors per map
+  const int vpr = A.W >> 3;        // 16-byte vectors per map row
+  const int vecs = A.H * vpr;      // ... per map
   auto prefetch = [&](int k) {
     const int n = __float_as_int(plist[k].x);
     const uint4* src = reinterpret_cast<const uint4*>(simb + (size_t)n * HW);
-    uint4* dst = reinterpret_cast<uint4*>(maps + (size_t)(k % A.nbuf) * HW);
-    for (int v = tid; v < vecs; v += 512) cp_async16(dst + v, src + v);
+    unsigned short* dst = maps + (size_t)(k % A.nbuf) * MAPSZ;
+    for (int v = tid; v < vecs; v += NT) {
+      const int row = v / vpr, cvec = v - row * vpr;
+      cp_async16(dst + row * RS + cvec * 8, src + v);
+    }
     cp_async_commit();
   };
-  const float fH = (float)A.H, fW = (float)A.W;
-  const int Hm1 = A.H - 1, Wm1 = A.W - 1;
+  const float uH = (float)(A.H - 1), uW = (float)(A.W - 1);
+  const unsigned magic_off = 0x4B000000u * (unsigned)RS + 0x4B000000u;  // bits of 2^23, folded out of the index (mod 2^32)
   if (count > 0) prefetch(0);
   for (int k = 0; k < count; ++k) {
     if (A.nbuf == 2 && k + 1 < count) {
@@ -448,34 +473,42 @@ loc_pose_scoring_kernel(const LocScoreArgs A) {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const unsigned short* mp = maps + (size_t)(k % A.nbuf) * HW;
+    const unsigned short* mp = maps + (size_t)(k % A.nbuf) * MAPSZ;
     const float4 pt = plist[k];
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
-      // Transform2D.transform (geometry.py:138-140) then / cell_size (:75)
-      const float jx = __fadd_rn(ptx[q], __fadd_rn(__fmul_rn(pc[q], pt.y), __fmul_rn(-psn[q], pt.z)));
-      const float jy = __fadd_rn(pty[q], __fadd_rn(__fmul_rn(psn[q], pt.y), __fmul_rn(pc[q], pt.z)));
-      const float u = __fdiv_rn(jx, A.cell), v = __fdiv_rn(jy, A.cell);
-      const float cu = __fadd_rn(u, -0.5f), cv = __fadd_rn(v, -0.5f);
-      const float fu = floorf(cu), fv = floorf(cv);
-      const float whu = __fadd_rn(cu, -fu), whv = __fadd_rn(cv, -fv);
-      const float wlu = __fadd_rn(1.f, -whu), wlv = __fadd_rn(1.f, -whv);
-      // clamp in float first: far-away poses must not overflow the int conversion
-      const int iu = (int)fminf(fmaxf(fu, -2.f), fH), iv = (int)fminf(fmaxf(fv, -2.f), fW);
-      const int r0 = min(max(iu, 0), Hm1), r1 = min(max(iu + 1, 0), Hm1);
-      const int c0 = min(max(iv, 0), Wm1), c1 = min(max(iv + 1, 0), Wm1);
-      const float s00 = bf16_bits_to_float(mp[r0 * A.W + c0]), s01 = bf16_bits_to_float(mp[r0 * A.W + c1]);
-      const float s10 = bf16_bits_to_float(mp[r1 * A.W + c0]), s11 = bf16_bits_to_float(mp[r1 * A.W + c1]);
-      float val = __fmul_rn(__fmul_rn(wlu, wlv), s00);
-      val = __fadd_rn(val, __fmul_rn(__fmul_rn(wlu, whv), s01));
-      val = __fadd_rn(val, __fmul_rn(__fmul_rn(whu, wlv), s10));
-      val = __fadd_rn(val, __fmul_rn(__fmul_rn(whu, whv), s11));
-      bool ok = true;
-      if (A.mask_oob) {
-        ok = u >= 0.f && u < fH && v >= 0.f && v < fW &&
-             (vj[r0 * A.W + c0] & vj[r0 * A.W + c1] & vj[r1 * A.W + c0] & vj[r1 * A.W + c1]) != 0;
+      // Transform2D.transform (geometry.py:138-140), / cell_size (:75), - 0.5 (grids.py:129): two FMAs per axis
+      const float cu0 = fmaf(pc[q], pt.y, fmaf(-psn[q], pt.z, ptx[q]));
+      const float cv0 = fmaf(psn[q], pt.y, fmaf(pc[q], pt.z, pty[q]));
+      const float cu = fminf(fmaxf(cu0, 0.f), uH), cv = fminf(fmaxf(cv0, 0.f), uW);
+      // floor + float->int without the conversion unit (FRND / F2I are quarter rate): for 0 <= x < 2^22,
+      // x + 2^23 rounded toward zero is 2^23 + floor(x), whose mantissa bits are the integer
+      const float mu = __fadd_rz(cu, 8388608.f), mv = __fadd_rz(cv, 8388608.f);
+      const float fu = mu - 8388608.f, fv = mv - 8388608.f;
+      const float whu = cu - fu, whv = cv - fv;
+      const float wlu = 1.f - whu, wlv = 1.f - whv;
+      const unsigned off = (unsigned)__float_as_int(mu) * (unsigned)RS + (unsigned)__float_as_int(mv) - magic_off;
+      const unsigned short* a = mp + off;
+      const float s00 = bf16_bits_to_float(a[0]), s01 = bf16_bits_to_float(a[1]);
+      const float s10 = bf16_bits_to_float(a[RS]), s11 = bf16_bits_to_float(a[RS + 1]);
+      // corner order (0,0),(0,1),(1,0),(1,1) of map_coordinates
+      float val = (wlu * wlv) * s00;
+      val = fmaf(wlu * whv, s01, val);
+      val = fmaf(whu * wlv, s10, val);
+      val = fmaf(whu * whv, s11, val);
+      if (MASK) {
+        // point inside the map (0 <= uv < size <=> -0.5 <= uv - 0.5 < size - 0.5) and the reference's four
+        // index-clamped taps valid (grids.py:131-136)
+        const float gu = floorf(cu0), gv = floorf(cv0);
+        const int iu = (int)fminf(fmaxf(gu, -2.f), uH + 1.f), iv = (int)fminf(fmaxf(gv, -2.f), uW + 1.f);
+        const int r0 = min(max(iu, 0), A.H - 1) * A.W, r1 = min(max(iu + 1, 0), A.H - 1) * A.W;
+        const int c0 = min(max(iv, 0), A.W - 1), c1 = min(max(iv + 1, 0), A.W - 1);
+        const bool ok = cu0 >= -0.5f && cu0 < uH + 0.5f && cv0 >= -0.5f && cv0 < uW + 0.5f &&
+                        (vj[r0 + c0] & vj[r0 + c1] & vj[r1 + c0] & vj[r1 + c1]) != 0;
+        if (ok) acc[q] = fmaf(val, pt.w, acc[q]);
+      } else {
+        acc[q] = fmaf(val, pt.w, acc[q]);
       }
-      if (ok) acc[q] += val * pt.w;
     }
     if (A.nbuf == 1) {
       __syncthreads();  // everyone is done with the single buffer before it is overwritten
@@ -486,7 +519,7 @@ loc_pose_scoring_kernel(const LocScoreArgs A) {
   }
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
-    const int p = p0 + k * 512 + tid;
+    const int p = p0 + k * NT + tid;
     if (p < A.P) A.partial[((size_t)b * A.S + split) * A.P + p] = acc[k];
   }
 }
@@ -741,18 +774,19 @@ int snapb200_loc_refine_poses(const float* init, int B, const float* rot_rad, in
 static int loc_score_plan(const SnapLocScoreParams* p, int* ppt, int* chunks, int* splits, int* nbuf, size_t* smem) {
   SNAP_REQUIRE(p != nullptr, "null params");
   SNAP_REQUIRE(p->B >= 1 && p->N >= 1 && p->H >= 1 && p->W >= 1 && p->P >= 1, "empty problem");
-  SNAP_REQUIRE((p->H * p->W) % 8 == 0, "H*W must be a multiple of 8");
+  SNAP_REQUIRE(p->W % 8 == 0, "the map width must be a multiple of 8 (got %d)", p->W);
   SNAP_REQUIRE(p->cell_size > 0.f, "cell_size must be positive");
-  *ppt = p->P > 16384 ? 16 : 8;
-  *chunks = (p->P + 512 * *ppt - 1) / (512 * *ppt);
-  int S = (2 * num_sms() + *chunks * p->B - 1) / (*chunks * p->B);
+  *ppt = p->P > 2048 ? 16 : 8;
+  *chunks = (p->P + LOC_SCORE_THREADS * *ppt - 1) / (LOC_SCORE_THREADS * *ppt);
+  int S = (4 * num_sms() + *chunks * p->B - 1) / (*chunks * p->B);  // two resident blocks per SM, two waves
   S = S < 1 ? 1 : S;
   if (S > (p->N + 15) / 16) S = (p->N + 15) / 16;  // at least ~16 points per split
   *splits = S;
   const int per = (p->N + S - 1) / S;
-  const size_t map_bytes = (size_t)p->H * p->W * 2;
+  const size_t map_bytes = (size_t)(p->H + 1) * (p->W + 8) * 2;  // padded layout of loc_pose_scoring_kernel
   const size_t extra = (size_t)per * 16 + (p->mask_out_of_bounds ? (size_t)p->H * p->W : 0) + 16;
   const size_t cap = 227 * 1024 - 1024;
+  // double-buffer when two maps fit; the common 128 x 128 map (32 KB) then also leaves room for two blocks per SM
   *nbuf = 2 * map_bytes + extra <= cap ? 2 : 1;
   *smem = *nbuf * map_bytes + extra;
   SNAP_REQUIRE(*smem <= cap, "similarity map of %d x %d does not fit in shared memory", p->H, p->W);
@@ -787,14 +821,25 @@ int snapb200_loc_pose_scoring(const SnapLocScoreParams* p, const void* sim, cons
   a.mask_oob = p->mask_out_of_bounds;
   a.cell = p->cell_size;
   cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid(splits, chunks, p->B);
+  const dim3 grid(chunks, splits, p->B);
+#define SNAP_LOC_SCORE(PPT_, MASK_)                                                                              \
+  do {                                                                                                          \
+    static size_t configured = 0; /* largest dynamic shared memory size set so far (attribute is sticky) */     \
+    if (smem > configured) {                                                                                    \
+      if (int rc = check_cuda(cudaFuncSetAttribute(loc_pose_scoring_kernel<PPT_, MASK_>,                        \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),     \
+                              "cudaFuncSetAttribute(loc_pose_scoring)"))                                        \
+        return rc;                                                                                              \
+      configured = smem;                                                                                        \
+    }                                                                                                           \
+    loc_pose_scoring_kernel<PPT_, MASK_><<<grid, LOC_SCORE_THREADS, smem, s>>>(a);                              \
+  } while (0)
   if (ppt == 16) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(loc_pose_scoring_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
-    loc_pose_scoring_kernel<16><<<grid, 512, smem, s>>>(a);
+    if (p->mask_out_of_bounds) SNAP_LOC_SCORE(16, true); else SNAP_LOC_SCORE(16, false);
   } else {
-    if (int rc = check_cuda(cudaFuncSetAttribute(loc_pose_scoring_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr")) return rc;
-    loc_pose_scoring_kernel<8><<<grid, 512, smem, s>>>(a);
+    if (p->mask_out_of_bounds) SNAP_LOC_SCORE(8, true); else SNAP_LOC_SCORE(8, false);
   }
+#undef SNAP_LOC_SCORE
   if (int rc = check_launch("loc_pose_scoring_kernel")) return rc;
   const long long total = (long long)p->B * p->P;
   loc_score_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a.partial, splits, p->P, total, scores);

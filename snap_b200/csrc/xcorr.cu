@@ -121,16 +121,38 @@ __global__ void pad_map_kernel(const __nv_bfloat16* __restrict__ m, int B, int G
 }
 
 // cnt[b,r,u,v] = sum_{i,j} qv[b,r,i,j] * mv[b,u-i,v-j]   (mv = 0 outside the map)
-// One block per (b, r, u, chunk of 256 v); rows as G-bit masks in shared memory.
+//
+// flag[b*R] (the `den` output, overwritten afterwards by xcorr_den_kernel) = 1 if the whole map of example b is valid
+// (every aerial-fused map is, bev_mapper.py:208-211): then the count is a rectangle sum of q_valid and the kernel
+// below leaves the work to xcorr_count_allvalid_kernel.
+__global__ void __launch_bounds__(256)
+xcorr_allvalid_flag_kernel(const uint8_t* __restrict__ m_valid, int GG, int R, float* __restrict__ flag) {
+  __shared__ int s_all;
+  if (threadIdx.x == 0) s_all = 1;
+  __syncthreads();
+  const uint8_t* mv = m_valid + (size_t)blockIdx.x * GG;
+  bool all = true;
+  for (int k = threadIdx.x; k < GG; k += 256) all &= mv[k] != 0;
+  if (!__all_sync(0xffffffffu, all) && (threadIdx.x & 31) == 0) s_all = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) flag[(size_t)blockIdx.x * R] = s_all ? 1.f : 0.f;
+}
+
+constexpr int COUNT_UT = 8;  // consecutive u per block of the generic kernel
+
+// Generic map validity.  One block per (b, r, tile of COUNT_UT shifts u, chunk of 256 v); rows as G-bit masks in shared
+// memory.  Thread v walks the map rows a: the row shifted by v (W funnel shifts) is built once and and-popcounted
+// against the template rows i = u - a of the COUNT_UT shifts of the tile (one broadcast LDS.128 per row at G = 128).
 template <int W>  // words per row, G = 32*W
 __global__ void __launch_bounds__(256)
 xcorr_count_kernel(const uint8_t* __restrict__ t_valid, const uint8_t* __restrict__ m_valid, int R, int G,
-                   int U, float* __restrict__ cnt) {
-  __shared__ uint32_t qbits[32 * W][W];     // qbits[i][w] bit t = qv[i][32w+t]
-  __shared__ uint32_t mrev[32 * W][W + 2];  // mrev[a][w] bit t = mv[a][G-1-(32w+t)], zero padded words
-  const int u = blockIdx.y;
+                   int U, const float* __restrict__ flag, float* __restrict__ cnt) {
+  __shared__ __align__(16) uint32_t qbits[32 * W][W];  // qbits[i][w] bit t = qv[i][32w+t]
+  __shared__ uint32_t mrev[32 * W][W + 2];             // mrev[a][w] bit t = mv[a][G-1-(32w+t)], zero padded words
   const int br = blockIdx.z;  // b*R + r
   const int b = br / R;
+  if (flag[(size_t)b * R] != 0.f) return;  // all-valid map: xcorr_count_allvalid_kernel
+  const int u0 = blockIdx.y * COUNT_UT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* qv = t_valid + (size_t)br * G * G;
   const uint8_t* mv = m_valid + (size_t)b * G * G;
@@ -152,31 +174,93 @@ xcorr_count_kernel(const uint8_t* __restrict__ t_valid, const uint8_t* __restric
   if (v >= U) return;
   // sum_j qv[i][j] * mv[a][v-j] = popc(qrow_i & (mrev_a >> s)), s = G-1-v (left shift if negative)
   const int s = G - 1 - v;
-  int total = 0;
-  const int i_lo = max(0, u - (G - 1)), i_hi = min(G - 1, u);
-  for (int i = i_lo; i <= i_hi; ++i) {
-    const int a = u - i;
+  int total[COUNT_UT];
+#pragma unroll
+  for (int t = 0; t < COUNT_UT; ++t) total[t] = 0;
+  const int a_lo = max(0, u0 - (G - 1)), a_hi = min(G - 1, min(U - 1, u0 + COUNT_UT - 1));
+  for (int a = a_lo; a <= a_hi; ++a) {
+    uint32_t x[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-      uint32_t x;
       if (s >= 0) {
         const int ws = s >> 5, bs = s & 31;
         const int w0 = w + ws;
         const uint32_t lo = (w0 < W) ? mrev[a][w0] : 0u;
         const uint32_t hi = (w0 + 1 < W) ? mrev[a][w0 + 1] : 0u;
-        x = __funnelshift_r(lo, hi, bs);
+        x[w] = __funnelshift_r(lo, hi, bs);
       } else {
         const int t = -s;
         const int ws = t >> 5, bs = t & 31;
         const int w0 = w - ws;
         const uint32_t hi = (w0 >= 0) ? mrev[a][w0] : 0u;
         const uint32_t lo = (w0 - 1 >= 0) ? mrev[a][w0 - 1] : 0u;
-        x = __funnelshift_l(lo, hi, bs);
+        x[w] = __funnelshift_l(lo, hi, bs);
       }
-      total += __popc(qbits[i][w] & x);
+    }
+#pragma unroll
+    for (int t = 0; t < COUNT_UT; ++t) {
+      const int i = u0 + t - a;  // template row paired with map row a at shift u0 + t (warp-uniform)
+      if (i >= 0 && i < G) {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) c += __popc(qbits[i][w] & x[w]);
+        total[t] += c;
+      }
     }
   }
-  cnt[((size_t)br * U + u) * U + v] = (float)total;
+#pragma unroll
+  for (int t = 0; t < COUNT_UT; ++t)
+    if (u0 + t < U) cnt[((size_t)br * U + u0 + t) * U + v] = (float)total[t];
+}
+
+constexpr int COUNT_USEG = 32;  // consecutive u per block of the all-valid kernel
+
+// All-valid map: cnt[u,v] = sum of qv over rows [max(0,u-G+1), min(G-1,u)] x columns [max(0,v-G+1), min(G-1,v)].
+// Thread v holds the column-range mask; the row window slides by one per u (add the entering row, drop the leaving one).
+template <int W>
+__global__ void __launch_bounds__(256)
+xcorr_count_allvalid_kernel(const uint8_t* __restrict__ t_valid, int R, int G, int U, const float* __restrict__ flag,
+                            float* __restrict__ cnt) {
+  __shared__ __align__(16) uint32_t qbits[32 * W][W];
+  const int br = blockIdx.z;
+  const int b = br / R;
+  if (flag[(size_t)b * R] == 0.f) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint8_t* qv = t_valid + (size_t)br * G * G;
+  for (int task = warp; task < G * W; task += 8) {
+    const int row = task / W, w = task % W;
+    const uint32_t qb = __ballot_sync(0xffffffffu, qv[row * G + 32 * w + lane] != 0);
+    if (lane == 0) qbits[row][w] = qb;
+  }
+  __syncthreads();
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= U) return;
+  const int jlo = max(0, v - (G - 1)), jhi = min(G - 1, v);
+  uint32_t mask[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const int lo = max(jlo - 32 * w, 0), hi = min(jhi - 32 * w, 31);  // bits [lo, hi] of word w
+    mask[w] = hi < lo ? 0u : ((hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u));
+  }
+  auto row_count = [&](int i) {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) c += __popc(qbits[i][w] & mask[w]);
+    return c;
+  };
+  const int u0 = blockIdx.y * COUNT_USEG, u1 = min(U, u0 + COUNT_USEG);
+  int ilo = max(0, u0 - (G - 1)), ihi = min(G - 1, u0);
+  int total = 0;
+  for (int i = ilo; i <= ihi; ++i) total += row_count(i);
+  cnt[((size_t)br * U + u0) * U + v] = (float)total;
+  for (int u = u0 + 1; u < u1; ++u) {
+    const int nhi = min(G - 1, u), nlo = max(0, u - (G - 1));
+    if (nhi > ihi) total += row_count(nhi);
+    if (nlo > ilo) total -= row_count(ilo);
+    ihi = nhi;
+    ilo = nlo;
+    cnt[((size_t)br * U + u) * U + v] = (float)total;
+  }
 }
 
 __global__ void xcorr_den_kernel(const uint8_t* __restrict__ t_valid, int GG, float* __restrict__ den) {
@@ -240,19 +324,37 @@ int snapb200_xcorr_count(const uint8_t* t_valid, const uint8_t* m_valid, int B, 
   SNAP_REQUIRE(t_valid && m_valid && cnt && den, "null pointer");
   SNAP_REQUIRE(G % 32 == 0 && G >= 32 && G <= 256, "grid side must be a multiple of 32 in [32, 256] (got %d)", G);
   const int U = 2 * G - 1;
-  dim3 grid((U + 255) / 256, U, B * R);
   cudaStream_t s = (cudaStream_t)stream;
+  // den[b*R] doubles as the "map b is all valid" flag until xcorr_den_kernel overwrites it at the end
+  xcorr_allvalid_flag_kernel<<<B, 256, 0, s>>>(m_valid, G * G, R, den);
+  int rc = check_launch("xcorr_allvalid_flag_kernel");
+  if (rc) return rc;
+  const dim3 grid((U + 255) / 256, (U + COUNT_UT - 1) / COUNT_UT, B * R);
+  const dim3 grid_av((U + 255) / 256, (U + COUNT_USEG - 1) / COUNT_USEG, B * R);
+#define SNAP_COUNT_CASE(W_)                                                                          \
+  case W_:                                                                                           \
+    xcorr_count_kernel<W_><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, den, cnt);                \
+    rc = check_launch("xcorr_count_kernel");                                                         \
+    if (rc) return rc;                                                                               \
+    xcorr_count_allvalid_kernel<W_><<<grid_av, 256, 0, s>>>(t_valid, R, G, U, den, cnt);             \
+    break;
   switch (G / 32) {
-    case 1: xcorr_count_kernel<1><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    case 2: xcorr_count_kernel<2><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    case 3: xcorr_count_kernel<3><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    case 4: xcorr_count_kernel<4><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    case 5: xcorr_count_kernel<5><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    case 6: xcorr_count_kernel<6><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    case 7: xcorr_count_kernel<7><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
-    default: xcorr_count_kernel<8><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, cnt); break;
+    SNAP_COUNT_CASE(1)
+    SNAP_COUNT_CASE(2)
+    SNAP_COUNT_CASE(3)
+    SNAP_COUNT_CASE(4)
+    SNAP_COUNT_CASE(5)
+    SNAP_COUNT_CASE(6)
+    SNAP_COUNT_CASE(7)
+    default:
+      xcorr_count_kernel<8><<<grid, 256, 0, s>>>(t_valid, m_valid, R, G, U, den, cnt);
+      rc = check_launch("xcorr_count_kernel");
+      if (rc) return rc;
+      xcorr_count_allvalid_kernel<8><<<grid_av, 256, 0, s>>>(t_valid, R, G, U, den, cnt);
+      break;
   }
-  int rc = check_launch("xcorr_count_kernel");
+#undef SNAP_COUNT_CASE
+  rc = check_launch("xcorr_count_allvalid_kernel");
   if (rc) return rc;
   xcorr_den_kernel<<<B * R, 256, 0, s>>>(t_valid, G * G, den);
   return check_launch("xcorr_den_kernel");

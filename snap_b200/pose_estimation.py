@@ -117,6 +117,9 @@ def refinement_offsets() -> Tuple[np.ndarray, np.ndarray]:
     return rot, pos
 
 
+_REFINE_AXES: dict = {}
+
+
 def grid_refinement_batched(j_t_i_init: torch.Tensor, maps: SimilarityMaps, i_xy_points: torch.Tensor,
                             valid_j: Optional[torch.Tensor], grid: types.Grid2D,
                             mask_out_of_bounds: bool) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -124,8 +127,9 @@ def grid_refinement_batched(j_t_i_init: torch.Tensor, maps: SimilarityMaps, i_xy
     B = j_t_i_init.shape[0]
     dev = j_t_i_init.device
     rot, pos = refinement_offsets()
-    rot_rad = torch.from_numpy(np.deg2rad(rot).astype(F)).to(dev)
-    pos_t = torch.from_numpy(pos).to(dev)
+    if str(dev) not in _REFINE_AXES:    # uploaded once per device (no H2D copy inside a captured graph)
+        _REFINE_AXES[str(dev)] = (torch.from_numpy(np.deg2rad(rot).astype(F)).to(dev), torch.from_numpy(pos).to(dev))
+    rot_rad, pos_t = _REFINE_AXES[str(dev)]
     P = len(rot) * len(pos) * len(pos)
     poses = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
     ops.loc_refine_poses(j_t_i_init.contiguous(), rot_rad, pos_t, pos_t, poses)

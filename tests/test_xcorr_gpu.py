@@ -118,3 +118,29 @@ def test_voting_full_size_properties():
     # checksum of checksums: sum over all shifts of the un-normalised, un-masked correlation of rotation 0
     # equals (sum of template) . (sum of padded map window counts) -- verified on a coarse statistic:
     assert np.isfinite(a[fin]).all()
+
+
+@pytest.mark.parametrize("G", [32, 64, 128])
+def test_overlap_count_exact_generic_and_all_valid(G):
+    """cnt = true convolution of the un-flipped template validity with the zero-padded map validity, exact
+    integers; example 0 has a map with holes (popcount kernel), example 1 an all-valid map (rectangle-sum kernel)."""
+    import scipy.signal
+    from snap_b200 import ops
+    rng = np.random.default_rng(G)
+    B, R = 2, 4
+    tv = rng.random((B, R, G, G)) < 0.4
+    tv[0, 1] = False
+    tv[1, 2] = True
+    mv = rng.random((B, G, G)) < 0.8
+    mv[1] = True
+    U = 2 * G - 1
+    cnt = torch.full((B, R, U, U), -1.0, dtype=torch.float32, device="cuda")
+    den = torch.empty((B, R), dtype=torch.float32, device="cuda")
+    ops.xcorr_count(torch.from_numpy(tv.astype(np.uint8)).cuda(), torch.from_numpy(mv.astype(np.uint8)).cuda(), cnt, den)
+    got = cnt.cpu().numpy()
+    assert np.array_equal(den.cpu().numpy(), tv.sum((-1, -2)).astype(F))
+    for b in range(B):
+        for r in range(R):
+            ref = scipy.signal.convolve2d(tv[b, r].astype(np.int64), mv[b].astype(np.int64), mode="full")
+            assert ref.shape == (U, U)
+            assert np.array_equal(got[b, r], ref.astype(F)), (b, r, np.abs(got[b, r] - ref).max())
