@@ -16,6 +16,7 @@
 // (:157) before the fp32 soft-max, so bf16 storage is lossless; exp(T) and the per-point weight are applied on the fly.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host_common.h"
@@ -381,7 +382,7 @@ constexpr int LOC_SCORE_THREADS = 256;
 // (1, 0) on taps (last, zero padding) -- the same value as the reference's index-clamped taps (whose two weights sum
 // to 1 on the same edge texel), with no per-tap clamps in the inner loop.
 template <int PPT, bool MASK>
-__global__ void __launch_bounds__(LOC_SCORE_THREADS, 2)
+__global__ void __launch_bounds__(LOC_SCORE_THREADS, PPT <= 8 ? 3 : 2)
 loc_pose_scoring_kernel(const LocScoreArgs A) {
   constexpr int NT = LOC_SCORE_THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -452,28 +453,40 @@ loc_pose_scoring_kernel(const LocScoreArgs A) {
   const __nv_bfloat16* simb = A.sim + (size_t)b * A.N * HW;
   const int vpr = A.W >> 3;        // 16-byte vectors per map row
   const int vecs = A.H * vpr;      // ... per map
-  auto prefetch = [&](int k) {
+  // vector v = tid + i * NT of a map goes to padded element offset d0 + i * dstep (+ RS - W when the column wraps)
+  const int row0 = tid / vpr, cvec0 = tid - row0 * vpr;
+  const int drow = NT / vpr, dcvec = NT - drow * vpr;
+  auto prefetch = [&](int k, int buf) {
     const int n = __float_as_int(plist[k].x);
-    const uint4* src = reinterpret_cast<const uint4*>(simb + (size_t)n * HW);
-    unsigned short* dst = maps + (size_t)(k % A.nbuf) * MAPSZ;
+    const uint4* src = reinterpret_cast<const uint4*>(simb + (size_t)n * HW) + tid;
+    unsigned short* dst = maps + buf * MAPSZ;
+    int off = row0 * RS + cvec0 * 8, cvec = cvec0;
     for (int v = tid; v < vecs; v += NT) {
-      const int row = v / vpr, cvec = v - row * vpr;
-      cp_async16(dst + row * RS + cvec * 8, src + v);
+      cp_async16(dst + off, src);
+      src += NT;
+      off += drow * RS + dcvec * 8;
+      cvec += dcvec;
+      if (cvec >= vpr) {
+        cvec -= vpr;
+        off += RS - A.W;   // next row: +RS, back to column cvec - vpr: -W
+      }
     }
     cp_async_commit();
   };
   const float uH = (float)(A.H - 1), uW = (float)(A.W - 1);
   const unsigned magic_off = 0x4B000000u * (unsigned)RS + 0x4B000000u;  // bits of 2^23, folded out of the index (mod 2^32)
-  if (count > 0) prefetch(0);
+  if (count > 0) prefetch(0, 0);
+  const int other = A.nbuf - 1;  // double buffering: the other buffer is cur ^ 1; single buffer: always 0
+  int cur = 0;
   for (int k = 0; k < count; ++k) {
-    if (A.nbuf == 2 && k + 1 < count) {
-      prefetch(k + 1);
+    if (other && k + 1 < count) {
+      prefetch(k + 1, cur ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const unsigned short* mp = maps + (size_t)(k % A.nbuf) * MAPSZ;
+    const unsigned short* mp = maps + cur * MAPSZ;
     const float4 pt = plist[k];
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
@@ -510,11 +523,11 @@ loc_pose_scoring_kernel(const LocScoreArgs A) {
         acc[q] = fmaf(val, pt.w, acc[q]);
       }
     }
-    if (A.nbuf == 1) {
-      __syncthreads();  // everyone is done with the single buffer before it is overwritten
-      if (k + 1 < count) prefetch(k + 1);
+    __syncthreads();  // everyone is done with buffer `cur` before it is refilled
+    if (!other) {
+      if (k + 1 < count) prefetch(k + 1, 0);
     } else {
-      __syncthreads();  // buffer k % 2 is refilled by the prefetch of iteration k + 1
+      cur ^= 1;
     }
   }
 #pragma unroll
@@ -777,8 +790,12 @@ static int loc_score_plan(const SnapLocScoreParams* p, int* ppt, int* chunks, in
   SNAP_REQUIRE(p->W % 8 == 0, "the map width must be a multiple of 8 (got %d)", p->W);
   SNAP_REQUIRE(p->cell_size > 0.f, "cell_size must be positive");
   *ppt = p->P > 2048 ? 16 : 8;
+  if (const char* e = getenv("SNAPB200_LOC_PPT")) {  // tuning knob: poses per thread (8: 3 blocks per SM, 16: 2)
+    const int v = atoi(e);
+    if (v == 8 || v == 16) *ppt = v;
+  }
   *chunks = (p->P + LOC_SCORE_THREADS * *ppt - 1) / (LOC_SCORE_THREADS * *ppt);
-  int S = (4 * num_sms() + *chunks * p->B - 1) / (*chunks * p->B);  // two resident blocks per SM, two waves
+  int S = (2 * (*ppt <= 8 ? 3 : 2) * num_sms() + *chunks * p->B - 1) / (*chunks * p->B);  // resident blocks x two waves
   S = S < 1 ? 1 : S;
   if (S > (p->N + 15) / 16) S = (p->N + 15) / 16;  // at least ~16 points per split
   *splits = S;

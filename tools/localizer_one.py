@@ -17,6 +17,7 @@ ap.add_argument("--grid", type=int, default=128)
 ap.add_argument("--poses", type=int, default=10_000)
 ap.add_argument("--retries", type=int, default=8)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--time", action="store_true")
 args = ap.parse_args()
 G = args.grid
 dev = torch.device("cuda", 0)
@@ -52,3 +53,17 @@ for _ in range(args.reps):
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("refined", refined.cpu().numpy(), "volume", tuple(vol.shape))
+if args.time:   # GPU-bound timing of the two scoring calls alone (20 back-to-back launches each)
+    maps = pe.point_similarities(fq, vq, fm, 2.0, True, None)
+    poses = pe.sample_transforms_ransac_batched(gen, maps, q_xy_d, args.poses, args.retries, grid)
+    lattice = torch.randn((1, 68921, 3), device=dev) * torch.tensor([0.05, 2.0, 2.0], device=dev) + torch.tensor([0.3, 12.0, 12.0], device=dev)
+    for name, P in (("ransac", poses), ("refine", lattice.contiguous())):
+        for _ in range(3):
+            pe.pose_scoring_many_batched(P, maps, q_xy_d, None, grid, False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            pe.pose_scoring_many_batched(P, maps, q_xy_d, None, grid, False)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"pose_scoring[{name}, P={P.shape[1]}] {e0.elapsed_time(e1) / 20:.4f} ms  (SNAPB200_LOC_PPT={os.environ.get('SNAPB200_LOC_PPT', 'auto')})")
