@@ -25,3 +25,98 @@ def semantic_decoder(features: np.ndarray, valid: np.ndarray, p: Dict, rd: Calla
     x = resnet.resnet_stage(t(x), tt(p["layers_1"]), 1, rd).numpy()                 # ResNetStage (:159), final output (:160)
     logits = layers.mlp(x, p["layers_3"], rd=rdn)                                    # MLP(dim, num_classes) (:161)
     return np.where(valid[..., None], logits.astype(F), F(0))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# losses / metrics (snap/models/semantic_net.py:31-110, 254-343)
+# ------------------------------------------------------------------------------------------------------------------
+def balancing_weights(frequencies: Dict[str, float], classes, binary: bool = False, eps: float = 1e-3):
+    """:31-53."""
+    f = np.array([frequencies[c] for c in classes], dtype=np.float64)
+    if not binary:
+        f = f / f.sum()
+    f = f.clip(min=eps)
+    w = (1 / (f * len(classes))).astype(F)
+    if binary:
+        return w, (1 / ((1 - f).clip(min=eps) * len(classes))).astype(F)
+    return w
+
+
+def masked_mean(x: np.ndarray, mask: np.ndarray, axis):
+    """layers.py:30-33."""
+    div = np.sum(np.where(mask.any(axis, keepdims=True), mask, True), axis)
+    return (np.sum(x * mask, axis, dtype=F) / div).astype(F)
+
+
+def multiclass_crossentropy_metrics(logits: np.ndarray, labels: np.ndarray, valid: np.ndarray, weights=None):
+    """:56-84.  optax.softmax_cross_entropy_with_integer_labels = logsumexp(logits) - logits[label].
+    Returns (nll [B], accuracy [B], recall [B, N])."""
+    l = logits.astype(F)
+    m = l.max(-1, keepdims=True)
+    lse = np.log(np.exp(l - m).sum(-1, dtype=F)).astype(F)
+    nll = (lse - (np.take_along_axis(l, labels[..., None], -1)[..., 0] - m[..., 0])).astype(F)
+    if weights is not None:
+        nll = (nll * weights[labels]).astype(F)
+    nll = masked_mean(nll, valid, (1, 2))
+    mask = labels[..., None] == np.arange(l.shape[-1])
+    correct = np.argmax(l, axis=-1) == labels
+    acc = masked_mean(correct, valid, (1, 2))
+    recall = masked_mean(correct[..., None], valid[..., None] & mask, (1, 2))
+    return nll, acc, recall
+
+
+def binary_crossentropy_metrics(logits: np.ndarray, gt_mask: np.ndarray, valid: np.ndarray, w_pos=None, w_neg=None):
+    """:87-110.  optax.sigmoid_binary_cross_entropy = -y log_sigmoid(x) - (1 - y) log_sigmoid(-x).
+    Returns (nll [B], recall [B, N])."""
+    x = logits.astype(F)
+    ls = lambda t: -(np.maximum(-t, 0) + np.log1p(np.exp(-np.abs(t)))).astype(F)
+    y = gt_mask.astype(F)
+    nll = (-y * ls(x) - (1 - y) * ls(-x)).astype(F)
+    if w_pos is not None:
+        nll = (nll * np.where(gt_mask, w_pos, w_neg)).astype(F)
+    nll = masked_mean(nll.mean(-1, dtype=F), valid, (1, 2))
+    correct = ((1 / (1 + np.exp(-x))) > 0.5) == gt_mask
+    recall = masked_mean(correct, valid[..., None] & gt_mask, (1, 2))
+    return nll, recall
+
+
+def create_exclusive_labels(masks_all: np.ndarray, gt_classes, classes, add_void: bool = False):
+    """:254-276: argmax over the selected ground-truth masks ('line' absorbs the other lane-marking classes)."""
+    gi = {c: i for i, c in enumerate(gt_classes)}
+    masks = masks_all[..., [gi[c] for c in classes]].copy()
+    if "line" in classes:
+        ml = masks_all[..., gi["line"]].copy()
+        for c in ("stopline", "otherlanemarking"):
+            if c in gi and c not in classes:
+                ml |= masks_all[..., gi[c]]
+        masks[..., list(classes).index("line")] = ml
+    valid = masks.any(-1)
+    labels = np.argmax(masks, -1)
+    if add_void:
+        labels = np.where(valid, labels, len(classes))
+    return labels, valid
+
+
+def loss_metrics(logits_areas, logits_excl, logits_indep, bev_valid, masks_all, gt_classes, area_classes, excl_classes,
+                 indep_classes, area_frequencies=None, object_frequencies=None):
+    """:300-343 (without transfer_labels_from_pcm).  Returns (losses dict of [B], metrics dict)."""
+    la, va = create_exclusive_labels(masks_all, gt_classes, area_classes)
+    wa = balancing_weights(area_frequencies, area_classes) if area_frequencies else None
+    nll_a, acc_a, rec_a = multiclass_crossentropy_metrics(logits_areas, la, bev_valid & va, wa)
+    losses = {"nll_areas": nll_a}
+    metrics = {"accuracy": acc_a, "recall/average": rec_a.mean(-1), "recall_areas": rec_a}
+    total = nll_a
+    if logits_excl is not None:
+        le, _ = create_exclusive_labels(masks_all, gt_classes, excl_classes, add_void=True)
+        gi = {c: i for i, c in enumerate(gt_classes)}
+        mi = masks_all[..., [gi[c] for c in indep_classes]]
+        we = balancing_weights(object_frequencies, (*excl_classes, "void")) if object_frequencies else None
+        nll_e, acc_e, rec_e = multiclass_crossentropy_metrics(logits_excl, le, bev_valid, we)
+        wp, wn = balancing_weights(object_frequencies, indep_classes, binary=True) if object_frequencies else (None, None)
+        nll_i, rec_i = binary_crossentropy_metrics(logits_indep, mi, bev_valid, wp, wn)
+        total = ((total + (nll_e + nll_i) / 2) / 2).astype(F)
+        losses.update(nll_objects_exclusive=nll_e, nll_objects_indep=nll_i)
+        metrics.update({"accuracy/excl": acc_e, "recall/average/excl": rec_e.mean(-1), "recall_excl": rec_e,
+                        "recall/average/indep": rec_i.mean(-1), "recall_indep": rec_i})
+    losses["total"] = total
+    return losses, metrics

@@ -121,8 +121,16 @@ EXPORTED_SYMBOLS += [
     "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores", "snapb200_xcorr_scores_sw", "snapb200_xcorr_scores_rows", "snapb200_xcorr_scores_rows_workspace",
     "snapb200_loc_softmax_stats", "snapb200_loc_point_weights", "snapb200_loc_sample", "snapb200_loc_ransac_poses",
     "snapb200_loc_refine_poses", "snapb200_loc_pose_scoring_workspace", "snapb200_loc_pose_scoring",
-    "snapb200_argmax_rows", "snapb200_loc_nll",
+    "snapb200_argmax_rows", "snapb200_loc_nll", "snapb200_sem_loss",
 ]
+
+
+SEM_OUT = 40
+
+
+class SemLossParams(C.Structure):
+    _fields_ = [("B", C.c_int), ("cells", C.c_int), ("num_area", C.c_int), ("num_excl", C.c_int),
+                ("num_indep", C.c_int), ("ld", C.c_int)]
 
 
 class LocScoreParams(C.Structure):

@@ -558,3 +558,27 @@ def loc_nll(scores: torch.Tensor, samples: torch.Tensor, best: torch.Tensor, gt:
         C.c_void_p(_ptr(scores)), C.c_void_p(_ptr(samples)), C.c_void_p(_ptr(best)), C.c_void_p(_ptr(gt)), B, P1,
         int(remove is not None), C.c_float(dr_min), C.c_float(dt_min), C.c_void_p(_ptr(out)),
         C.c_void_p(_ptr(dr_samples)), C.c_void_p(_ptr(dt_samples)), _stream()))
+
+
+def sem_loss(logits: torch.Tensor, labels_area: torch.Tensor, valid_area: torch.Tensor,
+             labels_excl: Optional[torch.Tensor], masks_indep: Optional[torch.Tensor], valid: torch.Tensor,
+             num_area: int, num_excl: int, num_indep: int, weights: Optional[Sequence[Optional[torch.Tensor]]],
+             out: torch.Tensor) -> None:
+    """logits f32 [B, cells, ld]; labels i32 [B, cells]; masks u8; out f32 [B, SEM_OUT] (see include/snapb200.h)."""
+    _require(logits, torch.float32, "logits")
+    _require(labels_area, torch.int32, "labels_area")
+    _require(valid_area, torch.uint8, "valid_area")
+    _require(valid, torch.uint8, "valid")
+    _require(out, torch.float32, "out")
+    B, cells, ld = logits.shape
+    assert logits.is_contiguous() and out.shape == (B, _lib.SEM_OUT)
+    for t in (labels_area, valid_area, valid, labels_excl, masks_indep):
+        assert t is None or t.is_contiguous()
+    p = _lib.SemLossParams()
+    p.B, p.cells, p.num_area, p.num_excl, p.num_indep, p.ld = B, cells, num_area, num_excl, num_indep, ld
+    w = list(weights) if weights is not None else [None] * 4
+    _lib.check(_lib.lib().snapb200_sem_loss(
+        C.byref(p), C.c_void_p(_ptr(logits)), C.c_void_p(_ptr(labels_area)), C.c_void_p(_ptr(valid_area)),
+        C.c_void_p(_ptr(labels_excl)), C.c_void_p(_ptr(masks_indep)), C.c_void_p(_ptr(valid)),
+        C.c_void_p(_ptr(w[0])), C.c_void_p(_ptr(w[1])), C.c_void_p(_ptr(w[2])), C.c_void_p(_ptr(w[3])),
+        C.c_void_p(_ptr(out)), _stream()))

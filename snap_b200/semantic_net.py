@@ -114,3 +114,94 @@ class SemanticHead:
         return pred
 
     __call__ = apply
+
+
+def balancing_weights(frequencies: Dict[str, float], classes, binary: bool = False, eps: float = 1e-3):
+    """`semantic_net.py:31-53` (host side: a handful of class weights)."""
+    f = np.array([frequencies[c] for c in classes], dtype=np.float64)
+    if not binary:
+        f = f / f.sum()
+    f = f.clip(min=eps)
+    w = (1 / (f * len(classes))).astype(F)
+    if binary:
+        return w, (1 / ((1 - f).clip(min=eps) * len(classes))).astype(F)
+    return w
+
+
+def create_exclusive_labels(masks_all: np.ndarray, gt_classes, classes, add_void: bool = False):
+    """`SemanticNetModel._create_exclusive_labels` (`semantic_net.py:254-276`), host side (label preparation)."""
+    gi = {c: i for i, c in enumerate(gt_classes)}
+    masks = masks_all[..., [gi[c] for c in classes]].copy()
+    if "line" in classes:
+        ml = masks_all[..., gi["line"]].copy()
+        for c in ("stopline", "otherlanemarking"):
+            if c in gi and c not in classes:
+                ml |= masks_all[..., gi[c]]
+        masks[..., list(classes).index("line")] = ml
+    valid = masks.any(-1)
+    labels = np.argmax(masks, -1)
+    if add_void:
+        labels = np.where(valid, labels, len(classes))
+    return labels.astype(np.int32), valid
+
+
+class SemanticNetModel:
+    """Loss / metric side of `snap.models.semantic_net.SemanticNetModel` (`semantic_net.py:300-343`) for the logits of
+    `SemanticHead`; `gt_classes` = dataset_meta_data['semantic_classes_gt']."""
+
+    def __init__(self, config=None, gt_classes=()):
+        self.config = config if config is not None else configs.semantic_net()
+        self.gt_classes = tuple(gt_classes)
+
+    def loss_metrics_function(self, pred: Dict, data: Dict, model_params=None):
+        """pred: logits dict of SemanticHead + 'bev_features' (FeaturePlane); data['rasters']['gt_semantics'] bool
+        [B,G,G,N_gt] (NumPy).  Returns (losses, metrics) as dicts of per-example device tensors."""
+        c = self.config
+        if "map" in data:
+            data = data["map"]
+        masks = np.asarray(data["rasters"]["gt_semantics"]).astype(bool)
+        la, va = create_exclusive_labels(masks, self.gt_classes, c.area_classes)             # :301
+        logits_a = pred["logits_areas"]
+        dev = logits_a.device
+        B, G0, G1, Ka = logits_a.shape
+        cells = G0 * G1
+        bev_valid = pred["bev_features"].valid.reshape(B, cells).contiguous()
+        dv = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt).reshape(B, cells, *a.shape[3:]).contiguous()
+        has_obj = "logits_objects_exclusive" in pred
+        parts = [logits_a]
+        Ke = Ki = 0
+        le_d = mi_d = None
+        if has_obj:
+            le, _ = create_exclusive_labels(masks, self.gt_classes, c.object_classes_exclusive, add_void=True)   # :278-281
+            gi = {n: i for i, n in enumerate(self.gt_classes)}
+            mi = masks[..., [gi[n] for n in c.object_classes_independent]]
+            parts += [pred["logits_objects_exclusive"], pred["logits_objects_independent"]]
+            Ke, Ki = parts[1].shape[-1], parts[2].shape[-1]
+            le_d, mi_d = dv(le, torch.int32), dv(mi, torch.uint8)
+        logits = torch.cat(parts, -1).reshape(B, cells, Ka + Ke + Ki).contiguous()          # [areas | excl | indep]
+        valid_area = dv(va, torch.uint8) & bev_valid                                        # :302
+        weights = None
+        fa, fo = c.get("area_frequencies"), c.get("object_frequencies")
+        if fa or fo:
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(dev)
+            weights = [None] * 4
+            if fa:
+                weights[0] = t(balancing_weights(dict(fa), c.area_classes))
+            if fo and has_obj:
+                weights[1] = t(balancing_weights(dict(fo), (*c.object_classes_exclusive, "void")))
+                wp, wn = balancing_weights(dict(fo), c.object_classes_independent, binary=True)
+                weights[2], weights[3] = t(wp), t(wn)
+        out = torch.empty((B, ops._lib.SEM_OUT), dtype=torch.float32, device=dev)
+        ops.sem_loss(logits, dv(la, torch.int32), valid_area.contiguous(), le_d, mi_d, bev_valid, Ka, Ke, Ki, weights, out)
+        losses = {"nll_areas": out[:, 0], "total": out[:, 3]}
+        metrics = {"accuracy": out[:, 4], "recall/average": out[:, 6]}
+        for i, n in enumerate(c.area_classes):
+            metrics[f"recall/{n}"] = out[:, 16 + i]
+        if has_obj:
+            losses.update(nll_objects_exclusive=out[:, 1], nll_objects_indep=out[:, 2])
+            metrics.update({"accuracy/excl": out[:, 5], "recall/average/excl": out[:, 7], "recall/average/indep": out[:, 8]})
+            for i, n in enumerate((*c.object_classes_exclusive, "void")):
+                metrics[f"recall/{n}"] = out[:, 24 + i]
+            for i, n in enumerate(c.object_classes_independent):
+                metrics[f"recall/{n}"] = out[:, 32 + i]
+        return losses, {f"semantics/{k}": v for k, v in metrics.items()}

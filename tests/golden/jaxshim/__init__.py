@@ -108,6 +108,11 @@ class _Spec:
     def inner_rank(self):
         return len([t for t in self.spec.split() if t != "..."])
 
+    def __or__(self, other):   # `FloatArray['N'] | tuple[...]` in return annotations
+        return self
+
+    __ror__ = __or__
+
 
 class _ArrayType:
     def __getitem__(self, spec):
@@ -319,20 +324,36 @@ def install(reference_root: str) -> None:
     jax.random.choice = random_choice
     jnn.log_softmax = log_softmax
     jnn.relu = lambda x: np.maximum(x, 0)
+    jnn.sigmoid = lambda x: (1 / (1 + np.exp(-np.asarray(x)))).astype(np.asarray(x).dtype)
+    # optax (published definitions): logsumexp(logits) - logits[label]; -y log_sigmoid(x) - (1 - y) log_sigmoid(-x)
+    optax = types.ModuleType("optax")
+
+    def _sxent(logits, labels):
+        l = np.asarray(logits)
+        l = l - l.max(-1, keepdims=True)
+        return (np.log(np.exp(l).sum(-1)) - np.take_along_axis(l, np.asarray(labels)[..., None], -1)[..., 0]).astype(l.dtype)
+
+    def _bxent(logits, labels):
+        x = np.asarray(logits)
+        ls = lambda t: -(np.maximum(-t, 0) + np.log1p(np.exp(-np.abs(t))))
+        y = np.asarray(labels).astype(x.dtype)
+        return (-y * ls(x) - (1 - y) * ls(-x)).astype(x.dtype)
+    optax.softmax_cross_entropy_with_integer_labels, optax.sigmoid_binary_cross_entropy = _sxent, _bxent
     mods = {"jax": jax, "jax.numpy": jnp, "jax.scipy": jsp, "jax.scipy.ndimage": jnd, "jax.scipy.signal": jsg,
             "jax.lax": lax, "jax.nn": jnn, "jax.nn.initializers": jnn.initializers, "jax.random": jax.random}
     dca = types.ModuleType("dataclass_array"); dca.DataclassArray = DataclassArray
     dca.utils = types.SimpleNamespace(np_utils=types.SimpleNamespace(get_xnp=lambda x: jnp))
     mods["dataclass_array"] = dca
     et = types.ModuleType("etils"); at = types.ModuleType("etils.array_types")
-    at.BoolArray = at.FloatArray = at.IntArray = _ArrayType()
+    at.BoolArray = at.FloatArray = at.IntArray = at.Array = _ArrayType()
     et.array_types = at; et.epath = _Permissive("etils.epath")
     mods.update({"etils": et, "etils.array_types": at, "etils.epath": et.epath})
     chex = types.ModuleType("chex"); chex.dataclass = dataclasses.dataclass
     mods["chex"] = chex
     for name in ("flax", "flax.linen", "flax.training", "flax.training.checkpoints", "ml_collections",
-                 "ml_collections.config_dict", "tensorflow_datasets", "tensorflow", "scenic", "clu", "optax"):
+                 "ml_collections.config_dict", "tensorflow_datasets", "tensorflow", "scenic", "clu"):
         mods[name] = _Permissive(name)
+    mods["optax"] = optax
     mods["flax"].linen = mods["flax.linen"]
     mods["flax"].training = mods["flax.training"]
     mods["flax.training"].checkpoints = mods["flax.training.checkpoints"]

@@ -32,3 +32,48 @@ def test_semantic_head_vs_oracle():
     print(f"semantic head: vs bf16-oracle {e:.4f}, vs fp32-oracle {e32:.4f}, bf16-oracle vs fp32-oracle {eref:.4f}")
     # two residual units + 3 dense layers with identical rounding points: bf16 flips only
     assert e < 1e-2
+
+
+@pytest.mark.parametrize("balanced", [False, True])
+def test_semantic_losses_against_oracle(balanced):
+    """loss_metrics_function (semantic_net.py:300-343) on the GPU vs the oracle (pinned by tests/test_golden_semantics.py)."""
+    from oracle import semantic_net as osn
+    from snap_b200 import configs, semantic_net, types
+    rng = np.random.default_rng(12)
+    B, G = 3, 64
+    cfg = configs.semantic_net()
+    gt_classes = ("road", "crosswalk", "sidewalk", "terrain", "building", "fence", "pole", "tree", "traffic_sign",
+                  "traffic_light", "street_light", "line")
+    if balanced:
+        cfg.area_frequencies = tuple(zip(cfg.area_classes, (0.02, 0.2, 0.5, 0.1, 0.3)))
+        cfg.object_frequencies = tuple(zip((*cfg.object_classes_exclusive, "void", *cfg.object_classes_independent),
+                                           (0.01, 0.002, 0.05, 0.9, 0.0005, 0.0002, 0.003)))
+    masks = rng.random((B, G, G, len(gt_classes))) < 0.25
+    bev_valid = rng.random((B, G, G)) < 0.7
+    bev_valid[2] = False
+    la = (rng.standard_normal((B, G, G, 5)) * 2).astype(F)
+    le = (rng.standard_normal((B, G, G, 4)) * 2).astype(F)
+    li = (rng.standard_normal((B, G, G, 3)) * 2).astype(F)
+    t = lambda a: torch.from_numpy(a).cuda()
+    pred = {"logits_areas": t(la), "logits_objects_exclusive": t(le), "logits_objects_independent": t(li),
+            "bev_features": types.FeaturePlane(features=None, valid=t(bev_valid.astype(np.uint8)))}
+    model = semantic_net.SemanticNetModel(cfg, gt_classes)
+    losses, metrics = model.loss_metrics_function(pred, {"rasters": {"gt_semantics": masks}})
+    torch.cuda.synchronize()
+    ol, om = osn.loss_metrics(la, le, li, bev_valid, masks, gt_classes, cfg.area_classes, cfg.object_classes_exclusive,
+                              cfg.object_classes_independent, dict(cfg.area_frequencies) if balanced else None,
+                              dict(cfg.object_frequencies) if balanced else None)
+    for k in ("nll_areas", "nll_objects_exclusive", "nll_objects_indep", "total"):
+        got, ref = losses[k].cpu().numpy(), ol[k]
+        assert np.abs(got - ref).max() <= 1e-4 * (1 + np.abs(ref).max()), (k, got, ref)
+    assert losses["total"][2].item() == 0.0
+    chk = lambda key, ref: np.testing.assert_allclose(metrics[f"semantics/{key}"].cpu().numpy(), ref, atol=1e-6)
+    chk("accuracy", om["accuracy"]); chk("accuracy/excl", om["accuracy/excl"])
+    chk("recall/average", om["recall/average"]); chk("recall/average/excl", om["recall/average/excl"])
+    chk("recall/average/indep", om["recall/average/indep"])
+    for i, n in enumerate(cfg.area_classes):
+        chk(f"recall/{n}", om["recall_areas"][:, i])
+    for i, n in enumerate((*cfg.object_classes_exclusive, "void")):
+        chk(f"recall/{n}", om["recall_excl"][:, i])
+    for i, n in enumerate(cfg.object_classes_independent):
+        chk(f"recall/{n}", om["recall_indep"][:, i])
