@@ -126,7 +126,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="tiles per GPU per step (the reference trains / evaluates with 4 per device)")
+    ap.add_argument("--batch", type=int, default=8,
+                    help="tiles (scenes) per GPU per step; the reference trains with 4 per device (B = 32 on 8 GPUs), map building "
+                         "batches freely: measured 636 / 765 / 857 tiles/s at 2 / 4 / 8 on one B200 (per-kernel fixed costs amortise)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase CUDA-event timings to stderr")
