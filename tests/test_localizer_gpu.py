@@ -354,3 +354,45 @@ def test_localizer_end_to_end_full_size():
     ref = ope.pose_scoring_many(samples[sub, 0], samples[sub, 1:], sim_pts, loc.q_xy_p[:, 0], vq[0, :, 0].cpu().numpy().astype(bool),
                                 pred["map"]["bev_matching"].valid[0].cpu().numpy().astype(bool), ogrids.Grid2D((G, G), 0.2), False)
     assert np.abs(sc[sub] - ref).max() <= 1e-3 * np.abs(ref).max(), np.abs(sc[sub] - ref).max()
+
+
+def test_pose_scoring_edge_cases():
+    """a 256 x 256 map (one similarity map no longer fits twice in shared memory: single-buffer path), no valid point
+    at all (scores are exactly zero), a pose count that is not a multiple of the chunk size, batched query points."""
+    from oracle import grids, pose_estimation as ope
+    from snap_b200 import pose_estimation as pe, types
+    rng, fq, fm, vq, vm, i_xy = _problem(7, B=1, N=24, H=256, W=256)
+    maps = _maps(fq, fm, vq, 2.0)
+    P = 2049 + 17
+    ang = rng.uniform(-np.pi, np.pi, (1, P)).astype(F)
+    t = (rng.random((1, P, 2)) * 51.2).astype(F)
+    poses = np.concatenate([ang[..., None], t], -1).astype(F)
+    i_xy_b = np.ascontiguousarray(i_xy[None])                      # [B,N,2]: per-example query points
+    g256 = types.Grid2D((256, 256), 0.2)
+    sc = pe.pose_scoring_many_batched(_dev(poses), maps, _dev(i_xy_b), None, g256, False).cpu().numpy()
+    ref = ope.pose_scoring_many(ang[0], t[0], maps.sim_points()[0].cpu().numpy(), i_xy, vq[0], vm[0],
+                                grids.Grid2D((256, 256), 0.2), False)
+    assert np.abs(sc[0] - ref).max() <= 1e-3 * np.abs(ref).max()
+    # no valid point: num_valid clips to 1, every point is masked -> all scores 0 (pose_estimation.py:78-84)
+    vq0 = np.zeros_like(vq)
+    maps0 = _maps(fq * 0, fm, vq0, 2.0)
+    sc0 = pe.pose_scoring_many_batched(_dev(poses), maps0, _dev(i_xy), None, g256, False).cpu().numpy()
+    assert np.array_equal(sc0, np.zeros_like(sc0))
+    assert np.allclose(maps0.row_cdf[0].cpu().numpy(), np.arange(1, 25, dtype=F), rtol=1e-6)   # masses 1 / max(0, 1)
+    # sampling still works on the uniform maps of an all-invalid query (sim = 0 everywhere)
+    idx = pe.sample_correspondences(maps0, _dev(rng.random((1, 500, 2)).astype(F))).cpu().numpy()
+    assert idx.min() >= 0 and (idx[..., 0] < 24).all() and (idx[..., 1:] < 256).all()
+    assert len(np.unique(idx[0, :, 1])) > 100, "uniform soft-max: the draws spread over the map rows"
+
+
+def test_ransac_single_retry_and_degenerate_sets():
+    """num_retries = 1 skips the ratio test (:153-163); coincident correspondences give the identity rotation."""
+    from snap_b200 import pose_estimation as pe, types
+    i_xy = np.array([[0.0, 1.0], [2.0, 1.0], [0.5, 3.0]], F)
+    idx = np.array([[[0, 10, 10], [1, 10, 20],        # pose 0: (0,1)->(2.1,2.1), (2,1)->(2.1,4.1): +90 degrees
+                     [2, 5, 5], [2, 5, 5]]], np.int32)  # pose 1: the same correspondence twice
+    poses = pe.transforms_from_correspondences(_dev(idx), _dev(i_xy), 2, 1, types.Grid2D((32, 32), 0.2)).cpu().numpy()[0]
+    assert abs(poses[0, 0] - np.pi / 2) < 1e-5
+    # t = mu_j - R mu_i with R = +90 degrees: mu_j = (2.1, 3.1), mu_i = (1, 1) -> R mu_i = (-1, 1)
+    assert np.abs(poses[0, 1:] - np.array([3.1, 2.1], F)).max() < 1e-5
+    assert poses[1, 0] == 0.0 and np.abs(poses[1, 1:] - (np.array([1.1, 1.1], F) - i_xy[2])).max() < 1e-6
