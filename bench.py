@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[1]): one tile = 4 StreetView images 640x480 -> ResNet-50(BiT)+FPN encoder
 -> proj MLP -> camera->BEV lift (128x128x60 voxels) -> fusion MLP -> vertical max -> matching head, bf16.
-A "step" is one tile per GPU.  `value` = tiles/s with the images already resident in HBM; `e2e` = the same
+A "step" is one batch of `--batch` (default 8) tiles per GPU.  `value` = tiles/s with the images already resident in HBM; `e2e` = the same
 metric through the public `BEVMapper.apply` call with HOST (pinned) images, H2D + D2H inside the timed
 region.  N > 1: independent tiles per rank (weak scaling, no data-path collective); time = max over ranks.
 

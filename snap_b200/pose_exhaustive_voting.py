@@ -42,6 +42,9 @@ def template_rotation_params(num_rotations: int, grid: types.Grid2D) -> np.ndarr
     return np.stack([np.cos(a2[:nq]).astype(F), np.sin(a2[:nq]).astype(F), t2[:nq, 0], t2[:nq, 1]], -1).astype(F)
 
 
+_CENTERS: dict = {}
+
+
 def sample_query_templates(features: torch.Tensor, valid: torch.Tensor, num_rotations: int, grid: types.Grid2D,
                            conf_q: Optional[torch.Tensor] = None):
     """`:37-69`, batched: features bf16 [B,G,G,D], valid u8 [B,G,G] -> templates, t_valid u8 [B,R,G,G].
@@ -54,7 +57,10 @@ def sample_query_templates(features: torch.Tensor, valid: torch.Tensor, num_rota
     B, G, _, D = features.shape
     dev = features.device
     rot = template_rotation_params(num_rotations, grid)
-    centers = torch.from_numpy(grid.cell_centers(0)).to(dev)
+    key = (str(dev), grid.extent[0], float(grid.cell_size))
+    if key not in _CENTERS:      # uploaded once per device and grid (no H2D copy inside a captured graph)
+        _CENTERS[key] = torch.from_numpy(grid.cell_centers(0)).to(dev)
+    centers = _CENTERS[key]
     templates = torch.empty((B, G, G, ops.xcorr_padded_rotations(num_rotations), D), dtype=torch.bfloat16, device=dev)
     t_valid = torch.empty((B, num_rotations, G, G), dtype=torch.uint8, device=dev)
     ops.rot_templates(features.contiguous(), valid.contiguous(), conf_q, rot, centers, float(F(grid.cell_size)),
