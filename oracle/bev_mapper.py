@@ -102,7 +102,8 @@ def np_rd(rd_t: Callable) -> Callable:
 def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene: geometry.Transform3D,
                xyz: np.ndarray, fusion_params: Dict, feature_dim: int = 128, top_k: int = 4,
                depth_min_max=(1.0, 32.0), rd: Callable = _id, chunk: int = 1 << 16,
-               max_view_distance: Optional[float] = None, debug: Optional[Dict] = None):
+               max_view_distance: Optional[float] = None, debug: Optional[Dict] = None,
+               add_minmax: bool = False, use_variance: bool = True):
     """streetview_encoder.py:232-286 for one scene, chunked over voxels.
 
     f_proj_images [V,Hf,Wf,feature_dim+S] = proj_mlp output; camera ALREADY scaled by 1/stride (:224).
@@ -130,7 +131,7 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
         f_proj = rdn(f_proj)
         feats, scales = f_proj[..., :feature_dim], f_proj[..., feature_dim:]
         scores = rdn(sv.interpolate_depth_score(scales, depth, depth_min_max))
-        stats, valid = sv.pool_multiview_features(feats, vis, scores, False, True, rd=rdn)
+        stats, valid = sv.pool_multiview_features(feats, vis, scores, add_minmax, use_variance, rd=rdn)  # :268-274
         if max_view_distance is not None and min_dist is not None:  # :275-279
             valid = valid & (min_dist <= F(max_view_distance))
         if debug is not None:

@@ -109,7 +109,8 @@ class LiftParams(C.Structure):
     _fields_ = [("V", C.c_int), ("Hf", C.c_int), ("Wf", C.c_int), ("CF", C.c_int), ("D", C.c_int),
                 ("S", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
                 ("depth_min", C.c_float), ("depth_max", C.c_float), ("inv_log_range", C.c_float),
-                ("stats_ld", C.c_int), ("xy_paired", C.c_int)]
+                ("stats_ld", C.c_int), ("xy_paired", C.c_int),
+                ("no_variance", C.c_int), ("add_minmax", C.c_int)]
 
 
 EXPORTED_SYMBOLS += [

@@ -27,6 +27,7 @@ struct LiftParams {
   float depth_min, depth_max, inv_log_range;  // 1 / log(max/min)
   int stats_ld;                               // row pitch of the stats matrix (>= 2*D + 1, mult of 32)
   int xy_paired;                              // 0: xs[X], ys[Y] (separable grid); 1: xs[X*Y], ys[X*Y] per column
+  int no_variance, add_minmax;                // statistics blocks of the unfused gather/pool kernel (0, 0 = default)
 };
 
 struct Proj {

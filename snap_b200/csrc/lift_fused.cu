@@ -655,6 +655,7 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
                "null pointer");
   SNAP_REQUIRE(q->V >= 1 && q->V <= FL_MAXV, "fused lift handles 1..%d views (got %d)", FL_MAXV, q->V);
   SNAP_REQUIRE(q->D == 128 && q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
+  SNAP_REQUIRE(!q->no_variance && !q->add_minmax, "the fused lift implements the default statistics only");
   SNAP_REQUIRE(q->Z >= 1 && q->Z <= 64, "Z must be <= 64 (got %d)", q->Z);
   SNAP_REQUIRE((long long)q->V * q->Hf * q->Wf * q->CF < (1LL << 31), "feature maps too large for 32-bit tap offsets");
   SNAP_REQUIRE((long long)q->X * q->Y <= 65536, "too many BEV columns (X*Y <= 65536: 16-bit column ids in the z-max scan)");

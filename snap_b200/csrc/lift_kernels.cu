@@ -144,17 +144,40 @@ lift_gather_pool_kernel(const __grid_constant__ LiftParams P, const LiftView* __
     } else {
       smax = 0.f;
     }
-    // --- write the statistics row: [mean(D) | var(D) | score_max | 0 ...] -----------------------
+    // --- write the statistics row: [mean(D) | var(D)? | max(D) min(D)? | score_max | 0 ...] -------
+    // (pool_multiview_features :165-177: fusion_use_variance / fusion_add_minmax select the blocks)
     __nv_bfloat16* row = stats + n * P.stats_ld;
-    const float* src = half ? var : mean;
-    *reinterpret_cast<uint4*>(row + half * P.D + c8 * 8) =
-        make_uint4(pack_bf16(src[0], src[1]), pack_bf16(src[2], src[3]), pack_bf16(src[4], src[5]),
-                   pack_bf16(src[6], src[7]));
-    const int tail_vecs = (P.stats_ld - 2 * P.D) / 8;
-    if (lane < tail_vecs) {
+    const int use_var = P.no_variance ? 0 : 1;
+    const int off_minmax = P.D * (1 + use_var), off_score = off_minmax + (P.add_minmax ? 2 * P.D : 0);
+    if (half == 0 || use_var) {
+      const float* src = half ? var : mean;
+      *reinterpret_cast<uint4*>(row + half * P.D + c8 * 8) =
+          make_uint4(pack_bf16(src[0], src[1]), pack_bf16(src[2], src[3]), pack_bf16(src[4], src[5]),
+                     pack_bf16(src[6], src[7]));
+    }
+    if (P.add_minmax) {  // half 0: max over the visible views, half 1: min; zero when no view sees the voxel
+      float ext[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ext[j] = half ? INFINITY : -INFINITY;
+#pragma unroll
+      for (int v = 0; v < LIFT_MAX_VIEWS; ++v)
+        if (vis_mask & (1u << v)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ext[j] = half ? fminf(ext[j], fv[v][j]) : fmaxf(ext[j], fv[v][j]);
+        }
+      if (vis_mask == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ext[j] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(row + off_minmax + half * P.D + c8 * 8) =
+          make_uint4(pack_bf16(ext[0], ext[1]), pack_bf16(ext[2], ext[3]), pack_bf16(ext[4], ext[5]),
+                     pack_bf16(ext[6], ext[7]));
+    }
+    const int tail_vecs = (P.stats_ld - off_score) / 8;
+    for (int tv = lane; tv < tail_vecs; tv += 32) {
       uint4 z = make_uint4(0, 0, 0, 0);
-      if (lane == 0) z.x = pack_bf16(smax, 0.f);
-      *reinterpret_cast<uint4*>(row + 2 * P.D + lane * 8) = z;
+      if (tv == 0) z.x = pack_bf16(smax, 0.f);
+      *reinterpret_cast<uint4*>(row + off_score + tv * 8) = z;
     }
     if (lane == 0) valid[n] = vis_mask != 0 ? 1 : 0;
   }
@@ -259,8 +282,11 @@ int snapb200_lift_gather_pool(const SnapLiftParams* q, const SnapLiftView* views
   SNAP_REQUIRE(q->V >= 1 && q->V <= LIFT_MAX_VIEWS, "1 <= V <= %d required (got %d)", LIFT_MAX_VIEWS, q->V);
   SNAP_REQUIRE(q->D == 128, "feature_dim must be 128 (got %d)", q->D);
   SNAP_REQUIRE(q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
-  SNAP_REQUIRE(q->stats_ld % 32 == 0 && q->stats_ld >= 2 * q->D + 8 && q->stats_ld <= 2 * q->D + 256,
-               "bad stats_ld %d", q->stats_ld);
+  {
+    const int width = q->D * (1 + (q->no_variance ? 0 : 1) + (q->add_minmax ? 2 : 0));
+    SNAP_REQUIRE(q->stats_ld % 32 == 0 && q->stats_ld >= width + 8 && q->stats_ld <= width + 256,
+                 "stats_ld must be a multiple of 32 in [%d, %d] (got %d)", width + 8, width + 256, q->stats_ld);
+  }
   SNAP_REQUIRE((dbg_vis == nullptr) == (dbg_taps == nullptr), "debug outputs come as a pair");
   static_assert(sizeof(SnapLiftView) == sizeof(LiftView), "SnapLiftView layout");
   static_assert(sizeof(SnapLiftParams) == sizeof(LiftParams), "SnapLiftParams layout");

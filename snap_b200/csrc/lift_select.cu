@@ -259,6 +259,7 @@ extern "C" int snapb200_lift_select_pool(const SnapLiftParams* q, int top_k, flo
                "view selection needs top_k < V <= %d (got V=%d, top_k=%d); V <= top_k is the all-views path",
                SELECT_MAX_VIEWS, q->V, top_k);
   SNAP_REQUIRE(q->D == 128, "feature_dim must be 128 (got %d)", q->D);
+  SNAP_REQUIRE(!q->no_variance && !q->add_minmax, "the view-selection kernel implements the default statistics only");
   SNAP_REQUIRE(q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
   SNAP_REQUIRE(q->stats_ld % 32 == 0 && q->stats_ld >= 2 * q->D + 8 && q->stats_ld <= 2 * q->D + 256,
                "bad stats_ld %d", q->stats_ld);

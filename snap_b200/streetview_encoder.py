@@ -40,6 +40,8 @@ def fill_lift_params(cfg, V: int, hf: int, wf: int, X: int, Y: int, Z: int, stat
     p.inv_log_range = float(F(1.0) / np.log(F(dmax / dmin)).astype(F))
     p.stats_ld = stats_ld
     p.xy_paired = int(xy_paired)
+    p.no_variance = int(not cfg.get("fusion_use_variance", True))
+    p.add_minmax = int(bool(cfg.get("fusion_add_minmax", False)))
     return p
 
 
@@ -78,10 +80,14 @@ class StreetViewEncoder:
     def __init__(self, config=None, dtype=torch.bfloat16):
         self.config = config if config is not None else configs.streetview_encoder()
         c = self.config
-        if not c.do_weighted_fusion or c.fusion_add_minmax or not c.fusion_use_variance or c.depth_mlp is not None:
-            raise NotImplementedError("only the default weighted fusion (mean+var+score_max) is built")
+        if not c.do_weighted_fusion or c.depth_mlp is not None:
+            raise NotImplementedError("only the weighted fusion branch (streetview_encoder.py:254-261) is built")
         if tuple(c.fusion.layers) != (256, 128) or c.feature_dim != 128:
-            raise NotImplementedError("fusion MLP must be 257->256->128")
+            raise NotImplementedError("fusion MLP must be stats->256->128")
+        # statistics = [mean | var? | max min? | score_max] (pool_multiview_features :165-177)
+        self.stats_dim = c.feature_dim * (1 + int(c.fusion_use_variance) + 2 * int(c.fusion_add_minmax)) + 1
+        self.stats_ld = (self.stats_dim + 31) // 32 * 32
+        self.default_stats = bool(c.fusion_use_variance) and not c.fusion_add_minmax
         self.dtype = dtype
         self.image_encoder = image_encoder.ImageEncoder(c.image_encoder, dtype)
         self._cache: Dict = {}
@@ -98,7 +104,7 @@ class StreetViewEncoder:
                      proj_b=f32(params["proj_mlp"]["Dense_0"]["bias"]),
                      fus0_b=f32(params["fusion_mlp"]["Dense_0"]["bias"]),
                      fus1_b=f32(params["fusion_mlp"]["Dense_1"]["bias"]),
-                     w256=f32(params["fusion_mlp"]["Dense_0"]["kernel"][256]))
+                     w256=f32(params["fusion_mlp"]["Dense_0"]["kernel"][self.stats_dim - 1]))
             bank.finalize()
             self._cache[key] = w
         return self._cache[key]
@@ -111,7 +117,7 @@ class StreetViewEncoder:
             pin = lambda *s, dt: torch.zeros(s, dtype=dt).pin_memory()
             rows_img = max(V * hf * wf, 128)
             self._cache[key] = dict(
-                crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, 288), hid=z(N, 256),
+                crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, self.stats_ld), hid=z(N, 256),
                 volume=None, valid=None,   # [B,N,128] / [B,N]: allocated on first unfused call
                 plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 16, dt=torch.int32),
                 scratch=z(ops.lift_fused_scratch_bytes(), dt=torch.uint8),
@@ -244,7 +250,9 @@ class StreetViewEncoder:
         bank.run()
         Bm = bank.b_mats
         N = X * Y * Z
-        lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, 288, paired)
+        lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, self.stats_ld, paired)
+        if (fused or select) and not self.default_stats:
+            raise NotImplementedError("fusion_add_minmax / fusion_use_variance=False run on the unfused all-views lift only")
         dbg = {}
         if not fused and buf["volume"] is None:
             buf["volume"] = torch.zeros((B, N, 128), dtype=torch.bfloat16, device=dev)
@@ -276,7 +284,7 @@ class StreetViewEncoder:
                 ops.lift_gather_pool(lp, stg["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b],
                                      buf["stats"], buf["valid"][b], dv, dt)
             # fusion MLP 257 -> 256 -> 128 (`:281`), zero where invalid (`:282`)
-            ops.gemm(buf["stats"], Bm[wts["fus0"]], buf["hid"], m_rows=N, seg_k=288, bias=wts["fus0_b"], relu=True)
+            ops.gemm(buf["stats"], Bm[wts["fus0"]], buf["hid"], m_rows=N, seg_k=self.stats_ld, bias=wts["fus0_b"], relu=True)
             ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],
                      row_mask=buf["valid"][b])
         pred = {"image_feature_pyramid": pyr,

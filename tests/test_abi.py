@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     from snap_b200 import _lib
     # sizes asserted in csrc/lift_kernels.cu (static_assert) and mirrored here
     assert C.sizeof(_lib.LiftView) == 92
-    assert C.sizeof(_lib.LiftParams) == 56
+    assert C.sizeof(_lib.LiftParams) == 64
     assert C.sizeof(_lib.WeightDesc) == 48
     assert C.sizeof(_lib.GemmParams) % 8 == 0
 

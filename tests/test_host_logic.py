@@ -102,9 +102,14 @@ def _leaves(t):
 def test_unsupported_configs_fail_loudly():
     import pytest
     c = configs.bev_mapper()
-    c.streetview_encoder.fusion_add_minmax = True
+    c.streetview_encoder.do_weighted_fusion = False      # the un-weighted branch has no proj MLP (:207-215): not built
     with pytest.raises(NotImplementedError):
         bev_mapper.BEVMapper(c, types.Grid2D((8, 8), 0.2))
+    c3 = configs.bev_mapper()
+    c3.streetview_encoder.fusion_add_minmax = True       # built on the unfused lift: [mean | var | max | min | score_max]
+    m = bev_mapper.BEVMapper(c3, types.Grid2D((8, 8), 0.2))
+    assert m.streetview_encoder.stats_dim == 513 and m.streetview_encoder.stats_ld == 544
+    assert not m.streetview_encoder.default_stats
     c2 = configs.image_encoder()
     c2.encoder_name = "vit"
     with pytest.raises(ValueError):

@@ -341,3 +341,84 @@ def test_view_selection_stats_and_volume_vs_oracle(max_dist):
     assert e_stats < 5e-3 and e_vol < 5e-3
     assert not vol.float().cpu().numpy()[~v].any(), "invalid voxels must be zero (streetview_encoder.py:282)"
     assert not stats.float().cpu().numpy()[~any_vis].any(), "statistics of unseen voxels must be zero (:177)"
+
+
+@pytest.mark.parametrize("add_minmax,use_variance", [(True, True), (True, False), (False, False)])
+def test_lift_nondefault_statistics_vs_oracle(add_minmax, use_variance):
+    """fusion_add_minmax / fusion_use_variance (pool_multiview_features :165-177): statistics rows
+    [mean | var? | max min? | score_max] of the unfused lift and the fusion MLP on them, vs the oracle."""
+    from oracle import bev_mapper as obm, grids as ogrids
+    from snap_b200 import configs, ops, params, streetview_encoder as sve
+    from snap_b200.image_encoder import _WeightBank
+    G, V, hw_img = 24, 3, (64, 96)
+    data, grid, mapper, xs, ys, zs = _lift_inputs(G, hw_img, V, 5)
+    hf, wf = 16, 24
+    rng = np.random.default_rng(13)
+    cfg = configs.streetview_encoder()
+    cfg.fusion_add_minmax, cfg.fusion_use_variance = add_minmax, use_variance
+    enc = sve.StreetViewEncoder(cfg)
+    width, ld = enc.stats_dim, enc.stats_ld
+    assert width == 128 * (1 + int(use_variance) + 2 * int(add_minmax)) + 1
+    Z = zs.shape[1]
+    N = G * G * Z
+    fimg_np = bf16_np(rng.standard_normal((V, hf, wf, 160)))
+    fp = params.round_to_bf16(params.perturb_affine(rng, params.init_mlp(rng, width, (256, 128))))
+    dev = "cuda"
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, ld)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    fimg = _t(fimg_np).to(torch.bfloat16).to(dev)
+    stats = torch.full((N, ld), 7.0, dtype=torch.bfloat16, device=dev)       # garbage: every column must be overwritten
+    valid = torch.zeros(N, dtype=torch.uint8, device=dev)
+    ops.lift_gather_pool(lp, views, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), stats, valid)
+    bank = _WeightBank(torch.device(dev))
+    w0 = bank.add(fp["Dense_0"]["kernel"], False, 32)
+    w1 = bank.add(fp["Dense_1"]["kernel"], False)
+    bank.finalize(); bank.run()
+    hid = torch.zeros((N, 256), dtype=torch.bfloat16, device=dev)
+    vol = torch.zeros((N, 128), dtype=torch.bfloat16, device=dev)
+    ops.gemm(stats, bank.b_mats[w0], hid, m_rows=N, seg_k=ld, bias=_t(fp["Dense_0"]["bias"]).to(dev), relu=True)
+    ops.gemm(hid, bank.b_mats[w1], vol, m_rows=N, bias=_t(fp["Dense_1"]["bias"]).to(dev), row_mask=valid)
+    torch.cuda.synchronize()
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    dbg = {}
+    f_grid, ovalid, _, _ = obm.lift_scene(fimg_np, ocam, oT, xyz, fp, rd=rd_bf16, debug=dbg, add_minmax=add_minmax,
+                                          use_variance=use_variance)
+    ostats = np.concatenate(dbg["stats"])
+    assert ostats.shape == (N, width)
+    v = valid.cpu().numpy().astype(bool)
+    assert np.array_equal(v, ovalid.reshape(-1))
+    got = stats.float().cpu().numpy()
+    assert not got[:, width:].any(), "padding columns must be zero"
+    assert not got[~v].any(), "rows of unseen voxels must be zero (:177)"
+    if add_minmax:   # max / min of bf16 values are exact
+        o = 128 * (1 + int(use_variance))
+        assert (np.abs(got[v, o:o + 256] - bf16_np(ostats[v, o:o + 256])) > 0).mean() < 2e-3
+    e_stats = rel_l2(got[v, :width], bf16_np(ostats[v]))
+    e_vol = rel_l2(vol.float().cpu().numpy()[v], f_grid.reshape(-1, 128)[v])
+    print(f"add_minmax={add_minmax} use_variance={use_variance}: rel_l2 stats {e_stats:.5f}, volume {e_vol:.5f}")
+    assert e_stats < 5e-3 and e_vol < 5e-3
+
+
+def test_bev_mapper_runs_with_minmax_statistics():
+    """BEVMapper with fusion_add_minmax=True takes the unfused lift (513-wide statistics) end to end; the valid plane is
+    the one of the default configuration (visibility does not depend on the statistics)."""
+    from snap_b200 import bev_mapper, configs, params, synthetic, types
+    G, hw = 32, (96, 128)
+    rng = np.random.default_rng(14)
+    data = synthetic.make_tile(81, 2, hw, G)
+    grid = types.Grid2D((G, G), 0.2)
+    cfg0 = configs.bev_mapper(("streetview",))
+    cfg1 = configs.bev_mapper(("streetview",))
+    cfg1.streetview_encoder.fusion_add_minmax = True
+    p1 = params.round_to_bf16(params.init_bev_mapper(rng, cfg1))
+    assert p1["streetview_encoder"]["fusion_mlp"]["Dense_0"]["kernel"].shape == (513, 256)
+    out1 = bev_mapper.BEVMapper(cfg1, grid).apply({"params": p1}, dict(data))
+    assert "feature_volume" in out1["streetview"], "non-default statistics run on the unfused path"
+    v1 = out1["bev_matching"].valid.cpu().numpy().astype(bool)
+    f1 = out1["bev_matching"].features.float().cpu().numpy()
+    p0 = params.round_to_bf16(params.init_bev_mapper(np.random.default_rng(14), cfg0))
+    v0 = bev_mapper.BEVMapper(cfg0, grid).apply({"params": p0}, dict(data))["bev_matching"].valid.cpu().numpy().astype(bool)
+    assert np.array_equal(v0, v1) and 0.02 < v1.mean() < 0.98
+    assert np.isfinite(f1).all() and np.abs(np.linalg.norm(f1[v1], axis=-1) - 1).max() < 2e-2 and not f1[~v1].any()
