@@ -90,4 +90,33 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_xcorr_scores, XcorrScoresImpl,
 // AnyBuffer pointers + dims -> the C ABI call, PlatformStream -> `stream`.
 #else
 // xla/ffi/api/ffi.h not available: nothing to compile (see the header comment).
+
+// ---- loc_pose_scoring (pose_estimation.py:65-85,206-209): (sim bf16[B,N,H,W], point_scale f32[B,N], i_xy f32[N,2],
+//      valid_j u8[B,H,W], poses f32[B,P,3], workspace u8[ws]) -> scores f32[B,P].  The workspace is an extra operand so
+//      that XLA owns the memory (size = snapb200_loc_pose_scoring_workspace(), computed at trace time on the host).
+static ffi::Error LocPoseScoringImpl(cudaStream_t stream, ffi::AnyBuffer sim, ffi::AnyBuffer point_scale,
+                                     ffi::AnyBuffer i_xy, ffi::AnyBuffer valid_j, ffi::AnyBuffer poses,
+                                     ffi::AnyBuffer workspace, ffi::Result<ffi::AnyBuffer> scores, float cell_size,
+                                     int32_t mask_out_of_bounds) {
+  auto d = sim.dimensions();
+  SnapLocScoreParams p{};
+  p.B = (int)d[0]; p.N = (int)d[1]; p.H = (int)d[2]; p.W = (int)d[3];
+  p.P = (int)poses.dimensions()[1];
+  p.cell_size = cell_size;
+  p.mask_out_of_bounds = mask_out_of_bounds;
+  p.i_xy_batched = i_xy.dimensions().size() == 3;
+  return to_error(snapb200_loc_pose_scoring(
+      &p, sim.untyped_data(), static_cast<const float*>(point_scale.untyped_data()),
+      static_cast<const float*>(i_xy.untyped_data()), static_cast<const uint8_t*>(valid_j.untyped_data()),
+      static_cast<const float*>(poses.untyped_data()), workspace.untyped_data(), workspace.size_bytes(),
+      static_cast<float*>(scores->untyped_data()), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_loc_pose_scoring, LocPoseScoringImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<float>("cell_size").Attr<int32_t>("mask_out_of_bounds"));
+
 #endif
