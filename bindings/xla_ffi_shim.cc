@@ -85,12 +85,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_xcorr_scores, XcorrScoresImpl,
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()
                                   .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::AnyBuffer>().Ret<ffi::AnyBuffer>().Attr<float>("thr"));
-// The remaining entry points (gn_stats/gn_apply, root_im2col, maxpool, upsample2x, crop_relu, vertical_max,
-// match_head, fuse_max, rot_templates, xcorr_pad_map, xcorr_count, std_weights_batched) bind the same way:
-// AnyBuffer pointers + dims -> the C ABI call, PlatformStream -> `stream`.
-#else
-// xla/ffi/api/ffi.h not available: nothing to compile (see the header comment).
-
 // ---- loc_pose_scoring (pose_estimation.py:65-85,206-209): (sim bf16[B,N,H,W], point_scale f32[B,N], i_xy f32[N,2],
 //      valid_j u8[B,H,W], poses f32[B,P,3], workspace u8[ws]) -> scores f32[B,P].  The workspace is an extra operand so
 //      that XLA owns the memory (size = snapb200_loc_pose_scoring_workspace(), computed at trace time on the host).
@@ -118,5 +112,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_loc_pose_scoring, LocPoseScoringImpl,
                                   .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
                                   .Ret<ffi::AnyBuffer>()
                                   .Attr<float>("cell_size").Attr<int32_t>("mask_out_of_bounds"));
+
+
+// The remaining entry points (gn_stats/gn_apply, root_im2col, maxpool, upsample2x, crop_relu, vertical_max,
+// match_head, fuse_max, rot_templates, xcorr_pad_map, xcorr_count, std_weights_batched) bind the same way:
+// AnyBuffer pointers + dims -> the C ABI call, PlatformStream -> `stream`.
+#else
+// xla/ffi/api/ffi.h not available: nothing to compile (see the header comment).
 
 #endif
