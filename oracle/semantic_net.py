@@ -120,3 +120,51 @@ def loss_metrics(logits_areas, logits_excl, logits_indep, bev_valid, masks_all, 
                         "recall/average/indep": rec_i.mean(-1), "recall_indep": rec_i})
     losses["total"] = total
     return losses, metrics
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training loss of the head as a differentiable torch function (gradient oracle = torch autograd of this restatement)
+# ------------------------------------------------------------------------------------------------------------------
+def total_loss_torch(logits: "torch.Tensor", la, va, le, mi, bev_valid, num_area: int, num_excl: int,
+                     w_area=None, w_excl=None, w_pos=None, w_neg=None):
+    """mean over the batch (trainer.py:221) of `total` (:300-343) for logits f32 [B,H,W,K] (already masked, :186);
+    labels / masks as NumPy arrays.  Same arithmetic as `loss_metrics` above (checked in tests/test_golden_semantics.py)."""
+    t = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+    B = logits.shape[0]
+    cells = logits.shape[1] * logits.shape[2]
+
+    def mmean(x, mask):  # layers.masked_mean over (1, 2)
+        m = t(mask)
+        cnt = m.sum((1, 2))
+        return (x * m).sum((1, 2)) / torch.where(cnt > 0, cnt, torch.full_like(cnt, float(cells)))
+
+    def xent(l, labels, w):
+        nll = torch.logsumexp(l, -1) - torch.gather(l, -1, t(labels, torch.int64)[..., None])[..., 0]
+        return nll * t(w)[t(labels, torch.int64)] if w is not None else nll
+    la_l, rest = logits[..., :num_area], logits[..., num_area:]
+    total = mmean(xent(la_l, la, w_area), bev_valid & va)
+    if rest.shape[-1] > 0:
+        le_l, li_l = rest[..., :num_excl], rest[..., num_excl:]
+        nll_e = mmean(xent(le_l, le, w_excl), bev_valid)
+        y = t(mi)
+        ls = torch.nn.functional.logsigmoid
+        bce = -y * ls(li_l) - (1 - y) * ls(-li_l)
+        if w_pos is not None:
+            bce = bce * torch.where(y > 0, t(w_pos), t(w_neg))
+        nll_i = mmean(bce.mean(-1), bev_valid)
+        total = (total + (nll_e + nll_i) / 2) / 2
+    return total.mean(), total
+
+
+def mlp_head_forward_torch(features: "torch.Tensor", valid: np.ndarray, params: Dict, rd: Callable = _id):
+    """semantic_net.py:147-152,185-186 in torch (differentiable): layers.MLP on the BEV features, f32 logits, zero where
+    invalid.  params: {'Dense_i': {'kernel', 'bias'}} of torch tensors (requires_grad for the gradient oracle)."""
+    x = features
+    n = len(params)
+    for i in range(n):
+        if i > 0:
+            x = torch.relu(x)
+        x = rd(x @ params[f"Dense_{i}"]["kernel"])
+        x = rd(x + params[f"Dense_{i}"]["bias"])
+    v = torch.from_numpy(np.ascontiguousarray(valid))[..., None]
+    return torch.where(v, x.float(), torch.zeros((), dtype=torch.float32))

@@ -582,3 +582,71 @@ def sem_loss(logits: torch.Tensor, labels_area: torch.Tensor, valid_area: torch.
         C.c_void_p(_ptr(labels_excl)), C.c_void_p(_ptr(masks_indep)), C.c_void_p(_ptr(valid)),
         C.c_void_p(_ptr(w[0])), C.c_void_p(_ptr(w[1])), C.c_void_p(_ptr(w[2])), C.c_void_p(_ptr(w[3])),
         C.c_void_p(_ptr(out)), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# head-only training step (semantic fine-tuning, default 'mlp' decoder)
+# --------------------------------------------------------------------------------------------
+def sem_loss_grad(logits: torch.Tensor, labels_area: torch.Tensor, valid_area: torch.Tensor,
+                  labels_excl: Optional[torch.Tensor], masks_indep: Optional[torch.Tensor], valid: torch.Tensor,
+                  num_area: int, num_excl: int, num_indep: int, weights: Optional[Sequence[Optional[torch.Tensor]]],
+                  counts: torch.Tensor, dlogits: torch.Tensor) -> None:
+    """d mean_b(total_b) / d logits: logits f32 [B, cells, ld] -> dlogits bf16 [B*cells, ld_out]; counts f32 [B,2] scratch."""
+    _require(logits, torch.float32, "logits")
+    _require(dlogits, torch.bfloat16, "dlogits")
+    _require(counts, torch.float32, "counts")
+    B, cells, ld = logits.shape
+    assert logits.is_contiguous() and dlogits.is_contiguous() and dlogits.shape[0] >= B * cells and counts.shape == (B, 2)
+    p = _lib.SemLossParams()
+    p.B, p.cells, p.num_area, p.num_excl, p.num_indep, p.ld = B, cells, num_area, num_excl, num_indep, ld
+    w = list(weights) if weights is not None else [None] * 4
+    _lib.check(_lib.lib().snapb200_sem_loss_grad(
+        C.byref(p), C.c_void_p(_ptr(logits)), C.c_void_p(_ptr(labels_area)), C.c_void_p(_ptr(valid_area)),
+        C.c_void_p(_ptr(labels_excl)), C.c_void_p(_ptr(masks_indep)), C.c_void_p(_ptr(valid)),
+        C.c_void_p(_ptr(w[0])), C.c_void_p(_ptr(w[1])), C.c_void_p(_ptr(w[2])), C.c_void_p(_ptr(w[3])),
+        C.c_void_p(_ptr(counts)), C.c_int(dlogits.shape[1]), C.c_void_p(_ptr(dlogits)), _stream()))
+
+
+def relu_bwd(h: torch.Tensor, dx: torch.Tensor, elems: int) -> None:
+    _require(h, torch.bfloat16, "h")
+    _require(dx, torch.bfloat16, "dx")
+    assert h.is_contiguous() and dx.is_contiguous() and h.numel() >= elems and dx.numel() >= elems
+    _lib.check(_lib.lib().snapb200_relu_bwd(C.c_void_p(_ptr(h)), C.c_void_p(_ptr(dx)), C.c_longlong(elems), _stream()))
+
+
+def dense_wgrad(x: torch.Tensor, dy: torch.Tensor, M: int, K: int, N: int, dW: torch.Tensor,
+                db: Optional[torch.Tensor], workspace: Optional[torch.Tensor] = None) -> None:
+    """dW f32 [K,N] = x[:M,:K]^T dy[:M,:N], db f32 [N] = column sums of dy (bf16 inputs, fp32 accumulation)."""
+    _require(x, torch.bfloat16, "x")
+    _require(dy, torch.bfloat16, "dy")
+    _require(dW, torch.float32, "dW")
+    assert x.stride(1) == 1 and dy.stride(1) == 1 and dW.is_contiguous() and dW.shape == (K, N)
+    f = _lib.lib().snapb200_dense_wgrad_workspace
+    f.restype = C.c_size_t
+    need = int(f(C.c_longlong(M), K, N))
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+    assert workspace.numel() * workspace.element_size() >= need
+    _lib.check(_lib.lib().snapb200_dense_wgrad(
+        C.c_void_p(_ptr(x)), C.c_longlong(x.stride(0)), C.c_void_p(_ptr(dy)), C.c_longlong(dy.stride(0)),
+        C.c_longlong(M), K, N, C.c_void_p(_ptr(dW)), C.c_void_p(_ptr(db)), C.c_void_p(_ptr(workspace)),
+        C.c_size_t(workspace.numel() * workspace.element_size()), _stream()))
+
+
+def cast_pad_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    _require(src, torch.float32, "src")
+    _require(dst, torch.bfloat16, "dst")
+    rows, cols = src.shape
+    assert src.is_contiguous() and dst.is_contiguous() and dst.shape[0] == rows and dst.shape[1] >= cols
+    _lib.check(_lib.lib().snapb200_cast_pad_bf16(C.c_void_p(_ptr(src)), rows, cols, dst.shape[1], C.c_void_p(_ptr(dst)),
+                                                 _stream()))
+
+
+def adam_step(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor, lr: float, step: int,
+              b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> None:
+    for t, nm in ((p, "p"), (m, "m"), (v, "v"), (g, "g")):
+        _require(t, torch.float32, nm)
+        assert t.is_contiguous() and t.numel() == p.numel()
+    _lib.check(_lib.lib().snapb200_adam_step(
+        C.c_void_p(_ptr(p)), C.c_void_p(_ptr(m)), C.c_void_p(_ptr(v)), C.c_void_p(_ptr(g)), C.c_longlong(p.numel()),
+        C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(eps), step, _stream()))

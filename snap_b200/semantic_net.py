@@ -54,8 +54,8 @@ class SemanticHead:
 
     def __init__(self, config=None, dtype=torch.bfloat16):
         self.config = config if config is not None else configs.semantic_net()
-        if self.config.decoder_type != "resnet_stage":
-            raise NotImplementedError("only decoder_type='resnet_stage' (snap/configs/train_semantics.py:28-30) is built")
+        if self.config.decoder_type not in ("resnet_stage", "mlp"):
+            raise ValueError(f"Unknown {self.config.decoder_type}")                           # semantic_net.py:164-165
         c = self.config
         self.num_area = len(c.area_classes)
         self.num_excl = len(c.object_classes_exclusive)
@@ -86,6 +86,11 @@ class SemanticHead:
     def apply(self, variables: Dict, plane: types.FeaturePlane) -> Dict:
         params = variables["params"] if "params" in variables else variables
         params = params.get("decoder", params)
+        if self.config.decoder_type == "mlp":                                                # :147-152
+            key = ("mlp", id(params), str(plane.features.device))
+            if key not in self._cache:
+                self._cache[key] = MLPHeadTrainer(self.config, params, plane.features.device)
+            return self._cache[key].forward(plane)
         f, valid = plane.features.contiguous(), plane.valid.contiguous()
         B, G0, G1, C = f.shape
         dev = f.device
@@ -114,6 +119,129 @@ class SemanticHead:
         return pred
 
     __call__ = apply
+
+
+
+class MLPHeadTrainer:
+    """Forward and head-only training step of the default 'mlp' decoder (`semantic_net.py:147-152`: layers.MLP with
+    layers (dim,) * mlp_num_layers + (num_classes,)) on frozen BEV features, as `snap/configs/train_semantics.py:35-36`
+    fine-tunes it (`freeze_params_reg_exp = 'bev_mapper/'`): forward -> loss (`:300-343`) -> mean over the batch
+    (`trainer.py:221`) -> backward through the MLP -> gradient mean over ranks (`trainer.py:231-234`) -> optax.adam
+    (`defaults.py:81`).  Master parameters and Adam moments are fp32 device arrays (the reference keeps them in the
+    model dtype); GEMM operands are re-derived from the masters at every step."""
+
+    def __init__(self, config, params: Dict, device, lr: float = 5e-5):
+        c = self.config = config
+        self.dev = device
+        self.lr = lr
+        self.num_area = len(c.area_classes)
+        self.num_excl = len(c.object_classes_exclusive) + 1 if (c.object_classes_exclusive or c.object_classes_independent) else 0
+        self.num_indep = len(c.object_classes_independent)
+        self.num_classes = self.num_area + self.num_excl + self.num_indep
+        names = [f"Dense_{i}" for i in range(c.mlp_num_layers + 1)]
+        if sorted(params) != names:
+            raise KeyError(f"decoder params must be {names} (layers.MLP), got {sorted(params)}")
+        self.names = names
+        bank = self.bank = image_encoder._WeightBank(device)
+        self.dims = []
+        for n in names:
+            k = np.ascontiguousarray(params[n]["kernel"], dtype=F)
+            cin, cout = k.shape
+            last = n == names[-1]
+            if last:                       # logits padded to 32 columns (GEMM N multiple of 16, backward K multiple of 32)
+                kp = np.zeros((cin, 32), F)
+                kp[:, :cout] = k
+                k = kp
+            if cin % 32 or k.shape[1] % 16:
+                raise NotImplementedError("MLP widths must be multiples of 32")
+            bank.add(k, False, k_multiple=32)
+            self.dims.append((cin, k.shape[1], cout))
+        bank.finalize()
+        # views of the fp32 masters [in, out(padded)] inside the bank + biases, gradients, Adam moments
+        self.W, o = [], 0
+        for cin, coutp, _ in self.dims:
+            self.W.append(bank.master[o:o + cin * coutp].view(cin, coutp))
+            o += cin * coutp
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=device)
+        self.b = []
+        for n, (cin, coutp, cout) in zip(names, self.dims):
+            b = z(coutp)
+            b[:cout] = torch.from_numpy(np.ascontiguousarray(params[n]["bias"], dtype=F)).to(device)
+            self.b.append(b)
+        self.dW = [z(cin, coutp) for cin, coutp, _ in self.dims]
+        self.db = [z(coutp) for _, coutp, _ in self.dims]
+        self.mom = [[z(*t.shape), z(*t.shape)] for t in self.W + self.b]
+        self.Wc = [z(cin, coutp, dt=torch.bfloat16) for cin, coutp, _ in self.dims]   # bf16 [in, out]: B operand of dX
+        self.step = 0
+        self._buf: Dict = {}
+
+    def _buffers(self, rows: int):
+        if rows not in self._buf:
+            R = image_encoder._round_up(max(rows, 128), 128)
+            z = lambda c, dt=torch.bfloat16: torch.zeros((R, c), dtype=dt, device=self.dev)
+            self._buf[rows] = dict(h=[z(coutp) for _, coutp, _ in self.dims], d=[z(cin) for cin, _, _ in self.dims],
+                                   dlogits=z(32), counts=torch.zeros((1, 2), dtype=torch.float32, device=self.dev))
+        return self._buf[rows]
+
+    def forward(self, plane: types.FeaturePlane, keep: bool = False) -> Dict:
+        f, valid = plane.features.contiguous(), plane.valid.contiguous()
+        B, G0, G1, C = f.shape
+        rows = B * G0 * G1
+        buf = self._buffers(rows)
+        self.bank.run()
+        x = f.view(rows, C)
+        last = len(self.names) - 1
+        for i in range(len(self.names)):                                   # Dense -> (relu -> Dense)* (layers.py:73-77)
+            ops.gemm(x, self.bank.b_mats[i], buf["h"][i], m_rows=rows, bias=self.b[i], relu=i < last,
+                     row_mask=valid.view(rows) if i == last else None)     # zero invalid cells (:186)
+            x = buf["h"][i]
+        logits = buf["h"][last][:rows, : self.num_classes].float().view(B, G0, G1, self.num_classes)
+        pred = {"logits_areas": logits[..., : self.num_area]}
+        if self.num_classes > self.num_area:
+            rest = logits[..., self.num_area:]
+            pred["logits_objects_exclusive"] = rest[..., : self.num_excl]
+            pred["logits_objects_independent"] = rest[..., self.num_excl:]
+        return pred
+
+    def params_tree(self) -> Dict:
+        """Current parameters as the Flax tree (host, fp32)."""
+        return {n: {"kernel": self.W[i][:, :cout].cpu().numpy().copy(), "bias": self.b[i][:cout].cpu().numpy().copy()}
+                for i, (n, (_, _, cout)) in enumerate(zip(self.names, self.dims))}
+
+    def train_step(self, plane: types.FeaturePlane, model: "SemanticNetModel", data: Dict, update: bool = True):
+        """One training step on frozen BEV features.  Returns (loss tensor [], losses, metrics); gradients stay in
+        `self.dW` / `self.db` (averaged over ranks when torch.distributed is initialised)."""
+        from . import parallel
+        pred = self.forward(plane)
+        pred["bev_features"] = plane
+        losses, metrics, ctx = model.loss_metrics_function(pred, data, return_context=True)
+        B, cells = ctx["logits"].shape[:2]
+        rows = B * cells
+        buf = self._buffers(rows)
+        if buf["counts"].shape[0] != B:
+            buf["counts"] = torch.zeros((B, 2), dtype=torch.float32, device=self.dev)
+        ops.sem_loss_grad(ctx["logits"], ctx["labels_area"], ctx["valid_area"], ctx["labels_excl"], ctx["masks_indep"],
+                          ctx["valid"], self.num_area, self.num_excl, self.num_indep, ctx["weights"], buf["counts"],
+                          buf["dlogits"])
+        x0 = plane.features.contiguous().view(rows, -1)
+        acts = [x0] + buf["h"][:-1]                       # input of layer i
+        dy = buf["dlogits"]
+        for i in reversed(range(len(self.names))):
+            cin, coutp, _ = self.dims[i]
+            ops.dense_wgrad(acts[i], dy, rows, cin, coutp, self.dW[i], self.db[i])
+            if i > 0:                                     # dX = dY W^T, then the ReLU in front of this layer
+                ops.cast_pad_bf16(self.W[i], self.Wc[i])
+                ops.gemm(dy, self.Wc[i], buf["d"][i], m_rows=rows, seg_k=coutp)
+                ops.relu_bwd(acts[i], buf["d"][i], rows * cin)
+                dy = buf["d"][i]
+        grads = {n: {"kernel": self.dW[i], "bias": self.db[i]} for i, n in enumerate(self.names)}
+        parallel.pmean_tree(grads)                        # jax.lax.pmean(grad, 'batch') (trainer.py:231-234)
+        if update:
+            self.step += 1
+            for k, (pt, g) in enumerate(zip(self.W + self.b, self.dW + self.db)):
+                ops.adam_step(pt.view(-1) if pt.is_contiguous() else pt, self.mom[k][0].view(-1), self.mom[k][1].view(-1),
+                              g.view(-1), self.lr, self.step)
+        return losses["total"], losses, metrics
 
 
 def balancing_weights(frequencies: Dict[str, float], classes, binary: bool = False, eps: float = 1e-3):
@@ -153,7 +281,7 @@ class SemanticNetModel:
         self.config = config if config is not None else configs.semantic_net()
         self.gt_classes = tuple(gt_classes)
 
-    def loss_metrics_function(self, pred: Dict, data: Dict, model_params=None):
+    def loss_metrics_function(self, pred: Dict, data: Dict, model_params=None, return_context: bool = False):
         """pred: logits dict of SemanticHead + 'bev_features' (FeaturePlane); data['rasters']['gt_semantics'] bool
         [B,G,G,N_gt] (NumPy).  Returns (losses, metrics) as dicts of per-example device tensors."""
         c = self.config
@@ -204,4 +332,8 @@ class SemanticNetModel:
                 metrics[f"recall/{n}"] = out[:, 24 + i]
             for i, n in enumerate(c.object_classes_independent):
                 metrics[f"recall/{n}"] = out[:, 32 + i]
-        return losses, {f"semantics/{k}": v for k, v in metrics.items()}
+        metrics = {f"semantics/{k}": v for k, v in metrics.items()}
+        if return_context:   # device-side labels / masks / weights, reused by the backward of the training step
+            return losses, metrics, dict(logits=logits, labels_area=dv(la, torch.int32), valid_area=valid_area.contiguous(),
+                                         labels_excl=le_d, masks_indep=mi_d, valid=bev_valid, weights=weights)
+        return losses, metrics

@@ -52,3 +52,29 @@ def test_exclusive_labels():
     assert labels[0, 0] == 0 and valid[0, 0] and labels[0, 1] == 2 and valid[0, 1] and not valid[1, 2]
     labels, valid = osn.create_exclusive_labels(m, gt, ("tree",), add_void=True)
     assert labels[1, 2] == 0 and labels[0, 0] == 1 and not valid[0, 0]
+
+
+def test_torch_loss_restatement_equals_numpy_oracle():
+    """oracle.semantic_net.total_loss_torch (the differentiable form used as gradient oracle) == loss_metrics (pinned above)."""
+    import torch
+    d = load()
+    fa = dict(zip(AREA, d["fa"]))
+    fo = dict(zip(EXCL + INDEP, d["fo"]))
+    gt_classes = AREA + EXCL[:-1] + INDEP
+    rng = np.random.default_rng(5)
+    B, H, W = d["la"].shape
+    masks = rng.random((B, H, W, len(gt_classes))) < 0.3
+    bev_valid = d["valid"]
+    la, va = osn.create_exclusive_labels(masks, gt_classes, AREA)
+    le, _ = osn.create_exclusive_labels(masks, gt_classes, EXCL[:-1], add_void=True)
+    gi = {c: i for i, c in enumerate(gt_classes)}
+    mi = masks[..., [gi[c] for c in INDEP]]
+    logits = np.concatenate([d["logits_a"], d["logits_e"], d["logits_i"]], -1)
+    for bal in (False, True):
+        ol, _ = osn.loss_metrics(d["logits_a"], d["logits_e"], d["logits_i"], bev_valid, masks, gt_classes, AREA, EXCL[:-1],
+                                 INDEP, fa if bal else None, fo if bal else None)
+        w = (osn.balancing_weights(fa, AREA), osn.balancing_weights(fo, EXCL), *osn.balancing_weights(fo, INDEP, binary=True)) \
+            if bal else (None,) * 4
+        mean, total = osn.total_loss_torch(torch.from_numpy(logits), la, va, le, mi, bev_valid, len(AREA), len(EXCL), *w)
+        close(total.numpy(), ol["total"])
+        assert abs(float(mean) - float(ol["total"].mean())) < 1e-5

@@ -69,3 +69,41 @@ def test_single_process_fallbacks():
     assert parallel.shard_tiles(list(range(5)), 0, 1) == [0, 1, 2, 3, 4]
     assert parallel.pmean_tree({"a": torch.ones(3)}) == 0
     assert parallel.max_over_ranks(3.0) == 3.0 and parallel.job_throughput(4, 2.0) == 2.0
+
+
+def _grad_mean_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from snap_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the gradient tree of the MLP semantic head (Dense_0..2), different on every rank
+    g = torch.Generator().manual_seed(100 + rank)
+    tree = {f"Dense_{i}": {"kernel": torch.randn((128, 128 if i < 2 else 32), generator=g), "bias": torch.randn((128 if i < 2 else 32,), generator=g)}
+            for i in range(3)}
+    calls = parallel.pmean_tree(tree)
+    q.put((rank, calls, {k: {n: t.numpy().copy() for n, t in v.items()} for k, v in tree.items()}))   # NumPy: picklable by value
+    dist.destroy_process_group()
+
+
+def test_head_gradient_mean_world_size_2():
+    """trainer.py:231-234 (pmean of the head gradients) on two gloo ranks: one bucketed all-reduce, identical means."""
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_mean_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1] == 1
+    for k in res[0][2]:
+        for n in res[0][2][k]:
+            assert (res[0][2][k][n] == res[1][2][k][n]).all()
+    g0, g1 = torch.Generator().manual_seed(100), torch.Generator().manual_seed(101)
+    a, b = torch.randn((128, 128), generator=g0), torch.randn((128, 128), generator=g1)
+    assert torch.allclose(torch.from_numpy(res[0][2]["Dense_0"]["kernel"]), (a + b) / 2, atol=1e-6)
