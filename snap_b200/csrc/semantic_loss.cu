@@ -165,9 +165,76 @@ sem_loss_kernel(const SnapSemLossParams P, const float* __restrict__ logits, con
   }
 }
 
+// Label preparation of SemanticNetModel (semantic_net.py:254-298) on the device: thread per cell.
+//   sel_area [Ka][4], sel_excl [Ke-1][4]: ground-truth mask channels OR-ed into each selected class (-1 = unused; 'line'
+//   absorbs 'stopline' / 'otherlanemarking', :263-270); sel_indep [Ki]: one channel each.
+//   labels = argmax over the selected masks (first true, 0 if none); the exclusive objects get the void index when none.
+struct SemLabelSel {
+  int area[SEM_MAXC][4];
+  int excl[SEM_MAXC][4];
+  int indep[SEM_MAXC];
+  int Ka, Ke, Ki, ngt;
+};
+
+__global__ void sem_labels_kernel(const SemLabelSel S, const uint8_t* __restrict__ masks, const uint8_t* __restrict__ bev_valid,
+                                  long long rows, int* __restrict__ labels_area, uint8_t* __restrict__ valid_area,
+                                  int* __restrict__ labels_excl, uint8_t* __restrict__ masks_indep) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= rows) return;
+  const uint8_t* m = masks + g * S.ngt;
+  auto on = [&](const int* sel) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (sel[j] >= 0) any |= m[sel[j]] != 0;
+    return any;
+  };
+  int la = 0;
+  bool va = false;
+  for (int c = S.Ka - 1; c >= 0; --c)
+    if (on(S.area[c])) {
+      la = c;
+      va = true;
+    }
+  labels_area[g] = la;
+  valid_area[g] = (va && bev_valid[g] != 0) ? 1 : 0;   // pred['bev_features'].valid & valid (:302)
+  if (labels_excl != nullptr) {
+    int le = S.Ke;                                     // void = len(classes) (:274-275)
+    for (int c = S.Ke - 1; c >= 0; --c)
+      if (on(S.excl[c])) le = c;
+    labels_excl[g] = le;
+  }
+  if (masks_indep != nullptr)
+    for (int c = 0; c < S.Ki; ++c) masks_indep[g * S.Ki + c] = m[S.indep[c]] != 0 ? 1 : 0;
+}
+
 }  // namespace snapb200
 
 using namespace snapb200;
+
+extern "C" int snapb200_sem_labels(const int* sel_area, int num_area, const int* sel_excl, int num_excl_classes,
+                                   const int* sel_indep, int num_indep, int num_gt, const uint8_t* masks,
+                                   const uint8_t* bev_valid, long long rows, int* labels_area, uint8_t* valid_area,
+                                   int* labels_excl, uint8_t* masks_indep, void* stream) {
+  SNAP_REQUIRE(sel_area && masks && bev_valid && labels_area && valid_area, "null pointer");
+  SNAP_REQUIRE(num_area >= 1 && num_area <= SEM_MAXC && num_excl_classes >= 0 && num_excl_classes <= SEM_MAXC - 1 &&
+                   num_indep >= 0 && num_indep <= SEM_MAXC, "at most %d classes per group", SEM_MAXC);
+  SNAP_REQUIRE((num_excl_classes == 0 && num_indep == 0) || (sel_excl || num_excl_classes == 0), "selection tables missing");
+  SemLabelSel S;
+  for (int c = 0; c < SEM_MAXC; ++c) {
+    for (int j = 0; j < 4; ++j) {
+      S.area[c][j] = c < num_area ? sel_area[c * 4 + j] : -1;
+      S.excl[c][j] = c < num_excl_classes ? sel_excl[c * 4 + j] : -1;
+      SNAP_REQUIRE(S.area[c][j] < num_gt && S.excl[c][j] < num_gt, "mask channel out of range");
+    }
+    S.indep[c] = c < num_indep ? sel_indep[c] : 0;
+    SNAP_REQUIRE(S.indep[c] >= 0 && S.indep[c] < num_gt, "mask channel out of range");
+  }
+  S.Ka = num_area; S.Ke = num_excl_classes; S.Ki = num_indep; S.ngt = num_gt;
+  sem_labels_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      S, masks, bev_valid, rows, labels_area, valid_area, labels_excl, masks_indep);
+  return check_launch("sem_labels_kernel");
+}
 
 extern "C" int snapb200_sem_loss(const SnapSemLossParams* p, const float* logits, const int* labels_area,
                                  const uint8_t* valid_area, const int* labels_excl, const uint8_t* masks_indep,

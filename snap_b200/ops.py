@@ -650,3 +650,25 @@ def adam_step(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor
     _lib.check(_lib.lib().snapb200_adam_step(
         C.c_void_p(_ptr(p)), C.c_void_p(_ptr(m)), C.c_void_p(_ptr(v)), C.c_void_p(_ptr(g)), C.c_longlong(p.numel()),
         C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(eps), step, _stream()))
+
+
+def sem_labels(sel_area: Sequence[Sequence[int]], sel_excl: Sequence[Sequence[int]], sel_indep: Sequence[int], num_gt: int,
+               masks: torch.Tensor, bev_valid: torch.Tensor, labels_area: torch.Tensor, valid_area: torch.Tensor,
+               labels_excl: Optional[torch.Tensor], masks_indep: Optional[torch.Tensor]) -> None:
+    """masks u8 [rows, num_gt] -> labels / validity as consumed by `sem_loss` (label preparation on the device)."""
+    _require(masks, torch.uint8, "masks")
+    _require(bev_valid, torch.uint8, "bev_valid")
+    rows = bev_valid.numel()
+    assert masks.is_contiguous() and masks.numel() == rows * num_gt
+
+    def table(sel):
+        flat = []
+        for s in sel:
+            s = list(s)[:4]
+            flat += s + [-1] * (4 - len(s))
+        return (C.c_int * max(len(flat), 1))(*flat)
+    ti = (C.c_int * max(len(sel_indep), 1))(*sel_indep)
+    _lib.check(_lib.lib().snapb200_sem_labels(
+        table(sel_area), len(sel_area), table(sel_excl), len(sel_excl), ti, len(sel_indep), num_gt,
+        C.c_void_p(_ptr(masks)), C.c_void_p(_ptr(bev_valid)), C.c_longlong(rows), C.c_void_p(_ptr(labels_area)),
+        C.c_void_p(_ptr(valid_area)), C.c_void_p(_ptr(labels_excl)), C.c_void_p(_ptr(masks_indep)), _stream()))

@@ -280,6 +280,7 @@ class SemanticNetModel:
     def __init__(self, config=None, gt_classes=()):
         self.config = config if config is not None else configs.semantic_net()
         self.gt_classes = tuple(gt_classes)
+        self._weights: Dict = {}
 
     def loss_metrics_function(self, pred: Dict, data: Dict, model_params=None, return_context: bool = False):
         """pred: logits dict of SemanticHead + 'bev_features' (FeaturePlane); data['rasters']['gt_semantics'] bool
@@ -287,40 +288,61 @@ class SemanticNetModel:
         c = self.config
         if "map" in data:
             data = data["map"]
-        masks = np.asarray(data["rasters"]["gt_semantics"]).astype(bool)
-        la, va = create_exclusive_labels(masks, self.gt_classes, c.area_classes)             # :301
         logits_a = pred["logits_areas"]
         dev = logits_a.device
         B, G0, G1, Ka = logits_a.shape
         cells = G0 * G1
+        masks = data["rasters"]["gt_semantics"]                      # bool / u8 [B,G,G,N_gt]: NumPy or a CUDA tensor
+        if not isinstance(masks, torch.Tensor):
+            masks = torch.from_numpy(np.ascontiguousarray(masks).view(np.uint8) if masks.dtype == bool
+                                     else np.ascontiguousarray(masks, dtype=np.uint8))
+        masks = masks.to(dev).to(torch.uint8).reshape(B * cells, -1).contiguous()
+        ngt = masks.shape[1]
+        assert ngt == len(self.gt_classes), "gt_semantics channels must follow semantic_classes_gt"
+        gi = {n: i for i, n in enumerate(self.gt_classes)}
+
+        def selection(classes):                                      # _create_exclusive_labels (:254-270)
+            sel = []
+            for n in classes:
+                idx = [gi[n]]
+                if n == "line":
+                    idx += [gi[x] for x in ("stopline", "otherlanemarking") if x in gi and x not in classes]
+                sel.append(idx)
+            return sel
         bev_valid = pred["bev_features"].valid.reshape(B, cells).contiguous()
-        dv = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt).reshape(B, cells, *a.shape[3:]).contiguous()
         has_obj = "logits_objects_exclusive" in pred
         parts = [logits_a]
         Ke = Ki = 0
         le_d = mi_d = None
+        la_d = torch.empty((B, cells), dtype=torch.int32, device=dev)
+        valid_area = torch.empty((B, cells), dtype=torch.uint8, device=dev)
+        sel_e, sel_i = [], []
         if has_obj:
-            le, _ = create_exclusive_labels(masks, self.gt_classes, c.object_classes_exclusive, add_void=True)   # :278-281
-            gi = {n: i for i, n in enumerate(self.gt_classes)}
-            mi = masks[..., [gi[n] for n in c.object_classes_independent]]
             parts += [pred["logits_objects_exclusive"], pred["logits_objects_independent"]]
             Ke, Ki = parts[1].shape[-1], parts[2].shape[-1]
-            le_d, mi_d = dv(le, torch.int32), dv(mi, torch.uint8)
+            sel_e = selection(c.object_classes_exclusive)            # + void (:278-281)
+            sel_i = [gi[n] for n in c.object_classes_independent]
+            le_d = torch.empty((B, cells), dtype=torch.int32, device=dev)
+            mi_d = torch.empty((B, cells, Ki), dtype=torch.uint8, device=dev)
+        ops.sem_labels(selection(c.area_classes), sel_e, sel_i, ngt, masks, bev_valid, la_d, valid_area, le_d, mi_d)  # :301-302
         logits = torch.cat(parts, -1).reshape(B, cells, Ka + Ke + Ki).contiguous()          # [areas | excl | indep]
-        valid_area = dv(va, torch.uint8) & bev_valid                                        # :302
         weights = None
         fa, fo = c.get("area_frequencies"), c.get("object_frequencies")
         if fa or fo:
-            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(dev)
-            weights = [None] * 4
-            if fa:
-                weights[0] = t(balancing_weights(dict(fa), c.area_classes))
-            if fo and has_obj:
-                weights[1] = t(balancing_weights(dict(fo), (*c.object_classes_exclusive, "void")))
-                wp, wn = balancing_weights(dict(fo), c.object_classes_independent, binary=True)
-                weights[2], weights[3] = t(wp), t(wn)
+            wkey = (str(dev), has_obj)
+            if wkey not in self._weights:    # class-balancing weights (:31-53), uploaded once per device
+                t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(dev)
+                w = [None] * 4
+                if fa:
+                    w[0] = t(balancing_weights(dict(fa), c.area_classes))
+                if fo and has_obj:
+                    w[1] = t(balancing_weights(dict(fo), (*c.object_classes_exclusive, "void")))
+                    wp, wn = balancing_weights(dict(fo), c.object_classes_independent, binary=True)
+                    w[2], w[3] = t(wp), t(wn)
+                self._weights[wkey] = w
+            weights = self._weights[wkey]
         out = torch.empty((B, ops._lib.SEM_OUT), dtype=torch.float32, device=dev)
-        ops.sem_loss(logits, dv(la, torch.int32), valid_area.contiguous(), le_d, mi_d, bev_valid, Ka, Ke, Ki, weights, out)
+        ops.sem_loss(logits, la_d, valid_area, le_d, mi_d, bev_valid, Ka, Ke, Ki, weights, out)
         losses = {"nll_areas": out[:, 0], "total": out[:, 3]}
         metrics = {"accuracy": out[:, 4], "recall/average": out[:, 6]}
         for i, n in enumerate(c.area_classes):
@@ -334,6 +356,6 @@ class SemanticNetModel:
                 metrics[f"recall/{n}"] = out[:, 32 + i]
         metrics = {f"semantics/{k}": v for k, v in metrics.items()}
         if return_context:   # device-side labels / masks / weights, reused by the backward of the training step
-            return losses, metrics, dict(logits=logits, labels_area=dv(la, torch.int32), valid_area=valid_area.contiguous(),
+            return losses, metrics, dict(logits=logits, labels_area=la_d, valid_area=valid_area,
                                          labels_excl=le_d, masks_indep=mi_d, valid=bev_valid, weights=weights)
         return losses, metrics

@@ -77,3 +77,28 @@ def test_semantic_losses_against_oracle(balanced):
         chk(f"recall/{n}", om["recall_excl"][:, i])
     for i, n in enumerate(cfg.object_classes_independent):
         chk(f"recall/{n}", om["recall_indep"][:, i])
+
+
+def test_label_preparation_kernel_equals_numpy():
+    """snapb200_sem_labels vs the NumPy restatement of _create_exclusive_labels (semantic_net.py:254-298), 'line' merging
+    included."""
+    from oracle import semantic_net as osn
+    from snap_b200 import ops
+    rng = np.random.default_rng(4)
+    gt = ("road", "sidewalk", "line", "stopline", "otherlanemarking", "tree", "pole", "traffic_sign", "street_light")
+    area, excl, indep = ("sidewalk", "road", "line"), ("pole", "tree"), ("street_light", "traffic_sign")
+    B, G = 2, 24
+    masks = rng.random((B, G, G, len(gt))) < 0.15
+    bev = rng.random((B, G, G)) < 0.8
+    gi = {c: i for i, c in enumerate(gt)}
+    sel = lambda cls: [[gi[n]] + ([gi[x] for x in ("stopline", "otherlanemarking") if x not in cls] if n == "line" else []) for n in cls]
+    rows = B * G * G
+    la = torch.empty(rows, dtype=torch.int32, device="cuda"); va = torch.empty(rows, dtype=torch.uint8, device="cuda")
+    le = torch.empty(rows, dtype=torch.int32, device="cuda"); mi = torch.empty((rows, 2), dtype=torch.uint8, device="cuda")
+    ops.sem_labels(sel(area), sel(excl), [gi[n] for n in indep], len(gt), torch.from_numpy(masks.view(np.uint8)).cuda().reshape(rows, -1),
+                   torch.from_numpy(bev.astype(np.uint8)).cuda().reshape(-1), la, va, le, mi)
+    ola, ova = osn.create_exclusive_labels(masks, gt, area)
+    ole, _ = osn.create_exclusive_labels(masks, gt, excl, add_void=True)
+    assert np.array_equal(la.cpu().numpy(), ola.reshape(-1)) and np.array_equal(va.cpu().numpy().astype(bool), (ova & bev).reshape(-1))
+    assert np.array_equal(le.cpu().numpy(), ole.reshape(-1)) and (ole == 2).any()
+    assert np.array_equal(mi.cpu().numpy().astype(bool), masks[..., [gi[n] for n in indep]].reshape(rows, 2))
