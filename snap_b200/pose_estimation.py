@@ -112,9 +112,10 @@ def pose_scoring_many_batched(j_t_i: torch.Tensor, maps: SimilarityMaps, i_xy_po
 def refinement_offsets() -> Tuple[np.ndarray, np.ndarray]:
     """`pose_estimation.py:177-184`: the axes of jnp.mgrid[slice_r, slice_p, slice_p] (degrees; metres)."""
     delta_p, delta_r, range_p, range_r = 0.2, 0.25, 4, 5
-    rot = np.mgrid[slice(-range_r, range_r + delta_r, delta_r)].astype(F)
-    pos = np.mgrid[slice(-range_p, range_p + delta_p, delta_p)].astype(F)
-    return rot, pos
+    slice_p = slice(-range_p, range_p + delta_p, delta_p)
+    slice_r = slice(-range_r, range_r + delta_r, delta_r)
+    off = np.mgrid[slice_r, slice_p, slice_p].astype(F)       # the reference's 3-D mgrid (:181); its axes:
+    return np.ascontiguousarray(off[0][:, 0, 0]), np.ascontiguousarray(off[1][0, :, 0])
 
 
 _REFINE_AXES: dict = {}

@@ -115,3 +115,48 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(ValueError):
         from snap_b200 import image_encoder
         image_encoder.ImageEncoder(c2)
+
+
+def test_xy_bev_points_separable_and_paired():
+    """data['xy_bev'] (bev_mapper.py:162-166): a regular (separable) point grid keeps the xs[X], ys[Y] layout, arbitrary
+    points (the field-of-view filtered query frustum [N,1,2] of BEVLocalizer) switch the lift to per-column coordinates."""
+    import pytest
+    from snap_b200 import bev_localizer
+    G = 16
+    data = synthetic.make_tile(3, 1, (96, 128), G, batch=2)
+    mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), types.Grid2D((G, G), 0.2))
+    # separable: a shifted regular grid
+    xs0, ys0 = types.Grid2D((6, 4), 0.5).cell_centers(0) - F(1.5), types.Grid2D((6, 4), 0.5).cell_centers(1)
+    xy = np.stack(np.meshgrid(xs0, ys0, indexing="ij"), -1).astype(F)
+    d = dict(data, xy_bev=xy)
+    xs, ys, zs = mapper.build_xyz_grid(d)
+    assert "xy_shape" not in d and np.array_equal(xs, xs0) and np.array_equal(ys, ys0) and zs.shape == (2, 60)
+    # batched copies of the same grid are accepted, different grids per example are not
+    d = dict(data, xy_bev=np.stack([xy, xy]))
+    assert np.array_equal(mapper.build_xyz_grid(d)[0], xs0)
+    with pytest.raises(NotImplementedError):
+        mapper.build_xyz_grid(dict(data, xy_bev=np.stack([xy, xy + F(0.1)])))
+    # arbitrary points: the query frustum of the localizer
+    _, _, q = bev_localizer.build_query_frustum_grid(0.2, 16.0, True, 72.0)
+    d = dict(data, xy_bev=q)
+    xs, ys, _ = mapper.build_xyz_grid(d)
+    assert d["xy_shape"] == (4652, 1) and np.array_equal(xs, q[:, 0, 0]) and np.array_equal(ys, q[:, 0, 1])
+    lp = sve.fill_lift_params(configs.streetview_encoder(), 1, 24, 32, 4652, 1, 60, 288, True)
+    assert lp.xy_paired == 1 and lp.no_variance == 0 and lp.add_minmax == 0 and lp.X == 4652 and lp.Y == 1
+
+
+def test_localizer_pose_helpers():
+    """Transform3D -> Transform2D of the ground truth (geometry.py:103-111) and the refinement lattice axes (pose_estimation.py:177-184)."""
+    from oracle import pose_estimation as ope
+    from snap_b200 import bev_localizer, pose_estimation
+    a = np.array([0.3, -2.0, 3.1], F)
+    R = np.stack([[[np.cos(x), -np.sin(x), 0], [np.sin(x), np.cos(x), 0], [0, 0, 1]] for x in a]).astype(F)
+    t = np.arange(9, dtype=F).reshape(3, 3)
+    out = bev_localizer.transform2d_from_transform3d(types.Transform3D(R=R, t=t))
+    ang, tt = ope.transform2d_from_transform3d(R, t)
+    assert np.array_equal(out[:, 0], ang) and np.array_equal(out[:, 1:], tt) and np.allclose(out[:, 0], a, atol=1e-6)
+    rot, pos = pose_estimation.refinement_offsets()
+    shape, off = ope.refinement_offsets()
+    assert (len(rot), len(pos), len(pos)) == tuple(shape) == (41, 41, 41)
+    assert np.array_equal(off[:, 0].reshape(shape)[:, 0, 0], rot) and np.array_equal(off[:, 2].reshape(shape)[0, 0, :], pos)
+    assert rot[20] == 0 and abs(pos[20]) < 1e-6
