@@ -160,3 +160,23 @@ def test_localizer_pose_helpers():
     assert (len(rot), len(pos), len(pos)) == tuple(shape) == (41, 41, 41)
     assert np.array_equal(off[:, 0].reshape(shape)[:, 0, 0], rot) and np.array_equal(off[:, 2].reshape(shape)[0, 0, :], pos)
     assert rot[20] == 0 and abs(pos[20]) < 1e-6
+
+
+def test_recover_dense_feature_plane():
+    """bev_localizer.py:111-129: the field-of-view points scatter back onto the dense 120 x 80 frustum grid."""
+    from snap_b200 import bev_localizer
+    cfg = configs.bev_localizer()
+    cfg.bev_mapper = configs.bev_mapper(("streetview",))
+    cfg.filter_points_in_fov = True
+    cfg.num_pose_samples = 16
+    loc = bev_localizer.BEVLocalizer(cfg, None, types.Grid2D((32, 32), 0.2))
+    N = loc.q_xy_p.shape[0]
+    feats = torch.arange(N * 3, dtype=torch.float32).reshape(N, 1, 3) + 1
+    valid = torch.ones((N, 1), dtype=torch.uint8)
+    dense = loc.recover_dense_feature_plane(types.FeaturePlane(feats, valid))
+    assert tuple(dense.features.shape) == (120, 80, 3) and int(dense.valid.sum()) == N == 4652
+    # point n sits in the cell its coordinates fall into; cells outside the field of view stay empty
+    q = loc.q_xy_p[:, 0] + loc.qgrid_p_q
+    ij = np.floor(q / F(0.2)).astype(int)
+    assert np.array_equal(dense.features[ij[:, 0], ij[:, 1]].numpy(), feats[:, 0].numpy())
+    assert not dense.features[0, 79].any() and not dense.valid[0, 79]        # far corner: |angle| > 36 degrees
