@@ -1,0 +1,55 @@
+"""Design checks for the round-2 backward kernels (tools/design/backward_formulas.py) against torch autograd on the CPU:
+GroupNorm and StdConv closed forms, and the 3x3 conv backward as segment GEMMs / shifted split-K products on the
+zero-bordered layout of the forward engine."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "design"))
+import backward_formulas as bf  # noqa: E402
+
+
+def test_groupnorm_backward_closed_form():
+    rng = np.random.default_rng(0)
+    N, H, W, C = 2, 5, 6, 64
+    x = torch.tensor(rng.standard_normal((N, H, W, C)), dtype=torch.float64, requires_grad=True)
+    scale = torch.tensor(rng.standard_normal(C) * 0.3 + 1, dtype=torch.float64, requires_grad=True)
+    bias = torch.tensor(rng.standard_normal(C) * 0.1, dtype=torch.float64, requires_grad=True)
+    xg = x.reshape(N, H * W, 32, C // 32)
+    mu = xg.mean(dim=(1, 3), keepdim=True)
+    var = ((xg - mu) ** 2).mean(dim=(1, 3), keepdim=True)
+    y = ((xg - mu) / torch.sqrt(var + 1e-5)).reshape(N, H, W, C) * scale + bias      # resnet.py:34-41,57-69
+    dy = torch.tensor(rng.standard_normal((N, H, W, C)), dtype=torch.float64)
+    y.backward(dy)
+    dx, dscale, dbias = bf.groupnorm_backward(x.detach().numpy(), dy.numpy(), scale.detach().numpy())
+    assert np.abs(dx - x.grad.numpy()).max() < 1e-10
+    assert np.abs(dscale - scale.grad.numpy()).max() < 1e-10 and np.abs(dbias - bias.grad.numpy()).max() < 1e-10
+
+
+def test_stdconv_weight_backward_closed_form():
+    rng = np.random.default_rng(1)
+    w = torch.tensor(rng.standard_normal((3, 3, 8, 5)), dtype=torch.float64, requires_grad=True)
+    mu = w.mean(dim=(0, 1, 2), keepdim=True)
+    var = ((w - mu) ** 2).mean(dim=(0, 1, 2), keepdim=True)
+    ws = (w - mu) / torch.sqrt(var + 1e-10)                                          # resnet.py:73-79
+    dws = torch.tensor(rng.standard_normal((3, 3, 8, 5)), dtype=torch.float64)
+    ws.backward(dws)
+    assert np.abs(bf.stdconv_weight_backward(w.detach().numpy(), dws.numpy()) - w.grad.numpy()).max() < 1e-10
+
+
+def test_conv3x3_backward_on_the_bordered_layout():
+    rng = np.random.default_rng(2)
+    N, H, W, Cin, Cout = 2, 6, 7, 4, 3
+    x = torch.tensor(rng.standard_normal((N, H, W, Cin)), dtype=torch.float64, requires_grad=True)
+    w = torch.tensor(rng.standard_normal((3, 3, Cin, Cout)), dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    # the forward decomposition the engine already runs
+    assert np.abs(bf.conv3x3_forward_segments(x.detach().numpy(), w.detach().numpy()) - y.detach().numpy()).max() < 1e-10
+    dy = torch.tensor(rng.standard_normal((N, H, W, Cout)), dtype=torch.float64)
+    y.backward(dy)
+    dx = bf.conv3x3_dx_segments(dy.numpy(), w.detach().numpy())
+    dw = bf.conv3x3_dw_shifted(x.detach().numpy(), dy.numpy())
+    assert np.abs(dx - x.grad.numpy()).max() < 1e-10
+    assert np.abs(dw - w.grad.numpy()).max() < 1e-10

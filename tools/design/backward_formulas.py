@@ -1,0 +1,109 @@
+"""Closed forms and launch decompositions for the backward kernels of round 2, written as NumPy so that
+tests/test_backward_design_cpu.py can check them against torch autograd BEFORE any CUDA is written:
+
+  * GroupNorm backward (resnet.py:46-70) as two per-(image, group) reductions + one elementwise pass,
+  * StdConv weight-standardisation backward (resnet.py:34-41,73-79),
+  * 3x3 / stride-1 conv backward on the zero-bordered activation layout of the forward GEMM engine:
+      dX = a 9-segment GEMM over the zero-bordered dY with the taps mirrored (same engine, same segment mechanism),
+      dW = 9 split-K products  X_bordered[m + off_tap]^T dY_bordered[m]  (snapb200_dense_wgrad with a row offset).
+
+Design notes only: nothing here is imported by the product package.
+"""
+import numpy as np
+
+
+def groupnorm_backward(x, dy, scale, groups=32, eps=1e-5):
+    """x, dy [N,H,W,C]; y = (x - mu) * rstd * scale + bias with statistics over (H, W, C/groups).
+    Returns dx, dscale, dbias.  Kernel plan: pass 1 accumulates per (n, g): s1 = sum(dy*scale), s2 = sum(dy*scale*xhat)
+    (and per channel dscale, dbias); pass 2: dx = rstd * (dy*scale - s1/m - xhat * s2/m)."""
+    N, H, W, C = x.shape
+    cpg = C // groups
+    xg = x.reshape(N, H * W, groups, cpg).astype(np.float64)
+    mu = xg.mean(axis=(1, 3), keepdims=True)
+    var = ((xg - mu) ** 2).mean(axis=(1, 3), keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    xhat = (xg - mu) * rstd
+    g = (dy.astype(np.float64) * scale.reshape(1, 1, 1, C)).reshape(N, H * W, groups, cpg)
+    m = H * W * cpg
+    s1 = g.sum(axis=(1, 3), keepdims=True)
+    s2 = (g * xhat).sum(axis=(1, 3), keepdims=True)
+    dx = rstd * (g - s1 / m - xhat * s2 / m)
+    dscale = (dy.astype(np.float64) * xhat.reshape(N, H, W, C)).sum(axis=(0, 1, 2))
+    dbias = dy.astype(np.float64).sum(axis=(0, 1, 2))
+    return dx.reshape(N, H, W, C), dscale, dbias
+
+
+def stdconv_weight_backward(w, dws, eps=1e-10):
+    """w [kh,kw,in,out] raw kernel, dws = gradient w.r.t. the standardised kernel ws = (w - mu) / sqrt(var + eps) with
+    statistics over (kh, kw, in) per output channel.  dw = (dws - mean(dws) - ws * mean(dws * ws)) / sqrt(var + eps)."""
+    w64, d64 = w.astype(np.float64), dws.astype(np.float64)
+    mu = w64.mean(axis=(0, 1, 2), keepdims=True)
+    var = ((w64 - mu) ** 2).mean(axis=(0, 1, 2), keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    ws = (w64 - mu) * rstd
+    return rstd * (d64 - d64.mean(axis=(0, 1, 2), keepdims=True) - ws * (d64 * ws).mean(axis=(0, 1, 2), keepdims=True))
+
+
+def bordered(x):
+    """[N,H,W,C] -> zero-bordered rows [N*(H+2)*(W+2), C] (the layout gn_apply writes for the forward 3x3 GEMM)."""
+    N, H, W, C = x.shape
+    out = np.zeros((N, H + 2, W + 2, C), x.dtype)
+    out[:, 1:-1, 1:-1] = x
+    return out.reshape(-1, C)
+
+
+def segment_gemm(a_rows, b, seg_off, seg_k, m_rows):
+    """The engine's semantics (include/snapb200.h): out[m] = sum_s A[m + seg_off[s], :seg_k] @ B[:, s*seg_k:(s+1)*seg_k]^T,
+    rows outside A read as zero (TMA zero fill)."""
+    R = a_rows.shape[0]
+    out = np.zeros((m_rows, b.shape[0]), np.float64)
+    for s, off in enumerate(seg_off):
+        idx = np.arange(m_rows) + off
+        ok = (idx >= 0) & (idx < R)
+        a = np.zeros((m_rows, seg_k))
+        a[ok] = a_rows[idx[ok], :seg_k]
+        out += a @ b[:, s * seg_k:(s + 1) * seg_k].T.astype(np.float64)
+    return out
+
+
+def conv3x3_forward_segments(x, w):
+    """Forward as the engine runs it: bordered input rows, tap (kh,kw) = row offset (kh-1)(W+2)+(kw-1), B = [out, 9*in];
+    returns the bordered-layout output [N,(H+2),(W+2),out] (only the interior is meaningful / stored)."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[-1]
+    xb = bordered(x)
+    seg = [(kh - 1) * (W + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
+    b = w.reshape(9 * Cin, Cout).T            # [out, tap*in + c]
+    y = segment_gemm(xb, b, seg, Cin, xb.shape[0]).reshape(N, H + 2, W + 2, Cout)
+    return y[:, 1:-1, 1:-1]
+
+
+def conv3x3_dx_segments(dy, w):
+    """dX[p] = sum_taps dY[p - off_tap] @ W[tap]^T: the SAME 9-segment GEMM over the zero-bordered dY with mirrored
+    offsets and B = [in, 9*out] (tap-major, W[tap] transposed)."""
+    N, H, W_, Cout = dy.shape
+    Cin = w.shape[2]
+    dyb = bordered(dy)
+    seg = [-((kh - 1) * (W_ + 2) + (kw - 1)) for kh in range(3) for kw in range(3)]
+    b = np.concatenate([w[kh, kw] for kh in range(3) for kw in range(3)], axis=1)   # [in, 9*out]
+    dx = segment_gemm(dyb, b, seg, Cout, dyb.shape[0]).reshape(N, H + 2, W_ + 2, Cin)
+    return dx[:, 1:-1, 1:-1]
+
+
+def conv3x3_dw_shifted(x, dy):
+    """dW[tap] = X_bordered[m + off_tap]^T dY_bordered[m], summed over all bordered rows m (the zero borders of dY kill
+    the rows where the shifted read would wrap): nine calls of the split-K weight-gradient kernel with a row offset."""
+    N, H, W_, Cin = x.shape
+    Cout = dy.shape[-1]
+    xb, dyb = bordered(x).astype(np.float64), bordered(dy).astype(np.float64)
+    R = xb.shape[0]
+    dw = np.zeros((3, 3, Cin, Cout))
+    for kh in range(3):
+        for kw in range(3):
+            off = (kh - 1) * (W_ + 2) + (kw - 1)
+            idx = np.arange(R) + off
+            ok = (idx >= 0) & (idx < R)
+            xs = np.zeros_like(xb)
+            xs[ok] = xb[idx[ok]]
+            dw[kh, kw] = xs.T @ dyb
+    return dw
