@@ -53,3 +53,23 @@ def test_conv3x3_backward_on_the_bordered_layout():
     dw = bf.conv3x3_dw_shifted(x.detach().numpy(), dy.numpy())
     assert np.abs(dx - x.grad.numpy()).max() < 1e-10
     assert np.abs(dw - w.grad.numpy()).max() < 1e-10
+
+
+def test_multiview_pooling_backward_closed_form():
+    rng = np.random.default_rng(3)
+    for valid in ([True, True, False, True], [False, True, False, False]):
+        V, D = 4, 6
+        valid = np.array(valid)
+        f = torch.tensor(rng.standard_normal((V, D)), dtype=torch.float64, requires_grad=True)
+        s = torch.tensor(rng.standard_normal(V) * 2, dtype=torch.float64, requires_grad=True)
+        vm = torch.tensor(valid)
+        mx = torch.clamp(torch.where(vm, s, torch.tensor(-np.inf, dtype=torch.float64)).max(), min=0.0).detach()
+        e = torch.where(vm, torch.exp(s - mx), torch.zeros((), dtype=torch.float64))
+        w = e / e.sum()
+        mean = (w[:, None] * f).sum(0)
+        var = (w[:, None] * (f - mean) ** 2).sum(0)
+        smax = torch.where(vm, s, torch.tensor(-np.inf, dtype=torch.float64)).max()
+        dmean, dvar, dsmax = rng.standard_normal(D), rng.standard_normal(D), float(rng.standard_normal())
+        ((mean * torch.tensor(dmean)).sum() + (var * torch.tensor(dvar)).sum() + smax * dsmax).backward()
+        df, ds = bf.pool_multiview_backward(f.detach().numpy(), s.detach().numpy(), valid, dmean, dvar, dsmax)
+        assert np.abs(df - f.grad.numpy()).max() < 1e-10 and np.abs(ds - s.grad.numpy()).max() < 1e-10

@@ -107,3 +107,28 @@ def conv3x3_dw_shifted(x, dy):
             xs[ok] = xb[idx[ok]]
             dw[kh, kw] = xs.T @ dyb
     return dw
+
+
+def pool_multiview_backward(feats, scores, valid, dmean, dvar, dsmax):
+    """Backward of the weighted branch of pool_multiview_features (streetview_encoder.py:156-177) for ONE voxel:
+    feats [V,D], scores [V], valid [V] (at least one valid) -> d feats [V,D], d scores [V].
+      w = softmax over the valid views;  mean = sum w f;  var = sum w (f - mean)^2;  smax = max valid s
+      d f_k = w_k dmean + 2 w_k (f_k - mean) dvar          (d var / d mean = -2 sum w (f - mean) = 0)
+      d w_k = f_k . dmean + (f_k - mean)^2 . dvar
+      d s_k = w_k (d w_k - sum_j w_j d w_j) + [k = argmax] dsmax
+    The lift's backward kernel evaluates this per (voxel, view) from the gather records of the forward pass and
+    scatter-adds d f_k through the four bilinear tap weights into the feature maps."""
+    f, s = feats.astype(np.float64), scores.astype(np.float64)
+    v = valid.astype(bool)
+    mx = max(0.0, s[v].max())                        # jax.nn.softmax(where=, initial=0)
+    e = np.where(v, np.exp(s - mx), 0.0)
+    w = e / e.sum()
+    mean = (w[:, None] * f).sum(0)
+    df = w[:, None] * dmean[None] + 2 * w[:, None] * (f - mean) * dvar[None]
+    dw = (f * dmean[None]).sum(-1) + ((f - mean) ** 2 * dvar[None]).sum(-1)
+    ds = w * (dw - (w * dw).sum())
+    k = int(np.argmax(np.where(v, s, -np.inf)))
+    ds[k] += dsmax
+    df[~v] = 0
+    ds[~v] = 0
+    return df, ds
