@@ -54,3 +54,23 @@ def test_ops_refuse_cpu_tensors():
     a = torch.zeros((128, 64), dtype=torch.bfloat16)
     with pytest.raises(_lib.SnapB200Error):
         ops.gemm(a, a, torch.zeros((128, 128)))
+
+
+def test_plain_c_client(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 program with nothing but include/snapb200.h and dlopen binds and calls it
+    (no Python, no torch); the library itself links only the C/C++ runtime (the CUDA runtime is linked statically)."""
+    import shutil
+    import subprocess
+    from snap_b200 import _lib
+    _lib.lib()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "abi_client"
+    src = os.path.join(ROOT, "tests", "c", "abi_client.c")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-ldl", "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe), str(_lib._LIB_PATH)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "null operand" in res.stdout and "multiple of 8" in res.stdout and res.stdout.strip().endswith("ok")
+    deps = subprocess.run(["ldd", str(_lib._LIB_PATH)], capture_output=True, text=True).stdout
+    assert "torch" not in deps and "python" not in deps
