@@ -107,3 +107,64 @@ def test_head_gradient_mean_world_size_2():
     g0, g1 = torch.Generator().manual_seed(100), torch.Generator().manual_seed(101)
     a, b = torch.randn((128, 128), generator=g0), torch.randn((128, 128), generator=g1)
     assert torch.allclose(torch.from_numpy(res[0][2]["Dense_0"]["kernel"]), (a + b) / 2, atol=1e-6)
+
+
+def _dp_case():
+    """Deterministic inputs of the DP-equivalence test: 4 scenes, MLP head, labels."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    B, G = 4, 8
+    p = {f"Dense_{i}": {"kernel": (rng.standard_normal((16, 16 if i < 2 else 12)) * 0.3).astype(np.float32),
+                        "bias": (rng.standard_normal(16 if i < 2 else 12) * 0.1).astype(np.float32)} for i in range(3)}
+    feats = rng.standard_normal((B, G, G, 16)).astype(np.float32)
+    valid = rng.random((B, G, G)) < 0.8
+    la, le = rng.integers(0, 5, (B, G, G)), rng.integers(0, 4, (B, G, G))
+    va = rng.random((B, G, G)) < 0.9
+    mi = rng.random((B, G, G, 3)) < 0.2
+    return p, feats, valid, la, va, le, mi
+
+
+def _dp_grads(sl):
+    import numpy as np
+    import torch
+    from oracle import semantic_net as osn
+    p, feats, valid, la, va, le, mi = _dp_case()
+    tp = {k: {n: torch.from_numpy(v[n]).requires_grad_(True) for n in v} for k, v in p.items()}
+    logits = osn.mlp_head_forward_torch(torch.from_numpy(feats[sl]), valid[sl], tp)
+    loss, _ = osn.total_loss_torch(logits, la[sl], va[sl], le[sl], mi[sl], valid[sl], 5, 4)
+    loss.backward()
+    return {k: {n: t.grad.clone() for n, t in v.items()} for k, v in tp.items()}
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snap_b200 import parallel
+    per = 4 // world
+    grads = _dp_grads(slice(rank * per, (rank + 1) * per))     # this rank's scenes (trainer.py:452-464 shards the batch)
+    parallel.pmean_tree(grads)                                 # trainer.py:231-234
+    q.put((rank, {k: {n: t.numpy().copy() for n, t in v.items()} for k, v in grads.items()}))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_data_parallel_step_equivalence_world_size_2():
+    """the mean over ranks of the per-shard gradients (2 ranks x 2 scenes) equals the gradient of the whole
+    batch (1 x 4 scenes): the loss is a mean of per-example losses (trainer.py:221) and shards are equally sized."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=150) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    full = _dp_grads(slice(0, 4))
+    for k in full:
+        for n in full[k]:
+            ref = full[k][n].numpy()
+            for r in range(2):
+                assert np.abs(res[r][1][k][n] - ref).max() <= 1e-6 * (1 + np.abs(ref).max()), (k, n)
