@@ -73,3 +73,16 @@ def test_multiview_pooling_backward_closed_form():
         ((mean * torch.tensor(dmean)).sum() + (var * torch.tensor(dvar)).sum() + smax * dsmax).backward()
         df, ds = bf.pool_multiview_backward(f.detach().numpy(), s.detach().numpy(), valid, dmean, dvar, dsmax)
         assert np.abs(df - f.grad.numpy()).max() < 1e-10 and np.abs(ds - s.grad.numpy()).max() < 1e-10
+
+
+def test_correlation_backward_as_two_correlations():
+    rng = np.random.default_rng(4)
+    R, G, D = 3, 5, 4
+    q = torch.tensor(rng.standard_normal((R, G, G, D)), dtype=torch.float64, requires_grad=True)
+    m = torch.tensor(rng.standard_normal((G, G, D)), dtype=torch.float64, requires_grad=True)
+    m_pad = torch.nn.functional.pad(m.permute(2, 0, 1)[None], (G - 1, G - 1, G - 1, G - 1), mode="replicate")
+    S = torch.nn.functional.conv2d(m_pad, q.permute(0, 3, 1, 2))[0]                  # [R, 2G-1, 2G-1]
+    dS = torch.tensor(rng.standard_normal(S.shape), dtype=torch.float64)
+    S.backward(dS)
+    dq, dm = bf.xcorr_backward(q.detach().numpy(), m.detach().numpy(), dS.numpy())
+    assert np.abs(dq - q.grad.numpy()).max() < 1e-10 and np.abs(dm - m.grad.numpy()).max() < 1e-10

@@ -132,3 +132,30 @@ def pool_multiview_backward(feats, scores, valid, dmean, dvar, dsmax):
     df[~v] = 0
     ds[~v] = 0
     return df, ds
+
+
+def xcorr_backward(q, m, dS):
+    """Backward of template_matching's score volume (pose_exhaustive_voting.py:72-104, before masking / normalisation):
+    S_r[u,v] = sum_{i,j,d} q_r[i,j,d] m_pad[u+i, v+j, d] with the edge-padded map m_pad [(3G-2)^2, D].
+      dq_r[i,j,d]    = sum_{u,v} dS_r[u,v] m_pad[u+i, v+j, d]     -> a correlation of m_pad with the (2G-1)^2 'template' dS_r:
+                        the forward's sliding-window kernel with the roles (template rows <-> shifts) exchanged
+      dm_pad[a,b,d]  = sum_r sum_{i,j} dS_r[a-i, b-j] q_r[i,j,d]   -> a full convolution = correlation of the zero-padded dS_r
+                        with the flipped templates, summed over r (one GEMM with K = R * G^2)
+      dm             = fold of dm_pad through the edge padding (every padded cell adds to the map cell it replicates).
+    q [R,G,G,D], m [G,G,D], dS [R,2G-1,2G-1] -> dq [R,G,G,D], dm [G,G,D]."""
+    R, G, _, D = q.shape
+    U = 2 * G - 1
+    P = 3 * G - 2
+    idx = np.clip(np.arange(P) - (G - 1), 0, G - 1)          # padded row/col -> map row/col (jnp.pad mode='edge')
+    m_pad = m[idx][:, idx].astype(np.float64)
+    dq = np.zeros((R, G, G, D))
+    for i in range(G):
+        for j in range(G):
+            dq[:, i, j] = np.einsum("ruv,uvd->rd", dS, m_pad[i:i + U, j:j + U])
+    dm_pad = np.zeros((P, P, D))
+    for i in range(G):
+        for j in range(G):
+            dm_pad[i:i + U, j:j + U] += np.einsum("ruv,rd->uvd", dS, q[:, i, j].astype(np.float64))
+    dm = np.zeros((G, G, D))
+    np.add.at(dm, (idx[:, None], idx[None, :]), dm_pad)
+    return dq, dm
