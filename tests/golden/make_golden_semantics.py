@@ -45,6 +45,18 @@ for tag, (f1, f2) in {"plain": (None, None), "bal": (fa, fo)}.items():
     nll, m = sn.binary_crossentropy_metrics(logits_i, mi, valid, indep, f2, namespace="indep")
     d[f"i_nll_{tag}"], d[f"i_recall_{tag}"] = nll, np.stack([m[f"recall/{c}"] for c in indep], -1)
     d[f"i_recall_avg_{tag}"] = m["recall/average/indep"]
+# ---- label preparation (:254-298) through the reference's own methods on a stand-in `self` ---------------------------
+import types as pytypes  # noqa: E402
+gt_classes = ("road", "crosswalk", "sidewalk", "terrain", "building", "fence", "pole", "tree", "traffic_sign",
+              "traffic_light", "street_light")
+fake = pytypes.SimpleNamespace(
+    gt_indices={c: i for i, c in enumerate(gt_classes)},
+    config=pytypes.SimpleNamespace(area_classes=area, object_classes_exclusive=excl[:-1], object_classes_independent=indep))
+fake._create_exclusive_labels = lambda *a, **k: sn.SemanticNetModel._create_exclusive_labels(fake, *a, **k)
+gt_masks = rng.random((B, H, W, len(gt_classes))) < 0.25
+lab_a, val_a = sn.SemanticNetModel.create_area_labels(fake, gt_masks)
+lab_e, m_i = sn.SemanticNetModel.create_object_labels(fake, gt_masks)
+d.update(gt_masks=gt_masks, lab_area=lab_a, valid_area=val_a, lab_excl=lab_e, masks_indep=m_i)
 d["w_area"] = sn.balancing_weights(dict(fa), area)
 wp, wn = sn.balancing_weights(dict(fo), indep, binary=True)
 d["w_pos"], d["w_neg"] = wp, wn

@@ -78,3 +78,15 @@ def test_torch_loss_restatement_equals_numpy_oracle():
         mean, total = osn.total_loss_torch(torch.from_numpy(logits), la, va, le, mi, bev_valid, len(AREA), len(EXCL), *w)
         close(total.numpy(), ol["total"])
         assert abs(float(mean) - float(ol["total"].mean())) < 1e-5
+
+
+def test_label_preparation_matches_the_reference_methods():
+    """create_area_labels / create_object_labels (semantic_net.py:254-298) of the reference, run on a stand-in `self`."""
+    d = load()
+    gt = AREA[2:3] + AREA[0:1] + AREA[1:2] + AREA[3:] + EXCL[:-1] + INDEP    # road, crosswalk, sidewalk, terrain, building, ...
+    la, va = osn.create_exclusive_labels(d["gt_masks"], gt, AREA)
+    assert np.array_equal(la, d["lab_area"]) and np.array_equal(va, d["valid_area"])
+    le, _ = osn.create_exclusive_labels(d["gt_masks"], gt, EXCL[:-1], add_void=True)
+    assert np.array_equal(le, d["lab_excl"]) and (le == 3).any()
+    gi = {c: i for i, c in enumerate(gt)}
+    assert np.array_equal(d["gt_masks"][..., [gi[c] for c in INDEP]], d["masks_indep"])
