@@ -106,7 +106,7 @@ def run_reference(args, rank: int, world: int):
     cores = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
         cpu_reference_tile(0, cores)
-    ts = [cpu_reference_tile(1 + i, cores) for i in range(max(1, min(args.steps, 3)))]
+    ts = [cpu_reference_tile(1 + i, cores) for i in range(max(1, min(args.steps, 2)))]   # bounded sample: ~1 min per tile
     sec = float(np.mean(ts))
     val = 1.0 / sec
     line = {"metric": "neural-map tiles/sec", "value": val, "unit": "tiles/s", "n_gpus": args.gpus,
