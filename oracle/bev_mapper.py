@@ -103,8 +103,9 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
                xyz: np.ndarray, fusion_params: Dict, feature_dim: int = 128, top_k: int = 4,
                depth_min_max=(1.0, 32.0), rd: Callable = _id, chunk: int = 1 << 16,
                max_view_distance: Optional[float] = None, debug: Optional[Dict] = None,
-               add_minmax: bool = False, use_variance: bool = True):
-    """streetview_encoder.py:232-286 for one scene, chunked over voxels.
+               add_minmax: bool = False, use_variance: bool = True, threads: int = 1):
+    """streetview_encoder.py:232-286 for one scene, chunked over voxels (`threads` > 1: chunks on a thread pool, used by
+    the timed CPU baseline of bench.py so that the lift uses the host cores like the torch-CPU encoder does).
 
     f_proj_images [V,Hf,Wf,feature_dim+S] = proj_mlp output; camera ALREADY scaled by 1/stride (:224).
     Returns f_grid [X,Y,Z,D], valid [X,Y,Z], and per-voxel debug (vis [N,V], p2d [N,V,2]); with view selection
@@ -114,15 +115,13 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
     grid_shape = xyz.shape[:-1]
     pts_all = xyz.reshape(-1, 3)
     V = f_proj_images.shape[0]
-    outs, valids, vis_all, p2d_all = [], [], [], []
-    for s in range(0, len(pts_all), chunk):
+
+    def one_chunk(s):
         pts = pts_all[s:s + chunk]
         p2d, vis, depth, _ = sv.project_points_to_views(t_view2scene, camera, pts)
-        min_dist = None
+        min_dist, idx = None, None
         if top_k and V > top_k:  # :241-249
             idx, min_dist = sv.view_selection(pts, t_view2scene, vis, top_k)
-            if debug is not None:
-                debug.setdefault("view_indices", []).append(idx)
             p2d, vis, depth = (np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
                                for a in (p2d, vis, depth))
             f_proj = sv.interpolate_views_selective(f_proj_images, p2d, idx, cast=rdn)
@@ -134,11 +133,26 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
         stats, valid = sv.pool_multiview_features(feats, vis, scores, add_minmax, use_variance, rd=rdn)  # :268-274
         if max_view_distance is not None and min_dist is not None:  # :275-279
             valid = valid & (min_dist <= F(max_view_distance))
-        if debug is not None:
-            debug.setdefault("stats", []).append(stats)
         f = layers.mlp(rdn(stats), fusion_params, rd=rdn)  # :281
         f = np.where(valid[..., None], f, F(0))  # :282
-        outs.append(f.astype(F)); valids.append(valid); vis_all.append(vis); p2d_all.append(p2d)
+        return f.astype(F), valid, vis, p2d, idx, stats
+
+    if threads > 1:   # enough chunks to keep every thread busy (results do not depend on the chunking)
+        chunk = max(4096, min(chunk, -(-len(pts_all) // (2 * threads))))
+    starts = list(range(0, len(pts_all), chunk))
+    if threads > 1 and len(starts) > 1:   # chunks are independent; NumPy releases the GIL inside its kernels
+        import concurrent.futures as cf
+        with cf.ThreadPoolExecutor(max_workers=min(threads, len(starts))) as ex:
+            results = list(ex.map(one_chunk, starts))   # order preserved: identical to the sequential result
+    else:
+        results = [one_chunk(s) for s in starts]
+    outs, valids, vis_all, p2d_all = [], [], [], []
+    for f, valid, vis, p2d, idx, stats in results:
+        if debug is not None:
+            if idx is not None:
+                debug.setdefault("view_indices", []).append(idx)
+            debug.setdefault("stats", []).append(stats)
+        outs.append(f); valids.append(valid); vis_all.append(vis); p2d_all.append(p2d)
     f_grid = np.concatenate(outs).reshape(*grid_shape, -1)
     valid = np.concatenate(valids).reshape(grid_shape)
     return f_grid, valid, np.concatenate(vis_all), np.concatenate(p2d_all)
@@ -154,7 +168,7 @@ def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = 
 
 def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callable = _id,
                        scene_z_offset: float = 4.0, scene_z_height: float = 12.0, top_k: int = 4,
-                       return_volume: bool = False) -> Dict:
+                       return_volume: bool = False, threads: int = 1) -> Dict:
     """bev_mapper.py:254-296 for a batch (inference, train=False).
 
     data: 'images' f32 [B,V,H,W,3]; 'camera' geometry.Camera with fields [B,V,2];
@@ -176,7 +190,7 @@ def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callabl
         f_proj = layers.mlp(f_img, svp["proj_mlp"], apply_input_activation=True, rd=rdn)  # :229
         T = geometry.Transform3D(R=data["T_view2scene"].R[b], t=data["T_view2scene"].t[b])
         xyz, z_off = build_xyz_query(grid, T.t, scene_z_offset, scene_z_height)
-        f_grid, valid, vis, p2d = lift_scene(f_proj, cam, T, xyz, svp["fusion_mlp"], top_k=top_k, rd=rd)
+        f_grid, valid, vis, p2d = lift_scene(f_proj, cam, T, xyz, svp["fusion_mlp"], top_k=top_k, rd=rd, threads=threads)
         plane, pvalid = vertical_pooling_max(f_grid, valid)
         item = {"f_proj_images": f_proj, "feature_plane": plane, "valid": pvalid, "vis": vis, "p2d": p2d,
                 "z_offset": z_off, "pyramid": [f.numpy() for f in feats]}
