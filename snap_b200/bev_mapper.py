@@ -133,15 +133,15 @@ class BEVMapper:
                 if not all(np.array_equal(xy[0], xy[b]) for b in range(1, len(xy))):
                     raise NotImplementedError("per-example xy_bev is not built (BEVLocalizer repeats one frustum, bev_localizer.py:140)")
                 xy = xy[0]
-            key = ("xy_bev", id(data["xy_bev"]))
-            if key not in self._cache:
-                if np.array_equal(xy[..., 0], np.broadcast_to(xy[:, :1, 0], xy.shape[:2])) and \
-                        np.array_equal(xy[..., 1], np.broadcast_to(xy[:1, :, 1], xy.shape[:2])):
-                    self._cache[key] = (np.ascontiguousarray(xy[:, 0, 0]), np.ascontiguousarray(xy[0, :, 1]), None, data["xy_bev"])
-                else:           # arbitrary BEV points (e.g. the field-of-view filtered query frustum, [N,1,2])
-                    self._cache[key] = (np.ascontiguousarray(xy[..., 0].reshape(-1)), np.ascontiguousarray(xy[..., 1].reshape(-1)),
-                                        tuple(xy.shape[:2]), data["xy_bev"])
-            xs, ys, xy_shape, _ = self._cache[key]
+            if data.get("xy_bev_cache", True):
+                # a persistent point set (BEVLocalizer.q_xy_p): analysed once, and the SAME host arrays are handed out
+                # so that the lift's device copy is reused (the entry keeps the key object alive, so its id is unique)
+                key = ("xy_bev", id(data["xy_bev"]))
+                if key not in self._cache:
+                    self._cache[key] = (*self._xy_layout(xy), data["xy_bev"])
+                xs, ys, xy_shape, _ = self._cache[key]
+            else:
+                xs, ys, xy_shape = self._xy_layout(xy)
         z_offset = data.get("z_offset")
         if z_offset is None:
             cam_h = np.median(t[..., -1].astype(F), axis=-1).astype(F)                      # :171
@@ -151,11 +151,42 @@ class BEVMapper:
         zs = ((base[None] + z_offset[:, None]).astype(F) + F(self.grid.cell_size / 2)).astype(F)  # :188-192
         if xy_shape is not None:
             data["xy_shape"] = xy_shape
+        if xy is not None:
+            data["xy_custom"] = True     # the lift re-uploads its (x, y) tables when these host arrays change
         return xs, ys, zs
+
+    @staticmethod
+    def _xy_layout(xy: np.ndarray):
+        """[X,Y,2] BEV points -> (xs, ys, None) if they form a separable grid, else per-column (xs, ys, (X, Y))."""
+        if np.array_equal(xy[..., 0], np.broadcast_to(xy[:, :1, 0], xy.shape[:2])) and \
+                np.array_equal(xy[..., 1], np.broadcast_to(xy[:1, :, 1], xy.shape[:2])):
+            return np.ascontiguousarray(xy[:, 0, 0]), np.ascontiguousarray(xy[0, :, 1]), None
+        # arbitrary BEV points (e.g. the field-of-view filtered query frustum, [N,1,2])
+        return (np.ascontiguousarray(xy[..., 0].reshape(-1)), np.ascontiguousarray(xy[..., 1].reshape(-1)),
+                tuple(xy.shape[:2]))
+
+    def split_xyz_query(self, data: Dict):
+        """An explicit `data['xyz_query']` [B,X,Y,Z,3] (`bev_mapper.py:162,193-196`) in the layout the kernels take:
+        the points of a voxel column share (x, y) and every column uses the same z levels per example -- which is how
+        the reference itself builds the tensor (`:187-196`).  Anything else is refused."""
+        xyz = np.asarray(data["xyz_query"], dtype=F)
+        if xyz.ndim != 5 or xyz.shape[-1] != 3:
+            raise ValueError("xyz_query must be [B,X,Y,Z,3]")
+        xy, z = xyz[..., :2], xyz[..., 2]
+        if not (np.array_equal(xy, np.broadcast_to(xy[:, :, :, :1], xy.shape))
+                and np.array_equal(z, np.broadcast_to(z[:, :1, :1], z.shape))):
+            raise NotImplementedError("xyz_query must be column-structured: (x, y) per BEV column, z levels per example")
+        sub = dict(data, xy_bev=xy[:, :, :, 0], xy_bev_cache=False, z_offset=np.zeros(len(xyz), F))
+        xs, ys, _ = self.build_xyz_grid(sub)
+        if "xy_shape" in sub:
+            data["xy_shape"] = sub["xy_shape"]
+        data["xy_custom"] = True
+        return xs, ys, np.ascontiguousarray(z[:, 0, 0])
 
     def encode_streetview(self, params, data, train, is_query, debug=False) -> Dict:
         if "xyz_query" in data and "xyz_grid" not in data:
-            raise NotImplementedError("explicit non-separable xyz_query (BEVLocalizer frustum) is a 'next' row")
+            data = dict(data)
+            data["xyz_grid"] = self.split_xyz_query(data)          # precomputed data['xyz_query'] (bev_mapper.py:162)
         if "xyz_grid" not in data:
             data = dict(data)
             data["xyz_grid"] = self.build_xyz_grid(data)

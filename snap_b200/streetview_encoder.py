@@ -202,9 +202,10 @@ class StreetViewEncoder:
         hf, wf = enc_plan.cropped_shapes()[-1]
         stride = enc_plan.strides[-1]
         buf = self._buffers(dev, B, V, H, W, hf, wf, X, Y, Z)
-        if buf["xs"] is None or (paired and buf.get("xs_src") is not xs):
+        custom = bool(paired or data.get("xy_custom"))   # data['xy_bev'] / data['xyz_query'] instead of the mapper's grid
+        if buf["xs"] is None or (custom and buf.get("xs_src") is not xs) or (not custom and buf.get("xs_custom")):
             buf["xs"], buf["ys"] = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
-            buf["xs_src"] = xs
+            buf["xs_src"], buf["xs_custom"] = xs, custom
         capturing = torch.cuda.is_current_stream_capturing()
         slot = data.get("staging_slot")
         if slot is None:

@@ -180,3 +180,30 @@ def test_recover_dense_feature_plane():
     ij = np.floor(q / F(0.2)).astype(int)
     assert np.array_equal(dense.features[ij[:, 0], ij[:, 1]].numpy(), feats[:, 0].numpy())
     assert not dense.features[0, 79].any() and not dense.valid[0, 79]        # far corner: |angle| > 36 degrees
+
+
+def test_explicit_xyz_query_is_split_into_the_kernel_layout():
+    """data['xyz_query'] (bev_mapper.py:162): the tensor the reference builds (:187-196) decomposes exactly into the
+    (xs, ys, zs) the kernels take; a tensor without column structure is refused."""
+    import pytest
+    G = 8
+    data = synthetic.make_tile(3, 2, (96, 128), G, batch=2)
+    mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), types.Grid2D((G, G), 0.2))
+    xs, ys, zs = mapper.build_xyz_grid(dict(data))
+    xyz = np.zeros((2, G, G, zs.shape[1], 3), F)
+    xyz[..., 0] = xs[None, :, None, None]
+    xyz[..., 1] = ys[None, None, :, None]
+    xyz[..., 2] = zs[:, None, None, :]
+    d = dict(data, xyz_query=xyz)
+    xs2, ys2, zs2 = mapper.split_xyz_query(d)
+    assert np.array_equal(xs2, xs) and np.array_equal(ys2, ys) and np.array_equal(zs2, zs) and "xy_shape" not in d
+    # arbitrary (x, y) per column: paired layout
+    xyz2 = xyz.copy()
+    xyz2[:, 3, 4, :, 0] += F(0.05)
+    d = dict(data, xyz_query=xyz2)
+    xs3, ys3, _ = mapper.split_xyz_query(d)
+    assert d["xy_shape"] == (G, G) and xs3.shape == (G * G,) and xs3[3 * G + 4] == xyz2[0, 3, 4, 0, 0]
+    bad = xyz.copy()
+    bad[0, 1, 1, 5, 2] += F(0.1)          # one column with its own z level
+    with pytest.raises(NotImplementedError):
+        mapper.split_xyz_query(dict(data, xyz_query=bad))
