@@ -324,6 +324,7 @@ def install(reference_root: str) -> None:
     jax.random.choice = random_choice
     jnn.log_softmax = log_softmax
     jnn.relu = lambda x: np.maximum(x, 0)
+    jnn.log_sigmoid = lambda x: (-(np.maximum(-np.asarray(x), 0) + np.log1p(np.exp(-np.abs(np.asarray(x)))))).astype(np.asarray(x).dtype)
     jnn.sigmoid = lambda x: (1 / (1 + np.exp(-np.asarray(x)))).astype(np.asarray(x).dtype)
     # optax (published definitions): logsumexp(logits) - logits[label]; -y log_sigmoid(x) - (1 - y) log_sigmoid(-x)
     optax = types.ModuleType("optax")

@@ -107,3 +107,19 @@ def test_exhaustive_voting():
     tf = opv.exhaustive_index_to_tfm(np.array([3, 14, 9]), grid, 8)
     close(tf.angle, d["tfm_angle"], 1e-6); close(tf.t, d["tfm_t"], 1e-5)
     close(opv.exhaustive_tfm_to_index(tf, grid, 8), d["index_back"], 1e-5)
+
+
+@pytest.mark.parametrize("mode", ["max", "sum", "mean", "softmax", "weighted"])
+def test_vertical_pooling_modes(mode):
+    """oracle.bev_mapper.vertical_pooling vs the reference's own VerticalPooling.__call__ (tests/golden/make_golden_pooling.py)."""
+    from oracle import bev_mapper as obm
+    d = load("vertical_pooling")
+    params = {"confidence_head": {"kernel": d["head_kernel"], "bias": d["head_bias"]}}
+    out = obm.vertical_pooling(d["feats"], d["valid"], mode, params)
+    plane, pvalid = out["plane"]
+    assert np.array_equal(pvalid, d[f"{mode}_valid"]) and not pvalid[0] and not plane[0].any()
+    close(plane, d[f"{mode}_plane"])
+    if mode in ("softmax", "weighted"):
+        close(out["scores"], d[f"{mode}_scores"])
+        close(out["weights"], d[f"{mode}_weights"])
+        assert not out["weights"][~d["valid"]].any()
