@@ -123,3 +123,24 @@ def test_vertical_pooling_modes(mode):
         close(out["scores"], d[f"{mode}_scores"])
         close(out["weights"], d[f"{mode}_weights"])
         assert not out["weights"][~d["valid"]].any()
+
+
+@pytest.mark.parametrize("tag", ["allviews", "select"])
+def test_lift_scene_vs_reference_streetview_encoder_call(tag):
+    """oracle.bev_mapper.lift_scene (+ proj MLP) against the reference's OWN StreetViewEncoder.__call__
+    (streetview_encoder.py:217-287) run under the stand-in (tests/golden/make_golden_sve.py): the whole lift orchestration,
+    all-views path and view-selection path with max_view_distance."""
+    from oracle import bev_mapper as obm
+    d = load("sve_call_" + tag)
+    tree = lambda pre: {n: {"kernel": d[f"{pre}_{n}_kernel"], "bias": d[f"{pre}_{n}_bias"]}
+                        for n in ("Dense_0", "Dense_1") if f"{pre}_{n}_kernel" in d}
+    f_proj = layers.mlp(d["f_img"][0], tree("proj"), apply_input_activation=True)          # :228-230
+    close(f_proj[..., 8:], d["scores_images"][0])
+    cam = geometry.Camera(wh=d["wh"][0], f=d["f"][0], c=d["c"][0]).scale(np.asarray([0.25, 0.25], F))   # :224
+    T = geometry.Transform3D(R=d["R"][0], t=d["t"][0])
+    mvd = float(d["max_view_distance"])
+    f_grid, valid, _, _ = obm.lift_scene(f_proj, cam, T, d["xyz"][0], tree("fusion"), feature_dim=8, top_k=4,
+                                         max_view_distance=None if mvd < 0 else mvd)
+    assert np.array_equal(valid, d["valid"][0].astype(bool)) and 0.3 < valid.mean() < 0.95
+    close(f_grid, d["volume"][0], tol=5e-5)
+    assert not f_grid[~valid].any()
