@@ -168,29 +168,36 @@ def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = 
 
 def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callable = _id,
                        scene_z_offset: float = 4.0, scene_z_height: float = 12.0, top_k: int = 4,
-                       return_volume: bool = False, threads: int = 1) -> Dict:
+                       return_volume: bool = False, threads: int = 1, precomputed: Optional[Dict] = None,
+                       feature_dim: int = 128) -> Dict:
     """bev_mapper.py:254-296 for a batch (inference, train=False).
 
     data: 'images' f32 [B,V,H,W,3]; 'camera' geometry.Camera with fields [B,V,2];
           'T_view2scene' Transform3D R [B,V,3,3], t [B,V,3]; optional 'rasters' {'rgb' [B,G,G,3]}.
     params: Flax tree under 'bev_mapper'  with numpy leaves.
+    precomputed (tests): {'sv_features' [B,V,Hf,Wf,C], 'sv_stride' (si, sj), 'aerial' [B,G,G,C]} replaces the image
+    encoders (data['image_feature_pyr'] of streetview_encoder.py:218 and the aerial encoder output).
     """
     rdn = np_rd(rd)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F))
     tt = lambda tree: {k: (tt(v) if isinstance(v, dict) else t(v)) for k, v in tree.items()}
-    B, V = data["images"].shape[:2]
+    B, V = (precomputed["sv_features"] if precomputed is not None else data["images"]).shape[:2]
     svp = params["streetview_encoder"]
     planes, valids, pred = [], [], {"streetview": []}
     for b in range(B):
-        feats, strides = image_encoder.image_encoder(t(data["images"][b]), tt(svp["image_encoder"]), False, rd)
-        f_img = feats[-1].numpy()
-        stride = strides[-1]
+        if precomputed is not None:
+            feats, f_img, stride = [], precomputed["sv_features"][b], precomputed["sv_stride"]
+        else:
+            feats, strides = image_encoder.image_encoder(t(data["images"][b]), tt(svp["image_encoder"]), False, rd)
+            f_img = feats[-1].numpy()
+            stride = strides[-1]
         cam = geometry.Camera(wh=data["camera"].wh[b], f=data["camera"].f[b], c=data["camera"].c[b])
         cam = cam.scale(np.asarray([1 / stride[1], 1 / stride[0]], dtype=F))  # :224 (i,j) -> (x,y)
         f_proj = layers.mlp(f_img, svp["proj_mlp"], apply_input_activation=True, rd=rdn)  # :229
         T = geometry.Transform3D(R=data["T_view2scene"].R[b], t=data["T_view2scene"].t[b])
         xyz, z_off = build_xyz_query(grid, T.t, scene_z_offset, scene_z_height)
-        f_grid, valid, vis, p2d = lift_scene(f_proj, cam, T, xyz, svp["fusion_mlp"], top_k=top_k, rd=rd, threads=threads)
+        f_grid, valid, vis, p2d = lift_scene(f_proj, cam, T, xyz, svp["fusion_mlp"], feature_dim=feature_dim, top_k=top_k, rd=rd,
+                                             threads=threads)
         plane, pvalid = vertical_pooling_max(f_grid, valid)
         item = {"f_proj_images": f_proj, "feature_plane": plane, "valid": pvalid, "vis": vis, "p2d": p2d,
                 "z_offset": z_off, "pyramid": [f.numpy() for f in feats]}
@@ -198,7 +205,11 @@ def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callabl
             item["feature_volume"], item["volume_valid"] = f_grid, valid
         pred["streetview"].append(item)
         planes_b, valids_b = [plane], [pvalid]
-        if "rasters" in data and "aerial_encoder" in params:
+        if precomputed is not None and "aerial" in precomputed:
+            aplane = precomputed["aerial"][b]
+            pred.setdefault("aerial", []).append(aplane)
+            planes_b.append(aplane); valids_b.append(np.ones(aplane.shape[:-1], bool))
+        elif "rasters" in data and "aerial_encoder" in params:
             afeats, _ = image_encoder.image_encoder(t(data["rasters"]["rgb"][b:b + 1]), tt(params["aerial_encoder"]), True, rd)
             aplane = afeats[-1].numpy()[0]
             pred.setdefault("aerial", []).append(aplane)

@@ -355,6 +355,7 @@ def install(reference_root: str) -> None:
                  "ml_collections.config_dict", "tensorflow_datasets", "tensorflow", "scenic", "clu"):
         mods[name] = _Permissive(name)
     mods["optax"] = optax
+    mods["flax.linen"].log_sigmoid = jnn.log_sigmoid
     mods["flax"].linen = mods["flax.linen"]
     mods["flax"].training = mods["flax.training"]
     mods["flax.training"].checkpoints = mods["flax.training.checkpoints"]

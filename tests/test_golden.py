@@ -144,3 +144,33 @@ def test_lift_scene_vs_reference_streetview_encoder_call(tag):
     assert np.array_equal(valid, d["valid"][0].astype(bool)) and 0.3 < valid.mean() < 0.95
     close(f_grid, d["volume"][0], tol=5e-5)
     assert not f_grid[~valid].any()
+
+
+def test_bev_mapper_forward_vs_reference_bevmapper_call():
+    """oracle.bev_mapper_forward (encoders bypassed) against the reference's OWN BEVMapper.__call__ chain
+    (bev_mapper.py:159-296 + StreetViewEncoder.__call__ + VerticalPooling.__call__) run under the stand-in
+    (tests/golden/make_golden_bevmapper.py): voxel grid from the median camera height, lift, vertical max, modality max
+    with the aerial plane, matching head, confidence."""
+    from oracle import bev_mapper as obm
+    d = load("bevmapper_call")
+    tree = lambda pre: {n: {"kernel": d[f"{pre}_{n}_kernel"], "bias": d[f"{pre}_{n}_bias"]}
+                        for n in ("Dense_0", "Dense_1") if f"{pre}_{n}_kernel" in d}
+    params = {"streetview_encoder": {"proj_mlp": tree("proj"), "fusion_mlp": tree("fusion")},
+              "matching_proj": {"kernel": d["Wm"], "bias": d["bm"]}}
+    data = {"camera": geometry.Camera(wh=d["wh"], f=d["f"], c=d["c"]), "T_view2scene": geometry.Transform3D(R=d["R"], t=d["t"])}
+    grid = grids.Grid2D((6, 6), float(d["cell"]))
+    pred = obm.bev_mapper_forward(data, params, grid, scene_z_offset=1.0, scene_z_height=1.6, feature_dim=8,
+                                  precomputed={"sv_features": d["f_img"], "sv_stride": (4.0, 4.0), "aerial": d["aerial"]})
+    for b in range(2):   # the voxel grid (bev_mapper.py:162-196): z offset = median camera height - scene_z_offset
+        xyz, _ = obm.build_xyz_query(grid, d["t"][b], 1.0, 1.6)
+        close(xyz, d["xyz"][b], tol=1e-6)
+        sv = pred["streetview"][b]
+        assert np.array_equal(sv["valid"], d["sv_valid"][b].astype(bool))
+        close(sv["feature_plane"], d["sv_plane"][b], tol=5e-5)
+    assert 0.3 < d["sv_valid"].mean() < 0.95
+    assert np.array_equal(pred["bev_features"]["valid"], d["bev_valid"].astype(bool)) and d["bev_valid"].all()
+    close(pred["bev_features"]["features"], d["bev_features"], tol=5e-5)
+    close(pred["bev_matching"]["features"], d["bev_matching"], tol=5e-5)
+    conf = obm.bev_confidence(pred["bev_features"]["features"], pred["bev_features"]["valid"],
+                              {"layers_0": {"kernel": d["wc"], "bias": d["bc"]}})
+    close(conf, d["bev_confidence"], tol=5e-5)
