@@ -322,6 +322,24 @@ def install(reference_root: str) -> None:
     jax.scipy, jax.lax, jax.nn = jsp, lax, jnn
     jax.random, jax.image, jax.tree_util = _Permissive("jax.random"), _Permissive("jax.image"), _Permissive("jax.tree_util")
     jax.random.choice = random_choice
+    def _split(rng, n=2):   # an object array so that vmap indexes it like the key array jax.random.split returns
+        keys = np.empty(n, dtype=object)
+        for i in range(n):
+            keys[i] = np.random.default_rng(int(rng.integers(1 << 62)))
+        return keys
+    jax.random.split = _split
+    lax.stop_gradient = lambda x: x
+
+    def tree_map(fn, *trees):
+        first = trees[0]
+        if _is_dca(first):
+            return type(first)(**{n: fn(*[getattr(t, n) for t in trees]) for n in first._fields})
+        if isinstance(first, dict):
+            return {k: tree_map(fn, *[t[k] for t in trees]) for k in first}
+        if isinstance(first, (list, tuple)):
+            return type(first)(tree_map(fn, *parts) for parts in zip(*trees))
+        return fn(*trees)
+    jax.tree_util.tree_map = tree_map
     jnn.log_softmax = log_softmax
     jnn.relu = lambda x: np.maximum(x, 0)
     jnn.log_sigmoid = lambda x: (-(np.maximum(-np.asarray(x), 0) + np.log1p(np.exp(-np.abs(np.asarray(x)))))).astype(np.asarray(x).dtype)

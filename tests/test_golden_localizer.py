@@ -102,3 +102,32 @@ def test_frustum_grid_and_loss():
         for k, key in enumerate(["loc/recall_samples_0.5m_1", "loc/recall_samples_1m_2", "loc/recall_samples_2m_4"]):
             assert abs(m[key] - d[f"rec{k}"][b]) <= 1e-6
         assert d["rec2"][b] > 0   # the fixture plants near-ground-truth samples
+
+
+def test_matching_block_vs_reference_bevlocalizer_call():
+    """oracle point_similarities + pose_scoring_many against the reference's OWN BEVLocalizer.__call__ (bev_localizer.py:131-218)
+    run under the stand-in on given BEV planes (tests/golden/make_golden_localizer_call.py): similarity normalisation
+    (1/num_valid or the masked soft-max of the query confidences), temperature, scoring with and without the out-of-bounds
+    mask, ground truth prepended, arg-max over the sampled poses."""
+    for tag in ("plain", "conf_mask"):
+        d = load("loc_call_" + tag)
+        B, N = d["vq"].shape[:2]
+        H, W = d["vm"].shape[1:]
+        grid = grids.Grid2D((H, W), float(d["cell"]))
+        gt_angle, gt_t = ope.transform2d_from_transform3d(d["gt_R"], d["gt_t"])
+        for b in range(B):
+            assert abs(d["samples_angle"][b, 0] - gt_angle[b]) < 1e-6 and np.array_equal(d["samples_t"][b, 0], gt_t[b])
+            sim, prob = ope.point_similarities(d["fq"][b, :, 0], d["vq"][b, :, 0], d["fm"][b], float(d["temperature"]), True,
+                                               d["conf"][b, :, 0] if bool(d["add_conf"]) else None)
+            sc = ope.pose_scoring_many(d["samples_angle"][b], d["samples_t"][b], sim, d["q_xy_p"][:, 0], d["vq"][b, :, 0],
+                                       d["vm"][b], grid, bool(d["mask_oob"]))
+            assert np.abs(sc - d["scores_poses"][b]).max() <= 2e-5 * (1 + np.abs(d["scores_poses"][b]).max()), (tag, b)
+            k = int(np.argmax(sc[1:]))
+            assert k == int(d["best_index"][b])
+            assert abs(d["samples_angle"][b, 1 + k] - d["best_angle"][b]) < 1e-7 and np.array_equal(d["samples_t"][b, 1 + k], d["best_t"][b])
+            # prob_points: every point's map sums to its weight (1 / num_valid, or its confidence soft-max weight)
+            w = prob.reshape(N, -1).sum(-1)
+            if bool(d["add_conf"]):
+                assert abs(w.sum() - 1) < 1e-5 and not w[~d["vq"][b, :, 0]].any()
+            else:
+                assert np.allclose(w, 1.0 / max(int(d["vq"][b].sum()), 1), rtol=1e-5)
