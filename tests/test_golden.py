@@ -174,3 +174,26 @@ def test_bev_mapper_forward_vs_reference_bevmapper_call():
     conf = obm.bev_confidence(pred["bev_features"]["features"], pred["bev_features"]["valid"],
                               {"layers_0": {"kernel": d["wc"], "bias": d["bc"]}})
     close(conf, d["bev_confidence"], tol=5e-5)
+
+
+def test_image_encoder_wrapper_vs_reference_call(monkeypatch):
+    """The wrapper logic of oracle.image_encoder.image_encoder (pad, level order, strides, crop) against the reference's OWN
+    ImageEncoder.__call__ (image_encoder.py:119-144) run with a stand-in encoder / identity decoder
+    (tests/golden/make_golden_image_encoder_call.py); the same stand-ins are patched into the oracle."""
+    d = load("image_encoder_call")
+
+    def pool(x, s):
+        B, H, W, C = x.shape
+        return x.reshape(B, H // s, s, W // s, s, C).mean((2, 4))
+    for tag, skip_root in (("sv_30x44", False), ("sv_64x32", False), ("aerial_20x24", True)):
+        base = 1 if skip_root else 4
+        monkeypatch.setattr(ores, "resnet_v2", lambda img, p, skip, rd, trace=None, base=base: [pool(img, base * 2 ** k) for k in range(4)])
+        monkeypatch.setattr(oie, "fpn_decoder", lambda feats, p, rd=None: feats)
+        params = {"encoder": {f"block{k + 1}": {} for k in range(4)}, "decoder": {}}
+        feats, strides = oie.image_encoder(torch.from_numpy(d[f"{tag}_image"]), params, skip_root)
+        assert len(feats) == 4
+        for k in range(4):
+            ref = d[f"{tag}_feat{k}"]
+            assert tuple(feats[k].shape) == ref.shape, (tag, k, feats[k].shape, ref.shape)
+            close(feats[k].numpy(), ref, tol=1e-5)   # stand-in pooling: torch vs NumPy summation order
+            assert tuple(float(x) for x in strides[k]) == tuple(float(x) for x in d[f"{tag}_stride{k}"])
