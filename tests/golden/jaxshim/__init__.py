@@ -62,6 +62,8 @@ class _Jnp(types.ModuleType):
     @staticmethod
     def _reduce(name):
         def f(a, *args, where=None, **kw):
+            if isinstance(kw.get("axis"), list):  # jax accepts a list of axes
+                kw["axis"] = tuple(kw["axis"])
             if where is not None:  # jax accepts any dtype as a mask
                 kw["where"] = np.asarray(where).astype(bool)
             return getattr(np, name)(a, *args, **kw)
@@ -308,7 +310,7 @@ def _Anything(name):
     return _A
 
 
-def install(reference_root: str) -> None:
+def install(reference_root: str, flax_modules: bool = False) -> None:
     """Register the stand-ins in sys.modules and the reference tree as bare packages (no __init__ execution)."""
     jax = types.ModuleType("jax")
     jax.numpy, jax.vmap, jax.jit, jax.checkpoint = jnp, vmap, jit, checkpoint
@@ -378,6 +380,9 @@ def install(reference_root: str) -> None:
     mods["flax"].training = mods["flax.training"]
     mods["flax.training"].checkpoints = mods["flax.training.checkpoints"]
     mods["ml_collections"].config_dict = mods["ml_collections.config_dict"]
+    if flax_modules:   # executable stand-ins for nn.Module / nn.Conv / ... (tests/golden/jaxshim/flaxshim.py)
+        from . import flaxshim
+        flaxshim.install(mods, jax)
     sys.modules.update(mods)
     import os
     for pkg in ("snap", "snap.models", "snap.utils", "snap.configs", "snap.data"):

@@ -197,3 +197,42 @@ def test_image_encoder_wrapper_vs_reference_call(monkeypatch):
             assert tuple(feats[k].shape) == ref.shape, (tag, k, feats[k].shape, ref.shape)
             close(feats[k].numpy(), ref, tol=1e-5)   # stand-in pooling: torch vs NumPy summation order
             assert tuple(float(x) for x in strides[k]) == tuple(float(x) for x in d[f"{tag}_stride{k}"])
+
+
+def _golden_encoder_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_encoder", os.path.join(G, "make_golden_encoder.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)      # only defines the seeded case builders (the reference is not needed here)
+    return mod
+
+
+def _tt(tree):
+    return {k: (_tt(v) if isinstance(v, dict) else torch.from_numpy(np.ascontiguousarray(v, dtype=F))) for k, v in tree.items()}
+
+
+@pytest.mark.parametrize("tag", ["sv", "aerial"])
+def test_image_encoder_vs_reference_modules(tag):
+    """oracle.image_encoder (ResNetV2 + FPN, street-view and aerial variants) against the reference's OWN ResNetV2 /
+    ResidualUnit / RootBlock / GroupNorm / StdConv / FPNDecoder / ImageEncoder modules executed under the jax + flax.linen
+    stand-ins (tests/golden/make_golden_encoder.py); parameters are re-created from the fixture's seeds."""
+    mod = _golden_encoder_module()
+    d = load("encoder_modules")
+    _, p, img, skip_root = mod.encoder_case(tag)
+    feats, strides = oie.image_encoder(torch.from_numpy(img), _tt(p), skip_root)
+    assert len(feats) == 4
+    for k, f in enumerate(feats):
+        ref = d[f"{tag}_feat{k}"]
+        assert tuple(f.shape) == ref.shape
+        close(f.numpy(), ref, tol=2e-4)      # fp32 conv summation order through ~20 layers with GroupNorm
+
+
+def test_resnet_stage_and_mlp_vs_reference_modules():
+    mod = _golden_encoder_module()
+    d = load("encoder_modules")
+    sp, x = mod.stage_case()
+    y = ores.resnet_stage(torch.from_numpy(x), _tt(sp), 1)
+    close(y.numpy(), d["stage_y"], tol=5e-5)
+    mp, xm = mod.mlp_case()
+    for act in (False, True):
+        close(layers.mlp(xm, mp, apply_input_activation=act), d[f"mlp_y{int(act)}"], tol=1e-5)
