@@ -153,6 +153,10 @@ class Sequential(Module):
     layers: list
 
     def __call__(self, x):
+        for i, layer in enumerate(self.layers):      # flax names the layers of a Sequential layers_<i> under it
+            if isinstance(layer, Module) and layer._params is None:
+                layer._parent = self
+                object.__setattr__(layer, "name", f"layers_{i}")
         for layer in self.layers:
             x = layer(x) if not isinstance(x, tuple) else layer(*x)
         return x
@@ -167,8 +171,38 @@ def image_resize(x, shape, method):
     return y.permute(0, 2, 3, 1).numpy()
 
 
+class ConfigDict(dict):
+    """ml_collections.ConfigDict subset: attribute access, nested dicts converted, lock() / placeholder."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in {**(d or {}), **kw}.items():
+            self[k] = ConfigDict(v) if isinstance(v, dict) and not isinstance(v, ConfigDict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def lock(self):
+        return self
+
+    def unlocked(self):
+        import contextlib
+        return contextlib.nullcontext(self)
+
+
 def install(mods, jax):
     """Replace the permissive flax stubs of jaxshim.install by this stand-in."""
+    mlc = types.ModuleType("ml_collections")
+    cd = types.ModuleType("ml_collections.config_dict")
+    cd.ConfigDict, cd.placeholder = ConfigDict, (lambda t: None)
+    mlc.ConfigDict, mlc.config_dict = ConfigDict, cd
+    mods["ml_collections"], mods["ml_collections.config_dict"] = mlc, cd
     nn = types.ModuleType("flax.linen")
     for k, v in dict(Module=Module, compact=compact, remat=remat, relu=relu, Conv=Conv, Dense=Dense, max_pool=max_pool,
                      Sequential=Sequential).items():

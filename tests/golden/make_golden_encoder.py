@@ -72,8 +72,41 @@ def mlp_case():
     return params.perturb_affine(prng, params.init_mlp(prng, 10, (7, 4))), prng.standard_normal((5, 10)).astype(F)
 
 
+def semantic_case(decoder_type):
+    prng = np.random.default_rng(505 if decoder_type == "mlp" else 506)
+    cfg = configs.semantic_net()
+    cfg.decoder_type = decoder_type
+    cfg.decoder_dim, cfg.resnet_num_units, cfg.mlp_num_layers = 128, 2, 2
+    if decoder_type == "mlp":
+        p = params.perturb_affine(prng, params.init_mlp(prng, 128, (128, 128, 12)))
+    else:
+        p = params.perturb_affine(prng, params.init_semantic_decoder(prng, cfg))
+    feats = prng.standard_normal((2, 6, 5, 128)).astype(F)
+    valid = prng.random((2, 6, 5)) < 0.8
+    return cfg, p, feats * valid[..., None], valid
+
+
 if __name__ == "__main__":
+    import types as pytypes
     import jaxshim.flaxshim as fs
+    from snap.models import semantic_net as sn, types as rtypes
+    for dt in ("mlp", "resnet_stage"):       # SemanticNet.__call__ (semantic_net.py:167-198) with a stand-in bev_mapper
+        scfg, p, feats, valid = semantic_case(dt)
+        rcfg = Cfg(bev_mapper=Cfg(pretrained_path=None), decoder_type=dt, decoder_dim=128, mlp_num_layers=2, resnet_num_units=2,
+                   apply_random_flip=False, area_classes=scfg.area_classes, object_classes_exclusive=scfg.object_classes_exclusive,
+                   object_classes_independent=scfg.object_classes_independent)
+        m = sn.SemanticNet(rcfg, None, F)
+        m._params, m._counters = {"decoder": p}, {}
+        fs._STACK.append(m)
+        m.setup()
+        fs._STACK.pop()
+        m.decoder._parent = m
+        object.__setattr__(m.decoder, "name", "decoder")
+        m.bev_mapper = lambda data, train: {"bev_features": rtypes.FeaturePlane(features=feats, valid=valid)}
+        pred = sn.SemanticNet.__call__(m, {"map": {}}, False)
+        out[f"sem_{dt}_areas"], out[f"sem_{dt}_excl"] = pred["logits_areas"], pred["logits_objects_exclusive"]
+        out[f"sem_{dt}_indep"] = pred["logits_objects_independent"]
+        print("semantic", dt, np.asarray(pred["logits_areas"]).shape, np.asarray(pred["logits_objects_exclusive"]).shape)
     for tag in ("sv", "aerial"):
         enc_cfg, p, img, skip_root = encoder_case(tag)
         cfg = Cfg(encoder_name="resnet", output_dim=128, num_pyr_levels=None,

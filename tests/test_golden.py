@@ -236,3 +236,23 @@ def test_resnet_stage_and_mlp_vs_reference_modules():
     mp, xm = mod.mlp_case()
     for act in (False, True):
         close(layers.mlp(xm, mp, apply_input_activation=act), d[f"mlp_y{int(act)}"], tol=1e-5)
+
+
+@pytest.mark.parametrize("decoder_type", ["mlp", "resnet_stage"])
+def test_semantic_head_vs_reference_semanticnet_call(decoder_type):
+    """The semantic head (both decoder types) against the reference's OWN SemanticNet.__call__ (semantic_net.py:145-198:
+    Dense -> ResNetStage -> MLP or the plain MLP, f32 logits zeroed where invalid, split into areas / exclusive / independent)
+    executed under the stand-ins with a stand-in bev_mapper (tests/golden/make_golden_encoder.py)."""
+    from oracle import semantic_net as osn
+    mod = _golden_encoder_module()
+    d = load("encoder_modules")
+    cfg, p, feats, valid = mod.semantic_case(decoder_type)
+    if decoder_type == "mlp":
+        tp = {k: {n: torch.from_numpy(np.ascontiguousarray(v[n], dtype=F)) for n in v} for k, v in p.items()}
+        logits = osn.mlp_head_forward_torch(torch.from_numpy(feats), valid, tp).numpy()
+    else:
+        logits = osn.semantic_decoder(feats, valid, p)
+    assert logits.shape == (2, 6, 5, 12) and not logits[~valid].any()
+    close(logits[..., :5], d[f"sem_{decoder_type}_areas"], tol=5e-5)
+    close(logits[..., 5:9], d[f"sem_{decoder_type}_excl"], tol=5e-5)
+    close(logits[..., 9:], d[f"sem_{decoder_type}_indep"], tol=5e-5)
