@@ -74,3 +74,27 @@ def test_plain_c_client(tmp_path):
     assert "null operand" in res.stdout and "multiple of 8" in res.stdout and res.stdout.strip().endswith("ok")
     deps = subprocess.run(["ldd", str(_lib._LIB_PATH)], capture_output=True, text=True).stdout
     assert "torch" not in deps and "python" not in deps
+
+
+def test_host_side_planning_functions_without_gpu():
+    """Workspace / plan queries are host-only (148 SMs assumed without a device): caller-owned workspaces can be sized at
+    trace time, and shapes the kernels cannot take are refused with a message."""
+    from snap_b200 import _lib
+    lib = _lib.lib()
+    ws = lib.snapb200_loc_pose_scoring_workspace
+    ws.restype = C.c_size_t
+    p = _lib.LocScoreParams()
+    p.B, p.N, p.H, p.W, p.P, p.cell_size = 1, 4652, 128, 128, 10001, 0.2
+    # 16 poses per thread x 256 threads -> 3 pose chunks; 2 blocks per SM x 2 waves over 148 SMs -> 198 point splits
+    assert ws(C.byref(p)) == 198 * 10001 * 4
+    p.P = 68921          # 41^3 refinement lattice: 17 chunks -> 35 splits
+    assert ws(C.byref(p)) == 35 * 68921 * 4
+    p.H = p.W = 256      # one map no longer fits twice: single-buffer path, still supported
+    assert ws(C.byref(p)) > 0
+    p.H = p.W = 512
+    assert ws(C.byref(p)) == 0 and b"does not fit in shared memory" in lib.snapb200_last_error()
+    p.H, p.W = 128, 100
+    assert ws(C.byref(p)) == 0 and b"multiple of 8" in lib.snapb200_last_error()
+    wg = lib.snapb200_dense_wgrad_workspace
+    wg.restype = C.c_size_t
+    assert wg(C.c_longlong(65536), 128, 128) == 293 * (128 * 128 + 128) * 4      # 224 rows per slab -> 293 slabs of partials
