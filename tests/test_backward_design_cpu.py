@@ -86,3 +86,35 @@ def test_correlation_backward_as_two_correlations():
     S.backward(dS)
     dq, dm = bf.xcorr_backward(q.detach().numpy(), m.detach().numpy(), dS.numpy())
     assert np.abs(dq - q.grad.numpy()).max() < 1e-10 and np.abs(dm - m.grad.numpy()).max() < 1e-10
+
+
+def test_residual_unit_backward_composition():
+    """The whole pre-activation bottleneck unit (resnet.py:103-134) backward, composed of the building blocks in the launch
+    order planned for round 2, against torch autograd of the oracle's residual_unit."""
+    from oracle import resnet as ores
+    rng = np.random.default_rng(5)
+    N, H, W, C, M = 2, 5, 6, 128, 32
+    p = {g: {"scale": 1 + 0.2 * rng.standard_normal((1, 1, 1, c)), "bias": 0.2 * rng.standard_normal((1, 1, 1, c))}
+         for g, c in (("gn1", C), ("gn2", M), ("gn3", M))}
+    p.update(conv1={"kernel": rng.standard_normal((1, 1, C, M)) * 0.1}, conv2={"kernel": rng.standard_normal((3, 3, M, M)) * 0.1},
+             conv3={"kernel": rng.standard_normal((1, 1, M, C)) * 0.1})
+    x = rng.standard_normal((N, H, W, C))
+    dy = rng.standard_normal((N, H, W, C))
+    tp = {k: {n: torch.tensor(v, dtype=torch.float64, requires_grad=True) for n, v in d.items()} for k, d in p.items()}
+    tx = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    # the oracle casts to fp32 inside standardize: run it in float64 by patching .float() away
+    orig = ores.standardize
+    ores.standardize = lambda t, dims, eps: (t - t.mean(dim=dims, keepdim=True)) / torch.sqrt(((t - t.mean(dim=dims, keepdim=True)) ** 2).mean(dim=dims, keepdim=True) + eps)
+    try:
+        ty = ores.residual_unit(tx, tp, 1)
+    finally:
+        ores.standardize = orig
+    ty.backward(torch.tensor(dy))
+    y, saved = bf.residual_unit_forward(x, p)
+    assert np.abs(y - ty.detach().numpy()).max() < 1e-9
+    dx, g = bf.residual_unit_backward(dy, saved, p)
+    assert np.abs(dx - tx.grad.numpy()).max() < 1e-8
+    for k, d in tp.items():
+        for n, t in d.items():
+            ref = t.grad.numpy().reshape(g[f"{k}/{n}"].shape)
+            assert np.abs(g[f"{k}/{n}"] - ref).max() < 1e-8 * (1 + np.abs(ref).max()), (k, n)

@@ -159,3 +159,62 @@ def xcorr_backward(q, m, dS):
     dm = np.zeros((G, G, D))
     np.add.at(dm, (idx[:, None], idx[None, :]), dm_pad)
     return dq, dm
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# A whole pre-activation bottleneck unit (resnet.py:103-134, stride 1, identity shortcut) backward, composed ONLY of the
+# building blocks above, in the order the round-2 launch plan will run them.  Saved from the forward: x, the three
+# GroupNorm inputs (x, c1, c2) and their normalised+ReLU'd outputs (a1, a2, a3) -- exactly the tensors the forward plan
+# already materialises (the raw conv outputs and the gn_apply outputs).
+# ----------------------------------------------------------------------------------------------------------------------
+def _gn_relu_forward(x, scale, bias, groups=32, eps=1e-5):
+    N, H, W, C = x.shape
+    xg = x.reshape(N, H * W, groups, C // groups).astype(np.float64)
+    mu = xg.mean(axis=(1, 3), keepdims=True)
+    var = ((xg - mu) ** 2).mean(axis=(1, 3), keepdims=True)
+    y = ((xg - mu) / np.sqrt(var + eps)).reshape(N, H, W, C) * scale.reshape(1, 1, 1, C) + bias.reshape(1, 1, 1, C)
+    return np.maximum(y, 0)
+
+
+def _std(w, eps=1e-10):
+    w = w.astype(np.float64)
+    mu = w.mean(axis=(0, 1, 2), keepdims=True)
+    return (w - mu) / np.sqrt(((w - mu) ** 2).mean(axis=(0, 1, 2), keepdims=True) + eps)
+
+
+def residual_unit_forward(x, p):
+    a1 = _gn_relu_forward(x, p["gn1"]["scale"], p["gn1"]["bias"])
+    c1 = np.einsum("nhwi,io->nhwo", a1, _std(p["conv1"]["kernel"])[0, 0])
+    a2 = _gn_relu_forward(c1, p["gn2"]["scale"], p["gn2"]["bias"])
+    c2 = conv3x3_forward_segments(a2, _std(p["conv2"]["kernel"]))
+    a3 = _gn_relu_forward(c2, p["gn3"]["scale"], p["gn3"]["bias"])
+    c3 = np.einsum("nhwi,io->nhwo", a3, _std(p["conv3"]["kernel"])[0, 0])
+    return c3 + x, dict(x=x, a1=a1, c1=c1, a2=a2, c2=c2, a3=a3)
+
+
+def residual_unit_backward(dy, saved, p):
+    """Returns dx and the parameter gradients {gn*/scale,bias, conv*/kernel}.  Launch order of round 2:
+    conv3: dW (split-K), dX (engine)  -> ReLU mask + GroupNorm backward (2 reductions + 1 pass)
+    conv2: 9 shifted dW, 9-segment dX -> ReLU mask + GroupNorm backward
+    conv1: dW, dX                     -> ReLU mask + GroupNorm backward, + dy (identity shortcut)
+    and one StdConv weight-standardisation backward per kernel."""
+    g = {}
+    w3, w2, w1 = _std(p["conv3"]["kernel"]), _std(p["conv2"]["kernel"]), _std(p["conv1"]["kernel"])
+    # conv3 (1x1): dW = a3^T dy, da3 = dy W3^T
+    dws3 = np.einsum("nhwi,nhwo->io", saved["a3"], dy)[None, None]
+    da3 = np.einsum("nhwo,io->nhwi", dy, w3[0, 0])
+    d = da3 * (saved["a3"] > 0)                                     # ReLU backward on the saved activation
+    dc2, g["gn3/scale"], g["gn3/bias"] = groupnorm_backward(saved["c2"], d, p["gn3"]["scale"].reshape(-1))
+    # conv2 (3x3): nine shifted products / nine-segment GEMM on the bordered layout
+    dws2 = conv3x3_dw_shifted(saved["a2"], dc2)
+    da2 = conv3x3_dx_segments(dc2, w2)
+    d = da2 * (saved["a2"] > 0)
+    dc1, g["gn2/scale"], g["gn2/bias"] = groupnorm_backward(saved["c1"], d, p["gn2"]["scale"].reshape(-1))
+    # conv1 (1x1)
+    dws1 = np.einsum("nhwi,nhwo->io", saved["a1"], dc1)[None, None]
+    da1 = np.einsum("nhwo,io->nhwi", dc1, w1[0, 0])
+    d = da1 * (saved["a1"] > 0)
+    dx, g["gn1/scale"], g["gn1/bias"] = groupnorm_backward(saved["x"], d, p["gn1"]["scale"].reshape(-1))
+    for name, dws in (("conv1", dws1), ("conv2", dws2), ("conv3", dws3)):
+        g[name + "/kernel"] = stdconv_weight_backward(p[name]["kernel"], dws)
+    return dx + dy, g                                               # identity shortcut (:134)
