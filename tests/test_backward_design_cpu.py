@@ -118,3 +118,26 @@ def test_residual_unit_backward_composition():
         for n, t in d.items():
             ref = t.grad.numpy().reshape(g[f"{k}/{n}"].shape)
             assert np.abs(g[f"{k}/{n}"] - ref).max() < 1e-8 * (1 + np.abs(ref).max()), (k, n)
+
+
+def test_lift_gather_backward_scatter():
+    """Bilinear gather + depth-score interpolation of one (voxel, view) pair: the scatter-add backward vs autograd, including a
+    point at the image border whose clamped taps coincide."""
+    rng = np.random.default_rng(6)
+    Hf, Wf, D, S = 6, 7, 5, 8
+    for p2d, depth in (((2.3, 4.6), 5.0), ((0.2, 6.9), 20.0)):          # (row, col) in texels; second: clamped taps
+        fimg = torch.tensor(rng.standard_normal((Hf, Wf, D + S)), dtype=torch.float64, requires_grad=True)
+        cr, cc = p2d[0] - 0.5, p2d[1] - 0.5                             # grids.py:129
+        r0, c0 = int(np.floor(cr)), int(np.floor(cc))
+        wr1, wc1 = cr - r0, cc - c0
+        taps = [(min(max(r0 + i, 0), Hf - 1), min(max(c0 + j, 0), Wf - 1)) for i in (0, 1) for j in (0, 1)]
+        weights = [(wr1 if i else 1 - wr1) * (wc1 if j else 1 - wc1) for i in (0, 1) for j in (0, 1)]
+        t = np.log(np.clip(depth, 1.0, 32.0)) / np.log(32.0)            # streetview_encoder.py:112-116
+        bi = t * (S - 1)                                                 # (0.5 + t (S-1)) - 0.5
+        b0 = int(np.floor(bi)); b1 = min(b0 + 1, S - 1); wb1 = bi - b0
+        samp = sum(w * fimg[r, c] for (r, c), w in zip(taps, weights))
+        feat, score = samp[:D], (1 - wb1) * samp[D + b0] + wb1 * samp[D + b1]
+        dfeat, dscore = rng.standard_normal(D), float(rng.standard_normal())
+        ((feat * torch.tensor(dfeat)).sum() + score * dscore).backward()
+        g = bf.lift_gather_backward((Hf, Wf, D + S), taps, weights, (b0, b1), wb1, dfeat, dscore, D)
+        assert np.abs(g - fimg.grad.numpy()).max() < 1e-12

@@ -218,3 +218,20 @@ def residual_unit_backward(dy, saved, p):
     for name, dws in (("conv1", dws1), ("conv2", dws2), ("conv3", dws3)):
         g[name + "/kernel"] = stdconv_weight_backward(p[name]["kernel"], dws)
     return dx + dy, g                                               # identity shortcut (:134)
+
+
+def lift_gather_backward(fimg_shape, taps, weights, bins, wb1, dfeat, dscore, D):
+    """Backward of the bilinear gather + depth-score interpolation of ONE (voxel, view) pair (streetview_encoder.py:69-76,
+    109-124; grids.py:116-137) into the projected feature map fimg [Hf,Wf,D+S]: the forward reads four (clamped) taps
+    (r_k, c_k) with weights w_k = w_row * w_col, features f = sum_k w_k fimg[tap_k, :D] and score
+    s = (1 - wb1) * sum_k w_k fimg[tap_k, D + b0] + wb1 * sum_k w_k fimg[tap_k, D + b1].
+    The backward scatter-adds  w_k * dfeat  into the D feature channels of every tap and  w_k * (1 - wb1) * dscore,
+    w_k * wb1 * dscore  into the two bin channels (clamped taps that coincide simply accumulate): one atomicAdd per
+    (tap, channel), the true 'scatter' of the lift."""
+    g = np.zeros(fimg_shape, np.float64)
+    b0, b1 = bins
+    for (r, c), w in zip(taps, weights):
+        g[r, c, :D] += w * dfeat
+        g[r, c, D + b0] += w * (1 - wb1) * dscore
+        g[r, c, D + b1] += w * wb1 * dscore
+    return g
