@@ -550,8 +550,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
             "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": BT, "launch": "cuda-graph replay (one graph per distinct tile)" if graphs is not None else "eager",
-                       "l2": "per-step working set ~1 GB (activations, voxel statistics) >> 126 MB L2; "
-                             "4 distinct tiles rotate",
+                       "l2": "per-step working set ~%.1f GB (activations, voxel statistics) >> 126 MB L2; "
+                             "4 distinct batches of tiles rotate" % (0.26 * BT),
                        "weights": "random-init Flax tree (48.1 M params), StdConv standardisation inside every step"},
             "e2e": {"value": e2e_val, "unit": "tiles/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + sum(
