@@ -49,7 +49,7 @@ class _Jnp(types.ModuleType):
 
     @staticmethod
     def zeros(shape, dtype=F):
-        return np.zeros(shape, dtype=dtype)
+        return np.zeros(shape, dtype=dtype).view(AtArray)
 
     @staticmethod
     def ones(shape, dtype=F):
@@ -83,6 +83,33 @@ class _Jnp(types.ModuleType):
 for _n in ("mean", "var", "max", "min", "sum"):
     setattr(_Jnp, _n, _Jnp._reduce(_n))
 jnp = _Jnp("jax.numpy")
+
+
+class AtArray(np.ndarray):
+    """ndarray with the functional update syntax of jax arrays: `x.at[idx].set(v)` returns an updated copy.  NumPy
+    ufuncs propagate the subclass, so results of arithmetic / comparisons on AtArrays support `.at` too."""
+
+    @property
+    def at(self):
+        return _At(self)
+
+
+class _At:
+    def __init__(self, a):
+        self.a = a
+
+    def __getitem__(self, idx):
+        return _AtIdx(self.a, idx)
+
+
+class _AtIdx:
+    def __init__(self, a, idx):
+        self.a, self.idx = a, idx
+
+    def set(self, v):
+        out = np.array(self.a, copy=True).view(AtArray)
+        out[self.idx] = v
+        return out
 
 
 class ClampArray(np.ndarray):
@@ -133,7 +160,7 @@ class DataclassArray:
 
     def __init__(self, **kw):
         for name in self._fields:
-            setattr(self, name, _f32(np.asarray(kw[name])))
+            setattr(self, name, _f32(np.asarray(kw[name])).view(AtArray))
 
     @property
     def shape(self):

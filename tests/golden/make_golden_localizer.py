@@ -113,6 +113,16 @@ try:
              top1=metrics["loc/recall_top1"],
              rec0=metrics["loc/recall_samples_0.5m_1°"], rec1=metrics["loc/recall_samples_1m_2°"],
              rec2=metrics["loc/recall_samples_2m_4°"])
+    # the same with threshold_remove_accurate_poses (:254-258: accurate samples are removed from the soft-max, never index 0)
+    self_t = pytypes.SimpleNamespace(config=pytypes.SimpleNamespace(threshold_remove_accurate_poses=(1.5, 0.6), add_temperature=False))
+    losses_t, _ = bl.BEVLocalizerModel.loss_metrics_function(self_t, pred, {"T_query2map": T3})
+    d["nll_removed"] = losses_t["total"]
+    # recover_dense_feature_plane (:111-129) on the field-of-view points
+    fake_loc = pytypes.SimpleNamespace(grid_query=g, qgrid_p_q=gp, q_xy_p=q)
+    from snap.models import types as rtypes
+    sparse = rtypes.FeaturePlane(features=rng.standard_normal((len(q), 1, 3)).astype(F), valid=rng.random((len(q), 1)) < 0.7)
+    dense = bl.BEVLocalizer.recover_dense_feature_plane(fake_loc, sparse)
+    d.update(sparse_features=sparse.features, sparse_valid=sparse.valid, dense_features=dense.features, dense_valid=dense.valid)
     out["loc_localizer"] = d
 except Exception as e:  # pragma: no cover
     import traceback

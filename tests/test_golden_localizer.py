@@ -131,3 +131,28 @@ def test_matching_block_vs_reference_bevlocalizer_call():
                 assert abs(w.sum() - 1) < 1e-5 and not w[~d["vq"][b, :, 0]].any()
             else:
                 assert np.allclose(w, 1.0 / max(int(d["vq"][b].sum()), 1), rtol=1e-5)
+
+
+def test_loss_with_removed_accurate_poses_and_dense_plane_recovery():
+    """threshold_remove_accurate_poses (bev_localizer.py:254-258) in the oracle loss, and the product's host-side
+    recover_dense_feature_plane (:111-129), against the reference's own methods run under the stand-in."""
+    import torch
+    from snap_b200 import bev_localizer as bl, configs, types
+    d = load("loc_localizer")
+    gt = bl.transform2d_from_transform3d(types.Transform3D(R=d["gt_R"], t=d["gt_t"]))
+    changed = 0
+    for b in range(len(d["scores"])):
+        nll, _, dr_s, dt_s = ope.loss_metrics(d["scores"][b], d["samples_angle"][b], d["samples_t"][b], d["best_angle"][b],
+                                              d["best_t"][b], gt[b, 0], gt[b, 1:], (1.5, 0.6))
+        assert abs(float(nll) - float(d["nll_removed"][b])) <= 1e-5 * (1 + abs(float(d["nll_removed"][b])))
+        changed += abs(float(d["nll_removed"][b]) - float(d["nll"][b])) > 1e-6
+        assert ((dr_s[1:] < 1.5) & (dt_s[1:] < 0.6)).any(), "the fixture plants samples inside the removal thresholds"
+    assert changed > 0
+    cfg = configs.bev_localizer()
+    cfg.bev_mapper = configs.bev_mapper(("streetview",))
+    cfg.filter_points_in_fov, cfg.num_pose_samples = True, 8
+    loc = bl.BEVLocalizer(cfg, None, types.Grid2D((32, 32), 0.2))
+    dense = loc.recover_dense_feature_plane(types.FeaturePlane(torch.from_numpy(d["sparse_features"]),
+                                                               torch.from_numpy(d["sparse_valid"].astype(np.uint8))))
+    assert np.array_equal(dense.valid.numpy().astype(bool), d["dense_valid"].astype(bool))
+    assert np.array_equal(dense.features.numpy(), d["dense_features"].astype(F))
