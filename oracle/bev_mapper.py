@@ -103,13 +103,19 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
                xyz: np.ndarray, fusion_params: Dict, feature_dim: int = 128, top_k: int = 4,
                depth_min_max=(1.0, 32.0), rd: Callable = _id, chunk: int = 1 << 16,
                max_view_distance: Optional[float] = None, debug: Optional[Dict] = None,
-               add_minmax: bool = False, use_variance: bool = True, threads: int = 1):
+               add_minmax: bool = False, use_variance: bool = True, threads: int = 1,
+               weighted: bool = True, depth_mlp_params: Optional[Dict] = None):
     """streetview_encoder.py:232-286 for one scene, chunked over voxels (`threads` > 1: chunks on a thread pool, used by
     the timed CPU baseline of bench.py so that the lift uses the host cores like the torch-CPU encoder does).
 
     f_proj_images [V,Hf,Wf,feature_dim+S] = proj_mlp output; camera ALREADY scaled by 1/stride (:224).
     Returns f_grid [X,Y,Z,D], valid [X,Y,Z], and per-voxel debug (vis [N,V], p2d [N,V,2]); with view selection
     (V > top_k) vis / p2d are the GATHERED [N,top_k] arrays and `debug` (if given) collects 'view_indices'.
+
+    weighted=False is the `do_weighted_fusion=False` branch (:262-267): `f_proj_images` [V,Hf,Wf,feature_dim] are the
+    encoder features themselves (no proj MLP, no scale logits), the views are pooled with plain mean / variance
+    (`scores=None`, :153-155) and, if `depth_mlp_params` is given, every observation first receives the residual
+    `depth_mlp([f, log10(clip(depth, 0.1, 100)), ray])` (:264-267; rays zeroed where the view does not see the point).
     """
     rdn = np_rd(rd)
     grid_shape = xyz.shape[:-1]
@@ -118,18 +124,26 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
 
     def one_chunk(s):
         pts = pts_all[s:s + chunk]
-        p2d, vis, depth, _ = sv.project_points_to_views(t_view2scene, camera, pts)
+        p2d, vis, depth, rays = sv.project_points_to_views(t_view2scene, camera, pts)
         min_dist, idx = None, None
         if top_k and V > top_k:  # :241-249
             idx, min_dist = sv.view_selection(pts, t_view2scene, vis, top_k)
-            p2d, vis, depth = (np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
-                               for a in (p2d, vis, depth))
+            p2d, vis, depth, rays = (np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
+                                     for a in (p2d, vis, depth, rays))
             f_proj = sv.interpolate_views_selective(f_proj_images, p2d, idx, cast=rdn)
         else:
             f_proj = sv.interpolate_views_all(f_proj_images, p2d)
         f_proj = rdn(f_proj)
-        feats, scales = f_proj[..., :feature_dim], f_proj[..., feature_dim:]
-        scores = rdn(sv.interpolate_depth_score(scales, depth, depth_min_max))
+        if weighted:  # :254-261
+            feats, scales = f_proj[..., :feature_dim], f_proj[..., feature_dim:]
+            scores = rdn(sv.interpolate_depth_score(scales, depth, depth_min_max))
+        else:  # :262-267
+            feats, scores = f_proj, None
+            if depth_mlp_params is not None:
+                log_depth = np.log10(np.clip(depth, F(0.1), F(100))).astype(F)
+                rays_ = np.where(vis[..., None], rays, F(0))
+                f_depth = rdn(np.concatenate([feats, log_depth[..., None], rays_], -1))
+                feats = rdn(feats + layers.mlp(f_depth, depth_mlp_params, rd=rdn))
         stats, valid = sv.pool_multiview_features(feats, vis, scores, add_minmax, use_variance, rd=rdn)  # :268-274
         if max_view_distance is not None and min_dist is not None:  # :275-279
             valid = valid & (min_dist <= F(max_view_distance))
@@ -169,7 +183,7 @@ def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = 
 def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callable = _id,
                        scene_z_offset: float = 4.0, scene_z_height: float = 12.0, top_k: int = 4,
                        return_volume: bool = False, threads: int = 1, precomputed: Optional[Dict] = None,
-                       feature_dim: int = 128) -> Dict:
+                       feature_dim: int = 128, weighted: bool = True) -> Dict:
     """bev_mapper.py:254-296 for a batch (inference, train=False).
 
     data: 'images' f32 [B,V,H,W,3]; 'camera' geometry.Camera with fields [B,V,2];
@@ -193,11 +207,14 @@ def bev_mapper_forward(data: Dict, params: Dict, grid: grids.Grid2D, rd: Callabl
             stride = strides[-1]
         cam = geometry.Camera(wh=data["camera"].wh[b], f=data["camera"].f[b], c=data["camera"].c[b])
         cam = cam.scale(np.asarray([1 / stride[1], 1 / stride[0]], dtype=F))  # :224 (i,j) -> (x,y)
-        f_proj = layers.mlp(f_img, svp["proj_mlp"], apply_input_activation=True, rd=rdn)  # :229
+        if weighted:
+            f_proj = layers.mlp(f_img, svp["proj_mlp"], apply_input_activation=True, rd=rdn)  # :229
+        else:   # do_weighted_fusion=False: the encoder features are sampled as they are (:227-230 skipped)
+            f_proj = np.asarray(f_img, dtype=F)
         T = geometry.Transform3D(R=data["T_view2scene"].R[b], t=data["T_view2scene"].t[b])
         xyz, z_off = build_xyz_query(grid, T.t, scene_z_offset, scene_z_height)
         f_grid, valid, vis, p2d = lift_scene(f_proj, cam, T, xyz, svp["fusion_mlp"], feature_dim=feature_dim, top_k=top_k, rd=rd,
-                                             threads=threads)
+                                             threads=threads, weighted=weighted, depth_mlp_params=svp.get("depth_mlp"))
         plane, pvalid = vertical_pooling_max(f_grid, valid)
         item = {"f_proj_images": f_proj, "feature_plane": plane, "valid": pvalid, "vis": vis, "p2d": p2d,
                 "z_offset": z_off, "pyramid": [f.numpy() for f in feats]}

@@ -47,15 +47,23 @@ def rot_cam(yaw):
     return np.stack([right, down, fwd], axis=1)
 
 
-def case(tag, V, max_view_distance, seed):
+def case(tag, V, max_view_distance, seed, weighted=True, depth_mlp=False):
     rng = np.random.default_rng(seed)
     B, X, Y, Z, Hf, Wf, Cin = 1, 6, 5, 4, 12, 16, 10
+    if not weighted:
+        Cin = D      # do_weighted_fusion=False samples the encoder features themselves (no proj MLP, :227-230)
     proj = {"Dense_0": {"kernel": (rng.standard_normal((Cin, D + S)) * 0.4).astype(F), "bias": (rng.standard_normal(D + S) * 0.1).astype(F)}}
     fusion = {"Dense_0": {"kernel": (rng.standard_normal((2 * D + 1, 12)) * 0.3).astype(F), "bias": (rng.standard_normal(12) * 0.1).astype(F)},
               "Dense_1": {"kernel": (rng.standard_normal((12, D)) * 0.3).astype(F), "bias": (rng.standard_normal(D) * 0.1).astype(F)}}
-    cfg = Cfg(do_weighted_fusion=True, num_scale_bins=S, top_k_view_selection=4, feature_dim=D, depth_min_max=(1.0, 32.0),
-              fusion_add_minmax=False, fusion_use_variance=True, depth_mlp=None, max_view_distance=max_view_distance)
-    fake = pytypes.SimpleNamespace(config=cfg, dtype=F, proj_mlp=mlp_fn(proj, True), fusion_mlp=mlp_fn(fusion, False))
+    if not weighted:   # statistics = [mean | var] (no score_max row, :174-177)
+        fusion["Dense_0"]["kernel"] = fusion["Dense_0"]["kernel"][: 2 * D]
+    dmlp = {"Dense_0": {"kernel": (rng.standard_normal((D + 4, 9)) * 0.4).astype(F), "bias": (rng.standard_normal(9) * 0.1).astype(F)},
+            "Dense_1": {"kernel": (rng.standard_normal((9, D)) * 0.4).astype(F), "bias": (rng.standard_normal(D) * 0.1).astype(F)}}
+    cfg = Cfg(do_weighted_fusion=weighted, num_scale_bins=S, top_k_view_selection=4, feature_dim=D, depth_min_max=(1.0, 32.0),
+              fusion_add_minmax=False, fusion_use_variance=True, depth_mlp=Cfg() if depth_mlp else None,
+              max_view_distance=max_view_distance)
+    fake = pytypes.SimpleNamespace(config=cfg, dtype=F, proj_mlp=mlp_fn(proj, True), fusion_mlp=mlp_fn(fusion, False),
+                                   depth_mlp=mlp_fn(dmlp, False))
     f_img = rng.standard_normal((B, V, Hf, Wf, Cin)).astype(F)
     R = np.stack([rot_cam(np.pi / 2 + rng.uniform(-0.4, 0.4)) for _ in range(V)])[None].astype(F)
     t = np.stack([[0.6 + 0.25 * v, 0.1 + rng.uniform(-0.1, 0.1), 0.5] for v in range(V)])[None].astype(F)
@@ -63,13 +71,14 @@ def case(tag, V, max_view_distance, seed):
                           c=np.tile(F([Wf * 2, Hf * 2]), (B, V, 1)))
     xs, ys, zs = (np.arange(X) + 0.5) * 0.4, (np.arange(Y) + 0.5) * 0.4 + 0.5, (np.arange(Z) + 0.5) * 0.3
     xyz = np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), -1)[None].astype(F)
-    data = {"image_feature_pyr": rtypes.FeatureImagePyramid(features=[f_img], strides=[np.array([[4.0, 4.0]], F)]),
+    f_in = f_img if weighted else jaxshim.clamp_indexing(f_img)   # JAX clamps out-of-bounds gather indices (:98-101)
+    data = {"image_feature_pyr": rtypes.FeatureImagePyramid(features=[f_in], strides=[np.array([[4.0, 4.0]], F)]),
             "camera": cam, "T_view2scene": geometry.Transform3D(R=R, t=t), "xyz_query": xyz}
     pred = sve.StreetViewEncoder.__call__(fake, data, False)
     vol = pred["feature_volume"]
     out = dict(f_img=f_img, R=R, t=t, wh=cam.wh, f=cam.f, c=cam.c, xyz=xyz, volume=vol.features, valid=vol.valid,
-               scores_images=pred["scores_images"], max_view_distance=np.asarray(-1.0 if max_view_distance is None else max_view_distance))
-    for k, v in {"proj": proj, "fusion": fusion}.items():
+               scores_images=pred.get("scores_images", np.zeros(0, F)), max_view_distance=np.asarray(-1.0 if max_view_distance is None else max_view_distance))
+    for k, v in {"proj": proj, "fusion": fusion, **({"depth": dmlp} if depth_mlp else {})}.items():
         for n, p in v.items():
             out[f"{k}_{n}_kernel"], out[f"{k}_{n}_bias"] = p["kernel"], p["bias"]
     np.savez_compressed(os.path.join(HERE, f"sve_call_{tag}.npz"), **{k: np.asarray(v) for k, v in out.items()})
@@ -78,3 +87,8 @@ def case(tag, V, max_view_distance, seed):
 
 case("allviews", 3, None, 1)
 case("select", 6, 1.6, 2)
+# do_weighted_fusion=False (:262-267): plain mean / variance pooling, without and with the per-observation depth_mlp
+case("plain_allviews", 3, None, 3, weighted=False)
+case("plain_select", 6, 1.6, 4, weighted=False)
+case("plain_depthmlp_allviews", 3, None, 5, weighted=False, depth_mlp=True)
+case("plain_depthmlp_select", 6, 1.6, 6, weighted=False, depth_mlp=True)

@@ -146,6 +146,47 @@ def test_lift_scene_vs_reference_streetview_encoder_call(tag):
     assert not f_grid[~valid].any()
 
 
+@pytest.mark.parametrize("tag", ["plain_allviews", "plain_select", "plain_depthmlp_allviews", "plain_depthmlp_select"])
+def test_lift_scene_unweighted_vs_reference_streetview_encoder_call(tag):
+    """The `do_weighted_fusion=False` branch (streetview_encoder.py:262-267: no proj MLP, plain mean / variance pooling,
+    optional per-observation `depth_mlp` residual on [f, log10 depth, ray]) of oracle.bev_mapper.lift_scene against the
+    reference's OWN StreetViewEncoder.__call__ run under the stand-in, all-views and view-selection paths."""
+    from oracle import bev_mapper as obm
+    d = load("sve_call_" + tag)
+    tree = lambda pre: {n: {"kernel": d[f"{pre}_{n}_kernel"], "bias": d[f"{pre}_{n}_bias"]}
+                        for n in ("Dense_0", "Dense_1") if f"{pre}_{n}_kernel" in d}
+    assert d["scores_images"].size == 0 and d["fusion_Dense_0_kernel"].shape[0] == 16      # [mean | var], no score_max row
+    cam = geometry.Camera(wh=d["wh"][0], f=d["f"][0], c=d["c"][0]).scale(np.asarray([0.25, 0.25], F))   # :224
+    T = geometry.Transform3D(R=d["R"][0], t=d["t"][0])
+    mvd = float(d["max_view_distance"])
+    f_grid, valid, _, _ = obm.lift_scene(d["f_img"][0], cam, T, d["xyz"][0], tree("fusion"), feature_dim=8, top_k=4,
+                                         max_view_distance=None if mvd < 0 else mvd, weighted=False,
+                                         depth_mlp_params=tree("depth") if "depthmlp" in tag else None)
+    assert np.array_equal(valid, d["valid"][0].astype(bool)) and 0.3 < valid.mean() < 0.95
+    close(f_grid, d["volume"][0], tol=5e-5)
+    assert not f_grid[~valid].any()
+
+
+@pytest.mark.parametrize("tag", ["plain_allviews", "plain_select"])
+def test_unweighted_lift_equals_weighted_lift_with_zero_logits(tag):
+    """Design check of the product's un-weighted path (snap_b200/streetview_encoder.py): with all-zero scale logits the
+    weighted soft-max is uniform over the valid views, so [mean | var] equal the plain statistics and the extra
+    score_max column (= 0) meets a zero row appended to the fusion MLP's first kernel -- the weighted kernels then
+    reproduce the reference's `do_weighted_fusion=False` volume."""
+    from oracle import bev_mapper as obm
+    d = load("sve_call_" + tag)
+    fusion = {n: {"kernel": d[f"fusion_{n}_kernel"], "bias": d[f"fusion_{n}_bias"]} for n in ("Dense_0", "Dense_1")}
+    fusion["Dense_0"]["kernel"] = np.concatenate([fusion["Dense_0"]["kernel"], np.zeros((1, 12), F)])
+    f_pad = np.concatenate([d["f_img"][0], np.zeros(d["f_img"][0].shape[:-1] + (6,), F)], -1)
+    cam = geometry.Camera(wh=d["wh"][0], f=d["f"][0], c=d["c"][0]).scale(np.asarray([0.25, 0.25], F))
+    T = geometry.Transform3D(R=d["R"][0], t=d["t"][0])
+    mvd = float(d["max_view_distance"])
+    f_grid, valid, _, _ = obm.lift_scene(f_pad, cam, T, d["xyz"][0], fusion, feature_dim=8, top_k=4,
+                                         max_view_distance=None if mvd < 0 else mvd)
+    assert np.array_equal(valid, d["valid"][0].astype(bool))
+    close(f_grid, d["volume"][0], tol=5e-5)
+
+
 def test_bev_mapper_forward_vs_reference_bevmapper_call():
     """oracle.bev_mapper_forward (encoders bypassed) against the reference's OWN BEVMapper.__call__ chain
     (bev_mapper.py:159-296 + StreetViewEncoder.__call__ + VerticalPooling.__call__) run under the stand-in
