@@ -93,10 +93,13 @@ def init_mlp(rng, in_dim, layers) -> Dict:
 def init_streetview_encoder(rng, cfg) -> Dict:
     """`snap/models/streetview_encoder.py:196-215`."""
     d, s = cfg.feature_dim, cfg.num_scale_bins
-    stats_dim = d * (1 + int(cfg.fusion_use_variance) + 2 * int(cfg.fusion_add_minmax)) + 1
-    return {"image_encoder": init_image_encoder(rng, cfg.image_encoder),
-            "proj_mlp": init_mlp(rng, cfg.image_encoder.output_dim, (d + s,)),
-            "fusion_mlp": init_mlp(rng, stats_dim, cfg.fusion.layers)}
+    weighted = bool(cfg.do_weighted_fusion)   # the score_max statistic exists only with weighted fusion (`:174-177`)
+    stats_dim = d * (1 + int(cfg.fusion_use_variance) + 2 * int(cfg.fusion_add_minmax)) + int(weighted)
+    p = {"image_encoder": init_image_encoder(rng, cfg.image_encoder)}
+    if weighted:                              # `:207-213`; without it the module has no proj_mlp
+        p["proj_mlp"] = init_mlp(rng, cfg.image_encoder.output_dim, (d + s,))
+    p["fusion_mlp"] = init_mlp(rng, stats_dim, cfg.fusion.layers)
+    return p
 
 
 def init_bev_mapper(rng, cfg) -> Dict:

@@ -80,8 +80,16 @@ class StreetViewEncoder:
     def __init__(self, config=None, dtype=torch.bfloat16):
         self.config = config if config is not None else configs.streetview_encoder()
         c = self.config
-        if not c.do_weighted_fusion or c.depth_mlp is not None:
-            raise NotImplementedError("only the weighted fusion branch (streetview_encoder.py:254-261) is built")
+        if c.depth_mlp is not None:
+            raise NotImplementedError("the per-observation depth_mlp residual (streetview_encoder.py:263-267) is not built")
+        # do_weighted_fusion=False (`:262-267` without depth_mlp) runs on the SAME kernels: the sampled maps are the
+        # encoder features followed by 32 all-zero scale logits (written by the GEMM engine with the constant operand
+        # [I | 0] instead of the proj MLP), which makes the soft-max over the valid views uniform, i.e. [mean | var]
+        # are the plain statistics of `pool_multiview_features` (`:153-155`), and the score_max column (= 0) meets a
+        # zero row appended to the fusion MLP's first kernel (tests/test_golden.py checks the identity on the oracle).
+        self.weighted = bool(c.do_weighted_fusion)
+        if not self.weighted and c.image_encoder.output_dim != c.feature_dim:
+            raise ValueError("do_weighted_fusion=False samples the encoder features: output_dim must equal feature_dim")
         if tuple(c.fusion.layers) != (256, 128) or c.feature_dim != 128:
             raise NotImplementedError("fusion MLP must be stats->256->128")
         # statistics = [mean | var? | max min? | score_max] (pool_multiview_features :165-177)
@@ -97,14 +105,24 @@ class StreetViewEncoder:
         if key not in self._cache:
             bank = image_encoder._WeightBank(device)
             f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).reshape(-1)).to(device)
+            fus0_k = np.asarray(params["fusion_mlp"]["Dense_0"]["kernel"], dtype=F)
+            if self.weighted:
+                proj_k, proj_b = params["proj_mlp"]["Dense_0"]["kernel"], params["proj_mlp"]["Dense_0"]["bias"]
+            else:
+                d, s = self.config.feature_dim, 160 - self.config.feature_dim
+                proj_k, proj_b = np.concatenate([np.eye(d, dtype=F), np.zeros((d, s), F)], 1), np.zeros(d + s, F)
+                fus0_k = np.concatenate([fus0_k, np.zeros((1, fus0_k.shape[1]), F)], 0)
+            if fus0_k.shape[0] != self.stats_dim:
+                raise ValueError(f"fusion_mlp/Dense_0/kernel has {fus0_k.shape[0]} input rows, the configuration needs "
+                                 f"{self.stats_dim - (not self.weighted)}")
             w = dict(bank=bank,
-                     proj=bank.add(params["proj_mlp"]["Dense_0"]["kernel"], False),
-                     fus0=bank.add(params["fusion_mlp"]["Dense_0"]["kernel"], False, k_multiple=32),
+                     proj=bank.add(proj_k, False),
+                     fus0=bank.add(fus0_k, False, k_multiple=32),
                      fus1=bank.add(params["fusion_mlp"]["Dense_1"]["kernel"], False),
-                     proj_b=f32(params["proj_mlp"]["Dense_0"]["bias"]),
+                     proj_b=f32(proj_b),
                      fus0_b=f32(params["fusion_mlp"]["Dense_0"]["bias"]),
                      fus1_b=f32(params["fusion_mlp"]["Dense_1"]["bias"]),
-                     w256=f32(params["fusion_mlp"]["Dense_0"]["kernel"][self.stats_dim - 1]))
+                     w256=f32(fus0_k[self.stats_dim - 1]))
             bank.finalize()
             self._cache[key] = w
         return self._cache[key]
@@ -259,8 +277,9 @@ class StreetViewEncoder:
             buf["volume"] = torch.zeros((B, N, 128), dtype=torch.bfloat16, device=dev)
             buf["valid"] = torch.zeros((B, N), dtype=torch.uint8, device=dev)
         for b in range(B):
-            # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`)
-            ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, True, buf["crop"])
+            # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`); un-weighted fusion: the crop
+            # itself, widened by zero logits (see __init__)
+            ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, self.weighted, buf["crop"])
             ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"][b], m_rows=V * hf * wf, bias=wts["proj_b"])
             if fused:
                 ops.lift_fused(lp, stg["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b],
@@ -288,8 +307,9 @@ class StreetViewEncoder:
             ops.gemm(buf["stats"], Bm[wts["fus0"]], buf["hid"], m_rows=N, seg_k=self.stats_ld, bias=wts["fus0_b"], relu=True)
             ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],
                      row_mask=buf["valid"][b])
-        pred = {"image_feature_pyramid": pyr,
-                "scores_images": buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)[..., 128:]}
+        pred = {"image_feature_pyramid": pyr}
+        if self.weighted:                      # `:229-230`
+            pred["scores_images"] = buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)[..., 128:]
         if fused:
             pred["feature_plane"] = types.FeaturePlane(features=buf["plane"].view(B, X, Y, 128),
                                                        valid=buf["pvalid"].view(B, X, Y))

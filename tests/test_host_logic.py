@@ -102,7 +102,7 @@ def _leaves(t):
 def test_unsupported_configs_fail_loudly():
     import pytest
     c = configs.bev_mapper()
-    c.streetview_encoder.do_weighted_fusion = False      # the un-weighted branch has no proj MLP (:207-215): not built
+    c.streetview_encoder.depth_mlp = configs.mlp()       # the per-observation depth_mlp residual (:263-267): not built
     with pytest.raises(NotImplementedError):
         bev_mapper.BEVMapper(c, types.Grid2D((8, 8), 0.2))
     c3 = configs.bev_mapper()
@@ -207,3 +207,24 @@ def test_explicit_xyz_query_is_split_into_the_kernel_layout():
     bad[0, 1, 1, 5, 2] += F(0.1)          # one column with its own z level
     with pytest.raises(NotImplementedError):
         mapper.split_xyz_query(dict(data, xyz_query=bad))
+
+
+def test_unweighted_fusion_configuration_host_side():
+    """do_weighted_fusion=False (streetview_encoder.py:196-215): the module has no proj_mlp, the fusion MLP's first kernel
+    has no score_max row; the product keeps the kernels' 257-wide statistics rows and refuses the depth_mlp residual."""
+    import pytest
+    from snap_b200 import configs, params, streetview_encoder as sve
+    cfg = configs.streetview_encoder()
+    cfg.do_weighted_fusion = False
+    tree = params.init_streetview_encoder(np.random.default_rng(0), cfg)
+    assert "proj_mlp" not in tree and tree["fusion_mlp"]["Dense_0"]["kernel"].shape == (256, 256)
+    enc = sve.StreetViewEncoder(cfg)
+    assert not enc.weighted and enc.stats_dim == 257 and enc.stats_ld == 288 and enc.default_stats
+    cfg.fusion_add_minmax = True
+    assert params.init_streetview_encoder(np.random.default_rng(0), cfg)["fusion_mlp"]["Dense_0"]["kernel"].shape == (512, 256)
+    cfg.depth_mlp = configs.mlp()
+    with pytest.raises(NotImplementedError):
+        sve.StreetViewEncoder(cfg)
+    # the default (weighted) tree is unchanged: [mean | var | score_max] rows and a 128 -> 160 proj MLP
+    tree = params.init_streetview_encoder(np.random.default_rng(0), configs.streetview_encoder())
+    assert tree["proj_mlp"]["Dense_0"]["kernel"].shape == (128, 160) and tree["fusion_mlp"]["Dense_0"]["kernel"].shape == (257, 256)
