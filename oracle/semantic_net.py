@@ -168,3 +168,14 @@ def mlp_head_forward_torch(features: "torch.Tensor", valid: np.ndarray, params: 
         x = rd(x + params[f"Dense_{i}"]["bias"])
     v = torch.from_numpy(np.ascontiguousarray(valid))[..., None]
     return torch.where(v, x.float(), torch.zeros((), dtype=torch.float32))
+
+
+def stage_head_forward_torch(features: "torch.Tensor", valid: np.ndarray, params: Dict, rd: Callable = _id):
+    """`semantic_decoder` above (semantic_net.py:153-161,185-186: Dense -> ResNetStage -> MLP) in torch, differentiable
+    w.r.t. `params` (torch tensors with requires_grad; dtype casts in `rd` pass the gradient straight through): the
+    gradient oracle of the 'resnet_stage' head-only training step."""
+    x = rd(features @ params["layers_0"]["kernel"])
+    x = rd(x + params["layers_0"]["bias"])
+    x = resnet.resnet_stage(x, params["layers_1"], 1, rd)
+    x = mlp_head_forward_torch(x, valid, params["layers_3"], rd)
+    return x

@@ -125,6 +125,7 @@ EXPORTED_SYMBOLS += [
     "snapb200_argmax_rows", "snapb200_loc_nll", "snapb200_sem_loss",
     "snapb200_sem_loss_grad", "snapb200_relu_bwd", "snapb200_dense_wgrad_workspace", "snapb200_dense_wgrad",
     "snapb200_adam_step", "snapb200_cast_pad_bf16", "snapb200_sem_labels",
+    "snapb200_gn_backward", "snapb200_wt_segments", "snapb200_stdconv_backward",
 ]
 
 

@@ -1,0 +1,334 @@
+// Backward building blocks of the 'resnet_stage' semantic decoder (snap/models/semantic_net.py:153-161 with
+// snap/models/resnet.py:34-155; BASELINE configs[4], snap/configs/train_semantics.py:27-36) beyond the dense layers of
+// train_head.cu:
+//
+//   GroupNorm (+ReLU) backward (resnet.py:46-70)      -> gn_bwd_reduce_kernel, gn_bwd_apply_kernel, gn_bwd_params_kernel
+//   StdConv weight-standardisation backward (:34-41)  -> stdconv_bwd_kernel
+//   B operand of dX = dY W^T for 1x1 / 3x3 kernels    -> wt_segments_kernel (transposed taps of the standardised kernel)
+//
+// The convolutions themselves reuse existing kernels: dX of a 1x1 conv is the tcgen05 GEMM engine with the transposed
+// kernel, dX of the 3x3 conv is the engine's 9-segment mode over the zero-bordered dY with mirrored row offsets, dW is
+// snapb200_dense_wgrad (nine row-shifted calls for the 3x3 kernel).  Closed forms and the launch decomposition are the
+// ones checked against torch autograd in tools/design/backward_formulas.py (tests/test_backward_design_cpu.py).
+//
+// GroupNorm backward, per image n and group g over m = H*W*C/32 elements, with xhat = (x - mu) * rstd,
+// a = relu(xhat * scale + bias) and d = dy * [a > 0]:
+//   dbias_c  = sum d            dscale_c = sum d * xhat
+//   s1(n,g)  = sum_{c in g} scale_c * sum_p d        s2(n,g) = sum_{c in g} scale_c * sum_p d * xhat
+//   dx       = rstd * (d * scale - s1 / m - xhat * s2 / m)
+// so ONE reduction per (image, channel) of (sum d, sum d * xhat) feeds both the parameter gradients and the group sums.
+// The ReLU mask is recomputed with the forward's bf16 rounding chain (gn_apply_kernel), i.e. it is exactly the mask of
+// the activation the forward produced.  Reductions: fixed-order tree inside a CTA, double atomics across CTAs.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace snapb200 {
+
+namespace {
+
+struct GnFwdStat {
+  float mean, rstd;
+};
+
+// finalise the forward statistics of (image n, group g) from the raw (sum, sumsq) double accumulators, exactly as
+// gn_apply_kernel does (8 replicas, fixed order, eps 1e-5 inside the square root)
+__device__ __forceinline__ GnFwdStat gn_finalize(const double* __restrict__ acc, int replica_stride, int n, int g,
+                                                 double count) {
+  double su = 0.0, sq = 0.0;
+#pragma unroll
+  for (int rep = 0; rep < 8; ++rep) {
+    su += acc[(size_t)rep * replica_stride + ((size_t)n * 32 + g) * 2];
+    sq += acc[(size_t)rep * replica_stride + ((size_t)n * 32 + g) * 2 + 1];
+  }
+  const double mu = su / count;
+  double var = sq / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  GnFwdStat s;
+  s.mean = (float)mu;
+  s.rstd = (float)(1.0 / sqrt(var + 1e-5));
+  return s;
+}
+
+// forward value of one channel pair (bf16 rounding chain of gn_apply_kernel) -> is the ReLU open?
+__device__ __forceinline__ void relu_open(float xh0, float xh1, __nv_bfloat162 sc, __nv_bfloat162 bi, bool& o0, bool& o1) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(xh0, xh1);
+  v = __hmul2_rn(v, sc);
+  v = __hadd2_rn(v, bi);
+  o0 = __low2float(v) > 0.f;
+  o1 = __high2float(v) > 0.f;
+}
+
+}  // namespace
+
+// accb [Nimg, C, 2] (double) += per-(image, channel) sums of (d, d * xhat).  grid (pixel blocks, Nimg), 256 threads:
+// thread = (pixel lane pl, channel vector cv of 8 channels).
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int HW, int C,
+                     const double* __restrict__ acc, int replica_stride, const float* __restrict__ scale,
+                     const float* __restrict__ bias, int post_relu, int pix_per_block, double* __restrict__ accb) {
+  const int CV = C / 8, PL = 256 / CV;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int n = blockIdx.y, c0 = cv * 8, cpg = C / 32;
+  __shared__ float2 s_stat[32];
+  __shared__ float s_part[256][17];   // [thread][8 x (d, d*xhat)], padded against bank conflicts
+  if (threadIdx.x < 32) {
+    const GnFwdStat st = gn_finalize(acc, replica_stride, n, threadIdx.x, (double)HW * (double)cpg);
+    s_stat[threadIdx.x] = make_float2(st.mean, st.rstd);
+  }
+  __syncthreads();
+  float sd[8], sx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sd[j] = sx[j] = 0.f;
+  if (pl < PL) {
+    float mean[8], rstd[8];
+    __nv_bfloat162 sc2[4], bi2[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 st = s_stat[(c0 + j) / cpg];
+      mean[j] = st.x;
+      rstd[j] = st.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc2[j] = __floats2bfloat162_rn(__ldg(scale + c0 + 2 * j), __ldg(scale + c0 + 2 * j + 1));
+      bi2[j] = __floats2bfloat162_rn(__ldg(bias + c0 + 2 * j), __ldg(bias + c0 + 2 * j + 1));
+    }
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    for (int p = p0 + pl; p < p1; p += PL) {
+      const size_t off = ((size_t)n * HW + p) * C + c0;
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off));
+      const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + off));
+      const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16(xu[j]), df = unpack_bf16(du[j]);
+        const float h0 = (xf.x - mean[2 * j]) * rstd[2 * j], h1 = (xf.y - mean[2 * j + 1]) * rstd[2 * j + 1];
+        bool o0 = true, o1 = true;
+        if (post_relu) relu_open(h0, h1, sc2[j], bi2[j], o0, o1);
+        const float d0 = o0 ? df.x : 0.f, d1 = o1 ? df.y : 0.f;
+        sd[2 * j] += d0;
+        sx[2 * j] += d0 * h0;
+        sd[2 * j + 1] += d1;
+        sx[2 * j + 1] += d1 * h1;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_part[threadIdx.x][2 * j] = sd[j];
+    s_part[threadIdx.x][2 * j + 1] = sx[j];
+  }
+  __syncthreads();
+  // fixed-order sum over the PL pixel lanes of every (channel, statistic); 2 * C <= 512 entries for 256 threads
+  for (int e = threadIdx.x; e < 2 * C; e += 256) {
+    const int c = e >> 1, which = e & 1;
+    const int tcv = c / 8, j = c % 8;
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += s_part[l * CV + tcv][2 * j + which];
+    atomicAdd(&accb[((size_t)n * C + c) * 2 + which], (double)s);
+  }
+}
+
+// dx = rstd * (d * scale - s1 / m - xhat * s2 / m) (+ add), written dense [Nimg*HW, C] or zero-bordered
+// [Nimg, H+2, W+2, C] (the layout the 3x3 dX GEMM and the shifted dW products read)
+template <bool PADDED>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                    const __nv_bfloat16* __restrict__ add, int H, int W, int C, const double* __restrict__ acc,
+                    int replica_stride, const float* __restrict__ scale, const float* __restrict__ bias, int post_relu,
+                    const double* __restrict__ accb, int pix_per_block, __nv_bfloat16* __restrict__ dx) {
+  const int CV = C / 8, PL = 256 / CV;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int n = blockIdx.y, c0 = cv * 8, cpg = C / 32, HW = H * W;
+  __shared__ float2 s_stat[32];
+  __shared__ float2 s_grp[32];   // (s1 / m, s2 / m)
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    const double m = (double)HW * (double)cpg;
+    const GnFwdStat st = gn_finalize(acc, replica_stride, n, g, m);
+    s_stat[g] = make_float2(st.mean, st.rstd);
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const double sc = (double)__bfloat162float(__float2bfloat16_rn(__ldg(scale + c)));
+      s1 += sc * accb[((size_t)n * C + c) * 2];
+      s2 += sc * accb[((size_t)n * C + c) * 2 + 1];
+    }
+    s_grp[g] = make_float2((float)(s1 / m), (float)(s2 / m));
+  }
+  __syncthreads();
+  if (pl >= PL) return;
+  float mean[8], rstd[8], g1[8], g2[8], scf[8];
+  __nv_bfloat162 sc2[4], bi2[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    mean[j] = s_stat[g].x;
+    rstd[j] = s_stat[g].y;
+    g1[j] = s_grp[g].x;
+    g2[j] = s_grp[g].y;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc2[j] = __floats2bfloat162_rn(__ldg(scale + c0 + 2 * j), __ldg(scale + c0 + 2 * j + 1));
+    bi2[j] = __floats2bfloat162_rn(__ldg(bias + c0 + 2 * j), __ldg(bias + c0 + 2 * j + 1));
+    scf[2 * j] = __low2float(sc2[j]);
+    scf[2 * j + 1] = __high2float(sc2[j]);
+  }
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  for (int p = p0 + pl; p < p1; p += PL) {
+    const size_t off = ((size_t)n * HW + p) * C + c0;
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off));
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + off));
+    uint4 av = make_uint4(0u, 0u, 0u, 0u);
+    if (add != nullptr) av = __ldg(reinterpret_cast<const uint4*>(add + off));
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w}, au[4] = {av.x, av.y, av.z, av.w};
+    uint32_t ov[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 xf = unpack_bf16(xu[j]), df = unpack_bf16(du[j]), af = unpack_bf16(au[j]);
+      const float h0 = (xf.x - mean[2 * j]) * rstd[2 * j], h1 = (xf.y - mean[2 * j + 1]) * rstd[2 * j + 1];
+      bool o0 = true, o1 = true;
+      if (post_relu) relu_open(h0, h1, sc2[j], bi2[j], o0, o1);
+      const float d0 = o0 ? df.x : 0.f, d1 = o1 ? df.y : 0.f;
+      const float r0 = rstd[2 * j] * (d0 * scf[2 * j] - g1[2 * j] - h0 * g2[2 * j]) + af.x;
+      const float r1 = rstd[2 * j + 1] * (d1 * scf[2 * j + 1] - g1[2 * j + 1] - h1 * g2[2 * j + 1]) + af.y;
+      ov[j] = pack_bf16(r0, r1);
+    }
+    size_t orow = (size_t)n * HW + p;
+    if (PADDED) {
+      const int h = p / W, w = p - h * W;
+      orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+    }
+    *reinterpret_cast<uint4*>(dx + orow * C + c0) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  }
+}
+
+// dscale_c = sum_n accb[n][c][1], dbias_c = sum_n accb[n][c][0]
+__global__ void gn_bwd_params_kernel(const double* __restrict__ accb, int Nimg, int C, float* __restrict__ dscale,
+                                     float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sb = 0.0, ss = 0.0;
+  for (int n = 0; n < Nimg; ++n) {
+    sb += accb[((size_t)n * C + c) * 2];
+    ss += accb[((size_t)n * C + c) * 2 + 1];
+  }
+  dscale[c] = (float)ss;
+  dbias[c] = (float)sb;
+}
+
+// out[cin, tap * Cout + cout] = in[cout, tap * Cin + cin]: the engine's B operand [N = Cin, K = taps * Cout] of
+// dX = sum_tap dY[. - off_tap] W_tap^T from the forward operand [Cout, taps * Cin] (taps = 1: a plain transpose)
+__global__ void wt_segments_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int Cout, int Cin, int taps,
+                                   __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int total = Cin * taps * Cout;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cout = i % Cout;
+  const int tap = (i / Cout) % taps;
+  const int cin = i / (Cout * taps);
+  out[(size_t)cin * ld_out + tap * Cout + cout] = in[(size_t)cout * ld_in + tap * Cin + cin];
+}
+
+// StdConv backward: one CTA (128 threads) per output channel o over the K = kh*kw*in elements of column o of the
+// [K, Cout] kernel: ws = (w - mu) * rstd (eps 1e-10), dw = rstd * (dws - mean(dws) - ws * mean(dws * ws)).
+__global__ void __launch_bounds__(128)
+stdconv_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dws, int K, int Cout, float* __restrict__ dw) {
+  __shared__ double s_red[128];
+  __shared__ double s_val[4];
+  const int o = blockIdx.x, t = threadIdx.x;
+  auto block_sum = [&](double v, int slot) {
+    s_red[t] = v;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+      if (t < s) s_red[t] += s_red[t + s];
+      __syncthreads();
+    }
+    if (t == 0) s_val[slot] = s_red[0];
+    __syncthreads();
+  };
+  double a = 0.0;
+  for (int k = t; k < K; k += 128) a += (double)w[(size_t)k * Cout + o];
+  block_sum(a, 0);
+  const double mu = s_val[0] / K;
+  a = 0.0;
+  for (int k = t; k < K; k += 128) {
+    const double c = (double)w[(size_t)k * Cout + o] - mu;
+    a += c * c;
+  }
+  block_sum(a, 1);
+  const double rstd = 1.0 / sqrt(s_val[1] / K + 1e-10);
+  double sd = 0.0, sdw = 0.0;
+  for (int k = t; k < K; k += 128) {
+    const double d = (double)dws[(size_t)k * Cout + o];
+    sd += d;
+    sdw += d * ((double)w[(size_t)k * Cout + o] - mu) * rstd;
+  }
+  block_sum(sd, 2);
+  block_sum(sdw, 3);
+  const double md = s_val[2] / K, mdw = s_val[3] / K;
+  for (int k = t; k < K; k += 128) {
+    const double ws = ((double)w[(size_t)k * Cout + o] - mu) * rstd;
+    dw[(size_t)k * Cout + o] = (float)(rstd * ((double)dws[(size_t)k * Cout + o] - md - ws * mdw));
+  }
+}
+
+}  // namespace snapb200
+
+using namespace snapb200;
+
+extern "C" {
+
+int snapb200_gn_backward(const void* x, const void* dy, const void* add, int Nimg, int H, int W, int C,
+                         const double* acc, int replica_stride, const float* scale, const float* bias, int post_relu,
+                         int padded_out, double* accb, void* dx, float* dscale, float* dbias, void* stream) {
+  SNAP_REQUIRE(x && dy && acc && scale && bias && accb && dx && dscale && dbias, "null pointer");
+  SNAP_REQUIRE(Nimg >= 1 && H >= 1 && W >= 1, "empty problem");
+  SNAP_REQUIRE(C == 64 || C == 128 || C == 256, "C must be 64, 128 or 256");
+  SNAP_REQUIRE(replica_stride >= Nimg * 64, "replica_stride must cover [Nimg][32][2] doubles");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = check_cuda(cudaMemsetAsync(accb, 0, (size_t)Nimg * C * 2 * sizeof(double), s), "cudaMemsetAsync(accb)"))
+    return rc;
+  const int HW = H * W;
+  const int PL = 256 / (C / 8);
+  int ppl = 32;
+  while (ppl > 4 && (long long)Nimg * ((HW + PL * ppl - 1) / (PL * ppl)) < 4LL * num_sms()) ppl >>= 1;
+  int ppb = ppl * PL;
+  if (ppb > HW) ppb = HW;
+  dim3 grid((HW + ppb - 1) / ppb, Nimg);
+  gn_bwd_reduce_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, HW, C, acc,
+                                            replica_stride, scale, bias, post_relu, ppb, accb);
+  if (int rc = check_launch("gn_bwd_reduce_kernel")) return rc;
+  if (padded_out)
+    gn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                   (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias,
+                                                   post_relu, accb, ppb, (__nv_bfloat16*)dx);
+  else
+    gn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                    (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias,
+                                                    post_relu, accb, ppb, (__nv_bfloat16*)dx);
+  if (int rc = check_launch("gn_bwd_apply_kernel")) return rc;
+  gn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, s>>>(accb, Nimg, C, dscale, dbias);
+  return check_launch("gn_bwd_params_kernel");
+}
+
+int snapb200_wt_segments(const void* in, int ld_in, int Cout, int Cin, int taps, void* out, int ld_out, void* stream) {
+  SNAP_REQUIRE(in && out && Cout >= 1 && Cin >= 1 && taps >= 1, "bad arguments");
+  SNAP_REQUIRE(ld_in >= taps * Cin && ld_out >= taps * Cout, "row pitch too small");
+  const int total = Cin * taps * Cout;
+  wt_segments_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ld_in, Cout, Cin,
+                                                                           taps, (__nv_bfloat16*)out, ld_out);
+  return check_launch("wt_segments_kernel");
+}
+
+int snapb200_stdconv_backward(const float* w, const float* dws, int K, int Cout, float* dw, void* stream) {
+  SNAP_REQUIRE(w && dws && dw && K >= 1 && Cout >= 1, "bad arguments");
+  stdconv_bwd_kernel<<<Cout, 128, 0, (cudaStream_t)stream>>>(w, dws, K, Cout, dw);
+  return check_launch("stdconv_bwd_kernel");
+}
+
+}  // extern "C"

@@ -672,3 +672,49 @@ def sem_labels(sel_area: Sequence[Sequence[int]], sel_excl: Sequence[Sequence[in
         table(sel_area), len(sel_area), table(sel_excl), len(sel_excl), ti, len(sel_indep), num_gt,
         C.c_void_p(_ptr(masks)), C.c_void_p(_ptr(bev_valid)), C.c_longlong(rows), C.c_void_p(_ptr(labels_area)),
         C.c_void_p(_ptr(valid_area)), C.c_void_p(_ptr(labels_excl)), C.c_void_p(_ptr(masks_indep)), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# backward building blocks of the 'resnet_stage' decoder (csrc/train_stage.cu)
+# --------------------------------------------------------------------------------------------
+def gn_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: int, acc: torch.Tensor,
+                scale: torch.Tensor, bias: torch.Tensor, accb: torch.Tensor, dx: torch.Tensor, dscale: torch.Tensor,
+                dbias: torch.Tensor, *, post_relu: bool = True, padded_out: bool = False,
+                add: Optional[torch.Tensor] = None) -> None:
+    """GroupNorm(+ReLU) backward: x = the forward's GroupNorm input, acc = its statistics accumulators, dy = gradient
+    w.r.t. the (activated) output; dx dense or zero-bordered; dscale / dbias f32 [Cc]; accb f64 scratch [n, Cc, 2]."""
+    for t, nm in ((x, "x"), (dy, "dy"), (dx, "dx")):
+        _require(t, torch.bfloat16, nm)
+        assert t.is_contiguous()
+    _require(acc, torch.float64, "acc")
+    _require(accb, torch.float64, "accb")
+    assert accb.numel() >= n * Cc * 2 and x.numel() >= n * H * W * Cc and dy.numel() >= n * H * W * Cc
+    assert dx.numel() >= n * ((H + 2) * (W + 2) if padded_out else H * W) * Cc
+    if add is not None:
+        _require(add, torch.bfloat16, "add")
+        assert add.is_contiguous() and add.numel() >= n * H * W * Cc
+    for t, nm in ((scale, "scale"), (bias, "bias"), (dscale, "dscale"), (dbias, "dbias")):
+        _require(t, torch.float32, nm)
+        assert t.numel() >= Cc
+    _lib.check(_lib.lib().snapb200_gn_backward(
+        C.c_void_p(_ptr(x)), C.c_void_p(_ptr(dy)), C.c_void_p(_ptr(add)), n, H, W, Cc, C.c_void_p(_ptr(acc)),
+        C.c_int(acc.stride(0)), C.c_void_p(_ptr(scale)), C.c_void_p(_ptr(bias)), int(post_relu), int(padded_out),
+        C.c_void_p(_ptr(accb)), C.c_void_p(_ptr(dx)), C.c_void_p(_ptr(dscale)), C.c_void_p(_ptr(dbias)), _stream()))
+
+
+def wt_segments(b_fwd: torch.Tensor, cout: int, cin: int, taps: int, out: torch.Tensor) -> None:
+    """out bf16 [cin, taps*cout] <- forward GEMM operand b_fwd bf16 [>= cout, >= taps*cin] with every tap transposed."""
+    _require(b_fwd, torch.bfloat16, "b_fwd")
+    _require(out, torch.bfloat16, "out")
+    assert b_fwd.stride(1) == 1 and out.stride(1) == 1 and b_fwd.shape[0] >= cout and out.shape[0] >= cin
+    _lib.check(_lib.lib().snapb200_wt_segments(C.c_void_p(_ptr(b_fwd)), C.c_int(b_fwd.stride(0)), cout, cin, taps,
+                                               C.c_void_p(_ptr(out)), C.c_int(out.stride(0)), _stream()))
+
+
+def stdconv_backward(w: torch.Tensor, dws: torch.Tensor, dw: torch.Tensor) -> None:
+    """w, dws, dw f32 [K, Cout]: gradient w.r.t. the raw kernel from the gradient w.r.t. the standardised kernel."""
+    for t, nm in ((w, "w"), (dws, "dws"), (dw, "dw")):
+        _require(t, torch.float32, nm)
+        assert t.is_contiguous() and t.shape == w.shape and t.dim() == 2
+    _lib.check(_lib.lib().snapb200_stdconv_backward(C.c_void_p(_ptr(w)), C.c_void_p(_ptr(dws)), w.shape[0], w.shape[1],
+                                                    C.c_void_p(_ptr(dw)), _stream()))

@@ -1,0 +1,194 @@
+"""torch-CPU emulation of the C-ABI operators the training step of the 'resnet_stage' decoder launches, with the
+semantics `include/snapb200.h` documents (segment GEMM with row remap / residual / bias / ReLU / row mask / fused GroupNorm
+statistics, GroupNorm apply / backward, split-K weight gradients, ...).  TEST INFRASTRUCTURE ONLY: it lets the CPU suite
+run the product's launch plan (`snap_b200/semantic_train.py`: which buffer, which offset, which operand layout, in which
+order) against torch autograd of the oracle without a GPU; the kernels themselves are checked on the GPU."""
+import contextlib
+
+import numpy as np
+import torch
+
+from snap_b200 import image_encoder, ops
+
+BF = torch.bfloat16
+
+
+def _rd(t):
+    return t.to(BF).float()
+
+
+def gemm(a, b, out, *, m_rows=None, n=None, seg_off=(0,), seg_k=None, a_col0=0, residual=None, bias=None, row_mask=None,
+         relu=False, remap=None, bn=0, gn_acc=None, gn_acc_relu=None, gn_rows_per_img=0):
+    num_seg = len(seg_off)
+    seg_k = seg_k if seg_k is not None else b.shape[1] // num_seg
+    m_rows = m_rows if m_rows is not None else a.shape[0]
+    n = n if n is not None else b.shape[0]
+    A, B = a.float(), b.float()
+    acc = torch.zeros((m_rows, n), dtype=torch.float32)
+    idx0 = torch.arange(m_rows)
+    for s, off in enumerate(seg_off):
+        idx = idx0 + int(off)
+        ok = (idx >= 0) & (idx < A.shape[0])            # TMA zero fill outside the A matrix
+        rows = torch.zeros((m_rows, seg_k), dtype=torch.float32)
+        rows[ok] = A[idx[ok], a_col0:a_col0 + seg_k]
+        acc += rows @ B[:n, s * seg_k:(s + 1) * seg_k].T
+    y = _rd(acc)
+    if remap is not None:                                # A rows are (img, r, c) of an [R, C] layout -> dense (Ho, Wo) rows
+        R, Cc, r0, c0, Ho, Wo = remap
+        img, rem = idx0 // (R * Cc), idx0 % (R * Cc)
+        r, c = rem // Cc - r0, rem % Cc - c0
+        keep = (r >= 0) & (r < Ho) & (c >= 0) & (c < Wo)
+        orow = (img * Ho + r) * Wo + c
+        y, orow = y[keep], orow[keep]
+    else:
+        orow = idx0
+    if bias is not None:
+        y = _rd(y + bias.float()[:n])
+    if relu:
+        y = torch.relu(y)
+    if residual is not None:
+        y = _rd(y + residual.float()[orow, :n])
+    if row_mask is not None:
+        y = y * (row_mask[orow] != 0).float()[:, None]
+    y = y.to(out.dtype)
+    out[orow, :n] = y
+    if gn_acc is not None:
+        v = y.double()
+        img = orow // gn_rows_per_img
+        g = v.reshape(len(orow), 32, n // 32)
+        for i in img.unique():
+            sel = g[img == i]
+            gn_acc[0, i, :, 0] += sel.sum(dim=(0, 2))
+            gn_acc[0, i, :, 1] += (sel * sel).sum(dim=(0, 2))
+    return out
+
+
+def gn_stats(x, n, hw, Cc, pre_relu, acc):
+    v = x[: n * hw, :Cc].double().reshape(n, hw, 32, Cc // 32)
+    if pre_relu:
+        v = torch.relu(v)
+    acc[0, :, :, 0] += v.sum(dim=(1, 3))
+    acc[0, :, :, 1] += (v * v).sum(dim=(1, 3))
+
+
+def _stats(acc, n, hw, Cc):
+    s = acc.sum(dim=0)                                   # replicas
+    cnt = hw * (Cc // 32)
+    mu = s[..., 0] / cnt
+    var = torch.clamp(s[..., 1] / cnt - mu * mu, min=0)
+    return mu.float(), (1.0 / torch.sqrt(var + 1e-5)).float()     # [n, 32]
+
+
+def _xhat(x, n, hw, Cc, acc):
+    mu, rstd = _stats(acc, n, hw, Cc)
+    xg = x[: n * hw, :Cc].float().reshape(n, hw, 32, Cc // 32)
+    return ((xg - mu[:, None, :, None]) * rstd[:, None, :, None]).reshape(n, hw, Cc), rstd
+
+
+def _gn_forward(xh, scale, bias, post_relu):
+    y = _rd(_rd(_rd(xh) * _rd(scale.float())) + _rd(bias.float()))
+    return torch.relu(y) if post_relu else y
+
+
+def _padded_rows(n, H, W):
+    i = torch.arange(n)[:, None, None]
+    h = torch.arange(H)[None, :, None]
+    w = torch.arange(W)[None, None, :]
+    return ((i * (H + 2) + h + 1) * (W + 2) + w + 1).reshape(-1)
+
+
+def gn_apply(x, n, H, W, Cc, acc, scale, bias, pre_relu, post_relu, layout, out, out_sub=None):
+    assert not pre_relu and out_sub is None and layout in (ops.LAYOUT_DENSE, ops.LAYOUT_PADDED)
+    xh, _ = _xhat(x, n, H * W, Cc, acc)
+    y = _gn_forward(xh, scale, bias, post_relu).reshape(n * H * W, Cc).to(out.dtype)
+    if layout == ops.LAYOUT_DENSE:
+        out[: n * H * W, :Cc] = y
+    else:
+        out[_padded_rows(n, H, W), :Cc] = y
+
+
+def gn_backward(x, dy, n, H, W, Cc, acc, scale, bias, accb, dx, dscale, dbias, *, post_relu=True, padded_out=False,
+                add=None):
+    hw = H * W
+    xh, rstd = _xhat(x, n, hw, Cc, acc)
+    d = dy[: n * hw, :Cc].float().reshape(n, hw, Cc)
+    if post_relu:
+        d = d * (_gn_forward(xh, scale, bias, False) > 0).float()
+    sc = _rd(scale.float())[:Cc]
+    sd, sx = d.double().sum(1), (d * xh).double().sum(1)                              # [n, Cc]
+    dbias[:Cc] = sd.sum(0).float()
+    dscale[:Cc] = sx.sum(0).float()
+    m = hw * (Cc // 32)
+    s1 = (sd * sc.double()).reshape(n, 32, Cc // 32).sum(-1) / m
+    s2 = (sx * sc.double()).reshape(n, 32, Cc // 32).sum(-1) / m
+    rep = lambda t: t.float().repeat_interleave(Cc // 32, dim=1)[:, None, :]           # [n, 1, Cc]
+    r = rep(rstd) * (d * sc - rep(s1) - xh * rep(s2))
+    if add is not None:
+        r = r + add[: n * hw, :Cc].float().reshape(n, hw, Cc)
+    r = r.reshape(n * hw, Cc).to(dx.dtype)
+    if padded_out:
+        dx.view(-1, Cc)[_padded_rows(n, H, W)] = r
+    else:
+        dx.view(-1, Cc)[: n * hw] = r
+
+
+def dense_wgrad(x, dy, M, K, N, dW, db, workspace=None):
+    assert M % 16 == 0 and x.shape[0] >= M and dy.shape[0] >= M
+    dW[:] = (x[:M, :K].double().T @ dy[:M, :N].double()).float()
+    if db is not None:
+        db[:N] = dy[:M, :N].double().sum(0).float()
+
+
+def cast_pad_bf16(src, dst):
+    dst.zero_()
+    dst[:, : src.shape[1]] = src.to(BF)
+
+
+def relu_bwd(h, dx, elems):
+    m = (h.reshape(-1)[:elems].float() > 0)
+    flat = dx.reshape(-1)
+    flat[:elems] = torch.where(m, flat[:elems], torch.zeros((), dtype=dx.dtype))
+
+
+def wt_segments(b_fwd, cout, cin, taps, out):
+    for t in range(taps):
+        out[:cin, t * cout:(t + 1) * cout] = b_fwd[:cout, t * cin:(t + 1) * cin].T
+
+
+def stdconv_backward(w, dws, dw):
+    w64, d64 = w.double(), dws.double()
+    mu = w64.mean(0, keepdim=True)
+    rstd = 1.0 / torch.sqrt(((w64 - mu) ** 2).mean(0, keepdim=True) + 1e-10)
+    ws = (w64 - mu) * rstd
+    dw[:] = (rstd * (d64 - d64.mean(0, keepdim=True) - ws * (d64 * ws).mean(0, keepdim=True))).float()
+
+
+def _bank_run(self):
+    """`_WeightBank.run`: StdConv standardisation (resnet.py:34-41,73-79) + relayout to the bf16 [Cout, K] B operands."""
+    off = 0
+    for i, (_, k, cout, ldb, std) in enumerate(self.entries):
+        w = self.master[off: off + k * cout].view(k, cout).float()
+        off += k * cout
+        if std:
+            w = w - w.mean(0, keepdim=True)
+            w = w / torch.sqrt((w * w).mean(0, keepdim=True) + 1e-10)
+        self.b_mats[i].zero_()
+        self.b_mats[i][:cout, :k] = w.T.to(BF)
+
+
+@contextlib.contextmanager
+def emulated_ops():
+    """Replace the product's operator wrappers (and the weight bank's device pass) by the emulation above."""
+    names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
+             "stdconv_backward")
+    saved = {n: getattr(ops, n) for n in names}
+    saved_run = image_encoder._WeightBank.run
+    try:
+        for n in names:
+            setattr(ops, n, globals()[n])
+        image_encoder._WeightBank.run = _bank_run
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+        image_encoder._WeightBank.run = saved_run

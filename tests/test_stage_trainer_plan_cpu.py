@@ -1,0 +1,87 @@
+"""The launch plan of the 'resnet_stage' head training step (`snap_b200/semantic_train.py`) executed on the CPU with
+the operator layer emulated in torch (`tests/ops_emulation.py`) against torch autograd of the oracle
+(`oracle/semantic_net.py::stage_head_forward_torch`, whose forward is the NumPy `semantic_decoder` pinned against the
+reference's own `SemanticNet.__call__`): buffers, offsets, operand layouts and launch order of forward and backward.
+The CUDA kernels behind the operators are checked on the GPU (tests/test_zz_stage_trainer_gpu.py)."""
+import numpy as np
+import torch
+
+from ops_emulation import emulated_ops
+from util import F, bf16_np, rd_bf16
+
+
+def _setup(seed, B=2, G=8):
+    from snap_b200 import configs, params
+    rng = np.random.default_rng(seed)
+    cfg = configs.semantic_net()
+    p = params.round_to_bf16(params.perturb_affine(rng, params.init_semantic_decoder(rng, cfg)))
+    feats = bf16_np(rng.standard_normal((B, G, G, 128)) * 0.7)
+    valid = rng.random((B, G, G)) < 0.8
+    feats = feats * valid[..., None]
+    return cfg, p, feats, valid, rng
+
+
+def _torch_tree(tree, grad):
+    return {k: (_torch_tree(v, grad) if isinstance(v, dict) else
+                torch.from_numpy(np.ascontiguousarray(v, dtype=F)).requires_grad_(grad)) for k, v in tree.items()}
+
+
+def _flat(tree, pre=()):
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            yield from _flat(v, pre + (k,))
+        else:
+            yield pre + (k,), v
+
+
+def test_torch_oracle_forward_equals_numpy_oracle():
+    from oracle import semantic_net as osn
+    cfg, p, feats, valid, _ = _setup(1)
+    for rd in (lambda t: t, rd_bf16):
+        ref = osn.semantic_decoder(feats, valid, p, rd)
+        got = osn.stage_head_forward_torch(torch.from_numpy(feats), valid, _torch_tree(p, False), rd).numpy()
+        assert got.shape == ref.shape == (2, 8, 8, 12)
+        assert np.abs(got - ref).max() <= 1e-5 * (1 + np.abs(ref).max())
+
+
+def test_stage_trainer_launch_plan_matches_autograd():
+    from oracle import semantic_net as osn
+    from snap_b200 import semantic_train, types
+    cfg, p, feats, valid, rng = _setup(2)
+    B, G = feats.shape[:2]
+    plane = types.FeaturePlane(torch.from_numpy(feats).to(torch.bfloat16), torch.from_numpy(valid.astype(np.uint8)))
+    Gmat = bf16_np(rng.standard_normal((B, G, G, 12)) * 0.05)
+    with emulated_ops():
+        tr = semantic_train.StageHeadTrainer(cfg, p, torch.device("cpu"))
+        pred = tr.forward(plane)
+        logits = torch.cat([pred["logits_areas"], pred["logits_objects_exclusive"], pred["logits_objects_independent"]], -1)
+        buf = tr._buffers(B, G, G)
+        buf["dlogits"].zero_()
+        buf["dlogits"][: B * G * G, :12] = torch.from_numpy(Gmat * valid[..., None]).reshape(-1, 12).to(torch.bfloat16)
+        tr.backward(plane, buf)
+        grads, now = tr.grads_tree(), tr.params_tree()
+    # forward: the plan reproduces the oracle in bf16-emulation mode
+    tp = _torch_tree(p, True)
+    ref_logits = osn.stage_head_forward_torch(torch.from_numpy(feats), valid, tp, rd_bf16)
+    got = logits.numpy()
+    assert not got[~valid].any()
+    assert np.abs(got - ref_logits.detach().numpy()).max() <= 3e-2 * np.abs(ref_logits.detach().numpy()).max()
+    # parameters round-trip through the trainer unchanged, with the Flax names and shapes
+    for path, v in _flat(p):
+        a = now
+        for k in path:
+            a = a[k]
+        assert a.shape == np.asarray(v).shape and np.array_equal(a, np.asarray(v, dtype=F)), path
+    # backward: every parameter gradient vs autograd of loss = sum(logits * G)
+    (ref_logits * torch.from_numpy(Gmat)).sum().backward()
+    worst = 0.0
+    for path, t in _flat(tp):
+        g = grads
+        for k in path:
+            g = g[k]
+        r = t.grad.numpy()
+        assert g.shape == r.shape, path
+        err = np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+        worst = max(worst, err)
+        assert err < 3e-2, ("/".join(path), err, np.linalg.norm(r))
+    print(f"worst relative gradient error over {len(list(_flat(tp)))} parameter arrays: {worst:.4f}")
