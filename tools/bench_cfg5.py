@@ -1,8 +1,9 @@
 """BASELINE.json configs[4] ("semantic-mapping fine-tune head on frozen BEV features") per GPU: B scenes per step =
 frozen BEVMapper forward (4 StreetView views 640x480 -> 128 x 128 BEV) + one training step of the semantic head
-(default 'mlp' decoder: forward, loss, backward, gradient mean over ranks, Adam).  CUDA-event timing after warm-up.
+('mlp' decoder, or `--decoder resnet_stage` = the decoder snap/configs/train_semantics.py:27-30 fine-tunes: forward, loss,
+backward, gradient mean over ranks, Adam).  CUDA-event timing after warm-up.
 
-    python tools/bench_cfg5.py [--batch 4] [--steps 10]                       # one GPU
+    python tools/bench_cfg5.py [--batch 4] [--steps 10] [--decoder mlp|resnet_stage]    # one GPU
     python -m torch.distributed.run --nproc-per-node N tools/bench_cfg5.py    # N GPUs (NCCL all-reduce of the head grads)
 """
 import argparse
@@ -22,6 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--decoder", choices=("mlp", "resnet_stage"), default="mlp")
 args = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -33,7 +35,8 @@ G, hw, B = 128, (480, 640), args.batch
 GT = ("road", "crosswalk", "sidewalk", "terrain", "building", "fence", "pole", "tree", "traffic_sign", "traffic_light", "street_light")
 rng = np.random.default_rng(5)
 cfg = configs.semantic_net()
-cfg.decoder_type, cfg.decoder_dim, cfg.mlp_num_layers = "mlp", 128, 2
+if args.decoder == "mlp":
+    cfg.decoder_type, cfg.decoder_dim, cfg.mlp_num_layers = "mlp", 128, 2
 cfg.bev_mapper = configs.bev_mapper(("streetview",))
 cfg.area_frequencies = tuple(zip(cfg.area_classes, (0.036434, 0.226553, 0.446990, 0.085374, 0.204649)))
 cfg.object_frequencies = (("fence", 0.006257), ("pole", 0.001172), ("tree", 0.001924), ("traffic_sign", 0.000960),
@@ -41,12 +44,19 @@ cfg.object_frequencies = (("fence", 0.006257), ("pole", 0.001172), ("tree", 0.00
 grid = types.Grid2D((G, G), 0.2)
 mapper = bev_mapper.BEVMapper(cfg.bev_mapper, grid)
 mp = params.round_to_bf16(params.init_bev_mapper(np.random.default_rng(7), cfg.bev_mapper))
-hp = params.round_to_bf16(params.init_mlp(np.random.default_rng(8), 128, (128, 128, 12)))
+if args.decoder == "mlp":
+    hp = params.round_to_bf16(params.init_mlp(np.random.default_rng(8), 128, (128, 128, 12)))
+else:
+    hp = params.round_to_bf16(params.init_semantic_decoder(np.random.default_rng(8), cfg))
 data = synthetic.make_tile(rank * 100 + 3, 4, hw, G, batch=B)
 data["images"] = torch.from_numpy(data["images"]).to(dev)
 masks = np.random.default_rng(9 + rank).random((B, G, G, len(GT))) < 0.2
 model = semantic_net.SemanticNetModel(cfg, GT)
-trainer = semantic_net.MLPHeadTrainer(cfg, hp, dev, lr=5e-5)
+if args.decoder == "mlp":
+    trainer = semantic_net.MLPHeadTrainer(cfg, hp, dev, lr=5e-5)
+else:
+    from snap_b200 import semantic_train
+    trainer = semantic_train.StageHeadTrainer(cfg, hp, dev, lr=5e-5)
 labels = {"rasters": {"gt_semantics": torch.from_numpy(masks.view(np.uint8)).to(dev)}}   # resident, like the images
 
 
@@ -80,7 +90,8 @@ plane = types.FeaturePlane(plane.features.clone(), plane.valid.clone())
 ms_head = timed(lambda: head_only(plane), args.steps)
 if rank == 0:
     print(json.dumps({"workload": f"cfg5 per GPU: {B} scenes per step = frozen BEV forward (4 views 640x480, G=128) + head training "
-                                  f"step ('mlp' decoder 128-128-128-12: forward, loss, backward, all-reduce, Adam); bf16",
+                                  f"step ({'mlp decoder 128-128-128-12' if args.decoder == 'mlp' else 'resnet_stage decoder: Dense 128-256, 2 bottleneck units, MLP 256-256-12'}"
+                                  f": forward, loss, backward, all-reduce, Adam); bf16",
                       "n_gpus": world, "batch_per_gpu": B, "ms_per_step": round(ms, 3), "head_train_step_ms": round(ms_head, 3),
                       "scenes_per_s": round(world * B / (ms * 1e-3), 1), "loss": float(loss.mean().item())}), flush=True)
 if world > 1:
