@@ -718,3 +718,31 @@ def stdconv_backward(w: torch.Tensor, dws: torch.Tensor, dw: torch.Tensor) -> No
         assert t.is_contiguous() and t.shape == w.shape and t.dim() == 2
     _lib.check(_lib.lib().snapb200_stdconv_backward(C.c_void_p(_ptr(w)), C.c_void_p(_ptr(dws)), w.shape[0], w.shape[1],
                                                     C.c_void_p(_ptr(dw)), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# backward of the lift (csrc/lift_backward.cu)
+# --------------------------------------------------------------------------------------------
+def lift_gather_pool_backward(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor,
+                              ys: torch.Tensor, zs: torch.Tensor, dstats: torch.Tensor, gimg: torch.Tensor) -> None:
+    """gimg f32 [V, Hf, Wf, D+S] += scatter-add of the cotangent of the statistics rows (zero gimg first)."""
+    _require(fimg, torch.bfloat16, "fimg")
+    _require(dstats, torch.bfloat16, "dstats")
+    _require(gimg, torch.float32, "gimg")
+    assert gimg.is_contiguous() and gimg.numel() == p.V * p.Hf * p.Wf * p.CF
+    assert dstats.is_contiguous() and dstats.shape[1] == p.stats_ld and dstats.shape[0] >= p.X * p.Y * p.Z
+    _lib.check(_lib.lib().snapb200_lift_gather_pool_backward(
+        C.byref(p), C.c_void_p(_ptr(views)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
+        C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(dstats)), C.c_void_p(_ptr(gimg)), _stream()))
+
+
+def vertical_max_backward(vol: torch.Tensor, valid: torch.Tensor, dplane: torch.Tensor, cells: int, Z: int, Cc: int,
+                          dvol: torch.Tensor) -> None:
+    for t, nm in ((vol, "vol"), (dplane, "dplane"), (dvol, "dvol")):
+        _require(t, torch.bfloat16, nm)
+        assert t.is_contiguous()
+    _require(valid, torch.uint8, "valid")
+    assert vol.numel() >= cells * Z * Cc and dvol.numel() >= cells * Z * Cc and dplane.numel() >= cells * Cc
+    _lib.check(_lib.lib().snapb200_vertical_max_backward(
+        C.c_void_p(_ptr(vol)), C.c_void_p(_ptr(valid)), C.c_void_p(_ptr(dplane)), C.c_longlong(cells), Z, Cc,
+        C.c_void_p(_ptr(dvol)), _stream()))

@@ -1,0 +1,80 @@
+"""Backward kernels of the lift (csrc/lift_backward.cu) on the GPU against torch autograd of tests/lift_torch_ref.py
+(whose forward equals the NumPy oracle and whose autograd equals the closed forms, tests/test_lift_backward_ref_cpu.py).
+
+NOTE: written after this round's GPU budget was spent; collected LAST and xfail(strict=False) until the first B200 run
+(see tests/test_zzz_stage_trainer_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from util import F, bf16_np, rel_l2, to_oracle_geometry
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
+              pytest.mark.xfail(strict=False, reason="first B200 run pending (written after the round-1 GPU budget was spent)")]
+
+
+@pytest.mark.parametrize("V,layout", [(3, {}), (4, dict(spacing=0.5, same_side=True))])
+def test_lift_gather_pool_backward_vs_autograd(V, layout):
+    from lift_torch_ref import gather_pool_stats
+    from oracle import bev_mapper as obm, grids as ogrids, streetview_encoder as osv
+    from snap_b200 import bev_mapper, configs, ops, streetview_encoder as sve, synthetic, types
+    G, hw = 24, (64, 96)
+    hf, wf = 16, 24
+    rng = np.random.default_rng(40 + V)
+    data = synthetic.make_tile(6, V, hw, G, **layout)
+    mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), types.Grid2D((G, G), 0.2))
+    xs, ys, zs = mapper.build_xyz_grid(data)
+    Z = zs.shape[1]
+    N = G * G * Z
+    fimg_np = bf16_np(rng.standard_normal((V, hf, wf, 160)))
+    dstats_np = bf16_np(rng.standard_normal((N, 288)) * 0.1)
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(dev)
+    cfg = configs.streetview_encoder()
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    gimg = torch.zeros((V, hf, wf, 160), dtype=torch.float32, device=dev)
+    ops.lift_gather_pool_backward(lp, views, t(fimg_np).to(torch.bfloat16), t(xs), t(ys), t(zs[0]),
+                                  t(dstats_np).to(torch.bfloat16), gimg)
+    torch.cuda.synchronize()
+    got = gimg.cpu().numpy()
+    # autograd reference on the same (bf16-representable) inputs, geometry from the NumPy oracle
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    p2d, vis, depth, _ = osv.project_points_to_views(oT, ocam, xyz.reshape(-1, 3))
+    ft = torch.from_numpy(fimg_np).requires_grad_(True)
+    stats = gather_pool_stats(ft, p2d, vis, depth)
+    (stats * torch.from_numpy(dstats_np[:, :257])).sum().backward()
+    ref = ft.grad.numpy()
+    multi = (vis.sum(-1) >= 2).mean()
+    e_f, e_s = rel_l2(got[..., :128], ref[..., :128]), rel_l2(got[..., 128:], ref[..., 128:])
+    print(f"V={V}: visible {vis.any(-1).mean():.3f}, seen by >= 2 views {multi:.3f}; rel_l2 features {e_f:.5f}, scale logits {e_s:.5f}")
+    assert np.abs(ref).sum() > 0 and (not layout or multi > 0.01)
+    # the forward's bf16 materialisation points (features, scores) are straight-through in the kernel
+    assert e_f < 1e-2 and e_s < 2e-2
+    assert not got[ref == 0].any() or np.abs(got[ref == 0]).max() < 1e-6
+
+
+def test_vertical_max_backward_vs_autograd():
+    from snap_b200 import ops
+    rng = np.random.default_rng(9)
+    cells, Z, C = 300, 20, 128
+    vol = bf16_np(np.round(rng.standard_normal((cells, Z, C)) * 2) / 2)          # coarse values: many tied maxima
+    valid = rng.random((cells, Z)) < 0.6
+    valid[:7] = False                                                           # columns without any valid voxel
+    dplane = bf16_np(rng.standard_normal((cells, C)))
+    dvol = torch.full((cells, Z, C), 7.0, dtype=torch.bfloat16, device="cuda")  # garbage: every element is overwritten
+    cu = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
+    ops.vertical_max_backward(cu(vol, torch.bfloat16), cu(valid.astype(np.uint8), torch.uint8), cu(dplane, torch.bfloat16),
+                              cells, Z, C, dvol)
+    torch.cuda.synchronize()
+    vt = torch.from_numpy(vol.astype(np.float64)).requires_grad_(True)
+    m = torch.from_numpy(valid)[..., None]
+    masked = torch.where(m, vt, torch.full_like(vt, -float("inf")))               # bev_mapper.py:58-60,80
+    plane = torch.where(m.any(1), masked.amax(1), torch.zeros((), dtype=torch.float64))   # :86
+    (plane * torch.from_numpy(dplane.astype(np.float64))).sum().backward()
+    ref = vt.grad.numpy()
+    got = dvol.float().cpu().numpy()
+    assert (np.abs(ref) > 0).any(1).sum() > 0 and not got[:7].any() and not got[~valid].any()
+    assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-6      # one bf16 rounding of g / count
