@@ -47,3 +47,26 @@ def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, dept
     smax = torch.where(v_, score, neg).amax(-1, keepdim=True)
     stats = torch.cat([mean, var, smax], -1)
     return torch.where(any_v[:, None], stats, torch.zeros_like(stats))
+
+
+def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd):
+    """Autograd through proj MLP -> gather / pooling -> fusion MLP -> mask (:282) -> vertical max (bev_mapper.py:80-86) with
+    the forward's materialisation points `rd`; loss = sum(plane * dplane).  Returns the forward tensors the product's
+    backward consumes, the parameter gradients {proj_mlp, fusion_mlp} and the cotangent of the encoder features."""
+    tp = {k: {n: {a: torch.from_numpy(np.ascontiguousarray(v, dtype=F)).requires_grad_(True) for a, v in d.items()}
+              for n, d in t.items()} for k, t in svp.items() if k in ("proj_mlp", "fusion_mlp")}
+    x = torch.from_numpy(enc).requires_grad_(True)
+    crop = torch.relu(x)
+    fimg = rd(rd(crop @ tp["proj_mlp"]["Dense_0"]["kernel"]) + tp["proj_mlp"]["Dense_0"]["bias"])
+    stats = rd(gather_pool_stats(fimg.reshape(V, hf, wf, -1), p2d, vis, depth))
+    hid = torch.relu(rd(rd(stats @ tp["fusion_mlp"]["Dense_0"]["kernel"]) + tp["fusion_mlp"]["Dense_0"]["bias"]))
+    vol = rd(rd(hid @ tp["fusion_mlp"]["Dense_1"]["kernel"]) + tp["fusion_mlp"]["Dense_1"]["bias"])
+    valid = torch.from_numpy(vis.any(-1))
+    vol = torch.where(valid[:, None], vol, torch.zeros(()))
+    m = valid.reshape(cells, Z, 1)
+    masked = torch.where(m, vol.reshape(cells, Z, -1), torch.full((), -float("inf")))
+    plane = torch.where(m.any(1), masked.amax(1), torch.zeros(()))
+    (plane * torch.from_numpy(dplane)).sum().backward()
+    grads = {k: {n: {a: t.grad.numpy() for a, t in d.items()} for n, d in tt.items()} for k, tt in tp.items()}
+    fwd = dict(crop=crop.detach().numpy(), fimg=fimg.detach().numpy(), vol=vol.detach().numpy(), plane=plane.detach().numpy())
+    return fwd, grads, x.grad.numpy()

@@ -176,16 +176,52 @@ def _bank_run(self):
         self.b_mats[i][:cout, :k] = w.T.to(BF)
 
 
+def vertical_max_backward(vol, valid, dplane, cells, Z, Cc, dvol):
+    v = vol.reshape(-1)[: cells * Z * Cc].float().reshape(cells, Z, Cc)
+    m = (valid.reshape(-1)[: cells * Z] != 0).reshape(cells, Z, 1)
+    mv = torch.where(m, v, torch.full_like(v, -float("inf")))
+    tie = (mv == mv.amax(1, keepdim=True)) & m
+    cnt = tie.sum(1, keepdim=True).clamp(min=1)
+    g = dplane.reshape(-1)[: cells * Cc].float().reshape(cells, 1, Cc) / cnt
+    dvol.reshape(-1)[: cells * Z * Cc] = torch.where(tie, g.expand(cells, Z, Cc), torch.zeros(())).to(dvol.dtype).reshape(-1)
+
+
+def make_lift_emulation(p2d, vis, depth):
+    """`ops.lift_gather_pool` / `ops.lift_gather_pool_backward` for ONE fixed scene whose projection (p2d, vis, depth:
+    NumPy oracle) is captured here; the float path is tests/lift_torch_ref.py (forward checked against the NumPy oracle,
+    autograd against the closed forms of the CUDA kernel, tests/test_lift_backward_ref_cpu.py)."""
+    from lift_torch_ref import gather_pool_stats
+
+    def lift_gather_pool(lp, views, fimg, xs, ys, zs, stats, valid, dbg_vis=None, dbg_taps=None):
+        N = lp.X * lp.Y * lp.Z
+        st = gather_pool_stats(fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF), p2d, vis, depth, lp.D)
+        stats[:N].zero_()
+        stats[:N, : st.shape[1]] = st.to(stats.dtype)
+        valid[:N] = torch.from_numpy(vis.any(-1).astype(np.uint8))
+
+    def lift_gather_pool_backward(lp, views, fimg, xs, ys, zs, dstats, gimg):
+        N = lp.X * lp.Y * lp.Z
+        f = fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF).clone().requires_grad_(True)
+        st = gather_pool_stats(f, p2d, vis, depth, lp.D)
+        (st * dstats[:N, : st.shape[1]].float()).sum().backward()
+        gimg += f.grad.reshape(gimg.shape)
+
+    return {"lift_gather_pool": lift_gather_pool, "lift_gather_pool_backward": lift_gather_pool_backward}
+
+
 @contextlib.contextmanager
-def emulated_ops():
+def emulated_ops(extra=None):
     """Replace the product's operator wrappers (and the weight bank's device pass) by the emulation above."""
     names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
-             "stdconv_backward")
+             "stdconv_backward", "vertical_max_backward")
+    table = {n: globals()[n] for n in names}
+    table.update(extra or {})
+    names = tuple(table)
     saved = {n: getattr(ops, n) for n in names}
     saved_run = image_encoder._WeightBank.run
     try:
         for n in names:
-            setattr(ops, n, globals()[n])
+            setattr(ops, n, table[n])
         image_encoder._WeightBank.run = _bank_run
         yield
     finally:

@@ -78,3 +78,71 @@ def test_vertical_max_backward_vs_autograd():
     got = dvol.float().cpu().numpy()
     assert (np.abs(ref) > 0).any(1).sum() > 0 and not got[:7].any() and not got[~valid].any()
     assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-6      # one bf16 rounding of g / count
+
+
+def test_lift_backward_chain_vs_autograd():
+    """proj MLP -> lift -> fusion MLP -> vertical max forward on the GPU (the verified forward kernels), then
+    `streetview_train.LiftBackward.scene_backward`; parameter gradients and the encoder-feature cotangent vs autograd of
+    the same chain (tests/lift_torch_ref.py::chain_reference)."""
+    from lift_torch_ref import chain_reference
+    from oracle import bev_mapper as obm, grids as ogrids, streetview_encoder as osv
+    from snap_b200 import bev_mapper, configs, ops, params, streetview_encoder as sve, streetview_train, synthetic, types
+    from snap_b200.image_encoder import _WeightBank
+    from util import rd_bf16
+    G, V, hw = 24, 3, (64, 96)
+    hf, wf = 16, 24
+    rng = np.random.default_rng(12)
+    data = synthetic.make_tile(6, V, hw, G, spacing=0.5, same_side=True)
+    mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), types.Grid2D((G, G), 0.2))
+    xs, ys, zs = mapper.build_xyz_grid(data)
+    Z = zs.shape[1]
+    N, cells, rows_img = G * G * Z, G * G, V * hf * wf
+    cfg = configs.streetview_encoder()
+    svp = params.round_to_bf16(params.perturb_affine(rng, {"proj_mlp": params.init_mlp(rng, 128, (160,)),
+                                                           "fusion_mlp": params.init_mlp(rng, 257, (256, 128))}))
+    enc = bf16_np(rng.standard_normal((rows_img, 128)))
+    dplane = bf16_np(rng.standard_normal((cells, 128)) * 0.1)
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(dev)
+    bf = lambda a: t(a).to(torch.bfloat16)
+    # forward on the GPU
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    bank = _WeightBank(torch.device(dev))
+    wp = bank.add(svp["proj_mlp"]["Dense_0"]["kernel"], False)
+    w0 = bank.add(svp["fusion_mlp"]["Dense_0"]["kernel"], False, 32)
+    w1 = bank.add(svp["fusion_mlp"]["Dense_1"]["kernel"], False)
+    bank.finalize(); bank.run()
+    crop = torch.relu(bf(enc))                                             # test-side plumbing for crop_relu's output
+    fimg = torch.zeros((rows_img, 160), dtype=torch.bfloat16, device=dev)
+    ops.gemm(crop, bank.b_mats[wp], fimg, m_rows=rows_img, bias=t(svp["proj_mlp"]["Dense_0"]["bias"]))
+    stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
+    valid = torch.zeros(N, dtype=torch.uint8, device=dev)
+    xs_d, ys_d, zs_d = t(xs), t(ys), t(zs[0])
+    ops.lift_gather_pool(lp, views, fimg, xs_d, ys_d, zs_d, stats, valid)
+    hid = torch.zeros((N, 256), dtype=torch.bfloat16, device=dev)
+    vol = torch.zeros((N, 128), dtype=torch.bfloat16, device=dev)
+    ops.gemm(stats, bank.b_mats[w0], hid, m_rows=N, seg_k=288, bias=t(svp["fusion_mlp"]["Dense_0"]["bias"]), relu=True)
+    ops.gemm(hid, bank.b_mats[w1], vol, m_rows=N, bias=t(svp["fusion_mlp"]["Dense_1"]["bias"]), row_mask=valid)
+    # backward
+    lb = streetview_train.LiftBackward(svp, torch.device(dev))
+    lb.zero_grads()
+    dcrop = lb.scene_backward(lp, views, fimg, crop, xs_d, ys_d, zs_d, vol, valid, bf(dplane))
+    torch.cuda.synchronize()
+    got = lb.grads_tree()
+    # reference
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    p2d, vis, depth, _ = osv.project_points_to_views(oT, ocam, xyz.reshape(-1, 3))
+    fwd, ref, ref_x = chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd_bf16)
+    assert np.array_equal(valid.cpu().numpy().astype(bool), vis.any(-1))
+    assert rel_l2(vol.float().cpu().numpy(), fwd["vol"]) < 5e-3
+    for k in ("proj_mlp", "fusion_mlp"):
+        for n, d in ref[k].items():
+            for a, r in d.items():
+                err = rel_l2(got[k][n][a], r)
+                print(f"{k}/{n}/{a}: |grad| {np.linalg.norm(r):.3e} rel err {err:.4f}")
+                # the max routes the cotangent through the arg-max level: a bf16 flip between near-tied levels moves it
+                assert err < 5e-2
+    assert rel_l2(dcrop[:rows_img].float().cpu().numpy(), ref_x) < 5e-2
