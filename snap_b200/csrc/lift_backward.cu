@@ -281,3 +281,112 @@ int snapb200_vertical_max_backward(const void* vol, const uint8_t* valid, const 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Matching head (snap/models/bev_mapper.py:284-291: Dense 128 -> 32, snap/models/layers.py:45-52 L2 normalisation, mask)
+// and modality fusion (bev_mapper.py:225-252, 'max' over the stacked modality axis) backward.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace snapb200 {
+
+// Warp per cell, lane = output channel.  Recomputes y = bf16(bf16(x K) + b) and n = |y| like match_head_kernel, then
+//   dy = (dz - z (z . dz)) / n   for valid cells with n >= eps (z = y / n), else 0
+// written as bf16 rows [cells, 32]; the Dense backward proper (dK = x^T dy, db, dx = dy K^T) runs on the split-K and
+// GEMM kernels.
+__global__ void __launch_bounds__(256)
+match_head_bwd_kernel(const __nv_bfloat16* __restrict__ plane, const uint8_t* __restrict__ valid, long long cells, int C,
+                      const float* __restrict__ kernel /*[C,32]*/, const float* __restrict__ bias,
+                      const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dy) {
+  extern __shared__ float wsm_b[];  // [C][32]
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) wsm_b[i] = kernel[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float b = bias[lane];
+  for (long long cell = (long long)blockIdx.x * 8 + warp; cell < cells; cell += (long long)gridDim.x * 8) {
+    float g = 0.f;
+    if (valid[cell]) {  // warp-uniform
+      float acc = 0.f;
+      for (int k0 = 0; k0 < C; k0 += 32) {
+        const float xk = __bfloat162float(plane[cell * C + k0 + lane]);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc += __shfl_sync(0xffffffffu, xk, k) * wsm_b[(k0 + k) * 32 + lane];
+      }
+      const float y = bf16_round(bf16_round(acc) + b);
+      const float dz = __bfloat162float(dout[cell * 32 + lane]);
+      float ss = y * y, zd = y * dz;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        zd += __shfl_xor_sync(0xffffffffu, zd, o);
+      }
+      const float nrm = sqrtf(ss);
+      if (nrm >= 1e-5f) {
+        const float z = y / nrm;
+        g = (dz - z * (zd / nrm)) / nrm;  // zd / nrm = z . dz
+      }
+    }
+    dy[cell * 32 + lane] = __float2bfloat16(g);
+  }
+}
+
+// da / db from dout for out = max over the valid ones of (a, b); a tie between two valid modalities splits evenly
+__global__ void fuse_max_bwd_kernel(const __nv_bfloat16* __restrict__ a, const uint8_t* __restrict__ va,
+                                    const __nv_bfloat16* __restrict__ b, const uint8_t* __restrict__ vb,
+                                    const __nv_bfloat16* __restrict__ dout, long long cells, int C,
+                                    __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ db) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cells * cv) return;
+  const int c8 = (int)(idx % cv);
+  const long long cell = idx / cv;
+  const bool oa = va[cell] != 0, ob = (vb == nullptr) ? true : vb[cell] != 0;
+  float fa[8], fb[8], g[8], ga[8], gb[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a + cell * C + c8 * 8)), fa);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + cell * C + c8 * 8)), fb);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dout + cell * C + c8 * 8)), g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = gb[j] = 0.f;
+    if (oa && ob) {
+      if (fa[j] > fb[j]) ga[j] = g[j];
+      else if (fb[j] > fa[j]) gb[j] = g[j];
+      else ga[j] = gb[j] = 0.5f * g[j];
+    } else if (oa) {
+      ga[j] = g[j];
+    } else if (ob) {
+      gb[j] = g[j];
+    }
+  }
+  *reinterpret_cast<uint4*>(da + cell * C + c8 * 8) =
+      make_uint4(pack_bf16(ga[0], ga[1]), pack_bf16(ga[2], ga[3]), pack_bf16(ga[4], ga[5]), pack_bf16(ga[6], ga[7]));
+  *reinterpret_cast<uint4*>(db + cell * C + c8 * 8) =
+      make_uint4(pack_bf16(gb[0], gb[1]), pack_bf16(gb[2], gb[3]), pack_bf16(gb[4], gb[5]), pack_bf16(gb[6], gb[7]));
+}
+
+}  // namespace snapb200
+
+extern "C" {
+
+int snapb200_match_head_backward(const void* plane, const uint8_t* valid, long long cells, int C, const float* kernel,
+                                 const float* bias, const void* dout, void* dy, void* stream) {
+  SNAP_REQUIRE(plane && valid && kernel && bias && dout && dy, "null pointer");
+  SNAP_REQUIRE(cells >= 1 && C % 32 == 0 && C >= 32 && C <= 256, "C must be a multiple of 32 in [32, 256]");
+  const size_t smem = (size_t)C * 32 * sizeof(float);
+  long long blocks = (cells + 7) / 8;
+  const long long cap = 8LL * snapb200::num_sms();
+  if (blocks > cap) blocks = cap;
+  snapb200::match_head_bwd_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)plane, valid, cells, C, kernel, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dy);
+  return snapb200::check_launch("match_head_bwd_kernel");
+}
+
+int snapb200_fuse_max_backward(const void* a, const uint8_t* va, const void* b, const uint8_t* vb, const void* dout,
+                               long long cells, int C, void* da, void* db, void* stream) {
+  SNAP_REQUIRE(a && va && b && dout && da && db && C % 8 == 0 && cells >= 1, "bad arguments");
+  const long long total = cells * (C / 8);
+  snapb200::fuse_max_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, va, (const __nv_bfloat16*)b, vb, (const __nv_bfloat16*)dout, cells, C,
+      (__nv_bfloat16*)da, (__nv_bfloat16*)db);
+  return snapb200::check_launch("fuse_max_bwd_kernel");
+}
+
+}  // extern "C"

@@ -746,3 +746,28 @@ def vertical_max_backward(vol: torch.Tensor, valid: torch.Tensor, dplane: torch.
     _lib.check(_lib.lib().snapb200_vertical_max_backward(
         C.c_void_p(_ptr(vol)), C.c_void_p(_ptr(valid)), C.c_void_p(_ptr(dplane)), C.c_longlong(cells), Z, Cc,
         C.c_void_p(_ptr(dvol)), _stream()))
+
+
+def match_head_backward(plane: torch.Tensor, valid: torch.Tensor, cells: int, Cc: int, kernel: torch.Tensor,
+                        bias: torch.Tensor, dout: torch.Tensor, dy: torch.Tensor) -> None:
+    """dy bf16 [cells, 32] = cotangent of the matching Dense output from dout = cotangent of mask(normalize(.))."""
+    for t, nm in ((plane, "plane"), (dout, "dout"), (dy, "dy")):
+        _require(t, torch.bfloat16, nm)
+        assert t.is_contiguous()
+    _require(kernel, torch.float32, "kernel")
+    _require(bias, torch.float32, "bias")
+    _require(valid, torch.uint8, "valid")
+    assert kernel.shape == (Cc, 32) and kernel.is_contiguous() and dout.numel() >= cells * 32 and dy.numel() >= cells * 32
+    _lib.check(_lib.lib().snapb200_match_head_backward(
+        C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Cc, C.c_void_p(_ptr(kernel)),
+        C.c_void_p(_ptr(bias)), C.c_void_p(_ptr(dout)), C.c_void_p(_ptr(dy)), _stream()))
+
+
+def fuse_max_backward(a: torch.Tensor, va: torch.Tensor, b: torch.Tensor, vb: Optional[torch.Tensor], dout: torch.Tensor,
+                      cells: int, Cc: int, da: torch.Tensor, db: torch.Tensor) -> None:
+    for t, nm in ((a, "a"), (b, "b"), (dout, "dout"), (da, "da"), (db, "db")):
+        _require(t, torch.bfloat16, nm)
+        assert t.is_contiguous() and t.numel() >= cells * Cc
+    _lib.check(_lib.lib().snapb200_fuse_max_backward(
+        C.c_void_p(_ptr(a)), C.c_void_p(_ptr(va)), C.c_void_p(_ptr(b)), C.c_void_p(_ptr(vb)), C.c_void_p(_ptr(dout)),
+        C.c_longlong(cells), Cc, C.c_void_p(_ptr(da)), C.c_void_p(_ptr(db)), _stream()))

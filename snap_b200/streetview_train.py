@@ -108,3 +108,44 @@ class LiftBackward:
         for k in self.g:                                       # accumulation over the scenes of a batch (a few 100 KB)
             self.g[k] += g[k]
         return buf["dcrop"]
+
+
+class MatchingHeadBackward:
+    """Backward of `BEVMapper`'s matching head (`bev_mapper.py:284-291`: Dense 128 -> 32, L2 normalisation, mask) and of
+    the modality fusion in front of it (`:225-252`, 'max' over street-view and aerial planes): from the cotangent of
+    `bev_matching` to the gradients of `matching_proj` and the cotangents of the two modality planes (the street-view one
+    feeds `LiftBackward.scene_backward`)."""
+
+    def __init__(self, matching_proj: Dict, device):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).copy()).to(device)
+        self.dev = device
+        self.K, self.b = t(matching_proj["kernel"]), t(matching_proj["bias"])           # [C, 32], [32]
+        self.C = self.K.shape[0]
+        self.Kc = self.K.to(torch.bfloat16).contiguous()                                 # dX operand [N = C, K = 32]
+        self.g = {"kernel": torch.zeros_like(self.K), "bias": torch.zeros_like(self.b)}
+        self._buf: Dict = {}
+
+    def backward(self, plane: torch.Tensor, valid: torch.Tensor, dmatch: torch.Tensor) -> torch.Tensor:
+        """plane bf16 [cells, C] / valid u8 [cells] = `bev_features`; dmatch bf16 [cells, 32].  Writes the gradients of
+        matching_proj into `self.g` and returns dplane bf16 [cells, C]."""
+        cells = valid.numel()
+        if cells % 16:
+            raise NotImplementedError("the number of BEV cells must be a multiple of 16 (split-K weight-gradient kernel)")
+        if cells not in self._buf:
+            R = image_encoder._round_up(max(cells, 128), 128)
+            self._buf[cells] = (torch.zeros((R, 32), dtype=torch.bfloat16, device=self.dev),
+                                torch.zeros((R, self.C), dtype=torch.bfloat16, device=self.dev))
+        dy, dplane = self._buf[cells]
+        ops.match_head_backward(plane, valid, cells, self.C, self.K, self.b, dmatch, dy)
+        ops.dense_wgrad(plane, dy, cells, self.C, 32, self.g["kernel"], self.g["bias"])
+        ops.gemm(dy, self.Kc, dplane, m_rows=cells, seg_k=32)
+        return dplane
+
+    def fusion_backward(self, sv_plane: torch.Tensor, sv_valid: torch.Tensor, aerial_plane: torch.Tensor,
+                        dplane: torch.Tensor):
+        """Cotangents (street-view, aerial) of the two modality planes from the cotangent of their valid-masked maximum
+        (the aerial plane is valid everywhere, `bev_mapper.py:208-211`)."""
+        cells = sv_valid.numel()
+        da, db = torch.zeros_like(dplane), torch.zeros_like(dplane)
+        ops.fuse_max_backward(sv_plane, sv_valid, aerial_plane, None, dplane, cells, self.C, da, db)
+        return da, db

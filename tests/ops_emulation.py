@@ -213,7 +213,7 @@ def make_lift_emulation(p2d, vis, depth):
 def emulated_ops(extra=None):
     """Replace the product's operator wrappers (and the weight bank's device pass) by the emulation above."""
     names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
-             "stdconv_backward", "vertical_max_backward")
+             "stdconv_backward", "vertical_max_backward", "match_head_backward", "fuse_max_backward")
     table = {n: globals()[n] for n in names}
     table.update(extra or {})
     names = tuple(table)
@@ -228,3 +228,25 @@ def emulated_ops(extra=None):
         for n, f in saved.items():
             setattr(ops, n, f)
         image_encoder._WeightBank.run = saved_run
+
+
+def match_head_backward(plane, valid, cells, Cc, kernel, bias, dout, dy):
+    x = plane.reshape(-1)[: cells * Cc].float().reshape(cells, Cc)
+    y = _rd(_rd(x @ kernel.float()) + bias.float())
+    n = y.norm(dim=-1, keepdim=True)
+    z = y / n.clamp(min=1e-30)
+    dz = dout.reshape(-1)[: cells * 32].float().reshape(cells, 32)
+    g = (dz - z * (z * dz).sum(-1, keepdim=True)) / n.clamp(min=1e-30)
+    ok = (valid.reshape(-1)[:cells] != 0)[:, None] & (n >= 1e-5)
+    dy.reshape(-1)[: cells * 32] = torch.where(ok, g, torch.zeros(())).to(dy.dtype).reshape(-1)
+
+
+def fuse_max_backward(a, va, b, vb, dout, cells, Cc, da, db):
+    fa, fb = (t.reshape(-1)[: cells * Cc].float().reshape(cells, Cc) for t in (a, b))
+    g = dout.reshape(-1)[: cells * Cc].float().reshape(cells, Cc)
+    oa = (va.reshape(-1)[:cells] != 0)[:, None]
+    ob = torch.ones_like(oa) if vb is None else (vb.reshape(-1)[:cells] != 0)[:, None]
+    wa = torch.where(oa & ob, (fa > fb).float() + 0.5 * (fa == fb).float(), oa.float().expand_as(fa))
+    wb = torch.where(oa & ob, (fb > fa).float() + 0.5 * (fa == fb).float(), (ob & ~oa).float().expand_as(fa))
+    da.reshape(-1)[: cells * Cc] = (wa * g).to(da.dtype).reshape(-1)
+    db.reshape(-1)[: cells * Cc] = (wb * g).to(db.dtype).reshape(-1)

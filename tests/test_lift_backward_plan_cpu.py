@@ -54,3 +54,44 @@ def test_lift_backward_launch_plan_matches_autograd():
     e_x = np.linalg.norm(dcrop[: V * hf * wf].float().numpy() - r) / np.linalg.norm(r)
     print(f"worst relative parameter-gradient error {worst:.4f}; encoder-feature cotangent {e_x:.4f}")
     assert e_x < 3e-2
+
+
+def test_matching_head_and_fusion_backward_plan_matches_autograd():
+    """`MatchingHeadBackward` (Dense 128 -> 32, L2 normalisation, mask; modality max in front) on the emulated operator
+    layer vs torch autograd of the same head (the forward is oracle.bev_mapper.matching_head / vertical_pooling_max)."""
+    from oracle import bev_mapper as obm
+    from snap_b200 import streetview_train
+    rng = np.random.default_rng(21)
+    cells, C = 16 * 16, 128
+    sv = bf16_np(np.round(rng.standard_normal((cells, C)) * 4) / 4)          # coarse values: ties with the aerial plane
+    ae = bf16_np(np.round(rng.standard_normal((cells, C)) * 4) / 4)
+    sv_valid = rng.random(cells) < 0.6
+    sv = sv * sv_valid[:, None]
+    mp = {"kernel": bf16_np(rng.standard_normal((C, 32)) * 0.1), "bias": bf16_np(rng.standard_normal(32) * 0.05)}
+    dmatch = bf16_np(rng.standard_normal((cells, 32)) * 0.1)
+    # reference
+    a, b = torch.from_numpy(sv).requires_grad_(True), torch.from_numpy(ae).requires_grad_(True)
+    K, bias = torch.from_numpy(mp["kernel"]).requires_grad_(True), torch.from_numpy(mp["bias"]).requires_grad_(True)
+    va = torch.from_numpy(sv_valid)[:, None]
+    stacked = torch.stack([torch.where(va, a, torch.full((), -float("inf"))), b], 1)       # bev_mapper.py:247-252
+    fused = stacked.amax(1)
+    fused_bf = rd_bf16(fused)
+    y = rd_bf16(rd_bf16(fused_bf @ K) + bias)
+    z = y / y.norm(dim=-1, keepdim=True)                                                     # all norms >> eps here
+    (rd_bf16(z) * torch.from_numpy(dmatch)).sum().backward()
+    ref_fwd = obm.matching_head(fused.detach().numpy(), np.ones(cells, bool), mp, rd_bf16)
+    assert np.abs(ref_fwd - rd_bf16(z).detach().numpy()).max() < 1e-2                      # same head as the oracle's
+    # plan
+    bf = lambda t: torch.from_numpy(np.ascontiguousarray(t, dtype=F)).to(torch.bfloat16)
+    with emulated_ops():
+        mh = streetview_train.MatchingHeadBackward(mp, torch.device("cpu"))
+        dplane = mh.backward(bf(fused.detach().numpy()), torch.ones(cells, dtype=torch.uint8), bf(dmatch))
+        da, db = mh.fusion_backward(bf(sv), torch.from_numpy(sv_valid.astype(np.uint8)), bf(ae), dplane[:cells].contiguous())
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    e = dict(kernel=rel(mh.g["kernel"].numpy(), K.grad.numpy()), bias=rel(mh.g["bias"].numpy(), bias.grad.numpy()),
+             sv=rel(da.float().numpy(), a.grad.numpy()), aerial=rel(db.float().numpy(), b.grad.numpy()))
+    print({k: round(float(v), 5) for k, v in e.items()})
+    assert (stacked[:, 0] == stacked[:, 1]).float().mean() > 0.01, "the fixture plants ties"
+    assert all(v < 2e-2 for v in e.values()), e
+    assert min(float(t.grad.norm()) for t in (a, b, K, bias)) > 1e-3
+    assert not da.float().numpy()[~sv_valid].any()

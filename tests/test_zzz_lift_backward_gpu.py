@@ -146,3 +146,38 @@ def test_lift_backward_chain_vs_autograd():
                 # the max routes the cotangent through the arg-max level: a bf16 flip between near-tied levels moves it
                 assert err < 5e-2
     assert rel_l2(dcrop[:rows_img].float().cpu().numpy(), ref_x) < 5e-2
+
+
+def test_match_head_and_fuse_max_backward_vs_emulation():
+    """`snapb200_match_head_backward` / `snapb200_fuse_max_backward` vs their torch emulation (tests/ops_emulation.py, which
+    tests/test_lift_backward_plan_cpu.py checks against autograd of the oracle's matching head and modality max)."""
+    import ops_emulation as emu
+    from snap_b200 import ops
+    rng = np.random.default_rng(33)
+    cells, C = 1000, 128
+    plane = bf16_np(rng.standard_normal((cells, C)))
+    plane[:5] = 0                                                                  # |y| = |b|; with b = 0 below: zero norm
+    valid = rng.random(cells) < 0.8
+    K = torch.from_numpy(bf16_np(rng.standard_normal((C, 32)) * 0.1))
+    b = torch.zeros(32)
+    dout = bf16_np(rng.standard_normal((cells, 32)) * 0.1)
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16)
+    dy = torch.full((cells, 32), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.match_head_backward(bf(plane).cuda(), torch.from_numpy(valid.astype(np.uint8)).cuda(), cells, C, K.cuda(), b.cuda(),
+                            bf(dout).cuda(), dy)
+    ref = torch.zeros((cells, 32), dtype=torch.bfloat16)
+    emu.match_head_backward(bf(plane), torch.from_numpy(valid.astype(np.uint8)), cells, C, K, b, bf(dout), ref)
+    got, want = dy.float().cpu().numpy(), ref.float().numpy()
+    assert not got[~valid].any() and not got[:5].any()
+    assert rel_l2(got, want) < 5e-3
+    # modality max with ties
+    a = bf16_np(np.round(rng.standard_normal((cells, C)) * 2) / 2)
+    c = bf16_np(np.round(rng.standard_normal((cells, C)) * 2) / 2)
+    g = bf16_np(rng.standard_normal((cells, C)))
+    va = torch.from_numpy(valid.astype(np.uint8))
+    for vb in (None, torch.from_numpy((rng.random(cells) < 0.5).astype(np.uint8))):
+        da, db = (torch.full((cells, C), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(2))
+        ops.fuse_max_backward(bf(a).cuda(), va.cuda(), bf(c).cuda(), None if vb is None else vb.cuda(), bf(g).cuda(), cells, C, da, db)
+        ra, rb = torch.zeros((cells, C), dtype=torch.bfloat16), torch.zeros((cells, C), dtype=torch.bfloat16)
+        emu.fuse_max_backward(bf(a), va, bf(c), vb, bf(g), cells, C, ra, rb)
+        assert torch.equal(da.cpu(), ra) and torch.equal(db.cpu(), rb)
