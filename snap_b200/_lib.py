@@ -128,6 +128,7 @@ EXPORTED_SYMBOLS += [
     "snapb200_gn_backward", "snapb200_wt_segments", "snapb200_stdconv_backward",
     "snapb200_lift_gather_pool_backward", "snapb200_vertical_max_backward",
     "snapb200_match_head_backward", "snapb200_fuse_max_backward",
+    "snapb200_loc_nll_backward", "snapb200_loc_pose_scoring_backward",
 ]
 
 

@@ -771,3 +771,45 @@ def fuse_max_backward(a: torch.Tensor, va: torch.Tensor, b: torch.Tensor, vb: Op
     _lib.check(_lib.lib().snapb200_fuse_max_backward(
         C.c_void_p(_ptr(a)), C.c_void_p(_ptr(va)), C.c_void_p(_ptr(b)), C.c_void_p(_ptr(vb)), C.c_void_p(_ptr(dout)),
         C.c_longlong(cells), Cc, C.c_void_p(_ptr(da)), C.c_void_p(_ptr(db)), _stream()))
+
+
+# --------------------------------------------------------------------------------------------
+# backward of the sampling localizer's loss (csrc/localizer_backward.cu)
+# --------------------------------------------------------------------------------------------
+def loc_nll_backward(scores: torch.Tensor, remove: Optional[Sequence[float]], dr_samples: Optional[torch.Tensor],
+                     dt_samples: Optional[torch.Tensor], dscores: torch.Tensor,
+                     dtemperature: Optional[torch.Tensor] = None) -> None:
+    """dscores f32 [B,P1] = d mean_b(nll_b) / d scores; remove = threshold_remove_accurate_poses (dr_min, dt_min) or None."""
+    _require(scores, torch.float32, "scores")
+    _require(dscores, torch.float32, "dscores")
+    B, P1 = scores.shape
+    assert scores.is_contiguous() and dscores.is_contiguous() and dscores.shape == (B, P1)
+    dr_min, dt_min = (float(remove[0]), float(remove[1])) if remove is not None else (0.0, 0.0)
+    _lib.check(_lib.lib().snapb200_loc_nll_backward(
+        C.c_void_p(_ptr(scores)), C.c_void_p(_ptr(dr_samples)), C.c_void_p(_ptr(dt_samples)), B, P1,
+        int(remove is not None), C.c_float(dr_min), C.c_float(dt_min), C.c_void_p(_ptr(dscores)),
+        C.c_void_p(_ptr(dtemperature)), _stream()))
+
+
+def loc_pose_scoring_backward(sim: torch.Tensor, point_scale: torch.Tensor, i_xy: torch.Tensor,
+                              valid_j: Optional[torch.Tensor], poses: torch.Tensor, dscores: torch.Tensor, H: int, W: int,
+                              cell_size: float, mask_out_of_bounds: bool, relu_mask: bool, dsim: torch.Tensor) -> None:
+    """dsim bf16 [B, rows >= N, H*W] from dscores f32 [B,P] (the arguments of `loc_pose_scoring`)."""
+    _require(sim, torch.bfloat16, "sim")
+    _require(dsim, torch.bfloat16, "dsim")
+    _require(poses, torch.float32, "poses")
+    _require(dscores, torch.float32, "dscores")
+    B, N = point_scale.shape
+    P = poses.shape[1]
+    assert poses.shape == (B, P, 3) and dscores.shape == (B, P) and poses.is_contiguous() and dscores.is_contiguous()
+    assert sim.is_contiguous() and dsim.is_contiguous() and i_xy.is_contiguous()
+    assert dsim.dim() == 3 and dsim.shape[0] == B and dsim.shape[1] >= N and dsim.shape[2] == H * W
+    p = _lib.LocScoreParams()
+    p.B, p.N, p.H, p.W, p.P = B, N, H, W, P
+    p.cell_size = cell_size
+    p.mask_out_of_bounds = int(mask_out_of_bounds)
+    p.i_xy_batched = int(i_xy.dim() == 3)
+    _lib.check(_lib.lib().snapb200_loc_pose_scoring_backward(
+        C.byref(p), C.c_void_p(_ptr(sim)), C.c_void_p(_ptr(point_scale)), C.c_void_p(_ptr(i_xy)),
+        C.c_void_p(_ptr(valid_j)), C.c_void_p(_ptr(poses)), C.c_void_p(_ptr(dscores)), int(relu_mask),
+        int(dsim.shape[1]), C.c_void_p(_ptr(dsim)), _stream()))

@@ -213,7 +213,8 @@ def make_lift_emulation(p2d, vis, depth):
 def emulated_ops(extra=None):
     """Replace the product's operator wrappers (and the weight bank's device pass) by the emulation above."""
     names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
-             "stdconv_backward", "vertical_max_backward", "match_head_backward", "fuse_max_backward")
+             "stdconv_backward", "vertical_max_backward", "match_head_backward", "fuse_max_backward",
+             "loc_nll_backward", "loc_pose_scoring_backward")
     table = {n: globals()[n] for n in names}
     table.update(extra or {})
     names = tuple(table)
@@ -250,3 +251,34 @@ def fuse_max_backward(a, va, b, vb, dout, cells, Cc, da, db):
     wb = torch.where(oa & ob, (fb > fa).float() + 0.5 * (fa == fb).float(), (ob & ~oa).float().expand_as(fa))
     da.reshape(-1)[: cells * Cc] = (wa * g).to(da.dtype).reshape(-1)
     db.reshape(-1)[: cells * Cc] = (wb * g).to(db.dtype).reshape(-1)
+
+
+def loc_nll_backward(scores, remove, dr_samples, dt_samples, dscores, dtemperature=None):
+    B, P1 = scores.shape
+    s = scores.clone().requires_grad_(True)
+    rem = torch.zeros((B, P1), dtype=torch.bool)
+    if remove is not None:
+        rem = (dr_samples < remove[0]) & (dt_samples < remove[1])
+        rem[:, 0] = False
+    sc = torch.where(rem, torch.full((), -float("inf")), s)
+    (torch.logsumexp(sc, 1) - sc[:, 0]).mean().backward()
+    dscores[:] = s.grad
+    if dtemperature is not None:
+        dtemperature[:] = (s.grad * scores).sum(1)
+
+
+def loc_pose_scoring_backward(sim, point_scale, i_xy, valid_j, poses, dscores, H, W, cell_size, mask_out_of_bounds,
+                              relu_mask, dsim):
+    from loc_torch_ref import pose_scores, pose_uv
+    B, N = point_scale.shape
+    for b in range(B):
+        s = sim[b].float().reshape(N, H, W).clone().requires_grad_(True)
+        uv = pose_uv(poses[b].numpy(), (i_xy[b] if i_xy.dim() == 3 else i_xy).numpy(), cell_size)
+        sp = s * point_scale[b][:, None, None]
+        sc = pose_scores(sp, uv, np.ones(N, bool), None if valid_j is None else valid_j[b].numpy().astype(bool).reshape(H, W),
+                         mask_out_of_bounds)
+        (sc * dscores[b]).sum().backward()
+        g = s.grad.reshape(N, H * W)
+        if relu_mask:
+            g = g * (sim[b].float() > 0)
+        dsim[b, :N] = g.to(dsim.dtype)
