@@ -49,10 +49,9 @@ def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, dept
     return torch.where(any_v[:, None], stats, torch.zeros_like(stats))
 
 
-def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd):
-    """Autograd through proj MLP -> gather / pooling -> fusion MLP -> mask (:282) -> vertical max (bev_mapper.py:80-86) with
-    the forward's materialisation points `rd`; loss = sum(plane * dplane).  Returns the forward tensors the product's
-    backward consumes, the parameter gradients {proj_mlp, fusion_mlp} and the cotangent of the encoder features."""
+def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd):
+    """proj MLP -> gather / pooling -> fusion MLP -> mask (:282) -> vertical max (bev_mapper.py:80-86) as ONE autograd graph.
+    Returns the leaves (parameters tp, encoder features x) and the forward tensors (crop, fimg, vol, plane, plane_valid)."""
     tp = {k: {n: {a: torch.from_numpy(np.ascontiguousarray(v, dtype=F)).requires_grad_(True) for a, v in d.items()}
               for n, d in t.items()} for k, t in svp.items() if k in ("proj_mlp", "fusion_mlp")}
     x = torch.from_numpy(enc).requires_grad_(True)
@@ -66,7 +65,14 @@ def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd):
     m = valid.reshape(cells, Z, 1)
     masked = torch.where(m, vol.reshape(cells, Z, -1), torch.full((), -float("inf")))
     plane = torch.where(m.any(1), masked.amax(1), torch.zeros(()))
-    (plane * torch.from_numpy(dplane)).sum().backward()
-    grads = {k: {n: {a: t.grad.numpy() for a, t in d.items()} for n, d in tt.items()} for k, tt in tp.items()}
-    fwd = dict(crop=crop.detach().numpy(), fimg=fimg.detach().numpy(), vol=vol.detach().numpy(), plane=plane.detach().numpy())
+    return tp, x, dict(crop=crop, fimg=fimg, vol=vol, plane=plane, plane_valid=m.any(1)[:, 0])
+
+
+def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd):
+    """Autograd of loss = sum(plane * dplane) through `chain_forward`.  Returns the forward tensors the product's backward
+    consumes (NumPy), the parameter gradients {proj_mlp, fusion_mlp} and the cotangent of the encoder features."""
+    tp, x, t = chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd)
+    (t["plane"] * torch.from_numpy(dplane)).sum().backward()
+    grads = {k: {n: {a: v.grad.numpy() for a, v in d.items()} for n, d in tt.items()} for k, tt in tp.items()}
+    fwd = {k: t[k].detach().numpy() for k in ("crop", "fimg", "vol", "plane")}
     return fwd, grads, x.grad.numpy()

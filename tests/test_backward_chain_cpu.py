@@ -1,0 +1,91 @@
+"""Capstone of the CPU-verified backward plans: the three product plans chained exactly as a config-4 training step with
+frozen image encoders will chain them --
+
+    NLL of the sampled poses -> `LocalizerLossBackward` -> cotangent of the map's `bev_matching`
+                             -> `MatchingHeadBackward` -> cotangent of the street-view plane
+                             -> `LiftBackward.scene_backward` -> gradients of fusion_mlp / proj_mlp, encoder-feature cotangent
+
+on the emulated operator layer, against ONE torch autograd graph of the oracle chain
+encoder features -> proj MLP -> lift -> fusion MLP -> vertical max -> matching head -> similarities -> pose scores -> NLL.
+This pins the interfaces between the plans (layouts, dtypes, masks), which the per-plan tests cannot."""
+import numpy as np
+import torch
+
+from lift_torch_ref import chain_forward
+from loc_torch_ref import nll, pose_scores, pose_uv
+from ops_emulation import emulated_ops, make_lift_emulation
+from util import F, bf16_np, rd_bf16, to_oracle_geometry
+
+
+def test_loss_to_lift_backward_chain_matches_autograd():
+    from oracle import bev_mapper as obm, grids as ogrids, streetview_encoder as osv
+    from snap_b200 import configs, localizer_train, params, pose_estimation, streetview_encoder as sve, streetview_train, synthetic
+    G, V, hw, hf, wf, D = 16, 3, (64, 96), 16, 24, 32
+    cell = 0.2
+    rng = np.random.default_rng(17)
+    data = synthetic.make_tile(6, V, hw, G, spacing=0.5, same_side=True)
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), cell), oT.t)
+    Z = xyz.shape[2]
+    cells, N_vox = G * G, G * G * Z
+    p2d, vis, depth, _ = osv.project_points_to_views(oT, ocam, xyz.reshape(-1, 3))
+    svp = params.round_to_bf16(params.perturb_affine(rng, {"proj_mlp": params.init_mlp(rng, 128, (160,)),
+                                                           "fusion_mlp": params.init_mlp(rng, 257, (256, 128))}))
+    mp = {"kernel": bf16_np(rng.standard_normal((128, D)) * 0.2), "bias": bf16_np(rng.standard_normal(D) * 0.05)}
+    enc = bf16_np(rng.standard_normal((V * hf * wf, 128)))
+    # query side (constants here: the query mapper's chain is the same code) and sampled poses
+    Nq, P1, temp = 24, 48, 0.2
+    fq = bf16_np(rng.standard_normal((Nq, D)) / np.sqrt(D) * 2)
+    valid_q = rng.random(Nq) < 0.85
+    q_xy = np.stack([rng.uniform(0.2, 1.5, Nq), rng.uniform(-0.8, 0.8, Nq)], -1).astype(F)
+    poses = np.stack([rng.uniform(-0.5, 0.5, P1), rng.uniform(0.2, 1.5, P1), rng.uniform(0.8, 2.4, P1)], -1).astype(F)
+
+    # ---- reference: one autograd graph ---------------------------------------------------------------------------------
+    tp, x, t = chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd_bf16)
+    K, bias = torch.from_numpy(mp["kernel"]).requires_grad_(True), torch.from_numpy(mp["bias"]).requires_grad_(True)
+    T = torch.tensor(temp, requires_grad=True)
+    pvalid = t["plane_valid"]
+    y = rd_bf16(rd_bf16(t["plane"] @ K) + bias)                                             # bev_mapper.py:284-287
+    nrm = y.norm(dim=-1, keepdim=True)
+    fm = torch.where(pvalid[:, None] & (nrm >= 1e-5), rd_bf16(y / nrm.clamp(min=1e-30)), torch.zeros(()))   # :288-291
+    sim = torch.relu(rd_bf16(torch.from_numpy(fq) @ fm.T))                                  # bev_localizer.py:157-159
+    w = 1.0 / max(int(valid_q.sum()), 1)
+    sc = pose_scores((sim * torch.exp(T) * w).reshape(Nq, G, G), pose_uv(poses, q_xy, cell), valid_q, pvalid.numpy().reshape(G, G), True)
+    nll(sc, np.zeros(P1, bool)).backward()
+    assert pvalid.float().mean() > 0.05 and float(sc.detach().abs().max()) > 0
+
+    # ---- the product's plans, chained ----------------------------------------------------------------------------------
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16)
+    nump = lambda a: a.detach().numpy()
+    lp = sve.fill_lift_params(configs.streetview_encoder(), V, hf, wf, G, G, Z, 288)
+    scale = float(np.exp(F(temp)))
+    maps = pose_estimation.SimilarityMaps(sim=bf(nump(sim))[None], scale=scale,
+                                          point_scale=torch.from_numpy(np.where(valid_q, scale * w, 0).astype(F))[None],
+                                          row_cdf=None, row_max=None, chunk_sum=None, row_sum=None, H=G, W=G)
+    pv_u8 = torch.from_numpy(nump(pvalid).astype(np.uint8))
+    with emulated_ops(make_lift_emulation(p2d, vis, depth)):
+        dev = torch.device("cpu")
+        loc = localizer_train.LocalizerLossBackward(dev)
+        _, dfm, dtemp = loc.backward(maps, bf(fq)[None], bf(nump(fm)).reshape(1, G, G, D), torch.from_numpy(q_xy), pv_u8[None],
+                                     torch.from_numpy(poses)[None], sc.detach()[None], cell, True, True)
+        mh = streetview_train.MatchingHeadBackward(mp, dev)
+        dplane = mh.backward(bf(nump(t["plane"])), pv_u8, dfm[0].to(torch.bfloat16).contiguous())
+        lb = streetview_train.LiftBackward(svp, dev)
+        lb.zero_grads()
+        dcrop = lb.scene_backward(lp, None, bf(nump(t["fimg"])), bf(nump(t["crop"])), None, None, None, bf(nump(t["vol"])),
+                                  torch.from_numpy(vis.any(-1).astype(np.uint8)), dplane[:cells].contiguous())
+        got = lb.grads_tree()
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    errs = {"matching_proj/kernel": rel(mh.g["kernel"].numpy(), K.grad.numpy()),
+            "matching_proj/bias": rel(mh.g["bias"].numpy(), bias.grad.numpy()),
+            "temperature": abs(float(dtemp.sum()) - float(T.grad)) / (abs(float(T.grad)) + 1e-30),
+            "encoder features": rel(dcrop[: V * hf * wf].float().numpy(), x.grad.numpy())}
+    for k in ("proj_mlp", "fusion_mlp"):
+        for n, d in tp[k].items():
+            for a, leaf in d.items():
+                assert float(leaf.grad.norm()) > 1e-6, (k, n, a)
+                errs[f"{k}/{n}/{a}"] = rel(got[k][n][a], leaf.grad.numpy())
+    print({k: round(float(v), 4) for k, v in errs.items()})
+    # bf16 cotangents between the plans (d f_m, dplane) against fp32 cotangents in autograd: a few 1e-3
+    assert max(errs.values()) < 3e-2, errs
