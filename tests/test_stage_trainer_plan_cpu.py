@@ -85,3 +85,63 @@ def test_stage_trainer_launch_plan_matches_autograd():
         worst = max(worst, err)
         assert err < 3e-2, ("/".join(path), err, np.linalg.norm(r))
     print(f"worst relative gradient error over {len(list(_flat(tp)))} parameter arrays: {worst:.4f}")
+
+
+def _dp_worker(rank, world, port, out):
+    """One gloo rank: the stage trainer's backward on this rank's half of the batch + the gradient mean over ranks."""
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snap_b200 import parallel, semantic_train, types
+    cfg, p, feats, valid, rng = _setup(7, B=2)
+    Gm = bf16_np(np.random.default_rng(8).standard_normal(feats.shape[:3] + (12,)) * 0.05)
+    sl = slice(rank, rank + 1)                                                   # per-GPU batch 1 (trainer.py:452-464)
+    with emulated_ops():
+        tr = semantic_train.StageHeadTrainer(cfg, p, torch.device("cpu"))
+        plane = types.FeaturePlane(torch.from_numpy(feats[sl]).to(torch.bfloat16), torch.from_numpy(valid[sl].astype(np.uint8)))
+        tr.forward(plane)
+        buf = tr._buffers(1, feats.shape[1], feats.shape[2])
+        buf["dlogits"].zero_()
+        buf["dlogits"][: feats.shape[1] * feats.shape[2], :12] = torch.from_numpy(
+            (Gm[sl] * valid[sl][..., None]).reshape(-1, 12)).to(torch.bfloat16)   # d mean over the LOCAL batch (of 1) / d logits
+        tr.backward(plane, buf)
+        calls = parallel.pmean_tree({"/".join(r["path"]): r["g"] for r in tr.rec})      # as train_step does
+        grads = tr.grads_tree()
+    if rank == 0:
+        torch.save({"grads": grads, "calls": calls}, out)
+    dist.destroy_process_group()
+
+
+def test_stage_trainer_gradient_mean_world_size_2(tmp_path):
+    """Two gloo ranks with one scene each: mean over ranks of the shard gradients (one bucketed all-reduce) == the
+    gradient of the whole batch on one process (GroupNorm statistics are per image, so the split is exact)."""
+    import socket
+    import torch.multiprocessing as mp
+    from snap_b200 import semantic_train, types
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    assert got["calls"] == 1
+    cfg, p, feats, valid, rng = _setup(7, B=2)
+    Gm = bf16_np(np.random.default_rng(8).standard_normal(feats.shape[:3] + (12,)) * 0.05)
+    B, G = feats.shape[:2]
+    with emulated_ops():
+        tr = semantic_train.StageHeadTrainer(cfg, p, torch.device("cpu"))
+        plane = types.FeaturePlane(torch.from_numpy(feats).to(torch.bfloat16), torch.from_numpy(valid.astype(np.uint8)))
+        tr.forward(plane)
+        buf = tr._buffers(B, G, G)
+        buf["dlogits"].zero_()
+        # whole batch on one process: the loss is the mean over the B examples (trainer.py:221)
+        buf["dlogits"][: B * G * G, :12] = torch.from_numpy((Gm * valid[..., None]).reshape(-1, 12) / B).to(torch.bfloat16)
+        tr.backward(plane, buf)
+        ref = tr.grads_tree()
+    for path, r in _flat(ref):
+        g = got["grads"]
+        for k in path:
+            g = g[k]
+        err = np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)               # pmean of per-rank means = global mean
+        assert err < 2e-2, ("/".join(path), err)
