@@ -12,7 +12,7 @@
 // (pool_multiview_backward + lift_gather_backward, checked against autograd on the CPU):
 //     w = softmax_valid(s), mean = sum w f, var = sum w (f - mean)^2, smax = max_valid s
 //     d f_k = w_k dmean + 2 w_k (f_k - mean) dvar
-//     d w_k = f_k . dmean + (f_k - mean)^2 . dvar          d s_k = w_k (d w_k - sum_j w_j d w_j) + [k = argmax] dsmax
+//     d w_k = f_k . dmean + (f_k - mean)^2 . dvar          d s_k = w_k (d w_k - sum_j w_j d w_j) + [s_k = smax] dsmax / #ties
 // and scatter-adds w_tap * d f_k into the D feature channels of the four taps and w_tap * (1 - wb1 | wb1) * d s_k into
 // the two scale-bin channels: fp32 atomics into a gradient image gimg f32 [V, Hf, Wf, D + S] (zeroed by the caller).
 // Rounding of the forward (bf16 materialisation points) is treated as the identity (straight-through), the geometry
@@ -111,17 +111,16 @@ lift_gather_pool_bwd_kernel(const __grid_constant__ LiftParams P, const LiftView
       score[v] = __shfl_sync(0xffffffffu, sp, 0);
     }
     if (vis_mask == 0) continue;  // statistics of unseen voxels are the constant 0 (:177): no gradient
-    float mx = 0.f, smax = -INFINITY;
-    int kmax = -1;
+    float mx = 0.f, smax = -INFINITY, nmax = 0.f;
 #pragma unroll
     for (int v = 0; v < LIFT_MAX_VIEWS; ++v)
       if (vis_mask & (1u << v)) {
         mx = fmaxf(mx, score[v]);
-        if (score[v] > smax) {  // first maximum takes the gradient of score_max
-          smax = score[v];
-          kmax = v;
-        }
+        smax = fmaxf(smax, score[v]);
       }
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v)  // jnp.max splits the cotangent of score_max evenly among tied views
+      if ((vis_mask & (1u << v)) && score[v] == smax) nmax += 1.f;
     float wv[LIFT_MAX_VIEWS], den = 0.f, mean[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) mean[j] = 0.f;
@@ -164,7 +163,7 @@ lift_gather_pool_bwd_kernel(const __grid_constant__ LiftParams P, const LiftView
     for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
       if (v >= P.V) break;
       if (!(vis_mask & (1u << v))) continue;
-      const float ds = wv[v] * (dw[v] - wdw) + (v == kmax ? dsmax : 0.f);
+      const float ds = wv[v] * (dw[v] - wdw) + (score[v] == smax ? dsmax / nmax : 0.f);
       // the tap geometry again (cheap, and keeps no per-view state alive across the pooling math)
       const Proj pr = project_point(sview[v], px, py, pz);
       const Taps t = make_taps(pr.row, pr.col, P.Hf, P.Wf);
