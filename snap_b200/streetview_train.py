@@ -16,7 +16,7 @@ Parameters are the Flax kernels `[in, out]`; the gradients are fp32 arrays of th
 of a batch by the caller (`zero_grads`).  The image encoder below `dcrop` has no backward yet."""
 from __future__ import annotations
 
-from typing import Dict
+from typing import Dict, Optional
 
 import numpy as np
 import torch
@@ -42,6 +42,7 @@ class LiftBackward:
         self._g1 = {k: z(*v.shape) for k, v in {**self.W, **self.b}.items()}    # one scene
         # bf16 operands: forward B operands [out, in] and dX operands [in, out] (the Flax kernel as stored)
         self.Bf0 = self.W["fusion_mlp/Dense_0/kernel"].t().contiguous().to(torch.bfloat16)       # [256, ld]
+        self.Bf1 = self.W["fusion_mlp/Dense_1/kernel"].t().contiguous().to(torch.bfloat16)       # [128, 256]
         self.Wc = {k: v.to(torch.bfloat16).contiguous() for k, v in self.W.items()}
         self._buf: Dict = {}
 
@@ -66,19 +67,22 @@ class LiftBackward:
             bf = lambda r, c: torch.zeros((r, c), dtype=torch.bfloat16, device=self.dev)
             R = image_encoder._round_up(max(N, 128), 128)
             Ri = image_encoder._round_up(max(rows_img, 128), 128)
-            self._buf[key] = dict(stats=bf(R, self.ld), hid=bf(R, 256), dvol=bf(R, 128), dhid=bf(R, 256), dstats=bf(R, self.ld),
+            self._buf[key] = dict(stats=bf(R, self.ld), hid=bf(R, 256), vol=bf(R, 128), dvol=bf(R, 128), dhid=bf(R, 256),
+                                  dstats=bf(R, self.ld),
                                   valid=torch.zeros(R, dtype=torch.uint8, device=self.dev),
                                   gimg=torch.zeros((V, hf, wf, self.CF), dtype=torch.float32, device=self.dev),
                                   gimg_bf=bf(Ri, self.CF), dcrop=bf(Ri, self.D))
         return self._buf[key]
 
     def scene_backward(self, lp, views: torch.Tensor, fimg: torch.Tensor, crop: torch.Tensor, xs: torch.Tensor,
-                       ys: torch.Tensor, zs: torch.Tensor, volume: torch.Tensor, valid: torch.Tensor,
+                       ys: torch.Tensor, zs: torch.Tensor, volume: Optional[torch.Tensor], valid: Optional[torch.Tensor],
                        dplane: torch.Tensor) -> torch.Tensor:
         """lp / views / fimg / xs / ys / zs: the arguments of the scene's forward `ops.lift_gather_pool`; crop bf16
         [V*hf*wf, 128] = relu(cropped finest FPN level) (the proj MLP's input); volume bf16 [N,128] / valid u8 [N] = the
-        forward's feature volume; dplane bf16 [X*Y, 128].  Adds this scene's parameter gradients to `self.g` and returns
-        dcrop bf16 [V*hf*wf, 128] (cotangent of the un-activated encoder features)."""
+        forward's feature volume, or None after the FUSED forward (`lift_fused_kernel` never materialises the volume): it is
+        then recomputed here with one more GEMM, so training can keep the single-kernel forward; dplane bf16 [X*Y, 128].
+        Adds this scene's parameter gradients to `self.g` and returns dcrop bf16 [V*hf*wf, 128] (cotangent of the
+        un-activated encoder features)."""
         N, cells, Z = lp.X * lp.Y * lp.Z, lp.X * lp.Y, lp.Z
         rows_img = lp.V * lp.Hf * lp.Wf
         if N % 16 or rows_img % 16:
@@ -87,6 +91,9 @@ class LiftBackward:
         # recompute this scene's statistics and hidden rows (the forward keeps them for one scene at a time)
         ops.lift_gather_pool(lp, views, fimg, xs, ys, zs, buf["stats"], buf["valid"])
         ops.gemm(buf["stats"], self.Bf0, buf["hid"], m_rows=N, seg_k=self.ld, bias=self.b["fusion_mlp/Dense_0/bias"], relu=True)
+        if volume is None:      # fused forward: the volume rows of this scene again (Dense 256 -> 128, zero where invalid, :281-282)
+            ops.gemm(buf["hid"], self.Bf1, buf["vol"], m_rows=N, bias=self.b["fusion_mlp/Dense_1/bias"], row_mask=buf["valid"])
+            volume, valid = buf["vol"], buf["valid"]
         # vertical max -> volume rows (invalid voxels and non-maximal levels get 0)
         ops.vertical_max_backward(volume, valid, dplane, cells, Z, self.D, buf["dvol"])
         # fusion MLP

@@ -42,6 +42,16 @@ def test_lift_backward_launch_plan_matches_autograd():
         dcrop = lb.scene_backward(lp, None, bf(fwd["fimg"]), bf(fwd["crop"]), None, None, None, bf(fwd["vol"]),
                                   torch.from_numpy(vis.any(-1).astype(np.uint8)), bf(dplane))
         got = lb.grads_tree()
+        # after the fused forward there is no volume: the backward recomputes it and must give the same gradients
+        lb2 = streetview_train.LiftBackward(svp, torch.device("cpu"))
+        lb2.zero_grads()
+        dcrop2 = lb2.scene_backward(lp, None, bf(fwd["fimg"]), bf(fwd["crop"]), None, None, None, None, None, bf(dplane))
+        got2 = lb2.grads_tree()
+    for k in got:
+        for n in got[k]:
+            for a in got[k][n]:
+                assert np.array_equal(got[k][n][a], got2[k][n][a]), (k, n, a)
+    assert torch.equal(dcrop, dcrop2)
     worst = 0.0
     for k in ("proj_mlp", "fusion_mlp"):
         for n, d in ref[k].items():
