@@ -146,6 +146,14 @@ def test_lift_backward_chain_vs_autograd():
                 # the max routes the cotangent through the arg-max level: a bf16 flip between near-tied levels moves it
                 assert err < 5e-2
     assert rel_l2(dcrop[:rows_img].float().cpu().numpy(), ref_x) < 5e-2
+    # after the fused forward there is no volume: the backward recomputes it (same kernels -> same bits)
+    dcrop1 = dcrop.clone()
+    lb2 = streetview_train.LiftBackward(svp, torch.device(dev))
+    lb2.zero_grads()
+    dcrop2 = lb2.scene_backward(lp, views, fimg, crop, xs_d, ys_d, zs_d, None, None, bf(dplane))
+    torch.cuda.synchronize()
+    assert rel_l2(dcrop2.float().cpu().numpy(), dcrop1.float().cpu().numpy()) < 1e-3     # fp32 atomics: order-dependent
+    assert rel_l2(lb2.g["fusion_mlp/Dense_1/kernel"].cpu().numpy(), lb.g["fusion_mlp/Dense_1/kernel"].cpu().numpy()) < 1e-6
 
 
 def test_match_head_and_fuse_max_backward_vs_emulation():
