@@ -274,3 +274,247 @@ extern "C" int snapb200_lift_select_pool(const SnapLiftParams* q, int top_k, flo
       (const __nv_bfloat16*)fimg, xs, ys, zs, (__nv_bfloat16*)stats, valid, dbg_idx, dbg_vis, dbg_taps);
   return check_launch("lift_select_pool_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of lift_select_pool_kernel (the V > top_k path): same warp / half-warp organisation.  Pass 1 repeats the
+// forward of the voxel (projection by lane, k rounds of arg-min, sampling of the selected views two per round, soft-max
+// pooling); pass 2 walks over the rounds again and scatter-adds, per selected visible view, w_tap * d f_k into the D
+// feature channels of its four taps (w_tap = the bf16-rounded tap weights of :102) and w_tap * (1 - wb1 | wb1) * d s_k
+// into the two scale-bin channels of the gradient image gimg f32 [V, Hf, Wf, D + S].  Closed forms as in
+// lift_backward.cu; rounding points are straight-through, the selection and the geometry carry no gradient.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace snapb200 {
+
+__device__ __forceinline__ void sel_atomic_add8(float* dst, float w, const float (&v)[8]) {
+#if __CUDA_ARCH__ >= 900
+  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(w * v[0], w * v[1], w * v[2], w * v[3]));
+  atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(w * v[4], w * v[5], w * v[6], w * v[7]));
+#else
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dst + j, w * v[j]);
+#endif
+}
+
+__global__ void __launch_bounds__(256)
+lift_select_pool_bwd_kernel(const __grid_constant__ LiftParams P, const int K, const LiftView* __restrict__ views,
+                            const float* __restrict__ centers, const __nv_bfloat16* __restrict__ fimg,
+                            const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ zs,
+                            const __nv_bfloat16* __restrict__ dstats, float* __restrict__ gimg) {
+  __shared__ LiftView sview[SELECT_MAX_VIEWS];
+  __shared__ float scen[SELECT_MAX_VIEWS * 3];
+  for (int i = threadIdx.x; i < P.V * (int)(sizeof(LiftView) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sview)[i] = reinterpret_cast<const uint32_t*>(views)[i];
+  for (int i = threadIdx.x; i < P.V * 3; i += blockDim.x) scen[i] = centers[i];
+  __syncthreads();
+  const unsigned FULL = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col_id = blockIdx.x;
+  const int ix = col_id / P.Y, iy = col_id - ix * P.Y;
+  const float px = xs[P.xy_paired ? col_id : ix], py = ys[P.xy_paired ? col_id : iy];
+  const int half = lane >> 4, c8 = lane & 15;
+  const float score_scale = (float)(P.S - 1);
+
+  for (int iz = warp; iz < P.Z; iz += 8) {
+    const long long n = (long long)col_id * P.Z + iz;
+    const float pz = zs[iz];
+    Proj pr;
+    pr.row = pr.col = pr.depth = 0.f;
+    pr.vis = false;
+    unsigned key = 0xffffffffu;
+    if (lane < P.V) {
+      pr = project_point(sview[lane], px, py, pz);
+      const float dx = __fadd_rn(px, -scen[lane * 3 + 0]);
+      const float dy = __fadd_rn(py, -scen[lane * 3 + 1]);
+      const float dz = __fadd_rn(pz, -scen[lane * 3 + 2]);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      key = pr.vis ? __float_as_uint(__fsqrt_rn(d2)) : 0x7f800000u;
+    }
+    int sel[LIFT_MAX_VIEWS];
+    bool taken = false;
+#pragma unroll
+    for (int k = 0; k < LIFT_MAX_VIEWS; ++k) {
+      sel[k] = 0;
+      if (k >= K) continue;
+      const unsigned m = __reduce_min_sync(FULL, taken ? 0xffffffffu : key);
+      const unsigned b = __ballot_sync(FULL, !taken && key == m);
+      sel[k] = __ffs(b) - 1;
+      if (lane == sel[k]) taken = true;
+    }
+    // ---- pass 1: the forward's samples ---------------------------------------------------------------------------
+    float fv[LIFT_MAX_VIEWS][8], score[LIFT_MAX_VIEWS];
+    unsigned vis_mask = 0;
+#pragma unroll
+    for (int k = 0; k < LIFT_MAX_VIEWS; ++k) {
+      score[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fv[k][j] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < LIFT_MAX_VIEWS / 2; ++i) {
+      if (2 * i >= K) break;
+      const int k = 2 * i + half;
+      const bool act = k < K;
+      const int src = half ? sel[2 * i + 1] : sel[2 * i];
+      const float row = __shfl_sync(FULL, pr.row, src);
+      const float col = __shfl_sync(FULL, pr.col, src);
+      const float depth = __shfl_sync(FULL, pr.depth, src);
+      const bool vis = __shfl_sync(FULL, pr.vis ? 1 : 0, src) != 0 && act;
+      const SelTaps t = make_sel_taps(row, col, P.Hf, P.Wf);
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      float sp = 0.f;
+      if (vis) {
+        const __nv_bfloat16* img = fimg + (size_t)src * P.Hf * P.Wf * P.CF;
+        const __nv_bfloat16* p00 = img + ((size_t)t.r0 * P.Wf + t.c0) * P.CF;
+        const __nv_bfloat16* p01 = img + ((size_t)t.r0 * P.Wf + t.c1) * P.CF;
+        const __nv_bfloat16* p10 = img + ((size_t)t.r1 * P.Wf + t.c0) * P.CF;
+        const __nv_bfloat16* p11 = img + ((size_t)t.r1 * P.Wf + t.c1) * P.CF;
+        float a00[8], a01[8], a10[8], a11[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p00 + c8 * 8)), a00);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p01 + c8 * 8)), a01);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p10 + c8 * 8)), a10);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p11 + c8 * 8)), a11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = sel_sum(t, a00[j], a01[j], a10[j], a11[j]);
+        const float d = fminf(fmaxf(depth, P.depth_min), P.depth_max);
+        const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
+        const float bf = floorf(bi);
+        const int b0 = min(max((int)bf, 0), P.S - 1), b1 = min(max((int)bf + 1, 0), P.S - 1);
+        const float wb1 = bi - bf;
+        if (c8 < 2) {
+          const int ch = P.D + (c8 ? b1 : b0);
+          const float s = sel_sum(t, __bfloat162float(p00[ch]), __bfloat162float(p01[ch]),
+                                  __bfloat162float(p10[ch]), __bfloat162float(p11[ch]));
+          sp = s * (c8 ? wb1 : 1.0f - wb1);
+        }
+      }
+      sp += __shfl_xor_sync(FULL, sp, 1);
+      sp = bf16_round(sp);
+      const unsigned bal = __ballot_sync(FULL, vis);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o = __shfl_xor_sync(FULL, f[j], 16);
+        fv[2 * i][j] = half ? o : f[j];
+        fv[2 * i + 1][j] = half ? f[j] : o;
+      }
+      score[2 * i] = __shfl_sync(FULL, sp, 0);
+      score[2 * i + 1] = __shfl_sync(FULL, sp, 16);
+      if (bal & 1u) vis_mask |= 1u << (2 * i);
+      if (bal & 0x10000u) vis_mask |= 1u << (2 * i + 1);
+    }
+    if (vis_mask == 0) continue;  // warp-uniform: the statistics of an unseen voxel are the constant 0
+    // ---- pooling backward (closed form) ----------------------------------------------------------------------------
+    float mx = 0.f, smax = -INFINITY, nmax = 0.f;
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v)
+      if (vis_mask & (1u << v)) {
+        mx = fmaxf(mx, score[v]);
+        smax = fmaxf(smax, score[v]);
+      }
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v)
+      if ((vis_mask & (1u << v)) && score[v] == smax) nmax += 1.f;
+    float wv[LIFT_MAX_VIEWS], den = 0.f, mean[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean[j] = 0.f;
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+      wv[v] = (vis_mask & (1u << v)) ? expf(score[v] - mx) : 0.f;
+      den += wv[v];
+    }
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+      wv[v] = __fdiv_rn(wv[v], den);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mean[j] += wv[v] * fv[v][j];
+    }
+    const __nv_bfloat16* drow = dstats + n * P.stats_ld;
+    float dmean[8], dvar[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(drow + c8 * 8)), dmean);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(drow + P.D + c8 * 8)), dvar);
+    const float dsmax = __bfloat162float(drow[2 * P.D]);
+    float dw[LIFT_MAX_VIEWS], wdw = 0.f;
+#pragma unroll
+    for (int v = 0; v < LIFT_MAX_VIEWS; ++v) {
+      float s = 0.f;
+      if (vis_mask & (1u << v)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dd = fv[v][j] - mean[j];
+          s += fv[v][j] * dmean[j] + dd * dd * dvar[j];
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) s += __shfl_xor_sync(FULL, s, o);   // both half-warps hold all views
+      }
+      dw[v] = s;
+      wdw += wv[v] * s;
+    }
+    // ---- pass 2: scatter, two selected views per round (one per half-warp) -----------------------------------------------
+#pragma unroll
+    for (int i = 0; i < LIFT_MAX_VIEWS / 2; ++i) {
+      if (2 * i >= K) break;
+      const int k = 2 * i + half;
+      const bool act = k < K;
+      const int src = half ? sel[2 * i + 1] : sel[2 * i];
+      const float row = __shfl_sync(FULL, pr.row, src);
+      const float col = __shfl_sync(FULL, pr.col, src);
+      const float depth = __shfl_sync(FULL, pr.depth, src);
+      const bool vis = __shfl_sync(FULL, pr.vis ? 1 : 0, src) != 0 && act;
+      if (!vis) continue;  // uniform within a half-warp; no warp-wide operation follows in this iteration
+      const SelTaps t = make_sel_taps(row, col, P.Hf, P.Wf);
+      const float wk = half ? wv[2 * i + 1] : wv[2 * i];
+      const float sk = half ? score[2 * i + 1] : score[2 * i];
+      const float dwk = half ? dw[2 * i + 1] : dw[2 * i];
+      const float ds = wk * (dwk - wdw) + (sk == smax ? dsmax / nmax : 0.f);
+      float df[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float fk = half ? fv[2 * i + 1][j] : fv[2 * i][j];
+        df[j] = wk * (dmean[j] + 2.f * (fk - mean[j]) * dvar[j]);
+      }
+      float* gv = gimg + (size_t)src * P.Hf * P.Wf * P.CF;
+      float* g00 = gv + ((size_t)t.r0 * P.Wf + t.c0) * P.CF;
+      float* g01 = gv + ((size_t)t.r0 * P.Wf + t.c1) * P.CF;
+      float* g10 = gv + ((size_t)t.r1 * P.Wf + t.c0) * P.CF;
+      float* g11 = gv + ((size_t)t.r1 * P.Wf + t.c1) * P.CF;
+      sel_atomic_add8(g00 + c8 * 8, t.w00, df);
+      sel_atomic_add8(g01 + c8 * 8, t.w01, df);
+      sel_atomic_add8(g10 + c8 * 8, t.w10, df);
+      sel_atomic_add8(g11 + c8 * 8, t.w11, df);
+      if (c8 < 2) {
+        const float d = fminf(fmaxf(depth, P.depth_min), P.depth_max);
+        const float bi = logf(d / P.depth_min) * P.inv_log_range * score_scale;
+        const float bf = floorf(bi);
+        const int b0 = min(max((int)bf, 0), P.S - 1), b1 = min(max((int)bf + 1, 0), P.S - 1);
+        const float wb1 = bi - bf;
+        const int ch = P.D + (c8 ? b1 : b0);
+        const float gs = (c8 ? wb1 : 1.0f - wb1) * ds;
+        atomicAdd(g00 + ch, t.w00 * gs);
+        atomicAdd(g01 + ch, t.w01 * gs);
+        atomicAdd(g10 + ch, t.w10 * gs);
+        atomicAdd(g11 + ch, t.w11 * gs);
+      }
+    }
+  }
+}
+
+}  // namespace snapb200
+
+extern "C" int snapb200_lift_select_pool_backward(const SnapLiftParams* q, int top_k, const SnapLiftView* views,
+                                                  const float* view_centers, const void* fimg, const float* xs,
+                                                  const float* ys, const float* zs, const void* dstats, float* gimg,
+                                                  void* stream) {
+  SNAP_REQUIRE(q && views && view_centers && fimg && xs && ys && zs && dstats && gimg, "null pointer");
+  SNAP_REQUIRE(top_k >= 1 && top_k <= LIFT_MAX_VIEWS, "1 <= top_k <= %d required (got %d)", LIFT_MAX_VIEWS, top_k);
+  SNAP_REQUIRE(q->V > top_k && q->V <= SELECT_MAX_VIEWS, "view selection needs top_k < V <= %d", SELECT_MAX_VIEWS);
+  SNAP_REQUIRE(q->D == 128 && !q->no_variance && !q->add_minmax, "default statistics with feature_dim 128 only");
+  SNAP_REQUIRE(q->S >= 2 && q->CF == q->D + q->S && q->CF % 8 == 0, "bad channel split");
+  SNAP_REQUIRE(q->stats_ld % 8 == 0 && q->stats_ld >= 2 * q->D + 8, "stats_ld too small");
+  LiftParams P;
+  memcpy(&P, q, sizeof(P));
+  lift_select_pool_bwd_kernel<<<(unsigned)(q->X * q->Y), 256, 0, (cudaStream_t)stream>>>(
+      P, top_k, reinterpret_cast<const LiftView*>(views), view_centers, (const __nv_bfloat16*)fimg, xs, ys, zs,
+      (const __nv_bfloat16*)dstats, gimg);
+  return check_launch("lift_select_pool_bwd_kernel");
+}

@@ -813,3 +813,18 @@ def loc_pose_scoring_backward(sim: torch.Tensor, point_scale: torch.Tensor, i_xy
         C.byref(p), C.c_void_p(_ptr(sim)), C.c_void_p(_ptr(point_scale)), C.c_void_p(_ptr(i_xy)),
         C.c_void_p(_ptr(valid_j)), C.c_void_p(_ptr(poses)), C.c_void_p(_ptr(dscores)), int(relu_mask),
         int(dsim.shape[1]), C.c_void_p(_ptr(dsim)), _stream()))
+
+
+def lift_select_pool_backward(p: "_lib.LiftParams", top_k: int, views: torch.Tensor, view_centers: torch.Tensor,
+                              fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor, zs: torch.Tensor,
+                              dstats: torch.Tensor, gimg: torch.Tensor) -> None:
+    """View-selection path (V > top_k): gimg f32 [V, Hf, Wf, D+S] += scatter-add of the statistics cotangent."""
+    _require(fimg, torch.bfloat16, "fimg")
+    _require(dstats, torch.bfloat16, "dstats")
+    _require(gimg, torch.float32, "gimg")
+    assert gimg.is_contiguous() and gimg.numel() == p.V * p.Hf * p.Wf * p.CF
+    assert dstats.is_contiguous() and dstats.shape[1] == p.stats_ld and dstats.shape[0] >= p.X * p.Y * p.Z
+    _lib.check(_lib.lib().snapb200_lift_select_pool_backward(
+        C.byref(p), top_k, C.c_void_p(_ptr(views)), C.c_void_p(_ptr(view_centers)), C.c_void_p(_ptr(fimg)),
+        C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)), C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(dstats)),
+        C.c_void_p(_ptr(gimg)), _stream()))

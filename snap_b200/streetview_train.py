@@ -1,4 +1,5 @@
-"""Backward of the camera -> BEV lift of one scene (all-views path, default statistics, 'max' vertical pooling) from the
+"""Backward of the camera -> BEV lift of one scene (all-views and view-selection paths, default statistics, 'max' vertical
+pooling) from the
 cotangent of the street-view feature plane down to the parameters of `fusion_mlp` / `proj_mlp` and to the encoder
 features -- what `jax.grad` computes through `snap/models/streetview_encoder.py:228-286` and
 `snap/models/bev_mapper.py:56-88`.
@@ -76,11 +77,14 @@ class LiftBackward:
 
     def scene_backward(self, lp, views: torch.Tensor, fimg: torch.Tensor, crop: torch.Tensor, xs: torch.Tensor,
                        ys: torch.Tensor, zs: torch.Tensor, volume: Optional[torch.Tensor], valid: Optional[torch.Tensor],
-                       dplane: torch.Tensor) -> torch.Tensor:
+                       dplane: torch.Tensor, top_k: Optional[int] = None, view_centers: Optional[torch.Tensor] = None,
+                       max_view_distance: Optional[float] = None) -> torch.Tensor:
         """lp / views / fimg / xs / ys / zs: the arguments of the scene's forward `ops.lift_gather_pool`; crop bf16
         [V*hf*wf, 128] = relu(cropped finest FPN level) (the proj MLP's input); volume bf16 [N,128] / valid u8 [N] = the
         forward's feature volume, or None after the FUSED forward (`lift_fused_kernel` never materialises the volume): it is
         then recomputed here with one more GEMM, so training can keep the single-kernel forward; dplane bf16 [X*Y, 128].
+        top_k / view_centers (/ max_view_distance): the scene ran on the view-selection path (V > top_k,
+        `ops.lift_select_pool`), whose backward kernel repeats the selection.
         Adds this scene's parameter gradients to `self.g` and returns dcrop bf16 [V*hf*wf, 128] (cotangent of the
         un-activated encoder features)."""
         N, cells, Z = lp.X * lp.Y * lp.Z, lp.X * lp.Y, lp.Z
@@ -89,7 +93,11 @@ class LiftBackward:
             raise NotImplementedError("voxel and texel counts must be multiples of 16 (split-K weight-gradient kernel)")
         buf, g = self._buffers(N, rows_img, lp.V, lp.Hf, lp.Wf), self._g1
         # recompute this scene's statistics and hidden rows (the forward keeps them for one scene at a time)
-        ops.lift_gather_pool(lp, views, fimg, xs, ys, zs, buf["stats"], buf["valid"])
+        select = top_k is not None and lp.V > top_k
+        if select:
+            ops.lift_select_pool(lp, top_k, max_view_distance, views, view_centers, fimg, xs, ys, zs, buf["stats"], buf["valid"])
+        else:
+            ops.lift_gather_pool(lp, views, fimg, xs, ys, zs, buf["stats"], buf["valid"])
         ops.gemm(buf["stats"], self.Bf0, buf["hid"], m_rows=N, seg_k=self.ld, bias=self.b["fusion_mlp/Dense_0/bias"], relu=True)
         if volume is None:      # fused forward: the volume rows of this scene again (Dense 256 -> 128, zero where invalid, :281-282)
             ops.gemm(buf["hid"], self.Bf1, buf["vol"], m_rows=N, bias=self.b["fusion_mlp/Dense_1/bias"], row_mask=buf["valid"])
@@ -106,7 +114,10 @@ class LiftBackward:
         ops.gemm(buf["dhid"], Wc0[256:], buf["dstats"][:, 256:], m_rows=N, seg_k=256)
         # pooling + depth score + bilinear gather: scatter-add into the projected feature maps
         buf["gimg"].zero_()
-        ops.lift_gather_pool_backward(lp, views, fimg, xs, ys, zs, buf["dstats"], buf["gimg"])
+        if select:
+            ops.lift_select_pool_backward(lp, top_k, views, view_centers, fimg, xs, ys, zs, buf["dstats"], buf["gimg"])
+        else:
+            ops.lift_gather_pool_backward(lp, views, fimg, xs, ys, zs, buf["dstats"], buf["gimg"])
         # proj MLP: fimg = relu(crop) Wp + bp
         ops.cast_pad_bf16(buf["gimg"].view(rows_img, self.CF), buf["gimg_bf"][:rows_img])
         ops.dense_wgrad(crop, buf["gimg_bf"], rows_img, self.D, self.CF, g["proj_mlp/Dense_0/kernel"], g["proj_mlp/Dense_0/bias"])

@@ -76,3 +76,54 @@ def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd):
     grads = {k: {n: {a: v.grad.numpy() for a, v in d.items()} for n, d in tt.items()} for k, tt in tp.items()}
     fwd = {k: t[k].detach().numpy() for k in ("crop", "fimg", "vol", "plane")}
     return fwd, grads, x.grad.numpy()
+
+
+def _pool(feats, score, vis):
+    """pool_multiview_features (:141-178), weighted branch: feats [N,K,D], score [N,K], vis [N,K] (numpy bool)."""
+    v = torch.from_numpy(np.ascontiguousarray(vis))
+    any_v = v.any(-1)
+    v_ = torch.where(any_v[:, None], v, torch.ones_like(v))
+    neg = torch.full_like(score, -float("inf"))
+    mxs = torch.clamp(torch.where(v_, score, neg).amax(-1, keepdim=True), min=0.0)
+    e = torch.where(v_, torch.exp(score - mxs), torch.zeros_like(score))
+    w = e / e.sum(-1, keepdim=True)
+    mean = (w[..., None] * feats).sum(1)
+    var = (w[..., None] * (feats - mean[:, None]) ** 2).sum(1)
+    smax = torch.where(v_, score, neg).amax(-1, keepdim=True)
+    stats = torch.cat([mean, var, smax], -1)
+    return torch.where(any_v[:, None], stats, torch.zeros_like(stats))
+
+
+def gather_pool_stats_select(fimg: torch.Tensor, p2d: np.ndarray, idx: np.ndarray, vis: np.ndarray, depth: np.ndarray,
+                             D: int = 128, depth_min_max=(1.0, 32.0)) -> torch.Tensor:
+    """The V > top_k path: p2d [N,K,2], idx [N,K], vis [N,K], depth [N,K] = the GATHERED observations of the selected views
+    (streetview_encoder.py:241-249); sampling = interpolate_views_selective (:80-105) with the coordinate / weight
+    arithmetic in bf16 (constants here) and the value roundings straight-through."""
+    rd = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16).float()
+    V, Hf, Wf, CF = fimg.shape
+    S = CF - D
+    size = torch.tensor([Hf, Wf], dtype=torch.float32)
+    pt = rd(p2d)
+    pt = torch.clamp(torch.minimum((pt - 0.5).to(torch.bfloat16).float(), (size - 1).to(torch.bfloat16).float()), min=0.0)
+    lo = torch.floor(pt)
+    w_up = (pt - lo).to(torch.bfloat16).float()
+    w_lo = (1.0 - w_up).to(torch.bfloat16).float()
+    lo = lo.long()
+    vi = torch.from_numpy(np.ascontiguousarray(idx)).long()
+    f = 0
+    for a in range(2):
+        for b in range(2):
+            r = torch.clamp(lo[..., 0] + a, 0, Hf - 1)
+            c = torch.clamp(lo[..., 1] + b, 0, Wf - 1)
+            w = ((w_up[..., 0] if a else w_lo[..., 0]) * (w_up[..., 1] if b else w_lo[..., 1])).to(torch.bfloat16).float()
+            f = f + w[..., None] * fimg[vi, r, c]
+    feats, scales = f[..., :D], f[..., D:]
+    mn, mx = depth_min_max
+    d = torch.clamp(torch.from_numpy(depth.astype(F)), mn, mx)
+    c = torch.log(d / mn) / float(np.log(F(mx / mn))) * (S - 1)
+    blo = torch.floor(c)
+    wb = c - blo
+    b0 = torch.clamp(blo.long(), 0, S - 1)
+    b1 = torch.clamp(blo.long() + 1, 0, S - 1)
+    score = (1 - wb) * torch.gather(scales, -1, b0[..., None])[..., 0] + wb * torch.gather(scales, -1, b1[..., None])[..., 0]
+    return _pool(feats, score, vis)

@@ -75,3 +75,25 @@ def test_torch_lift_autograd_equals_closed_forms():
             b0, b1, wb = bins_all[v]
             closed[v] = bf.lift_gather_backward((Hf, Wf, CF), taps, wts, (b0, b1), wb, df[v], ds[v], D)
     assert np.abs(closed - auto).max() <= 1e-6 * (1 + np.abs(auto).max())
+
+
+def test_torch_select_lift_forward_close_to_numpy_oracle():
+    """V > top_k: the torch restatement of the selective path (bf16 coordinate / weight arithmetic as constants, value
+    roundings straight-through) against the NumPy oracle in bf16-emulation mode (which also rounds the values)."""
+    from oracle import bev_mapper as obm, streetview_encoder as osv
+    from util import bf16_np, rd_bf16, rel_l2
+    from lift_torch_ref import gather_pool_stats_select
+    fimg, ocam, oT, xyz, fp, p2d, vis, depth = _scene(V=6, seed=8, spacing=0.5, same_side=True)
+    fimg = bf16_np(fimg)
+    pts = xyz.reshape(-1, 3)
+    idx, _ = osv.view_selection(pts, oT, vis, 4)
+    g = lambda a: np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
+    dbg = {}
+    obm.lift_scene(fimg, ocam, oT, xyz, fp, rd=rd_bf16, debug=dbg, top_k=4)
+    ref = np.concatenate(dbg["stats"])
+    assert np.array_equal(np.concatenate(dbg["view_indices"]), idx)
+    got = gather_pool_stats_select(torch.from_numpy(fimg), g(p2d), idx, g(vis), g(depth)).numpy()
+    seen = g(vis).any(-1)
+    assert (g(vis).sum(-1) >= 2).mean() > 0.01 and not got[~seen].any() and not ref[~seen].any()
+    assert rel_l2(got[seen, :128], ref[seen, :128]) < 1e-2 and rel_l2(got[seen, 128:256], ref[seen, 128:256]) < 3e-2
+    assert np.abs(got[seen, 256] - ref[seen, 256]).max() < 5e-2

@@ -189,3 +189,47 @@ def test_match_head_and_fuse_max_backward_vs_emulation():
         ra, rb = torch.zeros((cells, C), dtype=torch.bfloat16), torch.zeros((cells, C), dtype=torch.bfloat16)
         emu.fuse_max_backward(bf(a), va, bf(c), vb, bf(g), cells, C, ra, rb)
         assert torch.equal(da.cpu(), ra) and torch.equal(db.cpu(), rb)
+
+
+def test_lift_select_pool_backward_vs_autograd():
+    """V > top_k: `snapb200_lift_select_pool_backward` vs autograd of the selective-path restatement
+    (tests/lift_torch_ref.py::gather_pool_stats_select; selection / gathered observations from the NumPy oracle)."""
+    from lift_torch_ref import gather_pool_stats_select
+    from oracle import bev_mapper as obm, grids as ogrids, streetview_encoder as osv
+    from snap_b200 import bev_mapper, configs, ops, streetview_encoder as sve, synthetic, types
+    G, V, K, hw, hf, wf = 24, 6, 4, (64, 96), 16, 24
+    rng = np.random.default_rng(51)
+    data = synthetic.make_tile(8, V, hw, G, spacing=0.5, same_side=True)
+    mapper = bev_mapper.BEVMapper(configs.bev_mapper(("streetview",)), types.Grid2D((G, G), 0.2))
+    xs, ys, zs = mapper.build_xyz_grid(data)
+    Z = zs.shape[1]
+    N = G * G * Z
+    fimg_np = bf16_np(rng.standard_normal((V, hf, wf, 160)))
+    dstats_np = bf16_np(rng.standard_normal((N, 288)) * 0.1)
+    dev = "cuda"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(dev)
+    cfg = configs.streetview_encoder()
+    cfg.top_k_view_selection = K
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    centers = t(data["T_view2scene"].t[0].reshape(-1))
+    gimg = torch.zeros((V, hf, wf, 160), dtype=torch.float32, device=dev)
+    ops.lift_select_pool_backward(lp, K, views, centers, t(fimg_np).to(torch.bfloat16), t(xs), t(ys), t(zs[0]),
+                                  t(dstats_np).to(torch.bfloat16), gimg)
+    torch.cuda.synchronize()
+    got = gimg.cpu().numpy()
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    pts = xyz.reshape(-1, 3)
+    p2d, vis, depth, _ = osv.project_points_to_views(oT, ocam, pts)
+    idx, _ = osv.view_selection(pts, oT, vis, K)
+    g = lambda a: np.take_along_axis(a, idx[..., None] if a.ndim == 3 else idx, 1)
+    ft = torch.from_numpy(fimg_np).requires_grad_(True)
+    stats = gather_pool_stats_select(ft, g(p2d), idx, g(vis), g(depth))
+    (stats * torch.from_numpy(dstats_np[:, :257])).sum().backward()
+    ref = ft.grad.numpy()
+    e_f, e_s = rel_l2(got[..., :128], ref[..., :128]), rel_l2(got[..., 128:], ref[..., 128:])
+    print(f"select V={V} K={K}: more than K visible {(vis.sum(-1) > K).mean():.3f}; rel_l2 features {e_f:.5f}, scale logits {e_s:.5f}")
+    assert (vis.sum(-1) > K).mean() > 0.002 and np.abs(ref).sum() > 0
+    assert e_f < 2e-2 and e_s < 3e-2          # the forward's bf16 value roundings are straight-through in the kernel
