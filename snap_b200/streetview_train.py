@@ -141,11 +141,17 @@ class MatchingHeadBackward:
         self.C = self.K.shape[0]
         self.Kc = self.K.to(torch.bfloat16).contiguous()                                 # dX operand [N = C, K = 32]
         self.g = {"kernel": torch.zeros_like(self.K), "bias": torch.zeros_like(self.b)}
+        self._g1 = {"kernel": torch.zeros_like(self.K), "bias": torch.zeros_like(self.b)}
         self._buf: Dict = {}
 
-    def backward(self, plane: torch.Tensor, valid: torch.Tensor, dmatch: torch.Tensor) -> torch.Tensor:
-        """plane bf16 [cells, C] / valid u8 [cells] = `bev_features`; dmatch bf16 [cells, 32].  Writes the gradients of
-        matching_proj into `self.g` and returns dplane bf16 [cells, C]."""
+    def zero_grads(self) -> None:
+        for v in self.g.values():
+            v.zero_()
+
+    def backward(self, plane: torch.Tensor, valid: torch.Tensor, dmatch: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+        """plane bf16 [cells, C] / valid u8 [cells] = `bev_features`; dmatch bf16 [cells, 32].  Writes (or, with
+        `accumulate`, adds) the gradients of matching_proj into `self.g` and returns dplane bf16 [cells, C] (a buffer that
+        the next call with the same number of cells overwrites)."""
         cells = valid.numel()
         if cells % 16:
             raise NotImplementedError("the number of BEV cells must be a multiple of 16 (split-K weight-gradient kernel)")
@@ -155,7 +161,11 @@ class MatchingHeadBackward:
                                 torch.zeros((R, self.C), dtype=torch.bfloat16, device=self.dev))
         dy, dplane = self._buf[cells]
         ops.match_head_backward(plane, valid, cells, self.C, self.K, self.b, dmatch, dy)
-        ops.dense_wgrad(plane, dy, cells, self.C, 32, self.g["kernel"], self.g["bias"])
+        g = self._g1 if accumulate else self.g
+        ops.dense_wgrad(plane, dy, cells, self.C, 32, g["kernel"], g["bias"])
+        if accumulate:
+            for k in self.g:
+                self.g[k] += g[k]
         ops.gemm(dy, self.Kc, dplane, m_rows=cells, seg_k=32)
         return dplane
 

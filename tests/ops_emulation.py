@@ -186,23 +186,28 @@ def vertical_max_backward(vol, valid, dplane, cells, Z, Cc, dvol):
     dvol.reshape(-1)[: cells * Z * Cc] = torch.where(tie, g.expand(cells, Z, Cc), torch.zeros(())).to(dvol.dtype).reshape(-1)
 
 
-def make_lift_emulation(p2d, vis, depth):
-    """`ops.lift_gather_pool` / `ops.lift_gather_pool_backward` for ONE fixed scene whose projection (p2d, vis, depth:
-    NumPy oracle) is captured here; the float path is tests/lift_torch_ref.py (forward checked against the NumPy oracle,
-    autograd against the closed forms of the CUDA kernel, tests/test_lift_backward_ref_cpu.py)."""
+def make_lift_emulation(p2d, vis, depth, more=None):
+    """`ops.lift_gather_pool` / `ops.lift_gather_pool_backward` for fixed scenes whose projection (p2d, vis, depth:
+    NumPy oracle) is captured here -- one scene, or several told apart by their voxel count (`more`: {N: (p2d, vis,
+    depth)}); the float path is tests/lift_torch_ref.py (forward checked against the NumPy oracle, autograd against the
+    closed forms of the CUDA kernel, tests/test_lift_backward_ref_cpu.py)."""
     from lift_torch_ref import gather_pool_stats
+    scenes = dict(more or {})
+    scenes[len(p2d)] = (p2d, vis, depth)
 
     def lift_gather_pool(lp, views, fimg, xs, ys, zs, stats, valid, dbg_vis=None, dbg_taps=None):
         N = lp.X * lp.Y * lp.Z
-        st = gather_pool_stats(fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF), p2d, vis, depth, lp.D)
+        sp2d, svis, sdepth = scenes[N]
+        st = gather_pool_stats(fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF), sp2d, svis, sdepth, lp.D)
         stats[:N].zero_()
         stats[:N, : st.shape[1]] = st.to(stats.dtype)
-        valid[:N] = torch.from_numpy(vis.any(-1).astype(np.uint8))
+        valid[:N] = torch.from_numpy(svis.any(-1).astype(np.uint8))
 
     def lift_gather_pool_backward(lp, views, fimg, xs, ys, zs, dstats, gimg):
         N = lp.X * lp.Y * lp.Z
+        sp2d, svis, sdepth = scenes[N]
         f = fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF).clone().requires_grad_(True)
-        st = gather_pool_stats(f, p2d, vis, depth, lp.D)
+        st = gather_pool_stats(f, sp2d, svis, sdepth, lp.D)
         (st * dstats[:N, : st.shape[1]].float()).sum().backward()
         gimg += f.grad.reshape(gimg.shape)
 
