@@ -219,7 +219,7 @@ def emulated_ops(extra=None):
     """Replace the product's operator wrappers (and the weight bank's device pass) by the emulation above."""
     names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
              "stdconv_backward", "vertical_max_backward", "match_head_backward", "fuse_max_backward",
-             "loc_nll_backward", "loc_pose_scoring_backward")
+             "loc_nll_backward", "loc_pose_scoring_backward", "sem_labels", "sem_loss", "sem_loss_grad", "adam_step")
     table = {n: globals()[n] for n in names}
     table.update(extra or {})
     names = tuple(table)
@@ -287,3 +287,46 @@ def loc_pose_scoring_backward(sim, point_scale, i_xy, valid_j, poses, dscores, H
         if relu_mask:
             g = g * (sim[b].float() > 0)
         dsim[b, :N] = g.to(dsim.dtype)
+
+
+# ---- semantic losses / optimizer (GPU-verified kernels; emulated here so that a whole train_step runs on the CPU) --------
+def sem_labels(sel_area, sel_excl, sel_indep, num_gt, masks, bev_valid, labels_area, valid_area, labels_excl, masks_indep):
+    m = masks.reshape(-1, num_gt) != 0
+
+    def pick(sel):
+        return torch.stack([m[:, list(s)].any(1) for s in sel], 1)                # 'line' absorbs its siblings (:259-266)
+    a = pick(sel_area)
+    labels_area.reshape(-1)[:] = a.int().argmax(1).int()
+    valid_area.reshape(-1)[:] = a.any(1).to(torch.uint8)
+    if labels_excl is not None:
+        e = pick(sel_excl)
+        labels_excl.reshape(-1)[:] = torch.where(e.any(1), e.int().argmax(1), torch.tensor(len(sel_excl))).int()   # void
+        masks_indep.reshape(m.shape[0], -1)[:] = m[:, list(sel_indep)].to(torch.uint8)
+
+
+def _total_loss(logits, labels_area, valid_area, labels_excl, masks_indep, valid, Ka, Ke, Ki, weights):
+    from oracle import semantic_net as osn
+    B, cells, _ = logits.shape
+    r = lambda t: t.reshape(B, 1, cells, *t.shape[2:]).numpy() if t is not None else None
+    w = [None if x is None else x.numpy() for x in (weights or [None] * 4)]
+    return osn.total_loss_torch(logits[..., : Ka + Ke + Ki].reshape(B, 1, cells, -1), r(labels_area), r(valid_area) != 0,
+                                r(labels_excl), r(masks_indep), r(valid) != 0, Ka, Ke, *w)
+
+
+def sem_loss(logits, labels_area, valid_area, labels_excl, masks_indep, valid, Ka, Ke, Ki, weights, out):
+    out.zero_()
+    out[:, 3] = _total_loss(logits, labels_area, valid_area, labels_excl, masks_indep, valid, Ka, Ke, Ki, weights)[1]
+
+
+def sem_loss_grad(logits, labels_area, valid_area, labels_excl, masks_indep, valid, Ka, Ke, Ki, weights, counts, dlogits):
+    lg = logits.clone().requires_grad_(True)
+    _total_loss(lg, labels_area, valid_area, labels_excl, masks_indep, valid, Ka, Ke, Ki, weights)[0].backward()
+    B, cells, ld = logits.shape
+    dlogits.zero_()
+    dlogits[: B * cells, :ld] = lg.grad.reshape(B * cells, ld).to(dlogits.dtype)
+
+
+def adam_step(p, m, v, g, lr, step, b1=0.9, b2=0.999, eps=1e-8):
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    p.sub_(lr * (m / (1 - b1 ** step)) / (torch.sqrt(v / (1 - b2 ** step)) + eps))
