@@ -68,7 +68,8 @@ __device__ __forceinline__ void relu_open(float xh0, float xh1, __nv_bfloat162 s
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int HW, int C,
                      const double* __restrict__ acc, int replica_stride, const float* __restrict__ scale,
-                     const float* __restrict__ bias, int post_relu, int pix_per_block, double* __restrict__ accb) {
+                     const float* __restrict__ bias, int pre_relu, int post_relu, int pix_per_block,
+                     double* __restrict__ accb) {
   const int CV = C / 8, PL = 256 / CV;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const int n = blockIdx.y, c0 = cv * 8, cpg = C / 32;
@@ -104,7 +105,12 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 xf = unpack_bf16(xu[j]), df = unpack_bf16(du[j]);
+        float2 xf = unpack_bf16(xu[j]);
+        const float2 df = unpack_bf16(du[j]);
+        if (pre_relu) {  // GroupNorm of relu(x) (FPN: image_encoder.py:86-88); the statistics in acc are those of relu(x)
+          xf.x = fmaxf(xf.x, 0.f);
+          xf.y = fmaxf(xf.y, 0.f);
+        }
         const float h0 = (xf.x - mean[2 * j]) * rstd[2 * j], h1 = (xf.y - mean[2 * j + 1]) * rstd[2 * j + 1];
         bool o0 = true, o1 = true;
         if (post_relu) relu_open(h0, h1, sc2[j], bi2[j], o0, o1);
@@ -138,8 +144,8 @@ template <bool PADDED>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                     const __nv_bfloat16* __restrict__ add, int H, int W, int C, const double* __restrict__ acc,
-                    int replica_stride, const float* __restrict__ scale, const float* __restrict__ bias, int post_relu,
-                    const double* __restrict__ accb, int pix_per_block, __nv_bfloat16* __restrict__ dx) {
+                    int replica_stride, const float* __restrict__ scale, const float* __restrict__ bias, int pre_relu,
+                    int post_relu, const double* __restrict__ accb, int pix_per_block, __nv_bfloat16* __restrict__ dx) {
   const int CV = C / 8, PL = 256 / CV;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const int n = blockIdx.y, c0 = cv * 8, cpg = C / 32, HW = H * W;
@@ -189,13 +195,21 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     uint32_t ov[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 xf = unpack_bf16(xu[j]), df = unpack_bf16(du[j]), af = unpack_bf16(au[j]);
+      float2 xf = unpack_bf16(xu[j]);
+      const float2 df = unpack_bf16(du[j]), af = unpack_bf16(au[j]);
+      const bool p0 = !pre_relu || xf.x > 0.f, p1 = !pre_relu || xf.y > 0.f;   // the ReLU in front of the GroupNorm
+      if (pre_relu) {
+        xf.x = fmaxf(xf.x, 0.f);
+        xf.y = fmaxf(xf.y, 0.f);
+      }
       const float h0 = (xf.x - mean[2 * j]) * rstd[2 * j], h1 = (xf.y - mean[2 * j + 1]) * rstd[2 * j + 1];
       bool o0 = true, o1 = true;
       if (post_relu) relu_open(h0, h1, sc2[j], bi2[j], o0, o1);
       const float d0 = o0 ? df.x : 0.f, d1 = o1 ? df.y : 0.f;
-      const float r0 = rstd[2 * j] * (d0 * scf[2 * j] - g1[2 * j] - h0 * g2[2 * j]) + af.x;
-      const float r1 = rstd[2 * j + 1] * (d1 * scf[2 * j + 1] - g1[2 * j + 1] - h1 * g2[2 * j + 1]) + af.y;
+      float r0 = rstd[2 * j] * (d0 * scf[2 * j] - g1[2 * j] - h0 * g2[2 * j]);
+      float r1 = rstd[2 * j + 1] * (d1 * scf[2 * j + 1] - g1[2 * j + 1] - h1 * g2[2 * j + 1]);
+      r0 = (p0 ? r0 : 0.f) + af.x;
+      r1 = (p1 ? r1 : 0.f) + af.y;
       ov[j] = pack_bf16(r0, r1);
     }
     size_t orow = (size_t)n * HW + p;
@@ -277,6 +291,46 @@ stdconv_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dws, i
   }
 }
 
+// Backward of the x2 bilinear up-sampling of the FPN (image_encoder.py:86-91; upsample2x_kernel): dx[n, hc, wc, :] = sum
+// over the (at most 4 x 4) fine pixels whose clamped taps hit the coarse pixel, with the forward's weights.  One thread
+// per (coarse pixel, 8 channels); a gather, so the result is deterministic.
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int Nimg, int h, int w, int C,
+                                      __nv_bfloat16* __restrict__ dx) {
+  const int cv = C / 8;
+  const int H = 2 * h, W = 2 * w;
+  const long long total = (long long)Nimg * h * w * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int wc = (int)(pix % w);
+  const int hc = (int)((pix / w) % h);
+  const int n = (int)(pix / ((long long)w * h));
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int ho = max(2 * hc - 1, 0); ho <= min(2 * hc + 2, H - 1); ++ho) {
+    const int h0 = (ho & 1) ? (ho >> 1) : (ho >> 1) - 1;
+    const float fh = (ho & 1) ? 0.25f : 0.75f;
+    const float wh = (max(h0, 0) == hc ? 1.f - fh : 0.f) + (min(h0 + 1, h - 1) == hc ? fh : 0.f);
+    if (wh == 0.f) continue;
+    for (int wo = max(2 * wc - 1, 0); wo <= min(2 * wc + 2, W - 1); ++wo) {
+      const int w0 = (wo & 1) ? (wo >> 1) : (wo >> 1) - 1;
+      const float fw = (wo & 1) ? 0.25f : 0.75f;
+      const float ww = (max(w0, 0) == wc ? 1.f - fw : 0.f) + (min(w0 + 1, w - 1) == wc ? fw : 0.f);
+      if (ww == 0.f) continue;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)n * H + ho) * W + wo) * C + c8 * 8));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16(uu[j]);
+        acc[2 * j] += wh * ww * t.x;
+        acc[2 * j + 1] += wh * ww * t.y;
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + pix * C + c8 * 8) =
+      make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+}
+
 }  // namespace snapb200
 
 using namespace snapb200;
@@ -284,11 +338,11 @@ using namespace snapb200;
 extern "C" {
 
 int snapb200_gn_backward(const void* x, const void* dy, const void* add, int Nimg, int H, int W, int C,
-                         const double* acc, int replica_stride, const float* scale, const float* bias, int post_relu,
-                         int padded_out, double* accb, void* dx, float* dscale, float* dbias, void* stream) {
+                         const double* acc, int replica_stride, const float* scale, const float* bias, int pre_relu,
+                         int post_relu, int padded_out, double* accb, void* dx, float* dscale, float* dbias, void* stream) {
   SNAP_REQUIRE(x && dy && acc && scale && bias && accb && dx && dscale && dbias, "null pointer");
   SNAP_REQUIRE(Nimg >= 1 && H >= 1 && W >= 1, "empty problem");
-  SNAP_REQUIRE(C == 64 || C == 128 || C == 256, "C must be 64, 128 or 256");
+  SNAP_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512 || C == 1024 || C == 2048, "C must be a power of two in [64, 2048]");
   SNAP_REQUIRE(replica_stride >= Nimg * 64, "replica_stride must cover [Nimg][32][2] doubles");
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = check_cuda(cudaMemsetAsync(accb, 0, (size_t)Nimg * C * 2 * sizeof(double), s), "cudaMemsetAsync(accb)"))
@@ -301,19 +355,27 @@ int snapb200_gn_backward(const void* x, const void* dy, const void* add, int Nim
   if (ppb > HW) ppb = HW;
   dim3 grid((HW + ppb - 1) / ppb, Nimg);
   gn_bwd_reduce_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, HW, C, acc,
-                                            replica_stride, scale, bias, post_relu, ppb, accb);
+                                            replica_stride, scale, bias, pre_relu, post_relu, ppb, accb);
   if (int rc = check_launch("gn_bwd_reduce_kernel")) return rc;
   if (padded_out)
     gn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
                                                    (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias,
-                                                   post_relu, accb, ppb, (__nv_bfloat16*)dx);
+                                                   pre_relu, post_relu, accb, ppb, (__nv_bfloat16*)dx);
   else
     gn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
                                                     (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias,
-                                                    post_relu, accb, ppb, (__nv_bfloat16*)dx);
+                                                    pre_relu, post_relu, accb, ppb, (__nv_bfloat16*)dx);
   if (int rc = check_launch("gn_bwd_apply_kernel")) return rc;
   gn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, s>>>(accb, Nimg, C, dscale, dbias);
   return check_launch("gn_bwd_params_kernel");
+}
+
+int snapb200_upsample2x_backward(const void* dy, int Nimg, int h, int w, int C, void* dx, void* stream) {
+  SNAP_REQUIRE(dy && dx && Nimg >= 1 && h >= 1 && w >= 1 && C % 8 == 0, "bad arguments");
+  const long long total = (long long)Nimg * h * w * (C / 8);
+  upsample2x_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, Nimg, h, w, C, (__nv_bfloat16*)dx);
+  return check_launch("upsample2x_bwd_kernel");
 }
 
 int snapb200_wt_segments(const void* in, int ld_in, int Cout, int Cin, int taps, void* out, int ld_out, void* stream) {

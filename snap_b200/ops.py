@@ -680,7 +680,7 @@ def sem_labels(sel_area: Sequence[Sequence[int]], sel_excl: Sequence[Sequence[in
 def gn_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: int, acc: torch.Tensor,
                 scale: torch.Tensor, bias: torch.Tensor, accb: torch.Tensor, dx: torch.Tensor, dscale: torch.Tensor,
                 dbias: torch.Tensor, *, post_relu: bool = True, padded_out: bool = False,
-                add: Optional[torch.Tensor] = None) -> None:
+                add: Optional[torch.Tensor] = None, pre_relu: bool = False) -> None:
     """GroupNorm(+ReLU) backward: x = the forward's GroupNorm input, acc = its statistics accumulators, dy = gradient
     w.r.t. the (activated) output; dx dense or zero-bordered; dscale / dbias f32 [Cc]; accb f64 scratch [n, Cc, 2]."""
     for t, nm in ((x, "x"), (dy, "dy"), (dx, "dx")):
@@ -698,7 +698,8 @@ def gn_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: i
         assert t.numel() >= Cc
     _lib.check(_lib.lib().snapb200_gn_backward(
         C.c_void_p(_ptr(x)), C.c_void_p(_ptr(dy)), C.c_void_p(_ptr(add)), n, H, W, Cc, C.c_void_p(_ptr(acc)),
-        C.c_int(acc.stride(0)), C.c_void_p(_ptr(scale)), C.c_void_p(_ptr(bias)), int(post_relu), int(padded_out),
+        C.c_int(acc.stride(0)), C.c_void_p(_ptr(scale)), C.c_void_p(_ptr(bias)), int(pre_relu), int(post_relu),
+        int(padded_out),
         C.c_void_p(_ptr(accb)), C.c_void_p(_ptr(dx)), C.c_void_p(_ptr(dscale)), C.c_void_p(_ptr(dbias)), _stream()))
 
 
@@ -828,3 +829,11 @@ def lift_select_pool_backward(p: "_lib.LiftParams", top_k: int, views: torch.Ten
         C.byref(p), top_k, C.c_void_p(_ptr(views)), C.c_void_p(_ptr(view_centers)), C.c_void_p(_ptr(fimg)),
         C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)), C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(dstats)),
         C.c_void_p(_ptr(gimg)), _stream()))
+
+
+def upsample2x_backward(dy: torch.Tensor, n: int, h: int, w: int, Cc: int, dx: torch.Tensor) -> None:
+    """dy bf16 [n, 2h, 2w, Cc] (cotangent of `upsample2x`'s output) -> dx bf16 [n, h, w, Cc]."""
+    _require(dy, torch.bfloat16, "dy")
+    _require(dx, torch.bfloat16, "dx")
+    assert dy.is_contiguous() and dx.is_contiguous() and dy.numel() >= 4 * n * h * w * Cc and dx.numel() >= n * h * w * Cc
+    _lib.check(_lib.lib().snapb200_upsample2x_backward(C.c_void_p(_ptr(dy)), n, h, w, Cc, C.c_void_p(_ptr(dx)), _stream()))

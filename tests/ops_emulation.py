@@ -79,9 +79,11 @@ def _stats(acc, n, hw, Cc):
     return mu.float(), (1.0 / torch.sqrt(var + 1e-5)).float()     # [n, 32]
 
 
-def _xhat(x, n, hw, Cc, acc):
+def _xhat(x, n, hw, Cc, acc, pre_relu=False):
     mu, rstd = _stats(acc, n, hw, Cc)
     xg = x[: n * hw, :Cc].float().reshape(n, hw, 32, Cc // 32)
+    if pre_relu:
+        xg = torch.relu(xg)
     return ((xg - mu[:, None, :, None]) * rstd[:, None, :, None]).reshape(n, hw, Cc), rstd
 
 
@@ -98,8 +100,8 @@ def _padded_rows(n, H, W):
 
 
 def gn_apply(x, n, H, W, Cc, acc, scale, bias, pre_relu, post_relu, layout, out, out_sub=None):
-    assert not pre_relu and out_sub is None and layout in (ops.LAYOUT_DENSE, ops.LAYOUT_PADDED)
-    xh, _ = _xhat(x, n, H * W, Cc, acc)
+    assert out_sub is None and layout in (ops.LAYOUT_DENSE, ops.LAYOUT_PADDED)
+    xh, _ = _xhat(x, n, H * W, Cc, acc, pre_relu)
     y = _gn_forward(xh, scale, bias, post_relu).reshape(n * H * W, Cc).to(out.dtype)
     if layout == ops.LAYOUT_DENSE:
         out[: n * H * W, :Cc] = y
@@ -108,9 +110,9 @@ def gn_apply(x, n, H, W, Cc, acc, scale, bias, pre_relu, post_relu, layout, out,
 
 
 def gn_backward(x, dy, n, H, W, Cc, acc, scale, bias, accb, dx, dscale, dbias, *, post_relu=True, padded_out=False,
-                add=None):
+                add=None, pre_relu=False):
     hw = H * W
-    xh, rstd = _xhat(x, n, hw, Cc, acc)
+    xh, rstd = _xhat(x, n, hw, Cc, acc, pre_relu)
     d = dy[: n * hw, :Cc].float().reshape(n, hw, Cc)
     if post_relu:
         d = d * (_gn_forward(xh, scale, bias, False) > 0).float()
@@ -123,6 +125,8 @@ def gn_backward(x, dy, n, H, W, Cc, acc, scale, bias, accb, dx, dscale, dbias, *
     s2 = (sx * sc.double()).reshape(n, 32, Cc // 32).sum(-1) / m
     rep = lambda t: t.float().repeat_interleave(Cc // 32, dim=1)[:, None, :]           # [n, 1, Cc]
     r = rep(rstd) * (d * sc - rep(s1) - xh * rep(s2))
+    if pre_relu:
+        r = r * (x[: n * hw, :Cc].float().reshape(n, hw, Cc) > 0)
     if add is not None:
         r = r + add[: n * hw, :Cc].float().reshape(n, hw, Cc)
     r = r.reshape(n * hw, Cc).to(dx.dtype)
@@ -219,7 +223,8 @@ def emulated_ops(extra=None):
     """Replace the product's operator wrappers (and the weight bank's device pass) by the emulation above."""
     names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
              "stdconv_backward", "vertical_max_backward", "match_head_backward", "fuse_max_backward",
-             "loc_nll_backward", "loc_pose_scoring_backward", "sem_labels", "sem_loss", "sem_loss_grad", "adam_step")
+             "loc_nll_backward", "loc_pose_scoring_backward", "sem_labels", "sem_loss", "sem_loss_grad", "adam_step",
+             "upsample2x", "upsample2x_backward")
     table = {n: globals()[n] for n in names}
     table.update(extra or {})
     names = tuple(table)
@@ -330,3 +335,17 @@ def adam_step(p, m, v, g, lr, step, b1=0.9, b2=0.999, eps=1e-8):
     m.mul_(b1).add_(g, alpha=1 - b1)
     v.mul_(b2).addcmul_(g, g, value=1 - b2)
     p.sub_(lr * (m / (1 - b1 ** step)) / (torch.sqrt(v / (1 - b2 ** step)) + eps))
+
+
+def upsample2x(x, n, h, w, Cc, y):
+    v = x.reshape(-1)[: n * h * w * Cc].float().reshape(n, h, w, Cc).permute(0, 3, 1, 2)
+    up = torch.nn.functional.interpolate(v, scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    y.reshape(-1)[: 4 * n * h * w * Cc] = up.reshape(-1).to(y.dtype)
+
+
+def upsample2x_backward(dy, n, h, w, Cc, dx):
+    v = torch.zeros((n, Cc, h, w), requires_grad=True)
+    up = torch.nn.functional.interpolate(v, scale_factor=2, mode="bilinear", align_corners=False)
+    g = dy.reshape(-1)[: 4 * n * h * w * Cc].float().reshape(n, 2 * h, 2 * w, Cc).permute(0, 3, 1, 2)
+    (up * g).sum().backward()
+    dx.reshape(-1)[: n * h * w * Cc] = v.grad.permute(0, 2, 3, 1).reshape(-1).to(dx.dtype)

@@ -1,0 +1,51 @@
+"""`snap_b200/encoder_train.py::FPNBackward` on the emulated operator layer vs torch autograd of the oracle's FPN decoder
+(`oracle/image_encoder.py::fpn_decoder`, pinned against the reference's own FPNDecoder): gradients of every skip_norm /
+skip_conv array and the cotangents of the four skip inputs, from a cotangent on the finest level only."""
+import numpy as np
+import torch
+
+from ops_emulation import emulated_ops, gn_stats
+from util import F, bf16_np, rd_bf16
+
+
+def test_fpn_backward_plan_matches_autograd():
+    from oracle import image_encoder as oie
+    from snap_b200 import configs, encoder_train, ops, params
+    rng = np.random.default_rng(41)
+    n, od = 2, 128
+    shapes = [(2, 4, 512), (4, 8, 256), (8, 16, 128), (16, 32, 64)]          # coarse -> fine (a narrow trunk for speed)
+    dec = {}
+    for level, (h, w, c) in enumerate(shapes):
+        dec[f"{level}_skip_norm"] = {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F),
+                                     "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+        dec[f"{level}_skip_conv"] = {"kernel": (rng.standard_normal((1, 1, c, od)) / np.sqrt(c)).astype(F)}
+    dec = params.round_to_bf16(dec)
+    skips_np = [bf16_np(rng.standard_normal((n, h, w, c))) for h, w, c in shapes]
+    dfin = bf16_np(rng.standard_normal((n, 16, 32, od)) * 0.1)
+    # reference
+    tp = {k: {a: torch.from_numpy(v).requires_grad_(True) for a, v in d.items()} for k, d in dec.items()}
+    xs = [torch.from_numpy(s).requires_grad_(True) for s in skips_np]
+    outs = oie.fpn_decoder(xs, tp, rd_bf16)
+    (outs[-1] * torch.from_numpy(dfin)).sum().backward()
+    # plan
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16)
+    with emulated_ops():
+        fb = encoder_train.FPNBackward(dec, n, shapes, torch.device("cpu"), od)
+        skips = [bf(s.reshape(-1, s.shape[-1])) for s in skips_np]
+        accs = []
+        for s, (h, w, c) in zip(skips, shapes):
+            acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64)
+            gn_stats(s, n, h * w, c, True, acc)                                  # the forward's statistics of relu(skip)
+            accs.append(acc)
+        dsk = fb.backward(skips, accs, bf(dfin.reshape(-1, od)))
+        got = fb.grads_tree()
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    errs = {}
+    for k, d in tp.items():
+        for a, t in d.items():
+            assert float(t.grad.norm()) > 1e-6, (k, a)
+            errs[f"{k}/{a}"] = rel(got[k][a], t.grad.numpy())
+    for level, (x, (h, w, c)) in enumerate(zip(xs, shapes)):
+        errs[f"skip{level}"] = rel(dsk[level][: n * h * w].float().numpy().reshape(n, h, w, c), x.grad.numpy())
+    print({k: round(float(v), 4) for k, v in errs.items()})
+    assert max(errs.values()) < 3e-2, errs

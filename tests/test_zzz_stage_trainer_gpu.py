@@ -148,3 +148,92 @@ def test_stage_head_training_reduces_the_loss():
     new = tr.params_tree()
     assert new["layers_1"]["unit01"]["conv2"]["kernel"].shape == (3, 3, 64, 64)
     assert not np.array_equal(new["layers_1"]["unit02"]["gn3"]["scale"], p["layers_1"]["unit02"]["gn3"]["scale"])
+
+
+@pytest.mark.parametrize("C", [64, 512, 2048])
+def test_gn_backward_pre_relu_and_wide_channels_vs_emulation(C):
+    """The FPN form of the GroupNorm backward (statistics of relu(x), dx masked by x > 0, no ReLU behind the norm) for the
+    channel counts of the FPN inputs (256 ... 2048)."""
+    import ops_emulation as emu
+    from snap_b200 import ops
+    rng = np.random.default_rng(C)
+    n, H, W = 2, 12, 16
+    rows = n * H * W
+    bf = lambda a: torch.from_numpy(bf16_np(a)).to(torch.bfloat16)
+    x, dy = bf(rng.standard_normal((rows, C))), bf(rng.standard_normal((rows, C)) * 0.1)
+    scale = torch.from_numpy(bf16_np(1 + 0.3 * rng.standard_normal(C)))
+    bias = torch.from_numpy(bf16_np(0.2 * rng.standard_normal(C)))
+
+    def run(mod, dev):
+        t = lambda a: a.to(dev)
+        acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64, device=dev)
+        mod.gn_stats(t(x), n, H * W, C, True, acc)
+        dx = torch.zeros((rows, C), dtype=torch.bfloat16, device=dev)
+        ds, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        accb = torch.zeros((n, C, 2), dtype=torch.float64, device=dev)
+        mod.gn_backward(t(x), t(dy), n, H, W, C, acc, t(scale), t(bias), accb, dx, ds, db, post_relu=False, pre_relu=True)
+        return dx.float().cpu().numpy(), ds.cpu().numpy(), db.cpu().numpy()
+
+    got, ref = run(ops, "cuda"), run(emu, "cpu")
+    e = [rel_l2(g, r) for g, r in zip(got, ref)]
+    print(f"C={C}: rel_l2 dx {e[0]:.5f}, dscale {e[1]:.6f}, dbias {e[2]:.6f}")
+    assert e[0] < 1e-2 and e[1] < 1e-3 and e[2] < 1e-3
+    assert not got[0][x.float().numpy() <= 0].any()
+
+
+def test_upsample2x_backward_vs_autograd():
+    import ops_emulation as emu
+    from snap_b200 import ops
+    rng = np.random.default_rng(6)
+    n, h, w, C = 2, 5, 7, 128
+    dy = torch.from_numpy(bf16_np(rng.standard_normal((n, 2 * h, 2 * w, C)))).to(torch.bfloat16)
+    dx = torch.full((n, h, w, C), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.upsample2x_backward(dy.cuda(), n, h, w, C, dx)
+    ref = torch.zeros((n, h, w, C), dtype=torch.bfloat16)
+    emu.upsample2x_backward(dy, n, h, w, C, ref)
+    assert rel_l2(dx.float().cpu().numpy(), ref.float().numpy()) < 5e-3
+    # adjointness with the forward kernel: <up(x), dy> == <x, up^T(dy)>
+    x = torch.from_numpy(bf16_np(rng.standard_normal((n, h, w, C)))).to(torch.bfloat16).cuda()
+    up = torch.zeros((n, 2 * h, 2 * w, C), dtype=torch.bfloat16, device="cuda")
+    ops.upsample2x(x, n, h, w, C, up)
+    lhs = float((up.float() * dy.cuda().float()).sum())
+    rhs = float((x.float() * dx.float()).sum())
+    assert abs(lhs - rhs) <= 2e-2 * (abs(lhs) + 1)
+
+
+def test_fpn_backward_vs_autograd():
+    """`encoder_train.FPNBackward` on the GPU vs autograd of the oracle's FPN decoder (the launch plan is CPU-verified in
+    tests/test_fpn_backward_plan_cpu.py)."""
+    from oracle import image_encoder as oie
+    from snap_b200 import encoder_train, ops, params
+    rng = np.random.default_rng(42)
+    n, od = 2, 128
+    shapes = [(4, 4, 2048), (8, 8, 1024), (16, 16, 512), (32, 32, 256)]
+    dec = {}
+    for level, (h, w, c) in enumerate(shapes):
+        dec[f"{level}_skip_norm"] = {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F),
+                                     "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+        dec[f"{level}_skip_conv"] = {"kernel": (rng.standard_normal((1, 1, c, od)) / np.sqrt(c)).astype(F)}
+    dec = params.round_to_bf16(dec)
+    skips_np = [bf16_np(rng.standard_normal((n, h, w, c))) for h, w, c in shapes]
+    dfin = bf16_np(rng.standard_normal((n, 32, 32, od)) * 0.1)
+    tp = {k: {a: torch.from_numpy(v).requires_grad_(True) for a, v in d.items()} for k, d in dec.items()}
+    xs = [torch.from_numpy(s).requires_grad_(True) for s in skips_np]
+    outs = oie.fpn_decoder(xs, tp, rd_bf16)
+    (outs[-1] * torch.from_numpy(dfin)).sum().backward()
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16).cuda()
+    fb = encoder_train.FPNBackward(dec, n, shapes, torch.device("cuda"), od)
+    skips = [bf(s.reshape(-1, s.shape[-1])) for s in skips_np]
+    accs = []
+    for s, (h, w, c) in zip(skips, shapes):
+        acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64, device="cuda")
+        ops.gn_stats(s, n, h * w, c, True, acc)
+        accs.append(acc)
+    dsk = fb.backward(skips, accs, bf(dfin.reshape(-1, od)))
+    torch.cuda.synchronize()
+    got = fb.grads_tree()
+    for k, d in tp.items():
+        for a, t in d.items():
+            assert rel_l2(got[k][a], t.grad.numpy()) < 3e-2, (k, a)
+    for level, (x, (h, w, c)) in enumerate(zip(xs, shapes)):
+        assert rel_l2(dsk[level][: n * h * w].float().cpu().numpy().reshape(n, h, w, c), x.grad.numpy()) < 3e-2, level
