@@ -1,0 +1,30 @@
+#!/usr/bin/env bash
+# First GPU call of round 2: everything written after the round-1 GPU budget was spent runs for the first
+# time.  Usage (from the repo root, on the GPU box):   bash tools/run_pending_gpu_tests.sh 2>&1 | tee gpurun_out/pending.log
+# Each stage runs under its own `timeout` so that a hanging kernel cannot hold the box.
+set -u
+mkdir -p gpurun_out
+PENDING="tests/test_zz_unweighted_fusion_gpu.py tests/test_zzz_lift_backward_gpu.py tests/test_zzz_localizer_backward_gpu.py tests/test_zzz_stage_trainer_gpu.py"
+
+echo "== 1. kernel-level tests under compute-sanitizer (small problem sizes) =="
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
+  python -m pytest --runxfail -q -s -x \
+    "tests/test_zzz_stage_trainer_gpu.py::test_wt_segments_and_stdconv_backward" \
+    "tests/test_zzz_stage_trainer_gpu.py::test_gn_backward_kernels_vs_emulation" \
+    "tests/test_zzz_stage_trainer_gpu.py::test_upsample2x_backward_vs_autograd" \
+    "tests/test_zzz_lift_backward_gpu.py::test_vertical_max_backward_vs_autograd" \
+    "tests/test_zzz_lift_backward_gpu.py::test_match_head_and_fuse_max_backward_vs_emulation" \
+    "tests/test_zzz_localizer_backward_gpu.py::test_loc_nll_backward_vs_emulation" \
+    "tests/test_zzz_localizer_backward_gpu.py::test_loc_pose_scoring_backward_vs_emulation" \
+  > gpurun_out/pending_sanitizer.log 2>&1
+echo "sanitizer stage: rc=$?"; tail -5 gpurun_out/pending_sanitizer.log
+
+echo "== 2. all pending tests, failures reported (not xfail-masked) =="
+timeout 1500 python -m pytest $PENDING --runxfail -q -s > gpurun_out/pending_pytest.log 2>&1
+echo "pytest stage: rc=$?"; tail -15 gpurun_out/pending_pytest.log
+
+echo "== 3. timings =="
+timeout 600 python tools/bench_cfg5.py --decoder resnet_stage > gpurun_out/pending_cfg5_stage.json 2> gpurun_out/pending_cfg5_stage.err
+echo "cfg5 resnet_stage: rc=$?"; cat gpurun_out/pending_cfg5_stage.json
+timeout 600 python tools/bench_backward.py > gpurun_out/pending_bench_backward.json 2> gpurun_out/pending_bench_backward.err
+echo "bench_backward: rc=$?"; cat gpurun_out/pending_bench_backward.json
