@@ -82,3 +82,131 @@ class FPNBackward:
                                          "bias": L["g"]["bias"].cpu().numpy().reshape(1, 1, 1, -1).copy()}
             out[f"{level}_skip_conv"] = {"kernel": L["g"]["kernel"].cpu().numpy().reshape(1, 1, L["c"], self.od).copy()}
         return out
+
+
+class BottleneckUnitTrainer:
+    """Training forward + backward of ONE stride-1 pre-activation bottleneck unit of the ResNet trunk
+    (`snap/models/resnet.py:103-134`), with the identity shortcut (cin == nout) or the 1x1 projection of the
+    PRE-ACTIVATED input (`:121-122`; first unit of stage 1), for any of the trunk's widths (GroupNorm backward up to 2048
+    channels; weight gradients in <= 1024-wide slices).  The launch plan is the one of `semantic_train.StageHeadTrainer`
+    (3x3 dX = mirrored 9-segment GEMM over the zero-bordered cotangent, dW = nine row-shifted split-K products), checked
+    on the emulated operator layer against autograd of the oracle's `residual_unit`.  Stride-2 units (phase-split layout)
+    are the next step of the encoder backward."""
+
+    def __init__(self, unit_params: Dict, n_img: int, H: int, W: int, device):
+        p = unit_params
+        k1, k2, k3 = (np.ascontiguousarray(p[c]["kernel"], dtype=F) for c in ("conv1", "conv2", "conv3"))
+        self.cin, self.nmid, self.nout = k1.shape[2], k1.shape[3], k3.shape[3]
+        self.proj = "conv_proj" in p
+        if not self.proj and self.cin != self.nout:
+            raise ValueError("a unit without conv_proj needs cin == nout (identity shortcut)")
+        self.n, self.H, self.W, self.dev = n_img, H, W, device
+        rows = self.rows = n_img * H * W
+        if rows % 16:
+            raise NotImplementedError("n * H * W must be a multiple of 16 (split-K weight-gradient kernel)")
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).reshape(-1).copy()).to(device)
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=device)
+        bf = lambda r, c: z(r, c, dt=torch.bfloat16)
+        bank = self.bank = image_encoder._WeightBank(device)
+        self.w = {c: bank.add(p[c]["kernel"], True) for c in ("conv1", "conv2", "conv3") + (("conv_proj",) if self.proj else ())}
+        bank.finalize()
+        off, self.master = 0, {}
+        for name, (_, k, cout, _, _) in zip(self.w, bank.entries):
+            self.master[name] = bank.master[off: off + k * cout].view(k, cout)
+            off += k * cout
+        self.gn = {g: (f32(p[g]["scale"]), f32(p[g]["bias"])) for g in ("gn1", "gn2", "gn3")}
+        self.g = {name: z(*m.shape) for name, m in self.master.items()}
+        self.gs = {name: z(*m.shape) for name, m in self.master.items()}
+        self.ggn = {g: (z(c), z(c)) for g, c in (("gn1", self.cin), ("gn2", self.nmid), ("gn3", self.nmid))}
+        R = image_encoder._round_up(max(rows, 128), 128)
+        self.Mb = n_img * (H + 2) * (W + 2)
+        Rb = image_encoder._round_up(self.Mb + 64, 128)
+        cin, nmid, nout = self.cin, self.nmid, self.nout
+        self.acc = torch.zeros((3, ops.GN_REPLICAS, n_img, 32, 2), dtype=torch.float64, device=device)
+        self.b = dict(a1=bf(R, cin), y1=bf(R, nmid), a2=bf(Rb, nmid), y2=bf(R, nmid), a3=bf(R, nmid), out=bf(R, nout),
+                      res=bf(R, nout) if self.proj else None, da3=bf(R, nmid), dc2b=bf(Rb, nmid), da2=bf(R, nmid),
+                      dc1=bf(R, nmid), da1p=bf(R, cin) if self.proj else None, da1=bf(R, cin), dx=bf(R, cin),
+                      accb=z(n_img, max(cin, nmid), 2, dt=torch.float64), tmp=z(1024, 1024))
+        self.bt = dict(conv1=bf(cin, nmid), conv2=bf(nmid, 9 * nmid), conv3=bf(nmid, nout),
+                       conv_proj=bf(cin, nout) if self.proj else None)
+
+    def _wgrad(self, x: torch.Tensor, dy: torch.Tensor, M: int, K: int, N: int, out: torch.Tensor) -> None:
+        """out f32 [K, N] = x^T dy with the split-K kernel's K, N <= 1024 limit lifted by slicing."""
+        for k0 in range(0, K, 1024):
+            kc = min(1024, K - k0)
+            for n0 in range(0, N, 1024):
+                nc = min(1024, N - n0)
+                if nc == N:
+                    ops.dense_wgrad(x[:, k0:k0 + kc], dy, M, kc, N, out[k0:k0 + kc], None)
+                else:           # column slices of dW are not contiguous: through a scratch tile
+                    tmp = self.b["tmp"].view(-1)[: kc * nc].view(kc, nc)
+                    ops.dense_wgrad(x[:, k0:k0 + kc], dy[:, n0:n0 + nc], M, kc, nc, tmp, None)
+                    out[k0:k0 + kc, n0:n0 + nc].copy_(tmp)
+
+    def forward(self, x: torch.Tensor, acc_x: torch.Tensor, next_acc=None) -> torch.Tensor:
+        """x bf16 [>= n*H*W, cin]; acc_x: the GroupNorm accumulators of x (f64 [REPLICAS, n, 32, 2])."""
+        n, H, W, rows, Bm, b = self.n, self.H, self.W, self.rows, self.bank.b_mats, self.b
+        hp, wp = H + 2, W + 2
+        seg = [(a - 1) * wp + (c - 1) for a in range(3) for c in range(3)]
+        self.bank.run()
+        self.acc.zero_()
+        self.x, self.acc_x = x, acc_x
+        ops.gn_apply(x, n, H, W, self.cin, acc_x, *self.gn["gn1"], False, True, ops.LAYOUT_DENSE, b["a1"])
+        res = x
+        if self.proj:                                                                        # resnet.py:121-122
+            ops.gemm(b["a1"], Bm[self.w["conv_proj"]], b["res"], m_rows=rows)
+            res = b["res"]
+        ops.gemm(b["a1"], Bm[self.w["conv1"]], b["y1"], m_rows=rows, gn_acc=self.acc[0], gn_rows_per_img=H * W)
+        ops.gn_apply(b["y1"], n, H, W, self.nmid, self.acc[0], *self.gn["gn2"], False, True, ops.LAYOUT_PADDED, b["a2"])
+        ops.gemm(b["a2"], Bm[self.w["conv2"]], b["y2"], m_rows=self.Mb, seg_off=seg, seg_k=self.nmid,
+                 remap=(hp, wp, 1, 1, H, W), gn_acc=self.acc[1], gn_rows_per_img=H * W)
+        ops.gn_apply(b["y2"], n, H, W, self.nmid, self.acc[1], *self.gn["gn3"], False, True, ops.LAYOUT_DENSE, b["a3"])
+        ops.gemm(b["a3"], Bm[self.w["conv3"]], b["out"], m_rows=rows, residual=res, gn_acc=next_acc, gn_rows_per_img=H * W)
+        return b["out"]
+
+    def backward(self, dout: torch.Tensor) -> torch.Tensor:
+        """dout bf16 [>= rows, nout] -> dx bf16 [rows.., cin]; parameter gradients in `grads_tree()`."""
+        n, H, W, rows, Bm, b = self.n, self.H, self.W, self.rows, self.bank.b_mats, self.b
+        cin, nmid, nout = self.cin, self.nmid, self.nout
+        hp, wp = H + 2, W + 2
+        seg = [(a - 1) * wp + (c - 1) for a in range(3) for c in range(3)]
+        lo = wp + 1
+        Mp = image_encoder._round_up(self.Mb - 2 * lo, 16)
+        # conv3
+        self._wgrad(b["a3"], dout, rows, nmid, nout, self.gs["conv3"])
+        ops.wt_segments(Bm[self.w["conv3"]], nout, nmid, 1, self.bt["conv3"])
+        ops.gemm(dout, self.bt["conv3"], b["da3"], m_rows=rows, seg_k=nout)
+        ops.gn_backward(b["y2"], b["da3"], n, H, W, nmid, self.acc[1], *self.gn["gn3"], b["accb"], b["dc2b"],
+                        *self.ggn["gn3"], post_relu=True, padded_out=True)
+        # conv2
+        for t, off in enumerate(seg):
+            ops.dense_wgrad(b["a2"][lo + off: lo + off + Mp], b["dc2b"][lo: lo + Mp], Mp, nmid, nmid,
+                            self.gs["conv2"][t * nmid: (t + 1) * nmid], None)
+        ops.wt_segments(Bm[self.w["conv2"]], nmid, nmid, 9, self.bt["conv2"])
+        ops.gemm(b["dc2b"], self.bt["conv2"], b["da2"], m_rows=self.Mb, seg_off=[-o for o in seg], seg_k=nmid,
+                 remap=(hp, wp, 1, 1, H, W))
+        ops.gn_backward(b["y1"], b["da2"], n, H, W, nmid, self.acc[0], *self.gn["gn2"], b["accb"], b["dc1"],
+                        *self.ggn["gn2"], post_relu=True)
+        # conv1 (+ conv_proj: both read the pre-activated a1)
+        self._wgrad(b["a1"], b["dc1"], rows, cin, nmid, self.gs["conv1"])
+        ops.wt_segments(Bm[self.w["conv1"]], nmid, cin, 1, self.bt["conv1"])
+        add = None
+        if self.proj:
+            self._wgrad(b["a1"], dout, rows, cin, nout, self.gs["conv_proj"])
+            ops.wt_segments(Bm[self.w["conv_proj"]], nout, cin, 1, self.bt["conv_proj"])
+            ops.gemm(dout, self.bt["conv_proj"], b["da1p"], m_rows=rows, seg_k=nout)
+            add = b["da1p"]
+        ops.gemm(b["dc1"], self.bt["conv1"], b["da1"], m_rows=rows, seg_k=nmid, residual=add)
+        ops.gn_backward(self.x, b["da1"], n, H, W, cin, self.acc_x, *self.gn["gn1"], b["accb"], b["dx"],
+                        *self.ggn["gn1"], post_relu=True, add=None if self.proj else dout)      # identity shortcut (:134)
+        for name in self.master:
+            ops.stdconv_backward(self.master[name], self.gs[name], self.g[name])
+        return b["dx"]
+
+    def grads_tree(self, unit_params: Dict) -> Dict:
+        out: Dict = {}
+        for name, g in self.g.items():
+            out[name] = {"kernel": g.cpu().numpy().reshape(np.asarray(unit_params[name]["kernel"]).shape).copy()}
+        for gname, (gs, gb) in self.ggn.items():
+            out[gname] = {"scale": gs.cpu().numpy().reshape(1, 1, 1, -1).copy(), "bias": gb.cpu().numpy().reshape(1, 1, 1, -1).copy()}
+        return out

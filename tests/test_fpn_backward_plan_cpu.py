@@ -49,3 +49,46 @@ def test_fpn_backward_plan_matches_autograd():
         errs[f"skip{level}"] = rel(dsk[level][: n * h * w].float().numpy().reshape(n, h, w, c), x.grad.numpy())
     print({k: round(float(v), 4) for k, v in errs.items()})
     assert max(errs.values()) < 3e-2, errs
+
+
+import pytest
+
+
+@pytest.mark.parametrize("cin,nmid,nout,proj,n,G", [(64, 64, 256, True, 1, 8), (256, 64, 256, False, 2, 4),
+                                                     (1024, 512, 2048, True, 1, 4)])
+def test_bottleneck_unit_backward_plan_matches_autograd(cin, nmid, nout, proj, n, G):
+    """`encoder_train.BottleneckUnitTrainer` (stride 1; identity or projection shortcut; weight gradients sliced for the
+    trunk's wide layers) on the emulated operator layer vs autograd of the oracle's `residual_unit` (resnet.py:103-134)."""
+    from oracle import resnet as ores
+    from snap_b200 import encoder_train, ops, params
+    rng = np.random.default_rng(cin + nout)
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+    p = {"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+         "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)}}
+    if proj:
+        p["conv_proj"] = {"kernel": ln(1, 1, cin, nout)}
+    p = params.round_to_bf16(p)
+    x_np = bf16_np(rng.standard_normal((n, G, G, cin)))
+    dout_np = bf16_np(rng.standard_normal((n, G, G, nout)) * 0.1)
+    tp = {k: {a: torch.from_numpy(v).requires_grad_(True) for a, v in d.items()} for k, d in p.items()}
+    xt = torch.from_numpy(x_np).requires_grad_(True)
+    y = ores.residual_unit(xt, tp, 1, rd_bf16)
+    (y * torch.from_numpy(dout_np)).sum().backward()
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16)
+    with emulated_ops():
+        ut = encoder_train.BottleneckUnitTrainer(p, n, G, G, torch.device("cpu"))
+        xb = bf(x_np.reshape(-1, cin))
+        acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64)
+        gn_stats(xb, n, G * G, cin, False, acc)
+        out = ut.forward(xb, acc)
+        dx = ut.backward(bf(dout_np.reshape(-1, nout)))
+        got = ut.grads_tree(p)
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    assert rel(out[: n * G * G].float().numpy().reshape(n, G, G, nout), y.detach().numpy()) < 2e-2
+    errs = {"dx": rel(dx[: n * G * G].float().numpy().reshape(n, G, G, cin), xt.grad.numpy())}
+    for k, d in tp.items():
+        for a, t in d.items():
+            errs[f"{k}/{a}"] = rel(got[k][a], t.grad.numpy())
+    print({k: round(float(v), 4) for k, v in errs.items()})
+    assert max(errs.values()) < 4e-2, errs

@@ -237,3 +237,38 @@ def test_fpn_backward_vs_autograd():
             assert rel_l2(got[k][a], t.grad.numpy()) < 3e-2, (k, a)
     for level, (x, (h, w, c)) in enumerate(zip(xs, shapes)):
         assert rel_l2(dsk[level][: n * h * w].float().cpu().numpy().reshape(n, h, w, c), x.grad.numpy()) < 3e-2, level
+
+
+@pytest.mark.parametrize("cin,nmid,nout,proj,n,G", [(64, 64, 256, True, 2, 16), (1024, 512, 2048, True, 1, 8)])
+def test_bottleneck_unit_trainer_vs_autograd(cin, nmid, nout, proj, n, G):
+    """`encoder_train.BottleneckUnitTrainer` on the GPU (projection shortcut; the wide case exercises the sliced weight
+    gradients and the 1024 / 2048-channel GroupNorm backward) vs autograd of the oracle's `residual_unit`."""
+    from oracle import resnet as ores
+    from snap_b200 import encoder_train, ops, params
+    rng = np.random.default_rng(cin + nout)
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+    p = {"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+         "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)},
+         "conv_proj": {"kernel": ln(1, 1, cin, nout)}}
+    p = params.round_to_bf16(p)
+    x_np = bf16_np(rng.standard_normal((n, G, G, cin)))
+    dout_np = bf16_np(rng.standard_normal((n, G, G, nout)) * 0.1)
+    tp = {k: {a: torch.from_numpy(v).requires_grad_(True) for a, v in d.items()} for k, d in p.items()}
+    xt = torch.from_numpy(x_np).requires_grad_(True)
+    y = ores.residual_unit(xt, tp, 1, rd_bf16)
+    (y * torch.from_numpy(dout_np)).sum().backward()
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16).cuda()
+    ut = encoder_train.BottleneckUnitTrainer(p, n, G, G, torch.device("cuda"))
+    xb = bf(x_np.reshape(-1, cin))
+    acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64, device="cuda")
+    ops.gn_stats(xb, n, G * G, cin, False, acc)
+    out = ut.forward(xb, acc)
+    dx = ut.backward(bf(dout_np.reshape(-1, nout)))
+    torch.cuda.synchronize()
+    got = ut.grads_tree(p)
+    assert rel_l2(out[: n * G * G].float().cpu().numpy().reshape(n, G, G, nout), y.detach().numpy()) < 2e-2
+    assert rel_l2(dx[: n * G * G].float().cpu().numpy().reshape(n, G, G, cin), xt.grad.numpy()) < 5e-2
+    for k, d in tp.items():
+        for a, t in d.items():
+            assert rel_l2(got[k][a], t.grad.numpy()) < 5e-2, (k, a)
