@@ -61,18 +61,46 @@ __device__ __forceinline__ void relu_open(float xh0, float xh1, __nv_bfloat162 s
   o1 = __high2float(v) > 0.f;
 }
 
+// cotangent of the (activated) GroupNorm output at pixel p of image n, channels [c0, c0 + 8): read from the dense layout
+// or from the phase-split layout of a stride-2 3x3 conv input (gn_apply's LAYOUT_PHASE: [2, 2, Nimg, H/2+1, W/2+1, C]);
+// dy_sub (optional, dense [Nimg, H/2, W/2, C]) is added at the even pixels (the stride-2 projection shortcut reads the
+// even-pixel subsample of the same activation, resnet.py:121-122)
+__device__ __forceinline__ void load_dy(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_sub,
+                                        int dy_phase, int Nimg, int H, int W, int C, int n, int p, int c0,
+                                        uint32_t (&du)[4]) {
+  const int h = p / W, w = p - h * W;
+  size_t row = (size_t)n * H * W + p;
+  if (dy_phase) {
+    const int hp = h + 1, wp = w + 1, Hq = H / 2 + 1, Wq = W / 2 + 1;
+    row = (size_t)((hp & 1) * 2 + (wp & 1)) * ((size_t)Nimg * Hq * Wq) + ((size_t)n * Hq + (hp >> 1)) * Wq + (wp >> 1);
+  }
+  const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + row * C + c0));
+  du[0] = dv.x; du[1] = dv.y; du[2] = dv.z; du[3] = dv.w;
+  if (dy_sub != nullptr && (h & 1) == 0 && (w & 1) == 0) {
+    const size_t srow = ((size_t)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(dy_sub + srow * C + c0));
+    const uint32_t su[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16(du[j]), b = unpack_bf16(su[j]);
+      du[j] = pack_bf16(a.x + b.x, a.y + b.y);
+    }
+  }
+}
+
 }  // namespace
 
 // accb [Nimg, C, 2] (double) += per-(image, channel) sums of (d, d * xhat).  grid (pixel blocks, Nimg), 256 threads:
 // thread = (pixel lane pl, channel vector cv of 8 channels).
 __global__ void __launch_bounds__(256)
-gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int HW, int C,
+gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                     const __nv_bfloat16* __restrict__ dy_sub, int dy_phase, int Nimg, int H, int W, int C,
                      const double* __restrict__ acc, int replica_stride, const float* __restrict__ scale,
                      const float* __restrict__ bias, int pre_relu, int post_relu, int pix_per_block,
                      double* __restrict__ accb) {
   const int CV = C / 8, PL = 256 / CV;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  const int n = blockIdx.y, c0 = cv * 8, cpg = C / 32;
+  const int n = blockIdx.y, c0 = cv * 8, cpg = C / 32, HW = H * W;
   __shared__ float2 s_stat[32];
   __shared__ float s_part[256][17];   // [thread][8 x (d, d*xhat)], padded against bank conflicts
   if (threadIdx.x < 32) {
@@ -101,8 +129,9 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     for (int p = p0 + pl; p < p1; p += PL) {
       const size_t off = ((size_t)n * HW + p) * C + c0;
       const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off));
-      const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + off));
-      const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+      uint32_t du[4];
+      load_dy(dy, dy_sub, dy_phase, Nimg, H, W, C, n, p, c0, du);
+      const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float2 xf = unpack_bf16(xu[j]);
@@ -140,9 +169,12 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 
 // dx = rstd * (d * scale - s1 / m - xhat * s2 / m) (+ add), written dense [Nimg*HW, C] or zero-bordered
 // [Nimg, H+2, W+2, C] (the layout the 3x3 dX GEMM and the shifted dW products read)
-template <bool PADDED>
+// OUT: 0 dense [Nimg*H*W, C]; 1 zero-bordered [Nimg, H+2, W+2, C]; 2 bottom/right zero-extended [Nimg, H+1, W+1, C] (the
+// row indexing of the stride-2 3x3 conv's output GEMM, whose A operand is the phase-split input with H/2+1 x W/2+1 planes)
+template <int OUT>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                    const __nv_bfloat16* __restrict__ dy_sub, int dy_phase, int Nimg,
                     const __nv_bfloat16* __restrict__ add, int H, int W, int C, const double* __restrict__ acc,
                     int replica_stride, const float* __restrict__ scale, const float* __restrict__ bias, int pre_relu,
                     int post_relu, const double* __restrict__ accb, int pix_per_block, __nv_bfloat16* __restrict__ dx) {
@@ -188,10 +220,11 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
   for (int p = p0 + pl; p < p1; p += PL) {
     const size_t off = ((size_t)n * HW + p) * C + c0;
     const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off));
-    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + off));
+    uint32_t du[4];
+    load_dy(dy, dy_sub, dy_phase, Nimg, H, W, C, n, p, c0, du);
     uint4 av = make_uint4(0u, 0u, 0u, 0u);
     if (add != nullptr) av = __ldg(reinterpret_cast<const uint4*>(add + off));
-    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w}, au[4] = {av.x, av.y, av.z, av.w};
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, au[4] = {av.x, av.y, av.z, av.w};
     uint32_t ov[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -213,9 +246,12 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
       ov[j] = pack_bf16(r0, r1);
     }
     size_t orow = (size_t)n * HW + p;
-    if (PADDED) {
+    if (OUT == 1) {
       const int h = p / W, w = p - h * W;
       orow = ((size_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+    } else if (OUT == 2) {
+      const int h = p / W, w = p - h * W;
+      orow = ((size_t)n * (H + 1) + h) * (W + 1) + w;
     }
     *reinterpret_cast<uint4*>(dx + orow * C + c0) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
   }
@@ -337,13 +373,16 @@ using namespace snapb200;
 
 extern "C" {
 
-int snapb200_gn_backward(const void* x, const void* dy, const void* add, int Nimg, int H, int W, int C,
-                         const double* acc, int replica_stride, const float* scale, const float* bias, int pre_relu,
-                         int post_relu, int padded_out, double* accb, void* dx, float* dscale, float* dbias, void* stream) {
+int snapb200_gn_backward(const void* x, const void* dy, const void* dy_sub, int dy_phase, const void* add, int Nimg,
+                         int H, int W, int C, const double* acc, int replica_stride, const float* scale,
+                         const float* bias, int pre_relu, int post_relu, int out_layout, double* accb, void* dx,
+                         float* dscale, float* dbias, void* stream) {
   SNAP_REQUIRE(x && dy && acc && scale && bias && accb && dx && dscale && dbias, "null pointer");
   SNAP_REQUIRE(Nimg >= 1 && H >= 1 && W >= 1, "empty problem");
   SNAP_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512 || C == 1024 || C == 2048, "C must be a power of two in [64, 2048]");
   SNAP_REQUIRE(replica_stride >= Nimg * 64, "replica_stride must cover [Nimg][32][2] doubles");
+  SNAP_REQUIRE(out_layout >= 0 && out_layout <= 2, "out_layout: 0 dense, 1 zero-bordered, 2 bottom/right extended");
+  SNAP_REQUIRE((!dy_phase && dy_sub == nullptr) || (H % 2 == 0 && W % 2 == 0), "phase / subsampled cotangents need even H, W");
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = check_cuda(cudaMemsetAsync(accb, 0, (size_t)Nimg * C * 2 * sizeof(double), s), "cudaMemsetAsync(accb)"))
     return rc;
@@ -354,17 +393,19 @@ int snapb200_gn_backward(const void* x, const void* dy, const void* add, int Nim
   int ppb = ppl * PL;
   if (ppb > HW) ppb = HW;
   dim3 grid((HW + ppb - 1) / ppb, Nimg);
-  gn_bwd_reduce_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, HW, C, acc,
-                                            replica_stride, scale, bias, pre_relu, post_relu, ppb, accb);
+  gn_bwd_reduce_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                            (const __nv_bfloat16*)dy_sub, dy_phase, Nimg, H, W, C, acc, replica_stride,
+                                            scale, bias, pre_relu, post_relu, ppb, accb);
   if (int rc = check_launch("gn_bwd_reduce_kernel")) return rc;
-  if (padded_out)
-    gn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
-                                                   (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias,
-                                                   pre_relu, post_relu, accb, ppb, (__nv_bfloat16*)dx);
-  else
-    gn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
-                                                    (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias,
-                                                    pre_relu, post_relu, accb, ppb, (__nv_bfloat16*)dx);
+#define SNAP_GN_BWD_APPLY(OUT_)                                                                                    \
+  gn_bwd_apply_kernel<OUT_><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,                \
+                                                 (const __nv_bfloat16*)dy_sub, dy_phase, Nimg,                       \
+                                                 (const __nv_bfloat16*)add, H, W, C, acc, replica_stride, scale, bias, \
+                                                 pre_relu, post_relu, accb, ppb, (__nv_bfloat16*)dx)
+  if (out_layout == 1) SNAP_GN_BWD_APPLY(1);
+  else if (out_layout == 2) SNAP_GN_BWD_APPLY(2);
+  else SNAP_GN_BWD_APPLY(0);
+#undef SNAP_GN_BWD_APPLY
   if (int rc = check_launch("gn_bwd_apply_kernel")) return rc;
   gn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, s>>>(accb, Nimg, C, dscale, dbias);
   return check_launch("gn_bwd_params_kernel");

@@ -210,3 +210,99 @@ class BottleneckUnitTrainer:
         for gname, (gs, gb) in self.ggn.items():
             out[gname] = {"scale": gs.cpu().numpy().reshape(1, 1, 1, -1).copy(), "bias": gb.cpu().numpy().reshape(1, 1, 1, -1).copy()}
         return out
+
+
+class StridedUnitTrainer(BottleneckUnitTrainer):
+    """The FIRST unit of stages 2-4 (`resnet.py:103-134` with strides=(2, 2)): the 3x3 conv and the 1x1 projection of the
+    pre-activated input subsample by two.  The forward is `EncoderPlan.run_unit`'s stride-2 branch (3x3 conv input in the
+    PHASE-SPLIT layout: four H/2+1 x W/2+1 planes of the zero-bordered tensor, nine constant-offset K-segments).  Backward:
+
+        conv2 dW   nine split-K products  a2_phase[plane(tap) + off(tap) + m]^T dc2[m]  with dc2 in the output GEMM's row
+                   indexing ([n, H/2+1, W/2+1], bottom / right zero-extended: `snapb200_gn_backward`, out_layout 2)
+        conv2 dX   one GEMM per phase plane over the taps of that parity (4 / 2 / 2 / 1 K-segments, mirrored offsets),
+                   written in the phase-split layout, which the GroupNorm backward in front reads directly (dy_phase)
+        conv_proj  dW from the even-pixel subsample a1_sub; its dX is added at the even pixels inside the GroupNorm
+                   backward of the unit's input (dy_sub)."""
+
+    def __init__(self, unit_params: Dict, n_img: int, H: int, W: int, device):
+        if "conv_proj" not in unit_params:
+            raise ValueError("a stride-2 unit always has conv_proj (resnet.py:117-122)")
+        if H % 2 or W % 2:
+            raise ValueError("stride-2 units need even H, W")
+        super().__init__(unit_params, n_img, H, W, device)
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=device)
+        bf = lambda r, c: z(r, c, dt=torch.bfloat16)
+        n, cin, nmid, nout = n_img, self.cin, self.nmid, self.nout
+        self.ho, self.wo, self.hq, self.wq = H // 2, W // 2, H // 2 + 1, W // 2 + 1
+        self.rows_out = n * self.ho * self.wo
+        self.plane = n * self.hq * self.wq
+        if self.rows_out % 16:
+            raise NotImplementedError("n * (H/2) * (W/2) must be a multiple of 16 (split-K weight-gradient kernel)")
+        Ro = image_encoder._round_up(max(self.rows_out, 128), 128)
+        self.Mp = image_encoder._round_up(self.plane, 16)
+        Rp = image_encoder._round_up(4 * self.plane + self.wq + 1 + self.Mp + 16, 128)
+        Rq = image_encoder._round_up(self.Mp + self.wq + 17, 128)
+        self.b.update(a1s=bf(Ro, cin), a2=bf(Rp, nmid), y2=bf(Ro, nmid), a3=bf(Ro, nmid), out=bf(Ro, nout), res=bf(Ro, nout),
+                      da3=bf(Ro, nmid), dc2b=bf(Rq, nmid), da2=bf(Rp, nmid), da1p=bf(Ro, cin))
+        self.btp = [bf(nmid, k * nmid) for k in (4, 2, 2, 1)]        # phase (0,0) (0,1) (1,0) (1,1): taps of that parity
+        self.taps = [(a, c) for a in range(3) for c in range(3)]
+
+    def _seg(self):
+        return [((a % 2) * 2 + (c % 2)) * self.plane + (a // 2) * self.wq + (c // 2) for a, c in self.taps]
+
+    def forward(self, x: torch.Tensor, acc_x: torch.Tensor, next_acc=None) -> torch.Tensor:
+        n, H, W, rows, Bm, b = self.n, self.H, self.W, self.rows, self.bank.b_mats, self.b
+        ho, wo, hq, wq = self.ho, self.wo, self.hq, self.wq
+        self.bank.run()
+        self.acc.zero_()
+        self.x, self.acc_x = x, acc_x
+        ops.gn_apply(x, n, H, W, self.cin, acc_x, *self.gn["gn1"], False, True, ops.LAYOUT_DENSE, b["a1"], b["a1s"])
+        ops.gemm(b["a1s"], Bm[self.w["conv_proj"]], b["res"], m_rows=self.rows_out)              # resnet.py:121-122
+        ops.gemm(b["a1"], Bm[self.w["conv1"]], b["y1"], m_rows=rows, gn_acc=self.acc[0], gn_rows_per_img=H * W)
+        ops.gn_apply(b["y1"], n, H, W, self.nmid, self.acc[0], *self.gn["gn2"], False, True, ops.LAYOUT_PHASE, b["a2"])
+        ops.gemm(b["a2"], Bm[self.w["conv2"]], b["y2"], m_rows=self.plane, seg_off=self._seg(), seg_k=self.nmid,
+                 remap=(hq, wq, 0, 0, ho, wo), gn_acc=self.acc[1], gn_rows_per_img=ho * wo)
+        ops.gn_apply(b["y2"], n, ho, wo, self.nmid, self.acc[1], *self.gn["gn3"], False, True, ops.LAYOUT_DENSE, b["a3"])
+        ops.gemm(b["a3"], Bm[self.w["conv3"]], b["out"], m_rows=self.rows_out, residual=b["res"], gn_acc=next_acc,
+                 gn_rows_per_img=ho * wo)
+        return b["out"]
+
+    def backward(self, dout: torch.Tensor) -> torch.Tensor:
+        n, H, W, rows, Bm, b = self.n, self.H, self.W, self.rows, self.bank.b_mats, self.b
+        cin, nmid, nout = self.cin, self.nmid, self.nout
+        ho, wo, wq, plane, ro, Mp = self.ho, self.wo, self.wq, self.plane, self.rows_out, self.Mp
+        # conv3 on the subsampled grid
+        self._wgrad(b["a3"], dout, ro, nmid, nout, self.gs["conv3"])
+        ops.wt_segments(Bm[self.w["conv3"]], nout, nmid, 1, self.bt["conv3"])
+        ops.gemm(dout, self.bt["conv3"], b["da3"], m_rows=ro, seg_k=nout)
+        ops.gn_backward(b["y2"], b["da3"], n, ho, wo, nmid, self.acc[1], *self.gn["gn3"], b["accb"], b["dc2b"],
+                        *self.ggn["gn3"], post_relu=True, out_layout=2)
+        # conv2 (3x3, stride 2): dW per tap, dX per phase plane
+        w2 = Bm[self.w["conv2"]]
+        slot = [0, 0, 0, 0]
+        offs = [[], [], [], []]
+        for t, (a, c) in enumerate(self.taps):
+            pl, off = (a % 2) * 2 + (c % 2), (a // 2) * wq + (c // 2)
+            ops.dense_wgrad(b["a2"][pl * plane + off: pl * plane + off + Mp], b["dc2b"][:Mp], Mp, nmid, nmid,
+                            self.gs["conv2"][t * nmid: (t + 1) * nmid], None)
+            ops.wt_segments(w2[:, t * nmid: (t + 1) * nmid], nmid, nmid, 1,
+                            self.btp[pl][:, slot[pl] * nmid: (slot[pl] + 1) * nmid])
+            slot[pl] += 1
+            offs[pl].append(-off)
+        for pl in range(4):
+            ops.gemm(b["dc2b"], self.btp[pl], b["da2"][pl * plane: (pl + 1) * plane], m_rows=plane, seg_off=offs[pl],
+                     seg_k=nmid)
+        ops.gn_backward(b["y1"], b["da2"], n, H, W, nmid, self.acc[0], *self.gn["gn2"], b["accb"], b["dc1"],
+                        *self.ggn["gn2"], post_relu=True, dy_phase=True)
+        # conv1 and the strided projection
+        self._wgrad(b["a1"], b["dc1"], rows, cin, nmid, self.gs["conv1"])
+        ops.wt_segments(Bm[self.w["conv1"]], nmid, cin, 1, self.bt["conv1"])
+        ops.gemm(b["dc1"], self.bt["conv1"], b["da1"], m_rows=rows, seg_k=nmid)
+        self._wgrad(b["a1s"], dout, ro, cin, nout, self.gs["conv_proj"])
+        ops.wt_segments(Bm[self.w["conv_proj"]], nout, cin, 1, self.bt["conv_proj"])
+        ops.gemm(dout, self.bt["conv_proj"], b["da1p"], m_rows=ro, seg_k=nout)
+        ops.gn_backward(self.x, b["da1"], n, H, W, cin, self.acc_x, *self.gn["gn1"], b["accb"], b["dx"],
+                        *self.ggn["gn1"], post_relu=True, dy_sub=b["da1p"])
+        for name in self.master:
+            ops.stdconv_backward(self.master[name], self.gs[name], self.g[name])
+        return b["dx"]

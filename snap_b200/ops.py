@@ -680,7 +680,8 @@ def sem_labels(sel_area: Sequence[Sequence[int]], sel_excl: Sequence[Sequence[in
 def gn_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: int, acc: torch.Tensor,
                 scale: torch.Tensor, bias: torch.Tensor, accb: torch.Tensor, dx: torch.Tensor, dscale: torch.Tensor,
                 dbias: torch.Tensor, *, post_relu: bool = True, padded_out: bool = False,
-                add: Optional[torch.Tensor] = None, pre_relu: bool = False) -> None:
+                add: Optional[torch.Tensor] = None, pre_relu: bool = False, out_layout: Optional[int] = None,
+                dy_phase: bool = False, dy_sub: Optional[torch.Tensor] = None) -> None:
     """GroupNorm(+ReLU) backward: x = the forward's GroupNorm input, acc = its statistics accumulators, dy = gradient
     w.r.t. the (activated) output; dx dense or zero-bordered; dscale / dbias f32 [Cc]; accb f64 scratch [n, Cc, 2]."""
     for t, nm in ((x, "x"), (dy, "dy"), (dx, "dx")):
@@ -688,8 +689,15 @@ def gn_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: i
         assert t.is_contiguous()
     _require(acc, torch.float64, "acc")
     _require(accb, torch.float64, "accb")
-    assert accb.numel() >= n * Cc * 2 and x.numel() >= n * H * W * Cc and dy.numel() >= n * H * W * Cc
-    assert dx.numel() >= n * ((H + 2) * (W + 2) if padded_out else H * W) * Cc
+    if out_layout is None:       # 0 dense, 1 zero-bordered (H+2, W+2), 2 bottom/right extended (H+1, W+1)
+        out_layout = 1 if padded_out else 0
+    opix = {0: H * W, 1: (H + 2) * (W + 2), 2: (H + 1) * (W + 1)}[out_layout]
+    dpix = 4 * (H // 2 + 1) * (W // 2 + 1) if dy_phase else H * W
+    assert accb.numel() >= n * Cc * 2 and x.numel() >= n * H * W * Cc and dy.numel() >= n * dpix * Cc
+    assert dx.numel() >= n * opix * Cc
+    if dy_sub is not None:
+        _require(dy_sub, torch.bfloat16, "dy_sub")
+        assert dy_sub.is_contiguous() and dy_sub.numel() >= n * (H // 2) * (W // 2) * Cc
     if add is not None:
         _require(add, torch.bfloat16, "add")
         assert add.is_contiguous() and add.numel() >= n * H * W * Cc
@@ -697,9 +705,9 @@ def gn_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: i
         _require(t, torch.float32, nm)
         assert t.numel() >= Cc
     _lib.check(_lib.lib().snapb200_gn_backward(
-        C.c_void_p(_ptr(x)), C.c_void_p(_ptr(dy)), C.c_void_p(_ptr(add)), n, H, W, Cc, C.c_void_p(_ptr(acc)),
-        C.c_int(acc.stride(0)), C.c_void_p(_ptr(scale)), C.c_void_p(_ptr(bias)), int(pre_relu), int(post_relu),
-        int(padded_out),
+        C.c_void_p(_ptr(x)), C.c_void_p(_ptr(dy)), C.c_void_p(_ptr(dy_sub)), int(dy_phase), C.c_void_p(_ptr(add)), n, H, W,
+        Cc, C.c_void_p(_ptr(acc)), C.c_int(acc.stride(0)), C.c_void_p(_ptr(scale)), C.c_void_p(_ptr(bias)), int(pre_relu),
+        int(post_relu), int(out_layout),
         C.c_void_p(_ptr(accb)), C.c_void_p(_ptr(dx)), C.c_void_p(_ptr(dscale)), C.c_void_p(_ptr(dbias)), _stream()))
 
 

@@ -99,21 +99,41 @@ def _padded_rows(n, H, W):
     return ((i * (H + 2) + h + 1) * (W + 2) + w + 1).reshape(-1)
 
 
+def _phase_rows(n, H, W):
+    """rows of gn_apply's LAYOUT_PHASE: [2, 2, n, H/2+1, W/2+1] planes of the zero-bordered tensor."""
+    Hq, Wq = H // 2 + 1, W // 2 + 1
+    i = torch.arange(n)[:, None, None]
+    hp = torch.arange(H)[None, :, None] + 1
+    wp = torch.arange(W)[None, None, :] + 1
+    plane = ((hp & 1) * 2 + (wp & 1)) * (n * Hq * Wq)
+    return (plane + (i * Hq + (hp >> 1)) * Wq + (wp >> 1)).reshape(-1)
+
+
 def gn_apply(x, n, H, W, Cc, acc, scale, bias, pre_relu, post_relu, layout, out, out_sub=None):
-    assert out_sub is None and layout in (ops.LAYOUT_DENSE, ops.LAYOUT_PADDED)
     xh, _ = _xhat(x, n, H * W, Cc, acc, pre_relu)
     y = _gn_forward(xh, scale, bias, post_relu).reshape(n * H * W, Cc).to(out.dtype)
     if layout == ops.LAYOUT_DENSE:
         out[: n * H * W, :Cc] = y
-    else:
+    elif layout == ops.LAYOUT_PADDED:
         out[_padded_rows(n, H, W), :Cc] = y
+    else:
+        out[_phase_rows(n, H, W), :Cc] = y
+    if out_sub is not None:                              # even-pixel subsample, dense [n, H/2, W/2, C]
+        out_sub[: n * (H // 2) * (W // 2), :Cc] = y.reshape(n, H, W, Cc)[:, ::2, ::2].reshape(-1, Cc)
 
 
 def gn_backward(x, dy, n, H, W, Cc, acc, scale, bias, accb, dx, dscale, dbias, *, post_relu=True, padded_out=False,
-                add=None, pre_relu=False):
+                add=None, pre_relu=False, out_layout=None, dy_phase=False, dy_sub=None):
     hw = H * W
     xh, rstd = _xhat(x, n, hw, Cc, acc, pre_relu)
-    d = dy[: n * hw, :Cc].float().reshape(n, hw, Cc)
+    if dy_phase:
+        d = dy.reshape(-1, Cc)[_phase_rows(n, H, W)].float().reshape(n, hw, Cc)
+    else:
+        d = dy[: n * hw, :Cc].float().reshape(n, hw, Cc)
+    if dy_sub is not None:
+        d = d.reshape(n, H, W, Cc).clone()
+        d[:, ::2, ::2] = _rd(d[:, ::2, ::2] + dy_sub[: n * (H // 2) * (W // 2), :Cc].float().reshape(n, H // 2, W // 2, Cc))
+        d = d.reshape(n, hw, Cc)
     if post_relu:
         d = d * (_gn_forward(xh, scale, bias, False) > 0).float()
     sc = _rd(scale.float())[:Cc]
@@ -130,8 +150,13 @@ def gn_backward(x, dy, n, H, W, Cc, acc, scale, bias, accb, dx, dscale, dbias, *
     if add is not None:
         r = r + add[: n * hw, :Cc].float().reshape(n, hw, Cc)
     r = r.reshape(n * hw, Cc).to(dx.dtype)
-    if padded_out:
+    if out_layout is None:
+        out_layout = 1 if padded_out else 0
+    if out_layout == 1:
         dx.view(-1, Cc)[_padded_rows(n, H, W)] = r
+    elif out_layout == 2:                                # bottom / right extended [n, H+1, W+1]
+        i, h, w = torch.arange(n)[:, None, None], torch.arange(H)[None, :, None], torch.arange(W)[None, None, :]
+        dx.view(-1, Cc)[((i * (H + 1) + h) * (W + 1) + w).reshape(-1)] = r
     else:
         dx.view(-1, Cc)[: n * hw] = r
 

@@ -272,3 +272,38 @@ def test_bottleneck_unit_trainer_vs_autograd(cin, nmid, nout, proj, n, G):
     for k, d in tp.items():
         for a, t in d.items():
             assert rel_l2(got[k][a], t.grad.numpy()) < 5e-2, (k, a)
+
+
+@pytest.mark.parametrize("cin,nmid,nout,n,G", [(256, 128, 512, 2, 32), (1024, 512, 2048, 1, 16)])
+def test_strided_unit_trainer_vs_autograd(cin, nmid, nout, n, G):
+    """`encoder_train.StridedUnitTrainer` on the GPU (phase-split 3x3 stride-2 backward, strided projection) vs autograd of
+    the oracle's `residual_unit(stride=2)`; the launch plan is CPU-verified in tests/test_fpn_backward_plan_cpu.py."""
+    from oracle import resnet as ores
+    from snap_b200 import encoder_train, ops, params
+    rng = np.random.default_rng(cin + nout + 1)
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+    p = params.round_to_bf16({"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+                              "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)},
+                              "conv_proj": {"kernel": ln(1, 1, cin, nout)}})
+    x_np = bf16_np(rng.standard_normal((n, G, G, cin)))
+    dout_np = bf16_np(rng.standard_normal((n, G // 2, G // 2, nout)) * 0.1)
+    tp = {k: {a: torch.from_numpy(v).requires_grad_(True) for a, v in d.items()} for k, d in p.items()}
+    xt = torch.from_numpy(x_np).requires_grad_(True)
+    y = ores.residual_unit(xt, tp, 2, rd_bf16)
+    (y * torch.from_numpy(dout_np)).sum().backward()
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16).cuda()
+    ut = encoder_train.StridedUnitTrainer(p, n, G, G, torch.device("cuda"))
+    xb = bf(x_np.reshape(-1, cin))
+    acc = torch.zeros((ops.GN_REPLICAS, n, 32, 2), dtype=torch.float64, device="cuda")
+    ops.gn_stats(xb, n, G * G, cin, False, acc)
+    out = ut.forward(xb, acc)
+    dx = ut.backward(bf(dout_np.reshape(-1, nout)))
+    torch.cuda.synchronize()
+    got = ut.grads_tree(p)
+    ro = n * (G // 2) ** 2
+    assert rel_l2(out[:ro].float().cpu().numpy().reshape(y.shape), y.detach().numpy()) < 2e-2
+    assert rel_l2(dx[: n * G * G].float().cpu().numpy().reshape(n, G, G, cin), xt.grad.numpy()) < 5e-2
+    for k, d in tp.items():
+        for a, t in d.items():
+            assert rel_l2(got[k][a], t.grad.numpy()) < 5e-2, (k, a)
