@@ -125,7 +125,7 @@ EXPORTED_SYMBOLS += [
     "snapb200_argmax_rows", "snapb200_loc_nll", "snapb200_sem_loss",
     "snapb200_sem_loss_grad", "snapb200_relu_bwd", "snapb200_dense_wgrad_workspace", "snapb200_dense_wgrad",
     "snapb200_adam_step", "snapb200_cast_pad_bf16", "snapb200_sem_labels",
-    "snapb200_gn_backward", "snapb200_upsample2x_backward", "snapb200_wt_segments", "snapb200_stdconv_backward",
+    "snapb200_gn_backward", "snapb200_upsample2x_backward", "snapb200_maxpool3x3s2_backward", "snapb200_wt_segments", "snapb200_stdconv_backward",
     "snapb200_lift_gather_pool_backward", "snapb200_lift_select_pool_backward", "snapb200_vertical_max_backward",
     "snapb200_match_head_backward", "snapb200_fuse_max_backward",
     "snapb200_loc_nll_backward", "snapb200_loc_pose_scoring_backward",

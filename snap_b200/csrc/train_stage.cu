@@ -367,6 +367,58 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
       make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
 }
 
+// Backward of the 3x3 / stride-2 / pad-1 max pool of the root block (resnet.py:99): dx[n, h, w, :] = sum of dy over the
+// (at most 2 x 2) windows that contain the pixel AND whose first maximum (row-major scan, strict >) it is.  A gather: one
+// thread per (input pixel, 8 channels) re-derives the arg-max of each candidate window, so the result is deterministic.
+__global__ void maxpool3x3s2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int Nimg,
+                                        int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+  const int cv = C / 8;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)Nimg * H * W * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv);
+  const long long pix = idx / cv;
+  const int w = (int)(pix % W);
+  const int h = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const __nv_bfloat16* xb = x + (size_t)n * H * W * C + c8 * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // window ho covers input rows 2ho-1 .. 2ho+1, so row h lies in the windows ho = h/2 .. (h+1)/2 (likewise for columns)
+  for (int ho = h / 2; ho <= min((h + 1) / 2, Ho - 1); ++ho) {
+    for (int wo = w / 2; wo <= min((w + 1) / 2, Wo - 1); ++wo) {
+      float best[8];
+      int bh[8], bw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        best[j] = -INFINITY;
+        bh[j] = bw[j] = -1;
+      }
+      for (int hi = max(2 * ho - 1, 0); hi <= min(2 * ho + 1, H - 1); ++hi)
+        for (int wi = max(2 * wo - 1, 0); wi <= min(2 * wo + 1, W - 1); ++wi) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)hi * W + wi) * C));
+          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 t = unpack_bf16(uu[j]);
+            if (t.x > best[2 * j]) { best[2 * j] = t.x; bh[2 * j] = hi; bw[2 * j] = wi; }
+            if (t.y > best[2 * j + 1]) { best[2 * j + 1] = t.y; bh[2 * j + 1] = hi; bw[2 * j + 1] = wi; }
+          }
+        }
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + (((size_t)n * Ho + ho) * Wo + wo) * C + c8 * 8));
+      const uint32_t gu[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16(gu[j]);
+        if (bh[2 * j] == h && bw[2 * j] == w) acc[2 * j] += t.x;
+        if (bh[2 * j + 1] == h && bw[2 * j + 1] == w) acc[2 * j + 1] += t.y;
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + pix * C + c8 * 8) =
+      make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+}
+
 }  // namespace snapb200
 
 using namespace snapb200;
@@ -417,6 +469,14 @@ int snapb200_upsample2x_backward(const void* dy, int Nimg, int h, int w, int C, 
   upsample2x_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, Nimg, h, w, C, (__nv_bfloat16*)dx);
   return check_launch("upsample2x_bwd_kernel");
+}
+
+int snapb200_maxpool3x3s2_backward(const void* x, const void* dy, int Nimg, int H, int W, int C, void* dx, void* stream) {
+  SNAP_REQUIRE(x && dy && dx && Nimg >= 1 && H >= 1 && W >= 1 && C % 8 == 0, "bad arguments");
+  const long long total = (long long)Nimg * H * W * (C / 8);
+  maxpool3x3s2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, Nimg, H, W, C, (__nv_bfloat16*)dx);
+  return check_launch("maxpool3x3s2_bwd_kernel");
 }
 
 int snapb200_wt_segments(const void* in, int ld_in, int Cout, int Cin, int taps, void* out, int ld_out, void* stream) {

@@ -45,9 +45,24 @@ class FPNBackward:
                                 wk=bank.add(decoder_params[f"{level}_skip_conv"]["kernel"], False),
                                 a=z(R, c, dt=torch.bfloat16), da=z(R, c, dt=torch.bfloat16), dx=z(R, c, dt=torch.bfloat16),
                                 bt=z(c, out_dim, dt=torch.bfloat16), dup=z(R, out_dim, dt=torch.bfloat16),
+                                out=z(R, out_dim, dt=torch.bfloat16), up=z(R, out_dim, dt=torch.bfloat16),
                                 accb=z(n_img, c, 2, dt=torch.float64),
                                 g=dict(kernel=z(c, out_dim), scale=z(c), bias=z(c))))
         bank.finalize()
+
+    def forward(self, skips: List[torch.Tensor], accs: List[torch.Tensor]) -> torch.Tensor:
+        """The FPN forward on this object's buffers (`EncoderPlan.run_fpn`); returns the finest level bf16 [n*h*w, out_dim]."""
+        n, od, Bm = self.n, self.od, self.bank.b_mats
+        self.bank.run()
+        prev = None
+        for level, L in enumerate(self.lv):
+            ops.gn_apply(skips[level], n, L["h"], L["w"], L["c"], accs[level], L["scale"], L["bias"], True, False,
+                         ops.LAYOUT_DENSE, L["a"])
+            if prev is not None:
+                ops.upsample2x(prev["out"], n, prev["h"], prev["w"], od, L["up"])
+            ops.gemm(L["a"], Bm[L["wk"]], L["out"], m_rows=L["rows"], residual=L["up"] if prev is not None else None)
+            prev = L
+        return prev["out"]
 
     def backward(self, skips: List[torch.Tensor], accs: List[torch.Tensor], dout_finest: torch.Tensor) -> List[torch.Tensor]:
         """skips[level] bf16 [n*h*w, c] (coarse -> fine) = the FPN inputs; accs[level] = the f64 GroupNorm accumulators of
@@ -267,7 +282,9 @@ class StridedUnitTrainer(BottleneckUnitTrainer):
                  gn_rows_per_img=ho * wo)
         return b["out"]
 
-    def backward(self, dout: torch.Tensor) -> torch.Tensor:
+    def backward(self, dout: torch.Tensor, add: torch.Tensor = None) -> torch.Tensor:
+        """`add` (bf16 dense [n*H*W, cin], optional): a second cotangent of the unit's input, e.g. the FPN's cotangent of the
+        previous stage's output, folded into the last GroupNorm backward."""
         n, H, W, rows, Bm, b = self.n, self.H, self.W, self.rows, self.bank.b_mats, self.b
         cin, nmid, nout = self.cin, self.nmid, self.nout
         ho, wo, wq, plane, ro, Mp = self.ho, self.wo, self.wq, self.plane, self.rows_out, self.Mp
@@ -302,7 +319,103 @@ class StridedUnitTrainer(BottleneckUnitTrainer):
         ops.wt_segments(Bm[self.w["conv_proj"]], nout, cin, 1, self.bt["conv_proj"])
         ops.gemm(dout, self.bt["conv_proj"], b["da1p"], m_rows=ro, seg_k=nout)
         ops.gn_backward(self.x, b["da1"], n, H, W, cin, self.acc_x, *self.gn["gn1"], b["accb"], b["dx"],
-                        *self.ggn["gn1"], post_relu=True, dy_sub=b["da1p"])
+                        *self.ggn["gn1"], post_relu=True, dy_sub=b["da1p"], add=add)
         for name in self.master:
             ops.stdconv_backward(self.master[name], self.gs[name], self.g[name])
         return b["dx"]
+
+
+class TrunkTrainer:
+    """Training forward + backward of the whole image encoder (`resnet.py:184-216` + `image_encoder.py:53-94`) for an input
+    whose sides are already multiples of the maximum stride: root block (7x7 / 2 StdConv as im2col GEMM, 3x3 / 2 max pool),
+    the four stages of bottleneck units (`BottleneckUnitTrainer` / `StridedUnitTrainer`) and the FPN (`FPNBackward`).  The
+    stage outputs feed both the next stage and the FPN: the FPN's cotangent is folded into the next stage's first GroupNorm
+    backward (`add`).  The first convolution needs no dX (the image is data): its weight gradient is one split-K product
+    with the im2col matrix."""
+
+    def __init__(self, enc_params: Dict, n_img: int, H: int, W: int, device, out_dim: int = 128):
+        if H % 32 or W % 32:
+            raise ValueError("H, W must be multiples of 32 (pad_to_multiple, image_encoder.py:32-39, is the caller's job)")
+        pe, pd = enc_params["encoder"], enc_params["decoder"]
+        self.n, self.H, self.W, self.dev = n_img, H, W, device
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=device)
+        bf = lambda r, c: z(r, c, dt=torch.bfloat16)
+        kroot = np.ascontiguousarray(pe["root_block"]["conv_root"]["kernel"], dtype=F)
+        self.root_shape, self.c0 = kroot.shape, kroot.shape[-1]
+        self.bank = image_encoder._WeightBank(device)
+        self.root_w = self.bank.add(kroot, True, 32)
+        self.bank.finalize()
+        self.K0 = int(np.prod(kroot.shape[:3]))
+        self.Kp = image_encoder._round_up(self.K0, 32)
+        self.root_master = self.bank.master[: self.K0 * self.c0].view(self.K0, self.c0)
+        h1, w1 = H // 2, W // 2
+        h, w = h1 // 2, w1 // 2
+        self.rows0, self.hw_root, self.hw0 = n_img * h1 * w1, (h1, w1), (h, w)
+        R0 = image_encoder._round_up(max(self.rows0, 128), 128)
+        self.A = bf(R0, self.Kp)
+        self.y_root, self.dy_root = bf(R0, self.c0), bf(R0, self.c0)
+        self.x0 = bf(image_encoder._round_up(max(n_img * h * w, 128), 128), self.c0)
+        self.g_root_s, self.g_root = z(self.Kp, self.c0), z(self.K0, self.c0)
+        self.units, shapes = [], []
+        i = 1
+        while f"block{i}" in pe:
+            names = sorted(k for k in pe[f"block{i}"] if k.startswith("unit"))
+            for j, name in enumerate(names):
+                pu = pe[f"block{i}"][name]
+                if j == 0 and i > 1:
+                    u = StridedUnitTrainer(pu, n_img, h, w, device)
+                    h, w = h // 2, w // 2
+                else:
+                    u = BottleneckUnitTrainer(pu, n_img, h, w, device)
+                self.units.append(dict(t=u, path=(f"block{i}", name), params=pu, last=(j == len(names) - 1), hw=(h, w)))
+            shapes.append((h, w, self.units[-1]["t"].nout))
+            i += 1
+        self.acc_in = [z(ops.GN_REPLICAS, n_img, 32, 2, dt=torch.float64) for _ in self.units]
+        self.acc_fpn = [z(ops.GN_REPLICAS, n_img, 32, 2, dt=torch.float64) for _ in shapes]
+        self.fpn = FPNBackward(pd, n_img, shapes[::-1], device, out_dim)        # coarse -> fine
+        self.dec_params = pd
+
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """images f32 [n, H, W, 3] in [0, 1] -> finest FPN level bf16 [n * H/4 * W/4, out_dim]."""
+        n = self.n
+        kh, kw = self.root_shape[:2]
+        self.bank.run()
+        ops.root_im2col(images, self.H, self.W, kh, kw, 2, 3, self.A)
+        ops.gemm(self.A, self.bank.b_mats[self.root_w], self.y_root, m_rows=self.rows0, seg_k=self.Kp)
+        ops.maxpool3x3s2(self.y_root, n, self.hw_root[0], self.hw_root[1], self.c0, self.x0)
+        for a in self.acc_in + self.acc_fpn:
+            a.zero_()
+        ops.gn_stats(self.x0, n, self.hw0[0] * self.hw0[1], self.c0, False, self.acc_in[0])
+        x, skips = self.x0, []
+        for k, u in enumerate(self.units):
+            nxt = self.acc_in[k + 1] if k + 1 < len(self.units) else None
+            x = u["t"].forward(x, self.acc_in[k], nxt)
+            if u["last"]:
+                ops.gn_stats(x, n, u["hw"][0] * u["hw"][1], u["t"].nout, True, self.acc_fpn[len(skips)])
+                skips.append(x)
+        self.skips = skips[::-1]                                                  # coarse -> fine
+        self.accs = self.acc_fpn[: len(skips)][::-1]
+        return self.fpn.forward(self.skips, self.accs)
+
+    def backward(self, dout_finest: torch.Tensor) -> None:
+        n = self.n
+        dsk = self.fpn.backward(self.skips, self.accs, dout_finest)[::-1]         # per stage, fine (stage 1) -> coarse
+        stage = len(dsk) - 1
+        dout = dsk[stage]
+        for u in reversed(self.units):
+            t = u["t"]
+            if isinstance(t, StridedUnitTrainer):
+                stage -= 1
+                dout = t.backward(dout, add=dsk[stage])                           # + the FPN's cotangent of the stage output
+            else:
+                dout = t.backward(dout)
+        # root block: max pool, then the weight gradient of the first convolution
+        ops.maxpool3x3s2_backward(self.y_root, dout, n, self.hw_root[0], self.hw_root[1], self.c0, self.dy_root)
+        ops.dense_wgrad(self.A, self.dy_root, self.rows0, self.Kp, self.c0, self.g_root_s, None)
+        ops.stdconv_backward(self.root_master, self.g_root_s[: self.K0], self.g_root)
+
+    def grads_tree(self) -> Dict:
+        enc: Dict = {"root_block": {"conv_root": {"kernel": self.g_root.cpu().numpy().reshape(self.root_shape).copy()}}}
+        for u in self.units:
+            enc.setdefault(u["path"][0], {})[u["path"][1]] = u["t"].grads_tree(u["params"])
+        return {"encoder": enc, "decoder": self.fpn.grads_tree()}

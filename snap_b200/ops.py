@@ -845,3 +845,14 @@ def upsample2x_backward(dy: torch.Tensor, n: int, h: int, w: int, Cc: int, dx: t
     _require(dx, torch.bfloat16, "dx")
     assert dy.is_contiguous() and dx.is_contiguous() and dy.numel() >= 4 * n * h * w * Cc and dx.numel() >= n * h * w * Cc
     _lib.check(_lib.lib().snapb200_upsample2x_backward(C.c_void_p(_ptr(dy)), n, h, w, Cc, C.c_void_p(_ptr(dx)), _stream()))
+
+
+def maxpool3x3s2_backward(x: torch.Tensor, dy: torch.Tensor, n: int, H: int, W: int, Cc: int, dx: torch.Tensor) -> None:
+    """x bf16 [n, H, W, Cc] (the pool's input), dy bf16 [n, (H-1)//2+1, (W-1)//2+1, Cc] -> dx bf16 [n, H, W, Cc]."""
+    for t, nm in ((x, "x"), (dy, "dy"), (dx, "dx")):
+        _require(t, torch.bfloat16, nm)
+        assert t.is_contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    assert x.numel() >= n * H * W * Cc and dx.numel() >= n * H * W * Cc and dy.numel() >= n * Ho * Wo * Cc
+    _lib.check(_lib.lib().snapb200_maxpool3x3s2_backward(C.c_void_p(_ptr(x)), C.c_void_p(_ptr(dy)), n, H, W, Cc,
+                                                         C.c_void_p(_ptr(dx)), _stream()))

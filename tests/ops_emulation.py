@@ -249,7 +249,7 @@ def emulated_ops(extra=None):
     names = ("gemm", "gn_stats", "gn_apply", "gn_backward", "dense_wgrad", "cast_pad_bf16", "relu_bwd", "wt_segments",
              "stdconv_backward", "vertical_max_backward", "match_head_backward", "fuse_max_backward",
              "loc_nll_backward", "loc_pose_scoring_backward", "sem_labels", "sem_loss", "sem_loss_grad", "adam_step",
-             "upsample2x", "upsample2x_backward")
+             "upsample2x", "upsample2x_backward", "root_im2col", "maxpool3x3s2", "maxpool3x3s2_backward")
     table = {n: globals()[n] for n in names}
     table.update(extra or {})
     names = tuple(table)
@@ -374,3 +374,31 @@ def upsample2x_backward(dy, n, h, w, Cc, dx):
     g = dy.reshape(-1)[: 4 * n * h * w * Cc].float().reshape(n, 2 * h, 2 * w, Cc).permute(0, 3, 1, 2)
     (up * g).sum().backward()
     dx.reshape(-1)[: n * h * w * Cc] = v.grad.permute(0, 2, 3, 1).reshape(-1).to(dx.dtype)
+
+
+def root_im2col(images, Hp, Wp, KH, KW, stride, pad, out):
+    """bf16 [n*Ho*Wo, Kp]: windows of 2 * bf16(image) - 1 (resnet.py:199; -1 in pad_to_multiple's zero padding, 0 in the
+    convolution's own padding), K ordered (kh, kw, c) like the Flax HWIO kernel."""
+    n, H, W, _ = images.shape
+    x = torch.full((n, Hp, Wp, 3), -1.0)
+    x[:, :H, :W] = _rd(_rd(images.float()) * 2 - 1)
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pad, pad, pad, pad))
+    Ho, Wo = (Hp + 2 * pad - KH) // stride + 1, (Wp + 2 * pad - KW) // stride + 1
+    cols = torch.nn.functional.unfold(xp, (KH, KW), stride=stride)              # [n, 3*KH*KW (c, kh, kw), Ho*Wo]
+    cols = cols.reshape(n, 3, KH, KW, Ho * Wo).permute(0, 4, 2, 3, 1).reshape(n * Ho * Wo, KH * KW * 3)
+    out[: n * Ho * Wo].zero_()
+    out[: n * Ho * Wo, : KH * KW * 3] = cols.to(out.dtype)
+
+
+def maxpool3x3s2(x, n, H, W, Cc, y):
+    v = x.reshape(-1)[: n * H * W * Cc].float().reshape(n, H, W, Cc).permute(0, 3, 1, 2)
+    o = torch.nn.functional.max_pool2d(v, 3, stride=2, padding=1).permute(0, 2, 3, 1)
+    y.reshape(-1)[: o.numel()] = o.reshape(-1).to(y.dtype)
+
+
+def maxpool3x3s2_backward(x, dy, n, H, W, Cc, dx):
+    v = x.reshape(-1)[: n * H * W * Cc].float().reshape(n, H, W, Cc).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    o = torch.nn.functional.max_pool2d(v, 3, stride=2, padding=1)
+    g = dy.reshape(-1)[: o.numel()].float().reshape(n, o.shape[2], o.shape[3], Cc).permute(0, 3, 1, 2)
+    (o * g).sum().backward()
+    dx.reshape(-1)[: n * H * W * Cc] = v.grad.permute(0, 2, 3, 1).reshape(-1).to(dx.dtype)

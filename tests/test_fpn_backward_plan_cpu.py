@@ -131,3 +131,105 @@ def test_strided_unit_backward_plan_matches_autograd(cin, nmid, nout, n, G):
             errs[f"{k}/{a}"] = rel(got[k][a], t.grad.numpy())
     print({k: round(float(v), 4) for k, v in errs.items()})
     assert max(errs.values()) < 4e-2, errs
+
+
+def test_whole_encoder_backward_plan_matches_autograd():
+    """`encoder_train.TrunkTrainer`: root block -> stage 1 (projection unit + identity unit) -> three strided stages -> FPN,
+    forward and backward on the emulated operator layer vs ONE autograd graph of the oracle's `resnet_v2` + `fpn_decoder`
+    (resnet.py:184-216, image_encoder.py:53-94) -- every kernel / GroupNorm array of the encoder, from a cotangent on the
+    finest FPN level (what the lift hands back)."""
+    from oracle import image_encoder as oie, resnet as ores
+    from snap_b200 import encoder_train, params
+    rng = np.random.default_rng(77)
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+
+    def unit(cin, nmid, nout, proj):
+        u = {"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+             "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)}}
+        if proj:
+            u["conv_proj"] = {"kernel": ln(1, 1, cin, nout)}
+        return u
+    enc = {"root_block": {"conv_root": {"kernel": ln(7, 7, 3, 64)}},
+           "block1": {"unit01": unit(64, 64, 256, True), "unit02": unit(256, 64, 256, False)},
+           "block2": {"unit01": unit(256, 128, 512, True)}, "block3": {"unit01": unit(512, 256, 1024, True)},
+           "block4": {"unit01": unit(1024, 512, 2048, True)}}
+    dec = {}
+    for level, c in enumerate((2048, 1024, 512, 256)):
+        dec[f"{level}_skip_norm"] = gnp(c)
+        dec[f"{level}_skip_conv"] = {"kernel": ln(1, 1, c, 128)}
+    p = params.round_to_bf16({"encoder": enc, "decoder": dec})
+    n, H = 1, 128
+    img = rng.random((n, H, H, 3)).astype(F)
+    dfin = bf16_np(rng.standard_normal((n, H // 4, H // 4, 128)) * 0.05)
+    # reference
+    tt = lambda t, g: {k: (tt(v, g) if isinstance(v, dict) else torch.from_numpy(v).requires_grad_(g)) for k, v in t.items()}
+    tp = tt(p, True)
+    stages = ores.resnet_v2(torch.from_numpy(img), tp["encoder"], False, rd_bf16)
+    outs = oie.fpn_decoder(stages[::-1], tp["decoder"], rd_bf16)
+    for st in stages:
+        st.retain_grad()
+    (outs[-1] * torch.from_numpy(dfin)).sum().backward()
+    # the same reference with fp32 summation-order-sized noise in front of every bf16 rounding: how far do the oracle's OWN
+    # gradients move?  (the yardstick for the comparison below)
+    gen = torch.Generator().manual_seed(0)
+    rd_noisy = lambda t: rd_bf16(t * (1 + 3e-7 * torch.randn(t.shape, generator=gen)))
+    tp2 = tt(p, True)
+    st2 = ores.resnet_v2(torch.from_numpy(img), tp2["encoder"], False, rd_noisy)
+    (oie.fpn_decoder(st2[::-1], tp2["decoder"], rd_noisy)[-1] * torch.from_numpy(dfin)).sum().backward()
+    # plan
+    with emulated_ops():
+        tr = encoder_train.TrunkTrainer(p, n, H, H, torch.device("cpu"))
+        fin = tr.forward(torch.from_numpy(img))
+        tr.backward(torch.from_numpy(dfin.reshape(-1, 128)).to(torch.bfloat16))
+        got = tr.grads_tree()
+        dbg_skips = [t.float().numpy().copy() for t in tr.skips]
+        dbg_dsk = [L["dx"].float().numpy().copy() for L in tr.fpn.lv]
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    fwd_stage = []
+    for lvl, st in enumerate(stages[::-1]):       # coarse -> fine
+        r = st.shape[0] * st.shape[1] * st.shape[2]
+        fwd_stage.append(round(float(rel(dbg_skips[lvl][:r].reshape(st.shape), st.detach().numpy())), 4))
+    e_dx4 = rel(dbg_dsk[0][: stages[-1][..., 0].numel()].reshape(stages[-1].shape), stages[-1].grad.numpy())
+    print("stage outputs (coarse -> fine), forward rel err:", fwd_stage, "| FPN cotangent of the stage-4 output:", round(float(e_dx4), 4))
+    rows = n * (H // 4) ** 2
+    e_fwd = rel(fin[:rows].float().numpy().reshape(outs[-1].shape), outs[-1].detach().numpy())
+    errs, cosines = {}, {}
+
+    def walk(gt, rt, pre):
+        for k, v in rt.items():
+            if isinstance(v, dict):
+                walk(gt[k], v, pre + (k,))
+            else:
+                assert float(v.grad.norm()) > 0, pre + (k,)
+                errs["/".join(pre + (k,))] = rel(gt[k], v.grad.numpy())
+                g, r = gt[k].reshape(-1).astype(np.float64), v.grad.numpy().reshape(-1).astype(np.float64)
+                cosines["/".join(pre + (k,))] = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+    walk(got, tp, ())
+    self_err = {}
+
+    def walk2(a, b_, pre):
+        for k, v in a.items():
+            if isinstance(v, dict):
+                walk2(v, b_[k], pre + (k,))
+            else:
+                self_err["/".join(pre + (k,))] = rel(b_[k].grad.numpy(), v.grad.numpy())
+    walk2(tp, tp2, ())
+    trunk = [k for k in errs if k.startswith("encoder/")]
+    print("oracle vs noisy oracle, trunk arrays: median rel", round(float(np.median([self_err[k] for k in trunk])), 4),
+          "max", round(float(max(self_err[k] for k in trunk)), 4), "| plan vs oracle: median",
+          round(float(np.median([errs[k] for k in trunk])), 4), "max", round(float(max(errs[k] for k in trunk)), 4))
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print(f"forward rel err {e_fwd:.4f}; {len(errs)} parameter arrays, worst: {[(k, round(float(v), 4)) for k, v in worst]}")
+    assert e_fwd < 3e-2
+    # The free-running bf16 trunk is chaotic (DESIGN.md 4): fp32 summation-order noise flips bf16 roundings, GroupNorm
+    # amplifies them (stage outputs differ by 0.1 % ... 1.3 % from the oracle's, see the print), and a 1 % difference of a
+    # pre-activation flips ~1 % of the ReLU / max-pool selections, i.e. ~10 % relative L2 of a cotangent -- for the oracle's
+    # own bf16-vs-fp32 modes just the same.  The tight checks of the arithmetic are the per-unit / FPN tests above (<= 0.6 %,
+    # teacher-forced); here the wiring is checked: every array's gradient points the same way and has the right size.
+    # yardstick: the oracle's own gradients move by MORE than that (median 28 %, max 36 % here) when noise of the size of an
+    # fp32 summation-order difference (3e-7 relative) is put in front of its bf16 roundings
+    assert max(errs[k] for k in trunk) < 1.5 * max(self_err[k] for k in trunk) + 2e-2
+    assert min(cosines.values()) > 0.97, sorted(cosines.items(), key=lambda kv: kv[1])[:4]
+    assert max(errs.values()) < 0.3, worst
+    assert errs["decoder/3_skip_conv/kernel"] < 2e-2 and errs["decoder/3_skip_norm/bias"] < 2e-2     # above the chaos

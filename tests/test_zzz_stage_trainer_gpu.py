@@ -307,3 +307,74 @@ def test_strided_unit_trainer_vs_autograd(cin, nmid, nout, n, G):
     for k, d in tp.items():
         for a, t in d.items():
             assert rel_l2(got[k][a], t.grad.numpy()) < 5e-2, (k, a)
+
+
+def test_maxpool_backward_vs_emulation():
+    import ops_emulation as emu
+    from snap_b200 import ops
+    rng = np.random.default_rng(15)
+    n, H, W, C = 2, 14, 18, 64
+    x = torch.from_numpy(bf16_np(np.round(rng.standard_normal((n, H, W, C)) * 4) / 4)).to(torch.bfloat16)   # ties inside windows
+    dy = torch.from_numpy(bf16_np(rng.standard_normal((n, H // 2, W // 2, C)))).to(torch.bfloat16)
+    dx = torch.full((n, H, W, C), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.maxpool3x3s2_backward(x.cuda(), dy.cuda(), n, H, W, C, dx)
+    ref = torch.zeros((n, H, W, C), dtype=torch.bfloat16)
+    emu.maxpool3x3s2_backward(x, dy, n, H, W, C, ref)                      # torch: the first maximum of a window takes it
+    assert rel_l2(dx.float().cpu().numpy(), ref.float().numpy()) < 5e-3
+    y = torch.zeros((n, H // 2, W // 2, C), dtype=torch.bfloat16, device="cuda")
+    ops.maxpool3x3s2(x.cuda(), n, H, W, C, y)
+    assert abs(float((y.float() * dy.cuda().float()).sum()) - float((x.cuda().float() * dx.float()).sum())) < 1e-1 * n * C
+
+
+def test_trunk_trainer_vs_autograd():
+    """`encoder_train.TrunkTrainer` (root block, 5 bottleneck units over 4 stages, FPN) on the GPU vs autograd of the
+    oracle's resnet_v2 + fpn_decoder.  The free-running bf16 trunk is chaotic (see tests/test_fpn_backward_plan_cpu.py:
+    the oracle's own gradients move by ~30 % under summation-order-sized noise), so the bound is directional."""
+    from oracle import image_encoder as oie, resnet as ores
+    from snap_b200 import encoder_train, params
+    rng = np.random.default_rng(77)
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+
+    def unit(cin, nmid, nout, proj):
+        u = {"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+             "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)}}
+        if proj:
+            u["conv_proj"] = {"kernel": ln(1, 1, cin, nout)}
+        return u
+    enc = {"root_block": {"conv_root": {"kernel": ln(7, 7, 3, 64)}},
+           "block1": {"unit01": unit(64, 64, 256, True), "unit02": unit(256, 64, 256, False)},
+           "block2": {"unit01": unit(256, 128, 512, True)}, "block3": {"unit01": unit(512, 256, 1024, True)},
+           "block4": {"unit01": unit(1024, 512, 2048, True)}}
+    dec = {}
+    for level, c in enumerate((2048, 1024, 512, 256)):
+        dec[f"{level}_skip_norm"] = gnp(c)
+        dec[f"{level}_skip_conv"] = {"kernel": ln(1, 1, c, 128)}
+    p = params.round_to_bf16({"encoder": enc, "decoder": dec})
+    n, H = 1, 128
+    img = rng.random((n, H, H, 3)).astype(F)
+    dfin = bf16_np(rng.standard_normal((n, H // 4, H // 4, 128)) * 0.05)
+    tt = lambda t: {k: (tt(v) if isinstance(v, dict) else torch.from_numpy(v).requires_grad_(True)) for k, v in t.items()}
+    tp = tt(p)
+    stages = ores.resnet_v2(torch.from_numpy(img), tp["encoder"], False, rd_bf16)
+    outs = oie.fpn_decoder(stages[::-1], tp["decoder"], rd_bf16)
+    (outs[-1] * torch.from_numpy(dfin)).sum().backward()
+    tr = encoder_train.TrunkTrainer(p, n, H, H, torch.device("cuda"))
+    fin = tr.forward(torch.from_numpy(img).cuda())
+    tr.backward(torch.from_numpy(dfin.reshape(-1, 128)).to(torch.bfloat16).cuda())
+    torch.cuda.synchronize()
+    got = tr.grads_tree()
+    rows = n * (H // 4) ** 2
+    assert rel_l2(fin[:rows].float().cpu().numpy().reshape(outs[-1].shape), outs[-1].detach().numpy()) < 3e-2
+    cos = []
+
+    def walk(gt, rt):
+        for k, v in rt.items():
+            if isinstance(v, dict):
+                walk(gt[k], v)
+            else:
+                g, r = gt[k].reshape(-1).astype(np.float64), v.grad.numpy().reshape(-1).astype(np.float64)
+                cos.append(float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)))
+    walk(got, tp)
+    print(f"{len(cos)} arrays, min cosine {min(cos):.4f}")
+    assert min(cos) > 0.95
