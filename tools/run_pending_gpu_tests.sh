@@ -12,6 +12,8 @@ timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
     "tests/test_zzz_stage_trainer_gpu.py::test_wt_segments_and_stdconv_backward" \
     "tests/test_zzz_stage_trainer_gpu.py::test_gn_backward_kernels_vs_emulation" \
     "tests/test_zzz_stage_trainer_gpu.py::test_upsample2x_backward_vs_autograd" \
+    "tests/test_zzz_stage_trainer_gpu.py::test_maxpool_backward_vs_emulation" \
+    "tests/test_zzz_stage_trainer_gpu.py::test_gn_backward_pre_relu_and_wide_channels_vs_emulation" \
     "tests/test_zzz_lift_backward_gpu.py::test_vertical_max_backward_vs_autograd" \
     "tests/test_zzz_lift_backward_gpu.py::test_match_head_and_fuse_max_backward_vs_emulation" \
     "tests/test_zzz_localizer_backward_gpu.py::test_loc_nll_backward_vs_emulation" \
