@@ -333,14 +333,18 @@ class TrunkTrainer:
     backward (`add`).  The first convolution needs no dX (the image is data): its weight gradient is one split-K product
     with the im2col matrix."""
 
-    def __init__(self, enc_params: Dict, n_img: int, H: int, W: int, device, out_dim: int = 128):
-        if H % 32 or W % 32:
-            raise ValueError("H, W must be multiples of 32 (pad_to_multiple, image_encoder.py:32-39, is the caller's job)")
+    def __init__(self, enc_params: Dict, n_img: int, H: int, W: int, device, out_dim: int = 128,
+                 skip_root_block: bool = False):
+        """skip_root_block: the aerial encoder (`defaults.py:187`, `resnet.py:200-208`): a 3x3 / stride-1 `conv_root` and no
+        max pool, i.e. the trunk runs at the raster's resolution and the maximum stride is 8."""
+        ms = 8 if skip_root_block else 32
+        if H % ms or W % ms:
+            raise ValueError(f"H, W must be multiples of {ms} (pad_to_multiple, image_encoder.py:32-39, is the caller's job)")
         pe, pd = enc_params["encoder"], enc_params["decoder"]
-        self.n, self.H, self.W, self.dev = n_img, H, W, device
+        self.n, self.H, self.W, self.dev, self.skip_root = n_img, H, W, device, skip_root_block
         z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=device)
         bf = lambda r, c: z(r, c, dt=torch.bfloat16)
-        kroot = np.ascontiguousarray(pe["root_block"]["conv_root"]["kernel"], dtype=F)
+        kroot = np.ascontiguousarray((pe if skip_root_block else pe["root_block"])["conv_root"]["kernel"], dtype=F)
         self.root_shape, self.c0 = kroot.shape, kroot.shape[-1]
         self.bank = image_encoder._WeightBank(device)
         self.root_w = self.bank.add(kroot, True, 32)
@@ -348,13 +352,13 @@ class TrunkTrainer:
         self.K0 = int(np.prod(kroot.shape[:3]))
         self.Kp = image_encoder._round_up(self.K0, 32)
         self.root_master = self.bank.master[: self.K0 * self.c0].view(self.K0, self.c0)
-        h1, w1 = H // 2, W // 2
-        h, w = h1 // 2, w1 // 2
+        h1, w1 = (H, W) if skip_root_block else (H // 2, W // 2)
+        h, w = (h1, w1) if skip_root_block else (h1 // 2, w1 // 2)
         self.rows0, self.hw_root, self.hw0 = n_img * h1 * w1, (h1, w1), (h, w)
         R0 = image_encoder._round_up(max(self.rows0, 128), 128)
         self.A = bf(R0, self.Kp)
         self.y_root, self.dy_root = bf(R0, self.c0), bf(R0, self.c0)
-        self.x0 = bf(image_encoder._round_up(max(n_img * h * w, 128), 128), self.c0)
+        self.x0 = self.y_root if skip_root_block else bf(image_encoder._round_up(max(n_img * h * w, 128), 128), self.c0)
         self.g_root_s, self.g_root = z(self.Kp, self.c0), z(self.K0, self.c0)
         self.units, shapes = [], []
         i = 1
@@ -380,9 +384,10 @@ class TrunkTrainer:
         n = self.n
         kh, kw = self.root_shape[:2]
         self.bank.run()
-        ops.root_im2col(images, self.H, self.W, kh, kw, 2, 3, self.A)
+        ops.root_im2col(images, self.H, self.W, kh, kw, 1 if self.skip_root else 2, kh // 2, self.A)
         ops.gemm(self.A, self.bank.b_mats[self.root_w], self.y_root, m_rows=self.rows0, seg_k=self.Kp)
-        ops.maxpool3x3s2(self.y_root, n, self.hw_root[0], self.hw_root[1], self.c0, self.x0)
+        if not self.skip_root:
+            ops.maxpool3x3s2(self.y_root, n, self.hw_root[0], self.hw_root[1], self.c0, self.x0)
         for a in self.acc_in + self.acc_fpn:
             a.zero_()
         ops.gn_stats(self.x0, n, self.hw0[0] * self.hw0[1], self.c0, False, self.acc_in[0])
@@ -410,12 +415,17 @@ class TrunkTrainer:
             else:
                 dout = t.backward(dout)
         # root block: max pool, then the weight gradient of the first convolution
-        ops.maxpool3x3s2_backward(self.y_root, dout, n, self.hw_root[0], self.hw_root[1], self.c0, self.dy_root)
-        ops.dense_wgrad(self.A, self.dy_root, self.rows0, self.Kp, self.c0, self.g_root_s, None)
+        if self.skip_root:
+            dy_root = dout
+        else:
+            ops.maxpool3x3s2_backward(self.y_root, dout, n, self.hw_root[0], self.hw_root[1], self.c0, self.dy_root)
+            dy_root = self.dy_root
+        ops.dense_wgrad(self.A, dy_root, self.rows0, self.Kp, self.c0, self.g_root_s, None)
         ops.stdconv_backward(self.root_master, self.g_root_s[: self.K0], self.g_root)
 
     def grads_tree(self) -> Dict:
-        enc: Dict = {"root_block": {"conv_root": {"kernel": self.g_root.cpu().numpy().reshape(self.root_shape).copy()}}}
+        groot = {"conv_root": {"kernel": self.g_root.cpu().numpy().reshape(self.root_shape).copy()}}
+        enc: Dict = dict(groot) if self.skip_root else {"root_block": groot}
         for u in self.units:
             enc.setdefault(u["path"][0], {})[u["path"][1]] = u["t"].grads_tree(u["params"])
         return {"encoder": enc, "decoder": self.fpn.grads_tree()}

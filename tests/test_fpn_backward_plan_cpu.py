@@ -233,3 +233,50 @@ def test_whole_encoder_backward_plan_matches_autograd():
     assert min(cosines.values()) > 0.97, sorted(cosines.items(), key=lambda kv: kv[1])[:4]
     assert max(errs.values()) < 0.3, worst
     assert errs["decoder/3_skip_conv/kernel"] < 2e-2 and errs["decoder/3_skip_norm/bias"] < 2e-2     # above the chaos
+
+
+def test_aerial_encoder_backward_plan_wiring():
+    """`TrunkTrainer(skip_root_block=True)`: the aerial encoder (3x3 / stride-1 conv_root, no max pool, resnet.py:200-208)
+    on the emulated layer vs autograd of the oracle (directional bound, see the test above)."""
+    from oracle import image_encoder as oie, resnet as ores
+    from snap_b200 import encoder_train, params
+    rng = np.random.default_rng(78)
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+    unit = lambda cin, nmid, nout: {"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+                                    "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)},
+                                    "conv_proj": {"kernel": ln(1, 1, cin, nout)}}
+    enc = {"conv_root": {"kernel": ln(3, 3, 3, 64)}, "block1": {"unit01": unit(64, 64, 256)}, "block2": {"unit01": unit(256, 128, 512)},
+           "block3": {"unit01": unit(512, 256, 1024)}, "block4": {"unit01": unit(1024, 512, 2048)}}
+    dec = {}
+    for level, c in enumerate((2048, 1024, 512, 256)):
+        dec[f"{level}_skip_norm"] = gnp(c)
+        dec[f"{level}_skip_conv"] = {"kernel": ln(1, 1, c, 128)}
+    p = params.round_to_bf16({"encoder": enc, "decoder": dec})
+    n, H = 1, 32
+    img = rng.random((n, H, H, 3)).astype(F)
+    dfin = bf16_np(rng.standard_normal((n, H, H, 128)) * 0.05)
+    tt = lambda t: {k: (tt(v) if isinstance(v, dict) else torch.from_numpy(v).requires_grad_(True)) for k, v in t.items()}
+    tp = tt(p)
+    stages = ores.resnet_v2(torch.from_numpy(img), tp["encoder"], True, rd_bf16)
+    outs = oie.fpn_decoder(stages[::-1], tp["decoder"], rd_bf16)
+    (outs[-1] * torch.from_numpy(dfin)).sum().backward()
+    with emulated_ops():
+        tr = encoder_train.TrunkTrainer(p, n, H, H, torch.device("cpu"), skip_root_block=True)
+        fin = tr.forward(torch.from_numpy(img))
+        tr.backward(torch.from_numpy(dfin.reshape(-1, 128)).to(torch.bfloat16))
+        got = tr.grads_tree()
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    assert rel(fin[: n * H * H].float().numpy().reshape(outs[-1].shape), outs[-1].detach().numpy()) < 3e-2
+    cos = {}
+
+    def walk(gt, rt, pre):
+        for k, v in rt.items():
+            if isinstance(v, dict):
+                walk(gt[k], v, pre + (k,))
+            else:
+                g, r = gt[k].reshape(-1).astype(np.float64), v.grad.numpy().reshape(-1).astype(np.float64)
+                cos["/".join(pre + (k,))] = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+    walk(got, tp, ())
+    print(len(cos), "arrays, min cosine", round(min(cos.values()), 4))
+    assert min(cos.values()) > 0.97, sorted(cos.items(), key=lambda kv: kv[1])[:3]
