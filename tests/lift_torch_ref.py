@@ -49,13 +49,14 @@ def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, dept
     return torch.where(any_v[:, None], stats, torch.zeros_like(stats))
 
 
-def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, tp=None):
+def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, tp=None, x=None):
     """proj MLP -> gather / pooling -> fusion MLP -> mask (:282) -> vertical max (bev_mapper.py:80-86) as ONE autograd graph.
     Returns the leaves (parameters tp, encoder features x) and the forward tensors (crop, fimg, vol, plane, plane_valid)."""
     if tp is None:      # fresh leaves; pass `tp` to share the parameters between several scenes of one graph
         tp = {k: {n: {a: torch.from_numpy(np.ascontiguousarray(v, dtype=F)).requires_grad_(True) for a, v in d.items()}
                   for n, d in t.items()} for k, t in svp.items() if k in ("proj_mlp", "fusion_mlp")}
-    x = torch.from_numpy(enc).requires_grad_(True)
+    if x is None:       # a leaf; pass `x` (e.g. the encoder's finest FPN level, [V*hf*wf, C]) to extend an existing graph
+        x = torch.from_numpy(enc).requires_grad_(True)
     crop = torch.relu(x)
     fimg = rd(rd(crop @ tp["proj_mlp"]["Dense_0"]["kernel"]) + tp["proj_mlp"]["Dense_0"]["bias"])
     stats = rd(gather_pool_stats(fimg.reshape(V, hf, wf, -1), p2d, vis, depth))

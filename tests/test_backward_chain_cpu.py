@@ -192,3 +192,76 @@ def test_frozen_encoder_step_backward_matches_autograd():
     print({k: round(float(v), 4) for k, v in errs.items()})
     assert float(x_q.grad.norm()) > 1e-6 and float(x_m.grad.norm()) > 1e-6, "both sides receive gradient"
     assert max(errs.values()) < 3e-2, errs
+
+
+def test_plane_cotangent_to_every_encoder_weight():
+    """One scene end to end: images -> `TrunkTrainer` (whole image encoder) -> proj MLP -> lift -> fusion MLP -> vertical
+    max, then `LiftBackward.scene_backward` hands the cotangent of the encoder features to `TrunkTrainer.backward`.
+    Against ONE autograd graph of the oracle chain: the lift / MLP gradients tightly, the encoder's arrays directionally
+    (the free-running bf16 trunk is chaotic, tests/test_fpn_backward_plan_cpu.py)."""
+    from oracle import image_encoder as oie, resnet as ores
+    from snap_b200 import configs, encoder_train, ops, params, streetview_encoder as sve, streetview_train
+    G, V, hw, cell = 16, 2, (128, 128), 0.2
+    hf, wf = hw[0] // 4, hw[1] // 4
+    rng = np.random.default_rng(91)
+    Z, p2d, vis, depth = _scene_geometry(6, G, V, hw, cell)
+    cells = G * G
+    assert vis.any(-1).mean() > 0.02
+    ln = lambda *s: (rng.standard_normal(s) / np.sqrt(np.prod(s[:-1]))).astype(F)
+    gnp = lambda c: {"scale": (1 + 0.2 * rng.standard_normal((1, 1, 1, c))).astype(F), "bias": (0.1 * rng.standard_normal((1, 1, 1, c))).astype(F)}
+    unit = lambda cin, nmid, nout: {"gn1": gnp(cin), "gn2": gnp(nmid), "gn3": gnp(nmid), "conv1": {"kernel": ln(1, 1, cin, nmid)},
+                                    "conv2": {"kernel": ln(3, 3, nmid, nmid)}, "conv3": {"kernel": ln(1, 1, nmid, nout)},
+                                    "conv_proj": {"kernel": ln(1, 1, cin, nout)}}
+    enc = {"root_block": {"conv_root": {"kernel": ln(7, 7, 3, 64)}}, "block1": {"unit01": unit(64, 64, 256)},
+           "block2": {"unit01": unit(256, 128, 512)}, "block3": {"unit01": unit(512, 256, 1024)},
+           "block4": {"unit01": unit(1024, 512, 2048)}}
+    dec = {}
+    for level, c in enumerate((2048, 1024, 512, 256)):
+        dec[f"{level}_skip_norm"] = gnp(c)
+        dec[f"{level}_skip_conv"] = {"kernel": ln(1, 1, c, 128)}
+    pe = params.round_to_bf16({"encoder": enc, "decoder": dec})
+    svp = params.round_to_bf16(params.perturb_affine(rng, {"proj_mlp": params.init_mlp(rng, 128, (160,)),
+                                                           "fusion_mlp": params.init_mlp(rng, 257, (256, 128))}))
+    img = rng.random((V, hw[0], hw[1], 3)).astype(F)
+    dplane = bf16_np(rng.standard_normal((cells, 128)) * 0.1)
+    # reference: one graph
+    tt = lambda t: {k: (tt(v) if isinstance(v, dict) else torch.from_numpy(v).requires_grad_(True)) for k, v in t.items()}
+    tpe = tt(pe)
+    stages = ores.resnet_v2(torch.from_numpy(img), tpe["encoder"], False, rd_bf16)
+    fin_ref = oie.fpn_decoder(stages[::-1], tpe["decoder"], rd_bf16)[-1]                        # [V, hf, wf, 128]
+    tp, _, t = chain_forward(svp, None, p2d, vis, depth, V, hf, wf, cells, Z, rd_bf16, x=fin_ref.reshape(V * hf * wf, 128))
+    (t["plane"] * torch.from_numpy(dplane)).sum().backward()
+    # product plans
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(torch.bfloat16)
+    lp = sve.fill_lift_params(configs.streetview_encoder(), V, hf, wf, G, G, Z, 288)
+    with emulated_ops(make_lift_emulation(p2d, vis, depth)):
+        tr = encoder_train.TrunkTrainer(pe, V, hw[0], hw[1], torch.device("cpu"))
+        fin = tr.forward(torch.from_numpy(img))
+        rows_img = V * hf * wf
+        crop = torch.relu(fin[:rows_img]).contiguous()                                        # ops.crop_relu on full-size maps
+        fimg = torch.zeros((rows_img, 160), dtype=torch.bfloat16)
+        lb = streetview_train.LiftBackward(svp, torch.device("cpu"))
+        ops.gemm(crop, lb.W["proj_mlp/Dense_0/kernel"].t().contiguous().to(torch.bfloat16), fimg, m_rows=rows_img,
+                 bias=lb.b["proj_mlp/Dense_0/bias"])
+        lb.zero_grads()
+        dcrop = lb.scene_backward(lp, None, fimg, crop, None, None, None, None, None, bf(dplane))
+        tr.backward(dcrop[:rows_img].contiguous())
+        g_lift, g_enc = lb.grads_tree(), tr.grads_tree()
+    rel = lambda g, r: np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+    assert rel(fin[:rows_img].float().numpy(), fin_ref.detach().numpy().reshape(rows_img, 128)) < 3e-2
+    cos = {}
+
+    def walk(gt, rt, pre):
+        for k, v in rt.items():
+            if isinstance(v, dict):
+                walk(gt[k], v, pre + (k,))
+            else:
+                g, r = gt[k].reshape(-1).astype(np.float64), v.grad.numpy().reshape(-1).astype(np.float64)
+                cos["/".join(pre + (k,))] = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+    walk(g_enc, tpe, ())
+    walk(g_lift, tp, ())
+    low = sorted(cos.items(), key=lambda kv: kv[1])[:3]
+    print(len(cos), "arrays from the plane cotangent; lowest cosines:", [(k, round(v, 4)) for k, v in low])
+    assert min(cos.values()) > 0.95, low
+    for k in ("fusion_mlp/Dense_1/kernel", "fusion_mlp/Dense_0/kernel", "proj_mlp/Dense_0/kernel"):
+        assert cos[k] > 0.98, (k, cos[k])      # their inputs (the encoder features) already differ by ~1 % from the oracle's
