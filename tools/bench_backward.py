@@ -112,3 +112,17 @@ dsim = torch.zeros((B, Nq + 12, G * G), dtype=torch.bfloat16, device=dev)
 ms_ps = timed(lambda: ops.loc_pose_scoring_backward(maps.sim, maps.point_scale, t(q_xy), vj, poses, dscores, G, G, cell, True, True, dsim))
 print(json.dumps({"plan": "LocalizerLossBackward.backward", "workload": f"N={Nq} points, {G}x{G} map, P={P1} poses, B={B}",
                   "valid_points": int(vq.sum()), "ms": round(ms_loc, 3), "ms_pose_scoring_backward_kernel": round(ms_ps, 3)}), flush=True)
+
+# ---- whole image encoder: training forward + backward (R50 + FPN, one tile = 4 views padded to 512 x 672) ------------------
+from snap_b200 import encoder_train  # noqa: E402
+
+ep = params.round_to_bf16(params.init_image_encoder(np.random.default_rng(3), configs.image_encoder()))
+Hp, Wp, nv = 512, 672, 4
+tr = encoder_train.TrunkTrainer(ep, nv, Hp, Wp, dev)
+img = torch.rand((nv, Hp, Wp, 3), dtype=torch.float32, device=dev)
+tr.forward(img)
+dfin = bf(rng.standard_normal((nv * (Hp // 4) * (Wp // 4), 128)) * 0.01)
+ms_ef = timed(lambda: tr.forward(img))
+ms_eb = timed(lambda: tr.backward(dfin))
+print(json.dumps({"plan": "TrunkTrainer forward / backward", "workload": f"R50 + FPN, {nv} views {Hp}x{Wp}",
+                  "ms_training_forward": round(ms_ef, 3), "ms_backward": round(ms_eb, 3)}), flush=True)
