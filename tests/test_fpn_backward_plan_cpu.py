@@ -280,3 +280,35 @@ def test_aerial_encoder_backward_plan_wiring():
     walk(got, tp, ())
     print(len(cos), "arrays, min cosine", round(min(cos.values()), 4))
     assert min(cos.values()) > 0.97, sorted(cos.items(), key=lambda kv: kv[1])[:3]
+
+
+def test_trunk_trainer_runs_the_reference_r50_tree():
+    """The real BiT-R50 parameter tree ([3, 4, 6, 3] units; `params.init_image_encoder`, names of SURVEY Appendix B) through
+    `TrunkTrainer` on the emulated layer: every one of its arrays receives a finite, non-zero gradient of the right shape
+    (identity units at 512 / 1024 / 2048 channels, weight gradients sliced at 1024)."""
+    from snap_b200 import configs, encoder_train, params
+    rng = np.random.default_rng(5)
+    p = params.round_to_bf16(params.perturb_affine(rng, params.init_image_encoder(rng, configs.image_encoder())))
+    n, H = 1, 128
+    img = rng.random((n, H, H, 3)).astype(F)
+    dfin = bf16_np(rng.standard_normal((n * (H // 4) ** 2, 128)) * 0.05)
+    with emulated_ops():
+        tr = encoder_train.TrunkTrainer(p, n, H, H, torch.device("cpu"))
+        assert len(tr.units) == 16 and sum(isinstance(u["t"], encoder_train.StridedUnitTrainer) for u in tr.units) == 3
+        fin = tr.forward(torch.from_numpy(img))
+        tr.backward(torch.from_numpy(dfin).to(torch.bfloat16))
+        got = tr.grads_tree()
+    assert torch.isfinite(fin.float()).all() and float(fin.float().abs().max()) > 0
+    count = 0
+
+    def walk(gt, pt, pre):
+        nonlocal count
+        for k, v in pt.items():
+            if isinstance(v, dict):
+                walk(gt[k], v, pre + (k,))
+            else:
+                g = gt[k]
+                assert g.shape == np.asarray(v).shape and np.isfinite(g).all() and np.abs(g).max() > 0, pre + (k,)
+                count += 1
+    walk(got, p, ())
+    assert count == 16 * 9 + 4 + 1 + 4 * 3, count     # 16 units x (3 convs + 3 x 2 GroupNorm arrays) + 4 projections + root + FPN
