@@ -98,3 +98,33 @@ def test_host_side_planning_functions_without_gpu():
     wg = lib.snapb200_dense_wgrad_workspace
     wg.restype = C.c_size_t
     assert wg(C.c_longlong(65536), 128, 128) == 293 * (128 * 128 + 128) * 4      # 224 rows per slab -> 293 slabs of partials
+
+
+def test_backward_entry_points_reject_null_arguments_without_touching_the_gpu():
+    """Every backward entry point added for SURVEY 8(f)1 validates its arguments before any CUDA call: NULL pointers /
+    empty problems return SNAPB200_ERR_INVALID with a message (no crash, no device needed)."""
+    import ctypes as C
+    from snap_b200 import _lib
+    lib = _lib.lib()
+    lib.snapb200_last_error.restype = C.c_char_p
+    null, i0 = C.c_void_p(0), 0
+    ll = C.c_longlong
+    lp, sp = _lib.LiftParams(), _lib.LocScoreParams()
+    calls = {
+        "snapb200_gn_backward": (null, null, null, i0, null, 1, 4, 4, 64, null, 64, null, null, i0, 1, i0, null, null, null, null, null),
+        "snapb200_upsample2x_backward": (null, 1, 4, 4, 128, null, null),
+        "snapb200_maxpool3x3s2_backward": (null, null, 1, 4, 4, 64, null, null),
+        "snapb200_wt_segments": (null, 64, 64, 64, 1, null, 64, null),
+        "snapb200_stdconv_backward": (null, null, 64, 64, null, null),
+        "snapb200_lift_gather_pool_backward": (C.byref(lp), null, null, null, null, null, null, null, null),
+        "snapb200_lift_select_pool_backward": (C.byref(lp), 4, null, null, null, null, null, null, null, null, null),
+        "snapb200_vertical_max_backward": (null, null, null, ll(16), 4, 128, null, null),
+        "snapb200_match_head_backward": (null, null, ll(16), 128, null, null, null, null, null),
+        "snapb200_fuse_max_backward": (null, null, null, null, null, ll(16), 128, null, null, null),
+        "snapb200_loc_nll_backward": (null, null, null, 1, 8, i0, C.c_float(0), C.c_float(0), null, null, null),
+        "snapb200_loc_pose_scoring_backward": (C.byref(sp), null, null, null, null, null, null, 1, 8, null, null),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        msg = lib.snapb200_last_error().decode()
+        assert rc != 0 and msg, (name, rc, msg)
