@@ -16,15 +16,10 @@ template <int BN, int BK, bool CONVEPI = false>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, GemmParams p, int ctas_per_sm, cudaStream_t s) {
   using Cfg = GemmCfg<BN, BK>;
-  static bool configured = false;
-  if (!configured) {
-    int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, AMODE_TMA, CONVEPI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::smem_bytes(Cfg::MAX_STAGES)),
-                        "cudaFuncSetAttribute(gemm_tc)");
-    if (rc) return rc;
-    configured = true;
-  }
+  static DynSmemState smem_state;  // per device (one process may drive several GPUs)
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, BK, AMODE_TMA, CONVEPI>),
+                               Cfg::smem_bytes(Cfg::MAX_STAGES), &smem_state, "cudaFuncSetAttribute(gemm_tc)"))
+    return rc;
   // occupancy plan: `ctas_per_sm` co-resident CTAs share the SM's 227 KB of shared memory and 512 TMEM
   // columns; memory-bound layers (small K) want several CTAs so that epilogues overlap main loops
   int max_by_tmem = 512 / Cfg::TMEM_COLS;
@@ -121,15 +116,13 @@ namespace snapb200 {
 template <int BN, int AMODE>
 static int launch_gn_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t s) {
   using Cfg = GemmCfg<BN, 64>;
-  static bool configured = false;
-  if (!configured) {
+  static DynSmemState smem_state;
+  {
     const int want = Cfg::smem_bytes(Cfg::MAX_STAGES, true);
-    int rc = check_cuda(cudaFuncSetAttribute(gemm_tc_kernel<BN, 64, AMODE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             want > 227 * 1024 ? 227 * 1024 : want),
-                        "cudaFuncSetAttribute(gemm_tc<gn>)");
-    if (rc) return rc;
-    configured = true;
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, 64, AMODE>),
+                                 want > 227 * 1024 ? 227 * 1024 : want, &smem_state,
+                                 "cudaFuncSetAttribute(gemm_tc<gn>)"))
+      return rc;
   }
   int stages = p.nkb < Cfg::MAX_STAGES ? p.nkb : Cfg::MAX_STAGES;
   if (stages < 2) stages = 2;

@@ -30,16 +30,33 @@ int check_launch(const char* what) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return 148;
+  static int cached[SNAP_MAX_DEVICES];  // per device ordinal; a racing first call writes the same value twice
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < SNAP_MAX_DEVICES) {
+    n = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+    if (n > 0) return n;
   }
-  return cached;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev >= 0 && dev < SNAP_MAX_DEVICES) __atomic_store_n(&cached[dev], n, __ATOMIC_RELAXED);
+  return n;
+}
+
+int ensure_dyn_smem(const void* func, size_t bytes, DynSmemState* st, const char* what) {
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  const bool tracked = dev >= 0 && dev < SNAP_MAX_DEVICES;
+  if (tracked && __atomic_load_n(&st->bytes[dev], __ATOMIC_ACQUIRE) >= (unsigned long long)bytes) return SNAPB200_OK;
+  if (int rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what))
+    return rc;
+  if (tracked) {
+    unsigned long long cur = __atomic_load_n(&st->bytes[dev], __ATOMIC_RELAXED);
+    while (cur < (unsigned long long)bytes &&
+           !__atomic_compare_exchange_n(&st->bytes[dev], &cur, (unsigned long long)bytes, true, __ATOMIC_RELEASE,
+                                        __ATOMIC_RELAXED)) {
+    }
+  }
+  return SNAPB200_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

@@ -13,8 +13,19 @@ namespace snapb200 {
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int check_launch(const char* what);  // cudaPeekAtLastError + launch counter
-int num_sms();
+int num_sms();  // SM count of the CURRENT device (cached per device ordinal)
 void count_launch();
+
+// Per-device "largest dynamic shared memory size opted in so far" for ONE kernel function.  The attribute
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): a host that drives several devices from one
+// process (the reference's pmap host, snap/trainer.py:452-464) has to opt every device in.  Zero-initialised static
+// storage; thread-safe (relaxed atomics: setting the attribute twice is harmless).
+constexpr int SNAP_MAX_DEVICES = 64;
+struct DynSmemState {
+  unsigned long long bytes[SNAP_MAX_DEVICES];
+};
+// Opt `func` in to `bytes` of dynamic shared memory on the current device unless a value >= bytes was already set there.
+int ensure_dyn_smem(const void* func, size_t bytes, DynSmemState* st, const char* what);
 
 // 2D bf16 tensor map: dims {cols (inner), rows}, row pitch ld elements, box {box_cols, box_rows},
 // swizzle = box_cols * 2 bytes (64 or 128), zero fill out of bounds.

@@ -662,14 +662,10 @@ extern "C" int snapb200_lift_fused(const SnapLiftParams* q, const SnapLiftView* 
   static_assert(sizeof(SnapLiftView) == sizeof(LiftView), "SnapLiftView layout");
   static_assert(sizeof(SnapLiftParams) == sizeof(LiftParams), "SnapLiftParams layout");
   cudaStream_t s = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
-    int rc = check_cuda(cudaFuncSetAttribute(lift_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             FL_SMEM_BYTES),
-                        "cudaFuncSetAttribute(lift_fused)");
-    if (rc) return rc;
-    configured = true;
-  }
+  static DynSmemState smem_state;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&lift_fused_kernel), FL_SMEM_BYTES, &smem_state,
+                               "cudaFuncSetAttribute(lift_fused)"))
+    return rc;
   CUtensorMap tmW1, tmW2;
   int rc = make_tmap_2d_bf16(&tmW1, w1t, 256, 256, ldw1, 256, 64);
   if (rc) return rc;

@@ -841,14 +841,10 @@ int snapb200_loc_pose_scoring(const SnapLocScoreParams* p, const void* sim, cons
   const dim3 grid(chunks, splits, p->B);
 #define SNAP_LOC_SCORE(PPT_, MASK_)                                                                              \
   do {                                                                                                          \
-    static size_t configured = 0; /* largest dynamic shared memory size set so far (attribute is sticky) */     \
-    if (smem > configured) {                                                                                    \
-      if (int rc = check_cuda(cudaFuncSetAttribute(loc_pose_scoring_kernel<PPT_, MASK_>,                        \
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),     \
-                              "cudaFuncSetAttribute(loc_pose_scoring)"))                                        \
-        return rc;                                                                                              \
-      configured = smem;                                                                                        \
-    }                                                                                                           \
+    static DynSmemState smem_state; /* largest size set so far, per device (the attribute is sticky) */         \
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&loc_pose_scoring_kernel<PPT_, MASK_>), smem,    \
+                                 &smem_state, "cudaFuncSetAttribute(loc_pose_scoring)"))                        \
+      return rc;                                                                                                \
     loc_pose_scoring_kernel<PPT_, MASK_><<<grid, LOC_SCORE_THREADS, smem, s>>>(a);                              \
   } while (0)
   if (ppt == 16) {

@@ -158,14 +158,11 @@ int snapb200_loc_pose_scoring_backward(const SnapLocScoreParams* p, const void* 
   SNAP_REQUIRE(dsim_rows >= p->N, "dsim_rows (rows per example of dsim) must be >= N");
   const size_t smem = (size_t)p->H * p->W * sizeof(float);
   SNAP_REQUIRE(smem <= 200 * 1024, "cotangent map of %d x %d does not fit in shared memory", p->H, p->W);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(loc_pose_scoring_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem),
-                            "cudaFuncSetAttribute(loc_pose_scoring_bwd)"))
+  static DynSmemState smem_state;
+  if (smem > 48 * 1024)
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&loc_pose_scoring_bwd_kernel), smem, &smem_state,
+                                 "cudaFuncSetAttribute(loc_pose_scoring_bwd)"))
       return rc;
-    configured = smem;
-  }
   dim3 grid((unsigned)p->N, (unsigned)p->B);
   loc_pose_scoring_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)sim, point_scale, i_xy, p->i_xy_batched, p->mask_out_of_bounds ? valid_j : nullptr, poses,

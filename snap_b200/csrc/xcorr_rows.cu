@@ -291,13 +291,10 @@ extern "C" int snapb200_xcorr_scores_rows(const void* templates, const void* m_p
   SNAP_REQUIRE(G % XR_JB == 0 && G >= 8 && 128 + G - 1 <= 256, "row-major correlation needs an even G <= 129");
   SNAP_REQUIRE(workspace_bytes >= snapb200_xcorr_scores_rows_workspace(B, R, G, D), "workspace too small");
   SNAP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
-    int rc = check_cuda(cudaFuncSetAttribute(xcorr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XR_SMEM_MAX),
-                        "cudaFuncSetAttribute(xcorr_rows)");
-    if (rc) return rc;
-    configured = true;
-  }
+  static DynSmemState smem_state;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&xcorr_rows_kernel), XR_SMEM_MAX, &smem_state,
+                               "cudaFuncSetAttribute(xcorr_rows)"))
+    return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const int RP = snapb200_xcorr_padded_rotations(R);
   {

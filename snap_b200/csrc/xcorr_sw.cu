@@ -270,13 +270,10 @@ extern "C" int snapb200_xcorr_scores_sw(const void* templates, const void* m_pad
   SNAP_REQUIRE(D == 32, "matching_dim must be 32 (got %d)", D);
   SNAP_REQUIRE(snapb200_xcorr_padded_rotations(R) == XS_N, "sliding-window correlation needs num_rotations <= 48");
   SNAP_REQUIRE(G % XS_JB == 0 && G >= 8 && 128 + G - 1 <= 256, "sliding-window correlation needs G %% 4 == 0, G <= 129");
-  static bool configured = false;
-  if (!configured) {
-    int rc = check_cuda(cudaFuncSetAttribute(xcorr_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM),
-                        "cudaFuncSetAttribute(xcorr_sw)");
-    if (rc) return rc;
-    configured = true;
-  }
+  static DynSmemState smem_state;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&xcorr_sw_kernel), XS_SMEM, &smem_state,
+                               "cudaFuncSetAttribute(xcorr_sw)"))
+    return rc;
   XsParams P;
   P.B = B; P.R = R; P.G = G; P.U = 2 * G - 1;
   P.Prows = 3 * G - 2; P.Pal = snapb200_xcorr_padded_cols(G);

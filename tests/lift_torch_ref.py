@@ -49,7 +49,7 @@ def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, dept
     return torch.where(any_v[:, None], stats, torch.zeros_like(stats))
 
 
-def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, tp=None, x=None):
+def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, tp=None, x=None, route_vol=None):
     """proj MLP -> gather / pooling -> fusion MLP -> mask (:282) -> vertical max (bev_mapper.py:80-86) as ONE autograd graph.
     Returns the leaves (parameters tp, encoder features x) and the forward tensors (crop, fimg, vol, plane, plane_valid)."""
     if tp is None:      # fresh leaves; pass `tp` to share the parameters between several scenes of one graph
@@ -67,13 +67,23 @@ def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, tp=None, x
     m = valid.reshape(cells, Z, 1)
     masked = torch.where(m, vol.reshape(cells, Z, -1), torch.full((), -float("inf")))
     plane = torch.where(m.any(1), masked.amax(1), torch.zeros(()))
+    if route_vol is not None:
+        # teacher-forced arg-max: the z level(s) that receive the cotangent are taken from ANOTHER forward's volume (the
+        # CUDA one), ties split evenly like jnp.max / torch.amax; the forward value is unchanged up to near-ties.  Removes
+        # the chaotic part of a GPU-vs-autograd comparison: a one-ulp difference between two near-tied levels otherwise
+        # re-routes that cell's whole cotangent.
+        rv = torch.from_numpy(np.ascontiguousarray(route_vol, dtype=F)).reshape(cells, Z, -1)
+        rmask = torch.where(m, rv, torch.full((), -float("inf")))
+        hit = (rmask == rmask.amax(1, keepdim=True)) & m
+        wgt = hit.float() / hit.float().sum(1, keepdim=True).clamp(min=1.0)
+        plane = (wgt * vol.reshape(cells, Z, -1)).sum(1)
     return tp, x, dict(crop=crop, fimg=fimg, vol=vol, plane=plane, plane_valid=m.any(1)[:, 0])
 
 
-def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd):
+def chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd, route_vol=None):
     """Autograd of loss = sum(plane * dplane) through `chain_forward`.  Returns the forward tensors the product's backward
     consumes (NumPy), the parameter gradients {proj_mlp, fusion_mlp} and the cotangent of the encoder features."""
-    tp, x, t = chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd)
+    tp, x, t = chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, route_vol=route_vol)
     (t["plane"] * torch.from_numpy(dplane)).sum().backward()
     grads = {k: {n: {a: v.grad.numpy() for a, v in d.items()} for n, d in tt.items()} for k, tt in tp.items()}
     fwd = {k: t[k].detach().numpy() for k in ("crop", "fimg", "vol", "plane")}

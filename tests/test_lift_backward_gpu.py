@@ -1,16 +1,14 @@
 """Backward kernels of the lift (csrc/lift_backward.cu) on the GPU against torch autograd of tests/lift_torch_ref.py
 (whose forward equals the NumPy oracle and whose autograd equals the closed forms, tests/test_lift_backward_ref_cpu.py).
 
-NOTE: written after this round's GPU budget was spent; collected LAST and xfail(strict=False) until the first B200 run
-(see tests/test_zzz_stage_trainer_gpu.py)."""
+First B200 run: round 2 (gpurun_out/r2a_pending.log); the chain test is teacher-forced on the arg-max routing since."""
 import numpy as np
 import pytest
 import torch
 
-from util import F, bf16_np, rel_l2, to_oracle_geometry
+from util import F, bf16_np, record_parity, rel_l2, to_oracle_geometry
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first B200 run pending (written after the round-1 GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.mark.parametrize("V,layout", [(3, {}), (4, dict(spacing=0.5, same_side=True))])
@@ -135,17 +133,28 @@ def test_lift_backward_chain_vs_autograd():
     ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
     xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
     p2d, vis, depth, _ = osv.project_points_to_views(oT, ocam, xyz.reshape(-1, 3))
-    fwd, ref, ref_x = chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd_bf16)
+    # The vertical max routes each cell's cotangent through its arg-max level, and the CUDA forward differs from the oracle's
+    # by bf16 flips (rel 1e-4): free-running, a flip between two near-tied levels re-routes the whole cotangent of that
+    # (cell, channel) and the gradients differ by 3-6 % (first B200 run: 0.047 / 0.038 / 0.047 / 0.039 / 0.028 / 0.000 and
+    # 0.057 for the feature cotangent).  So the comparison is TEACHER-FORCED: the reference routes through the levels of the
+    # CUDA volume (`route_vol`); what is left is bf16 rounding of the intermediate cotangents.  The free-running numbers
+    # are printed for the record.
+    vol_np = vol.float().cpu().numpy()
+    fwd, ref, ref_x = chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd_bf16, route_vol=vol_np)
+    _, ref_free, ref_x_free = chain_reference(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, dplane, rd_bf16)
     assert np.array_equal(valid.cpu().numpy().astype(bool), vis.any(-1))
-    assert rel_l2(vol.float().cpu().numpy(), fwd["vol"]) < 5e-3
+    assert rel_l2(vol_np, fwd["vol"]) < 1e-3
+    errs = {}
     for k in ("proj_mlp", "fusion_mlp"):
         for n, d in ref[k].items():
             for a, r in d.items():
-                err = rel_l2(got[k][n][a], r)
-                print(f"{k}/{n}/{a}: |grad| {np.linalg.norm(r):.3e} rel err {err:.4f}")
-                # the max routes the cotangent through the arg-max level: a bf16 flip between near-tied levels moves it
-                assert err < 5e-2
-    assert rel_l2(dcrop[:rows_img].float().cpu().numpy(), ref_x) < 5e-2
+                errs[f"{k}/{n}/{a}"] = (rel_l2(got[k][n][a], r), rel_l2(got[k][n][a], ref_free[k][n][a]), float(np.linalg.norm(r)))
+    got_x = dcrop[:rows_img].float().cpu().numpy()
+    errs["d encoder features"] = (rel_l2(got_x, ref_x), rel_l2(got_x, ref_x_free), float(np.linalg.norm(ref_x)))
+    for name, (e_tf, e_free, nrm) in errs.items():
+        print(f"{name}: |grad| {nrm:.3e} rel err teacher-forced {e_tf:.4f} (free-running {e_free:.4f})")
+        record_parity("lift backward chain", name, e_tf, 2e-2)
+    assert max(e for e, _, _ in errs.values()) < 2e-2, errs
     # after the fused forward there is no volume: the backward recomputes it (same kernels -> same bits)
     dcrop1 = dcrop.clone()
     lb2 = streetview_train.LiftBackward(svp, torch.device(dev))

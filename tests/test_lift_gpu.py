@@ -242,6 +242,58 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
     assert np.abs(a - b).max() <= 2.0 ** -6 * np.abs(b).max()
 
 
+@pytest.mark.parametrize("G,V,hw_img,dense", [(24, 3, (64, 96), False), (64, 2, (224, 224), False), (32, 4, (96, 128), True)])
+def test_fused_lift_vs_oracle(G, V, hw_img, dense):
+    """The DEFAULT product kernel (`lift_fused_kernel`) against the CPU oracle directly (not against the unfused CUDA path):
+    `oracle.bev_mapper.lift_scene` (streetview_encoder.py:232-286) + `vertical_pooling_max` (bev_mapper.py:56-88) in
+    bf16-emulation mode on identical bf16 feature maps / weights.  valid plane bit-exact; floats <= 1e-3 relative L2
+    (north_star), measured 1e-4 .. 3e-4 (profiles/r02_parity_table.md).  `dense`: cameras packed so that most voxels are seen
+    by several views (exercises the multi-view pooling branch rather than the single-view fast path)."""
+    from oracle import bev_mapper as obm, grids as ogrids
+    from snap_b200 import configs, ops, params, streetview_encoder as sve
+    from snap_b200.image_encoder import _WeightBank
+    layout = dict(spacing=0.5, same_side=True) if dense else {}
+    data, grid, mapper, xs, ys, zs = _lift_inputs(G, hw_img, V, 9, **layout)
+    hf, wf = -(-hw_img[0] // 4), -(-hw_img[1] // 4)
+    rng = np.random.default_rng(23)
+    cfg = configs.streetview_encoder()
+    Z = zs.shape[1]
+    dev = "cuda"
+    fimg_np = bf16_np(rng.standard_normal((V, hf, wf, 160)))
+    fp = params.round_to_bf16(params.perturb_affine(rng, params.init_mlp(rng, 257, (256, 128))))
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.from_numpy(sve.pack_views(data["camera"], data["T_view2scene"], 0, (4.0, 4.0))).to(dev)
+    bank = _WeightBank(torch.device(dev))
+    w0 = bank.add(fp["Dense_0"]["kernel"], False, 32)
+    w1 = bank.add(fp["Dense_1"]["kernel"], False)
+    bank.finalize(); bank.run()
+    b1, b2 = _t(fp["Dense_0"]["bias"]).to(dev), _t(fp["Dense_1"]["bias"]).to(dev)
+    plane = torch.full((G * G, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    pv = torch.full((G * G,), 9, dtype=torch.uint8, device=dev)
+    counter = torch.zeros(16, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(ops.lift_fused_scratch_bytes(), dtype=torch.uint8, device=dev)
+    ops.lift_fused(lp, views, _t(fimg_np).to(torch.bfloat16).to(dev), _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev),
+                   bank.b_mats[w0], _t(fp["Dense_0"]["kernel"][256]).to(dev), b1, bank.b_mats[w1], b2, plane, pv, counter,
+                   scratch)
+    torch.cuda.synchronize()
+    ocam, oT = to_oracle_geometry(data, 0)
+    ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
+    xyz, _ = obm.build_xyz_query(ogrids.Grid2D((G, G), 0.2), oT.t)
+    f_grid, ovalid, ovis, _ = obm.lift_scene(fimg_np, ocam, oT, xyz, fp, rd=rd_bf16)
+    oplane, opvalid = obm.vertical_pooling_max(f_grid, ovalid)
+    assert np.array_equal(pv.cpu().numpy().astype(bool), opvalid.reshape(-1)), "valid plane differs from the oracle"
+    assert int(counter[2]) == int(ovalid.sum()), "the fused kernel must run the MLP on exactly the oracle's valid voxels"
+    multi = float((ovis.sum(-1) > 1).sum()) / max(1, int(ovalid.sum()))
+    a, b = plane.float().cpu().numpy(), oplane.reshape(-1, 128)
+    e = rel_l2(a, b)
+    print(f"fused lift vs oracle G={G} V={V} dense={dense}: valid voxels {int(ovalid.sum())} ({multi:.0%} multi-view), "
+          f"valid cells {int(opvalid.sum())}, rel_l2 {e:.2e}, max abs {np.abs(a - b).max():.3e} (max |ref| {np.abs(b).max():.3f})")
+    if dense:
+        assert multi > 0.3
+    assert e < 1e-3
+    assert not a[~opvalid.reshape(-1)].any(), "cells without a valid voxel must be zero (bev_mapper.py:86)"
+
+
 # ------------------------------------------------------------------------------------------------------------
 # V > top_k_view_selection: view selection + selective sampling (SURVEY §8a rows 8 and 10)
 # ------------------------------------------------------------------------------------------------------------

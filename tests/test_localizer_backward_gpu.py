@@ -2,15 +2,14 @@
 the GPU, against their torch emulation / torch autograd (tests/ops_emulation.py, tests/loc_torch_ref.py; both checked on
 the CPU in tests/test_localizer_backward_plan_cpu.py).
 
-NOTE: written after this round's GPU budget was spent; collected LAST and xfail(strict=False) until the first B200 run."""
+First B200 run: round 2 (green at first run)."""
 import numpy as np
 import pytest
 import torch
 
 from util import F, bf16_np, rd_bf16, rel_l2
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first B200 run pending (written after the round-1 GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.mark.parametrize("remove", [None, (1.5, 0.6)])

@@ -1,18 +1,15 @@
 """Backward kernels and the head-only training step of the 'resnet_stage' semantic decoder on the GPU.
 
-NOTE: written after this round's GPU budget was spent.  The launch plan is verified on the CPU against autograd
-(tests/test_stage_trainer_plan_cpu.py, operator layer emulated); the new CUDA kernels (csrc/train_stage.cu) have NOT run
-on a B200 yet.  The tests are therefore collected LAST (file name) and marked xfail(strict=False) until their first GPU
-run: a pass shows up as XPASS, a failure cannot mask or fail the verified suite before it.
+The launch plan is also verified on the CPU against autograd (tests/test_stage_trainer_plan_cpu.py, operator layer
+emulated).  First B200 run: round 2.
 """
 import numpy as np
 import pytest
 import torch
 
-from util import F, bf16_np, rd_bf16, rel_l2
+from util import F, bf16_np, rd_bf16, record_parity, rel_l2
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first B200 run pending (written after the round-1 GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 GT = ("road", "crosswalk", "sidewalk", "terrain", "building", "fence", "pole", "tree", "traffic_sign", "traffic_light",
       "street_light")
@@ -124,14 +121,35 @@ def test_stage_head_gradients_match_autograd():
     loss.backward()
     got_total = total.cpu().numpy()
     assert np.abs(got_total - ref_total.detach().numpy()).max() <= 2e-2 * (1 + np.abs(ref_total.detach().numpy()).max())
+    # Noise twin: the SAME oracle graph with summation-order-sized noise (1e-6 of each tensor's RMS, what a different fp32
+    # accumulation order over K = 64..576 terms produces) in front of every bf16 rounding.  Seven GroupNorm+ReLU layers
+    # turn those one-ulp flips into ReLU-mask flips, each of which re-routes a gradient path: the oracle's own gradients
+    # move by several per cent under that noise (first B200 run: the CUDA step was 0.080 away on layers_0/kernel with the
+    # fixed 5 % bound of round 1).  The CUDA gradients must be no farther from the oracle than 1.5 x the oracle is from its
+    # noise twin (+ 1e-2); the arithmetic of each backward kernel is pinned tightly, teacher-forced, by the per-kernel tests
+    # of this file (<= 1e-2 on dx, <= 1e-3 on the parameter sums).
+    gen = torch.Generator().manual_seed(5)
+    def rd_noisy(t):
+        rms = t.detach().pow(2).mean().sqrt()
+        return (t + 1e-6 * rms * torch.randn(t.shape, generator=gen)).to(torch.bfloat16).float()
+    tp2 = _tree(p, lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=F)).requires_grad_(True))
+    loss2, _ = osn.total_loss_torch(osn.stage_head_forward_torch(torch.from_numpy(feats), valid, tp2, rd_noisy),
+                                    la, va, le, mi, valid, 5, 4, *w)
+    loss2.backward()
+    twin = {path: t.grad.numpy() for path, t in _flat(tp2)}
+    worst = []
     for path, t in _flat(tp):
         g = grads
         for k in path:
             g = g[k]
         r = t.grad.numpy()
         err = np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
-        print(f"{'/'.join(path)}: |grad| {np.linalg.norm(r):.3e} rel err {err:.4f}")
-        assert g.shape == r.shape and err < 5e-2, path
+        err_twin = np.linalg.norm(twin[path] - r) / (np.linalg.norm(r) + 1e-30)
+        print(f"{'/'.join(path)}: |grad| {np.linalg.norm(r):.3e} rel err {err:.4f} (oracle vs its noise twin {err_twin:.4f})")
+        record_parity("stage head step (free-running)", "/".join(path), err, 1.5 * err_twin + 1e-2)
+        assert g.shape == r.shape
+        worst.append((err - (1.5 * err_twin + 1e-2), "/".join(path), float(err), float(err_twin)))
+    assert max(worst)[0] <= 0, max(worst)
 
 
 def test_stage_head_training_reduces_the_loss():
@@ -192,13 +210,30 @@ def test_upsample2x_backward_vs_autograd():
     ref = torch.zeros((n, h, w, C), dtype=torch.bfloat16)
     emu.upsample2x_backward(dy, n, h, w, C, ref)
     assert rel_l2(dx.float().cpu().numpy(), ref.float().numpy()) < 5e-3
-    # adjointness with the forward kernel: <up(x), dy> == <x, up^T(dy)>
+    # element-wise against fp32 autograd of the forward's definition (jax.image.resize 'bilinear' == F.interpolate with
+    # half-pixel centres): the kernel's only rounding is the final bf16 store
+    v = torch.zeros((n, C, h, w), requires_grad=True)
+    (torch.nn.functional.interpolate(v, scale_factor=2, mode="bilinear", align_corners=False)
+     * dy.float().permute(0, 3, 1, 2)).sum().backward()
+    ref32 = v.grad.permute(0, 2, 3, 1).numpy()
+    err = np.abs(dx.float().cpu().numpy() - ref32)
+    assert (err <= 2.0 ** -8 * np.abs(ref32) + 1e-6).all(), float(err.max())
+    # adjointness with the forward kernel: <up(x), dy> == <x, up^T(dy)>.  Both inner products are sums of 35,840 signed
+    # O(1) terms that cancel to O(10), and `up` / `dx` each carry one bf16 rounding (relative 2^-9, independent per
+    # element), so the two sides differ by ~2^-9 * sqrt(sum of squared terms); the round-1 form of this check compared
+    # them relative to the cancelled sum itself (|lhs| ~ 6.5) and failed on rounding noise alone (0.43 on the B200).
     x = torch.from_numpy(bf16_np(rng.standard_normal((n, h, w, C)))).to(torch.bfloat16).cuda()
     up = torch.zeros((n, 2 * h, 2 * w, C), dtype=torch.bfloat16, device="cuda")
     ops.upsample2x(x, n, h, w, C, up)
-    lhs = float((up.float() * dy.cuda().float()).sum())
-    rhs = float((x.float() * dx.float()).sum())
-    assert abs(lhs - rhs) <= 2e-2 * (abs(lhs) + 1)
+    t1, t2 = (up.double() * dy.cuda().double()), (x.double() * dx.double())
+    lhs, rhs = float(t1.sum()), float(t2.sum())
+    noise = 2.0 ** -9 * float(torch.sqrt((t1 ** 2).sum() + (t2 ** 2).sum()))
+    print(f"upsample2x adjointness: lhs {lhs:.4f} rhs {rhs:.4f} |diff| {abs(lhs - rhs):.4f} rounding noise (1 sigma) {noise:.4f}")
+    assert abs(lhs - rhs) <= 4 * noise
+    # and exactly (no rounding on either side) for the fp32 autograd pair
+    up32 = torch.nn.functional.interpolate(x.float().cpu().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                                           align_corners=False).permute(0, 2, 3, 1)
+    assert (up.float().cpu() - up32).abs().max() <= 2.0 ** -8 * up32.abs().max()
 
 
 def test_fpn_backward_vs_autograd():

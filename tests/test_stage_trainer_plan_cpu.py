@@ -2,7 +2,7 @@
 the operator layer emulated in torch (`tests/ops_emulation.py`) against torch autograd of the oracle
 (`oracle/semantic_net.py::stage_head_forward_torch`, whose forward is the NumPy `semantic_decoder` pinned against the
 reference's own `SemanticNet.__call__`): buffers, offsets, operand layouts and launch order of forward and backward.
-The CUDA kernels behind the operators are checked on the GPU (tests/test_zz_stage_trainer_gpu.py)."""
+The CUDA kernels behind the operators are checked on the GPU (tests/test_stage_trainer_gpu.py)."""
 import numpy as np
 import torch
 

@@ -5,8 +5,7 @@ row appended to the fusion MLP's first kernel; `snap_b200/streetview_encoder.py`
 oracle in tests/test_golden.py::test_unweighted_lift_equals_weighted_lift_with_zero_logits, and the oracle branch is
 pinned against the reference's own `StreetViewEncoder.__call__`.
 
-NOTE: written after this round's GPU budget was spent -- the file is named to be collected after the verified tests and
-marked xfail(strict=False) until its first run on a B200 (a pass shows up as XPASS), like tests/test_zzz_*_gpu.py.
+First B200 run: round 2 (green).
 """
 import numpy as np
 import pytest
@@ -14,8 +13,7 @@ import torch
 
 from util import F, rd_bf16, rel_l2, to_oracle_geometry
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first B200 run pending (written after the round-1 GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.mark.parametrize("V", [1, 3])

@@ -115,9 +115,56 @@ def test_voting_full_size_properties():
     assert np.array_equal(fin, np.isfinite(b)) and np.array_equal(2 * a[fin], b[fin])
     k = np.unravel_index(np.argmax(np.where(fin, a, -np.inf)), a.shape)
     assert tuple(int(x) for x in k[1:]) == (0, G - 1, G - 1)
-    # checksum of checksums: sum over all shifts of the un-normalised, un-masked correlation of rotation 0
-    # equals (sum of template) . (sum of padded map window counts) -- verified on a coarse statistic:
-    assert np.isfinite(a[fin]).all()
+    # all-valid map: no shift falls below the minimum overlap except where the template itself has too few valid cells
+    assert fin.any()
+
+
+def test_xcorr_rows_full_size_vs_direct_dot():
+    """G=128, R=36, D=32 -- the shape of the 0.95-of-roofline headline (`xcorr_rows_kernel`) -- checked NUMERICALLY:
+    12,000 randomly chosen outputs (r, u, v) against direct fp32 dot products of the SAME bf16 templates with the edge-padded
+    map (`pose_exhaustive_voting.py:83-103`: S_r[u,v] = sum_ijd q_r[i,j,d] m_pad[u+i,v+j,d] / sum q_valid_r), NumPy on the
+    CPU; and the -inf (minimum-overlap) mask of the WHOLE [36,255,255] volume bit-exact against an FFT convolution of the
+    validity masks (integers <= 16384: exact after rounding).  Tolerance <= 1e-3 * max|ref| (north_star); measured 1e-6."""
+    import scipy.signal
+    from snap_b200 import pose_exhaustive_voting as pv, types
+    G, R, D = 128, 36, 32
+    q, qv, m, mv = _planes(G, D, 11, 1)
+    grid = types.Grid2D((G, G), 0.2)
+    dev = "cuda"
+    qd, md = _t(q).to(torch.bfloat16).to(dev), _t(m).to(torch.bfloat16).to(dev)
+    qvd, mvd = torch.from_numpy(qv.astype(np.uint8)).to(dev), torch.from_numpy(mv.astype(np.uint8)).to(dev)
+    templates, t_valid = pv.sample_query_templates(qd, qvd, R, grid)
+    scores = pv.template_matching(templates, t_valid, md, mvd, kernel="rows")
+    torch.cuda.synchronize()
+    got = scores[0].cpu().numpy()
+    tq = pv.templates_to_reference_layout(templates, R)[0].float().cpu().numpy()      # [R,G,G,D], the kernel's bf16 operands
+    tv = t_valid[0].cpu().numpy().astype(bool)
+    U = 2 * G - 1
+    # -inf mask of the whole volume: cnt = true convolution of the un-flipped template validity with the zero-padded map
+    # validity (SURVEY D2), threshold 0.05 G^2 (`:100-101`)
+    thr = F(0.05 * G * G)
+    for r in range(R):
+        cnt = np.rint(scipy.signal.fftconvolve(tv[r].astype(np.float64), mv[0].astype(np.float64), mode="full"))
+        assert cnt.shape == (U, U)
+        assert np.array_equal(np.isneginf(got[r]), cnt.astype(F) <= thr), f"-inf mask differs at rotation {r}"
+    fin = np.isfinite(got)
+    assert 0.2 < fin.mean() < 1.0
+    m_pad = np.pad(m[0], ((G - 1, G - 1), (G - 1, G - 1), (0, 0)), mode="edge")       # `:83-85`
+    den = tv.reshape(R, -1).sum(-1).astype(F)
+    rng = np.random.default_rng(0)
+    cand = np.argwhere(fin)
+    pick = cand[rng.choice(len(cand), 12000, replace=False)]
+    ref = np.empty(len(pick), F)
+    for k, (r, u, v) in enumerate(pick):
+        ref[k] = np.dot(tq[r].reshape(-1), m_pad[u:u + G, v:v + G].reshape(-1)) / den[r]
+    val = got[pick[:, 0], pick[:, 1], pick[:, 2]]
+    scale = float(np.abs(ref).max())
+    err = float(np.abs(val - ref).max())
+    print(f"xcorr_rows G=128 R=36: {len(pick)} sampled outputs, max |err| {err:.3e} / max |ref| {scale:.3e} = {err / scale:.2e}; "
+          f"finite fraction {fin.mean():.3f}")
+    from util import record_parity
+    record_parity("xcorr_rows G=128 R=36", "12000 sampled (r,u,v) vs direct fp32 dot, max err / max |ref|", err / scale, 1e-3)
+    assert err <= 1e-3 * scale
 
 
 @pytest.mark.parametrize("G", [32, 64, 128])

@@ -42,3 +42,16 @@ def assert_close_bf16(out, ref, what, atol_scale=2e-3, rtol=2.0 ** -7):
     err = np.abs(out - ref)
     bad = err > rtol * np.abs(ref) + atol_scale * scale
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.size} mismatches, max err {err.max():.4g}, scale {scale:.4g}"
+
+
+def record_parity(block, what, err, tol):
+    """Appends one measured error to gpurun_out/parity_table.jsonl (the per-block error table of profiles/rNN_parity_table.md
+    is generated from it by tools/parity_table.py); silently does nothing when the directory is not writable."""
+    import json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_table.jsonl"), "a") as f:
+            f.write(json.dumps({"block": block, "what": what, "err": float(err), "tol": float(tol)}) + "\n")
+    except OSError:
+        pass
