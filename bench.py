@@ -339,7 +339,7 @@ def main():
 
     def phase_timer():
         import snap_b200.ops as ops_mod
-        names = ["lift_fused", "lift_gather_pool", "vertical_max", "gemm", "conv_gn", "gn_stats", "gn_apply", "std_weights_batched",
+        names = ["lift_fused", "lift_fused_batched", "lift_gather_pool", "vertical_max", "gemm", "conv_gn", "gn_stats", "gn_apply", "std_weights_batched",
                  "root_pack_image", "root_pack_weights", "root_conv", "maxpool3x3s2", "upsample2x", "crop_relu",
                  "match_head"]
         orig = {n: getattr(ops_mod, n) for n in names}
@@ -370,7 +370,12 @@ def main():
             for n in names:
                 setattr(ops_mod, n, orig[n])
     phase_timer()
-    if "lift_fused" in phases:
+    lift_batched = "lift_fused_batched" in phases
+    if lift_batched:
+        lift_ms, lift_desc = phases["lift_fused_batched"], ("fused camera->BEV lift, one launch per batch (lift_fused2_kernel, warp-specialised: "
+                                                            "frustum culling + projection + compaction + async gather/pool | tcgen05 fusion MLP | "
+                                                            "epilogues + z-max)")
+    elif "lift_fused" in phases:
         lift_ms, lift_desc = phases["lift_fused"], "fused camera->BEV lift (lift_fused_kernel: visibility, compaction, gather/pool, tcgen05 fusion MLP, z-max)"
     else:
         lift_ms = sum(v for k, v in phases.items() if k.startswith("lift_gather") or k.startswith("vertical_max")
@@ -379,7 +384,9 @@ def main():
     enc_plan = sve.image_encoder.plan(p["streetview_encoder"]["image_encoder"], BT * V, *IMG_HW, dev)
     hf_, wf_ = enc_plan.cropped_shapes()[-1]
     cnt = sve._buffers(dev, BT, V, *IMG_HW, hf_, wf_, G, G, Z)["counter"][0].cpu().tolist()
-    lift_ms = lift_ms / BT   # the fused lift is launched once per tile of the batch
+    lift_ms = lift_ms / BT   # per tile: one launch per tile (v1) or one launch for the BT tiles of the step (v2)
+    if lift_batched:         # the batched kernel's counters cover the whole batch
+        cnt = [c / BT for c in cnt]
     executed_flops = 2.0 * (257 * 256 + 256 * 128) * 128 * cnt[1] if cnt[1] else LIFT_FLOPS
     hbm_peak, tf_sus, tf_burst, peak_src = _peaks()
     achieved_tf = LIFT_FLOPS / (lift_ms * 1e-3) / 1e12
@@ -569,9 +576,15 @@ def main():
                          "peak_source": peak_src,
                          "ms_per_launch": lift_ms, "algorithmic_flops": LIFT_FLOPS, "algorithmic_bytes": LIFT_BYTES,
                          "executed_flops": executed_flops, "executed_tflops": executed_flops / (lift_ms * 1e-3) / 1e12,
-                         "visible_voxels": cnt[2], "voxels": G * G * Z,
-                         "worker_phase_share": dict(zip(["fill", "gather", "wait_mma1", "epilogue1", "wait_mma2", "epilogue2", "zmax"],
-                                                        [round(c / max(1, sum(cnt[4:11])), 3) for c in cnt[4:11]])),
+                         "visible_voxels": int(cnt[2]), "voxels": G * G * Z,
+                         "worker_phase_share": (
+                             {"producers": dict(zip(["cull+project", "wait_buffer", "gather+pool"],
+                                                    [round(c / max(1, sum(cnt[4:7])), 3) for c in cnt[4:7]])),
+                              "consumers": dict(zip(["wait_gemm1", "epilogue1", "wait_gemm2", "epilogue2", "zmax"],
+                                                    [round(c / max(1, sum(cnt[7:12])), 3) for c in cnt[7:12]]))}
+                             if lift_batched else
+                             dict(zip(["fill", "gather", "wait_mma1", "epilogue1", "wait_mma2", "epilogue2", "zmax"],
+                                      [round(c / max(1, sum(cnt[4:11])), 3) for c in cnt[4:11]]))),
                          "note": "achieved uses the ALGORITHMIC flops of the reference (MLP on every voxel); the kernel "
                                  "skips the MLP on voxels no camera sees (zero/invalid by streetview_encoder.py:282), so "
                                  "executed_flops < algorithmic_flops and frac may exceed the dense-GEMM ceiling",

@@ -280,6 +280,38 @@ def lift_fused_scratch_bytes() -> int:
     return int(f())
 
 
+def lift_fused_batched(p: "_lib.LiftParams", B: int, views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor,
+                       ys: torch.Tensor, zs: torch.Tensor, w1t: torch.Tensor, w256: torch.Tensor, b1: torch.Tensor,
+                       w2t: torch.Tensor, b2: torch.Tensor, plane: torch.Tensor, pvalid: torch.Tensor,
+                       counter: torch.Tensor, scratch: torch.Tensor) -> None:
+    """All B scenes in one launch of the warp-specialised lift: views [B, >= V * words] i32 (SnapLiftView tables),
+    fimg bf16 [B, rows, CF], zs f32 [B, Z], plane bf16 [B, X*Y, 128], pvalid u8 [B, X*Y]."""
+    _require(fimg, torch.bfloat16, "fimg")
+    _require(w1t, torch.bfloat16, "w1t")
+    _require(w2t, torch.bfloat16, "w2t")
+    for t, n in ((w256, "w256"), (b1, "b1"), (b2, "b2"), (zs, "zs")):
+        _require(t, torch.float32, n)
+    _require(counter, torch.int32, "counter")
+    assert w1t.shape[0] >= 256 and w2t.shape == (128, 256) and w2t.is_contiguous()
+    assert views.dim() == 2 and fimg.dim() == 3 and zs.dim() == 2 and views.shape[0] >= B and fimg.shape[0] >= B
+    assert plane.is_contiguous() and pvalid.is_contiguous()
+    view_words = C.sizeof(_lib.LiftView) // 4
+    assert views.stride(0) % view_words == 0 and views.stride(1) == 1
+    _lib.check(_lib.lib().snapb200_lift_fused_batched(
+        C.byref(p), C.c_int(B), C.c_void_p(_ptr(views)), C.c_longlong(views.stride(0) // view_words),
+        C.c_void_p(_ptr(fimg)), C.c_longlong(fimg.stride(0)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
+        C.c_void_p(_ptr(zs)), C.c_longlong(zs.stride(0)), C.c_void_p(_ptr(w1t)), C.c_longlong(w1t.stride(0)),
+        C.c_void_p(_ptr(w256)), C.c_void_p(_ptr(b1)), C.c_void_p(_ptr(w2t)), C.c_void_p(_ptr(b2)),
+        C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(pvalid)), C.c_void_p(_ptr(counter)), C.c_void_p(_ptr(scratch)),
+        C.c_size_t(scratch.numel() * scratch.element_size()), _stream()))
+
+
+def lift_fused_batched_scratch_bytes() -> int:
+    f = _lib.lib().snapb200_lift_fused_batched_scratch_bytes
+    f.restype = C.c_size_t
+    return int(f())
+
+
 def vertical_max(volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, Cc: int,
                  plane: torch.Tensor, pvalid: torch.Tensor) -> None:
     _lib.check(_lib.lib().snapb200_vertical_max(

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -135,7 +136,7 @@ class StreetViewEncoder:
             pin = lambda *s, dt: torch.zeros(s, dtype=dt).pin_memory()
             rows_img = max(V * hf * wf, 128)
             self._cache[key] = dict(
-                crop=z(rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, self.stats_ld), hid=z(N, 256),
+                crop=z(B * rows_img, 128), fimg=z(B, rows_img, 160), stats=z(N, self.stats_ld), hid=z(N, 256),
                 volume=None, valid=None,   # [B,N,128] / [B,N]: allocated on first unfused call
                 plane=z(B, X * Y, 128), pvalid=z(B, X * Y, dt=torch.uint8), counter=z(B, 16, dt=torch.int32),
                 scratch=z(ops.lift_fused_scratch_bytes(), dt=torch.uint8),
@@ -276,7 +277,23 @@ class StreetViewEncoder:
         if not fused and buf["volume"] is None:
             buf["volume"] = torch.zeros((B, N, 128), dtype=torch.bfloat16, device=dev)
             buf["valid"] = torch.zeros((B, N), dtype=torch.uint8, device=dev)
-        for b in range(B):
+        # The batched path: ONE crop + ONE proj GEMM + ONE launch of the warp-specialised lift for all scenes
+        # (`SNAPB200_LIFT_V=1` keeps the first-generation per-scene kernel for A/B measurements).
+        batched = fused and os.environ.get("SNAPB200_LIFT_V", "2") != "1" and B * V <= 32 and B * X * Y <= (1 << 18)
+        rows_img = buf["fimg"].shape[1]
+        if batched:
+            if rows_img == V * hf * wf:
+                ops.crop_relu(full, B * V, Hs, Ws, 128, hf, wf, self.weighted, buf["crop"])
+                ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"].view(B * rows_img, 160), m_rows=B * rows_img,
+                         bias=wts["proj_b"])
+            else:   # tiny feature maps (a scene's rows are padded to the GEMM's 128-row tile): per scene
+                for b in range(B):
+                    ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, self.weighted, buf["crop"])
+                    ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"][b], m_rows=V * hf * wf, bias=wts["proj_b"])
+            ops.lift_fused_batched(lp, B, stg["views"], buf["fimg"], buf["xs"], buf["ys"], stg["zs"], Bm[wts["fus0"]],
+                                   wts["w256"], wts["fus0_b"], Bm[wts["fus1"]], wts["fus1_b"], buf["plane"], buf["pvalid"],
+                                   buf["counter"][0], buf["scratch"])
+        for b in range(0 if not batched else B, B):
             # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`); un-weighted fusion: the crop
             # itself, widened by zero logits (see __init__)
             ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, self.weighted, buf["crop"])

@@ -9,8 +9,12 @@ F = np.float32
 
 
 def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, depth: np.ndarray, D: int = 128,
-                      depth_min_max=(1.0, 32.0)) -> torch.Tensor:
-    """fimg [V,Hf,Wf,D+S] (torch, may require grad); p2d [N,V,2] (row, col), vis [N,V], depth [N,V] -> stats [N, 2D+1]."""
+                      depth_min_max=(1.0, 32.0), rd=None) -> torch.Tensor:
+    """fimg [V,Hf,Wf,D+S] (torch, may require grad); p2d [N,V,2] (row, col), vis [N,V], depth [N,V] -> stats [N, 2D+1].
+    `rd` (optional): the half-precision materialisation of the interpolated maps and of the scores, at the points where
+    `oracle.bev_mapper.lift_scene` applies it (gradient passes straight through the casts)."""
+    if rd is None:
+        rd = lambda t: t
     V, Hf, Wf, CF = fimg.shape
     S = CF - D
     N = p2d.shape[0]
@@ -26,6 +30,7 @@ def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, dept
             c = torch.clamp(lo[..., 1] + b, 0, Wf - 1)
             w = (w1[..., 0] if a else 1 - w1[..., 0]) * (w1[..., 1] if b else 1 - w1[..., 1])
             f = f + w[..., None] * fimg[vi, r, c]                                     # [N, V, CF]
+    f = rd(f)
     feats, scales = f[..., :D], f[..., D:]
     mn, mx = depth_min_max
     d = torch.clamp(torch.from_numpy(depth.astype(F)), mn, mx)
@@ -34,7 +39,7 @@ def gather_pool_stats(fimg: torch.Tensor, p2d: np.ndarray, vis: np.ndarray, dept
     wb = c - blo
     b0 = torch.clamp(blo.long(), 0, S - 1)
     b1 = torch.clamp(blo.long() + 1, 0, S - 1)
-    score = (1 - wb) * torch.gather(scales, -1, b0[..., None])[..., 0] + wb * torch.gather(scales, -1, b1[..., None])[..., 0]
+    score = rd((1 - wb) * torch.gather(scales, -1, b0[..., None])[..., 0] + wb * torch.gather(scales, -1, b1[..., None])[..., 0])
     v = torch.from_numpy(np.ascontiguousarray(vis))
     any_v = v.any(-1)
     v_ = torch.where(any_v[:, None], v, torch.ones_like(v))                           # double-where (:150-152)
@@ -59,7 +64,7 @@ def chain_forward(svp, enc, p2d, vis, depth, V, hf, wf, cells, Z, rd, tp=None, x
         x = torch.from_numpy(enc).requires_grad_(True)
     crop = torch.relu(x)
     fimg = rd(rd(crop @ tp["proj_mlp"]["Dense_0"]["kernel"]) + tp["proj_mlp"]["Dense_0"]["bias"])
-    stats = rd(gather_pool_stats(fimg.reshape(V, hf, wf, -1), p2d, vis, depth))
+    stats = rd(gather_pool_stats(fimg.reshape(V, hf, wf, -1), p2d, vis, depth, rd=rd))
     hid = torch.relu(rd(rd(stats @ tp["fusion_mlp"]["Dense_0"]["kernel"]) + tp["fusion_mlp"]["Dense_0"]["bias"]))
     vol = rd(rd(hid @ tp["fusion_mlp"]["Dense_1"]["kernel"]) + tp["fusion_mlp"]["Dense_1"]["bias"])
     valid = torch.from_numpy(vis.any(-1))

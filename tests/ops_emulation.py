@@ -227,7 +227,7 @@ def make_lift_emulation(p2d, vis, depth, more=None):
     def lift_gather_pool(lp, views, fimg, xs, ys, zs, stats, valid, dbg_vis=None, dbg_taps=None):
         N = lp.X * lp.Y * lp.Z
         sp2d, svis, sdepth = scenes[N]
-        st = gather_pool_stats(fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF), sp2d, svis, sdepth, lp.D)
+        st = gather_pool_stats(fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF), sp2d, svis, sdepth, lp.D, rd=_rd)
         stats[:N].zero_()
         stats[:N, : st.shape[1]] = st.to(stats.dtype)
         valid[:N] = torch.from_numpy(svis.any(-1).astype(np.uint8))
@@ -236,7 +236,7 @@ def make_lift_emulation(p2d, vis, depth, more=None):
         N = lp.X * lp.Y * lp.Z
         sp2d, svis, sdepth = scenes[N]
         f = fimg.float().reshape(lp.V, lp.Hf, lp.Wf, lp.CF).clone().requires_grad_(True)
-        st = gather_pool_stats(f, sp2d, svis, sdepth, lp.D)
+        st = gather_pool_stats(f, sp2d, svis, sdepth, lp.D, rd=_rd)
         (st * dstats[:N, : st.shape[1]].float()).sum().backward()
         gimg += f.grad.reshape(gimg.shape)
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import F, assert_close_bf16, bf16_np, rd_bf16, rel_l2, to_oracle_geometry
+from util import F, assert_close_bf16, bf16_np, rd_bf16, record_parity, rel_l2, to_oracle_geometry
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
@@ -235,6 +235,14 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
     torch.cuda.synchronize()
     assert torch.equal(pv, pv_ref), "valid plane differs"
     assert int(counter[2]) == int(valid.sum()), "fused kernel must process exactly the visible voxels"
+    # second-generation kernel: same rounding points -> bit-identical to the first-generation kernel
+    plane2 = torch.full((1, G * G, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    pv2 = torch.full((1, G * G), 9, dtype=torch.uint8, device=dev)
+    ops.lift_fused_batched(lp, 1, views.view(1, -1), fimg.view(1, V * hf * wf, 160), xs_d, ys_d, zs_d.view(1, -1), bank.b_mats[w0],
+                           w256, b1, bank.b_mats[w1], b2, plane2, pv2, counter, scratch)
+    torch.cuda.synchronize()
+    assert torch.equal(pv2[0], pv_ref) and int(counter[2]) == int(valid.sum())
+    assert torch.equal(plane2[0], plane), "v2 kernel differs from the v1 kernel"
     a, b = plane.float().cpu().numpy(), plane_ref.float().cpu().numpy()
     ne = a != b
     print(f"G={G} V={V}: valid cells {int(pv_ref.sum())}, differing elements {ne.mean():.5%}, rel_l2 {rel_l2(a, b):.2e}")
@@ -242,9 +250,11 @@ def test_fused_lift_equals_unfused_path(G, V, hw_img):
     assert np.abs(a - b).max() <= 2.0 ** -6 * np.abs(b).max()
 
 
+@pytest.mark.parametrize("kernel", ["v2", "v1"])
 @pytest.mark.parametrize("G,V,hw_img,dense", [(24, 3, (64, 96), False), (64, 2, (224, 224), False), (32, 4, (96, 128), True)])
-def test_fused_lift_vs_oracle(G, V, hw_img, dense):
-    """The DEFAULT product kernel (`lift_fused_kernel`) against the CPU oracle directly (not against the unfused CUDA path):
+def test_fused_lift_vs_oracle(G, V, hw_img, dense, kernel):
+    """The DEFAULT product kernel (v2 = `lift_fused2_kernel`, warp-specialised, batched; v1 = `lift_fused_kernel`, the
+    first-generation per-scene kernel kept for A/B runs) against the CPU oracle directly (not against the unfused CUDA path):
     `oracle.bev_mapper.lift_scene` (streetview_encoder.py:232-286) + `vertical_pooling_max` (bev_mapper.py:56-88) in
     bf16-emulation mode on identical bf16 feature maps / weights.  valid plane bit-exact; floats <= 1e-3 relative L2
     (north_star), measured 1e-4 .. 3e-4 (profiles/r02_parity_table.md).  `dense`: cameras packed so that most voxels are seen
@@ -272,9 +282,16 @@ def test_fused_lift_vs_oracle(G, V, hw_img, dense):
     pv = torch.full((G * G,), 9, dtype=torch.uint8, device=dev)
     counter = torch.zeros(16, dtype=torch.int32, device=dev)
     scratch = torch.zeros(ops.lift_fused_scratch_bytes(), dtype=torch.uint8, device=dev)
-    ops.lift_fused(lp, views, _t(fimg_np).to(torch.bfloat16).to(dev), _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev),
-                   bank.b_mats[w0], _t(fp["Dense_0"]["kernel"][256]).to(dev), b1, bank.b_mats[w1], b2, plane, pv, counter,
-                   scratch)
+    fimg = _t(fimg_np).to(torch.bfloat16).to(dev)
+    w256 = _t(fp["Dense_0"]["kernel"][256]).to(dev)
+    if kernel == "v1":
+        ops.lift_fused(lp, views, fimg, _t(xs).to(dev), _t(ys).to(dev), _t(zs[0]).to(dev), bank.b_mats[w0], w256, b1,
+                       bank.b_mats[w1], b2, plane, pv, counter, scratch)
+    else:
+        for _ in range(2):   # twice: re-entrant on the same buffers
+            ops.lift_fused_batched(lp, 1, views.view(1, -1), fimg.view(1, V * hf * wf, 160), _t(xs).to(dev), _t(ys).to(dev),
+                                   _t(zs[:1]).to(dev), bank.b_mats[w0], w256, b1, bank.b_mats[w1], b2, plane.view(1, G * G, 128),
+                                   pv.view(1, G * G), counter, scratch)
     torch.cuda.synchronize()
     ocam, oT = to_oracle_geometry(data, 0)
     ocam = ocam.scale(np.asarray([0.25, 0.25], dtype=F))
@@ -286,12 +303,67 @@ def test_fused_lift_vs_oracle(G, V, hw_img, dense):
     multi = float((ovis.sum(-1) > 1).sum()) / max(1, int(ovalid.sum()))
     a, b = plane.float().cpu().numpy(), oplane.reshape(-1, 128)
     e = rel_l2(a, b)
-    print(f"fused lift vs oracle G={G} V={V} dense={dense}: valid voxels {int(ovalid.sum())} ({multi:.0%} multi-view), "
+    record_parity("fused lift " + kernel, f"plane rel-L2 vs oracle, G={G} V={V} dense={dense}", e, 1e-3)
+    print(f"fused lift {kernel} vs oracle G={G} V={V} dense={dense}: valid voxels {int(ovalid.sum())} ({multi:.0%} multi-view), "
           f"valid cells {int(opvalid.sum())}, rel_l2 {e:.2e}, max abs {np.abs(a - b).max():.3e} (max |ref| {np.abs(b).max():.3f})")
     if dense:
         assert multi > 0.3
     assert e < 1e-3
     assert not a[~opvalid.reshape(-1)].any(), "cells without a valid voxel must be zero (bev_mapper.py:86)"
+
+
+def test_fused_lift_batched_scenes_equal_single_scene_launches():
+    """One launch over B = 3 scenes (different cameras, voxel heights and feature maps; tiles mix rows of neighbouring
+    scenes) must give bit-identical planes to three single-scene launches, and the full-size visibility count must equal
+    the unfused kernel's (conservative frustum culling never drops a visible voxel; G = 128, 480 x 640 cameras)."""
+    from snap_b200 import configs, ops, params, streetview_encoder as sve
+    from snap_b200.image_encoder import _WeightBank
+    G, V, hw_img, B = 128, 4, (480, 640), 3
+    hf, wf = 120, 160
+    rng = np.random.default_rng(5)
+    cfg = configs.streetview_encoder()
+    dev = "cuda"
+    fp = params.round_to_bf16(params.perturb_affine(rng, params.init_mlp(rng, 257, (256, 128))))
+    bank = _WeightBank(torch.device(dev))
+    w0 = bank.add(fp["Dense_0"]["kernel"], False, 32)
+    w1 = bank.add(fp["Dense_1"]["kernel"], False)
+    bank.finalize(); bank.run()
+    b1, b2 = _t(fp["Dense_0"]["bias"]).to(dev), _t(fp["Dense_1"]["bias"]).to(dev)
+    w256 = _t(fp["Dense_0"]["kernel"][256]).to(dev)
+    scenes = [_lift_inputs(G, hw_img, V, 30 + b) for b in range(B)]
+    xs, ys = scenes[0][3], scenes[0][4]
+    Z = scenes[0][5].shape[1]
+    lp = sve.fill_lift_params(cfg, V, hf, wf, G, G, Z, 288)
+    views = torch.stack([torch.from_numpy(sve.pack_views(d["camera"], d["T_view2scene"], 0, (4.0, 4.0))) for d, *_ in scenes]).to(dev)
+    zs = torch.stack([_t(sc[5][0]) for sc in scenes]).to(dev)
+    fimg = _t(bf16_np(rng.standard_normal((B, V * hf * wf, 160)))).to(torch.bfloat16).to(dev)
+    scratch = torch.zeros(ops.lift_fused_batched_scratch_bytes(), dtype=torch.uint8, device=dev)
+    counter = torch.zeros(16, dtype=torch.int32, device=dev)
+    plane = torch.full((B, G * G, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    pv = torch.full((B, G * G), 9, dtype=torch.uint8, device=dev)
+    xs_d, ys_d = _t(xs).to(dev), _t(ys).to(dev)
+    ops.lift_fused_batched(lp, B, views, fimg, xs_d, ys_d, zs, bank.b_mats[w0], w256, b1, bank.b_mats[w1], b2, plane, pv,
+                           counter, scratch)
+    torch.cuda.synchronize()
+    total_rows = int(counter[2])
+    single_rows = 0
+    for b in range(B):
+        p1 = torch.full((1, G * G, 128), 3.0, dtype=torch.bfloat16, device=dev)
+        v1 = torch.full((1, G * G), 5, dtype=torch.uint8, device=dev)
+        ops.lift_fused_batched(lp, 1, views[b:b + 1], fimg[b:b + 1], xs_d, ys_d, zs[b:b + 1], bank.b_mats[w0], w256, b1,
+                               bank.b_mats[w1], b2, p1, v1, counter, scratch)
+        torch.cuda.synchronize()
+        single_rows += int(counter[2])
+        assert torch.equal(v1[0], pv[b]) and torch.equal(p1[0], plane[b]), f"scene {b} differs between batched and single launch"
+        # visible voxels of the unfused kernel (no culling: every (voxel, view) pair goes through the exact projection)
+        N = G * G * Z
+        stats = torch.zeros((N, 288), dtype=torch.bfloat16, device=dev)
+        valid = torch.zeros(N, dtype=torch.uint8, device=dev)
+        ops.lift_gather_pool(lp, views[b], fimg[b], xs_d, ys_d, zs[b], stats, valid)
+        torch.cuda.synchronize()
+        assert int(valid.sum()) == int(counter[2]), "culling changed the visible set"
+        assert torch.equal(valid.view(G * G, Z).any(1).to(torch.uint8), pv[b])
+    assert total_rows == single_rows and total_rows > 100000
 
 
 # ------------------------------------------------------------------------------------------------------------
