@@ -7,7 +7,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib, configs, image_encoder, ops, streetview_encoder, types
+from . import _cache, _lib, configs, image_encoder, ops, streetview_encoder, types
 
 F = np.float32
 
@@ -24,11 +24,13 @@ class VerticalPooling:
         self.config = config if config is not None else configs.vertical_pooling()
         if self.config.pooling not in self.POOLINGS:
             raise NotImplementedError(self.config.pooling)   # bev_mapper.py:53-54
-        self._cache: Dict = {}
+        self._cache = _cache.ParamCache()
+
+    def clear_cache(self) -> None:
+        self._cache.clear()
 
     def _mlp_weights(self, params: Dict, device):
-        key = (id(params), str(device))
-        if key not in self._cache:
+        def build():
             bank = image_encoder._WeightBank(device)
             f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).reshape(-1)).to(device)
             n = 0
@@ -37,8 +39,8 @@ class VerticalPooling:
             ids = [bank.add(params["fusion_mlp"][f"Dense_{i}"]["kernel"], False) for i in range(n)]
             bias = [f32(params["fusion_mlp"][f"Dense_{i}"]["bias"]) for i in range(n)]
             bank.finalize()
-            self._cache[key] = (bank, ids, bias)
-        return self._cache[key]
+            return bank, ids, bias
+        return self._cache.lookup(params, ("mlp", str(device)), build)
 
     def apply(self, variables, feature_volume: types.FeatureVolume) -> Dict:
         f, v = feature_volume.features.contiguous(), feature_volume.valid.contiguous()
@@ -56,11 +58,9 @@ class VerticalPooling:
         elif mode in ("softmax", "weighted"):
             params = variables["params"] if "params" in variables else variables
             head = params["confidence_head"]
-            key = ("conf", id(params), str(dev))
-            if key not in self._cache:
-                self._cache[key] = (torch.from_numpy(np.ascontiguousarray(head["kernel"], dtype=F).reshape(-1)).to(dev),
-                                    float(np.asarray(head["bias"], dtype=F).reshape(-1)[0]))
-            w, b = self._cache[key]
+            w, b = self._cache.lookup(params, ("conf", str(dev)), lambda: (
+                torch.from_numpy(np.ascontiguousarray(head["kernel"], dtype=F).reshape(-1)).to(dev),
+                float(np.asarray(head["bias"], dtype=F).reshape(-1)[0])))
             pred["scores"] = torch.empty((*lead, Z), dtype=torch.float32, device=dev)
             pred["weights"] = torch.empty((*lead, Z), dtype=torch.float32, device=dev)
             ops.vertical_pool(mode, f, v, cells, Z, C, w, b, plane, pvalid, pred["scores"], pred["weights"])
@@ -118,7 +118,8 @@ class BEVMapper:
             raise ValueError("Need to create at least one input encoder.")
         if self.streetview_encoder is not None and self.aerial_encoder is not None:
             self.modality_fusion = VerticalPooling(c.modality_fusion, dtype)
-        self._cache: Dict = {}
+        self._cache: Dict = {}           # xy_bev layouts (the entry keeps the keyed array alive)
+        self._wcache = _cache.ParamCache()  # device copies of the head parameters, per parameter tree
 
     def build_xyz_grid(self, data: Dict):
         """`bev_mapper.py:159-196` (inference): separable voxel-centre coordinates, fp32, host side."""
@@ -244,12 +245,10 @@ class BEVMapper:
         plane = pred["bev_features"] = self.fuse_neural_maps(planes, train, params)
         if self.config.matching_dim is not None:  # bev_mapper.py:284-291
             dev = plane.features.device
-            key = (id(params), str(dev))
-            if key not in self._cache:
-                mp = params["matching_proj"]
-                self._cache[key] = (torch.from_numpy(np.ascontiguousarray(mp["kernel"], dtype=F)).to(dev),
-                                    torch.from_numpy(np.ascontiguousarray(mp["bias"], dtype=F)).to(dev))
-            k, bvec = self._cache[key]
+            mp = params["matching_proj"]
+            k, bvec = self._wcache.lookup(params, ("match", str(dev)), lambda: (
+                torch.from_numpy(np.ascontiguousarray(mp["kernel"], dtype=F)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(mp["bias"], dtype=F)).to(dev)))
             f = plane.features.contiguous()
             cells = f.numel() // f.shape[-1]
             out = torch.empty((*f.shape[:-1], self.config.matching_dim), dtype=torch.bfloat16, device=dev)
@@ -257,12 +256,10 @@ class BEVMapper:
             pred["bev_matching"] = types.FeaturePlane(features=out, valid=plane.valid)
         if self.config.add_confidence:  # bev_mapper.py:292-295
             dev = plane.features.device
-            key = ("conf", id(params), str(dev))
-            if key not in self._cache:
-                head = params["confidence_head"]["layers_0"]
-                self._cache[key] = (torch.from_numpy(np.ascontiguousarray(head["kernel"], dtype=F).reshape(-1)).to(dev),
-                                    float(np.asarray(head["bias"], dtype=F).reshape(-1)[0]))
-            cw, cb = self._cache[key]
+            head = params["confidence_head"]["layers_0"]
+            cw, cb = self._wcache.lookup(params, ("conf", str(dev)), lambda: (
+                torch.from_numpy(np.ascontiguousarray(head["kernel"], dtype=F).reshape(-1)).to(dev),
+                float(np.asarray(head["bias"], dtype=F).reshape(-1)[0])))
             f = plane.features.contiguous()
             conf = torch.empty(f.shape[:-1], dtype=torch.float32, device=dev)
             ops.confidence(f, plane.valid.contiguous(), f.numel() // f.shape[-1], f.shape[-1], cw, cb, conf)

@@ -6,7 +6,7 @@
 //                          shared-memory staging ring, one pair ahead) + depth score + multi-view softmax pooling ->
 //                          statistics tile A[128 x 256] in 128B-swizzled shared memory (double-buffered)
 //   MMA issuer (1 thread)  tcgen05 GEMM1 (A x W1^T -> TMEM, W1 streamed as 8 chunks of 16 KB), GEMM2 (H x W2^T)
-//   TMA producer (1 thread) weight chunks through a 3-slot ring
+//   TMA producer (1 thread) weight chunks through a 2-slot ring
 //   consumers (4 warps, one per TMEM lane quadrant)  epilogue 1 (rank-1 score term, bias, ReLU -> H written over A),
 //                          epilogue 2 (bias) -> staged volume rows -> running max over z per BEV column ->
 //                          plane[B, X*Y, 128] + valid[B, X*Y]
@@ -44,21 +44,24 @@ constexpr int F2_MAX_VIEWS_TOTAL = 32;             // B * V per launch
 constexpr int F2_NHW = 2 * F2_NP;                  // half-warps that gather (one tile row each per iteration)
 constexpr int F2_NIT = (128 + F2_NHW - 1) / F2_NHW;  // 7 row iterations per tile
 constexpr int F2_NROUND = (F2_NIT + 3) / 4;        // record-prefetch rounds of 4 iterations
-constexpr int F2_WSLOTS = 3;                       // weight ring slots (16 KB each)
-constexpr int F2_GSLOTS = 2;                       // gather staging slots per half-warp (1 KB each)
+constexpr int F2_WSLOTS = 2;                       // weight ring slots (16 KB each)
+constexpr int F2_GSLOTS = 2;                       // gather staging slots per half-warp
+constexpr int F2_GSLOT_BYTES = 1088;               // 4 taps x 256 B of features + 16 x 4 B depth-score words
 static_assert((2 + F2_NP) % 4 == 0, "consumer warps must start at a multiple of 4 (TMEM lane quadrants)");
 
 constexpr int S2_A = 0;                                      // 2 x A / H / volume staging [128 x 256] bf16   (131072)
-constexpr int S2_W = 131072;                                 // weight ring                                  ( 49152)
-constexpr int S2_STG = S2_W + F2_WSLOTS * 16384;             // gather staging                               ( 40960)
-constexpr int S2_LIST = S2_STG + F2_NHW * F2_GSLOTS * 1024;  // uint32[F2_LIST_CAP]
+constexpr int S2_W = 131072;                                 // weight ring
+constexpr int S2_STG = S2_W + F2_WSLOTS * 16384;             // gather staging
+constexpr int S2_LIST = S2_STG + F2_NHW * F2_GSLOTS * F2_GSLOT_BYTES;  // uint32[F2_LIST_CAP]
 constexpr int S2_SMAX = S2_LIST + 4 * F2_LIST_CAP;           // bf16[2][128]
 constexpr int S2_RCOL = S2_SMAX + 512;                       // uint32[2][128] global BEV column of every tile row
 constexpr int S2_CTL = S2_RCOL + 1024;
 constexpr int S2_VIEW = S2_CTL + 512;                        // LiftView[32]
-constexpr int S2_CULL = S2_VIEW + 3072;                      // CullView[32]
-constexpr int F2_SMEM_BYTES = S2_CULL + 2688;
-static_assert(sizeof(LiftView) * F2_MAX_VIEWS_TOTAL <= 3072, "view table");
+constexpr int S2_CULL = S2_VIEW + 2944;                      // CullView[32]
+constexpr int S2_TBL = S2_CULL + 2688;                       // epilogue tables: w256 f32[256], b1 bf16x2[128], b2 bf16x2[64]
+constexpr int F2_SMEM_BYTES = S2_TBL + 1024 + 512 + 256;
+static_assert(sizeof(LiftView) * F2_MAX_VIEWS_TOTAL <= 2944, "view table");
+static_assert(S2_STG % 16 == 0 && F2_GSLOT_BYTES % 16 == 0 && S2_TBL % 16 == 0, "16-byte aligned staging / tables");
 static_assert(F2_SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 constexpr int VOL2_STRIDE = 272;                             // bytes per staged volume row (256 + 16)
 constexpr int S2_BREC = 128 * VOL2_STRIDE;                   // z-max boundary records inside the tile buffer
@@ -98,12 +101,12 @@ struct Fused2Args {
 struct Ctl2 {
   uint64_t a_full[2], a_empty[2], w_full[F2_WSLOTS], w_empty[F2_WSLOTS], acc1_full, acc1_empty, h_full[4], acc2_full;
   uint32_t tmem_ptr;
-  int batch_col0;
+  int batch_col0[2];   // claimed visibility batches, double-buffered (one producer barrier per batch)
   // tiles announced by the producers / no more tiles: plain counters polled by the TMA thread (an mbarrier would lose a
   // phase when the producers run two tiles ahead of it)
   int ann_tiles, ann_done;
   int rows[2];
-  int warp_cnt[F2_NP];
+  int warp_cnt[2][F2_NP];
 };
 static_assert(sizeof(Ctl2) <= 512, "control block");
 
@@ -112,10 +115,61 @@ __device__ __forceinline__ void cbar() { asm volatile("bar.sync 2, %0;" ::"n"(F2
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint2 hmax2x2(uint2 a, uint2 b) { return make_uint2(hmax2_bf16(a.x, b.x), hmax2_bf16(a.y, b.y)); }
+
+// weighted pooling of >= 2 views (streetview_encoder.py:156-164): softmax over the visible views' scores (shifted by
+// max(0, max score), A.6), mean = sum w f, var = sum w (f - mean)^2 in fp32 -> feature dtype; score_max.
+__device__ __forceinline__ void pool_views(const uint32_t (&fvp)[F2_MAXV][4], const float (&score)[F2_MAXV], int nv,
+                                        uint32_t (&mean_p)[4], uint32_t (&var_p)[4], float& smaxv) {
+  float mean[8], var[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) mean[jj] = var[jj] = 0.f;
+  float mx = 0.f;
+  smaxv = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < F2_MAXV; ++k)
+    if (k < nv) {
+      mx = fmaxf(mx, score[k]);
+      smaxv = fmaxf(smaxv, score[k]);
+    }
+  float wv[F2_MAXV], den = 0.f;
+#pragma unroll
+  for (int k = 0; k < F2_MAXV; ++k) {
+    wv[k] = (k < nv) ? expf(score[k] - mx) : 0.f;
+    den += wv[k];
+  }
+#pragma unroll
+  for (int k = 0; k < F2_MAXV; ++k) {
+    if (k >= nv) continue;
+    wv[k] = __fdiv_rn(wv[k], den);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      mean[2 * jj] += wv[k] * bf16_lo(fvp[k][jj]);
+      mean[2 * jj + 1] += wv[k] * bf16_hi(fvp[k][jj]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < F2_MAXV; ++k) {
+    if (k >= nv) continue;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float da = bf16_lo(fvp[k][jj]) - mean[2 * jj], db = bf16_hi(fvp[k][jj]) - mean[2 * jj + 1];
+      var[2 * jj] += wv[k] * da * da;
+      var[2 * jj + 1] += wv[k] * db * db;
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    mean_p[jj] = pack_bf16(mean[2 * jj], mean[2 * jj + 1]);
+    var_p[jj] = pack_bf16(var[2 * jj], var[2 * jj + 1]);
+  }
+}
 
 __global__ void __launch_bounds__(F2_THREADS, 1)
 lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -128,6 +182,9 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   uint32_t* rowcol = reinterpret_cast<uint32_t*>(smem + S2_RCOL);
   LiftView* sview = reinterpret_cast<LiftView*>(smem + S2_VIEW);
   CullView* scull = reinterpret_cast<CullView*>(smem + S2_CULL);
+  float* tbl_w256 = reinterpret_cast<float*>(smem + S2_TBL);                 // W1[256, :] (score_max input row)
+  uint32_t* tbl_b1 = reinterpret_cast<uint32_t*>(smem + S2_TBL + 1024);      // b1 as packed bf16 pairs
+  uint32_t* tbl_b2 = reinterpret_cast<uint32_t*>(smem + S2_TBL + 1536);      // b2 as packed bf16 pairs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled operands need a 1024 B aligned base
@@ -138,6 +195,10 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     const int sc = v / P.V, vv = v - sc * P.V;
     reinterpret_cast<uint32_t*>(sview)[i] = reinterpret_cast<const uint32_t*>(A.views + (size_t)sc * A.views_stride + vv)[w];
   }
+  // epilogue constants: there is next to no L1 beside 226 KB of shared memory, so a per-chunk __ldg is an L2 round trip
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) tbl_w256[i] = A.w256[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) tbl_b1[i] = pack_bf16(A.b1[2 * i], A.b1[2 * i + 1]);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) tbl_b2[i] = pack_bf16(A.b2[2 * i], A.b2[2 * i + 1]);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -278,8 +339,8 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     const float score_scale = (float)(P.S - 1);
     const unsigned FULL = 0xffffffffu;
     TapRec2* const my_scratch = A.scratch + (size_t)blockIdx.x * F2_LIST_CAP * F2_MAXV;
-    const uint32_t stage_base = smem_u32(smem + S2_STG + hw * (F2_GSLOTS * 1024));
-    const uint8_t* const stage_ptr = smem + S2_STG + hw * (F2_GSLOTS * 1024);
+    const uint32_t stage_base = smem_u32(smem + S2_STG + hw * (F2_GSLOTS * F2_GSLOT_BYTES));
+    const uint8_t* const stage_ptr = smem + S2_STG + hw * (F2_GSLOTS * F2_GSLOT_BYTES);
     int list_head = 0, list_count = 0;       // replicated in every producer thread (same decisions)
     bool cols_done = false;
     int n_tiles = 0, n_rows = 0;
@@ -292,17 +353,22 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
     tmark = now_;                            \
   } while (0)
 
-    if (ptid == 0) ctl->batch_col0 = atomicAdd(A.col_counter, F2_BATCH_COLS);  // first batch claim
+    if (ptid == 0) ctl->batch_col0[0] = atomicAdd(A.col_counter, F2_BATCH_COLS);  // first batch claim
+    uint32_t bpar = 0;   // parity of the batch being processed (selects batch_col0 / warp_cnt copies)
+    pbar();
 
     for (uint32_t tile = 0;; ++tile) {
       // ---------- visibility batches until >= 128 visible voxels are pending ----------
+      // One producer barrier per batch: the claim of batch n + 1 (a global atomic, requested before the projection work
+      // of batch n and stored just before the barrier) and the per-warp counts are double-buffered by batch parity.
       while (list_count < 128 && !cols_done) {
-        pbar();  // batch_col0 of this round visible; previous readers of warp_cnt are done
-        const int c0 = ctl->batch_col0;
+        const int c0 = ctl->batch_col0[bpar];
         if (c0 >= total_cols) {
           cols_done = true;
           break;
         }
+        int next_claim = 0;
+        if (ptid == 0) next_claim = atomicAdd(A.col_counter, F2_BATCH_COLS);
         const int cl = ptid >> 6, z = ptid & 63;
         const int gcol = c0 + cl;
         float prow[F2_MAXV], pcol[F2_MAXV], pdep[F2_MAXV];
@@ -342,13 +408,13 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         }
         const bool valid = vm != 0;
         const uint32_t bal = __ballot_sync(FULL, valid);
-        if (lane == 0) ctl->warp_cnt[pw] = __popc(bal);
+        if (lane == 0) ctl->warp_cnt[bpar][pw] = __popc(bal);
+        if (ptid == 0) ctl->batch_col0[bpar ^ 1] = next_claim;
         pbar();
-        if (ptid == 0) ctl->batch_col0 = atomicAdd(A.col_counter, F2_BATCH_COLS);  // everyone has read c0
         int before = 0, tot = 0;
 #pragma unroll
         for (int w2 = 0; w2 < F2_NP; ++w2) {
-          const int c = ctl->warp_cnt[w2];
+          const int c = ctl->warp_cnt[bpar][w2];
           tot += c;
           if (w2 < pw) before += c;
         }
@@ -374,6 +440,7 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           }
         }
         list_count += tot;
+        bpar ^= 1;
       }
       F2_MARK(tprof, 0);
 
@@ -431,49 +498,53 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
         const uint32_t pvm = pvm_n;
         const uint4 pq0 = pq0_n, pq1 = pq1_n;
         if (round + 1 < F2_NROUND) prefetch_records(round + 1);
-        // per-iteration visible-view counts: own half / maximum of the two halves (warp-uniform)
-        int nv_own[4], nv_any[4];
+        // per-iteration visible-view counts, 4 bits per iteration: own half / maximum of the two halves (warp-uniform)
+        uint32_t nvo_p = 0u, nva_p = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t vmj = __shfl_sync(FULL, pvm, (lane & 16) + 4 * j);
-          nv_own[j] = __popc(vmj);
-          nv_any[j] = max(nv_own[j], __shfl_xor_sync(FULL, nv_own[j], 16));
+          const uint32_t o = (uint32_t)__popc(__shfl_sync(FULL, pvm, (lane & 16) + 4 * j));
+          const uint32_t a = max(o, __shfl_xor_sync(FULL, o, 16));
+          nvo_p |= o << (4 * j);
+          nva_p |= a << (4 * j);
         }
-        // issue the asynchronous tap copies of step (j, k) into staging slot `gs`; returns the raw depth-score tap
-        auto issue = [&](int j, int k, int gs) -> uint32_t {
+        // issue the asynchronous copies of step (j, k) -- four 256-byte feature taps and the 8 depth-score taps (4 taps x
+        // 2 bins, one 4-byte word each on the first 8 lanes of the half) -- into staging slot `gs`
+        auto issue = [&](int j, int k, int gs) {
           const int src = (lane & 16) + 4 * j + k;
           const uint32_t x0 = __shfl_sync(FULL, pq0.x, src), x1 = __shfl_sync(FULL, pq0.y, src);
           const uint32_t x2 = __shfl_sync(FULL, pq0.z, src), x3 = __shfl_sync(FULL, pq0.w, src);
           const uint32_t y3 = __shfl_sync(FULL, pq1.w, src);
-          const int own = __popc(__shfl_sync(FULL, pvm, (lane & 16) + 4 * j));
-          uint32_t sraw = 0u;
+          const int own = (int)((nvo_p >> (4 * j)) & 15u);
           if (k < own) {
-            const uint32_t dst = stage_base + gs * 1024 + l16 * 16;
+            const uint32_t dst = stage_base + gs * F2_GSLOT_BYTES + l16 * 16;
             cp_async16(dst, A.fimg + x0 + l16 * 8);
             cp_async16(dst + 256, A.fimg + x1 + l16 * 8);
             cp_async16(dst + 512, A.fimg + x2 + l16 * 8);
             cp_async16(dst + 768, A.fimg + x3 + l16 * 8);
-            if (l16 < 8) {  // depth-score taps: 4 taps x 2 bins on the first 8 lanes of the half
+            if (l16 < 8) {
               const int tap = l16 >> 1;
               const uint32_t xt = (tap & 2) ? ((tap & 1) ? x3 : x2) : ((tap & 1) ? x1 : x0);
               const uint32_t bin = (l16 & 1) ? (y3 >> 16) : (y3 & 0xffffu);
-              sraw = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(A.fimg + xt + P.D + bin));
+              // the aligned 32-bit word that holds the bf16 logit (tap offsets and D are even: its half is bin & 1)
+              cp_async4(stage_base + gs * F2_GSLOT_BYTES + 1024 + l16 * 4, A.fimg + xt + P.D + (bin & ~1u));
             }
           }
           cp_async_commit();
-          return sraw;
         };
-        // first step of the round
+        auto next_row = [&](int j) {  // next iteration of this round with at least one pair, or 4
+          int nj = j + 1;
+          while (nj < 4 && ((nva_p >> (4 * nj)) & 15u) == 0u) ++nj;
+          return nj;
+        };
         int gs = 0;
-        uint32_t sraw_cur = 0u;
-        // the loops below are written with static j / k so that every register array is indexed statically
-        bool primed = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = hw + F2_NHW * (4 * round + j);  // this half-warp's row
-          const int nva = nv_any[j];
-          const int nv = nv_own[j];
-          if (nva == 0) continue;                        // warp-uniform: both halves are past the end of the tile
+        int cj = next_row(-1);
+        if (cj < 4) issue(cj, 0, gs);
+#pragma unroll 1
+        while (cj < 4) {
+          const int r = hw + F2_NHW * (4 * round + cj);  // this half-warp's row
+          const int nva = (int)((nva_p >> (4 * cj)) & 15u);
+          const int nv = (int)((nvo_p >> (4 * cj)) & 15u);
+          const int nj = next_row(cj);
           uint32_t fvp[F2_MAXV][4];
           float score[F2_MAXV];
 #pragma unroll
@@ -482,40 +553,29 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) fvp[k][jj] = 0u;
           }
-          if (!primed) {
-            sraw_cur = issue(j, 0, gs);
-            primed = true;
-          }
 #pragma unroll
           for (int k = 0; k < F2_MAXV; ++k) {
             if (k >= nva) break;  // warp-uniform
-            // next step: (j, k + 1) or the first view of the next non-empty iteration of this round
-            uint32_t sraw_next = 0u;
+            // next step: (cj, k + 1) or the first view of the next non-empty iteration of this round
             {
-              int nj = j, nk = k + 1;
-              if (nk >= nva) {
-                nk = 0;
-                nj = j + 1;
-#pragma unroll
-                for (int t = 1; t < 4; ++t)
-                  if (t > j && nj == t && nv_any[t] == 0) nj = t + 1;
-              }
-              if (nj < 4)
-                sraw_next = issue(nj, nk, gs ^ 1);
+              const bool same = k + 1 < nva;
+              const int ij = same ? cj : nj, ik = same ? k + 1 : 0;
+              if (ij < 4)
+                issue(ij, ik, gs ^ 1);
               else
                 cp_async_commit();
             }
-            cp_async_wait<1>();  // the copies of step (j, k) have landed (this thread reads only what it copied itself)
-            const int src = (lane & 16) + 4 * j + k;
+            cp_async_wait<1>();  // the copies of step (cj, k) have landed (this thread reads only what it copied itself)
+            const int src = (lane & 16) + 4 * cj + k;
             const uint32_t y0 = __shfl_sync(FULL, pq1.x, src), y1 = __shfl_sync(FULL, pq1.y, src);
-            const uint32_t y2 = __shfl_sync(FULL, pq1.z, src);
+            const uint32_t y2 = __shfl_sync(FULL, pq1.z, src), y3 = __shfl_sync(FULL, pq1.w, src);
             const bool mine = k < nv;
             float sp = 0.f, wb1 = 0.f;
             if (mine) {
               const float wr1 = __uint_as_float(y0), wc1 = __uint_as_float(y1);
               wb1 = __uint_as_float(y2);
               const float wr0 = __fadd_rn(1.0f, -wr1), wc0 = __fadd_rn(1.0f, -wc1);
-              const uint8_t* sp_ = stage_ptr + gs * 1024 + l16 * 16;
+              const uint8_t* sp_ = stage_ptr + gs * F2_GSLOT_BYTES + l16 * 16;
               const uint4 u00 = *reinterpret_cast<const uint4*>(sp_);
               const uint4 u01 = *reinterpret_cast<const uint4*>(sp_ + 256);
               const uint4 u10 = *reinterpret_cast<const uint4*>(sp_ + 512);
@@ -526,7 +586,9 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
               if (l16 < 8) {
                 const int tap = l16 >> 1;
                 const float wt = ((tap & 2) ? wr1 : 1.0f - wr1) * ((tap & 1) ? wc1 : 1.0f - wc1);
-                sp = wt * __uint_as_float(sraw_cur << 16);
+                const uint32_t word = *reinterpret_cast<const uint32_t*>(stage_ptr + gs * F2_GSLOT_BYTES + 1024 + l16 * 4);
+                const uint32_t bin = (l16 & 1) ? (y3 >> 16) : (y3 & 0xffffu);
+                sp = wt * ((bin & 1u) ? bf16_hi(word) : bf16_lo(word));
               }
               const uint32_t a00[4] = {u00.x, u00.y, u00.z, u00.w}, a01[4] = {u01.x, u01.y, u01.z, u01.w};
               const uint32_t a10[4] = {u10.x, u10.y, u10.z, u10.w}, a11[4] = {u11.x, u11.y, u11.z, u11.w};
@@ -548,7 +610,6 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
             sp += __shfl_xor_sync(FULL, sp, 1);
             score[k] = __shfl_sync(FULL, bf16_round(sp), lane & 16);  // broadcast from the half's lane 0
             gs ^= 1;
-            sraw_cur = sraw_next;
           }
           if (r < rows) {
             uint32_t mean_p[4], var_p[4];
@@ -564,48 +625,7 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
               }
               smaxv = ssum;
             } else {
-              float mean[8], var[8];
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) mean[jj] = var[jj] = 0.f;
-              float mx = 0.f;
-              smaxv = -INFINITY;
-#pragma unroll
-              for (int k = 0; k < F2_MAXV; ++k)
-                if (k < nv) {
-                  mx = fmaxf(mx, score[k]);
-                  smaxv = fmaxf(smaxv, score[k]);
-                }
-              float wv[F2_MAXV], den = 0.f;
-#pragma unroll
-              for (int k = 0; k < F2_MAXV; ++k) {
-                wv[k] = (k < nv) ? expf(score[k] - mx) : 0.f;
-                den += wv[k];
-              }
-#pragma unroll
-              for (int k = 0; k < F2_MAXV; ++k) {
-                if (k >= nv) continue;
-                wv[k] = __fdiv_rn(wv[k], den);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  mean[2 * jj] += wv[k] * bf16_lo(fvp[k][jj]);
-                  mean[2 * jj + 1] += wv[k] * bf16_hi(fvp[k][jj]);
-                }
-              }
-#pragma unroll
-              for (int k = 0; k < F2_MAXV; ++k) {
-                if (k >= nv) continue;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  const float da = bf16_lo(fvp[k][jj]) - mean[2 * jj], db = bf16_hi(fvp[k][jj]) - mean[2 * jj + 1];
-                  var[2 * jj] += wv[k] * da * da;
-                  var[2 * jj + 1] += wv[k] * db * db;
-                }
-              }
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                mean_p[jj] = pack_bf16(mean[2 * jj], mean[2 * jj + 1]);
-                var_p[jj] = pack_bf16(var[2 * jj], var[2 * jj + 1]);
-              }
+              pool_views(fvp, score, nv, mean_p, var_p, smaxv);
             }
             // A[r][k]: mean at k = 8*l16.., var at k = 128 + 8*l16..; K-chunk of 64, 16-byte slot (k%64)/8 XOR (r%8)
             // inside the 128-byte row (SWIZZLE_128B, as TMA would write it)
@@ -617,6 +637,7 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
                 make_uint4(var_p[0], var_p[1], var_p[2], var_p[3]);
             if (l16 == 0) smax_s[b * 128 + r] = __float2bfloat16(smaxv);
           }
+          cj = nj;
         }
         cp_async_wait<0>();
       }
@@ -658,28 +679,30 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       {
         const float sm = __bfloat162float(smax_s[b * 128 + row]);
         const uint32_t taddr = tmem_acc1 + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+        uint32_t v[2][16];
+        tmem_ld16(taddr, v[0]);
+#pragma unroll
         for (int c16 = 0; c16 < 16; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
           tmem_ld_wait();
+          if (c16 + 1 < 16) tmem_ld16(taddr + (uint32_t)((c16 + 1) * 16), v[(c16 + 1) & 1]);
           if (c16 == 15) {  // acc1 is drained: GEMM1 of the next tile may overwrite it
             tc_fence_before_sync();
             mbar_arrive(&ctl->acc1_empty);
           }
+          const uint32_t(&vv)[16] = v[c16 & 1];
           const int n0 = c16 * 16;
           uint32_t h[8];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w256 + n0) + j4);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.b1 + n0) + j4);
+            const float4 w4 = *reinterpret_cast<const float4*>(tbl_w256 + n0 + 4 * j4);
+            const uint2 b2p = *reinterpret_cast<const uint2*>(tbl_b1 + (n0 >> 1) + 2 * j4);
             // dot over all 257 inputs -> dtype, + bias -> dtype, ReLU (packed bf16 after the first rounding)
-            uint32_t p0 = pack_bf16(__fmaf_rn(sm, w4.x, __uint_as_float(v[j4 * 4 + 0])),
-                                    __fmaf_rn(sm, w4.y, __uint_as_float(v[j4 * 4 + 1])));
-            uint32_t p1 = pack_bf16(__fmaf_rn(sm, w4.z, __uint_as_float(v[j4 * 4 + 2])),
-                                    __fmaf_rn(sm, w4.w, __uint_as_float(v[j4 * 4 + 3])));
-            p0 = hadd2_bf16_rn(p0, pack_bf16(b4.x, b4.y));
-            p1 = hadd2_bf16_rn(p1, pack_bf16(b4.z, b4.w));
+            uint32_t p0 = pack_bf16(__fmaf_rn(sm, w4.x, __uint_as_float(vv[j4 * 4 + 0])),
+                                    __fmaf_rn(sm, w4.y, __uint_as_float(vv[j4 * 4 + 1])));
+            uint32_t p1 = pack_bf16(__fmaf_rn(sm, w4.z, __uint_as_float(vv[j4 * 4 + 2])),
+                                    __fmaf_rn(sm, w4.w, __uint_as_float(vv[j4 * 4 + 3])));
+            p0 = hadd2_bf16_rn(p0, b2p.x);
+            p1 = hadd2_bf16_rn(p1, b2p.y);
             h[j4 * 2 + 0] = hmax2_bf16(p0, 0u);
             h[j4 * 2 + 1] = hmax2_bf16(p1, 0u);
           }
@@ -701,21 +724,21 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       F2_MARK(tprof, 2);
       {
         const uint32_t taddr = tmem_acc2 + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+        uint32_t v[2][16];
+        tmem_ld16(taddr, v[0]);
+#pragma unroll
         for (int c16 = 0; c16 < 8; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(c16 * 16), v);
           tmem_ld_wait();
+          if (c16 + 1 < 8) tmem_ld16(taddr + (uint32_t)((c16 + 1) * 16), v[(c16 + 1) & 1]);
+          const uint32_t(&vv)[16] = v[c16 & 1];
           const int n0 = c16 * 16;
+          const uint4 ba = *reinterpret_cast<const uint4*>(tbl_b2 + (n0 >> 1));
+          const uint4 bb = *reinterpret_cast<const uint4*>(tbl_b2 + (n0 >> 1) + 4);
+          const uint32_t bp[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t o[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(A.b2 + n0) + j4);
-            o[j4 * 2 + 0] = hadd2_bf16_rn(pack_bf16(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1])),
-                                          pack_bf16(b4.x, b4.y));
-            o[j4 * 2 + 1] = hadd2_bf16_rn(pack_bf16(__uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3])),
-                                          pack_bf16(b4.z, b4.w));
-          }
+          for (int j = 0; j < 8; ++j)
+            o[j] = hadd2_bf16_rn(pack_bf16(__uint_as_float(vv[2 * j]), __uint_as_float(vv[2 * j + 1])), bp[j]);
           uint8_t* rowp = Ab + row * VOL2_STRIDE + n0 * 2;
           *reinterpret_cast<uint4*>(rowp) = make_uint4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<uint4*>(rowp + 16) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -729,24 +752,42 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
       // segments that start and end strictly inside the warp's rows are complete and written directly; the first /
       // last segment go to shared memory and are stitched (with the carry from the previous tile) by warp 0.
       {
-        const int r_lo = q * 32, r_hi = min(rows, r_lo + 32);
+        const int r_lo = q * 32;
+        const int nr = min(max(rows - r_lo, 0), 32);            // this warp's rows
+        const uint32_t mycol = lane < nr ? rowcol[b * 128 + r_lo + lane] : 0xffffffffu;
+        const uint32_t prevcol = __shfl_up_sync(0xffffffffu, mycol, 1);
+        uint32_t starts = __ballot_sync(0xffffffffu, lane < nr && (lane == 0 || mycol != prevcol));  // segment starts
         uint32_t fcol = 0xffffffffu, lcol = 0xffffffffu;
         uint2 fmax_ = make_uint2(0u, 0u), lmax_ = make_uint2(0u, 0u);
-        for (int r = r_lo; r < r_hi; ++r) {
-          const uint32_t col = rowcol[b * 128 + r];
-          const uint2 x = *reinterpret_cast<const uint2*>(Ab + r * VOL2_STRIDE + lane * 8);
-          if (col != lcol) {
-            if (lcol != 0xffffffffu && lcol != fcol) {  // a middle segment just ended: complete
-              plane64[(size_t)lcol * 32 + lane] = lmax_;
-              if (lane == 0) A.pvalid[lcol] = 1;
-            }
-            if (fcol == 0xffffffffu) fcol = col;
-            lcol = col;
-            lmax_ = x;
-          } else {
-            lmax_ = hmax2x2(lmax_, x);
+        const uint8_t* base = Ab + r_lo * VOL2_STRIDE + lane * 8;
+        while (starts != 0u) {   // warp-uniform
+          const int s0 = __ffs(starts) - 1;
+          starts &= starts - 1u;
+          const int s1 = starts != 0u ? __ffs(starts) - 1 : nr;
+          const uint32_t col = __shfl_sync(0xffffffffu, mycol, s0);
+          uint2 acc = *reinterpret_cast<const uint2*>(base + s0 * VOL2_STRIDE);
+          int r = s0 + 1;
+          for (; r + 3 < s1; r += 4) {   // independent loads, max tree
+            const uint2 x0 = *reinterpret_cast<const uint2*>(base + r * VOL2_STRIDE);
+            const uint2 x1 = *reinterpret_cast<const uint2*>(base + (r + 1) * VOL2_STRIDE);
+            const uint2 x2 = *reinterpret_cast<const uint2*>(base + (r + 2) * VOL2_STRIDE);
+            const uint2 x3 = *reinterpret_cast<const uint2*>(base + (r + 3) * VOL2_STRIDE);
+            acc = hmax2x2(acc, hmax2x2(hmax2x2(x0, x1), hmax2x2(x2, x3)));
           }
-          if (lcol == fcol) fmax_ = lmax_;
+          for (; r < s1; ++r) acc = hmax2x2(acc, *reinterpret_cast<const uint2*>(base + r * VOL2_STRIDE));
+          const bool first = s0 == 0, last = starts == 0u;
+          if (first) {
+            fcol = col;
+            fmax_ = acc;
+          }
+          if (last) {
+            lcol = col;
+            lmax_ = acc;
+          }
+          if (!first && !last) {  // a segment that starts and ends inside this warp's rows: complete
+            plane64[(size_t)col * 32 + lane] = acc;
+            if (lane == 0) A.pvalid[col] = 1;
+          }
         }
         uint4* brA = reinterpret_cast<uint4*>(Ab + S2_BREC);
         uint2* brB = reinterpret_cast<uint2*>(Ab + S2_BREC + 2048);

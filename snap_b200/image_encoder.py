@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from . import _lib, configs, ops, types
+from . import _cache, _lib, configs, ops, types
 
 
 def _round_up(x: int, m: int) -> int:
@@ -373,13 +373,14 @@ class ImageEncoder:
         if self.config.encoder_name != "resnet":
             raise ValueError(self.config.encoder_name)  # image_encoder.py:112-113
         self.dtype = dtype
-        self._plans: Dict = {}
+        self._plans = _cache.ParamCache()
 
     def plan(self, params: Dict, n: int, H: int, W: int, device) -> EncoderPlan:
-        key = (id(params), n, H, W, str(device))
-        if key not in self._plans:
-            self._plans[key] = EncoderPlan(params, self.config, n, H, W, device, fused_gn=self.fused_gn)
-        return self._plans[key]
+        return self._plans.lookup(params, (n, H, W, str(device)),
+                                  lambda: EncoderPlan(params, self.config, n, H, W, device, fused_gn=self.fused_gn))
+
+    def clear_cache(self) -> None:
+        self._plans.clear()
 
     def apply(self, variables: Dict, image: torch.Tensor, train: bool = False) -> types.FeatureImagePyramid:
         if train:

@@ -11,7 +11,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from . import configs, image_encoder, ops, types
+from . import _cache, configs, image_encoder, ops, types
 
 F = np.float32
 
@@ -61,11 +61,13 @@ class SemanticHead:
         self.num_excl = len(c.object_classes_exclusive)
         self.num_classes = self.num_area + (self.num_excl + len(c.object_classes_independent) + 1
                                             if (c.object_classes_exclusive or c.object_classes_independent) else 0)
-        self._cache: Dict = {}
+        self._cache = _cache.ParamCache()
+
+    def clear_cache(self) -> None:
+        self._cache.clear()
 
     def _plan(self, params: Dict, B: int, G0: int, G1: int, C: int, dev):
-        key = (id(params), B, G0, G1, C, str(dev))
-        if key not in self._cache:
+        def build():
             dim = self.config.decoder_dim
             stage = _StagePlan(params["layers_1"], B, G0, G1, dim, dev)
             bank = stage.bank
@@ -80,17 +82,15 @@ class SemanticHead:
             bank.finalize()
             rows = image_encoder._round_up(max(B * G0 * G1, 128), 128)
             z = lambda c, dt=torch.bfloat16: torch.zeros((rows, c), dtype=dt, device=dev)
-            self._cache[key] = dict(stage=stage, w=w, x0=z(dim), h=z(dim), logits=z(16))
-        return self._cache[key]
+            return dict(stage=stage, w=w, x0=z(dim), h=z(dim), logits=z(16))
+        return self._cache.lookup(params, (B, G0, G1, C, str(dev)), build)
 
     def apply(self, variables: Dict, plane: types.FeaturePlane) -> Dict:
         params = variables["params"] if "params" in variables else variables
         params = params.get("decoder", params)
         if self.config.decoder_type == "mlp":                                                # :147-152
-            key = ("mlp", id(params), str(plane.features.device))
-            if key not in self._cache:
-                self._cache[key] = MLPHeadTrainer(self.config, params, plane.features.device)
-            return self._cache[key].forward(plane)
+            return self._cache.lookup(params, ("mlp", str(plane.features.device)),
+                                      lambda: MLPHeadTrainer(self.config, params, plane.features.device)).forward(plane)
         f, valid = plane.features.contiguous(), plane.valid.contiguous()
         B, G0, G1, C = f.shape
         dev = f.device

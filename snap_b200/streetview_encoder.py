@@ -16,7 +16,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib, configs, image_encoder, ops, types
+from . import _cache, _lib, configs, image_encoder, ops, types
 
 F = np.float32
 
@@ -99,11 +99,15 @@ class StreetViewEncoder:
         self.default_stats = bool(c.fusion_use_variance) and not c.fusion_add_minmax
         self.dtype = dtype
         self.image_encoder = image_encoder.ImageEncoder(c.image_encoder, dtype)
-        self._cache: Dict = {}
+        self._cache: Dict = {}              # shape-keyed workspaces / staging buffers
+        self._wcache = _cache.ParamCache()  # weight banks, per parameter tree
+
+    def clear_cache(self) -> None:
+        self._wcache.clear()
+        self.image_encoder.clear_cache()
 
     def _weights(self, params: Dict, device):
-        key = (id(params), str(device))
-        if key not in self._cache:
+        def build():
             bank = image_encoder._WeightBank(device)
             f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F).reshape(-1)).to(device)
             fus0_k = np.asarray(params["fusion_mlp"]["Dense_0"]["kernel"], dtype=F)
@@ -125,8 +129,8 @@ class StreetViewEncoder:
                      fus1_b=f32(params["fusion_mlp"]["Dense_1"]["bias"]),
                      w256=f32(fus0_k[self.stats_dim - 1]))
             bank.finalize()
-            self._cache[key] = w
-        return self._cache[key]
+            return w
+        return self._wcache.lookup(params, str(device), build)
 
     def _buffers(self, device, B, V, H, W, hf, wf, X, Y, Z):
         key = ("buf", str(device), B, V, H, W, hf, wf, X, Y, Z)
