@@ -89,3 +89,72 @@ def pmean_tree(tree, bucket_bytes: int = 256 << 20, group=None):
         calls += 1
         i = j
     return calls
+
+
+class GradBucket:
+    """Persistent flat fp32 gradient bucket: the counterpart of `jax.lax.pmean(grad, axis_name='batch')` on the ~48 M
+    parameter tree of the localisation model (`snap/trainer.py:231-234`, ~193 MB fp32 per step) without the three extra
+    passes of `pmean_tree` (torch.cat -> all-reduce -> divide -> copy back).
+
+    The bucket owns ONE flat fp32 device buffer; `views[i]` is the gradient array of leaf i inside it (16-byte aligned), so
+    the backward kernels write gradients straight into the bucket and `allreduce_mean` is a single in-place all-reduce
+    (NCCL: ReduceOp.AVG, no separate division; gloo: SUM + one in-place scale).  Nothing is allocated per call, so the
+    collective can be captured into a CUDA graph, or enqueued on a side stream (`stream=`) to overlap the tail of the
+    backward pass: the caller's stream waits for it with `wait()`.  Identity without a process group."""
+
+    ALIGN = 4   # elements (16 bytes)
+
+    def __init__(self, shapes, device, group=None):
+        self.shapes = [tuple(int(d) for d in sh) for sh in shapes]
+        self.group = group
+        offs, o = [], 0
+        for sh in self.shapes:
+            n = 1
+            for d in sh:
+                n *= d
+            offs.append((o, n))
+            o += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(max(o, self.ALIGN), dtype=torch.float32, device=device)
+        self.views = [self.flat[a:a + n].view(sh) for (a, n), sh in zip(offs, self.shapes)]
+        self._event = None
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def allreduce_mean(self, stream=None) -> int:
+        """In-place mean over ranks of the whole bucket; returns the number of collectives issued (0 or 1)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 0
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return 0
+
+        def run():
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / world)
+        if stream is None or not self.flat.is_cuda:
+            run()
+        else:
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                run()
+                self._event = torch.cuda.Event()
+                self._event.record(stream)
+        return 1
+
+    def wait(self) -> None:
+        """Make the current stream wait for a collective enqueued on a side stream."""
+        if self._event is not None:
+            torch.cuda.current_stream().wait_event(self._event)
+            self._event = None
+
+    def all_finite(self) -> torch.Tensor:
+        """Device-side 0-dim bool: every gradient is finite (`trainer.py:260-276` skips the update otherwise)."""
+        return torch.isfinite(self.flat).all()

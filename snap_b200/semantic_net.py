@@ -168,8 +168,12 @@ class MLPHeadTrainer:
             b = z(coutp)
             b[:cout] = torch.from_numpy(np.ascontiguousarray(params[n]["bias"], dtype=F)).to(device)
             self.b.append(b)
-        self.dW = [z(cin, coutp) for cin, coutp, _ in self.dims]
-        self.db = [z(coutp) for _, coutp, _ in self.dims]
+        from . import parallel
+        # gradients live in one flat fp32 bucket: the mean over ranks is a single in-place all-reduce (parallel.GradBucket)
+        self.bucket = parallel.GradBucket([(cin, coutp) for cin, coutp, _ in self.dims] + [(coutp,) for _, coutp, _ in self.dims],
+                                          device)
+        self.dW = self.bucket.views[: len(self.dims)]
+        self.db = self.bucket.views[len(self.dims):]
         self.mom = [[z(*t.shape), z(*t.shape)] for t in self.W + self.b]
         self.Wc = [z(cin, coutp, dt=torch.bfloat16) for cin, coutp, _ in self.dims]   # bf16 [in, out]: B operand of dX
         self.step = 0
@@ -234,11 +238,10 @@ class MLPHeadTrainer:
                 ops.gemm(dy, self.Wc[i], buf["d"][i], m_rows=rows, seg_k=coutp)
                 ops.relu_bwd(acts[i], buf["d"][i], rows * cin)
                 dy = buf["d"][i]
-        grads = {n: {"kernel": self.dW[i], "bias": self.db[i]} for i, n in enumerate(self.names)}
-        parallel.pmean_tree(grads)                        # jax.lax.pmean(grad, 'batch') (trainer.py:231-234)
-        if update:
+        self.bucket.allreduce_mean()                      # jax.lax.pmean(grad, 'batch') (trainer.py:231-234)
+        if update and bool(self.bucket.all_finite().item()):   # non-finite gradients: keep parameters and Adam state (trainer.py:260-276)
             self.step += 1
-            for k, (pt, g) in enumerate(zip(self.W + self.b, self.dW + self.db)):
+            for k, (pt, g) in enumerate(zip(self.W + self.b, list(self.dW) + list(self.db))):
                 ops.adam_step(pt.view(-1) if pt.is_contiguous() else pt, self.mom[k][0].view(-1), self.mom[k][1].view(-1),
                               g.view(-1), self.lr, self.step)
         return losses["total"], losses, metrics

@@ -73,7 +73,7 @@ class StageHeadTrainer:
             for g, cc in (("gn1", dim), ("gn2", nmid), ("gn3", nmid)):
                 u[g] = (add_vec(("layers_1", name, g, "scale"), pu[g]["scale"]),
                         add_vec(("layers_1", name, g, "bias"), pu[g]["bias"]))
-                u["d" + g] = (self.rec[-2]["g"], self.rec[-1]["g"])
+                u["d" + g + "_idx"] = (len(self.rec) - 2, len(self.rec) - 1)
             for cv in ("conv1", "conv2", "conv3"):
                 u[cv] = add_kernel(("layers_1", name, cv, "kernel"), pu[cv]["kernel"], True)
             self.units.append(u)
@@ -97,6 +97,16 @@ class StageHeadTrainer:
                 r["g"] = z(*r["p"].shape)
                 if r["std"]:
                     r["gs"] = z(*r["p"].shape)          # gradient w.r.t. the standardised kernel
+        # all gradients live in ONE flat fp32 bucket (parallel.GradBucket): the backward kernels write into its views and
+        # the gradient mean over ranks (trainer.py:231-234) is a single in-place all-reduce
+        from . import parallel
+        self.bucket = parallel.GradBucket([r["g"].shape for r in self.rec], device)
+        for r, v in zip(self.rec, self.bucket.views):
+            r["g"] = v
+        for u in self.units:
+            for g in ("gn1", "gn2", "gn3"):
+                i, j = u["d" + g + "_idx"]
+                u["d" + g] = (self.rec[i]["g"], self.rec[j]["g"])
         self.by_bank = {r["bank"]: r for r in self.rec if "bank" in r}
         self.mom = [[z(*r["p"].shape), z(*r["p"].shape)] for r in self.rec]
         # B operands of the dX GEMMs
@@ -242,12 +252,21 @@ class StageHeadTrainer:
                           ctx["valid"], self.num_area, self.num_excl, self.num_indep, ctx["weights"], buf["counts"],
                           buf["dlogits"])
         self.backward(plane, buf)
-        parallel.pmean_tree({"/".join(r["path"]): r["g"] for r in self.rec})     # jax.lax.pmean (trainer.py:231-234)
+        self.bucket.allreduce_mean()                                             # jax.lax.pmean (trainer.py:231-234)
         if update:
-            self.step += 1
-            for r, (m, v) in zip(self.rec, self.mom):
-                ops.adam_step(r["p"].view(-1), m.view(-1), v.view(-1), r["g"].view(-1), self.lr, self.step)
+            self.apply_update()
         return losses["total"], losses, metrics
+
+    def apply_update(self) -> bool:
+        """optax.adam on the fp32 masters, skipped when any (averaged) gradient is non-finite (`trainer.py:260-276`: the
+        reference keeps the old parameters AND optimiser state for such a step).  Returns whether the step was applied."""
+        if not bool(self.bucket.all_finite().item()):
+            self.skipped_steps = getattr(self, "skipped_steps", 0) + 1
+            return False
+        self.step += 1
+        for r, (m, v) in zip(self.rec, self.mom):
+            ops.adam_step(r["p"].view(-1), m.view(-1), v.view(-1), r["g"].view(-1), self.lr, self.step)
+        return True
 
     # ------------------------------------------------------------------------------------------------------------
     def _tree(self, key: str) -> Dict:
