@@ -81,3 +81,26 @@ def test_config4_localization_pipeline_g128_r36():
     k = np.unravel_index(np.argmax(np.where(fin, s, -np.inf)), s.shape)
     print(f"cfg4: query cells {int(qv.sum())}, map cells {int(mv.sum())}, peak {k} score {s[k]:.4f}")
     assert tuple(int(x) for x in k) == (0, G - 1, G - 1)
+
+
+def test_cfg2_full_size_teacher_forced_parity_vs_oracle():
+    """BASELINE configs[1] at FULL size (4 x 480x640 views, 128 x 128 x 60 = 983,040 voxels), the benchmarked configuration,
+    compared NUMERICALLY with the oracle: the valid plane bit-exact, and -- the oracle (bf16 emulation) being fed the GPU's
+    own encoder features, which removes the chaos of a random-init 50-layer bf16 ResNet -- proj MLP -> lift -> fusion MLP ->
+    vertical max -> matching head to <= 1e-3 relative L2 (north_star).  The same check runs inside bench.py on the
+    cpu_baseline tile and is printed as the `parity` object of the JSON line."""
+    import os
+    import bench
+    from util import record_parity
+    from snap_b200 import bev_mapper, configs, params, types
+    cfg = configs.bev_mapper(("streetview",))
+    p = params.round_to_bf16(params.init_bev_mapper(np.random.default_rng(7), cfg))
+    mapper = bev_mapper.BEVMapper(cfg, types.Grid2D((bench.G, bench.G), 0.2))
+    parity, _ = bench.cfg2_parity(mapper, p, 99, os.cpu_count() or 1, torch.device("cuda"), free_running=False)
+    tf = parity["teacher_forced"]
+    print(f"cfg2 full size: valid_equal {parity['valid_equal']} ({parity['valid_cells']} valid cells), teacher-forced rel_l2 "
+          f"bev_features {tf['rel_l2_bev_features']:.2e}, bev_matching {tf['rel_l2_bev_matching']:.2e}")
+    record_parity("cfg2 full size (teacher-forced lift + head)", "bev_features rel-L2 vs oracle", tf["rel_l2_bev_features"], 1e-3)
+    record_parity("cfg2 full size (teacher-forced lift + head)", "bev_matching rel-L2 vs oracle", tf["rel_l2_bev_matching"], 1e-3)
+    assert parity["valid_equal"] and parity["valid_cells"] > 5000
+    assert tf["rel_l2_bev_features"] <= 1e-3 and tf["rel_l2_bev_matching"] <= 1e-3

@@ -168,3 +168,51 @@ def test_data_parallel_step_equivalence_world_size_2():
             ref = full[k][n].numpy()
             for r in range(2):
                 assert np.abs(res[r][1][k][n] - ref).max() <= 1e-6 * (1 + np.abs(ref).max()), (k, n)
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snap_b200 import parallel
+    shapes = [(257, 16), (16,), (3, 3, 5), (1,)]
+    b = parallel.GradBucket(shapes, "cpu")
+    g = torch.Generator().manual_seed(11)
+    base = [torch.randn(s, generator=g) for s in shapes]
+    for v, t in zip(b.views, base):          # "backward kernels" write straight into the bucket's views
+        v.copy_(t * (rank + 1))
+    ptr0 = b.flat.data_ptr()
+    calls = b.allreduce_mean()
+    err = max(float((v - t * 1.5).abs().max()) for v, t in zip(b.views, base))
+    aligned = all(v.data_ptr() % 16 == 0 for v in b.views)
+    finite = bool(b.all_finite())
+    if rank == 1:
+        b.views[2].view(-1)[7] = float("nan")
+    b.allreduce_mean()                       # a NaN on one rank reaches every rank through the mean
+    out.put((rank, calls, err, aligned, finite, bool(b.all_finite()), b.flat.data_ptr() == ptr0, b.nbytes))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_grad_bucket_single_in_place_all_reduce():
+    """`parallel.GradBucket`: gradients live in one flat fp32 buffer, the mean over ranks (trainer.py:231-234) is ONE in-place
+    collective with no allocation, and the non-finite guard (trainer.py:260-276) sees a NaN produced on any rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=90) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, calls, err, aligned, finite, finite_after, same_buffer, nbytes in res:
+        assert calls == 1 and err < 1e-6 and aligned and finite and not finite_after and same_buffer
+        assert nbytes == 4 * (4112 + 16 + 48 + 4)       # every leaf padded to 16 bytes
+
+
+def test_grad_bucket_without_process_group_is_identity():
+    from snap_b200 import parallel
+    b = parallel.GradBucket([(4, 4), (3,)], "cpu")
+    b.views[0].fill_(2.0)
+    assert b.allreduce_mean() == 0 and float(b.views[0].sum()) == 32.0 and bool(b.all_finite())
