@@ -274,6 +274,7 @@ def run_cfg4(args):
     grid = types.Grid2D((G, G), 0.2)
     cfg = configs.bev_localizer()
     cfg.bev_mapper = configs.bev_mapper(("streetview", "aerial"))
+    cfg.filter_points_in_fov = True
     loc = bev_localizer.BEVLocalizer(cfg, None, grid)
     mp = params.round_to_bf16(params.init_bev_mapper(np.random.default_rng(11), cfg.bev_mapper))
     mapper = loc.bev_mapper

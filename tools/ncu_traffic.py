@@ -30,10 +30,18 @@ OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 
 
-def capture(name, regex, cmd, count):
-    rep = os.path.join(OUT, f"{args.tag}_{name}")
-    full = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", f"regex:{regex}",
-            "--profile-from-start", "off", "-c", str(count), "-f", "-o", rep] + cmd
+REPS = os.environ.get("SNAPB200_NCU_REP_DIR", "/tmp/snapb200_ncu")   # raw reports stay OFF gpurun_out/ (64 MiB merge limit)
+os.makedirs(REPS, exist_ok=True)
+LIGHT = ("dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,"
+         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,"
+         "sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+
+
+def capture(name, regex, cmd, count, light=False, skip=0):
+    rep = os.path.join(REPS, f"{args.tag}_{name}")
+    what = ["--metrics", LIGHT] if light else ["--set", "full", "--import-source", "on"]
+    full = ["ncu", *what, "--clock-control", "none", "-k", f"regex:{regex}", "--profile-from-start", "off", "-s", str(skip),
+            "-c", str(count), "-f", "-o", rep] + cmd
     r = subprocess.run(full, capture_output=True, text=True, cwd=ROOT)
     if r.returncode != 0:
         print(f"ncu failed for {name}: {r.stdout[-400:]} {r.stderr[-400:]}", file=sys.stderr)
@@ -100,7 +108,14 @@ if rep:
                         "source": f"profiles/{args.tag}_xcorr_ncu_full.txt (ncu --set full, cold L2, G=128 R=36, one example)"}
     summarize(rep, f"{args.tag}_xcorr_ncu_full.txt")
 if not args.skip_step:
-    rep = capture("step", "gemm_tc_kernel|gn_apply_kernel", [py, "bench.py", "--profile-step", "--no-cpu-baseline"], 400)
+    # every GEMM / GroupNorm launch of one eager step with a light metric set (DRAM bytes, duration, tensor pipe, issue
+    # slots), then `--set full` summaries of the three instantiations that dominate the step
+    rep = capture("step", "gemm_tc_kernel|gn_apply_kernel", [py, "bench.py", "--profile-step", "--no-cpu-baseline"], 400, light=True)
+    for nm, rx, skip in (("gemm_128_64_conv", "gemm_tc_kernel<128, 64, 0, 1>", 3), ("gemm_256_64", "gemm_tc_kernel<256, 64, 0, 0>", 2),
+                         ("gn_apply_dense", "gn_apply_kernel<0, 0, 0>", 2)):
+        r2 = capture(nm, rx.replace("(", ".").replace("<", ".").replace(">", ".").replace(", ", ".."), [py, "bench.py", "--profile-step", "--no-cpu-baseline"], 1, skip=skip)
+        if r2:
+            summarize(r2, f"{args.tag}_{nm}_ncu_full.txt")
     if rep:
         stats = kernel_stats(rep)
         for key, pat in (("gemm", "gemm_tc_kernel"), ("gn_apply", "gn_apply_kernel")):
@@ -121,7 +136,7 @@ if not args.skip_step:
             traffic[key] = {"per_step_of_8_tiles": {"launches": len(sel), "dram_bytes": sum(s[1] for s in sel),
                                                     "duration_us": sum(s[2] for s in sel)},
                             "by_instantiation": by, "src_sha": bench.source_hash(key),
-                            "source": f"profiles/{args.tag}_step_kernels.json (ncu --set full over one eager bench step, cold L2)"}
+                            "source": f"profiles/{args.tag}_step_kernels.json (ncu, DRAM-bytes + duration + tensor-pipe metrics of every launch of one eager bench step, cold L2)"}
         with open(os.path.join(OUT, f"{args.tag}_step_kernels.json"), "w") as f:
             json.dump([{"kernel": s[0][:120], "dram_bytes": s[1], "duration_us": s[2], "tensor_pipe_pct": s[3]} for s in stats], f, indent=0)
 with open(os.path.join(OUT, "traffic.json"), "w") as f:
