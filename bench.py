@@ -710,7 +710,8 @@ def main():
         lift_desc = "camera->BEV lift, unfused = 4 launches (gather+pool, 2 tcgen05 GEMMs, vertical max)"
     enc_plan = sve.image_encoder.plan(p["streetview_encoder"]["image_encoder"], BT * V, *IMG_HW, dev)
     hf_, wf_ = enc_plan.cropped_shapes()[-1]
-    cnt = sve._buffers(dev, BT, V, *IMG_HW, hf_, wf_, G, G, Z)["counter"][0].cpu().tolist()
+    buf_ = sve._buffers(dev, BT, V, *IMG_HW, hf_, wf_, G, G, Z)
+    cnt = buf_["counter"][: buf_.get("lift_launches", 1)].sum(0).cpu().tolist()   # one counter row per lift launch
     lift_ms = lift_ms / BT   # per tile: one launch per tile (v1) or one launch for the BT tiles of the step (v2)
     if lift_batched:         # the batched kernel's counters cover the whole batch
         cnt = [c / BT for c in cnt]

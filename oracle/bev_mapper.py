@@ -172,11 +172,12 @@ def lift_scene(f_proj_images: np.ndarray, camera: geometry.Camera, t_view2scene:
     return f_grid, valid, np.concatenate(vis_all), np.concatenate(p2d_all)
 
 
-def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = _id):
-    """bev_mapper.py:284-291: Dense 128->32, L2-normalise, mask."""
+def matching_head(plane: np.ndarray, valid: np.ndarray, p: Dict, rd: Callable = _id, normalize: bool = True):
+    """bev_mapper.py:284-291: Dense 128->matching_dim, L2-normalise (if normalize_matching_features), mask."""
     rdn = np_rd(rd)
     f = rdn(rdn(layers.dense(plane, p["kernel"], None)) + p["bias"].astype(F))
-    f = rdn(layers.normalize(f))
+    if normalize:
+        f = rdn(layers.normalize(f))
     return np.where(valid[..., None], f, F(0)).astype(F)
 
 

@@ -104,10 +104,8 @@ class BEVMapper:
             raise NotImplementedError("semantic raster modality is out of scope (SURVEY.md §2)")
         if c.bev_net is not None:
             raise NotImplementedError("BEV network not yet implemented")  # bev_mapper.py:141-142
-        if c.matching_dim not in (None, 32):
-            raise NotImplementedError("matching_dim must be 32 (or None)")
-        if c.matching_dim is not None and not c.normalize_matching_features:
-            raise NotImplementedError("un-normalised matching features are not built (the default normalises, defaults.py:254)")
+        if c.matching_dim is not None and not 1 <= c.matching_dim <= 256:
+            raise NotImplementedError("matching_dim must be in 1..256")
         self.streetview_encoder = self.aerial_encoder = None
         if c.streetview_encoder is not None:
             self.streetview_encoder = streetview_encoder.StreetViewEncoder(c.streetview_encoder, dtype)
@@ -130,9 +128,9 @@ class BEVMapper:
             xs, ys = self.grid.cell_centers(0), self.grid.cell_centers(1)                   # :164-165
         else:
             xy = np.asarray(xy, dtype=F)
-            if xy.ndim == 4:    # batched: the kernels take one set of BEV points per call
+            if xy.ndim == 4:    # batched: the kernels take one set of BEV points per call (apply() splits other batches)
                 if not all(np.array_equal(xy[0], xy[b]) for b in range(1, len(xy))):
-                    raise NotImplementedError("per-example xy_bev is not built (BEVLocalizer repeats one frustum, bev_localizer.py:140)")
+                    raise ValueError("per-example xy_bev reaches build_xyz_grid only through BEVMapper.apply")
                 xy = xy[0]
             if data.get("xy_bev_cache", True):
                 # a persistent point set (BEVLocalizer.q_xy_p): analysed once, and the SAME host arrays are handed out
@@ -233,6 +231,10 @@ class BEVMapper:
         if train:
             raise NotImplementedError("training (backward kernels) is a 'next' row of SURVEY.md §8(f)")
         params = variables["params"] if "params" in variables else variables
+        xy = data.get("xy_bev")
+        if xy is not None and np.ndim(xy) == 4 and len(xy) > 1 and \
+                not all(np.array_equal(np.asarray(xy[0]), np.asarray(xy[b])) for b in range(1, len(xy))):
+            return self._apply_per_example(variables, data, train, debug, is_query)
         pred, planes = {}, []
         if self.streetview_encoder is not None:
             pred["streetview"] = self.encode_streetview(params, data, train, is_query, debug)
@@ -252,7 +254,8 @@ class BEVMapper:
             f = plane.features.contiguous()
             cells = f.numel() // f.shape[-1]
             out = torch.empty((*f.shape[:-1], self.config.matching_dim), dtype=torch.bfloat16, device=dev)
-            ops.match_head(f, plane.valid.contiguous(), cells, f.shape[-1], k, bvec, out)
+            ops.match_head(f, plane.valid.contiguous(), cells, f.shape[-1], k, bvec, out,
+                           normalize=bool(self.config.normalize_matching_features))
             pred["bev_matching"] = types.FeaturePlane(features=out, valid=plane.valid)
         if self.config.add_confidence:  # bev_mapper.py:292-295
             dev = plane.features.device
@@ -264,6 +267,38 @@ class BEVMapper:
             conf = torch.empty(f.shape[:-1], dtype=torch.float32, device=dev)
             ops.confidence(f, plane.valid.contiguous(), f.numel() // f.shape[-1], f.shape[-1], cw, cb, conf)
             pred["bev_confidence"] = conf
+        return pred
+
+    def _apply_per_example(self, variables: Dict, data: Dict, train: bool, debug: bool, is_query: bool) -> Dict:
+        """`data['xy_bev']` [B,X,Y,2] with DIFFERENT points per example (`bev_mapper.py:162-166` allows any batch of BEV
+        points): the kernels take one point set per launch, so the batch is split into single-example calls and the planes
+        are stacked.  (The one caller in the reference, BEVLocalizer, repeats one frustum: `bev_localizer.py:140`.)"""
+        import dataclasses
+        B = len(data["xy_bev"])
+
+        def take(v, b):
+            if isinstance(v, dict):
+                return {k: take(x, b) for k, x in v.items()}
+            if dataclasses.is_dataclass(v):
+                return dataclasses.replace(v, **{f.name: take(getattr(v, f.name), b) for f in dataclasses.fields(v)
+                                                 if getattr(v, f.name) is not None})
+            if isinstance(v, (np.ndarray, torch.Tensor)) and v.ndim >= 1 and v.shape[0] == B:
+                return v[b:b + 1]
+            return v
+        outs = []
+        for b in range(B):
+            sub = {k: take(v, b) for k, v in data.items() if k not in ("xyz_grid", "xy_shape", "xy_custom", "staging_slot")}
+            sub["xy_bev"] = np.asarray(data["xy_bev"])[b]
+            sub["xy_bev_cache"] = False
+            p = self.apply(variables, sub, train, debug, is_query)
+            outs.append({k: (types.FeaturePlane(p[k].features.clone(), p[k].valid.clone()) if isinstance(p[k], types.FeaturePlane)
+                             else p[k].clone()) for k in ("bev_features", "bev_matching", "bev_confidence") if k in p})
+        pred: Dict = {}
+        for k in outs[0]:
+            if isinstance(outs[0][k], types.FeaturePlane):
+                pred[k] = types.FeaturePlane(torch.cat([o[k].features for o in outs]), torch.cat([o[k].valid for o in outs]))
+            else:
+                pred[k] = torch.cat([o[k] for o in outs])
         return pred
 
     __call__ = apply

@@ -32,7 +32,10 @@ constexpr int S2_CTL = S2_RCOL + 1024;
 constexpr int S2_VIEW = S2_CTL + 512;                        // LiftView[32]
 constexpr int S2_CULL = S2_VIEW + 2944;                      // CullView[32]
 constexpr int S2_TBL = S2_CULL + 2688;                       // epilogue tables: w256 f32[256], b1 bf16x2[128], b2 bf16x2[64]
-constexpr int F2_SMEM_BYTES = S2_TBL + 1024 + 512 + 256;
+constexpr int S2_COORD = S2_TBL + 1024 + 512 + 256;           // voxel coordinates: zs f32[8][64] | xs f32[256] | ys f32[256]
+constexpr int F2_ZS_CACHE = 8 * 64;                          // floats: launches of up to 8 scenes (larger ones read global memory)
+constexpr int F2_XY_CACHE = 256;                             // floats per axis (separable grids up to 256 cells)
+constexpr int F2_SMEM_BYTES = S2_COORD + 4 * (F2_ZS_CACHE + 2 * F2_XY_CACHE);
 static_assert(sizeof(LiftView) * F2_MAX_VIEWS_TOTAL <= 2944, "view table");
 static_assert(S2_STG % 16 == 0 && F2_GSLOT_BYTES % 16 == 0 && S2_TBL % 16 == 0, "16-byte aligned staging / tables");
 static_assert(F2_SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
@@ -158,6 +161,22 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
   float* tbl_w256 = reinterpret_cast<float*>(smem + S2_TBL);                 // W1[256, :] (score_max input row)
   uint32_t* tbl_b1 = reinterpret_cast<uint32_t*>(smem + S2_TBL + 1024);      // b1 as packed bf16 pairs
   uint32_t* tbl_b2 = reinterpret_cast<uint32_t*>(smem + S2_TBL + 1536);      // b2 as packed bf16 pairs
+  // voxel coordinates in shared memory: with ~226 KB of it there is next to no L1, so the three coordinate loads at the top
+  // of every visibility batch were exposed L2 round trips
+  float* zs_s = reinterpret_cast<float*>(smem + S2_COORD);
+  float* xs_s = zs_s + F2_ZS_CACHE;
+  float* ys_s = xs_s + F2_XY_CACHE;
+  const bool zs_cached = A.B * 64 <= F2_ZS_CACHE;
+  const bool xy_cached = !P.xy_paired && P.X <= F2_XY_CACHE && P.Y <= F2_XY_CACHE;
+  if (zs_cached)
+    for (int i = threadIdx.x; i < A.B * 64; i += blockDim.x) {
+      const int sc = i >> 6, z = i & 63;
+      zs_s[i] = z < P.Z ? A.zs[(size_t)sc * A.zs_stride + z] : 0.f;
+    }
+  if (xy_cached) {
+    for (int i = threadIdx.x; i < P.X; i += blockDim.x) xs_s[i] = A.xs[i];
+    for (int i = threadIdx.x; i < P.Y; i += blockDim.x) ys_s[i] = A.ys[i];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled operands need a 1024 B aligned base
@@ -351,8 +370,9 @@ lift_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_consta
           scene = gcol / ncols;
           const int col = gcol - scene * ncols;
           const int ix = col / P.Y, iy = col - ix * P.Y;
-          const float px = A.xs[P.xy_paired ? col : ix], py = A.ys[P.xy_paired ? col : iy];
-          const float pz = A.zs[(size_t)scene * A.zs_stride + z];
+          const float px = xy_cached ? xs_s[ix] : A.xs[P.xy_paired ? col : ix];
+          const float py = xy_cached ? ys_s[iy] : A.ys[P.xy_paired ? col : iy];
+          const float pz = zs_cached ? zs_s[scene * 64 + z] : A.zs[(size_t)scene * A.zs_stride + z];
           const float s1 = fabsf(px) + fabsf(py) + fabsf(pz) + 1.0f;
 #pragma unroll
           for (int v = 0; v < F2_MAXV; ++v) {

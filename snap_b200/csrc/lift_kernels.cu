@@ -241,6 +241,51 @@ match_head_kernel(const __nv_bfloat16* __restrict__ plane, const uint8_t* __rest
   }
 }
 
+// General matching head (bev_mapper.py:284-291 with any matching_dim <= 256, optional normalisation): one warp per cell,
+// lane l computes outputs l, l + 32, ...; the kernel [C, DM] is read through L1.  The default configuration
+// (matching_dim 32, normalised) takes match_head_kernel above.
+__global__ void __launch_bounds__(256)
+match_head_general_kernel(const __nv_bfloat16* __restrict__ plane, const uint8_t* __restrict__ valid, long long cells,
+                          int C, const float* __restrict__ kernel, const float* __restrict__ bias, int DM, int normalize,
+                          __nv_bfloat16* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long cell = (long long)blockIdx.x * 8 + warp; cell < cells; cell += (long long)gridDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k0 = 0; k0 < C; k0 += 32) {
+      const float xk = k0 + lane < C ? __bfloat162float(plane[cell * C + k0 + lane]) : 0.f;
+      for (int k = 0; k < 32 && k0 + k < C; ++k) {
+        const float x = __shfl_sync(0xffffffffu, xk, k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = lane + 32 * j;
+          if (n < DM) acc[j] += x * __ldg(kernel + (size_t)(k0 + k) * DM + n);
+        }
+      }
+    }
+    float y[8], ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = lane + 32 * j;
+      y[j] = n < DM ? bf16_round(bf16_round(acc[j]) + __ldg(bias + n)) : 0.f;  // nn.Dense: dot -> dtype, + bias -> dtype
+      ss += y[j] * y[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(ss);
+    const bool ok = valid[cell] != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = lane + 32 * j;
+      if (n >= DM) continue;
+      float z = y[j];
+      if (normalize) z = (nrm < 1e-5f) ? 0.f : y[j] / nrm;   // layers.normalize (layers.py:45-52)
+      out[cell * DM + n] = __float2bfloat16(ok ? z : 0.f);
+    }
+  }
+}
+
 // modality fusion: max over up to 3 planes where valid (VerticalPooling('max') over the modality axis)
 __global__ void fuse_max_kernel(const __nv_bfloat16* __restrict__ a, const uint8_t* __restrict__ va,
                                 const __nv_bfloat16* __restrict__ b, const uint8_t* __restrict__ vb,
@@ -318,6 +363,19 @@ int snapb200_match_head(const void* plane, const uint8_t* valid, long long cells
   match_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)plane, valid, cells, C, kernel, bias, (__nv_bfloat16*)out);
   return check_launch("match_head_kernel");
+}
+
+int snapb200_match_head_ex(const void* plane, const uint8_t* valid, long long cells, int C, const float* kernel,
+                           const float* bias, int dm, int normalize, void* out, void* stream) {
+  SNAP_REQUIRE(plane && valid && kernel && bias && out, "null pointer");
+  SNAP_REQUIRE(dm >= 1 && dm <= 256 && C >= 1, "matching head needs 1 <= matching_dim <= 256 (got %d)", dm);
+  if (dm == 32 && normalize && C % 32 == 0 && C <= 256)
+    return snapb200_match_head(plane, valid, cells, C, kernel, bias, dm, out, stream);
+  unsigned grid = (unsigned)((cells + 7) / 8);
+  if (grid > 8u * 148u) grid = 8u * 148u;
+  match_head_general_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)plane, valid, cells, C, kernel, bias,
+                                                                    dm, normalize, (__nv_bfloat16*)out);
+  return check_launch("match_head_general_kernel");
 }
 
 int snapb200_fuse_max(const void* a, const uint8_t* va, const void* b, const uint8_t* vb, long long cells,

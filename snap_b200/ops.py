@@ -357,11 +357,13 @@ def valid_any(valid: torch.Tensor, cells: int, Z: int, out: torch.Tensor) -> Non
 
 
 def match_head(plane: torch.Tensor, valid: torch.Tensor, cells: int, Cc: int, kernel: torch.Tensor,
-               bias: torch.Tensor, out: torch.Tensor) -> None:
+               bias: torch.Tensor, out: torch.Tensor, normalize: bool = True) -> None:
+    """Dense(C -> matching_dim) + optional L2 normalisation + mask (`bev_mapper.py:284-291`)."""
     _require(kernel, torch.float32, "kernel")
-    _lib.check(_lib.lib().snapb200_match_head(
+    assert kernel.is_contiguous() and out.is_contiguous() and out.shape[-1] == kernel.shape[1]
+    _lib.check(_lib.lib().snapb200_match_head_ex(
         C.c_void_p(_ptr(plane)), C.c_void_p(_ptr(valid)), C.c_longlong(cells), Cc,
-        C.c_void_p(_ptr(kernel)), C.c_void_p(_ptr(bias)), C.c_int(kernel.shape[1]),
+        C.c_void_p(_ptr(kernel)), C.c_void_p(_ptr(bias)), C.c_int(kernel.shape[1]), C.c_int(int(normalize)),
         C.c_void_p(_ptr(out)), _stream()))
 
 

@@ -283,7 +283,8 @@ class StreetViewEncoder:
             buf["valid"] = torch.zeros((B, N), dtype=torch.uint8, device=dev)
         # The batched path: ONE crop + ONE proj GEMM + ONE launch of the warp-specialised lift for all scenes
         # (`SNAPB200_LIFT_V=1` keeps the first-generation per-scene kernel for A/B measurements).
-        batched = fused and os.environ.get("SNAPB200_LIFT_V", "2") != "1" and B * V <= 32 and B * X * Y <= (1 << 18)
+        batched = fused and os.environ.get("SNAPB200_LIFT_V", "2") != "1"
+        chunk = max(1, min(32 // V, (1 << 18) // (X * Y)))   # scenes per launch: B * V <= 32 views, B * X * Y <= 2^18 columns
         rows_img = buf["fimg"].shape[1]
         if batched:
             if rows_img == V * hf * wf:
@@ -294,9 +295,12 @@ class StreetViewEncoder:
                 for b in range(B):
                     ops.crop_relu(full[b * V:(b + 1) * V], V, Hs, Ws, 128, hf, wf, self.weighted, buf["crop"])
                     ops.gemm(buf["crop"], Bm[wts["proj"]], buf["fimg"][b], m_rows=V * hf * wf, bias=wts["proj_b"])
-            ops.lift_fused_batched(lp, B, stg["views"], buf["fimg"], buf["xs"], buf["ys"], stg["zs"], Bm[wts["fus0"]],
-                                   wts["w256"], wts["fus0_b"], Bm[wts["fus1"]], wts["fus1_b"], buf["plane"], buf["pvalid"],
-                                   buf["counter"][0], buf["scratch"])
+            for ci, b0 in enumerate(range(0, B, chunk)):
+                b1 = min(B, b0 + chunk)
+                ops.lift_fused_batched(lp, b1 - b0, stg["views"][b0:b1], buf["fimg"][b0:b1], buf["xs"], buf["ys"], stg["zs"][b0:b1],
+                                       Bm[wts["fus0"]], wts["w256"], wts["fus0_b"], Bm[wts["fus1"]], wts["fus1_b"],
+                                       buf["plane"][b0:b1], buf["pvalid"][b0:b1], buf["counter"][ci], buf["scratch"])
+            buf["lift_launches"] = -(-B // chunk)
         for b in range(0 if not batched else B, B):
             # proj_mlp: ReLU -> Dense(128 -> 160) on the cropped finest level (`:228-230`); un-weighted fusion: the crop
             # itself, widened by zero logits (see __init__)

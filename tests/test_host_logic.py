@@ -131,10 +131,11 @@ def test_xy_bev_points_separable_and_paired():
     d = dict(data, xy_bev=xy)
     xs, ys, zs = mapper.build_xyz_grid(d)
     assert "xy_shape" not in d and np.array_equal(xs, xs0) and np.array_equal(ys, ys0) and zs.shape == (2, 60)
-    # batched copies of the same grid are accepted, different grids per example are not
+    # batched copies of the same grid are one launch; different grids per example are split by BEVMapper.apply into
+    # single-example launches (tests/test_localizer_gpu.py) and never reach build_xyz_grid as a batch
     d = dict(data, xy_bev=np.stack([xy, xy]))
     assert np.array_equal(mapper.build_xyz_grid(d)[0], xs0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         mapper.build_xyz_grid(dict(data, xy_bev=np.stack([xy, xy + F(0.1)])))
     # arbitrary points: the query frustum of the localizer
     _, _, q = bev_localizer.build_query_frustum_grid(0.2, 16.0, True, 72.0)

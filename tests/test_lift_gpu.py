@@ -140,6 +140,33 @@ def test_match_head_and_fuse_vs_oracle():
     assert not mh.float().cpu().numpy()[5].any()
 
 
+@pytest.mark.parametrize("dm,normalize", [(64, True), (32, False), (48, True), (8, False)])
+def test_match_head_other_dims_and_unnormalised_vs_oracle(dm, normalize):
+    """Non-default heads (`bev_mapper.py:284-291`): matching_dim != 32 and normalize_matching_features = False."""
+    from oracle import bev_mapper as obm
+    from snap_b200 import ops
+    rng = np.random.default_rng(dm)
+    cells, C = 777, 128
+    a = bf16_np(rng.standard_normal((cells, C)))
+    va = rng.random(cells) > 0.3
+    a[5] = 0
+    k = bf16_np(rng.standard_normal((C, dm)) * 0.1)
+    bias = bf16_np(rng.standard_normal(dm) * 0.1) * (0 if normalize else 1)
+    dev = "cuda"
+    out = torch.full((cells, dm), 7.0, dtype=torch.bfloat16, device=dev)
+    ops.match_head(_t(a).to(torch.bfloat16).to(dev), torch.from_numpy(va.astype(np.uint8)).to(dev), cells, C, _t(k).to(dev),
+                   _t(bias).to(dev), out, normalize=normalize)
+    torch.cuda.synchronize()
+    ref = obm.matching_head(a, va, {"kernel": k, "bias": bias}, rd_bf16, normalize=normalize)
+    got = out.float().cpu().numpy()
+    assert_close_bf16(got, ref, f"match head dm={dm} normalize={normalize}")
+    assert not got[~va].any()
+    if normalize:
+        assert not got[5].any()
+        n = np.linalg.norm(got[va & (np.arange(cells) != 5)], axis=-1)
+        assert np.abs(n - 1).max() < 2e-2
+
+
 @pytest.mark.parametrize("name,V,hw_img,G,aerial", [
     ("config1", 1, (224, 224), 64, False),     # BASELINE.json configs[0]
     ("sv+aerial", 4, (96, 128), 32, True),

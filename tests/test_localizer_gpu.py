@@ -234,6 +234,31 @@ def test_query_points_lift_matches_grid_lift():
         assert np.array_equal(pf, ff[ci, cj]), f"fused={fused}"
 
 
+def test_per_example_xy_bev_matches_single_example_calls():
+    """data['xy_bev'] [B,N,1,2] with DIFFERENT points per example (`bev_mapper.py:162-166`): BEVMapper.apply splits the
+    batch into single-example launches; each example's result equals the result of calling it alone."""
+    from snap_b200 import bev_mapper, configs, params, synthetic, types
+    G, hw, B = 32, (96, 128), 2
+    rng = np.random.default_rng(12)
+    cfg = configs.bev_mapper(("streetview",))
+    p = params.round_to_bf16(params.perturb_affine(rng, params.init_bev_mapper(rng, cfg)))
+    data = synthetic.make_tile(52, 2, hw, G, batch=B)
+    grid = types.Grid2D((G, G), 0.2)
+    xy = np.stack([np.stack([rng.uniform(0.5, G * 0.2 - 0.5, 300), rng.uniform(0.5, G * 0.2 - 0.5, 300)], -1)[:, None]
+                   for _ in range(B)]).astype(F)                                   # [B,300,1,2], different per example
+    mapper = bev_mapper.BEVMapper(cfg, grid)
+    both = mapper.apply({"params": p}, {**data, "xy_bev": xy})
+    assert both["bev_features"].features.shape == (B, 300, 1, 128) and both["bev_matching"].features.shape == (B, 300, 1, 32)
+    for b in range(B):
+        cam, T = data["camera"], data["T_view2scene"]
+        one = {"images": data["images"][b:b + 1], "camera": types.Camera(wh=cam.wh[b:b + 1], f=cam.f[b:b + 1], c=cam.c[b:b + 1]),
+               "T_view2scene": types.Transform3D(R=T.R[b:b + 1], t=T.t[b:b + 1]), "xy_bev": xy[b]}
+        alone = mapper.apply({"params": p}, one)
+        for k in ("bev_features", "bev_matching"):
+            assert torch.equal(alone[k].features[0], both[k].features[b]) and torch.equal(alone[k].valid[0], both[k].valid[b]), (k, b)
+    assert 0.02 < float(both["bev_features"].valid.float().mean()) < 0.98
+
+
 def test_matching_recovers_known_pose_full_size():
     """Config-4 sized matching block (4,652 frustum points, 128 x 128 map, D = 32, 10,000 poses x 8 retries, 41^3
     refinement) on discriminative synthetic planes: the query features are the map features at the cells the ground
