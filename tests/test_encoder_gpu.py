@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import F, assert_close_bf16, bf16_np, rd_bf16, rel_l2
+from util import F, assert_close_bf16, bf16_np, rd_bf16, rel_l2, record_parity
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
@@ -131,7 +131,8 @@ def test_image_encoder_units_teacher_forced(skip_root, hw, fused_gn):
     rows0 = trace[0][1].numel() // trace[0][1].shape[-1]
     e = rel_l2(x0[:rows0].float().cpu().numpy(), trace[0][1].reshape(rows0, -1).numpy())
     print(f"root: rel_l2 {e:.5f}")
-    assert e < 4e-3
+    record_parity("encoder (teacher-forced)", f"root block, fused_gn={fused_gn}", e, 1e-4)
+    assert e < 1e-4            # measured 0 (a single bf16 rounding of an fp32-accumulated K = 147 dot product)
     worst = 0.0
     for i, u in enumerate(plan.units):
         xin, yout = trace[i + 1]
@@ -143,7 +144,9 @@ def test_image_encoder_units_teacher_forced(skip_root, hw, fused_gn):
         e = rel_l2(out[:rows_out].float().cpu().numpy(), yout.reshape(rows_out, -1).numpy())
         worst = max(worst, e)
         print(f"unit {i} (cin {u['cin']} stride {u['stride']} {u['h']}x{u['w']}): rel_l2 {e:.5f}")
-        assert e < 4e-3, f"unit {i}"
+        # measured <= 1.9e-3 over the 16 units (bf16 flips of the three GroupNorm inputs); tolerance = 1.5 x that
+        assert e < 3e-3, f"unit {i}"
+    record_parity("encoder (teacher-forced)", f"worst of the 16 bottleneck units, fused_gn={fused_gn}", worst, 3e-3)
     # FPN, teacher-forced with the oracle's stage outputs
     ends = np.cumsum(plan.blocks)
     for (buf, h, w, c), end in zip(plan.stage_out, ends):
@@ -154,7 +157,8 @@ def test_image_encoder_units_teacher_forced(skip_root, hw, fused_gn):
     for lvl, (o, (hh, ww), rb) in enumerate(zip(outs, plan.cropped_shapes(), ref_bf)):
         e = rel_l2(o[:, :hh, :ww].float().cpu().numpy(), rb.numpy())
         print(f"fpn level {lvl}: rel_l2 {e:.5f}")
-        assert e < 4e-3
+        record_parity("encoder (teacher-forced)", f"FPN level {lvl}, fused_gn={fused_gn}", e, 3e-4)
+        assert e < 3e-4          # measured <= 1e-4
 
 
 @pytest.mark.parametrize("skip_root,hw", [(False, (40, 72)), (True, (24, 24))])

@@ -153,8 +153,9 @@ def test_lift_backward_chain_vs_autograd():
     errs["d encoder features"] = (rel_l2(got_x, ref_x), rel_l2(got_x, ref_x_free), float(np.linalg.norm(ref_x)))
     for name, (e_tf, e_free, nrm) in errs.items():
         print(f"{name}: |grad| {nrm:.3e} rel err teacher-forced {e_tf:.4f} (free-running {e_free:.4f})")
-        record_parity("lift backward chain", name, e_tf, 2e-2)
-    assert max(e for e, _, _ in errs.values()) < 2e-2, errs
+        record_parity("lift backward chain (teacher-forced arg-max)", name, e_tf, 4e-3)
+    # measured: parameter gradients <= 1.5e-3, encoder-feature cotangent 2.4e-3 (bf16 cotangent rows); tolerance 1.5 x
+    assert max(e for e, _, _ in errs.values()) < 4e-3, errs
     # after the fused forward there is no volume: the backward recomputes it (same kernels -> same bits)
     dcrop1 = dcrop.clone()
     lb2 = streetview_train.LiftBackward(svp, torch.device(dev))

@@ -108,7 +108,9 @@ def test_lift_stats_and_volume_vs_oracle(fisheye):
     print(f"fisheye={fisheye}: valid frac {v.mean():.3f}, rel_l2 volume {e_vol:.5f}, plane {e_plane:.5f}")
     # Tolerance: identical bf16 inputs and rounding points; residual error = fp32 summation order plus
     # expf/logf ulps flipping a few bf16 roundings -> relative L2 <= 5e-3 (bf16 eps = 7.8e-3).
-    assert e_vol < 5e-3 and e_plane < 5e-3
+    record_parity("unfused lift", f"volume rel-L2 vs oracle, fisheye={fisheye}", e_vol, 1e-3)
+    record_parity("unfused lift", f"plane rel-L2 vs oracle, fisheye={fisheye}", e_plane, 1e-3)
+    assert e_vol < 1e-3 and e_plane < 1e-3       # north_star bound; measured 8e-5 (pinhole) / 2.3e-4 (fisheye)
     assert not vol.float().cpu().numpy()[~v].any(), "invalid voxels must be zero (streetview_encoder.py:282)"
 
 
@@ -489,7 +491,7 @@ def test_view_selection_stats_and_volume_vs_oracle(max_dist):
     print(f"max_dist={max_dist}: valid frac {v.mean():.3f}, rel_l2 stats {e_stats:.5f}, volume {e_vol:.5f}")
     # identical bf16 inputs and rounding points (every tap product / partial sum is rounded to bf16 on both sides);
     # residual = expf/logf ulps and fp32 summation order of the pooling -> relative L2 <= 5e-3
-    assert e_stats < 5e-3 and e_vol < 5e-3
+    assert e_stats < 1e-3 and e_vol < 1e-3      # north_star bound; measured <= 1e-5 (statistics) / 1.1e-4 (volume)
     assert not vol.float().cpu().numpy()[~v].any(), "invalid voxels must be zero (streetview_encoder.py:282)"
     assert not stats.float().cpu().numpy()[~any_vis].any(), "statistics of unseen voxels must be zero (:177)"
 
@@ -549,7 +551,7 @@ def test_lift_nondefault_statistics_vs_oracle(add_minmax, use_variance):
     e_stats = rel_l2(got[v, :width], bf16_np(ostats[v]))
     e_vol = rel_l2(vol.float().cpu().numpy()[v], f_grid.reshape(-1, 128)[v])
     print(f"add_minmax={add_minmax} use_variance={use_variance}: rel_l2 stats {e_stats:.5f}, volume {e_vol:.5f}")
-    assert e_stats < 5e-3 and e_vol < 5e-3
+    assert e_stats < 1e-3 and e_vol < 1e-3      # north_star bound; measured <= 1e-5 (statistics) / 1.1e-4 (volume)
 
 
 def test_bev_mapper_runs_with_minmax_statistics():

@@ -53,7 +53,7 @@ def test_vertical_pooling_modes_vs_oracle(mode, Z):
         e = rel_l2(got[rv], rp[rv])
         print(f"{mode} Z={Z}: rel_l2 {e:.2e}")
         # one bf16 rounding of an fp32 accumulation on identical inputs: the summation order flips a few roundings
-        assert e < 3e-3
+        assert e < 1e-3            # measured 0 (sum, mean) .. 2e-5 (softmax, weighted) .. 3.8e-4 (mlp)
     if mode in ("softmax", "weighted"):
         s, w = pred["scores"].cpu().numpy().reshape(cells, Z), pred["weights"].cpu().numpy().reshape(cells, Z)
         # logits are bf16 values of an fp32 dot: a flipped rounding moves one by a bf16 ulp (2^-8 relative)

@@ -66,4 +66,4 @@ def test_unweighted_fusion_volume_and_fused_plane_vs_oracle(V):
     e_m = rel_l2(match_f, ref["bev_matching"]["features"][0])
     print(f"V={V}: rel_l2 volume {e_vol:.5f}, plane unfused {e_pu:.5f}, plane fused {e_pf:.5f}, matching {e_m:.5f}")
     assert not vol[~vol_valid].any() and not plane_f[~pvalid_f].any()
-    assert e_vol < 5e-3 and e_pu < 5e-3 and e_pf < 5e-3 and e_m < 1e-2
+    assert e_vol < 1e-3 and e_pu < 1e-3 and e_pf < 1e-3 and e_m < 1e-3   # north_star bound; measured 8e-5 .. 2.5e-4
