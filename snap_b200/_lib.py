@@ -117,7 +117,7 @@ EXPORTED_SYMBOLS += [
     "snapb200_std_weights_batched", "snapb200_root_im2col", "snapb200_root_pack_image", "snapb200_root_pack_weights",
     "snapb200_root_conv_bf16", "snapb200_maxpool3x3s2",
     "snapb200_gn_stats", "snapb200_gn_apply", "snapb200_upsample2x",
-    "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_lift_select_pool", "snapb200_lift_fused", "snapb200_lift_fused_scratch_bytes", "snapb200_lift_fused_batched", "snapb200_lift_fused_batched_scratch_bytes", "snapb200_vertical_max", "snapb200_vertical_pool", "snapb200_mask_rows", "snapb200_confidence", "snapb200_valid_any", "snapb200_match_head", "snapb200_match_head_ex",
+    "snapb200_crop_relu", "snapb200_lift_gather_pool", "snapb200_lift_select_pool", "snapb200_lift_fused", "snapb200_lift_fused_scratch_bytes", "snapb200_lift_fused_batched", "snapb200_lift_fused_batched_scratch_bytes", "snapb200_lift_observe", "snapb200_lift_pool_observations", "snapb200_vertical_max", "snapb200_vertical_pool", "snapb200_mask_rows", "snapb200_confidence", "snapb200_valid_any", "snapb200_match_head", "snapb200_match_head_ex",
     "snapb200_fuse_max", "snapb200_xcorr_padded_cols", "snapb200_xcorr_padded_rotations", "snapb200_rot_templates",
     "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores", "snapb200_xcorr_scores_sw", "snapb200_xcorr_scores_rows", "snapb200_xcorr_scores_rows_workspace",
     "snapb200_loc_softmax_stats", "snapb200_loc_point_weights", "snapb200_loc_sample", "snapb200_loc_ransac_poses",

@@ -191,7 +191,8 @@ class BEVMapper:
             data["xyz_grid"] = self.build_xyz_grid(data)
         V = data["T_view2scene"].t.shape[1]
         fused = self.fused_lift and not debug and self.config.pooling.pooling == "max" and V <= 4 \
-            and not self.streetview_encoder.uses_view_selection(V) and self.streetview_encoder.default_stats
+            and not self.streetview_encoder.uses_view_selection(V) and self.streetview_encoder.default_stats \
+            and not self.streetview_encoder.has_depth_mlp
         pred = self.streetview_encoder.apply({"params": params["streetview_encoder"]}, data, train, debug=debug,
                                              fused=fused)
         if not fused:

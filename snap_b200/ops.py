@@ -312,6 +312,27 @@ def lift_fused_batched_scratch_bytes() -> int:
     return int(f())
 
 
+def lift_observe(p: "_lib.LiftParams", views: torch.Tensor, fimg: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                 zs: torch.Tensor, obs: torch.Tensor, vis: torch.Tensor) -> None:
+    """Per-observation rows [f(128) | log10 depth | ray(3) | 0...] of the depth_mlp branch (`streetview_encoder.py:262-267`)."""
+    _require(fimg, torch.bfloat16, "fimg")
+    _require(obs, torch.bfloat16, "obs")
+    assert obs.shape[1] == 160 and obs.is_contiguous() and vis.dtype == torch.uint8
+    _lib.check(_lib.lib().snapb200_lift_observe(
+        C.byref(p), C.c_void_p(_ptr(views)), C.c_void_p(_ptr(fimg)), C.c_void_p(_ptr(xs)), C.c_void_p(_ptr(ys)),
+        C.c_void_p(_ptr(zs)), C.c_void_p(_ptr(obs)), C.c_void_p(_ptr(vis)), _stream()))
+
+
+def lift_pool_observations(V: int, N: int, obs: torch.Tensor, d: torch.Tensor, vis: torch.Tensor, stats: torch.Tensor,
+                           valid: torch.Tensor) -> None:
+    """f' = bf16(f + d), plain mean / variance over the visible views -> statistics rows [mean | var | 0...], valid."""
+    _require(d, torch.bfloat16, "d")
+    assert d.shape[1] == 128 and d.is_contiguous() and stats.is_contiguous()
+    _lib.check(_lib.lib().snapb200_lift_pool_observations(
+        C.c_int(V), C.c_longlong(N), C.c_void_p(_ptr(obs)), C.c_void_p(_ptr(d)), C.c_void_p(_ptr(vis)),
+        C.c_int(stats.shape[1]), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(valid)), _stream()))
+
+
 def vertical_max(volume: torch.Tensor, valid: torch.Tensor, cells: int, Z: int, Cc: int,
                  plane: torch.Tensor, pvalid: torch.Tensor) -> None:
     _lib.check(_lib.lib().snapb200_vertical_max(

@@ -98,6 +98,8 @@ def init_streetview_encoder(rng, cfg) -> Dict:
     p = {"image_encoder": init_image_encoder(rng, cfg.image_encoder)}
     if weighted:                              # `:207-213`; without it the module has no proj_mlp
         p["proj_mlp"] = init_mlp(rng, cfg.image_encoder.output_dim, (d + s,))
+    elif cfg.get("depth_mlp") is not None:    # `:214-215`: per-observation MLP on [f | log10 depth | ray]
+        p["depth_mlp"] = init_mlp(rng, d + 4, tuple(cfg.depth_mlp.layers))
     p["fusion_mlp"] = init_mlp(rng, stats_dim, cfg.fusion.layers)
     return p
 

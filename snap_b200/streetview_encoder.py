@@ -81,8 +81,14 @@ class StreetViewEncoder:
     def __init__(self, config=None, dtype=torch.bfloat16):
         self.config = config if config is not None else configs.streetview_encoder()
         c = self.config
-        if c.depth_mlp is not None:
-            raise NotImplementedError("the per-observation depth_mlp residual (streetview_encoder.py:263-267) is not built")
+        # the per-observation depth_mlp residual (`:263-267`): only exists in the un-weighted branch (`:214-215`); runs on
+        # the unfused all-views lift (snapb200_lift_observe -> MLP on the GEMM engine -> snapb200_lift_pool_observations)
+        self.has_depth_mlp = c.depth_mlp is not None and not c.do_weighted_fusion
+        if self.has_depth_mlp:
+            layers_d = tuple(c.depth_mlp.layers or ())
+            if not layers_d or layers_d[-1] != c.feature_dim or any(d % 16 for d in layers_d) or \
+                    c.depth_mlp.get("activation", "relu") != "relu" or c.depth_mlp.get("apply_input_activation", False):
+                raise NotImplementedError("depth_mlp must be a ReLU MLP with layer widths that are multiples of 16 and end in feature_dim")
         # do_weighted_fusion=False (`:262-267` without depth_mlp) runs on the SAME kernels: the sampled maps are the
         # encoder features followed by 32 all-zero scale logits (written by the GEMM engine with the constant operand
         # [I | 0] instead of the proj MLP), which makes the soft-max over the valid views uniform, i.e. [mean | var]
@@ -120,7 +126,15 @@ class StreetViewEncoder:
             if fus0_k.shape[0] != self.stats_dim:
                 raise ValueError(f"fusion_mlp/Dense_0/kernel has {fus0_k.shape[0]} input rows, the configuration needs "
                                  f"{self.stats_dim - (not self.weighted)}")
-            w = dict(bank=bank,
+            depth = []
+            if self.has_depth_mlp:
+                dp = params["depth_mlp"]
+                nlay = len(self.config.depth_mlp.layers)
+                if np.asarray(dp["Dense_0"]["kernel"]).shape[0] != self.config.feature_dim + 4:
+                    raise ValueError("depth_mlp/Dense_0/kernel must have feature_dim + 4 input rows ([f | log depth | ray])")
+                depth = [(bank.add(dp[f"Dense_{i}"]["kernel"], False, k_multiple=32), f32(dp[f"Dense_{i}"]["bias"]))
+                         for i in range(nlay)]
+            w = dict(bank=bank, depth=depth,
                      proj=bank.add(proj_k, False),
                      fus0=bank.add(fus0_k, False, k_multiple=32),
                      fus1=bank.add(params["fusion_mlp"]["Dense_1"]["kernel"], False),
@@ -277,6 +291,9 @@ class StreetViewEncoder:
         lp = fill_lift_params(cfg, V, hf, wf, X, Y, Z, self.stats_ld, paired)
         if (fused or select) and not self.default_stats:
             raise NotImplementedError("fusion_add_minmax / fusion_use_variance=False run on the unfused all-views lift only")
+        if self.has_depth_mlp and (fused or select or not self.default_stats):
+            raise NotImplementedError("depth_mlp runs on the unfused all-views lift with the default statistics "
+                                      "(V <= top_k_view_selection, fused=False)")
         dbg = {}
         if not fused and buf["volume"] is None:
             buf["volume"] = torch.zeros((B, N, 128), dtype=torch.bfloat16, device=dev)
@@ -321,7 +338,21 @@ class StreetViewEncoder:
                 if select:
                     di = torch.zeros((N, Kd), dtype=torch.int32, device=dev)
                     dbg.setdefault("view_indices", []).append(di)
-            if select:   # V > top_k: view selection + selective sampling (`:241-249`)
+            if self.has_depth_mlp:   # un-weighted branch with the per-observation residual (`:263-267`)
+                ob = self._cache.get(("obs", str(dev), N, V))
+                if ob is None:
+                    widths = [160] + list(cfg.depth_mlp.layers)
+                    ob = self._cache[("obs", str(dev), N, V)] = dict(
+                        x=[torch.zeros((image_encoder._round_up(N * V, 128), wd), dtype=torch.bfloat16, device=dev) for wd in widths],
+                        vis=torch.zeros((N, V), dtype=torch.uint8, device=dev))
+                ops.lift_observe(lp, stg["views"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b], ob["x"][0], ob["vis"])
+                for i, (wi, bi) in enumerate(wts["depth"]):      # layers.MLP: Dense -> (relu -> Dense)*
+                    ops.gemm(ob["x"][i], Bm[wi], ob["x"][i + 1], m_rows=N * V, seg_k=ob["x"][i].shape[1], bias=bi,
+                             relu=i + 1 < len(wts["depth"]))
+                ops.lift_pool_observations(V, N, ob["x"][0], ob["x"][-1], ob["vis"], buf["stats"], buf["valid"][b])
+                if debug:
+                    dv.copy_(ob["vis"])
+            elif select:   # V > top_k: view selection + selective sampling (`:241-249`)
                 ops.lift_select_pool(lp, cfg.top_k_view_selection, cfg.get("max_view_distance"), stg["views"][b],
                                      stg["centers"][b], buf["fimg"][b], buf["xs"], buf["ys"], stg["zs"][b],
                                      buf["stats"], buf["valid"][b], di, dv, dt)

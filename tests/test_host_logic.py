@@ -102,9 +102,14 @@ def _leaves(t):
 def test_unsupported_configs_fail_loudly():
     import pytest
     c = configs.bev_mapper()
-    c.streetview_encoder.depth_mlp = configs.mlp()       # the per-observation depth_mlp residual (:263-267): not built
+    c.streetview_encoder.do_weighted_fusion = False
+    c.streetview_encoder.depth_mlp = configs.mlp()       # the per-observation depth_mlp residual (:263-267) needs its layers
     with pytest.raises(NotImplementedError):
         bev_mapper.BEVMapper(c, types.Grid2D((8, 8), 0.2))
+    c.streetview_encoder.depth_mlp.layers = (64, 128)
+    assert bev_mapper.BEVMapper(c, types.Grid2D((8, 8), 0.2)).streetview_encoder.has_depth_mlp
+    c.streetview_encoder.do_weighted_fusion = True      # the weighted branch never builds a depth_mlp (:207-215)
+    assert not bev_mapper.BEVMapper(c, types.Grid2D((8, 8), 0.2)).streetview_encoder.has_depth_mlp
     c3 = configs.bev_mapper()
     c3.streetview_encoder.fusion_add_minmax = True       # built on the unfused lift: [mean | var | max | min | score_max]
     m = bev_mapper.BEVMapper(c3, types.Grid2D((8, 8), 0.2))
@@ -224,8 +229,11 @@ def test_unweighted_fusion_configuration_host_side():
     cfg.fusion_add_minmax = True
     assert params.init_streetview_encoder(np.random.default_rng(0), cfg)["fusion_mlp"]["Dense_0"]["kernel"].shape == (512, 256)
     cfg.depth_mlp = configs.mlp()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # no layer widths given
         sve.StreetViewEncoder(cfg)
+    cfg.depth_mlp.layers = (64, 128)
+    assert sve.StreetViewEncoder(cfg).has_depth_mlp
+    cfg.depth_mlp = None
     # the default (weighted) tree is unchanged: [mean | var | score_max] rows and a 128 -> 160 proj MLP
     tree = params.init_streetview_encoder(np.random.default_rng(0), configs.streetview_encoder())
     assert tree["proj_mlp"]["Dense_0"]["kernel"].shape == (128, 160) and tree["fusion_mlp"]["Dense_0"]["kernel"].shape == (257, 256)
