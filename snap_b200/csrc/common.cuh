@@ -245,6 +245,45 @@ __device__ __forceinline__ void bf16_round2(float& a, float& b) {
   b = bf16_hi(u);
 }
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) { return make_float2(bf16_lo(u), bf16_hi(u)); }
+// Mixed-precision arithmetic of sm_100 (PTX ISA 8.6: {add,sub,fma}.rn.f32.bf16): one operand is a bf16 HALF of a packed
+// register, the result is fp32 with a single rounding -- SASS FHADD.BF16 / FHFMA.BF16 with .H0 / .H1 operand selectors,
+// i.e. no shift / mask to unpack first.  d = bf16 - c, d = bf16 + c, d = bf16 * bf16 + c.
+__device__ __forceinline__ float bf16_lo_sub(uint32_t u, float c) {
+  const unsigned short h = (unsigned short)(u & 0xffffu);
+  float d;
+  asm("sub.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float bf16_hi_sub(uint32_t u, float c) {
+  const unsigned short h = (unsigned short)(u >> 16);
+  float d;
+  asm("sub.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float bf16_lo_add(uint32_t u, float c) {
+  const unsigned short h = (unsigned short)(u & 0xffffu);
+  float d;
+  asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float bf16_hi_add(uint32_t u, float c) {
+  const unsigned short h = (unsigned short)(u >> 16);
+  float d;
+  asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float bf16_lo_sqacc(uint32_t u, float c) {  // lo * lo + c
+  const unsigned short h = (unsigned short)(u & 0xffffu);
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float bf16_hi_sqacc(uint32_t u, float c) {  // hi * hi + c
+  const unsigned short h = (unsigned short)(u >> 16);
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
 // packed bf16 max (HMNMX2.BF16)
 __device__ __forceinline__ uint32_t hmax2_bf16(uint32_t a, uint32_t b) {
   __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);

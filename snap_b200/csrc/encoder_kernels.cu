@@ -375,15 +375,12 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int Nimg, int H, int W, int
     uint32_t ov[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 t = unpack_bf16(uu[j]);
-      if (PRE) {
-        t.x = fmaxf(t.x, 0.f);
-        t.y = fmaxf(t.y, 0.f);
-      }
+      const uint32_t ww = PRE ? hmax2_bf16(uu[j], 0u) : uu[j];
       // resnet.py:39-41,57-69 with a bf16 dtype: standardise in fp32 -> bf16, * scale -> bf16, + bias -> bf16.
-      // The two bf16 ops run as packed HMUL2/HADD2.BF16 (exact product / sum, one rounding each).
-      __nv_bfloat162 v = __floats2bfloat162_rn((t.x - mean[2 * j]) * rstd[2 * j],
-                                               (t.y - mean[2 * j + 1]) * rstd[2 * j + 1]);
+      // x - mean is taken straight from the packed halves (FHADD.BF16: bf16 operand, fp32 result, no unpacking);
+      // the two bf16 ops run as packed HMUL2/HADD2.BF16 (exact product / sum, one rounding each).
+      __nv_bfloat162 v = __floats2bfloat162_rn(bf16_lo_sub(ww, mean[2 * j]) * rstd[2 * j],
+                                               bf16_hi_sub(ww, mean[2 * j + 1]) * rstd[2 * j + 1]);
       v = __hmul2_rn(v, sc2[j]);  // _rn: never contracted into an FMA (two roundings, like the reference)
       v = __hadd2_rn(v, bi2[j]);
       if (post_relu) v = __hmax2(v, zero2);

@@ -138,6 +138,52 @@ static int launch_gn_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPa
 }
 }  // namespace snapb200
 
+namespace snapb200 {
+// A_TGN1 launcher (1x1 convs, stride 1): TMA loads the raw tile, two transformer warps normalise it in shared memory,
+// conv epilogue with staged TMA stores.  Two CTAs per SM when two pipeline stages fit beside the staging slab.
+template <int BN>
+static int launch_t1_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                          const CUtensorMap& tmR, GemmParams p, cudaStream_t s) {
+  using Cfg = GemmCfg<BN, 64>;
+  static DynSmemState smem_state;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, 64, AMODE_TGN1, true>), 227 * 1024,
+                               &smem_state, "cudaFuncSetAttribute(gemm_tc<tgn1>)"))
+    return rc;
+  const int total = p.m_tiles * p.n_tiles;
+  const long long per_img = (long long)p.g_Ho * p.g_Wo;
+  static const int env_ctas = env_int("SNAPB200_T1_CTAS", 0);
+  int ctas = 2, stages = 2, tab = 1, grid = 1;
+  for (;; --ctas) {
+    const int cap = num_sms() * ctas;
+    grid = total < cap ? total : cap;
+    // images a CTA's contiguous tile range can touch: its m-tiles span <= ceil(tiles per CTA / n_tiles) + 1 row blocks
+    const long long tiles_per_cta = (total + grid - 1) / grid + 1;
+    const long long span_rows = ((tiles_per_cta + p.n_tiles - 1) / p.n_tiles + 1) * 128;
+    long long t = (span_rows + per_img - 1) / per_img + 1;
+    tab = (int)(t < p.g_nimg ? t : p.g_nimg);
+    const int budget = ctas == 2 ? (225 * 1024) / 2 : 225 * 1024;
+    stages = p.nkb < Cfg::MAX_STAGES ? p.nkb : Cfg::MAX_STAGES;
+    if (stages < 2) stages = 2;
+    while (stages > 2 && Cfg::smem_bytes_t1(stages, tab, p.g_C) > budget) --stages;
+    const bool fits = Cfg::smem_bytes_t1(stages, tab, p.g_C) <= budget;
+    // a deep K loop wants more than two stages: fall back to one CTA per SM with a deep ring
+    const bool deep_enough = stages >= 3 || p.nkb <= 2;
+    if (ctas == 1) {
+      if (!fits) return set_error(SNAPB200_ERR_INVALID, "conv_gn: shared memory budget exceeded (C=%d)", p.g_C);
+      break;
+    }
+    if (env_ctas == 1) continue;
+    if (fits && (deep_enough || env_ctas == 2)) break;
+  }
+  p.stages = stages;
+  p.g_tab_imgs = tab;
+  p.stage_out = 1;
+  gemm_tc_kernel<BN, 64, AMODE_TGN1, true><<<grid, GEMM_THREADS_T1, Cfg::smem_bytes_t1(stages, tab, p.g_C), s>>>(
+      tmA, tmB, tmO, tmR, p);
+  return check_launch("gemm_tc_kernel<tgn1>");
+}
+}  // namespace snapb200
+
 using namespace snapb200;
 
 /* conv( relu?( GroupNorm( relu?(x) ) ) ) in ONE launch: the A operand of the tcgen05 GEMM is produced in-kernel
@@ -199,6 +245,33 @@ extern "C" int snapb200_conv_gn_bf16(const SnapConvGnParams* q, void* stream) {
   int rc = make_tmap_2d_bf16(&tmB, q->b, q->b_rows, q->b_cols, q->b_ld, bn, 64);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const int env_t1 = env_int("SNAPB200_CONV_GN_T1", 1);
+  const int cpg_in = q->C / 32;
+  const bool t1_ok = env_t1 && q->stride == 1 && q->taps == 1 && q->n % 64 == 0 && M < (1LL << 31) &&
+                     (cpg_in & (cpg_in - 1)) == 0 &&
+                     (reinterpret_cast<uintptr_t>(q->out) & 15) == 0 &&
+                     (q->residual == nullptr || (q->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(q->residual) & 15) == 0));
+  if (t1_ok) {
+    // 1x1 conv: the two-CTAs-per-SM form with the conv epilogue (staged TMA stores, TMA residual)
+    bn = q->n % 128 == 0 ? 128 : 64;
+    p.n_tiles = q->n / bn;
+    while ((1 << p.g_cpg_log) < cpg_in) ++p.g_cpg_log;
+    CUtensorMap tmO, tmR;
+    memset(&tmR, 0, sizeof(tmR));
+    rc = make_tmap_2d_bf16(&tmB, q->b, q->b_rows, q->b_cols, q->b_ld, bn, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tmA, q->x, M, q->C, q->C, 128, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tmO, q->out, M, q->n, q->ldo, 32, 64);
+    if (rc) return rc;
+    p.res_tma = q->residual != nullptr;
+    if (p.res_tma) {
+      rc = make_tmap_2d_bf16(&tmR, q->residual, M, q->n, q->ldr, 32, 64);
+      if (rc) return rc;
+    }
+    if (bn == 64) return launch_t1_inst<64>(tmA, tmB, tmO, tmR, p, s);
+    return launch_t1_inst<128>(tmA, tmB, tmO, tmR, p, s);
+  }
   if (q->stride == 1) {
     // TMA loads the RAW tile from the dense tensor (row-shifted per tap); transformer warps normalise in smem
     rc = make_tmap_2d_bf16(&tmA, q->x, (long long)q->n_img * q->H * q->W, q->C, q->C, 128, 64);

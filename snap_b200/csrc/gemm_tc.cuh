@@ -71,6 +71,8 @@ struct GemmParams {
   const float* g_scale;
   const float* g_bias;
   int g_rep_stride, g_nimg, g_C, g_H, g_W, g_Ho, g_Wo, g_stride, g_taps, g_pre_relu, g_post_relu;
+  int g_cpg_log;   // A_TGN1: log2(C / 32)
+  int g_tab_imgs;  // A_TGN1: images a CTA's contiguous tile range can touch (rows of its statistics table)
   // EPI_XCORR
   const float* xc_cnt;
   const float* xc_den;
@@ -83,7 +85,8 @@ constexpr int GEMM_GN_WARPS = 4;                         // A_GN mode: producer 
 constexpr int GEMM_THREADS_GN = GEMM_THREADS + GEMM_GN_WARPS * 32;  // 448
 constexpr int GEMM_TGN_WARPS = 8;                        // A_TGN mode: in-smem transformer warps (2 threads per row)
 constexpr int GEMM_THREADS_TGN = GEMM_THREADS + GEMM_TGN_WARPS * 32;  // 576
-enum { AMODE_TMA = 0, AMODE_GN = 1, AMODE_TGN = 2 };
+constexpr int GEMM_THREADS_T1 = GEMM_THREADS;  // A_TGN1 mode: the eight epilogue warps also transform the A tiles
+enum { AMODE_TMA = 0, AMODE_GN = 1, AMODE_TGN = 2, AMODE_TGN1 = 3 };
 constexpr int GEMM_GN_MAX_IMG = 32;
 constexpr int GEMM_GN_TABLE_BYTES = GEMM_GN_MAX_IMG * 32 * 8 + 2048 * 4;  // statistics + packed scale/bias
 
@@ -105,6 +108,10 @@ struct GemmCfg {
   static constexpr int smem_bytes(int stages, bool gn_tables = false, bool stage_out = false) {
     return stages * STAGE_BYTES + (stage_out ? OUT_STAGE_BYTES : 0) + 1024 + 512 +
            (gn_tables ? GEMM_GN_TABLE_BYTES : 0);
+  }
+  // A_TGN1: staged output + tables sized for the images one CTA touches and the C input channels
+  static constexpr int smem_bytes_t1(int stages, int tab_imgs, int C) {
+    return stages * STAGE_BYTES + OUT_STAGE_BYTES + 1024 + 512 + tab_imgs * 256 + C * 4;
   }
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(BK == 64 || BK == 32, "BK is one swizzle span: 128B or 64B of bf16");
@@ -147,22 +154,12 @@ __device__ __forceinline__ int seg_row_offset(const GemmParams& p, int seg) {
 // are reduced with a recursive-halving exchange (NV-1 + (5 - log2 NV) shuffles instead of 5 * NV): after it, lane L
 // holds the warp total of value index L >> (5 - log2 NV), and those lanes issue ONE coalesced double atomic
 // instruction.  Warps straddling an image boundary fall back to per-row atomics.
-template <int SPAN>  // columns per group inside the 16-column chunk: 2, 4, 8 or 16
-__device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row_ok, int img, int group0,
-                                                  double* acc, bool uniform, int img_ref, int lane) {
-  constexpr int NG = 16 / SPAN;
-  constexpr int NV = 2 * NG;
-  float val[NV];
+template <int NV>  // NV = 2 * (groups in the chunk) partial moments per row: (sum, sumsq) per group
+__device__ __forceinline__ void gn_reduce_moments(float (&val)[NV], bool row_ok, int img, int group0, double* acc,
+                                                  bool uniform, int img_ref, int lane) {
+  if (!row_ok) {
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    float s = 0.f, q = 0.f;
-#pragma unroll
-    for (int j = 0; j < SPAN; ++j) {
-      s += v[g * SPAN + j];
-      q += v[g * SPAN + j] * v[g * SPAN + j];
-    }
-    val[2 * g] = row_ok ? s : 0.f;
-    val[2 * g + 1] = row_ok ? q : 0.f;
+    for (int i = 0; i < NV; ++i) val[i] = 0.f;
   }
   if (uniform) {
     int off = 16;
@@ -187,6 +184,61 @@ __device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row
   }
 }
 
+template <int SPAN>  // columns per group inside the 16-column chunk: 2, 4, 8 or 16
+__device__ __forceinline__ void gn_accumulate16_t(const float (&v)[16], bool row_ok, int img, int group0,
+                                                  double* acc, bool uniform, int img_ref, int lane) {
+  constexpr int NG = 16 / SPAN;
+  constexpr int NV = 2 * NG;
+  float val[NV];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < SPAN; ++j) {
+      s += v[g * SPAN + j];
+      q += v[g * SPAN + j] * v[g * SPAN + j];
+    }
+    val[2 * g] = s;
+    val[2 * g + 1] = q;
+  }
+  gn_reduce_moments<NV>(val, row_ok, img, group0, acc, uniform, img_ref, lane);
+}
+
+// Packed form: the 16 stored bf16 values of the chunk as 8 words.  Sums and sums of squares come straight from the
+// packed halves with the mixed-precision adds / FMAs of sm_100 (FHADD.BF16 / FHFMA.BF16): 2 instructions per value
+// instead of unpack + FADD + FFMA; same summation order as the fp32 form.
+template <int SPAN>
+__device__ __forceinline__ void gn_accumulate16p_t(const uint32_t (&pk)[8], bool row_ok, int img, int group0,
+                                                   double* acc, bool uniform, int img_ref, int lane) {
+  constexpr int NG = 16 / SPAN;
+  float val2[2 * NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < SPAN / 2; ++j) {
+      const uint32_t w = pk[g * (SPAN / 2) + j];
+      s = bf16_lo_add(w, s);
+      q = bf16_lo_sqacc(w, q);
+      s = bf16_hi_add(w, s);
+      q = bf16_hi_sqacc(w, q);
+    }
+    val2[2 * g] = s;
+    val2[2 * g + 1] = q;
+  }
+  gn_reduce_moments<2 * NG>(val2, row_ok, img, group0, acc, uniform, img_ref, lane);
+}
+__device__ __forceinline__ void gn_accumulate16p(const uint32_t (&pk)[8], bool row_ok, int img, int col, int cpg_log,
+                                                 double* acc, bool uniform, int img_ref, int lane) {
+  const int group0 = col >> cpg_log;
+  switch (cpg_log) {
+    case 1: gn_accumulate16p_t<2>(pk, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+    case 2: gn_accumulate16p_t<4>(pk, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+    case 3: gn_accumulate16p_t<8>(pk, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+    default: gn_accumulate16p_t<16>(pk, row_ok, img, group0, acc, uniform, img_ref, lane); break;
+  }
+}
+
 // cpg_log = log2(channels per group); group of column col = col >> cpg_log
 __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool row_ok, int img, int col,
                                                 int cpg_log, double* acc, bool uniform, int img_ref,
@@ -203,17 +255,26 @@ __device__ __forceinline__ void gn_accumulate16(const float (&v)[16], bool row_o
 // AMODE_TMA: A tiles come straight from TMA.  AMODE_GN: producer warps build the A tile from the raw tensor through
 // registers (any stride).  AMODE_TGN: TMA loads the RAW tile (dense layout, row-shifted per 3x3 tap) and
 // transformer warps apply GroupNorm + affine + ReLU IN PLACE in shared memory (stride 1 only).
+// AMODE_TGN1: the 1x1-conv form of A_TGN built for two CTAs per SM (320 threads, like the plain TMA mode): the eight
+// epilogue warps are "workers" that first normalise the raw K blocks of tile t in shared memory (16 rows per warp,
+// a thread owns one 16-byte channel chunk of 4 rows: scale / bias / statistics stay in registers for the K block) and
+// then drain the accumulator of tile t - 1 (conv epilogue with staged TMA stores / TMA residual), so the MMA of tile t
+// runs under that epilogue.  Statistics tables cover only the images the CTA's contiguous tile range touches.
 // CONVEPI: epilogue specialised for plain conv outputs (bf16, staged TMA store, optional TMA residual, optional
 // GroupNorm statistics; no bias / activation / mask / remap): the generic epilogue is compiled out.
 template <int BN, int BK, int AMODE = AMODE_TMA, bool CONVEPI = false>
-__global__ void __launch_bounds__(AMODE == AMODE_GN ? GEMM_THREADS_GN : (AMODE == AMODE_TGN ? GEMM_THREADS_TGN : GEMM_THREADS),
-                                  AMODE == AMODE_TMA ? 2 : 1)
+__global__ void __launch_bounds__(AMODE == AMODE_GN    ? GEMM_THREADS_GN
+                                  : AMODE == AMODE_TGN  ? GEMM_THREADS_TGN
+                                  : AMODE == AMODE_TGN1 ? GEMM_THREADS_T1
+                                                        : GEMM_THREADS,
+                                  (AMODE == AMODE_TMA || AMODE == AMODE_TGN1) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, BK>;
   constexpr bool AGN = AMODE == AMODE_GN;
   constexpr bool TGN = AMODE == AMODE_TGN;
+  constexpr bool T1 = AMODE == AMODE_TGN1;
   const int STAGES = p.stages;
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked), so every
   // buffer below is a constant offset from the window base instead of a runtime-aligned pointer
@@ -231,17 +292,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // A_GN / A_TGN tables (after the 512 B barrier block): per (image, group) (mean, rstd) and per channel pair packed
   // bf16x2 scale / bias
   float2* g_stat = reinterpret_cast<float2*>(out_stage + out_stage_bytes + 512);
-  uint32_t* g_sc2 = reinterpret_cast<uint32_t*>(g_stat + GEMM_GN_MAX_IMG * 32);
-  uint32_t* g_bi2 = g_sc2 + 1024;
+  uint32_t* g_sc2 = reinterpret_cast<uint32_t*>(g_stat + (T1 ? p.g_tab_imgs : GEMM_GN_MAX_IMG) * 32);
+  uint32_t* g_bi2 = g_sc2 + (T1 ? p.g_C / 2 : 1024);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int w_tma = 0, w_mma = 1;
   const int total_tiles = p.m_tiles * p.n_tiles;
   // contiguous tile range per CTA (same image / same A rows stay together: L2 locality, fewer GN flushes)
   const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
   const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == w_tma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.stage_out) tma_prefetch_desc(&tmO);
@@ -251,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], AGN ? 1 + GEMM_GN_WARPS * 32 : 1);
       mbar_init(&empty_bar[s], 1);
       if (TGN) mbar_init(&ready_bar[s], GEMM_TGN_WARPS * 32);
+      if (T1) mbar_init(&ready_bar[s], GEMM_EPI_WARPS);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -258,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  if (warp == w_mma) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
   if ((AGN || TGN) && warp >= 2 + GEMM_EPI_WARPS) {
     const int t = threadIdx.x - (2 + GEMM_EPI_WARPS) * 32;
     constexpr int NT = (TGN ? GEMM_TGN_WARPS : GEMM_GN_WARPS) * 32;
@@ -281,12 +344,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       g_bi2[c2] = pack_bf16(__ldg(p.g_bias + 2 * c2), __ldg(p.g_bias + 2 * c2 + 1));
     }
   }
+  // A_TGN1: first image of this CTA's statistics table (its tiles are contiguous in m)
+  const int t1_img0 = T1 ? (int)(((long long)(tile_begin / p.n_tiles) * 128) / ((long long)p.g_Ho * p.g_Wo)) : 0;
+  if (T1) {
+    // every thread helps: (mean, rstd) of the images this CTA touches, packed scale / bias of all channels
+    const int cpg = p.g_C / 32;
+    const double count = (double)p.g_H * (double)p.g_W * (double)cpg;
+    const int n_tab = min(p.g_tab_imgs, p.g_nimg - t1_img0);
+    for (int e = threadIdx.x; e < n_tab * 32; e += GEMM_THREADS_T1) {
+      const size_t src = ((size_t)t1_img0 * 32 + e) * 2;
+      double su = 0.0, sq = 0.0;
+#pragma unroll
+      for (int rep = 0; rep < GN_REPLICAS; ++rep) {
+        su += p.g_acc[(size_t)rep * p.g_rep_stride + src];
+        sq += p.g_acc[(size_t)rep * p.g_rep_stride + src + 1];
+      }
+      const double mu = su / count;
+      double var = sq / count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      g_stat[e] = make_float2((float)mu, (float)(1.0 / sqrt(var + 1e-5)));
+    }
+    for (int c2 = threadIdx.x; c2 < p.g_C / 2; c2 += GEMM_THREADS_T1) {
+      g_sc2[c2] = pack_bf16(__ldg(p.g_scale + 2 * c2), __ldg(p.g_scale + 2 * c2 + 1));
+      g_bi2[c2] = pack_bf16(__ldg(p.g_bias + 2 * c2), __ldg(p.g_bias + 2 * c2 + 1));
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (warp == w_tma) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       int stage = 0;
@@ -328,7 +416,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == w_mma) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
@@ -341,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(TGN ? &ready_bar[stage] : &full_bar[stage], phase);
+          mbar_wait((TGN || T1) ? &ready_bar[stage] : &full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -546,7 +634,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           p.gn_acc_relu != nullptr ? p.gn_acc_relu + (size_t)(blockIdx.x % GN_REPLICAS) * p.gn_replica_stride : nullptr;
       const int m_valid = (int)p.M_valid;
       const int rpi = (int)p.gn_rows_per_img;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      auto epi_tile = [&](int tile) {
         const TileCoord t = decode_tile(p, tile, BN);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after_sync();
@@ -590,19 +678,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           *reinterpret_cast<uint4*>(p0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(p1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          if (gacc != nullptr) {
-            float g[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 x = unpack_bf16(pk[j]);  // the stored (rounded) values
-              g[2 * j] = x.x;
-              g[2 * j + 1] = x.y;
-            }
-            gn_accumulate16(g, row_ok, gn_img, col0 + i * 16, p.gn_cpg_log, gacc, gn_uniform, gn_ref, lane);
+          if (gacc != nullptr) {  // statistics of the stored (rounded) values, straight from the packed words
+            gn_accumulate16p(pk, row_ok, gn_img, col0 + i * 16, p.gn_cpg_log, gacc, gn_uniform, gn_ref, lane);
             if (gacc_relu != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) g[j] = fmaxf(g[j], 0.f);
-              gn_accumulate16(g, row_ok, gn_img, col0 + i * 16, p.gn_cpg_log, gacc_relu, gn_uniform, gn_ref, lane);
+              for (int j = 0; j < 8; ++j) pk[j] = hmax2_bf16(pk[j], 0u);
+              gn_accumulate16p(pk, row_ok, gn_img, col0 + i * 16, p.gn_cpg_log, gacc_relu, gn_uniform, gn_ref, lane);
             }
           }
         }
@@ -625,6 +706,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           acc = 0;
           acc_phase ^= 1;
         }
+      };
+      if constexpr (!T1) {
+        for (int tile = tile_begin; tile < tile_end; ++tile) epi_tile(tile);
+      } else if constexpr (BK == 64) {
+        // ---------------- A_TGN1 worker loop: normalise tile t's K blocks in place, then drain tile t - 1 ----------
+        const int wk = warp - 2;                       // rows 16 wk .. 16 wk + 15 of every K block
+        const int c = lane & 7;                        // 16-byte chunk (8 channels) of the 128-byte row
+        const int r0 = 16 * wk + (lane >> 3);          // rows r0 + 4 i, i = 0..3: a warp touches 4 whole rows per step
+        // SWIZZLE_128B: chunk c of row r sits at c ^ (r % 8); r % 8 = (lane >> 3) + 4 (i & 1)
+        const uint32_t off_e = (uint32_t)(r0 * 128 + ((c ^ (lane >> 3)) << 4));
+        const uint32_t off_o = (uint32_t)((r0 + 4) * 128 + ((c ^ ((lane >> 3) + 4)) << 4));
+        const int cpg_log = p.g_cpg_log;  // channels per group = C / 32, a power of two (checked by the host)
+        const int per_img = p.g_Ho * p.g_Wo;
+        const uint32_t post_lo = p.g_post_relu ? 0u : 0xff80ff80u;  // optional ReLU = packed max against 0 or -inf
+        const bool pre = p.g_pre_relu != 0;
+        // resnet.py:39-41,57-69 in bf16: standardise (fp32) -> bf16, * scale -> bf16, + bias -> bf16 (-> ReLU).
+        // (x - mean) comes straight from the packed halves (FHADD.BF16): 8 instructions per channel pair.
+        auto xform = [&](const uint4& u, const float (&mean)[4], const float (&rstd)[4], const uint4& s4,
+                         const uint4& b4, bool pre_relu) -> uint4 {
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          const uint32_t sc[4] = {s4.x, s4.y, s4.z, s4.w};
+          const uint32_t bi[4] = {b4.x, b4.y, b4.z, b4.w};
+          uint32_t r[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t ww = pre_relu ? hmax2_bf16(w[jj], 0u) : w[jj];
+            __nv_bfloat162 v = __floats2bfloat162_rn(bf16_lo_sub(ww, mean[jj]) * rstd[jj],
+                                                     bf16_hi_sub(ww, mean[jj]) * rstd[jj]);
+            v = __hmul2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&sc[jj]));
+            v = __hadd2_rn(v, *reinterpret_cast<const __nv_bfloat162*>(&bi[jj]));
+            r[jj] = hmax2_bf16(*reinterpret_cast<uint32_t*>(&v), post_lo);
+          }
+          return make_uint4(r[0], r[1], r[2], r[3]);
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+          const int mt0 = (tile / p.n_tiles) * 128;
+          const int img_a = mt0 / per_img - t1_img0;
+          const bool uniform = (min(mt0 + 127, m_valid - 1) / per_img - t1_img0) == img_a;
+#pragma unroll 1
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            // per K block this thread's 8 channels are fixed: scale / bias / group statistics stay in registers
+            const int ch0 = kb * 64 + c * 8;
+            const uint4 s4 = *reinterpret_cast<const uint4*>(g_sc2 + (ch0 >> 1));
+            const uint4 b4 = *reinterpret_cast<const uint4*>(g_bi2 + (ch0 >> 1));
+            const int g0 = ch0 >> cpg_log;
+            float mean[4], rstd[4];
+            auto load_stats = [&](int img) {
+              if (cpg_log >= 3) {  // the chunk's 8 channels share one group
+                const float2 st = g_stat[img * 32 + g0];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  mean[jj] = st.x;
+                  rstd[jj] = st.y;
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float2 st = g_stat[img * 32 + g0 + ((2 * jj) >> cpg_log)];  // group of channel ch0 + 2 jj
+                  mean[jj] = st.x;
+                  rstd[jj] = st.y;
+                }
+              }
+            };
+            load_stats(img_a);
+            mbar_wait(&full_bar[stage], phase);  // raw tile (and the weights) have landed
+            uint8_t* base = smem + stage * Cfg::STAGE_BYTES;
+            uint4* slot[4] = {reinterpret_cast<uint4*>(base + off_e), reinterpret_cast<uint4*>(base + off_o),
+                              reinterpret_cast<uint4*>(base + off_e + 1024), reinterpret_cast<uint4*>(base + off_o + 1024)};
+            if (uniform) {
+              uint4 u[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) u[j] = *slot[j];
+              if (pre) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) u[j] = xform(u[j], mean, rstd, s4, b4, true);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) u[j] = xform(u[j], mean, rstd, s4, b4, false);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *slot[j] = u[j];
+            } else {  // the tile straddles images (or images smaller than a tile): statistics per row
+#pragma unroll 1
+              for (int i = 0; i < 4; ++i) {
+                const int m = min(mt0 + r0 + 4 * i, m_valid - 1);
+                load_stats(m / per_img - t1_img0);
+                *slot[i] = xform(*slot[i], mean, rstd, s4, b4, pre);
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready_bar[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (tile > tile_begin) epi_tile(tile - 1);
+        }
+        if (tile_begin < tile_end) epi_tile(tile_end - 1);
       }
       if (hw == 0 && lane == 0) bulk_wait_group0();
     } else
@@ -875,7 +1058,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == w_mma) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace snapb200

@@ -83,10 +83,11 @@ class EncoderPlan:
     """Launch plan + workspace of one ImageEncoder for a fixed input shape [n_img, H, W, 3]."""
 
     def __init__(self, params: Dict, config, n_img: int, H: int, W: int, device: torch.device,
-                 fused_gn: bool = False):
+                 fused_gn="auto"):
         # fused_gn: GroupNorm+ReLU fused into the conv's A-operand path (`snapb200_conv_gn_bf16`, one launch per
-        # conv, no normalised copies in HBM).  Parity-green but currently slower than the two-launch path
-        # (GroupNorm-apply kernel + TMA GEMM with two CTAs per SM), so off by default (profiles/r01_notes.md).
+        # conv, no normalised copy in HBM).  "auto" (default): see `run_unit`.  "1x1": every stride-1 1x1 conv (conv1, conv3, conv_proj, FPN
+        # skip convs) normalises its raw input in shared memory; the 3x3 convs keep the GroupNorm-apply kernel, which
+        # writes their zero-bordered / phase-split operand.  True: also the 3x3 convs (slower).  False: no fusion.
         self.fused_gn = fused_gn
         enc_cfg = config.encoder
         self.cfg = config
@@ -236,7 +237,7 @@ class EncoderPlan:
         if forced_input:
             acc1.zero_(); acc2.zero_(); acc3.zero_()
             ops.gn_stats(x, n, h * w, cin, False, acc1)
-        if self.fused_gn:
+        if self.fused_gn is True:
             gn1, gn2, gn3 = u["gn"]
             # every conv normalises its input on the fly (GroupNorm + ReLU fused into the GEMM's A producer)
             if u["wproj"] is not None:  # resnet.py:121-122 (projection of the pre-activated tensor, strided)
@@ -256,22 +257,41 @@ class EncoderPlan:
             ops.conv_gn(y2, n, ho, wo, nmid, acc3, gn3[0], gn3[1], B[u["w3"]], u["out"], taps=1, stride=1,
                         residual=res, gn_acc=next_acc, gn_acc_relu=fpn_acc)
             return u["out"]
-        a1 = self._view(self.buf_a, rows_in, cin)
-        ops.gn_apply(x, n, h, w, cin, acc1, u["gn"][0][0], u["gn"][0][1], False, True, ops.LAYOUT_DENSE, a1,
-                     u.get("a1_sub"))
+        # fused_gn == "1x1": every stride-1 1x1 conv normalises its raw input inside the GEMM (A_TGN1); only the 3x3
+        # conv's input goes through the GroupNorm-apply kernel (it writes the zero-bordered / phase-split copy).
+        # "auto" (default) fuses where it is measured to pay (profiles/r02_notes.md): conv1 / conv_proj of the units
+        # whose bottleneck width fits one N tile (stages 1-2: the 352 / 176 MB pre-activation copy disappears) and the
+        # FPN skip convs; conv3 (epilogue-bound: residual + statistics) and the narrow-M stages 3-4 keep the apply pass.
+        f1 = self.fused_gn == "1x1" or (self.fused_gn == "auto" and nmid <= 128)
+        f3 = self.fused_gn == "1x1"
+        gn1, gn2, gn3 = u["gn"]
         joined = True
-        if u["wproj"] is not None:  # resnet.py:121-122 (projection of the pre-activated tensor)
-            res = self._view(self.buf_res, rows_out, nout)
-            # conv_proj and conv1 both read a1 and are independent: run the projection on a side stream
-            main, side = torch.cuda.current_stream(), self._side()
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                ops.gemm(u["a1_sub"] if s == 2 else a1, B[u["wproj"]], res, m_rows=rows_out)
-            joined = False
-        else:
-            res = x
         y1 = self._view(self.buf_y, rows_in, nmid)
-        ops.gemm(a1, B[u["w1"]], y1, m_rows=rows_in, gn_acc=acc2, gn_rows_per_img=h * w)
+        if f1 and s == 1:
+            if u["wproj"] is not None:  # resnet.py:121-122 (projection of the pre-activated tensor)
+                res = self._view(self.buf_res, rows_out, nout)
+                main, side = torch.cuda.current_stream(), self._side()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.conv_gn(x, n, h, w, cin, acc1, gn1[0], gn1[1], B[u["wproj"]], res)
+                joined = False
+            else:
+                res = x
+            ops.conv_gn(x, n, h, w, cin, acc1, gn1[0], gn1[1], B[u["w1"]], y1, gn_acc=acc2)
+        else:
+            a1 = self._view(self.buf_a, rows_in, cin)
+            ops.gn_apply(x, n, h, w, cin, acc1, gn1[0], gn1[1], False, True, ops.LAYOUT_DENSE, a1, u.get("a1_sub"))
+            if u["wproj"] is not None:
+                res = self._view(self.buf_res, rows_out, nout)
+                # conv_proj and conv1 both read a1 and are independent: run the projection on a side stream
+                main, side = torch.cuda.current_stream(), self._side()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.gemm(u["a1_sub"] if s == 2 else a1, B[u["wproj"]], res, m_rows=rows_out)
+                joined = False
+            else:
+                res = x
+            ops.gemm(a1, B[u["w1"]], y1, m_rows=rows_in, gn_acc=acc2, gn_rows_per_img=h * w)
         if s == 1:
             ops.gn_apply(y1, n, h, w, nmid, acc2, u["gn"][1][0], u["gn"][1][1], False, True, ops.LAYOUT_PADDED, u["a2"])
             hp, wp = h + 2, w + 2
@@ -287,15 +307,20 @@ class EncoderPlan:
         ops.gemm(u["a2"], B[u["w2"]], y2, m_rows=m_rows, seg_off=seg, seg_k=nmid, remap=remap,
                  gn_acc=acc3, gn_rows_per_img=ho * wo)
         if not joined:
-            # a3 reuses the buffer of a1, which the projection (side stream) is still reading
+            # a3 reuses the buffer of a1, which the projection (side stream) is still reading; conv3 adds its result
             torch.cuda.current_stream().wait_stream(self._side())
-        a3 = self._view(self.buf_a, rows_out, nmid)
-        ops.gn_apply(y2, n, ho, wo, nmid, acc3, u["gn"][2][0], u["gn"][2][1], False, True, ops.LAYOUT_DENSE, a3)
         fpn_acc = u.get("fpn_acc")
         if forced_input and fpn_acc is not None:
             fpn_acc.zero_()
         if next_acc is None and fpn_acc is not None:
             next_acc = self.acc_scratch
+        if f3:
+            # conv2 wrote y2 (raw): conv3 normalises it while loading
+            ops.conv_gn(y2, n, ho, wo, nmid, acc3, gn3[0], gn3[1], B[u["w3"]], u["out"], residual=res,
+                        gn_acc=next_acc, gn_acc_relu=fpn_acc)
+            return u["out"]
+        a3 = self._view(self.buf_a, rows_out, nmid)
+        ops.gn_apply(y2, n, ho, wo, nmid, acc3, gn3[0], gn3[1], False, True, ops.LAYOUT_DENSE, a3)
         ops.gemm(a3, B[u["w3"]], u["out"], m_rows=rows_out, residual=res, gn_acc=next_acc, gn_acc_relu=fpn_acc,
                  gn_rows_per_img=ho * wo)
         return u["out"]
@@ -311,7 +336,7 @@ class EncoderPlan:
             if forced_input:
                 acc.zero_()
                 ops.gn_stats(f["x"], n, f["h"] * f["w"], f["c"], True, acc)
-            if self.fused_gn:
+            if self.fused_gn:  # True, "1x1" or "auto": the skip conv is a 1x1 conv
                 if prev is not None:
                     ops.upsample2x(prev["out"], n, prev["h"], prev["w"], self.out_dim, f["up"])
                 # relu -> GroupNorm -> 1x1 conv (+ up-sampled coarser level) in one launch
@@ -365,7 +390,7 @@ class ImageEncoder:
 
     default_config = staticmethod(configs.image_encoder)
 
-    def __init__(self, config=None, dtype=torch.bfloat16, fused_gn: bool = False):
+    def __init__(self, config=None, dtype=torch.bfloat16, fused_gn="auto"):
         self.fused_gn = fused_gn
         if dtype != torch.bfloat16:
             raise NotImplementedError("the B200 path computes in bf16 (fp32 accumulate / statistics)")

@@ -107,7 +107,9 @@ def test_gn_maxpool_upsample_im2col_vs_oracle():
 
 
 @pytest.mark.parametrize("skip_root,hw,fused_gn", [(False, (40, 72), False), (True, (24, 24), False),
-                                                   (False, (40, 72), True), (True, (24, 24), True)])
+                                                   (False, (40, 72), True), (True, (24, 24), True),
+                                                   (False, (40, 72), "1x1"), (True, (24, 24), "1x1"),
+                                                   (False, (40, 72), "auto")])
 def test_image_encoder_units_teacher_forced(skip_root, hw, fused_gn):
     """Every residual unit, the root block and the FPN, each fed the ORACLE's (bf16-mode) input of that
     block, vs the oracle's output of that block.  Both sides round at the same points, so the only
@@ -226,3 +228,49 @@ def test_implicit_root_conv_vs_im2col_gemm(KH, stride, pad, hw):
     g = got.reshape(n, Ho * Wo, 32, cout // 32).astype(np.float64)
     assert np.allclose(s[..., 0], g.sum((1, 3)), rtol=1e-6, atol=1e-3)
     assert np.allclose(s[..., 1], (g * g).sum((1, 3)), rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("n_img,hw,C,N,res,pre,post,relu_acc", [
+    (3, (40, 64), 256, 64, False, False, True, False),    # conv1 of stage 1; 2560 rows per image = 20 whole tiles
+    (3, (33, 40), 64, 256, True, False, True, True),      # conv3 + residual + both statistics; tiles straddle images
+    (2, (30, 44), 512, 128, False, False, True, False),   # conv1 of stage 2 (K = 8 blocks)
+    (5, (7, 9), 128, 512, True, False, True, False),      # images smaller than a tile
+    (2, (32, 48), 1024, 128, True, True, False, False),   # FPN skip conv: relu -> GN -> conv + up-sampled level
+    (2, (24, 40), 2048, 512, False, False, True, False),  # conv1 of stage 4: deep K loop (one CTA per SM)
+])
+def test_conv_gn_1x1_equals_apply_then_gemm(n_img, hw, C, N, res, pre, post, relu_acc):
+    """The A_TGN1 mode of `snapb200_conv_gn_bf16` (GroupNorm + ReLU applied to the raw tile in shared memory, conv
+    epilogue) against the two-launch path it replaces (`gn_apply` -> `gemm`): same rounding chain and the same
+    K order, so the stored outputs must be BIT-identical; the statistics of the output agree to double rounding."""
+    from snap_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(C + N)
+    dev = torch.device("cuda")
+    H, W = hw
+    rows = n_img * H * W
+    x = (torch.randn((rows, C), device=dev, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    b = (torch.randn((N, C), device=dev, generator=g) * C ** -0.5).to(torch.bfloat16)
+    r = torch.randn((rows, N), device=dev, generator=g).to(torch.bfloat16) if res else None
+    scale = (1 + 0.2 * torch.randn(C, device=dev, generator=g)).to(torch.bfloat16).float()
+    bias = (0.2 * torch.randn(C, device=dev, generator=g)).to(torch.bfloat16).float()
+    acc = torch.zeros((ops.GN_REPLICAS, n_img, 32, 2), dtype=torch.float64, device=dev)
+    ops.gn_stats(x, n_img, H * W, C, pre, acc)
+    outs, stats = [], []
+    for fused in (False, True):
+        out = torch.full((rows + 128, N), 7.0, dtype=torch.bfloat16, device=dev)
+        a1 = torch.zeros((ops.GN_REPLICAS, n_img, 32, 2), dtype=torch.float64, device=dev)
+        a2 = torch.zeros_like(a1)
+        if fused:
+            ops.conv_gn(x, n_img, H, W, C, acc, scale, bias, b, out, pre_relu=pre, post_relu=post, residual=r,
+                        gn_acc=a1, gn_acc_relu=a2 if relu_acc else None)
+        else:
+            a = torch.zeros((rows + 128, C), dtype=torch.bfloat16, device=dev)
+            ops.gn_apply(x, n_img, H, W, C, acc, scale, bias, pre, post, ops.LAYOUT_DENSE, a)
+            ops.gemm(a, b, out, m_rows=rows, residual=r, gn_acc=a1, gn_acc_relu=a2 if relu_acc else None,
+                     gn_rows_per_img=H * W)
+        torch.cuda.synchronize()
+        outs.append(out.view(torch.int16).cpu().numpy())
+        stats.append((a1.sum(0).cpu().numpy(), a2.sum(0).cpu().numpy()))
+    assert np.array_equal(outs[0][:rows], outs[1][:rows])
+    assert (outs[1][rows:] == outs[0][rows:]).all()  # rows beyond M stay untouched
+    for s0, s1 in zip(stats[0], stats[1]):
+        np.testing.assert_allclose(s1, s0, rtol=1e-12, atol=1e-9)

@@ -18,6 +18,14 @@ if which == "conv3":
 elif which == "conv1":
     a, b, out = bf(rows + 128, 256), bf(64, 256), bf(rows + 128, 64)
     fn = lambda: ops.gemm(a, b, out, m_rows=rows, gn_acc=acc, gn_rows_per_img=h * w)
+elif which in ("fconv1", "fconv3"):  # fused GroupNorm -> 1x1 conv (A_TGN1)
+    k, n = (256, 64) if which == "fconv1" else (64, 256)
+    x, b, out = bf(rows + 128, k), bf(n, k), bf(rows + 128, n)
+    r = bf(rows + 128, n) if which == "fconv3" else None
+    acc_in = torch.zeros_like(acc)
+    ops.gn_stats(x, NIMG, h * w, k, False, acc_in)
+    sc, bi = torch.ones(k, device=dev), torch.zeros(k, device=dev)
+    fn = lambda: ops.conv_gn(x, NIMG, h, w, k, acc_in, sc, bi, b, out, residual=r, gn_acc=acc)
 else:
     hp, wp = h + 2, w + 2
     a, b, out = bf(NIMG * hp * wp + 4 * wp + 256, 64), bf(64, 576), bf(rows + 128, 64)

@@ -59,6 +59,28 @@ def case(name, h, w, k, n, taps=1, res=False, gn=True, gn_relu=False, bn=0):
     return dict(name=name, ms=ms, gbps=byt / ms / 1e6, tflops=fl / ms / 1e9)
 
 
+def fused_case(name, h, w, k, n, res=False, gn=True, gn_relu=False):
+    """conv_gn (A_TGN1): GroupNorm + ReLU of the raw input inside the GEMM; compare with gn_apply + gemm."""
+    rows = NIMG * h * w
+    x = bf(rows + 128, k)
+    b = bf(max(n, 16), k)
+    acc_in = torch.zeros((ops.GN_REPLICAS, NIMG, 32, 2), dtype=torch.float64, device=dev)
+    ops.gn_stats(x, NIMG, h * w, k, False, acc_in)
+    acc = torch.zeros_like(acc_in)
+    acc2 = torch.zeros_like(acc_in)
+    out = torch.zeros((rows + 128, n), dtype=torch.bfloat16, device=dev)
+    r = bf(rows + 128, n) if res else None
+    sc = torch.ones(k, device=dev)
+    bi = torch.zeros(k, device=dev)
+    ms = timeit(lambda: ops.conv_gn(x, NIMG, h, w, k, acc_in, sc, bi, b, out, residual=r, gn_acc=acc if gn else None,
+                                    gn_acc_relu=acc2 if (gn and gn_relu) else None))
+    byt = rows * k * 2 + rows * n * 2 * (2 if res else 1) + n * k * 2
+    fl = 2.0 * rows * n * k
+    print(f"{name:34s} M={rows:7d} K={k:5d} N={n:5d} res={int(res)} gn={int(gn)}{'+r' if gn_relu else '  '} FUSED "
+          f"  {ms * 1e3:8.1f} us  {byt / ms / 1e6:7.0f} GB/s  {fl / ms / 1e9:7.0f} TF/s", flush=True)
+    return dict(name=name + " fused", ms=ms, gbps=byt / ms / 1e6, tflops=fl / ms / 1e9)
+
+
 def gn_case(name, h, w, c, layout):
     rows = NIMG * h * w
     x = bf(rows + 128, c)
@@ -94,6 +116,20 @@ res.append(case("s3.conv1 (1024->256)", *S[2], 1024, 256))
 res.append(case("s3.conv3 (256->1024)+res", *S[2], 256, 1024, res=True))
 res.append(case("s4.conv1 (2048->512)", *S[3], 2048, 512))
 res.append(case("s4.conv3 (512->2048)+res", *S[3], 512, 2048, res=True))
+print("== fused GroupNorm -> 1x1 convs (A_TGN1) ==")
+res.append(fused_case("s1.conv1 (256->64)", *S[0], 256, 64))
+res.append(fused_case("s1.conv3 (64->256)+res", *S[0], 64, 256, res=True))
+res.append(fused_case("s1.conv3 +res gn+relu", *S[0], 64, 256, res=True, gn_relu=True))
+res.append(fused_case("s1.proj (64->256)", *S[0], 64, 256, gn=False))
+res.append(fused_case("s2.conv1 unit1 (256->128)", *S[0], 256, 128))
+res.append(fused_case("s2.conv1 (512->128)", *S[1], 512, 128))
+res.append(fused_case("s2.conv3 (128->512)+res", *S[1], 128, 512, res=True))
+res.append(fused_case("s3.conv1 (1024->256)", *S[2], 1024, 256))
+res.append(fused_case("s3.conv3 (256->1024)+res", *S[2], 256, 1024, res=True))
+res.append(fused_case("s4.conv1 (2048->512)", *S[3], 2048, 512))
+res.append(fused_case("s4.conv3 (512->2048)+res", *S[3], 512, 2048, res=True))
+res.append(fused_case("fpn s1 (256->128)+res", *S[0], 256, 128, res=True, gn=False))
+res.append(fused_case("fpn s2 (512->128)+res", *S[1], 512, 128, res=True, gn=False))
 print("== 3x3 convs ==")
 res.append(case("s1.conv2 3x3 64", *S[0], 64, 64, taps=9))
 res.append(case("s1.conv2 3x3 64 no-gn", *S[0], 64, 64, taps=9, gn=False))
