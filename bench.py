@@ -438,13 +438,104 @@ def run_cfg5(args):
         dist.destroy_process_group()
 
 
+def run_cfg4_train(args):
+    """configs[3] as the reference TRAINS it (`snap/trainer.py:165-295` around `bev_localizer.py`), data-parallel, with frozen
+    image encoders: per example map BEV (4 views) + query BEV (1 view, field-of-view points) + sampling localizer with the
+    ground truth prepended + NLL, backward down to proj_mlp / fusion_mlp / matching_proj / temperature, the gradient mean over
+    ranks (ONE in-place NCCL all-reduce of the flat bucket, inside the timed region), Adam, non-finite skip."""
+    import torch
+    import torch.distributed as dist
+    from snap_b200 import _lib, bev_localizer, configs, localizer_trainer, params, synthetic, types
+    rank, world, local, dev = _dist_setup()
+    args.warmup = max(args.warmup, 3)
+    B = args.batch if args.batch_set else 4
+    cfg = configs.bev_localizer()
+    cfg.bev_mapper = configs.bev_mapper(("streetview",))
+    cfg.filter_points_in_fov = True
+    cfg.num_pose_samples = 10_000                       # configs/train_localization.py:27
+    grid = types.Grid2D((G, G), 0.2)
+    loc = bev_localizer.BEVLocalizer(cfg, None, grid)
+    mp = params.round_to_bf16(params.init_bev_mapper(np.random.default_rng(7), cfg.bev_mapper))
+    trainer = localizer_trainer.LocalizerTrainer(loc, loc.init_params(mp), lr=5e-5, device=dev)
+    data = synthetic.make_tile(rank * 100 + 5, 4, IMG_HW, G, batch=B)
+    v, F32 = 2, np.float32
+    T, cam = data["T_view2scene"], data["camera"]
+    t_q2m = (np.round(T.t[:, v, :2] / 0.2) * 0.2).astype(F32)
+    z_off = (np.median(T.t[..., -1].astype(F32), axis=-1).astype(F32) - F32(4.0)).astype(F32)
+    shift = np.concatenate([t_q2m, np.zeros((B, 1), F32)], -1)[:, None]
+    host_imgs = torch.from_numpy(data["images"]).pin_memory()
+    d_imgs = torch.empty_like(host_imgs, device=dev)
+    d_imgs.copy_(host_imgs)
+    query = {"images": d_imgs[:, v:v + 1], "z_offset": z_off,
+             "camera": types.Camera(wh=cam.wh[:, [v]].copy(), f=cam.f[:, [v]].copy(), c=cam.c[:, [v]].copy()),
+             "T_view2scene": types.Transform3D(R=T.R[:, [v]].copy(), t=(T.t[:, [v]] - shift).astype(F32))}
+    T_q2m = types.Transform3D(R=np.broadcast_to(np.eye(3, dtype=F32), (B, 3, 3)).copy(),
+                              t=np.concatenate([t_q2m, np.zeros((B, 1), F32)], -1))
+    batch = {"map": dict(data, images=d_imgs, z_offset=z_off), "query": query, "T_query2map": T_q2m}
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    loss_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    state = {}
+
+    def step(i=0):
+        state["loss"], _, state["metrics"] = trainer.train_step(batch, {"sampling": gen})
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    _lib.launch_count_reset()
+    step()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = _timed_steps(step, args.steps, world, dev)
+
+    def e2e(i):
+        d_imgs.copy_(host_imgs, non_blocking=True)
+        step()
+        loss_host.copy_(state["loss"].reshape(-1)[:B].float(), non_blocking=True)
+    e2e(0)
+    ms_e2e = _timed_steps(e2e, args.steps, world, dev)
+    ms_ar = _timed_steps(lambda i: trainer.bucket.allreduce_mean(), 20, world, dev) / 20
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if rank == 0:
+        units = args.steps * world * B
+        line = {"metric": "neural-map tiles/sec", "value": units / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
+                "config": {"workload": "cfg4-train: localisation training step with frozen image encoders: per example map tile "
+                                       "(4x StreetView 640x480 -> 128x128, R50+FPN, bf16) + query BEV (1 view, 4652 field-of-view points) + "
+                                       "sampling localizer (10,000 poses + ground truth) + NLL, backward to proj_mlp / fusion_mlp / "
+                                       "matching_proj / temperature, gradient all-reduce over ranks, Adam; a 'tile' is one example",
+                           "examples_per_step_per_gpu": B, "launch": "eager",
+                           "collective": "one in-place NCCL all-reduce(mean) of the flat fp32 gradient bucket (%d bytes) per step, inside the timed region"
+                                         % trainer.bucket.nbytes,
+                           "l2": "per-step working set > 1 GB >> 126 MB L2"},
+                "e2e": {"value": units / (ms_e2e * 1e-3), "unit": "tiles/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(host_imgs.numel() * 4), "d2h_bytes_per_step": int(loss_host.numel() * 4),
+                        "path": "pinned host images -> device -> LocalizerTrainer.train_step (BEVLocalizer.apply, loss, backward, "
+                                "all-reduce, Adam) -> per-example loss -> host"},
+                "gpu_launches": int(launches * args.steps), "tiles_per_step": B * world, "clocks": sampler.summary(),
+                "allreduce": {"bytes": trainer.bucket.nbytes, "ms": ms_ar,
+                              "bus_gbs": (2.0 * (world - 1) / world * trainer.bucket.nbytes / (ms_ar * 1e-3) / 1e9) if world > 1 and ms_ar > 0 else None},
+                "loss": float(state["loss"].float().mean().item()), "applied_steps": trainer.step, "skipped_steps": trainer.skipped_steps,
+                "roofline": {"kernel": "forward + backward of the BEV path; the headline kernels are those of the cfg2 line", "bound": "tensor",
+                             "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4", "cfg5", "cfg4train"],
                     help="BASELINE.json configuration: cfg2 (default, the headline: encoder + bev_mapper), cfg4 (full localisation "
                          "forward with the exhaustive 36-rotation voting), cfg5 (semantic head training on frozen BEV features, gradient "
                          "all-reduce inside the timed region)")
@@ -462,6 +553,8 @@ def main():
         return run_cfg4(args)
     if args.impl == "b200" and args.config == "cfg5":
         return run_cfg5(args)
+    if args.impl == "b200" and args.config == "cfg4train":
+        return run_cfg4_train(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

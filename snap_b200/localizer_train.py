@@ -41,6 +41,10 @@ class LocalizerLossBackward:
         [B,P1,3] (ground truth first) and scores f32 [B,P1] as scored by the forward; dr / dt = the per-sample errors of
         `loc_nll` when `remove` (threshold_remove_accurate_poses) is set.
         Returns (d f_q bf16 [B,N,D], d f_m f32 [B,H*W,D], dtemperature f32 [B])."""
+        if getattr(maps, "from_confidence", False):
+            # `bev_localizer.py:165-169`: sim_points is multiplied by masked_softmax(bev_confidence), whose gradient flows
+            # into the trainable confidence head; this plan treats the point weights as constants
+            raise NotImplementedError("add_confidence_query: the gradient of the query confidences is not implemented")
         B, N, D = f_p_q.shape
         H, W = maps.H, maps.W
         HW, P1 = H * W, scores.shape[1]

@@ -33,6 +33,7 @@ class SimilarityMaps:
     row_sum: torch.Tensor        # f32 [B,N]
     H: int = 0
     W: int = 0
+    from_confidence: bool = False   # w came from the query confidences (their head needs a gradient the backward lacks)
 
     def sim_points(self) -> torch.Tensor:
         """The reference's fp32 `sim_points` [B,N,H,W] (debugging / tests; not used by the kernels)."""
@@ -58,7 +59,7 @@ def point_similarities(f_p_q: torch.Tensor, valid_points: torch.Tensor, map_feat
     scale = float(np.exp(F(temperature)).astype(F)) if temperature is not None else 1.0     # :161-162
     f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     maps = SimilarityMaps(sim=sim, scale=scale, point_scale=f32(B, N), row_cdf=f32(B, N), row_max=f32(B, N),
-                          chunk_sum=f32(B, N, H), row_sum=f32(B, N), H=H, W=W)
+                          chunk_sum=f32(B, N, H), row_sum=f32(B, N), H=H, W=W, from_confidence=conf_p is not None)
     ops.loc_softmax_stats(sim, H, W, scale, maps.row_max, maps.chunk_sum, maps.row_sum)     # :163
     ops.loc_point_weights(valid_points.contiguous(), conf_p.contiguous() if conf_p is not None else None, scale,
                           maps.point_scale, maps.row_cdf)                                    # :165-172

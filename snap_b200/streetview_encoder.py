@@ -364,6 +364,12 @@ class StreetViewEncoder:
             ops.gemm(buf["hid"], Bm[wts["fus1"]], buf["volume"][b], m_rows=N, bias=wts["fus1_b"],
                      row_mask=buf["valid"][b])
         pred = {"image_feature_pyramid": pyr}
+        # what the lift's backward needs of this call (references to the live buffers: valid until the next call with the
+        # same shapes): `snap_b200.localizer_trainer` turns it into one `SceneContext` per example
+        pred["lift_context"] = dict(lp=lp, views=stg["views"], centers=stg["centers"], fimg=buf["fimg"], crop=buf["crop"],
+                                    xs=buf["xs"], ys=buf["ys"], zs=stg["zs"], rows_img=rows_img, V=V, hf=hf, wf=wf,
+                                    full=full, Hs=Hs, Ws=Ws, relu_crop=self.weighted,
+                                    crop_per_scene=not (batched and rows_img == V * hf * wf) and B > 1)
         if self.weighted:                      # `:229-230`
             pred["scores_images"] = buf["fimg"][:, :V * hf * wf].view(B, V, hf, wf, 160)[..., 128:]
         if fused:

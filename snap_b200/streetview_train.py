@@ -47,6 +47,20 @@ class LiftBackward:
         self.Wc = {k: v.to(torch.bfloat16).contiguous() for k, v in self.W.items()}
         self._buf: Dict = {}
 
+    def load_params(self, sv_params: Dict) -> None:
+        """Refresh the device copies after an optimiser step (same shapes; buffers and gradient arrays are kept)."""
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(self.dev)
+        self.W["fusion_mlp/Dense_0/kernel"][: 2 * self.D + 1].copy_(f(sv_params["fusion_mlp"]["Dense_0"]["kernel"]))
+        self.W["fusion_mlp/Dense_1/kernel"].copy_(f(sv_params["fusion_mlp"]["Dense_1"]["kernel"]))
+        self.W["proj_mlp/Dense_0/kernel"].copy_(f(sv_params["proj_mlp"]["Dense_0"]["kernel"]))
+        for k in self.b:
+            a, b, c = k.split("/")
+            self.b[k].copy_(f(sv_params[a][b][c]))
+        self.Bf0.copy_(self.W["fusion_mlp/Dense_0/kernel"].t())
+        self.Bf1.copy_(self.W["fusion_mlp/Dense_1/kernel"].t())
+        for k, v in self.W.items():
+            self.Wc[k].copy_(v)
+
     def zero_grads(self) -> None:
         for v in self.g.values():
             v.zero_()
@@ -143,6 +157,13 @@ class MatchingHeadBackward:
         self.g = {"kernel": torch.zeros_like(self.K), "bias": torch.zeros_like(self.b)}
         self._g1 = {"kernel": torch.zeros_like(self.K), "bias": torch.zeros_like(self.b)}
         self._buf: Dict = {}
+
+    def load_params(self, matching_proj: Dict) -> None:
+        """Refresh the device copies after an optimiser step."""
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=F)).to(self.dev)
+        self.K.copy_(f(matching_proj["kernel"]))
+        self.b.copy_(f(matching_proj["bias"]))
+        self.Kc.copy_(self.K)
 
     def zero_grads(self) -> None:
         for v in self.g.values():

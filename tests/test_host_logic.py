@@ -237,3 +237,39 @@ def test_unweighted_fusion_configuration_host_side():
     # the default (weighted) tree is unchanged: [mean | var | score_max] rows and a 128 -> 160 proj MLP
     tree = params.init_streetview_encoder(np.random.default_rng(0), configs.streetview_encoder())
     assert tree["proj_mlp"]["Dense_0"]["kernel"].shape == (128, 160) and tree["fusion_mlp"]["Dense_0"]["kernel"].shape == (257, 256)
+
+
+def test_localizer_trainer_host_side_layout_and_clipping():
+    """`localizer_trainer.LocalizerTrainer` without a GPU: leaf order / master layout, the clip factor of
+    `jax.example_libraries.optimizers.clip_grads`, refusal of configurations whose gradient would be incomplete."""
+    import numpy as np
+    import pytest
+    import torch
+    from snap_b200 import bev_localizer, configs, localizer_trainer, params, types
+    assert localizer_trainer.clip_scale(0.3, 1.0) == 1.0 and abs(localizer_trainer.clip_scale(4.0, 1.0) - 0.25) < 1e-12
+    rng = np.random.default_rng(0)
+    cfg = configs.bev_localizer()
+    cfg.bev_mapper = configs.bev_mapper(("streetview",))
+    cfg.filter_points_in_fov = True
+    cfg.num_pose_samples = 10
+    loc = bev_localizer.BEVLocalizer(cfg, None, types.Grid2D((32, 32), 0.2))
+    sv = {"proj_mlp": params.init_mlp(rng, 128, (160,)), "fusion_mlp": params.init_mlp(rng, 257, (256, 128)),
+          "image_encoder": {"frozen": True}}
+    p = loc.init_params({"streetview_encoder": sv, "matching_proj": {"kernel": np.ones((128, 32), np.float32),
+                                                                     "bias": np.zeros(32, np.float32)}})
+    tr = localizer_trainer.LocalizerTrainer(loc, p, device="cpu")
+    assert tr.paths[-1] == ("temperature",) and len(tr.paths) == 9
+    n = sum(int(np.prod(np.asarray(tr._get(p, q)).shape)) for q in tr.paths)
+    assert n == 128 * 160 + 160 + 257 * 256 + 256 + 256 * 128 + 128 + 128 * 32 + 32 + 1
+    assert tr.masters.flat.numel() >= n and float(tr.masters.views[-1][0]) == 2.0
+    tr.masters.views[6].mul_(3.0)          # matching_proj kernel
+    tr._rebuild_params()
+    assert tr.params["bev_mapper"]["streetview_encoder"]["image_encoder"] is sv["image_encoder"]
+    assert tr.params["bev_mapper"]["matching_proj"]["kernel"][0, 0] == 3.0 and p["bev_mapper"]["matching_proj"]["kernel"][0, 0] == 1.0
+    assert tr.params["bev_mapper"]["streetview_encoder"]["fusion_mlp"]["Dense_0"]["kernel"].shape == (257, 256)
+    cfg2 = configs.bev_localizer()
+    cfg2.bev_mapper = configs.bev_mapper(("streetview",))
+    cfg2.filter_points_in_fov = True
+    cfg2.add_confidence_query = True
+    with pytest.raises(NotImplementedError):
+        localizer_trainer.LocalizerTrainer(bev_localizer.BEVLocalizer(cfg2, None, types.Grid2D((32, 32), 0.2)), p, device="cpu")

@@ -1,0 +1,107 @@
+"""`snap_b200.localizer_trainer.LocalizerTrainer`: the config-4 training step (`snap/trainer.py:165-295` around
+`snap/models/bev_localizer.py`) with frozen image encoders, at BASELINE configs[3] size (G = 128, 4 x 640 x 480 map views,
+4,652 field-of-view query points, 10,000 pose samples)."""
+import numpy as np
+import pytest
+import torch
+
+from util import F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def _setup(batch=2, seed=9):
+    from snap_b200 import bev_localizer, configs, params, synthetic, types
+    G, hw = 128, (480, 640)
+    rng = np.random.default_rng(seed)
+    cfg = configs.bev_localizer()
+    cfg.bev_mapper = configs.bev_mapper(("streetview",))
+    cfg.filter_points_in_fov = True
+    cfg.num_pose_samples = 2_000
+    cfg.num_pose_sampling_retries = 2
+    grid = types.Grid2D((G, G), 0.2)
+    loc = bev_localizer.BEVLocalizer(cfg, None, grid)
+    mp = params.round_to_bf16(params.perturb_affine(rng, params.init_bev_mapper(rng, cfg.bev_mapper)))
+    p = loc.init_params(mp)
+    data = synthetic.make_tile(61, 4, hw, G, batch=batch)
+    v = 2
+    T, cam = data["T_view2scene"], data["camera"]
+    t_q2m = (np.round(T.t[:, v, :2] / 0.2) * 0.2).astype(F)                       # [B, 2]
+    z_off = (np.median(T.t[..., -1].astype(F), axis=-1).astype(F) - F(4.0)).astype(F)
+    shift = np.concatenate([t_q2m, np.zeros((batch, 1), F)], -1)[:, None]
+    query = {"images": np.ascontiguousarray(data["images"][:, [v]]),
+             "camera": types.Camera(wh=cam.wh[:, [v]].copy(), f=cam.f[:, [v]].copy(), c=cam.c[:, [v]].copy()),
+             "T_view2scene": types.Transform3D(R=T.R[:, [v]].copy(), t=(T.t[:, [v]] - shift).astype(F)), "z_offset": z_off}
+    T_q2m = types.Transform3D(R=np.broadcast_to(np.eye(3, dtype=F), (batch, 3, 3)).copy(),
+                              t=np.concatenate([t_q2m, np.zeros((batch, 1), F)], -1))
+    batch_data = {"map": {**data, "z_offset": z_off}, "query": query, "T_query2map": T_q2m}
+    return loc, p, batch_data
+
+
+def _gen(seed=1):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return g
+
+
+def test_training_step_reduces_the_loss_and_refreshes_the_forward_weights():
+    from snap_b200 import localizer_trainer
+    loc, p, data = _setup()
+    tr = localizer_trainer.LocalizerTrainer(loc, p, lr=2e-3)
+    enc_tree = p["bev_mapper"]["streetview_encoder"]["image_encoder"]
+    losses = []
+    for it in range(6):
+        total, _, metrics = tr.train_step(data, {"sampling": _gen()})
+        torch.cuda.synchronize()
+        losses.append(float(total.mean()))
+        assert metrics["is_finite"] and np.isfinite(metrics["l2_grads"]) and metrics["l2_grads"] > 0
+        print(f"step {it}: nll {losses[-1]:.4f}  |g| {metrics['l2_grads']:.4e}  T {float(tr.params['temperature']):.4f}")
+    assert tr.step == 6 and tr.skipped_steps == 0
+    assert losses[-1] < losses[0] - 1e-3, losses
+    # the frozen encoder tree kept its identity (cached launch plan), the trainable sub-trees are new objects with new values
+    new = tr.params
+    assert new["bev_mapper"]["streetview_encoder"]["image_encoder"] is enc_tree
+    assert new["bev_mapper"]["matching_proj"] is not p["bev_mapper"]["matching_proj"]
+    for a, b in ((new["bev_mapper"]["matching_proj"]["kernel"], p["bev_mapper"]["matching_proj"]["kernel"]),
+                 (new["bev_mapper"]["streetview_encoder"]["fusion_mlp"]["Dense_1"]["kernel"],
+                  p["bev_mapper"]["streetview_encoder"]["fusion_mlp"]["Dense_1"]["kernel"])):
+        assert a.shape == b.shape and np.abs(a - b).max() > 0
+    assert float(new["temperature"]) != float(p["temperature"])
+    # the encoder-feature cotangents are there for `TrunkTrainer.backward` (one per scene and side)
+    pred, _, _ = tr.loss_and_gradients(data, {"sampling": _gen()})
+    enc = pred["encoder_cotangents"]
+    assert len(enc["map"]) == 2 and len(enc["query"]) == 2
+    assert enc["map"][0].shape[1] == 128 and torch.isfinite(enc["map"][0].float()).all() and enc["map"][0].float().abs().max() > 0
+
+
+def test_temperature_gradient_matches_a_finite_difference_and_nan_steps_are_skipped():
+    from snap_b200 import localizer_trainer
+    loc, p, data = _setup(batch=1)
+    tr = localizer_trainer.LocalizerTrainer(loc, p, lr=1e-3, max_grad_norm=0.5)
+    total, _, metrics = tr.train_step(data, {"sampling": _gen()}, update=False)
+    g_T = float(tr.grads_tree()["temperature"])
+    # the sampled poses do not depend on the temperature's value beyond the soft-max they are drawn from: score the SAME
+    # poses at T +- eps through the forward's own kernels
+    from snap_b200 import pose_estimation
+    pred = loc.apply({"params": p}, data, rngs={"sampling": _gen()})
+    poses = pred["map_t_query_samples"]
+    pq, pm = pred["query"]["bev_matching"], pred["map"]["bev_matching"]
+    q_xy = torch.from_numpy(np.ascontiguousarray(loc.q_xy_p[:, 0])).cuda()
+
+    def nll_at(T):
+        maps = pose_estimation.point_similarities(pq.features.reshape(1, -1, 32), pq.valid.reshape(1, -1), pm.features, T, True, None)
+        sc = pose_estimation.pose_scoring_many_batched(poses, maps, q_xy, pm.valid, loc.grid_map, False).double()
+        return float(-(sc[0, 0] - torch.logsumexp(sc[0], 0)))
+    T0, eps = float(p["temperature"]), 0.05
+    fd = (nll_at(T0 + eps) - nll_at(T0 - eps)) / (2 * eps)
+    print(f"d nll / d temperature: backward {g_T:.5f}, finite difference {fd:.5f}; nll {float(total.mean()):.4f}")
+    assert abs(g_T - fd) <= 0.05 * abs(fd) + 1e-3
+    # clipping: the applied gradient has norm <= max_grad_norm
+    before = tr.params
+    tr.bucket.flat.mul_(100.0)
+    assert tr.apply_update() and tr.params is not before
+    # a non-finite gradient skips the update: parameters, optimiser state and step count stay
+    snap = (tr.params, tr.masters.flat.clone(), tr.mom[0].clone(), tr.step)
+    tr.bucket.flat[5] = float("nan")
+    assert tr.apply_update() is False and tr.skipped_steps == 1
+    assert tr.params is snap[0] and torch.equal(tr.masters.flat, snap[1]) and torch.equal(tr.mom[0], snap[2]) and tr.step == snap[3]
