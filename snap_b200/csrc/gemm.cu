@@ -52,8 +52,9 @@ int launch_gemm(const void* A, long long a_rows, int a_cols, long long a_ld, con
   memset(&tmR, 0, sizeof(tmR));
   // dense bf16 outputs leave through shared memory + TMA (whole 128-byte lines instead of 32 B per lane)
   static const int env_so = env_int("SNAPB200_GEMM_STAGE_OUT", 1);
-  p.stage_out = env_so && p.epi == EPI_STORE && !p.remap && !p.out_f32 && (bn == 64 || bn == 128) && bk == 64 &&
-                p.N % 64 == 0 && p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  p.stage_out = env_so && p.epi == EPI_STORE && !p.remap && !p.out_f32 && bk == 64 &&
+                (((bn == 64 || bn == 128) && p.N % 64 == 0) || (bn == 160 && p.N == 160 && p.residual == nullptr)) &&
+                p.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
   if (p.stage_out) {
     int rc = make_tmap_2d_bf16(&tmO, p.out, p.M_valid, p.N, p.ldo, 32, 64);
     if (rc) return rc;

@@ -104,7 +104,8 @@ struct GemmCfg {
                                    : (2 * BN <= 256) ? 256
                                                      : 512;
   // +1024 for manual alignment, +512 for barriers (2 x 16 stage + 4 accumulator) / tmem pointer
-  static constexpr int OUT_STAGE_BYTES = BM * BN * 2;  // staged-output buffer (one 32-row slab per TMEM quadrant)
+  static constexpr int NH = (BN + 63) / 64;            // 64-column boxes per output row (the last one may be partial)
+  static constexpr int OUT_STAGE_BYTES = 4 * NH * 4096;  // staged-output buffer: per TMEM quadrant NH slabs of 32 rows x 128 B
   static constexpr int smem_bytes(int stages, bool gn_tables = false, bool stage_out = false) {
     return stages * STAGE_BYTES + (stage_out ? OUT_STAGE_BYTES : 0) + 1024 + 512 +
            (gn_tables ? GEMM_GN_TABLE_BYTES : 0);
@@ -606,7 +607,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
-    uint8_t* slab = out_stage + q * (BN / 64) * 4096;  // this quadrant's 32-row staging slab
+    uint8_t* slab = out_stage + q * Cfg::NH * 4096;  // this quadrant's 32-row staging slab
     // residual slab of a tile: BN/64 boxes of 32 rows x 64 columns (issued by one thread per quadrant)
     auto issue_residual = [&](int tile_id) {
       if constexpr (BN % 64 == 0) {
@@ -1006,9 +1007,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           pair_bar_sync(q);
           if (hw == 0 && lane == 0) {
-            if constexpr (BN % 64 == 0) {
+            if constexpr (BN % 32 == 0) {   // a partial last box (N = 160) is clipped by the tensor map's bounds
 #pragma unroll
-              for (int h = 0; h < BN / 64; ++h)
+              for (int h = 0; h < Cfg::NH; ++h)
                 if (n0 + h * 64 < p.N)
                   tma_store_2d(&tmO, slab + h * 4096, n0 + h * 64, t.mt * 128 + q * 32);
             }

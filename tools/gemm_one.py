@@ -18,6 +18,20 @@ if which == "conv3":
 elif which == "conv1":
     a, b, out = bf(rows + 128, 256), bf(64, 256), bf(rows + 128, 64)
     fn = lambda: ops.gemm(a, b, out, m_rows=rows, gn_acc=acc, gn_rows_per_img=h * w)
+elif which == "root":  # implicit 7x7/2 root conv + max pool + statistics of 16 images of 480x640
+    import numpy as np
+    from snap_b200 import configs, image_encoder, params
+    cfg = configs.image_encoder()
+    p_ = params.init_image_encoder(np.random.default_rng(0), cfg)
+    plan = image_encoder.ImageEncoder(cfg).plan(p_, NIMG, 480, 640, dev)
+    imgs = torch.rand((NIMG, 480, 640, 3), device=dev)
+    plan.bank.run()
+    fn = lambda: plan.run_root(imgs)
+elif which == "proj160":  # proj MLP: Dense 128 -> 160 with bias over 16 x 120 x 160 texels
+    rows_p = NIMG * 120 * 160
+    a, b, out = bf(rows_p + 128, 128), bf(160, 128), bf(rows_p + 128, 160)
+    bias = torch.randn(160, device=dev)
+    fn = lambda: ops.gemm(a, b, out, m_rows=rows_p, bias=bias)
 elif which in ("fconv1", "fconv3"):  # fused GroupNorm -> 1x1 conv (A_TGN1)
     k, n = (256, 64) if which == "fconv1" else (64, 256)
     x, b, out = bf(rows + 128, k), bf(n, k), bf(rows + 128, n)
