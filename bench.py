@@ -456,7 +456,7 @@ def run_cfg4_train(args):
     grid = types.Grid2D((G, G), 0.2)
     loc = bev_localizer.BEVLocalizer(cfg, None, grid)
     mp = params.round_to_bf16(params.init_bev_mapper(np.random.default_rng(7), cfg.bev_mapper))
-    trainer = localizer_trainer.LocalizerTrainer(loc, loc.init_params(mp), lr=5e-5, device=dev)
+    trainer = localizer_trainer.LocalizerTrainer(loc, loc.init_params(mp), lr=5e-5, device=dev, train_encoder=args.train_encoder)
     data = synthetic.make_tile(rank * 100 + 5, 4, IMG_HW, G, batch=B)
     v, F32 = 2, np.float32
     T, cam = data["T_view2scene"], data["camera"]
@@ -498,6 +498,7 @@ def run_cfg4_train(args):
     e2e(0)
     ms_e2e = _timed_steps(e2e, args.steps, world, dev)
     ms_ar = _timed_steps(lambda i: trainer.bucket.allreduce_mean(), 20, world, dev) / 20
+    ms_ar_enc = (_timed_steps(lambda i: trainer.enc_bucket.allreduce_mean(), 20, world, dev) / 20) if trainer.enc_bucket is not None else None
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if rank == 0:
@@ -505,7 +506,8 @@ def run_cfg4_train(args):
         line = {"metric": "neural-map tiles/sec", "value": units / (ms * 1e-3), "unit": "tiles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
-                "config": {"workload": "cfg4-train: localisation training step with frozen image encoders: per example map tile "
+                "config": {"workload": ("cfg4-train (FULL: image encoder trained, ~23.5 M more gradients in the collective): " if args.train_encoder else "") +
+                                       "cfg4-train: localisation training step with frozen image encoders: per example map tile "
                                        "(4x StreetView 640x480 -> 128x128, R50+FPN, bf16) + query BEV (1 view, 4652 field-of-view points) + "
                                        "sampling localizer (10,000 poses + ground truth) + NLL, backward to proj_mlp / fusion_mlp / "
                                        "matching_proj / temperature, gradient all-reduce over ranks, Adam; a 'tile' is one example",
@@ -519,7 +521,9 @@ def run_cfg4_train(args):
                                 "all-reduce, Adam) -> per-example loss -> host"},
                 "gpu_launches": int(launches * args.steps), "tiles_per_step": B * world, "clocks": sampler.summary(),
                 "allreduce": {"bytes": trainer.bucket.nbytes, "ms": ms_ar,
-                              "bus_gbs": (2.0 * (world - 1) / world * trainer.bucket.nbytes / (ms_ar * 1e-3) / 1e9) if world > 1 and ms_ar > 0 else None},
+                              "bus_gbs": (2.0 * (world - 1) / world * trainer.bucket.nbytes / (ms_ar * 1e-3) / 1e9) if world > 1 and ms_ar > 0 else None,
+                              "encoder_bucket_bytes": trainer.enc_bucket.nbytes if trainer.enc_bucket is not None else 0,
+                              "encoder_bucket_ms": ms_ar_enc},
                 "loss": float(state["loss"].float().mean().item()), "applied_steps": trainer.step, "skipped_steps": trainer.skipped_steps,
                 "roofline": {"kernel": "forward + backward of the BEV path; the headline kernels are those of the cfg2 line", "bound": "tensor",
                              "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None},
@@ -538,7 +542,10 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4", "cfg5", "cfg4train"],
                     help="BASELINE.json configuration: cfg2 (default, the headline: encoder + bev_mapper), cfg4 (full localisation "
                          "forward with the exhaustive 36-rotation voting), cfg5 (semantic head training on frozen BEV features, gradient "
-                         "all-reduce inside the timed region)")
+                         "all-reduce inside the timed region), cfg4train (localisation TRAINING step: forward, NLL, backward, gradient "
+                         "all-reduce, Adam; --train-encoder includes the image encoder)")
+    ap.add_argument("--train-encoder", action="store_true",
+                    help="cfg4train: also train the street-view image encoder (the reference's full training step)")
     ap.add_argument("--batch", type=int, default=8,
                     help="tiles (scenes) per GPU per step; the reference trains with 4 per device (B = 32 on 8 GPUs), map building "
                          "batches freely: measured 636 / 765 / 857 tiles/s at 2 / 4 / 8 on one B200 (per-kernel fixed costs amortise)")

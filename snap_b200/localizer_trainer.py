@@ -18,9 +18,62 @@ from typing import Callable, Dict, List, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from . import bev_localizer, localizer_step, ops, parallel
+from . import bev_localizer, encoder_train, localizer_step, ops, parallel, types
 
 F = np.float32
+
+
+class EncoderTraining:
+    """The image encoder of the (shared) BEV mapper in training mode: `encoder_train.TrunkTrainer` over ALL images of a step
+    (map views and query views in one batch, so there is one set of masters and one gradient per array), padded like
+    `pad_to_multiple` (`image_encoder.py:32-39`: a full stride when already aligned).  Parameters and gradients stay on
+    the device: `leaves` lists (path, parameter tensor, gradient tensor) for the optimiser; the parameter tensors are the
+    ones the training forward reads (fp32 conv masters that every forward re-standardises, GroupNorm scale / bias)."""
+
+    def __init__(self, enc_params: Dict, n_img: int, H: int, W: int, device):
+        s = 32
+        self.n, self.H, self.W = n_img, H, W
+        self.Hp, self.Wp = H + (s - H % s), W + (s - W % s)
+        self.trunk = t = encoder_train.TrunkTrainer(enc_params, n_img, self.Hp, self.Wp, device)
+        self.padded = torch.zeros((n_img, self.Hp, self.Wp, 3), dtype=torch.float32, device=device)
+        self.Hs, self.Ws = self.Hp // 4, self.Wp // 4
+        self.dfin = torch.zeros((n_img, self.Hs, self.Ws, 128), dtype=torch.bfloat16, device=device)
+        leaves = [(("encoder", "root_block", "conv_root", "kernel"), t.root_master, t.g_root)]
+        for u in t.units:
+            ut = u["t"]
+            for name in ut.master:
+                leaves.append((("encoder", *u["path"], name, "kernel"), ut.master[name], ut.g[name]))
+            for g in ("gn1", "gn2", "gn3"):
+                leaves.append((("encoder", *u["path"], g, "scale"), ut.gn[g][0], ut.ggn[g][0]))
+                leaves.append((("encoder", *u["path"], g, "bias"), ut.gn[g][1], ut.ggn[g][1]))
+        off = 0
+        for level, (L, (_, k, cout, _, _)) in enumerate(zip(t.fpn.lv, t.fpn.bank.entries)):
+            leaves.append((("decoder", f"{level}_skip_conv", "kernel"), t.fpn.bank.master[off: off + k * cout].view(k, cout),
+                           L["g"]["kernel"]))
+            off += k * cout
+            leaves.append((("decoder", f"{level}_skip_norm", "scale"), L["scale"], L["g"]["scale"]))
+            leaves.append((("decoder", f"{level}_skip_norm", "bias"), L["bias"], L["g"]["bias"]))
+        self.leaves = leaves
+
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """images f32 [n, H, W, 3] (device) -> un-cropped finest FPN level bf16 [n, Hp/4, Wp/4, 128]."""
+        self.padded[:, : self.H, : self.W].copy_(images)
+        fin = self.trunk.forward(self.padded)
+        return fin[: self.n * self.Hs * self.Ws].view(self.n, self.Hs, self.Ws, 128)
+
+    def pyramid(self, feats: torch.Tensor, hf: int, wf: int) -> types.FeatureImagePyramid:
+        stride = np.asarray([self.Hp / self.Hs, self.Wp / self.Ws])
+        return types.FeatureImagePyramid(features=[feats[:, :hf, :wf]], strides=[stride], uncropped=[feats])
+
+    def backward(self, dcrops: List[torch.Tensor], V_of: List[int], hf: int, wf: int) -> None:
+        """dcrops[i] bf16 [>= V_i*hf*wf, 128]: cotangent of the cropped finest level of the i-th group of V_i consecutive
+        images (one scene of one side); the padding rows / columns get zero."""
+        self.dfin.zero_()
+        i0 = 0
+        for d, V in zip(dcrops, V_of):
+            self.dfin[i0:i0 + V, :hf, :wf].copy_(d[: V * hf * wf].view(V, hf, wf, 128))
+            i0 += V
+        self.trunk.backward(self.dfin.view(-1, 128))
 
 
 def clip_scale(norm: float, max_norm: float) -> float:
@@ -36,9 +89,13 @@ class LocalizerTrainer:
               ("matching_proj", "kernel"), ("matching_proj", "bias"))
 
     def __init__(self, model: bev_localizer.BEVLocalizer, params: Dict, lr: Union[float, Callable[[int], float]] = 5e-5,
-                 max_grad_norm: Optional[float] = None, device=None, group=None):
+                 max_grad_norm: Optional[float] = None, device=None, group=None, train_encoder: bool = False):
         """params: the Flax tree {'bev_mapper', ['bev_mapper_query',] 'temperature'} (host arrays); lr: a constant or the
-        schedule `step -> learning rate` (`configs/train_localization.py:86-92`)."""
+        schedule `step -> learning rate` (`configs/train_localization.py:86-92`).
+        train_encoder: also train the street-view image encoder (the reference's default for this model: no
+        `freeze_params_reg_exp` in `configs/train_localization.py`): its training forward / backward is
+        `encoder_train.TrunkTrainer` over the map and query images of the step; the ~23.5 M encoder gradients join the flat
+        bucket of the collective.  The aerial encoder, if any, stays frozen."""
         c = model.config
         if c.add_confidence_query:
             # the confidence head multiplies the point similarities (`bev_localizer.py:165-169`) and would need its own
@@ -60,6 +117,19 @@ class LocalizerTrainer:
         self.bwd = localizer_step.FrozenEncoderBackward(
             params["bev_mapper"], self.dev, params.get("bev_mapper_query") if len(self.sides) == 2 else None)
         self._crop: Dict = {}
+        self.train_encoder, self.enc, self.enc_bucket, self.enc_mom = train_encoder, None, None, None
+        if train_encoder and len(self.sides) == 2:
+            raise NotImplementedError("train_encoder with a separate query mapper (two encoders) is not wired")
+
+    def _encoder(self, n_img: int, H: int, W: int) -> EncoderTraining:
+        if self.enc is None or (self.enc.n, self.enc.H, self.enc.W) != (n_img, H, W):
+            if self.enc is not None:
+                raise ValueError("the encoder's training buffers are built for one input shape per trainer")
+            enc_params = self.params["bev_mapper"]["streetview_encoder"]["image_encoder"]
+            self.enc = EncoderTraining(enc_params, n_img, H, W, self.dev)
+            self.enc_bucket = parallel.GradBucket([tuple(p.shape) for _, p, _ in self.enc.leaves], self.dev, self.masters.group)
+            self.enc_mom = [(torch.zeros_like(p), torch.zeros_like(p)) for _, p, _ in self.enc.leaves]
+        return self.enc
 
     @staticmethod
     def _get(tree: Dict, path):
@@ -107,6 +177,8 @@ class LocalizerTrainer:
         m, c = self.model, self.model.config
         if data.get("T_query2map") is None:
             raise ValueError("training needs data['T_query2map'] (the ground truth is the first scored pose)")
+        if self.train_encoder:
+            data = self._encode_images(data)
         pred = m.apply({"params": self.params}, data, train=False, rngs=rngs)
         losses, metrics = m.loss_metrics_function(pred, data, self.params)
         maps, plane_q, plane_map = pred["similarity_maps"], pred["query"]["bev_matching"], pred["map"]["bev_matching"]
@@ -134,20 +206,50 @@ class LocalizerTrainer:
                 t = lift.g["/".join(leaf[1:])]
                 v.copy_(t[: v.shape[0]].reshape(v.shape) if t.shape != v.shape else t)   # Dense_0 kernel rows are padded
         pred["encoder_cotangents"] = g["encoder_cotangents"]
+        if self.train_encoder:
+            ec, B = g["encoder_cotangents"], plane_map.features.shape[0]
+            lc = pred["map"]["streetview"]["lift_context"]
+            Vm, Vq = lc["V"], pred["query"]["streetview"]["lift_context"]["V"]
+            self.enc.backward(ec["map"] + ec["query"], [Vm] * B + [Vq] * B, lc["hf"], lc["wf"])
+            for v, (_, _, gt) in zip(self.enc_bucket.views, self.enc.leaves):
+                v.copy_(gt.reshape(v.shape))
         return pred, losses, metrics
+
+    def _encode_images(self, data: Dict) -> Dict:
+        """Training forward of the shared image encoder over the map and the query images of the step; the two pyramids are
+        handed to the mappers through `data[...]['image_feature_pyr']` (`StreetViewEncoder.apply` skips its own encoder)."""
+        dev = self.dev
+        as_dev = lambda x: (x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=F))).to(dev)
+        im, iq = as_dev(data["map"]["images"]), as_dev(data["query"]["images"])
+        B, Vm, H, W, _ = im.shape
+        Vq = iq.shape[1]
+        if tuple(iq.shape[2:4]) != (H, W):
+            raise NotImplementedError("train_encoder: map and query images must have the same size (one encoder batch)")
+        enc = self._encoder(B * (Vm + Vq), H, W)
+        feats = enc.forward(torch.cat([im.reshape(B * Vm, H, W, 3), iq.reshape(B * Vq, H, W, 3)]))
+        hf, wf = -(-H // 4), -(-W // 4)                        # image_encoder.py:137-141: crop to ceil(input / stride)
+        out = dict(data)
+        out["map"] = dict(data["map"], images=im, image_feature_pyr=enc.pyramid(feats[: B * Vm], hf, wf))
+        out["query"] = dict(data["query"], images=iq, image_feature_pyr=enc.pyramid(feats[B * Vm:], hf, wf))
+        return out
 
     def apply_update(self) -> bool:
         """Clip, Adam on the masters, rebuild the parameter tree; the whole update is skipped when a gradient is not
         finite (`trainer.py:260-276` keeps the old parameters AND optimiser state).  Returns whether it was applied."""
-        if not bool(self.bucket.all_finite().item()):
+        buckets = [self.bucket] + ([self.enc_bucket] if self.enc_bucket is not None else [])
+        if not all(bool(b.all_finite().item()) for b in buckets):
             self.skipped_steps += 1
             return False
         if self.max_grad_norm is not None:
-            norm = float(self.bucket.flat.norm())
-            self.bucket.flat.mul_(clip_scale(norm, self.max_grad_norm))
+            norm = float(torch.sqrt(sum(b.flat.double().square().sum() for b in buckets)))
+            for b in buckets:
+                b.flat.mul_(clip_scale(norm, self.max_grad_norm))
         self.step += 1
         lr = self.lr(self.step - 1) if callable(self.lr) else self.lr      # optax schedules are evaluated at the step count before the update
         ops.adam_step(self.masters.flat, self.mom[0], self.mom[1], self.bucket.flat, float(lr), self.step)
+        if self.enc_bucket is not None:                                     # in place on the tensors the training forward reads
+            for (_, p, _), (m1, m2), g in zip(self.enc.leaves, self.enc_mom, self.enc_bucket.views):
+                ops.adam_step(p.view(-1), m1.view(-1), m2.view(-1), g.reshape(-1), float(lr), self.step)
         self._rebuild_params()
         return True
 
@@ -182,10 +284,26 @@ class LocalizerTrainer:
         tells whether the update was applied."""
         pred, losses, metrics = self.loss_and_gradients(data, rngs)
         self.bucket.allreduce_mean()                                   # jax.lax.pmean(grad, 'batch')
+        sq = self.bucket.flat.double().square().sum()
+        if self.enc_bucket is not None:
+            self.enc_bucket.allreduce_mean()                           # the ~94 MB of encoder gradients: one more collective
+            sq = sq + self.enc_bucket.flat.double().square().sum()
         metrics = dict(metrics)
-        metrics["l2_grads"] = float(self.bucket.flat.norm())
-        metrics["is_finite"] = self.apply_update() if update else bool(self.bucket.all_finite().item())
+        metrics["l2_grads"] = float(torch.sqrt(sq))
+        finite = bool(self.bucket.all_finite().item()) and (self.enc_bucket is None or bool(self.enc_bucket.all_finite().item()))
+        metrics["is_finite"] = self.apply_update() if update else finite
         return losses["total"], losses, metrics
+
+    def encoder_params_tree(self) -> Dict:
+        """The trained image-encoder parameters as the Flax tree `image_encoder` (host, fp32), for checkpoints."""
+        ref = self.params["bev_mapper"]["streetview_encoder"]["image_encoder"]
+        out: Dict = {}
+        for path, p, _ in self.enc.leaves:
+            d = out
+            for k in path[:-1]:
+                d = d.setdefault(k, {})
+            d[path[-1]] = p.detach().cpu().numpy().copy().reshape(np.asarray(self._get(ref, path)).shape)
+        return out
 
     def grads_tree(self) -> Dict:
         out: Dict = {}

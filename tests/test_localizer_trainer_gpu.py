@@ -105,3 +105,35 @@ def test_temperature_gradient_matches_a_finite_difference_and_nan_steps_are_skip
     tr.bucket.flat[5] = float("nan")
     assert tr.apply_update() is False and tr.skipped_steps == 1
     assert tr.params is snap[0] and torch.equal(tr.masters.flat, snap[1]) and torch.equal(tr.mom[0], snap[2]) and tr.step == snap[3]
+
+
+def test_full_training_step_with_the_image_encoder():
+    """`train_encoder=True`: the street-view encoder's training forward / backward (`encoder_train.TrunkTrainer` over the map
+    and query images) inside the step; all 23.5 M encoder gradients are finite and non-zero, the masters move, the loss on
+    the fixed batch goes down, and the un-trained forward (EncoderPlan) agrees with the training forward's first loss."""
+    from snap_b200 import localizer_trainer
+    loc, p, data = _setup(batch=1)
+    frozen = localizer_trainer.LocalizerTrainer(loc, p, lr=1e-3)
+    l_frozen = float(frozen.train_step(data, {"sampling": _gen()}, update=False)[0].mean())
+    tr = localizer_trainer.LocalizerTrainer(loc, p, lr=3e-4, train_encoder=True)
+    losses = []
+    for it in range(5):
+        total, _, metrics = tr.train_step(data, {"sampling": _gen()})
+        torch.cuda.synchronize()
+        losses.append(float(total.mean()))
+        assert metrics["is_finite"] and np.isfinite(metrics["l2_grads"])
+        if it == 0:
+            before = [pt.clone() for _, pt, _ in tr.enc.leaves[:3]]
+            n_par = sum(pt.numel() for _, pt, _ in tr.enc.leaves)
+            nz = [float(g.abs().max()) > 0 for g in tr.enc_bucket.views]
+            print(f"encoder leaves {len(tr.enc.leaves)}, parameters {n_par}, non-zero gradients {sum(nz)}/{len(nz)}")
+            assert n_par > 23_000_000 and all(nz) and tr.enc_bucket.nbytes > 90_000_000
+        print(f"step {it}: nll {losses[-1]:.4f}  |g| {metrics['l2_grads']:.4e}")
+    # the training forward (im2col root conv, per-unit buffers) and the inference plan are two launch sequences of the same
+    # network: the first loss agrees up to bf16 noise of the free-running encoder
+    assert abs(losses[0] - l_frozen) < 0.15 * abs(l_frozen) + 0.1, (losses[0], l_frozen)
+    assert losses[-1] < losses[0] - 1e-3, losses
+    tree = tr.encoder_params_tree()
+    k0 = np.asarray(p["bev_mapper"]["streetview_encoder"]["image_encoder"]["encoder"]["root_block"]["conv_root"]["kernel"])
+    assert tree["encoder"]["root_block"]["conv_root"]["kernel"].shape == k0.shape
+    assert np.abs(tree["encoder"]["root_block"]["conv_root"]["kernel"] - k0).max() > 0
