@@ -64,7 +64,7 @@ def launch_count_reset() -> None:
 # Every symbol include/snapb200.h declares; tests/test_abi.py checks the .so exports each of them.
 EXPORTED_SYMBOLS = [
     "snapb200_last_error", "snapb200_version", "snapb200_launch_count",
-    "snapb200_launch_count_reset", "snapb200_gemm_bf16", "snapb200_conv_gn_bf16",
+    "snapb200_launch_count_reset", "snapb200_gemm_bf16", "snapb200_conv_gn_bf16", "snapb200_selftest_shifted_desc",
 ]
 
 

@@ -29,8 +29,13 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   static const int env_ctas = env_int("SNAPB200_GEMM_CTAS", 0);  // tuning overrides (tools/gemm_sweep.py)
   if (env_ctas > 0) ctas_per_sm = env_ctas > 2 ? 2 : env_ctas;
   const bool so = p.stage_out != 0;
-  int stages = p.nkb < Cfg::MAX_STAGES ? p.nkb : Cfg::MAX_STAGES;
+  // the ring may be deeper than one tile's K blocks: the TMA producer then runs whole tiles ahead of the MMA
+  // (small-K layers: the root conv has 7 blocks of 12 KB per tile, conv3 of stage 1 a single one)
+  static const int env_deep = env_int("SNAPB200_GEMM_DEEP_RING", 1);
+  int stages = (env_deep || p.nkb >= Cfg::MAX_STAGES) ? Cfg::MAX_STAGES : p.nkb;
   if (stages < 2) stages = 2;
+  p.idx32 = p.M_valid < (1LL << 31) && (long long)p.m_tiles * 128 < (1LL << 31) &&
+            (!p.remap || (long long)p.rm_R * p.rm_C < (1LL << 31)) && p.gn_rows_per_img < (1LL << 31);
   while (stages > 2 && ctas_per_sm * Cfg::smem_bytes(stages, false, so) > 225 * 1024) --stages;
   while (ctas_per_sm > 1 && ctas_per_sm * Cfg::smem_bytes(stages, false, so) > 225 * 1024) --ctas_per_sm;
   p.stages = stages;

@@ -52,6 +52,7 @@ struct GemmParams {
   int relu;
   // row remap: m -> (img, r, c) over (rm_R, rm_C); valid iff r0<=r<r0+Ho && c0<=c<c0+Wo
   int remap, rm_R, rm_C, rm_r0, rm_c0, rm_Ho, rm_Wo;
+  int idx32;  // set by the launcher: M, the remap extents and gn_rows_per_img fit 32-bit arithmetic
   // fused GroupNorm statistics of the stored output (see snapb200.h)
   double* gn_acc;
   double* gn_acc_relu;
@@ -825,21 +826,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool row_ok = m < p.M_valid;
         long long orow = m;
         if (p.remap) {
-          const long long per_img = (long long)p.rm_R * p.rm_C;
-          const long long img = m / per_img;
-          const int rem = (int)(m - img * per_img);
-          const int r = rem / p.rm_C;
-          const int c = rem - r * p.rm_C;
-          row_ok = row_ok && r >= p.rm_r0 && r < p.rm_r0 + p.rm_Ho && c >= p.rm_c0 &&
-                   c < p.rm_c0 + p.rm_Wo;
-          orow = (img * p.rm_Ho + (r - p.rm_r0)) * p.rm_Wo + (c - p.rm_c0);
+          if (p.idx32) {   // every index fits 32 bits (the host checked): no software 64-bit divisions per tile
+            const unsigned per_img = (unsigned)(p.rm_R * p.rm_C);
+            const unsigned img = (unsigned)m / per_img;
+            const int rem = (int)((unsigned)m - img * per_img);
+            const int r = (int)((unsigned)rem / (unsigned)p.rm_C);
+            const int c = rem - r * p.rm_C;
+            row_ok = row_ok && r >= p.rm_r0 && r < p.rm_r0 + p.rm_Ho && c >= p.rm_c0 && c < p.rm_c0 + p.rm_Wo;
+            orow = (long long)((img * (unsigned)p.rm_Ho + (unsigned)(r - p.rm_r0)) * (unsigned)p.rm_Wo + (unsigned)(c - p.rm_c0));
+          } else {
+            const long long per_img = (long long)p.rm_R * p.rm_C;
+            const long long img = m / per_img;
+            const int rem = (int)(m - img * per_img);
+            const int r = rem / p.rm_C;
+            const int c = rem - r * p.rm_C;
+            row_ok = row_ok && r >= p.rm_r0 && r < p.rm_r0 + p.rm_Ho && c >= p.rm_c0 &&
+                     c < p.rm_c0 + p.rm_Wo;
+            orow = (img * p.rm_Ho + (r - p.rm_r0)) * p.rm_Wo + (c - p.rm_c0);
+          }
         }
         if (!row_ok) orow = 0;
         const bool keep = row_ok && (p.row_mask == nullptr || p.row_mask[orow] != 0);
         int gn_img = -1, gn_ref = -1;
         bool gn_uniform = true;
         if (p.gn_acc != nullptr) {
-          gn_img = row_ok ? (int)(orow / p.gn_rows_per_img) : -1;
+          gn_img = !row_ok ? -1 : (p.idx32 ? (int)((unsigned)orow / (unsigned)p.gn_rows_per_img) : (int)(orow / p.gn_rows_per_img));
           gn_ref = __reduce_max_sync(0xffffffffu, gn_img);
           gn_uniform = __all_sync(0xffffffffu, gn_img == gn_ref || gn_img == -1);
         }

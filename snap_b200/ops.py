@@ -129,6 +129,17 @@ def conv_gn(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int, acc: torch.Ten
     return out
 
 
+def selftest_shifted_desc(a: torch.Tensor, b: torch.Tensor, shift: int, mode: int) -> torch.Tensor:
+    """a bf16 [256,64], b bf16 [64,64] -> f32 [128,64] = a[shift:shift+128] @ b^T through a row-shifted smem descriptor."""
+    _require(a, torch.bfloat16, "a")
+    _require(b, torch.bfloat16, "b")
+    assert tuple(a.shape) == (256, 64) and tuple(b.shape) == (64, 64) and a.is_contiguous() and b.is_contiguous()
+    out = torch.zeros((128, 64), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.lib().snapb200_selftest_shifted_desc(C.c_void_p(_ptr(a)), C.c_void_p(_ptr(b)), int(shift), int(mode),
+                                                         C.c_void_p(_ptr(out)), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # image-encoder kernels
 # --------------------------------------------------------------------------------------------

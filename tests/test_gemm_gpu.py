@@ -117,3 +117,29 @@ def test_gemm_epilogue_groupnorm_accumulators(n, cpg_n):
         s, q = x.sum(dim=(1, 3)), (x * x).sum(dim=(1, 3))
         assert torch.allclose(accd.cpu().sum(0)[..., 0], s, rtol=1e-5, atol=1e-3)
         assert torch.allclose(accd.cpu().sum(0)[..., 1], q, rtol=1e-5, atol=1e-3)
+
+
+def test_row_shifted_swizzled_descriptor():
+    """The halo form of the 3x3 conv reads its nine taps from ONE shared-memory block by moving the A descriptor's start by
+    whole rows (128 B).  Shown here on the device, bit-exactly (integer data): with SWIZZLE_128B the hardware derives the
+    XOR phase from the ABSOLUTE shared-memory address, so any start row works with the matrix-base-offset field left 0
+    (the block is 1024-byte aligned and was written by TMA with the same address-based pattern); setting the field to
+    (address >> 7) & 7 breaks every start row that is not a multiple of 8."""
+    from snap_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(-4, 5, (256, 64), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randint(-4, 5, (64, 64), device="cuda", generator=g).to(torch.bfloat16)
+    shifts = (0, 1, 3, 7, 8, 13, 64, 100, 127, 128)
+    ok0, ok1 = [], []
+    for shift in shifts:
+        ref = a[shift:shift + 128].float() @ b.float().t()
+        r0 = ops.selftest_shifted_desc(a, b, shift, 0)
+        r1 = ops.selftest_shifted_desc(a, b, shift, 1)
+        torch.cuda.synchronize()
+        ok0.append(bool(torch.equal(r0, ref)))
+        ok1.append(bool(torch.equal(r1, ref)))
+    print("shift        :", shifts)
+    print("base_offset=0:", ok0)
+    print("base_offset  :", ok1)
+    assert all(ok0), "row-shifted descriptors (base offset 0) must address the shifted rows"
+    assert all(o == (sh % 8 == 0) for o, sh in zip(ok1, shifts)), "the base-offset field is not an address correction"

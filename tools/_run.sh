@@ -1,5 +1,1 @@
-mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --config cfg4train --train-encoder --steps 8 --warmup 3 > gpurun_out/r3o_cfg4train_full_2gpu.json 2> gpurun_out/r3o_cfg4train_full_2gpu.err; echo rc=$?; tail -3 gpurun_out/r3o_cfg4train_full_2gpu.err; python -c "
-import json; d=json.loads(open('gpurun_out/r3o_cfg4train_full_2gpu.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['loss'], d['n_gpus'], d['applied_steps'], d['skipped_steps'], d['allreduce'])"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --config cfg4train --steps 10 --warmup 3 > gpurun_out/r3o_cfg4train_2gpu.json 2> gpurun_out/r3o_cfg4train_2gpu.err; echo rc=$?; python -c "
-import json; d=json.loads(open('gpurun_out/r3o_cfg4train_2gpu.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['loss'], d['n_gpus'], d['allreduce'])"
+timeout 300 python -m pytest tests/test_gemm_gpu.py -x -q -s -k shifted 2>&1 | grep -A3 "^shift "
