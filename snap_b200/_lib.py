@@ -65,7 +65,16 @@ def launch_count_reset() -> None:
 EXPORTED_SYMBOLS = [
     "snapb200_last_error", "snapb200_version", "snapb200_launch_count",
     "snapb200_launch_count_reset", "snapb200_gemm_bf16", "snapb200_conv_gn_bf16", "snapb200_selftest_shifted_desc",
+    "snapb200_conv3x3_halo_supported", "snapb200_conv3x3_halo_bf16",
 ]
+
+
+class Conv3x3Params(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("n_img", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("b", C.c_void_p), ("b_ld", C.c_longlong), ("n", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong),
+        ("gn_acc", C.c_void_p), ("gn_replica_stride", C.c_int),
+    ]
 
 
 class ConvGnParams(C.Structure):

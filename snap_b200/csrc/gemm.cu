@@ -17,8 +17,8 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        const CUtensorMap& tmR, GemmParams p, int ctas_per_sm, cudaStream_t s) {
   using Cfg = GemmCfg<BN, BK>;
   static DynSmemState smem_state;  // per device (one process may drive several GPUs)
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, BK, AMODE_TMA, CONVEPI>),
-                               Cfg::smem_bytes(Cfg::MAX_STAGES), &smem_state, "cudaFuncSetAttribute(gemm_tc)"))
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, BK, AMODE_TMA, CONVEPI>), 227 * 1024,
+                               &smem_state, "cudaFuncSetAttribute(gemm_tc)"))
     return rc;
   // occupancy plan: `ctas_per_sm` co-resident CTAs share the SM's 227 KB of shared memory and 512 TMEM
   // columns; memory-bound layers (small K) want several CTAs so that epilogues overlap main loops

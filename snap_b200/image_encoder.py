@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -89,6 +90,7 @@ class EncoderPlan:
         # skip convs) normalises its raw input in shared memory; the 3x3 convs keep the GroupNorm-apply kernel, which
         # writes their zero-bordered / phase-split operand.  True: also the 3x3 convs (slower).  False: no fusion.
         self.fused_gn = fused_gn
+        self.halo_conv = os.environ.get("SNAPB200_HALO_CONV", "1") != "0"   # A/B switch for measurements
         enc_cfg = config.encoder
         self.cfg = config
         self.n, self.H, self.W = n_img, H, W
@@ -304,8 +306,12 @@ class EncoderPlan:
             seg = [((a % 2) * 2 + (b % 2)) * plane + (a // 2) * wq + (b // 2) for a in range(3) for b in range(3)]
             m_rows, remap = plane, (hq, wq, 0, 0, ho, wo)
         y2 = self._view(self.buf_y, rows_out, nmid)  # y1 is dead once a2 is written
-        ops.gemm(u["a2"], B[u["w2"]], y2, m_rows=m_rows, seg_off=seg, seg_k=nmid, remap=remap,
-                 gn_acc=acc3, gn_rows_per_img=ho * wo)
+        if s == 1 and self.halo_conv and ops.conv3x3_halo_supported(nmid, nmid, w):
+            # stages 1-2: one shared-memory halo block per K chunk serves all nine taps (csrc/conv3x3_halo.cu)
+            ops.conv3x3_halo(u["a2"], n, h, w, nmid, B[u["w2"]], y2, gn_acc=acc3)
+        else:
+            ops.gemm(u["a2"], B[u["w2"]], y2, m_rows=m_rows, seg_off=seg, seg_k=nmid, remap=remap,
+                     gn_acc=acc3, gn_rows_per_img=ho * wo)
         if not joined:
             # a3 reuses the buffer of a1, which the projection (side stream) is still reading; conv3 adds its result
             torch.cuda.current_stream().wait_stream(self._side())

@@ -129,6 +129,28 @@ def conv_gn(x: torch.Tensor, n_img: int, H: int, W: int, Cc: int, acc: torch.Ten
     return out
 
 
+def conv3x3_halo_supported(Cc: int, n: int, W: int) -> bool:
+    return bool(_lib.lib().snapb200_conv3x3_halo_supported(int(Cc), int(n), int(W)))
+
+
+def conv3x3_halo(a: torch.Tensor, n_img: int, H: int, W: int, Cc: int, b: torch.Tensor, out: torch.Tensor,
+                 gn_acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride-1 conv of the zero-bordered input a bf16 [n_img*(H+2)*(W+2) (+ slack), Cc] with b bf16 [n, 9*Cc] ->
+    out bf16 [n_img*H*W, n] (dense); gn_acc: f64 [GN_REPLICAS, n_img, 32, 2] statistics of the output."""
+    _require(a, torch.bfloat16, "a")
+    _require(b, torch.bfloat16, "b")
+    _require(out, torch.bfloat16, "out")
+    p = _lib.Conv3x3Params()
+    p.a, p.n_img, p.H, p.W, p.C = _ptr(a), n_img, H, W, Cc
+    p.b, p.b_ld, p.n = _ptr(b), b.stride(0), b.shape[0]
+    p.out, p.ldo = _ptr(out), out.stride(0)
+    if gn_acc is not None:
+        _require(gn_acc, torch.float64, "gn_acc")
+        p.gn_acc, p.gn_replica_stride = _ptr(gn_acc), gn_acc.stride(0)
+    _lib.check(_lib.lib().snapb200_conv3x3_halo_bf16(C.byref(p), _stream()))
+    return out
+
+
 def selftest_shifted_desc(a: torch.Tensor, b: torch.Tensor, shift: int, mode: int) -> torch.Tensor:
     """a bf16 [256,64], b bf16 [64,64] -> f32 [128,64] = a[shift:shift+128] @ b^T through a row-shifted smem descriptor."""
     _require(a, torch.bfloat16, "a")

@@ -3,6 +3,7 @@
 Tolerance: outputs are fp32 sums of exactly-representable bf16 products, so only the summation
 order differs: |err| <= 1e-4 * max|ref| (fp32 output) and one bf16 ulp on top for bf16 outputs.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -143,3 +144,47 @@ def test_row_shifted_swizzled_descriptor():
     print("base_offset  :", ok1)
     assert all(ok0), "row-shifted descriptors (base offset 0) must address the shifted rows"
     assert all(o == (sh % 8 == 0) for o, sh in zip(ok1, shifts)), "the base-offset field is not an address correction"
+
+
+@pytest.mark.parametrize("n_img,H,W,C,N", [(2, 24, 40, 64, 64), (3, 17, 23, 64, 64), (1, 128, 168, 64, 64),
+                                           (2, 16, 20, 128, 128), (1, 30, 44, 128, 64), (2, 64, 84, 128, 128)])
+def test_conv3x3_halo_equals_nine_segment_gemm(n_img, H, W, C, N):
+    """`snapb200_conv3x3_halo_bf16` (one shared-memory halo block per K chunk, nine row-shifted descriptors, resident
+    weights) against the 9-segment form of the GEMM engine on the same zero-bordered input: identical products; for
+    C = 64 also the same accumulation order, i.e. BIT-identical outputs; GroupNorm statistics to double rounding."""
+    from snap_b200 import ops
+    assert ops.conv3x3_halo_supported(C, N, W)
+    g = torch.Generator(device="cuda").manual_seed(H * W + C)
+    dev = torch.device("cuda")
+    hp, wp = H + 2, W + 2
+    a = torch.zeros((n_img, hp, wp, C), dtype=torch.bfloat16, device=dev)
+    a[:, 1:-1, 1:-1] = torch.randn((n_img, H, W, C), device=dev, generator=g).to(torch.bfloat16)
+    rows_p = n_img * hp * wp
+    a_flat = torch.zeros((rows_p + 256, C), dtype=torch.bfloat16, device=dev)
+    a_flat[:rows_p] = a.view(rows_p, C)
+    b = (torch.randn((N, 9 * C), device=dev, generator=g) * (9 * C) ** -0.5).to(torch.bfloat16)
+    rows = n_img * H * W
+    seg = [(i - 1) * wp + (j - 1) for i in range(3) for j in range(3)]
+    outs, accs = [], []
+    for halo in (False, True):
+        out = torch.full((rows + 128, N), 3.0, dtype=torch.bfloat16, device=dev)
+        acc = torch.zeros((ops.GN_REPLICAS, n_img, 32, 2), dtype=torch.float64, device=dev)
+        if halo:
+            ops.conv3x3_halo(a_flat, n_img, H, W, C, b, out, gn_acc=acc)
+        else:
+            ops.gemm(a_flat, b, out, m_rows=rows_p, seg_off=seg, seg_k=C, remap=(hp, wp, 1, 1, H, W), gn_acc=acc,
+                     gn_rows_per_img=H * W)
+        torch.cuda.synchronize()
+        outs.append(out.float().cpu().numpy())
+        accs.append(acc.sum(0).cpu().numpy())
+    ref = torch.nn.functional.conv2d(a[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2),
+                                     b.float().view(N, 3, 3, C).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(rows, N)
+    assert (outs[1][rows:] == 3.0).all(), "rows beyond the output stay untouched"
+    err = np.abs(outs[1][:rows] - ref.cpu().numpy()).max()
+    assert err <= 2.0 ** -7 * max(1.0, float(ref.abs().max())), err
+    if C == 64:
+        assert np.array_equal(outs[0][:rows], outs[1][:rows])
+    else:
+        d = np.abs(outs[0][:rows] - outs[1][:rows])
+        assert d.max() <= 2.0 ** -7 * max(1.0, np.abs(outs[0]).max()) and (d > 0).mean() < 0.05
+    np.testing.assert_allclose(accs[1], accs[0], rtol=1e-3 if C > 64 else 1e-12, atol=1e-3 if C > 64 else 1e-9)

@@ -81,6 +81,24 @@ def fused_case(name, h, w, k, n, res=False, gn=True, gn_relu=False):
     return dict(name=name + " fused", ms=ms, gbps=byt / ms / 1e6, tflops=fl / ms / 1e9)
 
 
+def halo_case(name, h, w, k, n, gn=True):
+    rows = NIMG * h * w
+    hp, wp = h + 2, w + 2
+    if not ops.conv3x3_halo_supported(k, n, w):
+        print(f"{name:34s} unsupported by the halo kernel", flush=True)
+        return dict(name=name + " halo", ms=None)
+    a = bf(NIMG * hp * wp + 256, k)
+    b = bf(n, 9 * k)
+    acc = torch.zeros((ops.GN_REPLICAS, NIMG, 32, 2), dtype=torch.float64, device=dev)
+    out = torch.zeros((rows + 128, n), dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: ops.conv3x3_halo(a, NIMG, h, w, k, b, out, gn_acc=acc if gn else None))
+    byt = NIMG * hp * wp * k * 2 + rows * n * 2 + 9 * n * k * 2
+    fl = 2.0 * rows * n * k * 9
+    print(f"{name:34s} M={rows:7d} K={k * 9:5d} N={n:5d} gn={int(gn)} HALO "
+          f"  {ms * 1e3:8.1f} us  {byt / ms / 1e6:7.0f} GB/s  {fl / ms / 1e9:7.0f} TF/s", flush=True)
+    return dict(name=name + " halo", ms=ms, gbps=byt / ms / 1e6, tflops=fl / ms / 1e9)
+
+
 def gn_case(name, h, w, c, layout):
     rows = NIMG * h * w
     x = bf(rows + 128, c)
@@ -137,6 +155,11 @@ res.append(case("s2.conv2 3x3 128", *S[1], 128, 128, taps=9))
 res.append(case("s3.conv2 3x3 256", *S[2], 256, 256, taps=9))
 res.append(case("s3.conv2 3x3 256 bn=256", *S[2], 256, 256, taps=9, bn=256))
 res.append(case("s4.conv2 3x3 512", *S[3], 512, 512, taps=9))
+print("== 3x3 convs, halo kernel ==")
+res.append(halo_case("s1.conv2 3x3 64", *S[0], 64, 64))
+res.append(halo_case("s1.conv2 3x3 64 no-gn", *S[0], 64, 64, gn=False))
+res.append(halo_case("s2.conv2 3x3 128", *S[1], 128, 128))
+res.append(halo_case("s3.conv2 3x3 256", *S[2], 256, 256))
 print("== GroupNorm apply ==")
 res.append(gn_case("gn s1 256 dense", *S[0], 256, ops.LAYOUT_DENSE))
 res.append(gn_case("gn s1 64 dense", *S[0], 64, ops.LAYOUT_DENSE))
