@@ -156,6 +156,55 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_conv, ConvImpl,
                                   .Attr<int64_t>("m_rows").Attr<int32_t>("seg_k").Attr<int32_t>("with_residual")
                                   .Attr<int64_t>("rows_per_img").Attr<int32_t>("with_relu_stats").Attr<int32_t>("n_img"));
 
+// GroupNorm -> ReLU -> 1x1 conv in one launch (resnet.py:117-133, image_encoder.py:79-85): x bf16[n_img*H*W, C] RAW
+// activation, acc f64[8, n_img, 32, 2] its statistics, scale / bias f32[C], b bf16[N, C], optional residual bf16[M, N];
+// statistics of the output into gn_acc / gn_acc_relu (aliased in/out) when with_stats.
+static ffi::Error ConvGnImpl(cudaStream_t s, Buf x, Buf acc, Buf scale, Buf bias, Buf b, Buf residual, Buf gn_acc_in,
+                             Buf gn_acc_relu_in, Out y, Out gn_acc, Out gn_acc_relu, int32_t n_img, int32_t H, int32_t W,
+                             int32_t pre_relu, int32_t post_relu, int32_t with_residual, int32_t with_stats,
+                             int32_t with_relu_stats) {
+  (void)gn_acc_in;
+  (void)gn_acc_relu_in;
+  SnapConvGnParams p{};
+  p.x = x.untyped_data(); p.n_img = n_img; p.H = H; p.W = W; p.C = dim(x, 1);
+  p.acc = in<double>(acc); p.replica_stride = n_img * 64;
+  p.scale = in<float>(scale); p.bias = in<float>(bias);
+  p.pre_relu = pre_relu; p.post_relu = post_relu; p.taps = 1; p.stride = 1;
+  p.b = b.untyped_data(); p.b_rows = b.dimensions()[0]; p.b_cols = dim(b, 1); p.b_ld = p.b_cols; p.n = (int)p.b_rows;
+  p.out = y->untyped_data(); p.ldo = y->dimensions()[1];
+  if (with_residual) { p.residual = residual.untyped_data(); p.ldr = residual.dimensions()[1]; }
+  if (with_stats) {
+    p.gn_acc = out<double>(gn_acc);
+    p.gn_acc_relu = with_relu_stats ? out<double>(gn_acc_relu) : nullptr;
+    p.gn_replica_stride = n_img * 64;
+  }
+  return to_error(snapb200_conv_gn_bf16(&p, s));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_conv_gn, ConvGnImpl,
+                              SNAP_BIND().Arg<Buf>().Arg<Buf>().Arg<Buf>().Arg<Buf>().Arg<Buf>().Arg<Buf>().Arg<Buf>().Arg<Buf>()
+                                  .Ret<Buf>().Ret<Buf>().Ret<Buf>().Attr<int32_t>("n_img").Attr<int32_t>("H").Attr<int32_t>("W")
+                                  .Attr<int32_t>("pre_relu").Attr<int32_t>("post_relu").Attr<int32_t>("with_residual")
+                                  .Attr<int32_t>("with_stats").Attr<int32_t>("with_relu_stats"));
+
+// 3x3 / stride-1 conv on the zero-bordered layout as a halo GEMM (resnet.py:117-127): a bf16[n_img*(H+2)*(W+2), C],
+// b bf16[N, 9*C]; y bf16[n_img*H*W, N]; statistics of the output into gn_acc (aliased in/out).  Shapes the halo kernel
+// does not cover (snapb200_conv3x3_halo_supported) go through snapb200_xla_conv with nine segments.
+static ffi::Error Conv3x3HaloImpl(cudaStream_t s, Buf a, Buf b, Buf gn_acc_in, Out y, Out gn_acc, int32_t n_img, int32_t H,
+                                  int32_t W, int32_t with_stats) {
+  (void)gn_acc_in;
+  SnapConv3x3Params p{};
+  p.a = a.untyped_data(); p.n_img = n_img; p.H = H; p.W = W; p.C = dim(a, 1);
+  p.b = b.untyped_data(); p.b_ld = dim(b, 1); p.n = dim(b, 0);
+  p.out = y->untyped_data(); p.ldo = y->dimensions()[1];
+  if (with_stats) { p.gn_acc = out<double>(gn_acc); p.gn_replica_stride = n_img * 64; }
+  if (!snapb200_conv3x3_halo_supported(p.C, p.n, W))
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "conv3x3_halo: shape not covered, use snapb200_xla_conv");
+  return to_error(snapb200_conv3x3_halo_bf16(&p, s));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(snapb200_xla_conv3x3_halo, Conv3x3HaloImpl,
+                              SNAP_BIND().Arg<Buf>().Arg<Buf>().Arg<Buf>().Ret<Buf>().Ret<Buf>().Attr<int32_t>("n_img")
+                                  .Attr<int32_t>("H").Attr<int32_t>("W").Attr<int32_t>("with_stats"));
+
 // dense / 1x1 conv with bias (+ ReLU): (a bf16[M,K], b bf16[N,K], bias f32[N]) -> out bf16[M,N]  (layers.py:55-78)
 static ffi::Error DenseImpl(cudaStream_t s, Buf a, Buf b, Buf bias, Out y, bool relu) {
   SnapGemmParams p{};

@@ -19,6 +19,7 @@ DEFAULT_PATH_ENTRY_POINTS = {
     "snapb200_maxpool3x3s2", "snapb200_gn_stats", "snapb200_gn_apply", "snapb200_gemm_bf16", "snapb200_upsample2x",
     "snapb200_crop_relu", "snapb200_lift_fused_batched", "snapb200_fuse_max", "snapb200_match_head", "snapb200_rot_templates",
     "snapb200_xcorr_pad_map", "snapb200_xcorr_count", "snapb200_xcorr_scores_rows",
+    "snapb200_conv_gn_bf16", "snapb200_conv3x3_halo_bf16",   # round 2: GroupNorm fused into the 1x1 convs, halo 3x3 conv
 }
 
 
