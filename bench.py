@@ -42,7 +42,7 @@ LIFT_BYTES = V * 120 * 160 * 160 * 2 + (257 * 256 + 256 + 256 * 128 + 128) * 2 +
 KERNEL_SOURCES = {   # the files whose hash ties a DRAM-traffic capture to the kernel it measured
     "lift": ("snap_b200/csrc/lift_fused2.cu", "snap_b200/csrc/lift_fused2_impl.cuh", "snap_b200/csrc/lift_common.cuh"),
     "xcorr": ("snap_b200/csrc/xcorr_rows.cu",),
-    "gemm": ("snap_b200/csrc/gemm_tc.cuh", "snap_b200/csrc/gemm.cu"),
+    "gemm": ("snap_b200/csrc/gemm_tc.cuh", "snap_b200/csrc/gemm.cu", "snap_b200/csrc/conv3x3_halo.cu"),
     "gn_apply": ("snap_b200/csrc/encoder_kernels.cu",),
 }
 
@@ -766,7 +766,8 @@ def main():
 
     def phase_timer():
         import snap_b200.ops as ops_mod
-        names = ["lift_fused", "lift_fused_batched", "lift_gather_pool", "vertical_max", "gemm", "conv_gn", "gn_stats", "gn_apply", "std_weights_batched",
+        names = ["lift_fused", "lift_fused_batched", "lift_gather_pool", "vertical_max", "gemm", "conv_gn", "conv3x3_halo", "gn_stats", "gn_apply",
+                 "std_weights_batched",
                  "root_pack_image", "root_pack_weights", "root_conv", "maxpool3x3s2", "upsample2x", "crop_relu",
                  "match_head"]
         orig = {n: getattr(ops_mod, n) for n in names}
@@ -779,6 +780,8 @@ def main():
                     key = f"gemm[k={a[0].shape[1]},n={a[1].shape[0]},seg={len(k.get('seg_off', (0,)))}]"
                 if n == "conv_gn":
                     key = f"conv_gn[c={a[4]},n={a[8].shape[0]},taps={k.get('taps', 1)},s={k.get('stride', 1)}]"
+                if n == "conv3x3_halo":
+                    key = f"conv3x3_halo[c={a[4]},n={a[5].shape[0]}]"
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record(); r = orig[n](*a, **k); e.record()
                 evs.append((key, s, e))
@@ -821,7 +824,7 @@ def main():
     lift_traffic, lift_traffic_src = measured_traffic("lift")
     xcorr_traffic, xcorr_traffic_src = measured_traffic("xcorr")
     # ---- image encoder: everything of a step that is not the lift / proj MLP / matching head ----
-    enc_keys = [k for k in phases if k.startswith(("gemm[", "conv_gn[", "gn_", "root_", "std_weights", "maxpool", "upsample"))
+    enc_keys = [k for k in phases if k.startswith(("gemm[", "conv_gn[", "conv3x3_halo[", "gn_", "root_", "std_weights", "maxpool", "upsample"))
                 and k not in ("gemm[k=128,n=160,seg=1]",)]
     enc_ms_tile = sum(phases[k] for k in enc_keys) / BT
     ENC_FLOPS = 2.0 * 28.1e9 * V                      # ~28.1 GMAC per 480x640 image
@@ -1061,8 +1064,10 @@ def main():
                                  "executed_flops < algorithmic_flops and frac may exceed the dense-GEMM ceiling",
                          "hbm_gbs_if_bytes_only": LIFT_BYTES / (lift_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak},
             "roofline_encoder": {
-                "kernel": "image encoder of a tile = 4 images: implicit-GEMM root conv, 48 conv GEMMs (gemm_tc_kernel, tcgen05 + TMA) "
-                          "with GroupNorm statistics in their epilogues, 52 GroupNorm-apply passes, FPN",
+                "kernel": "image encoder of a tile = 4 images: implicit-GEMM root conv, 52 conv launches (gemm_tc_kernel, tcgen05 + TMA: "
+                          "1x1 convs -- 11 of them with GroupNorm + ReLU applied to the raw A tile in shared memory (A_TGN1) --, "
+                          "conv3x3_halo_kernel for the 3x3 convs of stages 1-2, 9-segment GEMMs for the others) with GroupNorm "
+                          "statistics in their epilogues, 41 GroupNorm-apply passes, FPN",
                 "bound": "tensor", "achieved": ENC_FLOPS / (enc_ms_tile * 1e-3) / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
                 "frac": ENC_FLOPS / (enc_ms_tile * 1e-3) / 1e12 / tf_sus, "ms_per_tile": enc_ms_tile,
                 "algorithmic_flops": ENC_FLOPS, "algorithmic_bytes": ENC_BYTES,

@@ -306,7 +306,7 @@ class EncoderPlan:
             seg = [((a % 2) * 2 + (b % 2)) * plane + (a // 2) * wq + (b // 2) for a in range(3) for b in range(3)]
             m_rows, remap = plane, (hq, wq, 0, 0, ho, wo)
         y2 = self._view(self.buf_y, rows_out, nmid)  # y1 is dead once a2 is written
-        if s == 1 and self.halo_conv and ops.conv3x3_halo_supported(nmid, nmid, w):
+        if s == 1 and getattr(self, "halo_conv", True) and ops.conv3x3_halo_supported(nmid, nmid, w):
             # stages 1-2: one shared-memory halo block per K chunk serves all nine taps (csrc/conv3x3_halo.cu)
             ops.conv3x3_halo(u["a2"], n, h, w, nmid, B[u["w2"]], y2, gn_acc=acc3)
         else:

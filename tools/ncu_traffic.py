@@ -110,16 +110,17 @@ if rep:
 if not args.skip_step:
     # every GEMM / GroupNorm launch of one eager step with a light metric set (DRAM bytes, duration, tensor pipe, issue
     # slots), then `--set full` summaries of the three instantiations that dominate the step
-    rep = capture("step", "gemm_tc_kernel|gn_apply_kernel", [py, "bench.py", "--profile-step", "--no-cpu-baseline"], 400, light=True)
+    rep = capture("step", "gemm_tc_kernel|gn_apply_kernel|conv3x3_halo_kernel", [py, "bench.py", "--profile-step", "--no-cpu-baseline"], 400, light=True)
     for nm, rx, skip in (("gemm_128_64_conv", "gemm_tc_kernel<128, 64, 0, 1>", 3), ("gemm_256_64", "gemm_tc_kernel<256, 64, 0, 0>", 2),
-                         ("gn_apply_dense", "gn_apply_kernel<0, 0, 0>", 2)):
+                         ("gn_apply_dense", "gn_apply_kernel<0, 0, 0>", 2), ("conv_gn_tgn1", "gemm_tc_kernel<64, 64, 3, 1>", 1),
+                         ("conv3x3_halo", "conv3x3_halo_kernel<64, 1, 1>", 1)):
         r2 = capture(nm, rx.replace("(", ".").replace("<", ".").replace(">", ".").replace(", ", ".."), [py, "bench.py", "--profile-step", "--no-cpu-baseline"], 1, skip=skip)
         if r2:
             summarize(r2, f"{args.tag}_{nm}_ncu_full.txt")
     if rep:
         stats = kernel_stats(rep)
         for key, pat in (("gemm", "gemm_tc_kernel"), ("gn_apply", "gn_apply_kernel")):
-            sel = [s for s in stats if pat in s[0]]
+            sel = [s for s in stats if pat in s[0] or (key == "gemm" and "conv3x3_halo_kernel" in s[0])]
             if not sel:
                 continue
             by = {}
