@@ -410,6 +410,18 @@ extern "C" int snapb200_root_conv_bf16(const SnapRootConvParams* q, void* stream
   rc = make_tmap_2d_bf16(&tmB, q->b, q->n, q->KH * 32, q->KH * 32, bn, 32);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const int env_r3d = env_int("SNAPB200_ROOT_STAGED", 1);
+  if (env_r3d && bn == 64 && q->n == 64 && q->gn_acc == nullptr && q->ldo % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(q->out) & 15) == 0) {
+    // staged epilogue: 32-pixel slabs leave through a 3D TMA map over [n_img * Ho][Wo][C] that clips the columns >= Wo of
+    // the last 128-column block -- no per-row remap arithmetic, whole 128-byte lines instead of 32 B per lane
+    CUtensorMap tmO;
+    rc = make_tmap_rows3d_bf16(&tmO, q->out, q->n, q->ldo, q->Wo, (long long)q->n_img * q->Ho);
+    if (rc) return rc;
+    p.remap = 0;
+    p.stage_out = 1;
+    return launch_inst<64, 32, true>(tmA, tmB, tmO, tmO, p, 2, s);
+  }
   switch (bn) {
     case 64: return launch_inst<64, 32>(tmA, tmB, tmA, tmA, p, 2, s);
     case 128: return launch_inst<128, 32>(tmA, tmB, tmA, tmA, p, 2, s);

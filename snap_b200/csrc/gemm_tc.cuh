@@ -692,9 +692,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async_smem();
         pair_bar_sync(q);
         if (hw == 0 && lane == 0) {
+          if (p.a4d) {   // implicit root conv: tile = (image row block, block of 128 output columns); a 3D map clips at Wo
+            const int rb = t.mt / p.r4_wtiles, wb = t.mt - rb * p.r4_wtiles;
 #pragma unroll
-          for (int h = 0; h < BN / 64; ++h)
-            tma_store_2d(&tmO, slab + h * 4096, t.nt * BN + h * 64, t.mt * 128 + q * 32);
+            for (int h = 0; h < BN / 64; ++h) tma_store_3d(&tmO, slab + h * 4096, t.nt * BN + h * 64, wb * 128 + q * 32, rb);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              tma_store_2d(&tmO, slab + h * 4096, t.nt * BN + h * 64, t.mt * 128 + q * 32);
+          }
           bulk_commit_group();
           if (p.res_tma && tile + 1 < tile_end) {  // prefetch the next tile's residual behind the MMA wait
             bulk_wait_group_read0();

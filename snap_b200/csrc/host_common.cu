@@ -142,6 +142,24 @@ int make_tmap_window4d_bf16(CUtensorMap* out, const void* base, int Wo, long lon
   return SNAPB200_OK;
 }
 
+int make_tmap_rows3d_bf16(CUtensorMap* out, const void* base, int C, long long ld, int W, long long rows) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  SNAP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SNAP_REQUIRE((ld * 2) % 16 == 0 && C % 8 == 0, "TMA pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)W};
+  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SNAPB200_ERR_CUDA, "cuTensorMapEncodeTiled(rows3d) failed (%d) C=%d ld=%lld W=%d rows=%lld", (int)r, C, ld, W, rows);
+  return SNAPB200_OK;
+}
+
 int make_tmap_nd_bf16_plain(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                             const unsigned long long* strides_bytes, const unsigned* box) {
   EncodeTiledFn enc = get_encode();

@@ -42,6 +42,11 @@ int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, long long rows, 
 int make_tmap_window4d_bf16(CUtensorMap* out, const void* base, int Wo, long long step_bytes, int Hq,
                             long long row_bytes, int N);
 
+// 3D bf16 map over a dense NHWC output viewed as [rows = N*H][W][C] (pixel pitch ld elements): box {64 channels, 32 pixels,
+// 1 row}, SWIZZLE_128B.  A store of 32 consecutive pixels of one image row is clipped at W by the hardware, so a GEMM whose
+// M tiles run over W rounded up to 128 (the implicit root conv) needs no per-row remap in its epilogue.
+int make_tmap_rows3d_bf16(CUtensorMap* out, const void* base, int C, long long ld, int W, long long rows);
+
 // rank-N (<= 5) un-swizzled bf16 map: dims / box innermost first, strides_bytes[i] = pitch of dimension i + 1
 int make_tmap_nd_bf16_plain(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                             const unsigned long long* strides_bytes, const unsigned* box);
