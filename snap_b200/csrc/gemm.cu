@@ -260,6 +260,10 @@ extern "C" int snapb200_conv_gn_bf16(const SnapConvGnParams* q, void* stream) {
   if (t1_ok) {
     // 1x1 conv: the two-CTAs-per-SM form with the conv epilogue (staged TMA stores, TMA residual)
     bn = q->n % 128 == 0 ? 128 : 64;
+    // wide-K layers with N >= 256 (conv1 of stages 3-4): 128 x 256 tiles at one CTA per SM, so that the A tile is
+    // normalised once per 256 output columns instead of once per 128
+    static const int env_bn256 = env_int("SNAPB200_T1_BN256", 1);
+    if (env_bn256 && q->n % 256 == 0 && q->C >= 512) bn = 256;
     p.n_tiles = q->n / bn;
     while ((1 << p.g_cpg_log) < cpg_in) ++p.g_cpg_log;
     CUtensorMap tmO, tmR;
@@ -276,6 +280,7 @@ extern "C" int snapb200_conv_gn_bf16(const SnapConvGnParams* q, void* stream) {
       if (rc) return rc;
     }
     if (bn == 64) return launch_t1_inst<64>(tmA, tmB, tmO, tmR, p, s);
+    if (bn == 256) return launch_t1_inst<256>(tmA, tmB, tmO, tmR, p, s);
     return launch_t1_inst<128>(tmA, tmB, tmO, tmR, p, s);
   }
   if (q->stride == 1) {

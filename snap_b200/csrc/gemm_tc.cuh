@@ -666,8 +666,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           if (i + 1 < NCW) tmem_ld16(taddr + (uint32_t)((i + 1) * 16), v[(i + 1) & 1]);
           const uint32_t(&vv)[16] = v[i & 1];
-          uint8_t* p0 = rowp + (((uint32_t)(2 * i) << 4) ^ swz16);
-          uint8_t* p1 = rowp + (((uint32_t)(2 * i + 1) << 4) ^ swz16);
+          // chunk i of this warp = 16-column chunk cbase + i of the tile: 64-column half (cbase + i) / 4, 16-byte slots
+          // 2 ((cbase + i) % 4) and + 1 of this lane's 128-byte row, XOR-swizzled by row % 8 (i is a compile-time constant)
+          uint8_t* rp = rowp + ((((cbase & 3) + i) >> 2) * 4096);
+          uint8_t* p0 = rp + (((uint32_t)(2 * (i & 3)) << 4) ^ swz16);
+          uint8_t* p1 = rp + (((uint32_t)(2 * (i & 3) + 1) << 4) ^ swz16);
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(vv[2 * j]), __uint_as_float(vv[2 * j + 1]));

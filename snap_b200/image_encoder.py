@@ -262,9 +262,10 @@ class EncoderPlan:
         # fused_gn == "1x1": every stride-1 1x1 conv normalises its raw input inside the GEMM (A_TGN1); only the 3x3
         # conv's input goes through the GroupNorm-apply kernel (it writes the zero-bordered / phase-split copy).
         # "auto" (default) fuses where it is measured to pay (profiles/r02_notes.md): conv1 / conv_proj of the units
-        # whose bottleneck width fits one N tile (stages 1-2: the 352 / 176 MB pre-activation copy disappears) and the
-        # FPN skip convs; conv3 (epilogue-bound: residual + statistics) and the narrow-M stages 3-4 keep the apply pass.
-        f1 = self.fused_gn == "1x1" or (self.fused_gn == "auto" and nmid <= 128)
+        # whose bottleneck width fits one N tile (stages 1-2 with 128 x 64 / 128 x 128 tiles: the 352 / 176 MB
+        # pre-activation copy disappears; stage 3 with 128 x 256 tiles at one CTA per SM: 64 vs 42 + 36 us) and the FPN
+        # skip convs; conv3 (epilogue-bound: residual + statistics) and stage 4 (M = 10,752 rows) keep the apply pass.
+        f1 = self.fused_gn == "1x1" or (self.fused_gn == "auto" and nmid <= 256)
         f3 = self.fused_gn == "1x1"
         gn1, gn2, gn3 = u["gn"]
         joined = True
