@@ -123,16 +123,40 @@ def latest_checkpoint(ckpt_dir: str, prefix: str = "checkpoint_") -> Optional[st
     return os.path.join(ckpt_dir, sorted(names, key=_natural_key)[-1]) if names else None
 
 
-def save_checkpoint(ckpt_dir: str, state: Dict, step: int, prefix: str = "checkpoint_", overwrite: bool = False) -> str:
-    """Write `state` (e.g. {'params': ..., 'global_step': ...}) as `<ckpt_dir>/<prefix><step>` (atomic rename)."""
+class InvalidCheckpointError(Exception):
+    """`flax.errors.InvalidCheckpointError`: a checkpoint at an equal or later step already exists."""
+
+
+def _steps(ckpt_dir: str, prefix: str):
+    if not os.path.isdir(ckpt_dir):
+        return []
+    return sorted(int(n[len(prefix):]) for n in os.listdir(ckpt_dir) if n.startswith(prefix) and n[len(prefix):].isdigit())
+
+
+def save_checkpoint(ckpt_dir: str, state: Dict, step: int, prefix: str = "checkpoint_", keep: int = 1,
+                    overwrite: bool = False) -> str:
+    """Write `state` (e.g. {'params': ..., 'global_step': ...}) as `<ckpt_dir>/<prefix><step>` (atomic rename), with the
+    rules of the legacy `flax.training.checkpoints.save_checkpoint` (restated from flax's published source; flax is not
+    installed here): saving at a step that is not later than the newest existing checkpoint raises unless `overwrite`
+    (which then removes the checkpoints at later steps), and only the `keep` newest checkpoints are retained.
+    bf16 tensors are written widened to float32 (exact); a loaded bf16 checkpoint therefore comes back as float32."""
     os.makedirs(ckpt_dir, exist_ok=True)
     path = os.path.join(ckpt_dir, f"{prefix}{step}")
-    if os.path.exists(path) and not overwrite:
-        raise FileExistsError(path)
+    steps = _steps(ckpt_dir, prefix)
+    if steps and step <= steps[-1]:
+        if not overwrite:
+            raise InvalidCheckpointError(f"trying to save an outdated checkpoint at step {step} <= latest step {steps[-1]} "
+                                         f"in {ckpt_dir} (pass overwrite=True to replace it and drop the later ones)")
+        for st in steps:
+            if st > step:
+                os.remove(os.path.join(ckpt_dir, f"{prefix}{st}"))
     tmp = path + "tmp"
     with open(tmp, "wb") as f:
         f.write(msgpack_serialize(state))
     os.replace(tmp, path)
+    if keep is not None and keep > 0:
+        for st in _steps(ckpt_dir, prefix)[:-keep]:
+            os.remove(os.path.join(ckpt_dir, f"{prefix}{st}"))
     return path
 
 

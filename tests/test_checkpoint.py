@@ -3,6 +3,8 @@ msgpack specification + the ext-type layout of flax/serialization.py, round trip
 a full BEVLocalizer parameter tree through save / restore / check_tree."""
 import struct
 
+import os
+
 import numpy as np
 import pytest
 
@@ -55,10 +57,20 @@ def test_train_state_round_trip_and_tree_check(tmp_path):
     state = {"global_step": np.int32(1234), "params": tree, "model_state": {}, "rng": np.array([0, 1], np.uint32),
              "opt_state": {"0": {"count": np.int32(1234)}}, "metadata": {"lr": 1e-3}}
     for step in (9, 10, 1234):
-        path = ck.save_checkpoint(str(tmp_path), {**state, "global_step": np.int32(step)}, step)
+        path = ck.save_checkpoint(str(tmp_path), {**state, "global_step": np.int32(step)}, step, keep=3)
     assert ck.latest_checkpoint(str(tmp_path)) == path and path.endswith("checkpoint_1234")   # natural sort: 1234 > 10 > 9
-    with pytest.raises(FileExistsError):
-        ck.save_checkpoint(str(tmp_path), state, 1234)
+    # flax's legacy rules: an equal or earlier step is refused unless overwrite (which drops the later checkpoints) ...
+    with pytest.raises(ck.InvalidCheckpointError):
+        ck.save_checkpoint(str(tmp_path), state, 1234, keep=3)
+    with pytest.raises(ck.InvalidCheckpointError):
+        ck.save_checkpoint(str(tmp_path), state, 100, keep=3)
+    # ... and only the `keep` newest checkpoints survive a save
+    d2 = tmp_path / "rolling"
+    for step in (1, 2, 3, 4):
+        ck.save_checkpoint(str(d2), {"global_step": np.int32(step)}, step, keep=2)
+    assert sorted(os.listdir(d2)) == ["checkpoint_3", "checkpoint_4"]
+    ck.save_checkpoint(str(d2), {"global_step": np.int32(3)}, 3, keep=2, overwrite=True)
+    assert sorted(os.listdir(d2)) == ["checkpoint_3"] and ck.restore_checkpoint(str(d2))["global_step"] == 3
     back = ck.restore_checkpoint(str(tmp_path))
     assert back["global_step"] == 1234 and back["metadata"] == {"lr": 1e-3} and back["model_state"] == {}
     p = ck.load_params(str(tmp_path))
