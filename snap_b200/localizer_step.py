@@ -76,7 +76,8 @@ class FrozenEncoderBackward:
                  valid_j: Optional[torch.Tensor], poses: torch.Tensor, scores: torch.Tensor, cell_size: float,
                  mask_out_of_bounds: bool, clip_negative_scores: bool, remove: Optional[Sequence[float]],
                  dr_samples: Optional[torch.Tensor], dt_samples: Optional[torch.Tensor],
-                 map_scenes: List[SceneContext], query_scenes: List[SceneContext]) -> Dict:
+                 map_scenes: List[SceneContext], query_scenes: List[SceneContext],
+                 example_weights: Optional[torch.Tensor] = None) -> Dict:
         """Arguments up to `dt_samples`: those of `LocalizerLossBackward.backward`; then one `SceneContext` per example
         for the map and the query side.  Returns {'bev_mapper': grads tree, ['bev_mapper_query': grads tree,]
         'temperature': f32 [], 'encoder_cotangents': {'map': [dcrop per example], 'query': [...]}} (device tensors for the
@@ -87,7 +88,8 @@ class FrozenEncoderBackward:
         for m in {id(self.head_map): self.head_map, id(self.head_q): self.head_q}.values():
             m.zero_grads()
         dfq, dfm, dtemp = self.loc.backward(maps, f_p_q, map_features, q_xy_p, valid_j, poses, scores, cell_size,
-                                            mask_out_of_bounds, clip_negative_scores, remove, dr_samples, dt_samples)
+                                            mask_out_of_bounds, clip_negative_scores, remove, dr_samples, dt_samples,
+                                            example_weights=example_weights)
         enc = {"map": [], "query": []}
         for b in range(B):
             enc["map"].append(self._side(self.lift_map, self.head_map, map_scenes[b], dfm[b].to(torch.bfloat16)).clone())

@@ -36,7 +36,7 @@ class LocalizerLossBackward:
                  valid_j: Optional[torch.Tensor], poses: torch.Tensor, scores: torch.Tensor, cell_size: float,
                  mask_out_of_bounds: bool, clip_negative_scores: bool = True,
                  remove: Optional[Sequence[float]] = None, dr_samples: Optional[torch.Tensor] = None,
-                 dt_samples: Optional[torch.Tensor] = None):
+                 dt_samples: Optional[torch.Tensor] = None, example_weights: Optional[torch.Tensor] = None):
         """maps = the forward's `pose_estimation.SimilarityMaps`; f_p_q bf16 [B,N,D]; map_features bf16 [B,H,W,D]; poses f32
         [B,P1,3] (ground truth first) and scores f32 [B,P1] as scored by the forward; dr / dt = the per-sample errors of
         `loc_nll` when `remove` (threshold_remove_accurate_poses) is set.
@@ -53,6 +53,11 @@ class LocalizerLossBackward:
         buf = self._buffers(B, N, HW, D, P1)
         Np = buf["Np"]
         ops.loc_nll_backward(scores.contiguous(), remove, dr_samples, dt_samples, buf["dscores"], buf["dtemp"])
+        if example_weights is not None:
+            # the kernel differentiates mean_b(nll_b); `trainer.py:221` means over batch['batch_mask'] instead: example b
+            # gets the weight mask_b * B / sum(mask) (f32 [B], device)
+            buf["dscores"].mul_(example_weights[:, None])
+            buf["dtemp"].mul_(example_weights)
         ops.loc_pose_scoring_backward(maps.sim, maps.point_scale, q_xy_p.contiguous(), valid_j, poses.contiguous(),
                                       buf["dscores"], H, W, cell_size, mask_out_of_bounds, clip_negative_scores, buf["dsim"])
         buf["fq"][:, :N].copy_(f_p_q)                      # rows N..Np stay zero (split-K kernel: M multiple of 16)

@@ -193,7 +193,7 @@ class LocalizerTrainer:
                               valid_j, pred["map_t_query_samples"], pred["scores_poses"], m.grid_map.cell_size,
                               c.mask_score_out_of_bounds, c.clip_negative_scores, remove, dr, dt,
                               self._contexts(pred["map"], "bev_mapper"),
-                              self._contexts(pred["query"], self.sides[-1]))
+                              self._contexts(pred["query"], self.sides[-1]), example_weights=self._example_weights(data, B))
         for v, path in zip(self.bucket.views, self.paths):
             if path == ("temperature",):
                 v.copy_(g["temperature"].reshape(1))
@@ -214,6 +214,17 @@ class LocalizerTrainer:
             for v, (_, _, gt) in zip(self.enc_bucket.views, self.enc.leaves):
                 v.copy_(gt.reshape(v.shape))
         return pred, losses, metrics
+
+    def _example_weights(self, data: Dict, B: int) -> Optional[torch.Tensor]:
+        """`trainer.py:221`: the loss is the mean over `batch['batch_mask']` (padded last batches): weight of example b in
+        the mean-over-B gradient the backward kernels produce = mask_b * B / sum(mask).  None without a mask."""
+        mask = data.get("batch_mask")
+        if mask is None:
+            return None
+        m = np.asarray(mask, dtype=F).reshape(-1)
+        if m.shape[0] != B or m.sum() <= 0:
+            raise ValueError("batch_mask must have one entry per example and at least one valid example")
+        return torch.from_numpy((m * (B / m.sum())).astype(F)).to(self.dev)
 
     def _encode_images(self, data: Dict) -> Dict:
         """Training forward of the shared image encoder over the map and the query images of the step; the two pyramids are

@@ -16,6 +16,21 @@ from . import _cache, configs, image_encoder, ops, types
 F = np.float32
 
 
+def apply_batch_mask(dlogits: torch.Tensor, data, B: int) -> None:
+    """`trainer.py:221`: the reference means the loss over `batch['batch_mask']`; the loss-gradient kernel divides by B.
+    Rescale example b's rows of dlogits (bf16 [B * cells, C]) by mask_b * B / sum(mask) in place (no-op without a mask;
+    the factor is exact for the usual all-ones mask and one bf16 rounding otherwise)."""
+    mask = data.get("batch_mask") if isinstance(data, dict) else None
+    if mask is None:
+        return
+    m = np.asarray(mask, dtype=np.float32).reshape(-1)
+    if m.shape[0] != B or m.sum() <= 0:
+        raise ValueError("batch_mask must have one entry per example and at least one valid example")
+    w = torch.from_numpy((m * (B / m.sum())).astype(np.float32)).to(dlogits.device)
+    v = dlogits[: B * (dlogits.shape[0] // B)].view(B, -1, dlogits.shape[1])
+    v.copy_((v.float() * w.view(B, 1, 1)).to(dlogits.dtype))
+
+
 class _StagePlan(image_encoder.EncoderPlan):
     """A ResNetStage(block_size, nmid=C/4, stride 1) over [n_img, H, W, C] with the EncoderPlan unit machinery."""
 
@@ -227,6 +242,7 @@ class MLPHeadTrainer:
         ops.sem_loss_grad(ctx["logits"], ctx["labels_area"], ctx["valid_area"], ctx["labels_excl"], ctx["masks_indep"],
                           ctx["valid"], self.num_area, self.num_excl, self.num_indep, ctx["weights"], buf["counts"],
                           buf["dlogits"])
+        apply_batch_mask(buf["dlogits"], data, B)
         x0 = plane.features.contiguous().view(rows, -1)
         acts = [x0] + buf["h"][:-1]                       # input of layer i
         dy = buf["dlogits"]

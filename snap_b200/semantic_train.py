@@ -26,7 +26,7 @@ from typing import Dict, List
 import numpy as np
 import torch
 
-from . import image_encoder, ops, types
+from . import image_encoder, ops, semantic_net, types
 
 F = np.float32
 
@@ -251,6 +251,7 @@ class StageHeadTrainer:
         ops.sem_loss_grad(ctx["logits"], ctx["labels_area"], ctx["valid_area"], ctx["labels_excl"], ctx["masks_indep"],
                           ctx["valid"], self.num_area, self.num_excl, self.num_indep, ctx["weights"], buf["counts"],
                           buf["dlogits"])
+        semantic_net.apply_batch_mask(buf["dlogits"], data, n)
         self.backward(plane, buf)
         self.bucket.allreduce_mean()                                             # jax.lax.pmean (trainer.py:231-234)
         if update:

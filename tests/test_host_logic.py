@@ -273,3 +273,22 @@ def test_localizer_trainer_host_side_layout_and_clipping():
     cfg2.add_confidence_query = True
     with pytest.raises(NotImplementedError):
         localizer_trainer.LocalizerTrainer(bev_localizer.BEVLocalizer(cfg2, None, types.Grid2D((32, 32), 0.2)), p, device="cpu")
+
+
+def test_batch_mask_rescales_the_loss_gradient_rows():
+    """`trainer.py:221` means the loss over batch['batch_mask']: example b's cotangent rows get mask_b * B / sum(mask)."""
+    import numpy as np
+    import pytest
+    import torch
+    from snap_b200.semantic_net import apply_batch_mask
+    d = torch.arange(24, dtype=torch.float32).reshape(12, 2).to(torch.bfloat16)
+    ref = d.clone()
+    apply_batch_mask(d, {}, 3)
+    assert torch.equal(d, ref)
+    apply_batch_mask(d, {"batch_mask": np.array([1, 1, 1])}, 3)
+    assert torch.equal(d, ref)
+    apply_batch_mask(d, {"batch_mask": np.array([1, 0, 1])}, 3)
+    want = ref.float().view(3, 4, 2) * torch.tensor([1.5, 0.0, 1.5]).view(3, 1, 1)
+    assert torch.equal(d.float().view(3, 4, 2), want.to(torch.bfloat16).float())
+    with pytest.raises(ValueError):
+        apply_batch_mask(d, {"batch_mask": np.array([0, 0, 0])}, 3)

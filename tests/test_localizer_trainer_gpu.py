@@ -137,3 +137,23 @@ def test_full_training_step_with_the_image_encoder():
     k0 = np.asarray(p["bev_mapper"]["streetview_encoder"]["image_encoder"]["encoder"]["root_block"]["conv_root"]["kernel"])
     assert tree["encoder"]["root_block"]["conv_root"]["kernel"].shape == k0.shape
     assert np.abs(tree["encoder"]["root_block"]["conv_root"]["kernel"] - k0).max() > 0
+
+
+def test_batch_mask_weights_the_examples_like_a_masked_mean():
+    """`trainer.py:221`: loss = mean over batch['batch_mask'].  On one batch and one sampling seed the gradients are linear in
+    the example weights: g(mask [1,0]) + g(mask [0,1]) = 2 g(mask [1,1]), and an all-ones mask equals no mask."""
+    from snap_b200 import localizer_trainer
+    loc, p, data = _setup(batch=2)
+    tr = localizer_trainer.LocalizerTrainer(loc, p, lr=1e-3)
+
+    def grads(mask):
+        d = dict(data) if mask is None else dict(data, batch_mask=np.asarray(mask))
+        tr.train_step(d, {"sampling": _gen()}, update=False)
+        torch.cuda.synchronize()
+        return tr.bucket.flat.clone()
+    g_none, g11, g10, g01 = grads(None), grads([1, 1]), grads([1, 0]), grads([0, 1])
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    print(f"all-ones mask vs none {rel(g11, g_none):.2e}; g10 + g01 vs 2 g11 {rel(g10 + g01, 2 * g11):.2e}; |g10| {float(g10.norm()):.3e} |g01| {float(g01.norm()):.3e}")
+    assert rel(g11, g_none) < 1e-3            # fp32 atomics in the scatter-add: order-dependent last bits
+    assert rel(g10 + g01, 2 * g11) < 2e-2     # bf16 cotangent rows round differently at different scales
+    assert rel(g10, g01) > 1e-2               # the two examples do differ
