@@ -1,13 +1,8 @@
 mkdir -p gpurun_out
-( timeout 1500 python tools/ncu_traffic.py --tag r02 > gpurun_out/r3w_traffic.log 2>&1; echo traffic rc=$? )
-cp gpurun_out/traffic.json profiles/traffic.json
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r3w_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r3w_pytest.log
-timeout 600 python bench.py > gpurun_out/r3w_bench.json 2> gpurun_out/r3w_bench.err; echo bench rc=$?
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r3w_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r3w_ncu_bench.log 2>&1; echo ncu rc=$?
-timeout 600 python bench.py --config cfg4 > gpurun_out/r3w_cfg4.json 2> gpurun_out/r3w_cfg4.err; echo cfg4 rc=$?
-timeout 600 python bench.py --config cfg5 > gpurun_out/r3w_cfg5.json 2> gpurun_out/r3w_cfg5.err; echo cfg5 rc=$?
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --config cfg4train --train-encoder --steps 6 --warmup 3 > gpurun_out/r3x_cfg4train_full_8gpu.json 2> gpurun_out/r3x_cfg4train_full_8gpu.err; echo rc=$?
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r3x_bench_8gpu.json 2> gpurun_out/r3x_bench_8gpu.err; echo rc=$?
 python -c "
 import json
-for f in ('r3w_bench','r3w_cfg4','r3w_cfg5'):
-    d=json.loads(open('gpurun_out/'+f+'.json').read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d['e2e']['value'], d.get('roofline',{}).get('traffic'))
+for f in ('r3x_cfg4train_full_8gpu','r3x_bench_8gpu'):
+    d=json.loads(open('gpurun_out/'+f+'.json').read().strip().splitlines()[-1]); print(f, d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d.get('allreduce'))
 "
