@@ -546,9 +546,10 @@ def main():
                          "all-reduce, Adam; --train-encoder includes the image encoder)")
     ap.add_argument("--train-encoder", action="store_true",
                     help="cfg4train: also train the street-view image encoder (the reference's full training step)")
-    ap.add_argument("--batch", type=int, default=8,
+    ap.add_argument("--batch", type=int, default=16,
                     help="tiles (scenes) per GPU per step; the reference trains with 4 per device (B = 32 on 8 GPUs), map building "
-                         "batches freely: measured 636 / 765 / 857 tiles/s at 2 / 4 / 8 on one B200 (per-kernel fixed costs amortise)")
+                         "batches freely.  Final round-2 build on one B200: 1009 / 1062 / 1090 / 1104 / 1092 tiles/s at 8 / 12 / 16 / 24 "
+                         "/ 32 tiles per step (round 1: 636 / 765 / 857 at 2 / 4 / 8): per-kernel fixed costs amortise, 16 is the default")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase CUDA-event timings to stderr")
@@ -1046,7 +1047,8 @@ def main():
                          "traffic_source": lift_traffic_src,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch / tiles in that launch (cold L2: ncu "
                                          "flushes the caches before every replay); null when no capture of THIS kernel source exists",
-                         "peak_source": peak_src, "units": "per tile; one launch covers the %d tiles of a step" % BT if lift_batched else "per tile = per launch",
+                         "peak_source": peak_src, "units": ("per tile; %d launch(es) per step, each over up to 8 scenes (B * V <= 32 views)" % int(buf_.get("lift_launches", 1)))
+                         if lift_batched else "per tile = per launch",
                          "ms_per_launch": lift_ms * (BT if lift_batched else 1), "ms_per_tile": lift_ms,
                          "algorithmic_flops": LIFT_FLOPS, "algorithmic_bytes": LIFT_BYTES,
                          "executed_flops": executed_flops, "executed_tflops": executed_flops / (lift_ms * 1e-3) / 1e12,

@@ -237,6 +237,8 @@ def test_implicit_root_conv_vs_im2col_gemm(KH, stride, pad, hw):
     (5, (7, 9), 128, 512, True, False, True, False),      # images smaller than a tile
     (2, (32, 48), 1024, 128, True, True, False, False),   # FPN skip conv: relu -> GN -> conv + up-sampled level
     (2, (24, 40), 2048, 512, False, False, True, False),  # conv1 of stage 4: deep K loop (one CTA per SM)
+    (40, (8, 16), 256, 64, False, False, True, False),    # more than 32 images per call (12+ tiles per step)
+    (3, (20, 32), 1024, 256, False, False, True, False),  # conv1 of stage 3: 128 x 256 tiles
 ])
 def test_conv_gn_1x1_equals_apply_then_gemm(n_img, hw, C, N, res, pre, post, relu_acc):
     """The A_TGN1 mode of `snapb200_conv_gn_bf16` (GroupNorm + ReLU applied to the raw tile in shared memory, conv
