@@ -128,3 +128,21 @@ def test_backward_entry_points_reject_null_arguments_without_touching_the_gpu():
         rc = getattr(lib, name)(*args)
         msg = lib.snapb200_last_error().decode()
         assert rc != 0 and msg, (name, rc, msg)
+
+
+def test_round2_encoder_entry_points_plan_and_validate_without_a_gpu():
+    """`snapb200_conv3x3_halo_supported` is a host-only plan query (stage 1 / 2 shapes fit, stage 3 does not: its weight tiles
+    alone exceed shared memory); the halo conv, the fused GroupNorm conv and the descriptor self-test reject NULL / invalid
+    arguments with a message before any CUDA call."""
+    from snap_b200 import _lib
+    lib = _lib.lib()
+    lib.snapb200_last_error.restype = C.c_char_p
+    sup = lib.snapb200_conv3x3_halo_supported
+    assert sup(64, 64, 168) == 1 and sup(128, 128, 84) == 1          # conv2 of stages 1 and 2 at 480 x 640 inputs
+    assert sup(256, 256, 42) == 0 and sup(512, 512, 21) == 0         # stages 3 and 4: 9-segment GEMM
+    assert sup(64, 64, 100000) == 0 and sup(96, 64, 40) == 0 and sup(64, 32, 40) == 0
+    p = _lib.Conv3x3Params()
+    assert lib.snapb200_conv3x3_halo_bf16(C.byref(p), None) == -1 and b"null operand" in lib.snapb200_last_error()
+    q = _lib.ConvGnParams()
+    assert lib.snapb200_conv_gn_bf16(C.byref(q), None) == -1 and b"null operand" in lib.snapb200_last_error()
+    assert lib.snapb200_selftest_shifted_desc(None, None, 0, 0, None, None) == -1

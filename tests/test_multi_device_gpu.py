@@ -54,6 +54,24 @@ def _run_all(dev):
     ones = torch.ones((1, Gx, Gx), dtype=torch.uint8, device=dev)
     out["xcorr"] = pv.exhaustive_pose_voting(types.FeaturePlane(q, ones), types.FeaturePlane(m, ones), R,
                                              types.Grid2D((Gx, Gx), 0.2)).cpu()
+    # 4. round-2 kernels of the default encoder path: GroupNorm fused into a 1x1 conv (A_TGN1, 113 KB x 2 CTAs) and the halo
+    #    3x3 conv (200 KB), each with its own per-device shared-memory opt-in
+    n_img, H, W, Cc = 2, 24, 40, 256
+    x = t(bf16_np(rng.standard_normal((n_img * H * W, Cc)))).to(torch.bfloat16)
+    acc = torch.zeros((ops.GN_REPLICAS, n_img, 32, 2), dtype=torch.float64, device=dev)
+    ops.gn_stats(x, n_img, H * W, Cc, False, acc)
+    wb = t(bf16_np(rng.standard_normal((64, Cc)) * 0.1)).to(torch.bfloat16)
+    yc = torch.zeros((n_img * H * W + 128, 64), dtype=torch.bfloat16, device=dev)
+    ops.conv_gn(x, n_img, H, W, Cc, acc, torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev), wb, yc)
+    out["conv_gn"] = yc.float().cpu()
+    a3 = torch.zeros((n_img, H + 2, W + 2, 64), dtype=torch.bfloat16, device=dev)
+    a3[:, 1:-1, 1:-1] = t(bf16_np(rng.standard_normal((n_img, H, W, 64)))).to(torch.bfloat16)
+    a3f = torch.zeros((n_img * (H + 2) * (W + 2) + 256, 64), dtype=torch.bfloat16, device=dev)
+    a3f[: n_img * (H + 2) * (W + 2)] = a3.view(-1, 64)
+    w3 = t(bf16_np(rng.standard_normal((64, 9 * 64)) * 0.05)).to(torch.bfloat16)
+    y3 = torch.zeros((n_img * H * W + 128, 64), dtype=torch.bfloat16, device=dev)
+    ops.conv3x3_halo(a3f, n_img, H, W, 64, w3, y3)
+    out["conv3x3_halo"] = y3.float().cpu()
     torch.cuda.synchronize(dev)
     return out
 
